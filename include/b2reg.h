@@ -1,0 +1,151 @@
+/* b2reg.h — C ABI of libb2reg.so: the B200-native (sm_100a) scan-registration hot path.
+ *
+ * The reference (JBaien/multi-sensor-slam-tookit) has no plugin/FFI layer; its seams for this path are
+ * PCL class interfaces, four mapOptimization member functions and Open3D Python calls.
+ * Every entry point below names the reference interface (file:line under /root/reference) it replaces.
+ * INTEGRATION.md shows the reference-side binding a maintainer would add for each.
+ *
+ * Conventions
+ *   - plain C, no exceptions, no callbacks, no torch/CUDA types in signatures;
+ *   - every point-array argument is (base, stride_bytes, n): the first 3 floats at each stride are x,y,z and,
+ *     where the op carries intensity, the float at byte offset `B2_INTENSITY_OFFSET(stride)`:
+ *     PCL's 32 B PointXYZI (x,y,z,pad,intensity,...) and a packed 16 B xyzi are both accepted as they are;
+ *   - host buffers are caller-owned; device memory is owned by the handle; one handle = one CUDA stream;
+ *     a handle is not re-entrant, different handles are independent (the reference uses these objects from
+ *     three host threads: mapOptmization.cpp:1770-1771);
+ *   - return value: 0 = ok, < 0 = error (see b2_status). The reference's own `false` returns (fewer than 50
+ *     correspondences, not converged) are out-parameters, not errors;
+ *   - there is no CPU fallback: without a CUDA device every compute call returns B2_ERR_CUDA.
+ */
+#ifndef B2REG_H
+#define B2REG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    B2_OK = 0,
+    B2_ERR_ARG = -1,          /* null pointer / bad size / bad stride */
+    B2_ERR_CUDA = -2,         /* CUDA runtime error (message in b2_last_error) */
+    B2_ERR_STATE = -3,        /* call order (e.g. iterate before set_map) */
+    B2_ERR_CAPACITY = -4,     /* output buffer too small */
+    B2_ERR_TOO_LARGE = -5,    /* index grid would not fit the configured budget */
+    B2_ERR_NCCL = -6
+} b2_status;
+
+/* layout helper: where intensity sits for a given stride (PCL PointXYZI: 16, packed xyzi: 12) */
+#define B2_INTENSITY_OFFSET(stride_bytes) ((stride_bytes) >= 32 ? 16 : 12)
+
+int         b2_version(void);
+const char* b2_last_error(void);                 /* thread-local, never NULL */
+int         b2_device_count(void);
+int         b2_set_device(int ordinal);          /* device used by handles created afterwards on this thread */
+/* number of CUDA kernels this library has launched in this process so far (bench.py's gpu_launches) */
+unsigned long long b2_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * VoxelGrid — replaces pcl::VoxelGrid<PointT>::{setLeafSize,setMinimumPointsNumberPerVoxel,setInputCloud,filter}
+ *   liosam_ws/src/LIO-SAM/src/featureExtraction.cpp:233-234
+ *   liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:719,879,928,932,960,965
+ *   Calibration_Tookit/multi_lidar/src/multi_lidar_calibration/src/multi_lidar_calibrator.cpp:113-121
+ *   heading_ws/src/src/PointCloudProcessing.cpp:23-30
+ * Semantics: PCL 1.10 applyFilter — bbox, idx = sum((floor(p*inv_leaf) - min_b) * mul), one centroid of
+ * (x,y,z,intensity) per voxel with >= min_points points, output in ascending voxel index; when
+ * dx*dy*dz > INT32_MAX the filter refuses: *refused = 1 and the output is a copy of the input.
+ * Within a voxel the float sum runs in ascending input index. */
+typedef struct b2_voxel_s* b2_voxel_t;
+int b2_voxel_create(b2_voxel_t* out);
+int b2_voxel_destroy(b2_voxel_t h);
+int b2_voxel_set_leaf_size(b2_voxel_t h, float lx, float ly, float lz);
+int b2_voxel_set_min_points_per_voxel(b2_voxel_t h, unsigned min_points);
+/* n_fields: 3 (xyz only, PointXYZ) or 4 (xyz + intensity). out may alias nothing; out_capacity in points.
+ * voxel_of_point (optional, n ints): linear voxel index of every input point (-1 when refused). */
+int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, int n_fields,
+                    void* out, size_t out_stride, size_t out_capacity, size_t* n_out,
+                    int* refused, int32_t* voxel_of_point);
+
+/* ------------------------------------------------------------------------------------------------
+ * Batched nearest-neighbour index — replaces pcl::KdTreeFLANN<PointType>::{setInputCloud,nearestKSearch}
+ *   liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:1289-1290 (build), :987, :1079 (k = 5 queries)
+ * A per-query GPU call is useless, so the query is batched: m queries in, m*k (index, squared distance)
+ * out, ascending by (distance, index). Distances are ((dx*dx)+dy*dy)+dz*dz in float without FMA, i.e.
+ * FLANN's L2_Simple. The index is a uniform grid with cell edge >= max_dist, so results are exact for every
+ * neighbour closer than max_dist — the only ones the reference consumes (it rejects a feature unless
+ * sqDis[4] < 1.0, mapOptmization.cpp:993,1089). Slots with no neighbour inside max_dist hold index -1 and
+ * +inf. Equal distances are ordered by the smaller index (FLANN's order is traversal dependent). */
+typedef struct b2_knn_s* b2_knn_t;
+int b2_knn_create(b2_knn_t* out, float max_dist /* 1.0f for LIO-SAM */);
+int b2_knn_destroy(b2_knn_t h);
+int b2_knn_set_input_cloud(b2_knn_t h, const void* pts, size_t stride, size_t n);
+int b2_knn_nearest_k_search(b2_knn_t h, const void* queries, size_t stride, size_t m, int k /* 1..8 */,
+                            int32_t* indices, float* sq_dists);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scan-to-map Levenberg-Marquardt — replaces, as one fused device op per iteration,
+ *   mapOptimization::cornerOptimization        liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:974-1064
+ *   mapOptimization::surfOptimization          :1066-1135
+ *   mapOptimization::combineOptimizationCoeffs :1137-1156
+ *   mapOptimization::LMOptimization            :1158-1280
+ * and the loop of scan2MapOptimization :1282-1310 (guards included, transformUpdate excluded).
+ * pose = transformTobeMapped = (roll, pitch, yaw, x, y, z), float, in/out. */
+typedef struct b2_s2m_s* b2_s2m_t;
+typedef struct {
+    int   edge_feature_min_valid_num;   /* 10   utility.h:219 */
+    int   surf_feature_min_valid_num;   /* 100  utility.h:220 */
+    int   max_iterations;               /* 30   mapOptmization.cpp:1292 */
+    int   min_correspondences;          /* 50   mapOptmization.cpp:1178 */
+    float knn_max_dist;                 /* 1.0  (sqDis[4] < 1.0, :993,:1089) */
+    float degenerate_eigen_threshold;   /* 100  :1239 */
+    int   max_batch;                    /* scans that can be registered against the map in one call (>= 1) */
+} b2_s2m_params;
+void b2_s2m_default_params(b2_s2m_params* p);
+int  b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params /* NULL = defaults */);
+int  b2_s2m_destroy(b2_s2m_t h);
+/* replaces kdtreeCornerFromMap->setInputCloud / kdtreeSurfFromMap->setInputCloud (:1289-1290) */
+int  b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t corner_stride, size_t n_corner,
+                    const void* surf, size_t surf_stride, size_t n_surf);
+/* laserCloudCornerLastDS / laserCloudSurfLastDS of the current scan (:955-967) */
+int  b2_s2m_set_scan(b2_s2m_t h, const void* corner, size_t corner_stride, size_t n_corner,
+                     const void* surf, size_t surf_stride, size_t n_surf);
+/* One loop body: corner+surf+combine+LMOptimization(iter). The six sines/cosines of LMOptimization and the
+ * pose matrix are evaluated on the host with the C library (as the reference does) and shipped with the pose.
+ * n_sel = laserCloudSelNum; *ran = 0 when n_sel < min_correspondences (LMOptimization returned false early). */
+int  b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, int* converged,
+                    int* degenerate, float matP[36]);
+/* Whole loop on the device, no host round trip between iterations. Returns B2_OK and *status_not_enough = 1
+ * (pose untouched) when the feature-count guards of :1287 fail. pose_history (optional): max_iterations*6. */
+int  b2_s2m_solve(b2_s2m_t h, float pose[6], int max_iterations, int* iters_done, int* converged,
+                  int* degenerate, float matP[36], int* not_enough_features, float* pose_history);
+/* isDegenerate / matP are members that persist across scans in the reference (:136,:234) */
+int  b2_s2m_set_state(b2_s2m_t h, int degenerate, const float matP[36]);
+/* Introspection of the last iteration (parity tests): which = 0 corner / 1 surf; any pointer may be NULL.
+ * knn_idx/knn_d2: n*5, coeff: n*4 (coeffSel entries, valid where flag != 0), flag: n bytes. */
+int  b2_s2m_get_pass(b2_s2m_t h, int which, int32_t* knn_idx, float* knn_d2, float* coeff, uint8_t* flag);
+int  b2_s2m_get_normal_equations(b2_s2m_t h, float AtA[36], float AtB[6], float X[6]);
+
+/* Batched variant: B independent scans (ragged) against the one resident map, each with its own pose.
+ * corner_offsets / surf_offsets: B+1 prefix offsets into the concatenated feature arrays. */
+int  b2_s2m_set_scan_batch(b2_s2m_t h, int batch, const void* corner, size_t corner_stride, const int32_t* corner_offsets,
+                           const void* surf, size_t surf_stride, const int32_t* surf_offsets);
+/* poses: B*6 in/out; iters_done/converged/degenerate: B each (optional). */
+int  b2_s2m_solve_batch(b2_s2m_t h, float* poses, int max_iterations, int* iters_done, int* converged,
+                        int* degenerate);
+
+/* Timing hooks for bench.py: GPU time in ms of the last solve / solve_batch call, measured with CUDA events
+ * on the handle's own stream (torch.cuda.Event only sees torch's stream), and the kernel launches it made. */
+int  b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rigid transform of a cloud — replaces mapOptimization::transformPointCloud (mapOptmization.cpp:286-305)
+ * pose6 = (roll, pitch, yaw, x, y, z); matrix from pcl::getTransformation evaluated on the host in float. */
+int  b2_transform_cloud(const void* in, size_t in_stride, size_t n, const float pose6[6],
+                        void* out, size_t out_stride);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2REG_H */

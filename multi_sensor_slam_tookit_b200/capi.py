@@ -1,0 +1,96 @@
+"""ctypes binding of libb2reg.so (include/b2reg.h). No fallbacks: if the CUDA library is missing or a call fails,
+this raises — the product never routes around the device path."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb2reg.so")
+_LIB = None
+
+
+class B2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libb2reg error {code}: {msg}")
+        self.code = code
+
+
+class S2MParams(C.Structure):
+    _fields_ = [("edge_feature_min_valid_num", C.c_int), ("surf_feature_min_valid_num", C.c_int),
+                ("max_iterations", C.c_int), ("min_correspondences", C.c_int), ("knn_max_dist", C.c_float),
+                ("degenerate_eigen_threshold", C.c_float), ("max_batch", C.c_int)]
+
+
+# every symbol include/b2reg.h declares (tests/test_abi.py checks the library exports all of them)
+SYMBOLS = [
+    "b2_version", "b2_last_error", "b2_device_count", "b2_set_device", "b2_kernel_launch_count",
+    "b2_voxel_create", "b2_voxel_destroy", "b2_voxel_set_leaf_size", "b2_voxel_set_min_points_per_voxel", "b2_voxel_filter",
+    "b2_knn_create", "b2_knn_destroy", "b2_knn_set_input_cloud", "b2_knn_nearest_k_search",
+    "b2_s2m_default_params", "b2_s2m_create", "b2_s2m_destroy", "b2_s2m_set_map", "b2_s2m_set_scan", "b2_s2m_iterate",
+    "b2_s2m_solve", "b2_s2m_set_state", "b2_s2m_get_pass", "b2_s2m_get_normal_equations", "b2_s2m_set_scan_batch",
+    "b2_s2m_solve_batch", "b2_s2m_last_gpu_ms", "b2_transform_cloud",
+]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -m multi_sensor_slam_tookit_b200.build` "
+                          "(there is no CPU fallback for this path)")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32, f32 = C.c_void_p, C.c_size_t, C.c_int, C.c_float
+    pi, pf = C.POINTER(C.c_int), C.POINTER(C.c_float)
+    L.b2_last_error.restype = C.c_char_p
+    L.b2_set_device.argtypes = [i32]
+    L.b2_voxel_create.argtypes = [C.POINTER(vp)]
+    L.b2_voxel_destroy.argtypes = [vp]
+    L.b2_voxel_set_leaf_size.argtypes = [vp, f32, f32, f32]
+    L.b2_voxel_set_min_points_per_voxel.argtypes = [vp, C.c_uint]
+    L.b2_voxel_filter.argtypes = [vp, vp, sz, sz, i32, vp, sz, sz, C.POINTER(sz), pi, vp]
+    L.b2_knn_create.argtypes = [C.POINTER(vp), f32]
+    L.b2_knn_destroy.argtypes = [vp]
+    L.b2_knn_set_input_cloud.argtypes = [vp, vp, sz, sz]
+    L.b2_knn_nearest_k_search.argtypes = [vp, vp, sz, sz, i32, vp, vp]
+    L.b2_s2m_default_params.argtypes = [C.POINTER(S2MParams)]
+    L.b2_s2m_default_params.restype = None
+    L.b2_s2m_create.argtypes = [C.POINTER(vp), C.POINTER(S2MParams)]
+    L.b2_s2m_destroy.argtypes = [vp]
+    L.b2_s2m_set_map.argtypes = [vp, vp, sz, sz, vp, sz, sz]
+    L.b2_s2m_set_scan.argtypes = [vp, vp, sz, sz, vp, sz, sz]
+    L.b2_s2m_iterate.argtypes = [vp, vp, i32, pi, pi, pi, pi, vp]
+    L.b2_s2m_solve.argtypes = [vp, vp, i32, pi, pi, pi, vp, pi, vp]
+    L.b2_s2m_set_state.argtypes = [vp, i32, vp]
+    L.b2_s2m_get_pass.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.b2_s2m_get_normal_equations.argtypes = [vp, vp, vp, vp]
+    L.b2_s2m_set_scan_batch.argtypes = [vp, i32, vp, sz, vp, vp, sz, vp]
+    L.b2_s2m_solve_batch.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.b2_s2m_last_gpu_ms.argtypes = [vp, pf, pi]
+    L.b2_transform_cloud.argtypes = [vp, sz, sz, vp, vp, sz]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("b2_last_error", "b2_s2m_default_params", "b2_kernel_launch_count"):
+            fn.restype = C.c_int
+    L.b2_kernel_launch_count.restype = C.c_ulonglong
+    _LIB = L
+    return L
+
+
+def check(code):
+    if code != 0:
+        raise B2Error(code, lib().b2_last_error().decode(errors="replace"))
+
+
+def ptr(a):
+    """void* of a numpy array (or None)."""
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def as_points(a, min_cols=3):
+    """C-contiguous float32 (n, c) view; returns (array, stride_bytes)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] < min_cols:
+        raise ValueError(f"expected (n, >={min_cols}) float32 points, got {a.shape}")
+    return a, a.strides[0]

@@ -1,0 +1,120 @@
+// Shared host/device helpers for libb2reg (sm_100a). Compiled with -fmad=false: every float expression that
+// feeds a floor(), an ordering or a threshold must round exactly like the reference's baseline-x86-64 build
+// (no FMA contraction, liosam_ws/src/LIO-SAM/CMakeLists.txt:4-6).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "../../include/b2reg.h"
+
+namespace b2 {
+
+void set_error(const char* fmt, ...);
+
+#define B2_CUDA(expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            b2::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+            return B2_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+#define B2_CHECK(expr)                                                                             \
+    do {                                                                                           \
+        int _s = (expr);                                                                           \
+        if (_s != B2_OK) return _s;                                                                \
+    } while (0)
+
+// Growable device buffer owned by a handle.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B2_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e)); return B2_ERR_CUDA; }
+        cap = want;
+        return B2_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Pinned host staging buffer (H2D / D2H of caller-owned pageable memory goes through it so copies are async).
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B2_OK;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { set_error("cudaMallocHost(%zu) -> %s", want, cudaGetErrorString(e)); return B2_ERR_CUDA; }
+        cap = want;
+        return B2_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+int device_sm_count();
+void count_launch(int n = 1);     // bookkeeping for b2_kernel_launch_count()
+
+// ---- scan / sort primitives (b2_sort.cu) -------------------------------------------------------
+// exclusive prefix sum of n uint32 in place; d_tmp must hold scan_tmp_bytes(n)
+size_t scan_tmp_bytes(size_t n);
+int exclusive_scan_u32(uint32_t* d_data, size_t n, void* d_tmp, cudaStream_t s);
+// stable LSD radix sort of (key, value) pairs on bits [0, key_bits); result returned in *keys_out/*vals_out which
+// point at either the a or the b buffers. tmp must hold sort_tmp_bytes(n).
+size_t sort_tmp_bytes(size_t n);
+int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint32_t* vals_b, size_t n, int key_bits,
+                     void* d_tmp, cudaStream_t s, uint32_t** keys_out, uint32_t** vals_out);
+
+// ---- uniform-grid index (b2_grid.cu) -----------------------------------------------------------
+struct GridDev {               // passed by value to kernels
+    const float4* pts;         // cell-sorted points: x, y, z, __int_as_float(original index)
+    const uint32_t* cell_start;// ncell + 1
+    float ox, oy, oz, inv_h;
+    int nx, ny, nz;
+    int n;
+};
+struct GridIndex {
+    DevBuf pts, cell_start, cell_of, tmp, raw;
+    PinBuf stage;
+    GridDev dev{};
+    float h = 1.0078125f;
+    size_t n = 0;
+    int build(const void* host_pts, size_t stride, size_t n, float max_dist, cudaStream_t s);
+    void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); }
+};
+
+}  // namespace b2
+
+// ---- device-side helpers -----------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace b2 {
+
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// order-preserving float <-> uint mapping for atomicMin/Max on floats
+__device__ __forceinline__ uint32_t float_flip(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_unflip(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace b2
+#endif

@@ -1,0 +1,227 @@
+// Uniform-grid index build (replaces pcl::KdTreeFLANN::setInputCloud, mapOptmization.cpp:1289-1290) and the
+// batched k-NN entry points of the C ABI.
+//
+// HBM layout after build():  pts   float4[n]      cell-sorted (x, y, z, original index as int bits)
+//                            cell_start u32[ncell+2]  exclusive prefix of per-cell counts (x fastest)
+// Cell edge h = max_dist * (1 + 2^-7): any point closer than max_dist to a query lies in the 3x3x3 block
+// around the query's cell even after float rounding of (p - origin) * (1/h).
+#include "b2_grid.cuh"
+#include <cmath>
+#include <vector>
+
+namespace b2 {
+
+constexpr size_t GRID_MAX_CELLS = (size_t)1 << 27;   // 512 MiB of cell_start at most
+
+__global__ void k_bbox_init(uint32_t* bb) {
+    if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;        // min (flipped)
+    else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;            // max (flipped)
+}
+
+__global__ void __launch_bounds__(256) k_bbox(const unsigned char* __restrict__ raw, size_t stride, size_t n, uint32_t* __restrict__ bb) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float* p = reinterpret_cast<const float*>(raw + i * stride);
+        float x = p[0], y = p[1], z = p[2];
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+            mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            if (mn[d] <= mx[d]) { atomicMin(&bb[d], float_flip(mn[d])); atomicMax(&bb[3 + d], float_flip(mx[d])); }
+        }
+    }
+}
+
+struct GridGeom { float ox, oy, oz, inv_h; int nx, ny, nz; uint32_t ncell; };
+
+__device__ __forceinline__ uint32_t cell_of_point(const GridGeom& g, float x, float y, float z) {
+    if (!(isfinite(x) && isfinite(y) && isfinite(z))) return g.ncell;
+    int cx = (int)floorf((x - g.ox) * g.inv_h), cy = (int)floorf((y - g.oy) * g.inv_h), cz = (int)floorf((z - g.oz) * g.inv_h);
+    cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+    return (uint32_t)(((size_t)cz * g.ny + cy) * g.nx + cx);
+}
+
+__global__ void __launch_bounds__(256) k_cell_key(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, GridGeom g,
+                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    uint32_t c = cell_of_point(g, p[0], p[1], p[2]);
+    keys[i] = c; vals[i] = i;
+    atomicAdd(&count[c], 1u);
+}
+
+__global__ void __launch_bounds__(256) k_cell_gather(const unsigned char* __restrict__ raw, size_t stride, uint32_t n,
+                                                     const uint32_t* __restrict__ order, float4* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t src = order[i];
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)src * stride);
+    out[i] = make_float4(p[0], p[1], p[2], __int_as_float((int)src));
+}
+
+int GridIndex::build(const void* host_pts, size_t stride, size_t n_, float max_dist, cudaStream_t s) {
+    n = n_;
+    dev = GridDev{};
+    h = max_dist * 1.0078125f;
+    if (n == 0) {
+        B2_CHECK(cell_start.reserve(3 * sizeof(uint32_t)));
+        B2_CUDA(cudaMemsetAsync(cell_start.p, 0, 3 * sizeof(uint32_t), s));
+        dev.pts = nullptr; dev.cell_start = cell_start.as<uint32_t>();
+        dev.ox = dev.oy = dev.oz = 0.f; dev.inv_h = 1.0f / h; dev.nx = dev.ny = dev.nz = 1; dev.n = 0;
+        return B2_OK;
+    }
+    if (n > 0x7fffffffull) { set_error("grid index: too many points (%zu)", n); return B2_ERR_ARG; }
+    B2_CHECK(raw.reserve(n * stride));
+    B2_CUDA(cudaMemcpyAsync(raw.p, host_pts, n * stride, cudaMemcpyHostToDevice, s));
+    // bbox on device, one small readback to size the cell table
+    B2_CHECK(tmp.reserve(64));
+    uint32_t* bb = tmp.as<uint32_t>();
+    k_bbox_init<<<1, 32, 0, s>>>(bb); count_launch();
+    int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 4);
+    k_bbox<<<nb, 256, 0, s>>>(raw.as<unsigned char>(), stride, n, bb); count_launch();
+    B2_CUDA(cudaGetLastError());
+    uint32_t hbb[6];
+    B2_CUDA(cudaMemcpyAsync(hbb, bb, sizeof(hbb), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    auto unflip = [](uint32_t u) { uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
+    float mn[3], mx[3];
+    for (int d = 0; d < 3; d++) { mn[d] = unflip(hbb[d]); mx[d] = unflip(hbb[3 + d]); }
+    GridGeom g;
+    g.inv_h = 1.0f / h;
+    if (!(mn[0] <= mx[0])) { mn[0] = mn[1] = mn[2] = 0.f; mx[0] = mx[1] = mx[2] = 0.f; }   // no finite point
+    g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+    double ex[3];
+    for (int d = 0; d < 3; d++) ex[d] = std::floor(((double)mx[d] - (double)mn[d]) * (double)g.inv_h) + 2.0;
+    if (ex[0] * ex[1] * ex[2] > (double)GRID_MAX_CELLS) {
+        set_error("grid index: %.0f x %.0f x %.0f cells of %.3f m exceed the %zu-cell budget", ex[0], ex[1], ex[2], h, GRID_MAX_CELLS);
+        return B2_ERR_TOO_LARGE;
+    }
+    g.nx = (int)ex[0]; g.ny = (int)ex[1]; g.nz = (int)ex[2];
+    g.ncell = (uint32_t)((size_t)g.nx * g.ny * g.nz);
+    const size_t ncount = (size_t)g.ncell + 2;
+    B2_CHECK(cell_start.reserve(ncount * sizeof(uint32_t)));
+    B2_CUDA(cudaMemsetAsync(cell_start.p, 0, ncount * sizeof(uint32_t), s));
+    // keys/vals ping-pong + sort scratch
+    const size_t nal = (n + 63) & ~(size_t)63;
+    const size_t need = 4 * nal * sizeof(uint32_t) + sort_tmp_bytes(n) + scan_tmp_bytes(ncount) + 1024;
+    B2_CHECK(cell_of.reserve(need));
+    uint32_t* ka = cell_of.as<uint32_t>();
+    uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
+    char* scratch = reinterpret_cast<char*>(vb + nal);
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    k_cell_key<<<nblk, 256, 0, s>>>(raw.as<unsigned char>(), stride, (uint32_t)n, g, ka, va, cell_start.as<uint32_t>()); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CHECK(exclusive_scan_u32(cell_start.as<uint32_t>(), ncount, scratch, s));
+    int bits = 1;
+    while (((size_t)1 << bits) <= (size_t)g.ncell) bits++;
+    uint32_t *ks, *vs;
+    B2_CHECK(radix_sort_pairs(ka, va, kb, vb, n, bits, scratch, s, &ks, &vs));
+    B2_CHECK(pts.reserve(n * sizeof(float4)));
+    k_cell_gather<<<nblk, 256, 0, s>>>(raw.as<unsigned char>(), stride, (uint32_t)n, vs, pts.as<float4>()); count_launch();
+    B2_CUDA(cudaGetLastError());
+    dev.pts = pts.as<float4>(); dev.cell_start = cell_start.as<uint32_t>();
+    dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h;
+    dev.nx = g.nx; dev.ny = g.ny; dev.nz = g.nz; dev.n = (int)n;
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ batched kNN
+template <int K>
+__global__ void __launch_bounds__(256) k_knn(GridDev g, const unsigned char* __restrict__ q, size_t stride, uint32_t m,
+                                             float max_d2, int32_t* __restrict__ idx, float* __restrict__ d2) {
+    constexpr int LPF = 8;
+    const uint32_t qi = (blockIdx.x * blockDim.x + threadIdx.x) / LPF;
+    const bool active = qi < m;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (active) { const float* p = reinterpret_cast<const float*>(q + (size_t)qi * stride); qx = p[0]; qy = p[1]; qz = p[2]; }
+    unsigned long long key[K]; uint32_t pos[K];
+    knn_group<K, LPF>(g, qx, qy, qz, active, key, pos);
+    const int sub = threadIdx.x & (LPF - 1);
+    if (active && sub == 0) {
+#pragma unroll
+        for (int r = 0; r < K; r++) {
+            float d = __uint_as_float((uint32_t)(key[r] >> 32));
+            bool ok = key[r] != KNN_EMPTY && d < max_d2;
+            idx[(size_t)qi * K + r] = ok ? (int32_t)(uint32_t)key[r] : -1;
+            d2[(size_t)qi * K + r] = ok ? d : INFINITY;
+        }
+    }
+}
+
+}  // namespace b2
+
+struct b2_knn_s {
+    b2::GridIndex grid;
+    b2::DevBuf q, oidx, od2;
+    cudaStream_t stream = nullptr;
+    float max_dist = 1.0f;
+    bool built = false;
+};
+
+extern "C" {
+
+int b2_knn_create(b2_knn_t* out, float max_dist) {
+    if (!out || !(max_dist > 0.f)) { b2::set_error("b2_knn_create: bad argument"); return B2_ERR_ARG; }
+    b2_knn_s* h = new b2_knn_s();
+    h->max_dist = max_dist;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { b2::set_error("cudaStreamCreate -> %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
+    *out = h;
+    return B2_OK;
+}
+
+int b2_knn_destroy(b2_knn_t h) {
+    if (!h) return B2_ERR_ARG;
+    h->grid.release(); h->q.release(); h->oidx.release(); h->od2.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B2_OK;
+}
+
+int b2_knn_set_input_cloud(b2_knn_t h, const void* pts, size_t stride, size_t n) {
+    if (!h || (n && !pts) || stride < 12 || (stride & 3)) { b2::set_error("b2_knn_set_input_cloud: bad argument"); return B2_ERR_ARG; }
+    B2_CHECK(h->grid.build(pts, stride, n, h->max_dist, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    h->built = true;
+    return B2_OK;
+}
+
+int b2_knn_nearest_k_search(b2_knn_t h, const void* queries, size_t stride, size_t m, int k, int32_t* indices, float* sq_dists) {
+    if (!h || (m && (!queries || !indices || !sq_dists)) || stride < 12 || (stride & 3) || k < 1 || k > 8) {
+        b2::set_error("b2_knn_nearest_k_search: bad argument"); return B2_ERR_ARG;
+    }
+    if (!h->built) { b2::set_error("b2_knn_nearest_k_search: no input cloud"); return B2_ERR_STATE; }
+    if (m == 0) return B2_OK;
+    B2_CHECK(h->q.reserve(m * stride));
+    B2_CHECK(h->oidx.reserve(m * k * sizeof(int32_t)));
+    B2_CHECK(h->od2.reserve(m * k * sizeof(float)));
+    B2_CUDA(cudaMemcpyAsync(h->q.p, queries, m * stride, cudaMemcpyHostToDevice, h->stream));
+    const unsigned nblk = (unsigned)((m * 8 + 255) / 256);
+    const float md2 = h->max_dist * h->max_dist;
+#define B2_KNN_CASE(KK) case KK: b2::k_knn<KK><<<nblk, 256, 0, h->stream>>>(h->grid.dev, h->q.as<unsigned char>(), stride, (uint32_t)m, md2, \
+                                                                          h->oidx.as<int32_t>(), h->od2.as<float>()); b2::count_launch(); break;
+    switch (k) {
+        B2_KNN_CASE(1) B2_KNN_CASE(2) B2_KNN_CASE(3) B2_KNN_CASE(4) B2_KNN_CASE(5) B2_KNN_CASE(6) B2_KNN_CASE(7) B2_KNN_CASE(8)
+    }
+#undef B2_KNN_CASE
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaMemcpyAsync(indices, h->oidx.p, m * k * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaMemcpyAsync(sq_dists, h->od2.p, m * k * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}
+
+}  // extern "C"

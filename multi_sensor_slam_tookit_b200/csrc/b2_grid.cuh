@@ -1,0 +1,100 @@
+// Uniform-grid exact k-nearest-neighbour search, device side.
+// Replaces pcl::KdTreeFLANN::nearestKSearch (liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:987,1079).
+// One query is served by a group of LPF consecutive lanes: the 27 cells around the query are 9 x-rows that are
+// contiguous runs of the cell-sorted float4 array, each lane strides a row with 128-bit loads and keeps a
+// register top-K, then the group merges with shuffles. Ordering key = (d2 bits << 32) | original index, so ties
+// fall to the smaller index. d2 = ((dx*dx)+dy*dy)+dz*dz in float, no FMA (FLANN L2_Simple).
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+constexpr unsigned long long KNN_EMPTY = 0xffffffffffffffffull;
+
+template <int K>
+struct TopK {
+    unsigned long long key[K];
+    uint32_t pos[K];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < K; i++) { key[i] = KNN_EMPTY; pos[i] = 0; }
+    }
+    __device__ __forceinline__ void push(unsigned long long k, uint32_t p) {
+        if (k < key[K - 1]) {
+            key[K - 1] = k; pos[K - 1] = p;
+#pragma unroll
+            for (int j = K - 1; j > 0; j--) {
+                if (key[j] < key[j - 1]) {
+                    unsigned long long tk = key[j]; key[j] = key[j - 1]; key[j - 1] = tk;
+                    uint32_t tp = pos[j]; pos[j] = pos[j - 1]; pos[j - 1] = tp;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void pop() {
+#pragma unroll
+        for (int j = 0; j < K - 1; j++) { key[j] = key[j + 1]; pos[j] = pos[j + 1]; }
+        key[K - 1] = KNN_EMPTY;
+    }
+};
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned mask, unsigned long long v, int o) {
+    uint32_t lo = (uint32_t)v, hi = (uint32_t)(v >> 32);
+    lo = __shfl_xor_sync(mask, lo, o); hi = __shfl_xor_sync(mask, hi, o);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// All LPF lanes of a group call this with the same query. On return every lane holds the K winners:
+// out_key[r] (KNN_EMPTY when fewer than r+1 candidates exist in the 27 cells) and out_pos[r] (position in g.pts).
+template <int K, int LPF>
+__device__ __forceinline__ void knn_group(const GridDev& g, float qx, float qy, float qz, bool active,
+                                          unsigned long long (&out_key)[K], uint32_t (&out_pos)[K]) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (LPF - 1);
+    TopK<K> top; top.clear();
+    if (active) {
+        float fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+        // the comparisons are false for NaN, so a non-finite query scans nothing
+        if (fx > -2.f && fx < (float)(g.nx + 1) && fy > -2.f && fy < (float)(g.ny + 1) && fz > -2.f && fz < (float)(g.nz + 1)) {
+            const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+            uint32_t rs[9], re[9];
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
+                const bool ok = (x0 <= x1) && y >= 0 && y < g.ny && z >= 0 && z < g.nz;
+                const size_t row = ((size_t)(ok ? z : 0) * g.ny + (ok ? y : 0)) * g.nx;
+                rs[r] = ok ? __ldg(&g.cell_start[row + x0]) : 0u;
+                re[r] = ok ? __ldg(&g.cell_start[row + x1 + 1]) : 0u;
+            }
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                for (uint32_t p = rs[r] + sub; p < re[r]; p += LPF) {
+                    const float4 c = ldg4(&g.pts[p]);
+                    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                    float d = dx * dx;
+                    d = d + dy * dy;
+                    d = d + dz * dz;
+                    top.push(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)__float_as_int(c.w), p);
+                }
+            }
+        }
+    }
+    // merge the LPF sorted lists: K rounds of group-min
+    const unsigned full = 0xffffffffu;
+    const unsigned gmask = (LPF == 32) ? full : (((1u << LPF) - 1u) << (lane & ~(LPF - 1)));
+#pragma unroll
+    for (int r = 0; r < K; r++) {
+        unsigned long long m = top.key[0];
+#pragma unroll
+        for (int o = LPF >> 1; o > 0; o >>= 1) { unsigned long long t = shfl_xor_u64(full, m, o); m = t < m ? t : m; }
+        const bool own = (top.key[0] == m) && (m != KNN_EMPTY);
+        const unsigned owners = __ballot_sync(full, own) & gmask;
+        const int src = owners ? (__ffs(owners) - 1) : lane;
+        out_key[r] = m;
+        out_pos[r] = __shfl_sync(full, top.pos[0], src);
+        if (own) top.pop();
+    }
+}
+
+}  // namespace b2

@@ -1,0 +1,705 @@
+// Scan-to-map Levenberg-Marquardt on the device: ONE kernel per LM iteration, no host round trip in between.
+//
+// Replaces (liosam_ws/src/LIO-SAM/src/mapOptmization.cpp):
+//   cornerOptimization :974-1064, surfOptimization :1066-1135, combineOptimizationCoeffs :1137-1156,
+//   LMOptimization :1158-1280 and the loop of scan2MapOptimization :1282-1310.
+//
+// k_s2m_iteration, grid = (feature blocks, scans in the batch), 256 threads:
+//   phase 1  32 features per CTA, 8 lanes per feature: transform (pointAssociateToMap :278-284), exact 5-NN in
+//            the uniform grid (b2_grid.cuh), winners' coordinates parked in shared memory;
+//   phase 2  warp 0, one lane per feature: line fit (3x3 Jacobi) or plane fit (5x3 pivoted QR), thresholds in the
+//            reference's mixed float/double types, coeff, Euler-angle Jacobian row, 21+6 products + count in fp64,
+//            xor-shuffle tree -> one 28-double partial per CTA;
+//   epilogue the last CTA of each scan (atomic ticket) adds the partials in CTA order, rounds AtA/Atb to float as
+//            cv::gemm does, Householder-QR solve, degeneracy projection on iteration 0, pose update, convergence
+//            test, and prepares the next iteration's pose matrix and sines/cosines.
+#include "b2_grid.cuh"
+#include "b2_smallmath.cuh"
+#include <cmath>
+#include <vector>
+#include <algorithm>
+
+namespace b2 {
+
+constexpr int S2M_THREADS = 256;
+constexpr int S2M_LPF = 8;                          // lanes per feature in phase 1
+constexpr int S2M_FPB = S2M_THREADS / S2M_LPF;      // 32 features per CTA
+constexpr int S2M_NPART = 28;                       // 21 (AtA upper) + 6 (Atb) + 1 (count)
+
+struct S2MState {                 // one per scan in the batch, lives in HBM
+    float pose[6];                // roll pitch yaw x y z
+    float xf[12];                 // pcl::getTransformation(x,y,z,roll,pitch,yaw), rows
+    float trig[6];                // srx crx sry cry srz crz of LMOptimization :1170-1175
+    float matP[36];
+    float AtA[36], AtB[6], X[6];
+    int degenerate;
+    int done;                     // no further iterations for this scan
+    int converged;
+    int iters;                    // LM iterations executed
+    int n_sel;                    // laserCloudSelNum of the last iteration
+    int ran;                      // 0 when n_sel < min_correspondences
+    unsigned ticket;
+    int pad;
+};
+
+struct S2MArgs {
+    GridDev gc, gs;                               // corner / surf map grids
+    const float4* scan_c; const float4* scan_s;   // packed xyzi features, all scans concatenated
+    const int* off_c; const int* off_s;           // batch+1 offsets
+    S2MState* st;
+    double* partial;                              // [batch][max_blocks][28]
+    int max_blocks;
+    int iter;                                     // iterCount for host-driven single iteration; -1 = use st->iters
+    int device_driven;                            // epilogue prepares xf/trig for the next iteration
+    int max_iters;                                // loop bound of scan2MapOptimization (device-driven runs)
+    int min_corr; float eig_thr;
+    float* pose_hist; int hist_stride;            // optional [batch][max_iters][6]
+    // optional per-feature introspection (single-scan parity runs)
+    int32_t* dbg_idx_c; float* dbg_d2_c; float4* dbg_coeff_c; uint8_t* dbg_flag_c;
+    int32_t* dbg_idx_s; float* dbg_d2_s; float4* dbg_coeff_s; uint8_t* dbg_flag_s;
+};
+
+// sin/cos of a float angle, rounded once from double: agrees with a correctly rounded sinf/cosf
+__device__ __forceinline__ float sin_rn(float a) { return (float)sin((double)a); }
+__device__ __forceinline__ float cos_rn(float a) { return (float)cos((double)a); }
+
+__host__ __device__ inline void affine_from_trig(float x, float y, float z, float A, float B, float C, float D, float E, float F, float* t) {
+    // A=cos yaw B=sin yaw C=cos pitch D=sin pitch E=cos roll F=sin roll (PCL getTransformation operation order)
+    float DE = D * E, DF = D * F;
+    t[0] = A * C;  t[1] = A * DF - B * E;  t[2]  = B * F + A * DE;  t[3]  = x;
+    t[4] = B * C;  t[5] = A * E + B * DF;  t[6]  = B * DE - A * F;  t[7]  = y;
+    t[8] = -D;     t[9] = C * F;           t[10] = C * E;           t[11] = z;
+}
+
+__device__ void prepare_pose_device(S2MState& s) {
+    const float roll = s.pose[0], pitch = s.pose[1], yaw = s.pose[2];
+    const float sr = sin_rn(roll), cr = cos_rn(roll), sp = sin_rn(pitch), cp = cos_rn(pitch), sy = sin_rn(yaw), cy = cos_rn(yaw);
+    affine_from_trig(s.pose[3], s.pose[4], s.pose[5], cy, sy, cp, sp, cr, sr, s.xf);
+    s.trig[0] = sp; s.trig[1] = cp;     // srx crx <- pitch
+    s.trig[2] = sy; s.trig[3] = cy;     // sry cry <- yaw
+    s.trig[4] = sr; s.trig[5] = cr;     // srz crz <- roll
+}
+
+__global__ void k_s2m_prepare(S2MState* st, int batch, const int* off_c, const int* off_s, int edge_min, int surf_min, int* not_enough) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    S2MState& s = st[b];
+    prepare_pose_device(s);
+    s.done = 0; s.converged = 0; s.iters = 0; s.n_sel = 0; s.ran = 0; s.ticket = 0;
+    const int nc = off_c[b + 1] - off_c[b], ns = off_s[b + 1] - off_s[b];
+    const int ne = !(nc > edge_min && ns > surf_min);      // guard of scan2MapOptimization :1287
+    if (ne) s.done = 1;
+    if (not_enough) not_enough[b] = ne;
+}
+
+// ---- per-feature fits -------------------------------------------------------------------------------------------
+// Returns true when the feature is kept; coeff = coeffSel entry.
+__device__ __forceinline__ bool fit_line(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+                                         float x0, float y0, float z0, float4& coeff) {
+    float cx = 0, cy = 0, cz = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) { cx += nx[j]; cy += ny[j]; cz += nz[j]; }
+    cx /= 5; cy /= 5; cz /= 5;
+    float a11 = 0, a12 = 0, a13 = 0, a22 = 0, a23 = 0, a33 = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        float ax = nx[j] - cx, ay = ny[j] - cy, az = nz[j] - cz;
+        a11 += ax * ax; a12 += ax * ay; a13 += ax * az;
+        a22 += ay * ay; a23 += ay * az;
+        a33 += az * az;
+    }
+    a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
+    float m[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
+    float w[3], v[9];
+    sym_eigen_jacobi<3>(m, w, v);
+    if (!(w[0] > 3 * w[1])) return false;
+    // two points on the line, 0.1 either side of the centroid (double literal: evaluated in double, narrowed)
+    float x1 = cx + 0.1 * v[0], y1 = cy + 0.1 * v[1], z1 = cz + 0.1 * v[2];
+    float x2 = cx - 0.1 * v[0], y2 = cy - 0.1 * v[1], z2 = cz - 0.1 * v[2];
+    float mxy = (x0 - x1) * (y0 - y2) - (x0 - x2) * (y0 - y1);
+    float mxz = (x0 - x1) * (z0 - z2) - (x0 - x2) * (z0 - z1);
+    float myz = (y0 - y1) * (z0 - z2) - (y0 - y2) * (z0 - z1);
+    float a012 = sqrtf(mxy * mxy + mxz * mxz + myz * myz);
+    float l12 = sqrtf((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+    float la = ((y1 - y2) * mxy + (z1 - z2) * mxz) / a012 / l12;
+    float lb = -((x1 - x2) * mxy - (z1 - z2) * myz) / a012 / l12;
+    float lc = -((x1 - x2) * mxz + (y1 - y2) * myz) / a012 / l12;
+    float ld2 = a012 / l12;
+    float s = 1 - 0.9 * fabsf(ld2);
+    coeff = make_float4(s * la, s * lb, s * lc, s * ld2);
+    return s > 0.1;
+}
+
+__device__ __forceinline__ bool fit_plane(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+                                          float sx, float sy, float sz, float ox, float oy, float oz, float4& coeff) {
+    float pa, pb, pc, pd = 1;
+    plane_lsq_5x3(nx, ny, nz, pa, pb, pc);
+    float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+    pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+#pragma unroll
+    for (int j = 0; j < 5; j++)
+        if (fabsf(pa * nx[j] + pb * ny[j] + pc * nz[j] + pd) > 0.2) return false;
+    float pd2 = pa * sx + pb * sy + pc * sz + pd;
+    float s = 1 - 0.9 * fabsf(pd2) / sqrtf(sqrtf(ox * ox + oy * oy + oz * oz));
+    coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
+    return s > 0.1;
+}
+
+// ---- epilogue: normal equations -> pose update (single thread) ------------------------------------------------------
+__device__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, const S2MArgs& a, int scan) {
+    const int K = (int)(sums[27] + 0.5);
+    s.n_sel = K;
+    if (K < a.min_corr) {
+        // LMOptimization returns false before touching the pose (:1178-1180): every later iteration would repeat
+        // this one exactly, so the loop is over; iters counts the iterations the reference would have spent.
+        s.ran = 0;
+        if (a.device_driven) {
+            if (a.pose_hist)
+                for (int it = s.iters; it < a.max_iters; it++)
+                    for (int i = 0; i < 6; i++) a.pose_hist[((size_t)scan * a.hist_stride + it) * 6 + i] = s.pose[i];
+            s.iters = a.max_iters;
+            s.done = 1;
+        } else {
+            s.iters += 1;
+        }
+        return;
+    }
+    s.ran = 1;
+    float AtA[36], AtB[6], X[6];
+    {
+        int q = 0;
+        for (int r = 0; r < 6; r++)
+            for (int c = r; c < 6; c++) { float f = (float)sums[q++]; AtA[r * 6 + c] = f; AtA[c * 6 + r] = f; }
+        for (int r = 0; r < 6; r++) AtB[r] = (float)sums[21 + r];
+    }
+    for (int i = 0; i < 36; i++) s.AtA[i] = AtA[i];
+    for (int i = 0; i < 6; i++) s.AtB[i] = AtB[i];
+    {
+        float w[36];
+        for (int i = 0; i < 36; i++) w[i] = AtA[i];
+        for (int i = 0; i < 6; i++) X[i] = AtB[i];
+        if (!solve_householder<6>(w, X)) for (int i = 0; i < 6; i++) X[i] = 0.f;
+    }
+    if (iterCount == 0) {
+        float w[36], E[6], V[36], V2[36], Vi[36];
+        for (int i = 0; i < 36; i++) w[i] = AtA[i];
+        sym_eigen_jacobi<6>(w, E, V);
+        for (int i = 0; i < 36; i++) V2[i] = V[i];
+        int deg = 0;
+        for (int i = 5; i >= 0; i--) {
+            if (E[i] < a.eig_thr) { for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f; deg = 1; }
+            else break;
+        }
+        s.degenerate = deg;
+        for (int i = 0; i < 36; i++) w[i] = V[i];
+        invert_lu<6>(w, Vi);
+        matmul_dacc<6, 6>(Vi, V2, s.matP);
+    }
+    if (s.degenerate) {
+        float X2[6];
+        for (int i = 0; i < 6; i++) X2[i] = X[i];
+        matmul_dacc<6, 1>(s.matP, X2, X);
+    }
+    for (int i = 0; i < 6; i++) { s.X[i] = X[i]; s.pose[i] += X[i]; }
+    const float d0 = X[0] * 57.29578f, d1 = X[1] * 57.29578f, d2 = X[2] * 57.29578f;
+    const float t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
+    const float deltaR = (float)sqrt((double)d0 * (double)d0 + (double)d1 * (double)d1 + (double)d2 * (double)d2);
+    const float deltaT = (float)sqrt((double)t0 * (double)t0 + (double)t1 * (double)t1 + (double)t2 * (double)t2);
+    const int conv = (deltaR < 0.05 && deltaT < 0.05) ? 1 : 0;
+    s.converged = conv;
+    if (a.pose_hist) {
+        float* ph = a.pose_hist + ((size_t)scan * a.hist_stride + s.iters) * 6;
+        for (int i = 0; i < 6; i++) ph[i] = s.pose[i];
+    }
+    s.iters += 1;
+    if (a.device_driven) {
+        if (conv) s.done = 1;
+        else prepare_pose_device(s);
+    }
+}
+
+__global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) {
+    const int scan = blockIdx.y;
+    S2MState& st = a.st[scan];
+    if (st.done) return;                                       // uniform per CTA, written only by a previous launch
+    const int c0 = a.off_c[scan], nc = a.off_c[scan + 1] - c0;
+    const int s0 = a.off_s[scan], ns = a.off_s[scan + 1] - s0;
+    const int nbc = (nc + S2M_FPB - 1) / S2M_FPB, nbs = (ns + S2M_FPB - 1) / S2M_FPB;
+    const int nblk = nbc + nbs;
+    if ((int)blockIdx.x >= nblk) return;
+    const bool is_surf = (int)blockIdx.x >= nbc;
+    const int fb = is_surf ? ((int)blockIdx.x - nbc) * S2M_FPB : (int)blockIdx.x * S2M_FPB;   // first feature of this CTA
+    const int nfeat = is_surf ? ns : nc;
+    const float4* scanp = is_surf ? (a.scan_s + s0) : (a.scan_c + c0);
+    const GridDev& g = is_surf ? a.gs : a.gc;
+
+    __shared__ float s_nb[S2M_FPB][5][4];     // winners: x y z, original index bits
+    __shared__ float s_d2[S2M_FPB][5];
+    __shared__ float s_pt[S2M_FPB][8];        // pointOri xyz i, pointSel xyz
+    __shared__ float s_xf[12], s_trig[6];
+    __shared__ int s_last;
+    __shared__ double s_sum[S2M_NPART];
+
+    if (threadIdx.x < 12) s_xf[threadIdx.x] = st.xf[threadIdx.x];
+    else if (threadIdx.x < 18) s_trig[threadIdx.x - 12] = st.trig[threadIdx.x - 12];
+    __syncthreads();
+
+    // ---------------- phase 1: transform + 5-NN, 8 lanes per feature
+    const int grp = threadIdx.x / S2M_LPF, sub = threadIdx.x & (S2M_LPF - 1);
+    const int f = fb + grp;
+    const bool active = f < nfeat;
+    float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    if (active) {
+        po = __ldg(&scanp[f]);
+        sx = s_xf[0] * po.x + s_xf[1] * po.y + s_xf[2] * po.z + s_xf[3];
+        sy = s_xf[4] * po.x + s_xf[5] * po.y + s_xf[6] * po.z + s_xf[7];
+        sz = s_xf[8] * po.x + s_xf[9] * po.y + s_xf[10] * po.z + s_xf[11];
+    }
+    unsigned long long key[5]; uint32_t pos[5];
+    knn_group<5, S2M_LPF>(g, sx, sy, sz, active, key, pos);
+    if (active) {
+        if (sub < 5) {
+            // lane r of the group fetches winner r (static indexing keeps key/pos in registers)
+            unsigned long long kk = key[0]; uint32_t pp = pos[0];
+#pragma unroll
+            for (int r = 1; r < 5; r++) if (sub == r) { kk = key[r]; pp = pos[r]; }
+            float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            float d = INFINITY;
+            if (kk != KNN_EMPTY) { c = ldg4(&g.pts[pp]); d = __uint_as_float((uint32_t)(kk >> 32)); }
+            s_nb[grp][sub][0] = c.x; s_nb[grp][sub][1] = c.y; s_nb[grp][sub][2] = c.z; s_nb[grp][sub][3] = c.w;
+            s_d2[grp][sub] = d;
+        } else if (sub == 5) {
+            s_pt[grp][0] = po.x; s_pt[grp][1] = po.y; s_pt[grp][2] = po.z; s_pt[grp][3] = po.w;
+            s_pt[grp][4] = sx; s_pt[grp][5] = sy; s_pt[grp][6] = sz;
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: warp 0, one lane per feature
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const int ff = fb + lane;
+        bool keep = false;
+        float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ox = 0.f, oy = 0.f, oz = 0.f;
+        if (ff < nfeat) {
+            float nx[5], ny[5], nz[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) { nx[j] = s_nb[lane][j][0]; ny[j] = s_nb[lane][j][1]; nz[j] = s_nb[lane][j][2]; }
+            ox = s_pt[lane][0]; oy = s_pt[lane][1]; oz = s_pt[lane][2];
+            const float d4 = s_d2[lane][4];
+            if (d4 < 1.0) {
+                if (is_surf) keep = fit_plane(nx, ny, nz, s_pt[lane][4], s_pt[lane][5], s_pt[lane][6], ox, oy, oz, coeff);
+                else keep = fit_line(nx, ny, nz, s_pt[lane][4], s_pt[lane][5], s_pt[lane][6], coeff);
+            }
+            int32_t* di = is_surf ? a.dbg_idx_s : a.dbg_idx_c;
+            if (di) {
+                float* dd = is_surf ? a.dbg_d2_s : a.dbg_d2_c;
+                float4* dc = is_surf ? a.dbg_coeff_s : a.dbg_coeff_c;
+                uint8_t* df = is_surf ? a.dbg_flag_s : a.dbg_flag_c;
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    di[(size_t)ff * 5 + j] = __float_as_int(s_nb[lane][j][3]);
+                    dd[(size_t)ff * 5 + j] = s_d2[lane][j];
+                }
+                dc[ff] = coeff; df[ff] = keep ? 1 : 0;
+            }
+        }
+        // Jacobian row (LMOptimization :1191-1222): camera-frame swap p' = (y, z, x), c' = (cy, cz, cx)
+        double acc[S2M_NPART];
+#pragma unroll
+        for (int q = 0; q < S2M_NPART; q++) acc[q] = 0.0;
+        if (keep) {
+            const float srx = s_trig[0], crx = s_trig[1], sry = s_trig[2], cry = s_trig[3], srz = s_trig[4], crz = s_trig[5];
+            const float px = oy, py = oz, pz = ox;
+            const float cfx = coeff.y, cfy = coeff.z, cfz = coeff.x;
+            float arx = (crx*sry*srz*px + crx*crz*sry*py - srx*sry*pz) * cfx
+                      + (-srx*srz*px - crz*srx*py - crx*pz) * cfy
+                      + (crx*cry*srz*px + crx*cry*crz*py - cry*srx*pz) * cfz;
+            float ary = ((cry*srx*srz - crz*sry)*px
+                      + (sry*srz + cry*crz*srx)*py + crx*cry*pz) * cfx
+                      + ((-cry*crz - srx*sry*srz)*px
+                      + (cry*srz - crz*srx*sry)*py - crx*sry*pz) * cfz;
+            float arz = ((crz*srx*sry - cry*srz)*px + (-cry*crz-srx*sry*srz)*py)*cfx
+                      + (crx*crz*px - crx*srz*py) * cfy
+                      + ((sry*srz + cry*crz*srx)*px + (crz*sry-cry*srx*srz)*py)*cfz;
+            const double row[6] = {(double)arz, (double)arx, (double)ary, (double)cfz, (double)cfx, (double)cfy};
+            const double bb = (double)(-coeff.w);
+            int q = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = r; c < 6; c++) acc[q++] = row[r] * row[c];
+#pragma unroll
+            for (int r = 0; r < 6; r++) acc[21 + r] = row[r] * bb;
+            acc[27] = 1.0;
+        }
+#pragma unroll
+        for (int q = 0; q < S2M_NPART; q++) acc[q] = warp_sum(acc[q]);
+        if (lane == 0) {
+            double* out = a.partial + ((size_t)scan * a.max_blocks + blockIdx.x) * S2M_NPART;
+#pragma unroll
+            for (int q = 0; q < S2M_NPART; q++) __stcg(&out[q], acc[q]);
+            __threadfence();
+            unsigned t = atomicAdd(&st.ticket, 1u);
+            s_last = (t == (unsigned)(nblk - 1)) ? 1 : 0;
+        }
+        __syncwarp();
+        // ---------------- epilogue: last CTA of this scan
+        if (s_last) {
+            __threadfence();
+            if (lane < S2M_NPART) {
+                const double* base = a.partial + (size_t)scan * a.max_blocks * S2M_NPART + lane;
+                double sum = 0.0;
+                for (int b = 0; b < nblk; b++) sum += __ldcg(&base[(size_t)b * S2M_NPART]);
+                s_sum[lane] = sum;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                st.ticket = 0;
+                const int iterCount = a.iter >= 0 ? a.iter : st.iters;
+                lm_epilogue(st, s_sum, iterCount, a, scan);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pack_xyzi(const unsigned char* __restrict__ raw, size_t stride, int ioff, uint32_t n, float4* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* p = raw + (size_t)i * stride;
+    const float* f = reinterpret_cast<const float*>(p);
+    out[i] = make_float4(f[0], f[1], f[2], *reinterpret_cast<const float*>(p + ioff));
+}
+
+__global__ void __launch_bounds__(256) k_transform_cloud(const unsigned char* __restrict__ in, size_t istride, int ioff_in, uint32_t n,
+                                                         const float* __restrict__ xf, unsigned char* __restrict__ out, size_t ostride, int ioff_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char* p = in + (size_t)i * istride;
+    const float* f = reinterpret_cast<const float*>(p);
+    const float x = f[0], y = f[1], z = f[2];
+    float* o = reinterpret_cast<float*>(out + (size_t)i * ostride);
+    o[0] = xf[0] * x + xf[1] * y + xf[2] * z + xf[3];
+    o[1] = xf[4] * x + xf[5] * y + xf[6] * z + xf[7];
+    o[2] = xf[8] * x + xf[9] * y + xf[10] * z + xf[11];
+    *reinterpret_cast<float*>(out + (size_t)i * ostride + ioff_out) = *reinterpret_cast<const float*>(p + ioff_in);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_s2m_s {
+    b2_s2m_params prm;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    GridIndex gc, gs;
+    DevBuf raw_c, raw_s, scan_c, scan_s, off_c, off_s, state, partial, hist, ne;
+    DevBuf dbg_idx_c, dbg_d2_c, dbg_coeff_c, dbg_flag_c, dbg_idx_s, dbg_d2_s, dbg_coeff_s, dbg_flag_s;
+    PinBuf pin;
+    bool have_map = false, have_scan = false;
+    int batch = 0;
+    int max_blocks = 0;
+    size_t n_c = 0, n_s = 0;          // total features over the batch
+    std::vector<int> h_off_c, h_off_s;
+    int degenerate = 0;               // persistent members (:136,:234)
+    float matP[36] = {0};
+    float last_ms = 0.f; int last_launches = 0;
+};
+
+static void host_prepare_pose(const float pose[6], float xf[12], float trig[6]) {
+    // exactly what the reference evaluates on the CPU: float sin/cos from the C library
+    const float roll = pose[0], pitch = pose[1], yaw = pose[2];
+    const float sr = std::sin(roll), cr = std::cos(roll), sp = std::sin(pitch), cp = std::cos(pitch), sy = std::sin(yaw), cy = std::cos(yaw);
+    affine_from_trig(pose[3], pose[4], pose[5], cy, sy, cp, sp, cr, sr, xf);
+    trig[0] = sp; trig[1] = cp; trig[2] = sy; trig[3] = cy; trig[4] = sr; trig[5] = cr;
+}
+
+static int upload_points(b2_s2m_s* h, DevBuf& raw, DevBuf& packed, const void* pts, size_t stride, size_t n) {
+    if (n == 0) return B2_OK;
+    B2_CHECK(raw.reserve(n * stride));
+    B2_CHECK(packed.reserve(n * sizeof(float4)));
+    B2_CUDA(cudaMemcpyAsync(raw.p, pts, n * stride, cudaMemcpyHostToDevice, h->stream));
+    k_pack_xyzi<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(raw.as<unsigned char>(), stride, (int)B2_INTENSITY_OFFSET(stride), (uint32_t)n, packed.as<float4>()); count_launch();
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
+static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, float* pose_hist, int hist_stride) {
+    S2MArgs a{};
+    a.max_iters = hist_stride > 0 ? hist_stride : h->prm.max_iterations;
+    a.gc = h->gc.dev; a.gs = h->gs.dev;
+    a.scan_c = h->scan_c.as<float4>(); a.scan_s = h->scan_s.as<float4>();
+    a.off_c = h->off_c.as<int>(); a.off_s = h->off_s.as<int>();
+    a.st = h->state.as<S2MState>();
+    a.partial = h->partial.as<double>();
+    a.max_blocks = h->max_blocks;
+    a.iter = iter; a.device_driven = device_driven;
+    a.min_corr = h->prm.min_correspondences; a.eig_thr = h->prm.degenerate_eigen_threshold;
+    a.pose_hist = pose_hist; a.hist_stride = hist_stride;
+    if (debug) {
+        a.dbg_idx_c = h->dbg_idx_c.as<int32_t>(); a.dbg_d2_c = h->dbg_d2_c.as<float>(); a.dbg_coeff_c = h->dbg_coeff_c.as<float4>(); a.dbg_flag_c = h->dbg_flag_c.as<uint8_t>();
+        a.dbg_idx_s = h->dbg_idx_s.as<int32_t>(); a.dbg_d2_s = h->dbg_d2_s.as<float>(); a.dbg_coeff_s = h->dbg_coeff_s.as<float4>(); a.dbg_flag_s = h->dbg_flag_s.as<uint8_t>();
+    }
+    return a;
+}
+
+static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cstride, const int32_t* coff,
+                           const void* surf, size_t sstride, const int32_t* soff) {
+    if (batch < 1 || batch > h->prm.max_batch) { set_error("set_scan: batch %d outside [1, %d]", batch, h->prm.max_batch); return B2_ERR_ARG; }
+    h->h_off_c.assign(coff, coff + batch + 1);
+    h->h_off_s.assign(soff, soff + batch + 1);
+    for (int b = 0; b < batch; b++)
+        if (coff[b + 1] < coff[b] || soff[b + 1] < soff[b]) { set_error("set_scan: offsets must be non-decreasing"); return B2_ERR_ARG; }
+    h->n_c = (size_t)coff[batch]; h->n_s = (size_t)soff[batch];
+    if ((h->n_c && !corner) || (h->n_s && !surf)) { set_error("set_scan: null feature array"); return B2_ERR_ARG; }
+    B2_CHECK(upload_points(h, h->raw_c, h->scan_c, corner, cstride, h->n_c));
+    B2_CHECK(upload_points(h, h->raw_s, h->scan_s, surf, sstride, h->n_s));
+    B2_CHECK(h->off_c.reserve((batch + 1) * sizeof(int)));
+    B2_CHECK(h->off_s.reserve((batch + 1) * sizeof(int)));
+    B2_CUDA(cudaMemcpyAsync(h->off_c.p, h->h_off_c.data(), (batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    B2_CUDA(cudaMemcpyAsync(h->off_s.p, h->h_off_s.data(), (batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    int mb = 1;
+    for (int b = 0; b < batch; b++) {
+        int nb = (coff[b + 1] - coff[b] + S2M_FPB - 1) / S2M_FPB + (soff[b + 1] - soff[b] + S2M_FPB - 1) / S2M_FPB;
+        mb = std::max(mb, nb);
+    }
+    h->max_blocks = mb;
+    h->batch = batch;
+    B2_CHECK(h->state.reserve((size_t)batch * sizeof(S2MState)));
+    B2_CHECK(h->partial.reserve((size_t)batch * mb * S2M_NPART * sizeof(double)));
+    B2_CHECK(h->ne.reserve((size_t)batch * sizeof(int)));
+    if (batch == 1) {
+        const size_t nc = std::max<size_t>(h->n_c, 1), ns = std::max<size_t>(h->n_s, 1);
+        B2_CHECK(h->dbg_idx_c.reserve(nc * 5 * 4)); B2_CHECK(h->dbg_d2_c.reserve(nc * 5 * 4));
+        B2_CHECK(h->dbg_coeff_c.reserve(nc * 16)); B2_CHECK(h->dbg_flag_c.reserve(nc));
+        B2_CHECK(h->dbg_idx_s.reserve(ns * 5 * 4)); B2_CHECK(h->dbg_d2_s.reserve(ns * 5 * 4));
+        B2_CHECK(h->dbg_coeff_s.reserve(ns * 16)); B2_CHECK(h->dbg_flag_s.reserve(ns));
+    }
+    B2_CUDA(cudaStreamSynchronize(h->stream));     // caller may free its buffers on return
+    h->have_scan = true;
+    return B2_OK;
+}
+
+extern "C" {
+
+void b2_s2m_default_params(b2_s2m_params* p) {
+    if (!p) return;
+    p->edge_feature_min_valid_num = 10;
+    p->surf_feature_min_valid_num = 100;
+    p->max_iterations = 30;
+    p->min_correspondences = 50;
+    p->knn_max_dist = 1.0f;
+    p->degenerate_eigen_threshold = 100.f;
+    p->max_batch = 1;
+}
+
+int b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params) {
+    if (!out) { set_error("b2_s2m_create: null out"); return B2_ERR_ARG; }
+    b2_s2m_s* h = new b2_s2m_s();
+    if (params) h->prm = *params; else b2_s2m_default_params(&h->prm);
+    if (h->prm.max_batch < 1 || h->prm.max_iterations < 1 || !(h->prm.knn_max_dist > 0.f)) { delete h; set_error("b2_s2m_create: bad params"); return B2_ERR_ARG; }
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) { set_error("b2_s2m_create: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
+    *out = h;
+    return B2_OK;
+}
+
+int b2_s2m_destroy(b2_s2m_t h) {
+    if (!h) return B2_ERR_ARG;
+    h->gc.release(); h->gs.release();
+    DevBuf* bufs[] = {&h->raw_c, &h->raw_s, &h->scan_c, &h->scan_s, &h->off_c, &h->off_s, &h->state, &h->partial, &h->hist, &h->ne,
+                      &h->dbg_idx_c, &h->dbg_d2_c, &h->dbg_coeff_c, &h->dbg_flag_c, &h->dbg_idx_s, &h->dbg_d2_s, &h->dbg_coeff_s, &h->dbg_flag_s};
+    for (DevBuf* b : bufs) b->release();
+    h->pin.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B2_OK;
+}
+
+int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corner, const void* surf, size_t sstride, size_t n_surf) {
+    if (!h || (n_corner && !corner) || (n_surf && !surf) || cstride < 12 || sstride < 12 || (cstride & 3) || (sstride & 3)) {
+        set_error("b2_s2m_set_map: bad argument"); return B2_ERR_ARG;
+    }
+    B2_CHECK(h->gc.build(corner, cstride, n_corner, h->prm.knn_max_dist, h->stream));
+    B2_CHECK(h->gs.build(surf, sstride, n_surf, h->prm.knn_max_dist, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    h->have_map = true;
+    return B2_OK;
+}
+
+int b2_s2m_set_scan(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corner, const void* surf, size_t sstride, size_t n_surf) {
+    if (!h || cstride < 16 || sstride < 16 || (cstride & 3) || (sstride & 3) || n_corner > 0x7fffffff || n_surf > 0x7fffffff) {
+        set_error("b2_s2m_set_scan: bad argument"); return B2_ERR_ARG;
+    }
+    int32_t co[2] = {0, (int32_t)n_corner}, so[2] = {0, (int32_t)n_surf};
+    return set_scan_common(h, 1, corner, cstride, co, surf, sstride, so);
+}
+
+int b2_s2m_set_scan_batch(b2_s2m_t h, int batch, const void* corner, size_t cstride, const int32_t* coff,
+                          const void* surf, size_t sstride, const int32_t* soff) {
+    if (!h || !coff || !soff || cstride < 16 || sstride < 16 || (cstride & 3) || (sstride & 3)) { set_error("b2_s2m_set_scan_batch: bad argument"); return B2_ERR_ARG; }
+    return set_scan_common(h, batch, corner, cstride, coff, surf, sstride, soff);
+}
+
+int b2_s2m_set_state(b2_s2m_t h, int degenerate, const float matP[36]) {
+    if (!h) return B2_ERR_ARG;
+    h->degenerate = degenerate ? 1 : 0;
+    if (matP) memcpy(h->matP, matP, sizeof(h->matP));
+    return B2_OK;
+}
+
+int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, int* converged, int* degenerate, float matP[36]) {
+    if (!h || !pose || iter < 0) { set_error("b2_s2m_iterate: bad argument"); return B2_ERR_ARG; }
+    if (!h->have_map || !h->have_scan || h->batch != 1) { set_error("b2_s2m_iterate: set_map and set_scan (single scan) first"); return B2_ERR_STATE; }
+    B2_CHECK(h->pin.reserve(sizeof(S2MState)));
+    S2MState* hs = h->pin.as<S2MState>();
+    memset(hs, 0, sizeof(S2MState));
+    memcpy(hs->pose, pose, 24);
+    host_prepare_pose(pose, hs->xf, hs->trig);
+    memcpy(hs->matP, h->matP, sizeof(h->matP));
+    hs->degenerate = h->degenerate;
+    B2_CUDA(cudaMemcpyAsync(h->state.p, hs, sizeof(S2MState), cudaMemcpyHostToDevice, h->stream));
+    S2MArgs a = make_args(h, iter, 0, true, nullptr, 0);
+    dim3 grid((unsigned)h->max_blocks, 1);
+    k_s2m_iteration<<<grid, S2M_THREADS, 0, h->stream>>>(a); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaMemcpyAsync(hs, h->state.p, sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(pose, hs->pose, 24);
+    h->degenerate = hs->degenerate;
+    memcpy(h->matP, hs->matP, sizeof(h->matP));
+    if (n_sel) *n_sel = hs->n_sel;
+    if (ran) *ran = hs->ran;
+    if (converged) *converged = hs->ran ? hs->converged : 0;
+    if (degenerate) *degenerate = hs->degenerate;
+    if (matP) memcpy(matP, hs->matP, sizeof(h->matP));
+    return B2_OK;
+}
+
+static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_done, int* converged, int* degenerate,
+                     float* matP_out, int* not_enough, float* pose_history) {
+    const int B = h->batch;
+    if (max_iterations < 1) max_iterations = h->prm.max_iterations;
+    B2_CHECK(h->pin.reserve((size_t)B * sizeof(S2MState) + (size_t)B * sizeof(int)));
+    S2MState* hs = h->pin.as<S2MState>();
+    memset(hs, 0, (size_t)B * sizeof(S2MState));
+    for (int b = 0; b < B; b++) {
+        memcpy(hs[b].pose, poses + (size_t)b * 6, 24);
+        memcpy(hs[b].matP, h->matP, sizeof(h->matP));
+        hs[b].degenerate = h->degenerate;
+    }
+    float* d_hist = nullptr;
+    if (pose_history) {
+        B2_CHECK(h->hist.reserve((size_t)B * max_iterations * 6 * sizeof(float)));
+        d_hist = h->hist.as<float>();
+    }
+    B2_CUDA(cudaEventRecord(h->ev0, h->stream));
+    B2_CUDA(cudaMemcpyAsync(h->state.p, hs, (size_t)B * sizeof(S2MState), cudaMemcpyHostToDevice, h->stream));
+    if (d_hist) B2_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)B * max_iterations * 6 * sizeof(float), h->stream));
+    k_s2m_prepare<<<(B + 127) / 128, 128, 0, h->stream>>>(h->state.as<S2MState>(), B, h->off_c.as<int>(), h->off_s.as<int>(),
+                                                          h->prm.edge_feature_min_valid_num, h->prm.surf_feature_min_valid_num, h->ne.as<int>()); count_launch();
+    B2_CUDA(cudaGetLastError());
+    S2MArgs a = make_args(h, -1, 1, false, d_hist, max_iterations);
+    dim3 grid((unsigned)h->max_blocks, (unsigned)B);
+    for (int it = 0; it < max_iterations; it++) k_s2m_iteration<<<grid, S2M_THREADS, 0, h->stream>>>(a);
+    count_launch(max_iterations);
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaEventRecord(h->ev1, h->stream));
+    int* h_ne = reinterpret_cast<int*>(hs + B);
+    B2_CUDA(cudaMemcpyAsync(hs, h->state.p, (size_t)B * sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaMemcpyAsync(h_ne, h->ne.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (pose_history) B2_CUDA(cudaMemcpyAsync(pose_history, d_hist, (size_t)B * max_iterations * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->last_launches = 1 + max_iterations;
+    for (int b = 0; b < B; b++) {
+        if (!h_ne[b]) memcpy(poses + (size_t)b * 6, hs[b].pose, 24);
+        if (iters_done) iters_done[b] = hs[b].iters;
+        if (converged) converged[b] = hs[b].converged;
+        if (degenerate) degenerate[b] = hs[b].degenerate;
+        if (not_enough) not_enough[b] = h_ne[b];
+    }
+    if (B == 1 && !h_ne[0]) {
+        h->degenerate = hs[0].degenerate;
+        memcpy(h->matP, hs[0].matP, sizeof(h->matP));
+    }
+    if (matP_out) memcpy(matP_out, hs[0].matP, sizeof(h->matP));
+    return B2_OK;
+}
+
+int b2_s2m_solve(b2_s2m_t h, float pose[6], int max_iterations, int* iters_done, int* converged, int* degenerate,
+                 float matP[36], int* not_enough_features, float* pose_history) {
+    if (!h || !pose) { set_error("b2_s2m_solve: bad argument"); return B2_ERR_ARG; }
+    if (!h->have_map || !h->have_scan || h->batch != 1) { set_error("b2_s2m_solve: set_map and set_scan (single scan) first"); return B2_ERR_STATE; }
+    return run_solve(h, pose, max_iterations, iters_done, converged, degenerate, matP, not_enough_features, pose_history);
+}
+
+int b2_s2m_solve_batch(b2_s2m_t h, float* poses, int max_iterations, int* iters_done, int* converged, int* degenerate) {
+    if (!h || !poses) { set_error("b2_s2m_solve_batch: bad argument"); return B2_ERR_ARG; }
+    if (!h->have_map || !h->have_scan) { set_error("b2_s2m_solve_batch: set_map and set_scan_batch first"); return B2_ERR_STATE; }
+    return run_solve(h, poses, max_iterations, iters_done, converged, degenerate, nullptr, nullptr, nullptr);
+}
+
+int b2_s2m_get_pass(b2_s2m_t h, int which, int32_t* knn_idx, float* knn_d2, float* coeff, uint8_t* flag) {
+    if (!h || !h->have_scan || h->batch != 1) { set_error("b2_s2m_get_pass: single-scan state required"); return B2_ERR_STATE; }
+    const size_t n = which ? h->n_s : h->n_c;
+    if (n == 0) return B2_OK;
+    DevBuf& di = which ? h->dbg_idx_s : h->dbg_idx_c; DevBuf& dd = which ? h->dbg_d2_s : h->dbg_d2_c;
+    DevBuf& dc = which ? h->dbg_coeff_s : h->dbg_coeff_c; DevBuf& df = which ? h->dbg_flag_s : h->dbg_flag_c;
+    if (knn_idx) B2_CUDA(cudaMemcpyAsync(knn_idx, di.p, n * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (knn_d2) B2_CUDA(cudaMemcpyAsync(knn_d2, dd.p, n * 5 * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (coeff) B2_CUDA(cudaMemcpyAsync(coeff, dc.p, n * 16, cudaMemcpyDeviceToHost, h->stream));
+    if (flag) B2_CUDA(cudaMemcpyAsync(flag, df.p, n, cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}
+
+int b2_s2m_get_normal_equations(b2_s2m_t h, float AtA[36], float AtB[6], float X[6]) {
+    if (!h || !h->have_scan) { set_error("b2_s2m_get_normal_equations: no scan"); return B2_ERR_STATE; }
+    S2MState hs;
+    B2_CUDA(cudaMemcpyAsync(&hs, h->state.p, sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    if (AtA) memcpy(AtA, hs.AtA, sizeof(hs.AtA));
+    if (AtB) memcpy(AtB, hs.AtB, sizeof(hs.AtB));
+    if (X) memcpy(X, hs.X, sizeof(hs.X));
+    return B2_OK;
+}
+
+int b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches) {
+    if (!h) return B2_ERR_ARG;
+    if (ms) *ms = h->last_ms;
+    if (launches) *launches = h->last_launches;
+    return B2_OK;
+}
+
+int b2_transform_cloud(const void* in, size_t in_stride, size_t n, const float pose6[6], void* out, size_t out_stride) {
+    if ((n && (!in || !out)) || !pose6 || in_stride < 16 || out_stride < 16 || (in_stride & 3) || (out_stride & 3)) { set_error("b2_transform_cloud: bad argument"); return B2_ERR_ARG; }
+    if (n == 0) return B2_OK;
+    float xf[12], trig[6];
+    host_prepare_pose(pose6, xf, trig);
+    unsigned char *d_in = nullptr, *d_out = nullptr; float* d_xf = nullptr;
+    B2_CUDA(cudaMalloc(&d_in, n * in_stride));
+    cudaError_t e = cudaMalloc(&d_out, n * out_stride);
+    if (e == cudaSuccess) e = cudaMalloc(&d_xf, sizeof(xf));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, in, n * in_stride, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_out, 0, n * out_stride);
+    if (e == cudaSuccess) e = cudaMemcpy(d_xf, xf, sizeof(xf), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_transform_cloud<<<(unsigned)((n + 255) / 256), 256>>>(d_in, in_stride, (int)B2_INTENSITY_OFFSET(in_stride), (uint32_t)n, d_xf,
+                                                                d_out, out_stride, (int)B2_INTENSITY_OFFSET(out_stride)); count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * out_stride, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_xf);
+    if (e != cudaSuccess) { set_error("b2_transform_cloud: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
+    return B2_OK;
+}
+
+}  // extern "C"

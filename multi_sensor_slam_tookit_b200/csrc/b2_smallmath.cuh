@@ -1,0 +1,255 @@
+// Small dense solvers used inside the scan-to-map kernels, in the operation order of the library routines the
+// reference calls (so that accept/reject thresholds see the same bits as the CPU path):
+//   sym_eigen_jacobi<N>   cv::eigen on CV_32F        mapOptmization.cpp:1018 (3x3), :1235 (6x6)
+//   solve_householder<N>  cv::solve(DECOMP_QR)       mapOptmization.cpp:1227
+//   invert_lu<N>          cv::Mat::inv() (LU)        mapOptmization.cpp:1250
+//   plane_lsq_5x3         Eigen colPivHouseholderQr  mapOptmization.cpp:1096
+// All float, IEEE div/sqrt, no FMA (-fmad=false). Host+device so the host epilogue tests can reuse them.
+#pragma once
+#include <cfloat>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#else
+#define B2_HD inline
+#endif
+
+namespace b2 {
+
+B2_HD float scaled_hypot(float a, float b) {
+    a = fabsf(a); b = fabsf(b);
+    if (a > b) { b /= a; return a * sqrtf(1 + b * b); }
+    if (b > 0) { a /= b; return b * sqrtf(1 + a * a); }
+    return 0.f;
+}
+
+// largest |a(row, j)| for j in (row, N): index of first maximum
+template <int N>
+B2_HD int argmax_row(const float* a, int row) {
+    int m = row + 1; float mv = fabsf(a[N * row + m]);
+    for (int i = row + 2; i < N; i++) { float v = fabsf(a[N * row + i]); if (mv < v) { mv = v; m = i; } }
+    return m;
+}
+// largest |a(i, col)| for i in [0, col): index of first maximum
+template <int N>
+B2_HD int argmax_col(const float* a, int col) {
+    int m = 0; float mv = fabsf(a[col]);
+    for (int i = 1; i < col; i++) { float v = fabsf(a[N * i + col]); if (mv < v) { mv = v; m = i; } }
+    return m;
+}
+
+// Jacobi eigen-decomposition of a symmetric NxN (row-major, destroyed). w descending, v rows = eigenvectors.
+template <int N>
+B2_HD void sym_eigen_jacobi(float* a, float* w, float* v) {
+    int rmax[N], cmax[N];
+    for (int i = 0; i < N; i++) { for (int j = 0; j < N; j++) v[i * N + j] = (i == j) ? 1.f : 0.f; }
+    for (int k = 0; k < N; k++) {
+        w[k] = a[(N + 1) * k];
+        if (k < N - 1) rmax[k] = argmax_row<N>(a, k);
+        if (k > 0) cmax[k] = argmax_col<N>(a, k);
+    }
+    const int max_rot = N * N * 30;
+    for (int it = 0; it < max_rot; it++) {
+        int k = 0; float mv = fabsf(a[rmax[0]]);
+        for (int i = 1; i < N - 1; i++) { float val = fabsf(a[N * i + rmax[i]]); if (mv < val) { mv = val; k = i; } }
+        int l = rmax[k];
+        for (int i = 1; i < N; i++) { float val = fabsf(a[N * cmax[i] + i]); if (mv < val) { mv = val; k = cmax[i]; l = i; } }
+        float p = a[N * k + l];
+        if (fabsf(p) <= FLT_EPSILON) break;
+        float y = (float)((w[l] - w[k]) * 0.5);
+        float t = fabsf(y) + scaled_hypot(p, y);
+        float s = scaled_hypot(p, t);
+        float c = t / s;
+        s = p / s; t = (p / t) * p;
+        if (y < 0) { s = -s; t = -t; }
+        a[N * k + l] = 0;
+        w[k] -= t; w[l] += t;
+        for (int i = 0; i < k; i++)     { float a0 = a[N * i + k], b0 = a[N * i + l]; a[N * i + k] = a0 * c - b0 * s; a[N * i + l] = a0 * s + b0 * c; }
+        for (int i = k + 1; i < l; i++) { float a0 = a[N * k + i], b0 = a[N * i + l]; a[N * k + i] = a0 * c - b0 * s; a[N * i + l] = a0 * s + b0 * c; }
+        for (int i = l + 1; i < N; i++) { float a0 = a[N * k + i], b0 = a[N * l + i]; a[N * k + i] = a0 * c - b0 * s; a[N * l + i] = a0 * s + b0 * c; }
+        for (int i = 0; i < N; i++)     { float a0 = v[N * k + i], b0 = v[N * l + i]; v[N * k + i] = a0 * c - b0 * s; v[N * l + i] = a0 * s + b0 * c; }
+        for (int j = 0; j < 2; j++) {
+            int idx = j == 0 ? k : l;
+            if (idx < N - 1) rmax[idx] = argmax_row<N>(a, idx);
+            if (idx > 0) cmax[idx] = argmax_col<N>(a, idx);
+        }
+    }
+    for (int k = 0; k < N - 1; k++) {
+        int m = k;
+        for (int i = k + 1; i < N; i++) if (w[m] < w[i]) m = i;
+        if (k != m) {
+            float tw = w[m]; w[m] = w[k]; w[k] = tw;
+            for (int i = 0; i < N; i++) { float tv = v[N * m + i]; v[N * m + i] = v[N * k + i]; v[N * k + i] = tv; }
+        }
+    }
+}
+
+// Householder QR solve of a square system, one right-hand side; a, b destroyed, x left in b. 0 = singular.
+template <int N>
+B2_HD int solve_householder(float* a, float* b) {
+    const float eps = FLT_EPSILON * 10;
+    float u[N], hf[N];
+    for (int l = 0; l < N; l++) {
+        const int len = N - l;
+        float nrm = 0.f;
+        for (int i = 0; i < len; i++) { u[i] = a[(l + i) * N + l]; nrm += u[i] * u[i]; }
+        float head = u[0];
+        u[0] = u[0] + ((u[0] >= 0.0f) ? 1 : -1) * sqrtf(nrm);
+        nrm = sqrtf(nrm + u[0] * u[0] - head * head);
+        for (int i = 0; i < len; i++) u[i] /= nrm;
+        for (int j = l; j < N; j++) {
+            float dot = 0.f;
+            for (int i = l; i < N; i++) dot += u[i - l] * a[i * N + j];
+            for (int i = l; i < N; i++) a[i * N + j] -= 2 * u[i - l] * dot;
+        }
+        hf[l] = u[0] * u[0];
+        for (int i = 1; i < len; i++) a[(l + i) * N + l] = u[i] / u[0];
+    }
+    for (int l = 0; l < N; l++) {
+        u[0] = 1.f;
+        for (int j = 1; j < N - l; j++) u[j] = a[(j + l) * N + l];
+        float dot = 0.f;
+        for (int i = l; i < N; i++) dot += u[i - l] * b[i];
+        for (int i = l; i < N; i++) b[i] -= 2 * u[i - l] * dot * hf[l];
+    }
+    for (int i = N - 1; i >= 0; i--) {
+        for (int j = N - 1; j > i; j--) b[i] -= b[j] * a[i * N + j];
+        if (fabsf(a[i * N + i]) < eps) return 0;
+        b[i] /= a[i * N + i];
+    }
+    return 1;
+}
+
+// Inverse via LU with partial pivoting applied to an identity right-hand side; a destroyed. 0 = singular (inv zeroed).
+template <int N>
+B2_HD int invert_lu(float* a, float* inv) {
+    const float eps = FLT_EPSILON * 10;
+    for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) inv[i * N + j] = (i == j) ? 1.f : 0.f;
+    for (int i = 0; i < N; i++) {
+        int piv = i;
+        for (int j = i + 1; j < N; j++) if (fabsf(a[j * N + i]) > fabsf(a[piv * N + i])) piv = j;
+        if (fabsf(a[piv * N + i]) < eps) { for (int q = 0; q < N * N; q++) inv[q] = 0.f; return 0; }
+        if (piv != i) {
+            for (int j = i; j < N; j++) { float t = a[i * N + j]; a[i * N + j] = a[piv * N + j]; a[piv * N + j] = t; }
+            for (int j = 0; j < N; j++) { float t = inv[i * N + j]; inv[i * N + j] = inv[piv * N + j]; inv[piv * N + j] = t; }
+        }
+        float d = -1 / a[i * N + i];
+        for (int j = i + 1; j < N; j++) {
+            float alpha = a[j * N + i] * d;
+            for (int q = i + 1; q < N; q++) a[j * N + q] += alpha * a[i * N + q];
+            for (int q = 0; q < N; q++) inv[j * N + q] += alpha * inv[i * N + q];
+        }
+    }
+    for (int i = N - 1; i >= 0; i--)
+        for (int j = 0; j < N; j++) {
+            float s = inv[i * N + j];
+            for (int q = i + 1; q < N; q++) s -= a[i * N + q] * inv[q * N + j];
+            inv[i * N + j] = s / a[i * N + i];
+        }
+    return 1;
+}
+
+// C = A*B for NxN float with double accumulation and one rounding per element (cv::gemm on CV_32F)
+template <int N, int NC>
+B2_HD void matmul_dacc(const float* A, const float* B, float* C) {
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < NC; j++) {
+            double s = 0.0;
+            for (int q = 0; q < N; q++) s += (double)A[i * N + q] * (double)B[q * NC + j];
+            C[i * NC + j] = (float)s;
+        }
+}
+
+// min |M x + 1| over x for the 5x3 matrix of neighbour coordinates (rows = points): column-pivoted Householder QR
+// (pivot = largest running column norm, LAPACK WN176 downdate, rank threshold eps^2*maxnorm^2/rows*(rows-k)).
+B2_HD void plane_lsq_5x3(const float (&px)[5], const float (&py)[5], const float (&pz)[5], float& xa, float& xb, float& xc) {
+    float q[5][3];
+#pragma unroll
+    for (int i = 0; i < 5; i++) { q[i][0] = px[i]; q[i][1] = py[i]; q[i][2] = pz[i]; }
+    float tau[3], nu[3], nd[3];
+    int tr[3];
+    for (int k = 0; k < 3; k++) {
+        float s = 0.f;
+        for (int i = 0; i < 5; i++) s += q[i][k] * q[i][k];
+        nd[k] = sqrtf(s); nu[k] = nd[k];
+    }
+    float mx = fmaxf(nu[0], fmaxf(nu[1], nu[2]));
+    float th = mx * FLT_EPSILON;
+    const float thr_helper = (th * th) / 5.0f;
+    const float downdate_thr = sqrtf(FLT_EPSILON);
+    int rank = 3;
+    for (int k = 0; k < 3; k++) {
+        int big = k; float bv = nu[k];
+        for (int j = k + 1; j < 3; j++) if (nu[j] > bv) { bv = nu[j]; big = j; }
+        if (rank == 3 && bv * bv < thr_helper * (float)(5 - k)) rank = k;
+        tr[k] = big;
+        if (big != k) {
+            for (int i = 0; i < 5; i++) { float t = q[i][k]; q[i][k] = q[i][big]; q[i][big] = t; }
+            float t = nu[k]; nu[k] = nu[big]; nu[big] = t;
+            t = nd[k]; nd[k] = nd[big]; nd[big] = t;
+        }
+        float tail = 0.f;
+        for (int i = k + 1; i < 5; i++) tail += q[i][k] * q[i][k];
+        float c0 = q[k][k], beta, tk;
+        if (tail <= FLT_MIN) {
+            tk = 0.f; beta = c0;
+            for (int i = k + 1; i < 5; i++) q[i][k] = 0.f;
+        } else {
+            beta = sqrtf(c0 * c0 + tail);
+            if (c0 >= 0.f) beta = -beta;
+            float den = c0 - beta;
+            for (int i = k + 1; i < 5; i++) q[i][k] = q[i][k] / den;
+            tk = (beta - c0) / beta;
+        }
+        tau[k] = tk; q[k][k] = beta;
+        if (tk != 0.f) {
+            for (int j = k + 1; j < 3; j++) {
+                float t = 0.f;
+                for (int i = k + 1; i < 5; i++) t += q[i][k] * q[i][j];
+                t += q[k][j];
+                q[k][j] -= tk * t;
+                for (int i = k + 1; i < 5; i++) q[i][j] -= tk * q[i][k] * t;
+            }
+        }
+        for (int j = k + 1; j < 3; j++) {
+            if (nu[j] != 0.f) {
+                float t = fabsf(q[k][j]) / nu[j];
+                t = (1.f + t) * (1.f - t);
+                t = t < 0.f ? 0.f : t;
+                float r = nu[j] / nd[j];
+                float t2 = t * (r * r);
+                if (t2 <= downdate_thr) {
+                    float s = 0.f;
+                    for (int i = k + 1; i < 5; i++) s += q[i][j] * q[i][j];
+                    nd[j] = sqrtf(s); nu[j] = nd[j];
+                } else {
+                    nu[j] *= sqrtf(t);
+                }
+            }
+        }
+    }
+    int perm[3] = {0, 1, 2};
+    for (int k = 0; k < 3; k++) { int t = perm[k]; perm[k] = perm[tr[k]]; perm[tr[k]] = t; }
+    float c[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
+    float x[3] = {0.f, 0.f, 0.f};
+    if (rank > 0) {
+        for (int k = 0; k < rank; k++) {
+            if (tau[k] == 0.f) continue;
+            float t = 0.f;
+            for (int i = k + 1; i < 5; i++) t += q[i][k] * c[i];
+            t += c[k];
+            c[k] -= tau[k] * t;
+            for (int i = k + 1; i < 5; i++) c[i] -= tau[k] * q[i][k] * t;
+        }
+        for (int i = rank - 1; i >= 0; i--) {
+            float s = c[i];
+            for (int j = i + 1; j < rank; j++) s -= q[i][j] * c[j];
+            c[i] = s / q[i][i];
+        }
+        for (int i = 0; i < rank; i++) x[perm[i]] = c[i];
+    }
+    xa = x[0]; xb = x[1]; xc = x[2];
+}
+
+}  // namespace b2

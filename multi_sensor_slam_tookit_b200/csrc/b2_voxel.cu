@@ -1,0 +1,269 @@
+// VoxelGrid downsampling on the device. Replaces pcl::VoxelGrid<PointT>::filter at
+//   liosam_ws/src/LIO-SAM/src/featureExtraction.cpp:233-234, mapOptmization.cpp:719,879,928,932,960,965,
+//   Calibration_Tookit/multi_lidar/.../multi_lidar_calibrator.cpp:113-121, heading_ws/src/src/PointCloudProcessing.cpp:23-30.
+//
+// Pipeline on one stream: bbox reduce -> (host: PCL's leaf/extent arithmetic on 6 floats) -> voxel key per point
+// (float mul + floor, no FMA: the index must be bit-exact) -> stable LSD radix sort of (key, input index) ->
+// run heads -> exclusive scans -> one thread per voxel sums its run in ascending input index (the float sum order
+// the oracle pins) -> centroids in ascending voxel index, already in the caller's stride.
+#include "b2_common.cuh"
+#include <cmath>
+#include <climits>
+#include <algorithm>
+
+namespace b2 {
+
+__global__ void k_vx_bbox_init(uint32_t* bb) {
+    if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
+    else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(256) k_vx_bbox(const unsigned char* __restrict__ raw, size_t stride, size_t n, uint32_t* __restrict__ bb) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float* p = reinterpret_cast<const float*>(raw + i * stride);
+        float x = p[0], y = p[1], z = p[2];
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+            mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            if (mn[d] <= mx[d]) { atomicMin(&bb[d], float_flip(mn[d])); atomicMax(&bb[3 + d], float_flip(mx[d])); }
+}
+
+struct VoxelGeom { float inv[3]; int min_b[3]; int mul[3]; uint32_t invalid_key; };
+
+__global__ void __launch_bounds__(256) k_vx_key(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, VoxelGeom g,
+                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, int32_t* __restrict__ vop) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    const float x = p[0], y = p[1], z = p[2];
+    uint32_t key = g.invalid_key;
+    int32_t v = -1;
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+        int i0 = (int)(floorf(x * g.inv[0]) - (float)g.min_b[0]);
+        int i1 = (int)(floorf(y * g.inv[1]) - (float)g.min_b[1]);
+        int i2 = (int)(floorf(z * g.inv[2]) - (float)g.min_b[2]);
+        v = i0 * g.mul[0] + i1 * g.mul[1] + i2 * g.mul[2];
+        key = (uint32_t)v;
+    }
+    keys[i] = key; vals[i] = i;
+    if (vop) vop[i] = v;
+}
+
+// flags[i] = 1 where a new voxel run starts (invalid keys never start a run); flags[n] = 0
+__global__ void __launch_bounds__(256) k_vx_heads(const uint32_t* __restrict__ keys, uint32_t n, uint32_t invalid_key, uint32_t* __restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t f = 0;
+    if (i < n) { uint32_t k = keys[i]; f = (k != invalid_key) && (i == 0 || keys[i - 1] != k); }
+    flags[i] = f;
+}
+
+// after the scan: segid[i] = run index of element i (meaningful at heads), segid[n] = number of runs.
+// seg_start[run] = first element of the run; seg_start[nruns] = end of the valid (finite) elements.
+__global__ void __launch_bounds__(256) k_vx_seg_start(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ segid, uint32_t n,
+                                                      uint32_t invalid_key, uint32_t* __restrict__ seg_start) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { if (keys[n - 1] != invalid_key) seg_start[segid[n]] = n; return; }
+    const uint32_t k = keys[i];
+    const bool head = (i == 0) || (keys[i - 1] != k);
+    if (!head) return;
+    if (k == invalid_key) seg_start[segid[n]] = i;
+    else seg_start[segid[i]] = i;
+}
+
+// keep[s] = 1 when run s holds at least min_pts points (setMinimumPointsNumberPerVoxel); zero past the last run
+__global__ void __launch_bounds__(256) k_vx_keep(const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p, uint32_t n,
+                                                 uint32_t min_pts, uint32_t* __restrict__ keep) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n) return;
+    uint32_t f = 0;
+    if (s < *nseg_p) f = (seg_start[s + 1] - seg_start[s]) >= min_pts ? 1u : 0u;
+    keep[s] = f;
+}
+
+// one thread per voxel: float sums in ascending input index, then the mean, written as a full output record
+__global__ void __launch_bounds__(128) k_vx_centroid(const unsigned char* __restrict__ raw, size_t stride, int ioff, int n_fields,
+                                                     const uint32_t* __restrict__ order, const uint32_t* __restrict__ keys,
+                                                     const uint32_t* __restrict__ seg_start, const uint32_t* __restrict__ nseg_p,
+                                                     const uint32_t* __restrict__ keep_scan, uint32_t n, uint32_t out_cap,
+                                                     unsigned char* __restrict__ out, size_t ostride, int ooff, int32_t* __restrict__ out_key) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n || s >= *nseg_p) return;
+    const uint32_t rank = keep_scan[s];
+    if (keep_scan[s + 1] == rank || rank >= out_cap) return;
+    const uint32_t b = seg_start[s], e = seg_start[s + 1];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    for (uint32_t i = b; i < e; i++) {
+        const unsigned char* p = raw + (size_t)order[i] * stride;
+        const float* f = reinterpret_cast<const float*>(p);
+        sx += f[0]; sy += f[1]; sz += f[2];
+        if (n_fields == 4) si += *reinterpret_cast<const float*>(p + ioff);
+    }
+    const float cnt = (float)(e - b);
+    float* of = reinterpret_cast<float*>(out + (size_t)rank * ostride);
+    const int words = (int)(ostride >> 2);
+    for (int w = 3; w < words; w++) of[w] = 0.f;
+    of[0] = sx / cnt; of[1] = sy / cnt; of[2] = sz / cnt;
+    if (words >= 4 && !(n_fields == 4 && ooff == 12)) of[3] = 1.0f;          // PCL's homogeneous pad word
+    if (n_fields == 4) of[ooff >> 2] = si / cnt;
+    if (out_key) out_key[rank] = (int32_t)keys[b];
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_voxel_s {
+    float leaf[3] = {0.f, 0.f, 0.f};
+    unsigned min_pts = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf raw, work, out, small;
+    PinBuf pin;
+};
+
+extern "C" {
+
+int b2_voxel_create(b2_voxel_t* out) {
+    if (!out) { set_error("b2_voxel_create: null out"); return B2_ERR_ARG; }
+    b2_voxel_s* h = new b2_voxel_s();
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("b2_voxel_create: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
+    *out = h;
+    return B2_OK;
+}
+
+int b2_voxel_destroy(b2_voxel_t h) {
+    if (!h) return B2_ERR_ARG;
+    h->raw.release(); h->work.release(); h->out.release(); h->small.release(); h->pin.release();
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B2_OK;
+}
+
+int b2_voxel_set_leaf_size(b2_voxel_t h, float lx, float ly, float lz) {
+    if (!h || !(lx > 0.f) || !(ly > 0.f) || !(lz > 0.f)) { set_error("b2_voxel_set_leaf_size: leaf must be > 0"); return B2_ERR_ARG; }
+    h->leaf[0] = lx; h->leaf[1] = ly; h->leaf[2] = lz;
+    return B2_OK;
+}
+
+int b2_voxel_set_min_points_per_voxel(b2_voxel_t h, unsigned min_points) {
+    if (!h) return B2_ERR_ARG;
+    h->min_pts = min_points;
+    return B2_OK;
+}
+
+int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, int n_fields, void* out, size_t out_stride,
+                    size_t out_capacity, size_t* n_out, int* refused, int32_t* voxel_of_point) {
+    if (!h || !n_out || (n && (!in || !out)) || (n_fields != 3 && n_fields != 4) || in_stride < (size_t)(n_fields * 4) ||
+        out_stride < (size_t)(n_fields * 4) || (in_stride & 3) || (out_stride & 3) || n > 0x7ffffff0ull) {
+        set_error("b2_voxel_filter: bad argument"); return B2_ERR_ARG;
+    }
+    if (!(h->leaf[0] > 0.f)) { set_error("b2_voxel_filter: leaf size not set"); return B2_ERR_STATE; }
+    *n_out = 0;
+    if (refused) *refused = 0;
+    if (n == 0) return B2_OK;                       // PCL: empty input -> empty output
+    cudaStream_t s = h->stream;
+    const int ioff = (int)B2_INTENSITY_OFFSET(in_stride), ooff = (int)B2_INTENSITY_OFFSET(out_stride);
+    B2_CHECK(h->raw.reserve(n * in_stride));
+    B2_CUDA(cudaMemcpyAsync(h->raw.p, in, n * in_stride, cudaMemcpyHostToDevice, s));
+    B2_CHECK(h->small.reserve(256));
+    uint32_t* bb = h->small.as<uint32_t>();
+    k_vx_bbox_init<<<1, 32, 0, s>>>(bb); count_launch();
+    const int nbb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 8);
+    k_vx_bbox<<<nbb, 256, 0, s>>>(h->raw.as<unsigned char>(), in_stride, n, bb); count_launch();
+    B2_CUDA(cudaGetLastError());
+    uint32_t hbb[6];
+    B2_CUDA(cudaMemcpyAsync(hbb, bb, sizeof(hbb), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    auto unflip = [](uint32_t u) { uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
+    float mn[3], mx[3];
+    for (int d = 0; d < 3; d++) { mn[d] = unflip(hbb[d]); mx[d] = unflip(hbb[3 + d]); }
+    if (!(mn[0] <= mx[0])) return B2_OK;            // no finite point at all
+    // PCL applyFilter arithmetic on the host, in float exactly as written there
+    VoxelGeom g;
+    int64_t dxyz[3];
+    int max_b[3], div_b[3];
+    for (int d = 0; d < 3; d++) {
+        g.inv[d] = 1.0f / h->leaf[d];
+        dxyz[d] = (int64_t)((mx[d] - mn[d]) * g.inv[d]) + 1;
+    }
+    if (dxyz[0] * dxyz[1] * dxyz[2] > (int64_t)INT32_MAX) {
+        // "Leaf size is too small for the input dataset": output = input
+        if (refused) *refused = 1;
+        if (out_capacity < n) { set_error("b2_voxel_filter: refused (index overflow) and out_capacity < n"); return B2_ERR_CAPACITY; }
+        const unsigned char* src = static_cast<const unsigned char*>(in);
+        unsigned char* dst = static_cast<unsigned char*>(out);
+        if (in_stride == out_stride) memcpy(dst, src, n * in_stride);
+        else for (size_t i = 0; i < n; i++) {
+            memcpy(dst + i * out_stride, src + i * in_stride, 12);
+            if (n_fields == 4) memcpy(dst + i * out_stride + ooff, src + i * in_stride + ioff, 4);
+        }
+        if (voxel_of_point) for (size_t i = 0; i < n; i++) voxel_of_point[i] = -1;
+        *n_out = n;
+        return B2_OK;
+    }
+    uint64_t ncells = 1;
+    for (int d = 0; d < 3; d++) {
+        g.min_b[d] = (int)std::floor(mn[d] * g.inv[d]);
+        max_b[d] = (int)std::floor(mx[d] * g.inv[d]);
+        div_b[d] = max_b[d] - g.min_b[d] + 1;
+        ncells *= (uint64_t)div_b[d];
+    }
+    g.mul[0] = 1; g.mul[1] = div_b[0]; g.mul[2] = div_b[0] * div_b[1];
+    if (ncells > 0xfffffffeull) ncells = 0xfffffffeull;
+    g.invalid_key = (uint32_t)ncells;               // sorts after every real voxel
+    int bits = 1;
+    while (bits < 32 && ((uint64_t)1 << bits) <= ncells) bits++;
+
+    const size_t nal = (n + 64) & ~(size_t)63;       // room for n+1 entries
+    const size_t scratch_bytes = std::max(sort_tmp_bytes(n), scan_tmp_bytes(n + 1)) + 1024;
+    B2_CHECK(h->work.reserve(7 * nal * sizeof(uint32_t) + scratch_bytes + (voxel_of_point ? nal * sizeof(int32_t) : 0)));
+    uint32_t* ka = h->work.as<uint32_t>();
+    uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
+    uint32_t* segid = vb + nal; uint32_t* seg_start = segid + nal; uint32_t* keep = seg_start + nal;
+    char* scratch = reinterpret_cast<char*>(keep + nal);
+    int32_t* d_vop = voxel_of_point ? reinterpret_cast<int32_t*>(scratch + scratch_bytes) : nullptr;
+    const uint32_t n32 = (uint32_t)n;
+    const unsigned nblk = (unsigned)((n + 255) / 256), nblk1 = (unsigned)((n + 1 + 255) / 256);
+    k_vx_key<<<nblk, 256, 0, s>>>(h->raw.as<unsigned char>(), in_stride, n32, g, ka, va, d_vop); count_launch();
+    B2_CUDA(cudaGetLastError());
+    uint32_t *ks, *vs;
+    B2_CHECK(radix_sort_pairs(ka, va, kb, vb, n, bits, scratch, s, &ks, &vs));
+    k_vx_heads<<<nblk1, 256, 0, s>>>(ks, n32, g.invalid_key, segid); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CHECK(exclusive_scan_u32(segid, n + 1, scratch, s));
+    k_vx_seg_start<<<nblk1, 256, 0, s>>>(ks, segid, n32, g.invalid_key, seg_start); count_launch();
+    k_vx_keep<<<nblk1, 256, 0, s>>>(seg_start, segid + n, n32, h->min_pts, keep); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CHECK(exclusive_scan_u32(keep, n + 1, scratch, s));
+    const size_t cap = std::min(n, out_capacity);
+    B2_CHECK(h->out.reserve(std::max<size_t>(cap, 1) * out_stride));
+    k_vx_centroid<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(h->raw.as<unsigned char>(), in_stride, ioff, n_fields, vs, ks, seg_start, segid + n,
+                                                              keep, n32, (uint32_t)cap, h->out.as<unsigned char>(), out_stride, ooff, nullptr); count_launch();
+    B2_CUDA(cudaGetLastError());
+    uint32_t m = 0;
+    B2_CUDA(cudaMemcpyAsync(&m, keep + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (voxel_of_point) B2_CUDA(cudaMemcpyAsync(voxel_of_point, d_vop, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    if ((size_t)m > out_capacity) { set_error("b2_voxel_filter: %u voxels but out_capacity %zu", m, out_capacity); return B2_ERR_CAPACITY; }
+    if (m) B2_CUDA(cudaMemcpyAsync(out, h->out.p, (size_t)m * out_stride, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    *n_out = m;
+    return B2_OK;
+}
+
+}  // extern "C"

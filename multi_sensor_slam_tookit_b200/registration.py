@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's interfaces for the scan-registration path, on top of the C ABI.
+
+Class and method names follow the seams listed in SURVEY.md §8b so call sites read like the reference:
+  VoxelGrid           <- pcl::VoxelGrid<PointT>            (featureExtraction.cpp:233-234, mapOptmization.cpp:955-967, ...)
+  KdTreeFLANN         <- pcl::KdTreeFLANN<PointType>       (mapOptmization.cpp:1289-1290, :987, :1079), batched
+  ScanToMapOptimizer  <- mapOptimization::{cornerOptimization, surfOptimization, combineOptimizationCoeffs,
+                         LMOptimization, scan2MapOptimization}  (mapOptmization.cpp:974-1310)
+Clouds are numpy float32 arrays, (n, 4) packed x,y,z,intensity or (n, 8) in PCL's 32-byte PointXYZI layout.
+Everything computes on the GPU through libb2reg.so; there is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class VoxelGrid:
+    def __init__(self):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2_voxel_create(C.byref(self._h)))
+        self._cloud = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b2_voxel_destroy(self._h)
+        except Exception:
+            pass
+
+    def setLeafSize(self, lx, ly, lz):
+        capi.check(capi.lib().b2_voxel_set_leaf_size(self._h, lx, ly, lz))
+
+    def setMinimumPointsNumberPerVoxel(self, n):
+        capi.check(capi.lib().b2_voxel_set_min_points_per_voxel(self._h, int(n)))
+
+    def setInputCloud(self, cloud):
+        self._cloud = cloud
+
+    def filter(self, return_voxel_index=False):
+        """Returns the downsampled cloud (same column layout as the input). PCL semantics: empty in -> empty out;
+        index overflow -> the input is returned unchanged (self.refused = True)."""
+        if self._cloud is None:
+            raise RuntimeError("VoxelGrid.filter: no input cloud")
+        pts, stride = capi.as_points(self._cloud)
+        n, cols = pts.shape
+        n_fields = 3 if cols == 3 else 4
+        out = np.zeros((max(n, 1), cols), np.float32)
+        n_out = C.c_size_t(0)
+        refused = C.c_int(0)
+        vop = np.empty(max(n, 1), np.int32) if return_voxel_index else None
+        capi.check(capi.lib().b2_voxel_filter(self._h, capi.ptr(pts), stride, n, n_fields, capi.ptr(out), out.strides[0],
+                                              out.shape[0], C.byref(n_out), C.byref(refused), capi.ptr(vop)))
+        self.refused = bool(refused.value)
+        res = out[:n_out.value].copy()
+        return (res, vop[:n]) if return_voxel_index else res
+
+
+class KdTreeFLANN:
+    """Batched drop-in for the kd-tree queries of the LM loop. Exact for neighbours closer than max_dist."""
+
+    def __init__(self, max_dist=1.0):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2_knn_create(C.byref(self._h), max_dist))
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b2_knn_destroy(self._h)
+        except Exception:
+            pass
+
+    def setInputCloud(self, cloud):
+        pts, stride = capi.as_points(cloud)
+        self._keep = pts
+        capi.check(capi.lib().b2_knn_set_input_cloud(self._h, capi.ptr(pts), stride, pts.shape[0]))
+
+    def nearestKSearch(self, queries, k):
+        """queries (m, >=3) -> (indices (m,k) int32, sq_dists (m,k) float32), ascending (distance, index)."""
+        q, stride = capi.as_points(queries)
+        m = q.shape[0]
+        idx = np.empty((m, k), np.int32)
+        d2 = np.empty((m, k), np.float32)
+        capi.check(capi.lib().b2_knn_nearest_k_search(self._h, capi.ptr(q), stride, m, k, capi.ptr(idx), capi.ptr(d2)))
+        return idx, d2
+
+
+class ScanToMapOptimizer:
+    """Members named after the reference's: transformTobeMapped, isDegenerate, matP, laserCloud*DS."""
+
+    def __init__(self, max_batch=1, **overrides):
+        L = capi.lib()
+        self.params = capi.S2MParams()
+        L.b2_s2m_default_params(C.byref(self.params))
+        self.params.max_batch = max_batch
+        for k, v in overrides.items():
+            setattr(self.params, k, v)
+        self._h = C.c_void_p()
+        capi.check(L.b2_s2m_create(C.byref(self._h), C.byref(self.params)))
+        self.transformTobeMapped = np.zeros(6, np.float32)
+        self.isDegenerate = False
+        self.matP = np.zeros((6, 6), np.float32)
+        self._nc = self._ns = 0
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b2_s2m_destroy(self._h)
+        except Exception:
+            pass
+
+    # kdtreeCornerFromMap->setInputCloud(laserCloudCornerFromMapDS); kdtreeSurfFromMap->setInputCloud(...)
+    def setInputMap(self, laserCloudCornerFromMapDS, laserCloudSurfFromMapDS):
+        c, cs = capi.as_points(laserCloudCornerFromMapDS)
+        s, ss = capi.as_points(laserCloudSurfFromMapDS)
+        capi.check(capi.lib().b2_s2m_set_map(self._h, capi.ptr(c), cs, c.shape[0], capi.ptr(s), ss, s.shape[0]))
+
+    def setInputScan(self, laserCloudCornerLastDS, laserCloudSurfLastDS):
+        c, cs = capi.as_points(laserCloudCornerLastDS, 4)
+        s, ss = capi.as_points(laserCloudSurfLastDS, 4)
+        self._nc, self._ns = c.shape[0], s.shape[0]
+        capi.check(capi.lib().b2_s2m_set_scan(self._h, capi.ptr(c), cs, c.shape[0], capi.ptr(s), ss, s.shape[0]))
+
+    def setInputScanBatch(self, corners, surfs):
+        """corners / surfs: lists of (n_i, 4) clouds, one per scan."""
+        co = np.zeros(len(corners) + 1, np.int32)
+        so = np.zeros(len(surfs) + 1, np.int32)
+        co[1:] = np.cumsum([len(c) for c in corners])
+        so[1:] = np.cumsum([len(s) for s in surfs])
+        c = np.ascontiguousarray(np.concatenate(corners), np.float32) if co[-1] else np.zeros((0, 4), np.float32)
+        s = np.ascontiguousarray(np.concatenate(surfs), np.float32) if so[-1] else np.zeros((0, 4), np.float32)
+        self._batch = len(corners)
+        capi.check(capi.lib().b2_s2m_set_scan_batch(self._h, len(corners), capi.ptr(c), 16, capi.ptr(co), capi.ptr(s), 16, capi.ptr(so)))
+
+    def setState(self, isDegenerate, matP=None):
+        m = None if matP is None else np.ascontiguousarray(matP, np.float32).reshape(36)
+        capi.check(capi.lib().b2_s2m_set_state(self._h, int(isDegenerate), capi.ptr(m)))
+
+    def LMIteration(self, iterCount):
+        """cornerOptimization + surfOptimization + combineOptimizationCoeffs + LMOptimization(iterCount).
+        Returns the bool LMOptimization returns; updates transformTobeMapped / isDegenerate / matP in place."""
+        pose = np.ascontiguousarray(self.transformTobeMapped, np.float32)
+        n_sel, ran, conv, deg = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        matP = np.zeros(36, np.float32)
+        capi.check(capi.lib().b2_s2m_iterate(self._h, capi.ptr(pose), iterCount, C.byref(n_sel), C.byref(ran), C.byref(conv),
+                                             C.byref(deg), capi.ptr(matP)))
+        self.transformTobeMapped = pose
+        self.laserCloudSelNum = n_sel.value
+        self.ran = bool(ran.value)
+        self.isDegenerate = bool(deg.value)
+        self.matP = matP.reshape(6, 6)
+        return bool(conv.value)
+
+    def scan2MapOptimization(self, max_iterations=30, record_history=False):
+        """The whole loop on the device. Returns dict(iters, converged, not_enough, pose_history)."""
+        pose = np.ascontiguousarray(self.transformTobeMapped, np.float32)
+        it, conv, deg, ne = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        matP = np.zeros(36, np.float32)
+        hist = np.zeros((max_iterations, 6), np.float32) if record_history else None
+        capi.check(capi.lib().b2_s2m_solve(self._h, capi.ptr(pose), max_iterations, C.byref(it), C.byref(conv), C.byref(deg),
+                                           capi.ptr(matP), C.byref(ne), capi.ptr(hist)))
+        self.transformTobeMapped = pose
+        if not ne.value:
+            self.isDegenerate = bool(deg.value)
+            self.matP = matP.reshape(6, 6)
+        return dict(iters=it.value, converged=bool(conv.value), not_enough=bool(ne.value),
+                    pose_history=None if hist is None else hist[:it.value])
+
+    def scan2MapOptimizationBatch(self, poses, max_iterations=30):
+        poses = np.ascontiguousarray(poses, np.float32).reshape(-1, 6).copy()
+        B = poses.shape[0]
+        it = np.zeros(B, np.int32)
+        conv = np.zeros(B, np.int32)
+        deg = np.zeros(B, np.int32)
+        capi.check(capi.lib().b2_s2m_solve_batch(self._h, capi.ptr(poses), max_iterations, capi.ptr(it), capi.ptr(conv), capi.ptr(deg)))
+        return dict(poses=poses, iters=it, converged=conv.astype(bool), degenerate=deg.astype(bool))
+
+    def lastGpuMs(self):
+        ms, n = C.c_float(0), C.c_int(0)
+        capi.check(capi.lib().b2_s2m_last_gpu_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def getPass(self, which):
+        n = self._ns if which else self._nc
+        idx = np.empty((n, 5), np.int32)
+        d2 = np.empty((n, 5), np.float32)
+        coeff = np.empty((n, 4), np.float32)
+        flag = np.empty(n, np.uint8)
+        capi.check(capi.lib().b2_s2m_get_pass(self._h, which, capi.ptr(idx), capi.ptr(d2), capi.ptr(coeff), capi.ptr(flag)))
+        return dict(idx=idx, d2=d2, coeff=coeff, flag=flag)
+
+    def getNormalEquations(self):
+        AtA, AtB, X = np.zeros(36, np.float32), np.zeros(6, np.float32), np.zeros(6, np.float32)
+        capi.check(capi.lib().b2_s2m_get_normal_equations(self._h, capi.ptr(AtA), capi.ptr(AtB), capi.ptr(X)))
+        return AtA.reshape(6, 6), AtB, X
+
+
+def transformPointCloud(cloud, transformIn):
+    """mapOptimization::transformPointCloud (mapOptmization.cpp:286-305); transformIn = (roll,pitch,yaw,x,y,z)."""
+    pts, stride = capi.as_points(cloud, 4)
+    out = np.zeros_like(pts)
+    pose = np.ascontiguousarray(transformIn, np.float32)
+    capi.check(capi.lib().b2_transform_cloud(capi.ptr(pts), stride, pts.shape[0], capi.ptr(pose), capi.ptr(out), out.strides[0]))
+    return out

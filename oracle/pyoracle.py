@@ -1,0 +1,249 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.
+
+ctypes bindings to oracle/liboracle.so (the CPU restatement of the reference hot path).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module; the product package never does.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def _opt(ptr_type):
+    """ndpointer that also accepts None."""
+    base = ptr_type
+
+    class _P(base):
+        @classmethod
+        def from_param(cls, obj):
+            if obj is None:
+                return None
+            return base.from_param(obj)
+    return _P
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = os.path.join(_HERE, "liboracle.so")
+    if not os.path.exists(so):
+        build()
+    L = C.CDLL(so)
+    of32, oi32, ou8 = _opt(f32p), _opt(i32p), _opt(u8p)
+    L.o_voxel_grid.restype = C.c_int
+    L.o_voxel_grid.argtypes = [f32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint, f32p, oi32,
+                               C.POINTER(C.c_int), oi32]
+    L.o_s2m_create.restype = C.c_void_p
+    L.o_s2m_create.argtypes = [C.c_int]
+    L.o_s2m_destroy.argtypes = [C.c_void_p]
+    L.o_s2m_set_map.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
+    L.o_s2m_set_scan.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int]
+    L.o_s2m_set_state.argtypes = [C.c_void_p, C.c_int, of32]
+    L.o_s2m_get_state.argtypes = [C.c_void_p, C.POINTER(C.c_int), of32]
+    L.o_s2m_iterate.restype = C.c_int
+    L.o_s2m_iterate.argtypes = [C.c_void_p, f32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), of32, of32, of32]
+    L.o_s2m_get_pass.argtypes = [C.c_void_p, C.c_int, oi32, of32, of32, ou8]
+    L.o_s2m_solve.restype = C.c_int
+    L.o_s2m_solve.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                              of32, oi32]
+    for name in ("o_knn", "o_knn_brute"):
+        fn = getattr(L, name)
+        fn.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, i32p, f32p, C.c_int]
+    L.o_transform_cloud.argtypes = [f32p, C.c_int, f32p, f32p, C.c_int]
+    L.o_eigen3.argtypes = [f32p, f32p, f32p]
+    L.o_eigen6.argtypes = [f32p, f32p, f32p]
+    L.o_qr_solve6.restype = C.c_int
+    L.o_qr_solve6.argtypes = [f32p, f32p, f32p]
+    L.o_lu_invert6.restype = C.c_int
+    L.o_lu_invert6.argtypes = [f32p, f32p]
+    L.o_plane5.argtypes = [f32p, f32p]
+    L.o_pose_affine.argtypes = [f32p, f32p]
+    L.o_project.restype = C.c_int
+    L.o_project.argtypes = [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                            f64p, f64p, f64p, f64p, C.c_int, C.c_double, C.c_int,
+                            f32p, f32p, i32p, f32p, i32p, f32p, i32p, i32p]
+    L.o_curvature_masks.argtypes = [f32p, i32p, C.c_int, f32p, i32p, i32p]
+    L.o_extract_features.restype = C.c_int
+    L.o_extract_features.argtypes = [f32p, i32p, C.c_int, i32p, i32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
+                                     f32p, i32p, i32p, i32p, i32p, i32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    _LIB = L
+    return L
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+# ---------------------------------------------------------------- voxel grid
+def voxel_grid(pts_xyzi, leaf, min_points=0):
+    """pcl::VoxelGrid restatement. Returns dict(out, voxel_of_point, out_voxel_idx, refused)."""
+    L = lib()
+    p = _f32(pts_xyzi).reshape(-1, 4)
+    n = p.shape[0]
+    leaf3 = (leaf, leaf, leaf) if np.isscalar(leaf) else tuple(leaf)
+    out = np.empty((max(n, 1), 4), np.float32)
+    vop = np.empty(max(n, 1), np.int32)
+    ovi = np.empty(max(n, 1), np.int32)
+    refused = C.c_int(0)
+    m = L.o_voxel_grid(p, n, leaf3[0], leaf3[1], leaf3[2], min_points, out, vop, C.byref(refused), ovi)
+    return dict(out=out[:m].copy(), voxel_of_point=vop[:n].copy(), out_voxel_idx=ovi[:m].copy(), refused=bool(refused.value))
+
+
+# ---------------------------------------------------------------- scan-to-map
+class Scan2Map:
+    def __init__(self, threads=1):
+        self.L = lib()
+        self.h = self.L.o_s2m_create(threads)
+        self.nc = self.ns = 0
+
+    def __del__(self):
+        try:
+            self.L.o_s2m_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_map(self, corner, surf):
+        c, s = _f32(corner).reshape(-1, 4), _f32(surf).reshape(-1, 4)
+        self.L.o_s2m_set_map(self.h, c, len(c), s, len(s))
+
+    def set_scan(self, corner, surf):
+        c, s = _f32(corner).reshape(-1, 4), _f32(surf).reshape(-1, 4)
+        self.nc, self.ns = len(c), len(s)
+        self.L.o_s2m_set_scan(self.h, c, len(c), s, len(s))
+
+    def set_state(self, degenerate, matP=None):
+        self.L.o_s2m_set_state(self.h, int(degenerate), None if matP is None else _f32(matP).reshape(36))
+
+    def get_state(self):
+        d = C.c_int(0)
+        P = np.zeros(36, np.float32)
+        self.L.o_s2m_get_state(self.h, C.byref(d), P)
+        return bool(d.value), P.reshape(6, 6)
+
+    def iterate(self, pose, it):
+        pose = _f32(pose).copy()
+        nsel, ran = C.c_int(0), C.c_int(0)
+        AtA, AtB, X = np.zeros(36, np.float32), np.zeros(6, np.float32), np.zeros(6, np.float32)
+        conv = self.L.o_s2m_iterate(self.h, pose, it, C.byref(nsel), C.byref(ran), AtA, AtB, X)
+        return dict(pose=pose, converged=bool(conv), n_sel=nsel.value, ran=bool(ran.value),
+                    AtA=AtA.reshape(6, 6), AtB=AtB, X=X)
+
+    def get_pass(self, which):
+        n = self.ns if which else self.nc
+        idx = np.empty((n, 5), np.int32)
+        d2 = np.empty((n, 5), np.float32)
+        coeff = np.empty((n, 4), np.float32)
+        flag = np.empty(n, np.uint8)
+        self.L.o_s2m_get_pass(self.h, which, idx, d2, coeff, flag)
+        return dict(idx=idx, d2=d2, coeff=coeff, flag=flag)
+
+    def solve(self, pose, max_iters=30, edge_min=10, surf_min=100):
+        pose = _f32(pose).copy()
+        it, conv = C.c_int(0), C.c_int(0)
+        hist = np.zeros((max_iters, 6), np.float32)
+        nsel = np.zeros(max_iters, np.int32)
+        rc = self.L.o_s2m_solve(self.h, pose, max_iters, edge_min, surf_min, C.byref(it), C.byref(conv), hist, nsel)
+        return dict(rc=rc, pose=pose, iters=it.value, converged=bool(conv.value), pose_hist=hist[:it.value],
+                    nsel_hist=nsel[:it.value])
+
+
+def knn(pts, queries, k, brute=False, threads=8):
+    L = lib()
+    p, q = _f32(pts).reshape(-1, 4), _f32(queries).reshape(-1, 4)
+    idx = np.empty((len(q), k), np.int32)
+    d2 = np.empty((len(q), k), np.float32)
+    (L.o_knn_brute if brute else L.o_knn)(p, len(p), q, len(q), k, idx, d2, threads)
+    return idx, d2
+
+
+def transform_cloud(pts, pose, threads=1):
+    L = lib()
+    p = _f32(pts).reshape(-1, 4)
+    out = np.empty_like(p)
+    L.o_transform_cloud(p, len(p), _f32(pose), out, threads)
+    return out
+
+
+def pose_affine(pose):
+    t = np.zeros(12, np.float32)
+    lib().o_pose_affine(_f32(pose), t)
+    return t.reshape(3, 4)
+
+
+# ---------------------------------------------------------------- front end
+def project(raw_xyzirt, N_SCAN, H, imu=None, t_cur=0.0, downsample=1, rmin=1.0, rmax=1000.0, deskew=True):
+    """raw_xyzirt: structured/byte array of n*32 bytes. imu: (time, rx, ry, rz) float64 arrays or None."""
+    L = lib()
+    raw = np.ascontiguousarray(raw_xyzirt).view(np.uint8).reshape(-1)
+    n = raw.size // 32
+    cells = N_SCAN * H
+    if imu is None:
+        z = np.zeros(1, np.float64)
+        imu = (z, z, z, z)
+        n_imu = 0
+    else:
+        imu = tuple(np.ascontiguousarray(a, np.float64) for a in imu)
+        n_imu = len(imu[0])
+    rm = np.empty(cells, np.float32)
+    fc = np.empty((cells, 4), np.float32)
+    win = np.empty(cells, np.int32)
+    ext = np.empty((cells, 4), np.float32)
+    col = np.empty(cells, np.int32)
+    rng = np.empty(cells, np.float32)
+    sr = np.empty(N_SCAN, np.int32)
+    er = np.empty(N_SCAN, np.int32)
+    m = L.o_project(raw, n, N_SCAN, H, downsample, rmin, rmax, imu[0], imu[1], imu[2], imu[3], n_imu, t_cur,
+                    1 if deskew else -1, rm, fc, win, ext, col, rng, sr, er)
+    return dict(range_mat=rm.reshape(N_SCAN, H), full_cloud=fc, winner=win.reshape(N_SCAN, H), extracted=ext[:m].copy(),
+                pointColInd=col[:m].copy(), pointRange=rng[:m].copy(), startRingIndex=sr, endRingIndex=er)
+
+
+def curvature_masks(pointRange, pointColInd):
+    L = lib()
+    r = _f32(pointRange)
+    c = np.ascontiguousarray(pointColInd, np.int32)
+    n = len(r)
+    curv = np.empty(n, np.float32)
+    picked = np.empty(n, np.int32)
+    label = np.empty(n, np.int32)
+    L.o_curvature_masks(r, c, n, curv, picked, label)
+    return curv, picked, label
+
+
+def extract_features(proj, edge_th=1.0, surf_th=0.1, surf_leaf=0.4, stable=True):
+    """proj: dict from project(). Returns corner/surf clouds and the intermediate arrays."""
+    L = lib()
+    ext = proj["extracted"]
+    n = len(ext)
+    N_SCAN = len(proj["startRingIndex"])
+    curv, picked, label = curvature_masks(proj["pointRange"], proj["pointColInd"])
+    picked_after_mask = picked.copy()
+    cidx = np.empty(N_SCAN * 6 * 20 + 1, np.int32)
+    sidx = np.empty(max(n, 1), np.int32)
+    srs = np.empty(N_SCAN + 1, np.int32)
+    sds = np.empty((max(n, 1), 4), np.float32)
+    ns, nds = C.c_int(0), C.c_int(0)
+    nc = L.o_extract_features(np.ascontiguousarray(ext), proj["pointColInd"], n, proj["startRingIndex"], proj["endRingIndex"],
+                              N_SCAN, edge_th, surf_th, surf_leaf, 1 if stable else 0, curv, picked, label,
+                              cidx, sidx, srs, sds, C.byref(ns), C.byref(nds))
+    return dict(curvature=curv, picked_mask=picked_after_mask, picked=picked, label=label,
+                corner_idx=cidx[:nc].copy(), corner=ext[cidx[:nc]].copy(), surf_idx=sidx[:ns.value].copy(),
+                surf_ring_start=srs, surf=sds[:nds.value].copy())

@@ -1,0 +1,157 @@
+"""GPU parity (through the C ABI) for the scan-to-map LM step against the CPU oracle on the C1 workload.
+
+Bars (north_star):
+  kNN index sets / squared distances: bit-exact wherever sqDis[4] < 1.0
+  accept/reject flags: equal; coeff <= 1e-5 absolute
+  normal equations <= 1e-6 relative; per-iteration pose update <= 1e-5 m / 1e-6 rad; same iteration count
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL_M, TOL_RAD = 1e-5, 1e-6
+
+
+def _pair(b2, oracle, c1, threads=4):
+    from multi_sensor_slam_tookit_b200.registration import ScanToMapOptimizer
+    g = ScanToMapOptimizer()
+    g.setInputMap(c1["map_corner"], c1["map_surf"])
+    g.setInputScan(c1["scan_corner"], c1["scan_surf"])
+    o = oracle.Scan2Map(threads)
+    o.set_map(c1["map_corner"], c1["map_surf"])
+    o.set_scan(c1["scan_corner"], c1["scan_surf"])
+    return g, o
+
+
+def test_single_iteration_parity(b2, oracle, c1):
+    g, o = _pair(b2, oracle, c1)
+    g.transformTobeMapped = c1["pose_guess"].copy()
+    conv = g.LMIteration(0)
+    r = o.iterate(c1["pose_guess"], 0)
+    for which in (0, 1):
+        gp, op = g.getPass(which), o.get_pass(which)
+        near = op["d2"][:, 4] < 1.0
+        assert near.mean() > 0.5
+        assert np.array_equal(gp["idx"][near], op["idx"][near]), "5-NN index sets differ"
+        assert np.array_equal(gp["d2"][near], op["d2"][near]), "squared distances differ"
+        assert np.array_equal(gp["flag"], op["flag"]), "accept/reject flags differ"
+        kept = op["flag"] != 0
+        assert kept.sum() > 50
+        assert np.max(np.abs(gp["coeff"][kept] - op["coeff"][kept])) <= 1e-5
+    assert g.laserCloudSelNum == r["n_sel"] and g.ran == r["ran"] and conv == r["converged"]
+    AtA, AtB, X = g.getNormalEquations()
+    assert np.max(np.abs(AtA - r["AtA"]) / np.abs(r["AtA"]).max()) <= 1e-6
+    assert np.max(np.abs(AtB - r["AtB"]) / np.abs(r["AtB"]).max()) <= 1e-6
+    assert np.all(np.abs(g.transformTobeMapped[3:] - r["pose"][3:]) <= TOL_M)
+    assert np.all(np.abs(g.transformTobeMapped[:3] - r["pose"][:3]) <= TOL_RAD)
+    assert g.isDegenerate == o.get_state()[0]
+    assert np.allclose(g.matP, o.get_state()[1], atol=1e-5)
+
+
+def test_host_driven_loop_matches_oracle_every_iteration(b2, oracle, c1):
+    g, o = _pair(b2, oracle, c1)
+    g.transformTobeMapped = c1["pose_guess"].copy()
+    pose_o = c1["pose_guess"].copy()
+    for it in range(30):
+        cg = g.LMIteration(it)
+        r = o.iterate(pose_o, it)
+        pose_o = r["pose"]
+        assert g.laserCloudSelNum == r["n_sel"]
+        assert np.all(np.abs(g.transformTobeMapped[3:] - pose_o[3:]) <= TOL_M), f"iteration {it}"
+        assert np.all(np.abs(g.transformTobeMapped[:3] - pose_o[:3]) <= TOL_RAD), f"iteration {it}"
+        assert cg == r["converged"]
+        if cg:
+            break
+    assert cg and it >= 1
+
+
+def test_device_driven_solve_matches_oracle(b2, oracle, c1):
+    g, o = _pair(b2, oracle, c1)
+    g.transformTobeMapped = c1["pose_guess"].copy()
+    res = g.scan2MapOptimization(30, record_history=True)
+    ref = o.solve(c1["pose_guess"])
+    assert not res["not_enough"] and res["converged"] == ref["converged"] and res["iters"] == ref["iters"]
+    assert np.all(np.abs(res["pose_history"][:, 3:] - ref["pose_hist"][:, 3:]) <= TOL_M)
+    assert np.all(np.abs(res["pose_history"][:, :3] - ref["pose_hist"][:, :3]) <= TOL_RAD)
+    assert np.all(np.abs(g.transformTobeMapped[3:] - c1["pose_truth"][3:]) < 0.02)
+    ms, launches = g.lastGpuMs()
+    assert ms > 0 and launches == 31
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_solve_from_other_initial_guesses(b2, oracle, c1, seed):
+    rng = np.random.default_rng(seed)
+    g, o = _pair(b2, oracle, c1)
+    guess = c1["pose_truth"].copy()
+    guess[3:] += rng.uniform(-0.25, 0.25, 3).astype(np.float32)
+    guess[:3] += np.deg2rad(rng.uniform(-1.5, 1.5, 3)).astype(np.float32)
+    g.transformTobeMapped = guess.copy()
+    res = g.scan2MapOptimization(30, record_history=True)
+    ref = o.solve(guess)
+    assert res["iters"] == ref["iters"] and res["converged"] == ref["converged"]
+    assert np.all(np.abs(res["pose_history"][:, 3:] - ref["pose_hist"][:, 3:]) <= TOL_M)
+    assert np.all(np.abs(res["pose_history"][:, :3] - ref["pose_hist"][:, :3]) <= TOL_RAD)
+
+
+def test_guards_match_reference(b2, oracle, c1):
+    from multi_sensor_slam_tookit_b200.registration import ScanToMapOptimizer
+    g = ScanToMapOptimizer()
+    g.setInputMap(c1["map_corner"], c1["map_surf"])
+    g.setInputScan(c1["scan_corner"][:10], c1["scan_surf"])            # not more than edgeFeatureMinValidNum
+    g.transformTobeMapped = c1["pose_guess"].copy()
+    res = g.scan2MapOptimization()
+    assert res["not_enough"] and np.array_equal(g.transformTobeMapped, c1["pose_guess"])
+    g.setInputScan(c1["scan_corner"][:11], c1["scan_surf"][:101])      # passes the guard, but < 50 correspondences far away
+    far = c1["pose_guess"].copy(); far[3] += 500
+    g.transformTobeMapped = far.copy()
+    res = g.scan2MapOptimization()
+    assert not res["not_enough"] and not res["converged"] and res["iters"] == 30
+    assert np.array_equal(g.transformTobeMapped, far)
+
+
+def test_degenerate_case_matches_oracle(b2, oracle, c1):
+    # a corridor-like input: only ground-plane surf features -> x/y/yaw unobservable -> isDegenerate, matP projection
+    from multi_sensor_slam_tookit_b200.registration import ScanToMapOptimizer
+    ms = c1["map_surf"][np.abs(c1["map_surf"][:, 2]) < 0.15]
+    ss = c1["scan_surf"][np.abs(c1["scan_surf"][:, 2] + 1.8) < 0.15]
+    mc, sc = c1["map_corner"][:50], c1["scan_corner"][:11]
+    g = ScanToMapOptimizer(); g.setInputMap(mc, ms); g.setInputScan(sc, ss)
+    o = oracle.Scan2Map(2); o.set_map(mc, ms); o.set_scan(sc, ss)
+    g.transformTobeMapped = c1["pose_guess"].copy()
+    g.LMIteration(0)
+    r = o.iterate(c1["pose_guess"], 0)
+    assert r["ran"] and o.get_state()[0], "fixture is expected to be degenerate"
+    assert g.isDegenerate
+    assert np.allclose(g.matP, o.get_state()[1], atol=2e-4)
+    assert np.all(np.abs(g.transformTobeMapped[3:] - r["pose"][3:]) <= 1e-4)
+    assert np.all(np.abs(g.transformTobeMapped[:3] - r["pose"][:3]) <= 1e-5)
+
+
+def test_batched_scans_equal_single_scan_runs(b2, c1):
+    from multi_sensor_slam_tookit_b200.registration import ScanToMapOptimizer
+    rng = np.random.default_rng(9)
+    B = 6
+    poses = np.tile(c1["pose_truth"], (B, 1)).astype(np.float32)
+    poses[:, 3:] += rng.uniform(-0.2, 0.2, (B, 3)).astype(np.float32)
+    poses[:, :3] += np.deg2rad(rng.uniform(-1, 1, (B, 3))).astype(np.float32)
+    corners = [c1["scan_corner"][: len(c1["scan_corner"]) - 7 * b] for b in range(B)]      # ragged
+    surfs = [c1["scan_surf"][: len(c1["scan_surf"]) - 31 * b] for b in range(B)]
+    gb = ScanToMapOptimizer(max_batch=B)
+    gb.setInputMap(c1["map_corner"], c1["map_surf"])
+    gb.setInputScanBatch(corners, surfs)
+    rb = gb.scan2MapOptimizationBatch(poses)
+    for b in range(B):
+        g1 = ScanToMapOptimizer()
+        g1.setInputMap(c1["map_corner"], c1["map_surf"])
+        g1.setInputScan(corners[b], surfs[b])
+        g1.transformTobeMapped = poses[b].copy()
+        r1 = g1.scan2MapOptimization()
+        assert r1["iters"] == rb["iters"][b] and r1["converged"] == rb["converged"][b]
+        assert np.array_equal(g1.transformTobeMapped, rb["poses"][b])      # same kernels, same order: bit-identical
+
+
+def test_transform_point_cloud_bit_exact(b2, oracle, c1):
+    from multi_sensor_slam_tookit_b200.registration import transformPointCloud
+    out = transformPointCloud(c1["scan_surf"], c1["pose_guess"])
+    assert np.array_equal(out, oracle.transform_cloud(c1["scan_surf"], c1["pose_guess"]))
