@@ -93,4 +93,4 @@ def as_points(a, min_cols=3):
     a = np.ascontiguousarray(a, dtype=np.float32)
     if a.ndim != 2 or a.shape[1] < min_cols:
         raise ValueError(f"expected (n, >={min_cols}) float32 points, got {a.shape}")
-    return a, a.strides[0]
+    return a, a.shape[1] * 4          # (numpy reports stride 0 for empty arrays)

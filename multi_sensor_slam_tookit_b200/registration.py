@@ -49,7 +49,7 @@ class VoxelGrid:
         n_out = C.c_size_t(0)
         refused = C.c_int(0)
         vop = np.empty(max(n, 1), np.int32) if return_voxel_index else None
-        capi.check(capi.lib().b2_voxel_filter(self._h, capi.ptr(pts), stride, n, n_fields, capi.ptr(out), out.strides[0],
+        capi.check(capi.lib().b2_voxel_filter(self._h, capi.ptr(pts), stride, n, n_fields, capi.ptr(out), cols * 4,
                                               out.shape[0], C.byref(n_out), C.byref(refused), capi.ptr(vop)))
         self.refused = bool(refused.value)
         res = out[:n_out.value].copy()
@@ -200,5 +200,5 @@ def transformPointCloud(cloud, transformIn):
     pts, stride = capi.as_points(cloud, 4)
     out = np.zeros_like(pts)
     pose = np.ascontiguousarray(transformIn, np.float32)
-    capi.check(capi.lib().b2_transform_cloud(capi.ptr(pts), stride, pts.shape[0], capi.ptr(pose), capi.ptr(out), out.strides[0]))
+    capi.check(capi.lib().b2_transform_cloud(capi.ptr(pts), stride, pts.shape[0], capi.ptr(pose), capi.ptr(out), pts.shape[1] * 4))
     return out
