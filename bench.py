@@ -222,7 +222,7 @@ def run_b200(args, rank, local_rank, world):
 
     def solve(max_it=30):
         g.transformTobeMapped = guess.copy()
-        return g.scan2MapOptimization(max_it)
+        return g.scan2MapOptimization(max_it, want_matP=False)
 
     r0 = solve()
     iters_needed = r0["iters"]

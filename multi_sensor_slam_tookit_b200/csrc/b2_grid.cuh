@@ -67,15 +67,29 @@ __device__ __forceinline__ void knn_group(const GridDev& g, float qx, float qy, 
                 rs[r] = ok ? __ldg(&g.cell_start[row + x0]) : 0u;
                 re[r] = ok ? __ldg(&g.cell_start[row + x1 + 1]) : 0u;
             }
+            // first chunk of all nine rows is requested before any of it is consumed: nine independent 128-bit loads
+            // in flight per lane instead of a load->compare->load chain (rows rarely exceed LPF points)
+            float4 first[9];
 #pragma unroll
             for (int r = 0; r < 9; r++) {
-                for (uint32_t p = rs[r] + sub; p < re[r]; p += LPF) {
-                    const float4 c = ldg4(&g.pts[p]);
-                    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
-                    float d = dx * dx;
-                    d = d + dy * dy;
-                    d = d + dz * dz;
-                    top.push(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)__float_as_int(c.w), p);
+                const uint32_t p = rs[r] + sub;
+                first[r] = (p < re[r]) ? ldg4(&g.pts[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int r = 0; r < 9; r++) {
+                uint32_t p = rs[r] + sub;
+                if (p < re[r]) {
+                    float4 c = first[r];
+                    for (;;) {
+                        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                        float d = dx * dx;
+                        d = d + dy * dy;
+                        d = d + dz * dz;
+                        top.push(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)__float_as_int(c.w), p);
+                        p += LPF;
+                        if (p >= re[r]) break;
+                        c = ldg4(&g.pts[p]);
+                    }
                 }
             }
         }

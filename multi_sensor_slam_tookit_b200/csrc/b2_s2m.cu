@@ -22,8 +22,11 @@
 namespace b2 {
 
 constexpr int S2M_THREADS = 256;
-constexpr int S2M_LPF = 8;                          // lanes per feature in phase 1
-constexpr int S2M_FPB = S2M_THREADS / S2M_LPF;      // 32 features per CTA
+// two shapes of the one kernel: <lanes per feature, rounds>
+constexpr int S2M_LAT_LPF = 16, S2M_LAT_ROUNDS = 2;   // single scan: 32 features per CTA, many small CTAs (latency)
+constexpr int S2M_THR_LPF = 8,  S2M_THR_ROUNDS = 8;   // batch: 256 features per CTA, every warp busy in phase 2 (throughput)
+constexpr int S2M_LAT_FPB = S2M_THREADS / S2M_LAT_LPF * S2M_LAT_ROUNDS;
+constexpr int S2M_THR_FPB = S2M_THREADS / S2M_THR_LPF * S2M_THR_ROUNDS;
 constexpr int S2M_NPART = 28;                       // 21 (AtA upper) + 6 (Atb) + 1 (count)
 
 struct S2MState {                 // one per scan in the batch, lives in HBM
@@ -53,6 +56,9 @@ struct S2MArgs {
     int device_driven;                            // epilogue prepares xf/trig for the next iteration
     int max_iters;                                // loop bound of scan2MapOptimization (device-driven runs)
     int min_corr; float eig_thr;
+    int want_matP;                                // 0: iteration 0 may skip the 6x6 eigen-decomposition when the system is
+                                                  //    certified non-degenerate (matP is then left untouched)
+    int* done_count;                              // number of scans whose loop has ended (host polls it between chunks)
     float* pose_hist; int hist_stride;            // optional [batch][max_iters][6]
     // optional per-feature introspection (single-scan parity runs)
     int32_t* dbg_idx_c; float* dbg_d2_c; float4* dbg_coeff_c; uint8_t* dbg_flag_c;
@@ -80,7 +86,7 @@ __device__ void prepare_pose_device(S2MState& s) {
     s.trig[4] = sr; s.trig[5] = cr;     // srz crz <- roll
 }
 
-__global__ void k_s2m_prepare(S2MState* st, int batch, const int* off_c, const int* off_s, int edge_min, int surf_min, int* not_enough) {
+__global__ void k_s2m_prepare(S2MState* st, int batch, const int* off_c, const int* off_s, int edge_min, int surf_min, int* not_enough, int* done_count) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     S2MState& s = st[b];
@@ -88,7 +94,7 @@ __global__ void k_s2m_prepare(S2MState* st, int batch, const int* off_c, const i
     s.done = 0; s.converged = 0; s.iters = 0; s.n_sel = 0; s.ran = 0; s.ticket = 0;
     const int nc = off_c[b + 1] - off_c[b], ns = off_s[b + 1] - off_s[b];
     const int ne = !(nc > edge_min && ns > surf_min);      // guard of scan2MapOptimization :1287
-    if (ne) s.done = 1;
+    if (ne) { s.done = 1; if (done_count) atomicAdd(done_count, 1); }
     if (not_enough) not_enough[b] = ne;
 }
 
@@ -109,9 +115,8 @@ __device__ __forceinline__ bool fit_line(const float (&nx)[5], const float (&ny)
         a33 += az * az;
     }
     a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
-    float m[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
     float w[3], v[9];
-    sym_eigen_jacobi<3>(m, w, v);
+    sym_eigen_jacobi3(a11, a12, a13, a22, a23, a33, w, v);
     if (!(w[0] > 3 * w[1])) return false;
     // two points on the line, 0.1 either side of the centroid (double literal: evaluated in double, narrowed)
     float x1 = cx + 0.1 * v[0], y1 = cy + 0.1 * v[1], z1 = cz + 0.1 * v[2];
@@ -159,6 +164,7 @@ __device__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, cons
                     for (int i = 0; i < 6; i++) a.pose_hist[((size_t)scan * a.hist_stride + it) * 6 + i] = s.pose[i];
             s.iters = a.max_iters;
             s.done = 1;
+            if (a.done_count) atomicAdd(a.done_count, 1);
         } else {
             s.iters += 1;
         }
@@ -180,7 +186,31 @@ __device__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, cons
         for (int i = 0; i < 6; i++) X[i] = AtB[i];
         if (!solve_householder<6>(w, X)) for (int i = 0; i < 6; i++) X[i] = 0.f;
     }
-    if (iterCount == 0) {
+    bool full_eigen = iterCount == 0;
+    if (full_eigen && !a.want_matP) {
+        // Degeneracy needs only "is the smallest eigenvalue below the threshold". LDL^T of (AtA - shift*I) in fp64 with
+        // shift = threshold + 1e-4*trace has all-positive pivots iff lambda_min > shift; the margin is far above the
+        // error of a float Jacobi sweep (~1e-6*||AtA||), so a certified system is non-degenerate for the reference's
+        // cv::eigen as well. Anything closer to the threshold takes the literal path below.
+        double Ld[36];
+        double tr = 0.0;
+        for (int i = 0; i < 6; i++) tr += (double)AtA[i * 6 + i];
+        const double shift = (double)a.eig_thr + 1e-4 * tr;
+        bool pd = true;
+        for (int j = 0; j < 6 && pd; j++) {
+            double d = (double)AtA[j * 6 + j] - shift;
+            for (int q = 0; q < j; q++) d -= Ld[j * 6 + q] * Ld[j * 6 + q] * Ld[q * 6 + q];
+            if (!(d > 0.0)) { pd = false; break; }
+            Ld[j * 6 + j] = d;
+            for (int i = j + 1; i < 6; i++) {
+                double v = (double)AtA[i * 6 + j];
+                for (int q = 0; q < j; q++) v -= Ld[i * 6 + q] * Ld[j * 6 + q] * Ld[q * 6 + q];
+                Ld[i * 6 + j] = v / d;
+            }
+        }
+        if (pd) { s.degenerate = 0; full_eigen = false; }
+    }
+    if (full_eigen) {
         float w[36], E[6], V[36], V2[36], Vi[36];
         for (int i = 0; i < 36; i++) w[i] = AtA[i];
         sym_eigen_jacobi<6>(w, E, V);
@@ -213,85 +243,101 @@ __device__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, cons
     }
     s.iters += 1;
     if (a.device_driven) {
-        if (conv) s.done = 1;
+        if (conv) { s.done = 1; if (a.done_count) atomicAdd(a.done_count, 1); }
         else prepare_pose_device(s);
     }
 }
 
+// LPF lanes serve one feature in phase 1; a CTA of 256 threads makes ROUNDS passes, so it owns
+// FPB = 256 / LPF * ROUNDS features and phase 2 runs on FPB threads (one warp for the latency shape <16,2>,
+// all eight warps for the throughput shape <8,8>).
+template <int LPF, int ROUNDS>
 __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) {
+    constexpr int FPR = S2M_THREADS / LPF;
+    constexpr int FPB = FPR * ROUNDS;
+    static_assert(FPB <= S2M_THREADS && FPB % 32 == 0, "phase 2 maps one thread per feature in whole warps");
+    constexpr int P2_WARPS = FPB / 32;
     const int scan = blockIdx.y;
     S2MState& st = a.st[scan];
     if (st.done) return;                                       // uniform per CTA, written only by a previous launch
     const int c0 = a.off_c[scan], nc = a.off_c[scan + 1] - c0;
     const int s0 = a.off_s[scan], ns = a.off_s[scan + 1] - s0;
-    const int nbc = (nc + S2M_FPB - 1) / S2M_FPB, nbs = (ns + S2M_FPB - 1) / S2M_FPB;
+    const int nbc = (nc + FPB - 1) / FPB, nbs = (ns + FPB - 1) / FPB;
     const int nblk = nbc + nbs;
     if ((int)blockIdx.x >= nblk) return;
     const bool is_surf = (int)blockIdx.x >= nbc;
-    const int fb = is_surf ? ((int)blockIdx.x - nbc) * S2M_FPB : (int)blockIdx.x * S2M_FPB;   // first feature of this CTA
+    const int fb = is_surf ? ((int)blockIdx.x - nbc) * FPB : (int)blockIdx.x * FPB;   // first feature of this CTA
     const int nfeat = is_surf ? ns : nc;
     const float4* scanp = is_surf ? (a.scan_s + s0) : (a.scan_c + c0);
     const GridDev& g = is_surf ? a.gs : a.gc;
 
-    __shared__ float s_nb[S2M_FPB][5][4];     // winners: x y z, original index bits
-    __shared__ float s_d2[S2M_FPB][5];
-    __shared__ float s_pt[S2M_FPB][8];        // pointOri xyz i, pointSel xyz
+    __shared__ float4 s_nb[FPB][5];           // winners: x y z, original index bits
+    __shared__ float s_d2[FPB][5];
+    __shared__ float4 s_ori[FPB], s_sel[FPB]; // pointOri (xyzi), pointSel (xyz)
     __shared__ float s_xf[12], s_trig[6];
     __shared__ int s_last;
+    __shared__ double s_wsum[P2_WARPS][S2M_NPART];
+    __shared__ double s_red[S2M_THREADS / 32][S2M_NPART];
     __shared__ double s_sum[S2M_NPART];
 
     if (threadIdx.x < 12) s_xf[threadIdx.x] = st.xf[threadIdx.x];
     else if (threadIdx.x < 18) s_trig[threadIdx.x - 12] = st.trig[threadIdx.x - 12];
     __syncthreads();
 
-    // ---------------- phase 1: transform + 5-NN, 8 lanes per feature
-    const int grp = threadIdx.x / S2M_LPF, sub = threadIdx.x & (S2M_LPF - 1);
-    const int f = fb + grp;
-    const bool active = f < nfeat;
-    float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    if (active) {
-        po = __ldg(&scanp[f]);
-        sx = s_xf[0] * po.x + s_xf[1] * po.y + s_xf[2] * po.z + s_xf[3];
-        sy = s_xf[4] * po.x + s_xf[5] * po.y + s_xf[6] * po.z + s_xf[7];
-        sz = s_xf[8] * po.x + s_xf[9] * po.y + s_xf[10] * po.z + s_xf[11];
-    }
-    unsigned long long key[5]; uint32_t pos[5];
-    knn_group<5, S2M_LPF>(g, sx, sy, sz, active, key, pos);
-    if (active) {
-        if (sub < 5) {
-            // lane r of the group fetches winner r (static indexing keeps key/pos in registers)
-            unsigned long long kk = key[0]; uint32_t pp = pos[0];
+    // ---------------- phase 1: transform + 5-NN, LPF lanes per feature
+    const int grp = threadIdx.x / LPF, sub = threadIdx.x & (LPF - 1);
+#pragma unroll 1
+    for (int r = 0; r < ROUNDS; r++) {
+        const int slot = r * FPR + grp;
+        const int f = fb + slot;
+        const bool active = f < nfeat;
+        float4 po = make_float4(0.f, 0.f, 0.f, 0.f);
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        if (active) {
+            po = __ldg(&scanp[f]);
+            sx = s_xf[0] * po.x + s_xf[1] * po.y + s_xf[2] * po.z + s_xf[3];
+            sy = s_xf[4] * po.x + s_xf[5] * po.y + s_xf[6] * po.z + s_xf[7];
+            sz = s_xf[8] * po.x + s_xf[9] * po.y + s_xf[10] * po.z + s_xf[11];
+        }
+        unsigned long long key[5]; uint32_t pos[5];
+        knn_group<5, LPF>(g, sx, sy, sz, active, key, pos);
+        if (active) {
+            if (sub < 5) {
+                // lane j of the group fetches winner j (static indexing keeps key/pos in registers)
+                unsigned long long kk = key[0]; uint32_t pp = pos[0];
 #pragma unroll
-            for (int r = 1; r < 5; r++) if (sub == r) { kk = key[r]; pp = pos[r]; }
-            float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-            float d = INFINITY;
-            if (kk != KNN_EMPTY) { c = ldg4(&g.pts[pp]); d = __uint_as_float((uint32_t)(kk >> 32)); }
-            s_nb[grp][sub][0] = c.x; s_nb[grp][sub][1] = c.y; s_nb[grp][sub][2] = c.z; s_nb[grp][sub][3] = c.w;
-            s_d2[grp][sub] = d;
-        } else if (sub == 5) {
-            s_pt[grp][0] = po.x; s_pt[grp][1] = po.y; s_pt[grp][2] = po.z; s_pt[grp][3] = po.w;
-            s_pt[grp][4] = sx; s_pt[grp][5] = sy; s_pt[grp][6] = sz;
+                for (int j = 1; j < 5; j++) if (sub == j) { kk = key[j]; pp = pos[j]; }
+                float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                float d = INFINITY;
+                if (kk != KNN_EMPTY) { c = ldg4(&g.pts[pp]); d = __uint_as_float((uint32_t)(kk >> 32)); }
+                s_nb[slot][sub] = c;
+                s_d2[slot][sub] = d;
+            } else if (sub == 5) {
+                s_ori[slot] = po;
+                s_sel[slot] = make_float4(sx, sy, sz, 0.f);
+            }
         }
     }
     __syncthreads();
 
-    // ---------------- phase 2: warp 0, one lane per feature
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        const int ff = fb + lane;
+    // ---------------- phase 2: one thread per feature
+    if (threadIdx.x < FPB) {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const int slot = threadIdx.x;
+        const int ff = fb + slot;
         bool keep = false;
         float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
         float ox = 0.f, oy = 0.f, oz = 0.f;
         if (ff < nfeat) {
             float nx[5], ny[5], nz[5];
 #pragma unroll
-            for (int j = 0; j < 5; j++) { nx[j] = s_nb[lane][j][0]; ny[j] = s_nb[lane][j][1]; nz[j] = s_nb[lane][j][2]; }
-            ox = s_pt[lane][0]; oy = s_pt[lane][1]; oz = s_pt[lane][2];
-            const float d4 = s_d2[lane][4];
+            for (int j = 0; j < 5; j++) { const float4 c = s_nb[slot][j]; nx[j] = c.x; ny[j] = c.y; nz[j] = c.z; }
+            const float4 po = s_ori[slot], ps = s_sel[slot];
+            ox = po.x; oy = po.y; oz = po.z;
+            const float d4 = s_d2[slot][4];
             if (d4 < 1.0) {
-                if (is_surf) keep = fit_plane(nx, ny, nz, s_pt[lane][4], s_pt[lane][5], s_pt[lane][6], ox, oy, oz, coeff);
-                else keep = fit_line(nx, ny, nz, s_pt[lane][4], s_pt[lane][5], s_pt[lane][6], coeff);
+                if (is_surf) keep = fit_plane(nx, ny, nz, ps.x, ps.y, ps.z, ox, oy, oz, coeff);
+                else keep = fit_line(nx, ny, nz, ps.x, ps.y, ps.z, coeff);
             }
             int32_t* di = is_surf ? a.dbg_idx_s : a.dbg_idx_c;
             if (di) {
@@ -300,8 +346,8 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
                 uint8_t* df = is_surf ? a.dbg_flag_s : a.dbg_flag_c;
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
-                    di[(size_t)ff * 5 + j] = __float_as_int(s_nb[lane][j][3]);
-                    dd[(size_t)ff * 5 + j] = s_d2[lane][j];
+                    di[(size_t)ff * 5 + j] = __float_as_int(s_nb[slot][j].w);
+                    dd[(size_t)ff * 5 + j] = s_d2[slot][j];
                 }
                 dc[ff] = coeff; df[ff] = keep ? 1 : 0;
             }
@@ -338,30 +384,55 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
 #pragma unroll
         for (int q = 0; q < S2M_NPART; q++) acc[q] = warp_sum(acc[q]);
         if (lane == 0) {
-            double* out = a.partial + ((size_t)scan * a.max_blocks + blockIdx.x) * S2M_NPART;
 #pragma unroll
-            for (int q = 0; q < S2M_NPART; q++) __stcg(&out[q], acc[q]);
-            __threadfence();
-            unsigned t = atomicAdd(&st.ticket, 1u);
-            s_last = (t == (unsigned)(nblk - 1)) ? 1 : 0;
+            for (int q = 0; q < S2M_NPART; q++) s_wsum[warp][q] = acc[q];
         }
-        __syncwarp();
-        // ---------------- epilogue: last CTA of this scan
-        if (s_last) {
-            __threadfence();
-            if (lane < S2M_NPART) {
-                const double* base = a.partial + (size_t)scan * a.max_blocks * S2M_NPART + lane;
-                double sum = 0.0;
-                for (int b = 0; b < nblk; b++) sum += __ldcg(&base[(size_t)b * S2M_NPART]);
-                s_sum[lane] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x < S2M_NPART) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < P2_WARPS; w++) v += s_wsum[w][threadIdx.x];
+        __stcg(&a.partial[((size_t)scan * a.max_blocks + blockIdx.x) * S2M_NPART + threadIdx.x], v);
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(&st.ticket, 1u);
+        s_last = (t == (unsigned)(nblk - 1)) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+
+    // ---------------- epilogue: the last CTA of this scan adds the partials in a fixed (slice, CTA) order
+    __threadfence();
+    {
+        const int q = threadIdx.x & 31, slice = threadIdx.x >> 5;
+        if (q < S2M_NPART) {
+            const double* base = a.partial + (size_t)scan * a.max_blocks * S2M_NPART + q;
+            double sum = 0.0;
+            int b = slice;
+            for (; b + 24 < nblk; b += 32) {
+                const double v0 = __ldcg(&base[(size_t)b * S2M_NPART]), v1 = __ldcg(&base[(size_t)(b + 8) * S2M_NPART]);
+                const double v2 = __ldcg(&base[(size_t)(b + 16) * S2M_NPART]), v3 = __ldcg(&base[(size_t)(b + 24) * S2M_NPART]);
+                sum += v0; sum += v1; sum += v2; sum += v3;
             }
-            __syncwarp();
-            if (lane == 0) {
-                st.ticket = 0;
-                const int iterCount = a.iter >= 0 ? a.iter : st.iters;
-                lm_epilogue(st, s_sum, iterCount, a, scan);
-            }
+            for (; b < nblk; b += 8) sum += __ldcg(&base[(size_t)b * S2M_NPART]);
+            s_red[slice][q] = sum;
         }
+    }
+    __syncthreads();
+    if (threadIdx.x < S2M_NPART) {
+        double v = 0.0;
+#pragma unroll
+        for (int sl = 0; sl < S2M_THREADS / 32; sl++) v += s_red[sl][threadIdx.x];
+        s_sum[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st.ticket = 0;
+        const int iterCount = a.iter >= 0 ? a.iter : st.iters;
+        lm_epilogue(st, s_sum, iterCount, a, scan);
     }
 }
 
@@ -402,6 +473,7 @@ struct b2_s2m_s {
     bool have_map = false, have_scan = false;
     int batch = 0;
     int max_blocks = 0;
+    int max_feat_c = 0, max_feat_s = 0;   // largest per-scan feature counts in the batch
     size_t n_c = 0, n_s = 0;          // total features over the batch
     std::vector<int> h_off_c, h_off_s;
     int degenerate = 0;               // persistent members (:136,:234)
@@ -427,6 +499,20 @@ static int upload_points(b2_s2m_s* h, DevBuf& raw, DevBuf& packed, const void* p
     return B2_OK;
 }
 
+// One LM iteration for every scan of the batch. Shape: a single scan wants many small CTAs (latency), a batch wants
+// CTAs whose second phase keeps all eight warps busy (throughput).
+static void launch_iteration(b2_s2m_s* h, const S2MArgs& a, int batch) {
+    if (batch <= 2) {
+        dim3 grid((unsigned)h->max_blocks, (unsigned)batch);
+        k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS><<<grid, S2M_THREADS, 0, h->stream>>>(a);
+    } else {
+        const int nb = (h->max_feat_c + S2M_THR_FPB - 1) / S2M_THR_FPB + (h->max_feat_s + S2M_THR_FPB - 1) / S2M_THR_FPB;
+        dim3 grid((unsigned)std::max(nb, 1), (unsigned)batch);
+        k_s2m_iteration<S2M_THR_LPF, S2M_THR_ROUNDS><<<grid, S2M_THREADS, 0, h->stream>>>(a);
+    }
+    count_launch();
+}
+
 static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, float* pose_hist, int hist_stride) {
     S2MArgs a{};
     a.max_iters = hist_stride > 0 ? hist_stride : h->prm.max_iterations;
@@ -439,6 +525,7 @@ static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, f
     a.iter = iter; a.device_driven = device_driven;
     a.min_corr = h->prm.min_correspondences; a.eig_thr = h->prm.degenerate_eigen_threshold;
     a.pose_hist = pose_hist; a.hist_stride = hist_stride;
+    a.want_matP = 1; a.done_count = nullptr;
     if (debug) {
         a.dbg_idx_c = h->dbg_idx_c.as<int32_t>(); a.dbg_d2_c = h->dbg_d2_c.as<float>(); a.dbg_coeff_c = h->dbg_coeff_c.as<float4>(); a.dbg_flag_c = h->dbg_flag_c.as<uint8_t>();
         a.dbg_idx_s = h->dbg_idx_s.as<int32_t>(); a.dbg_d2_s = h->dbg_d2_s.as<float>(); a.dbg_coeff_s = h->dbg_coeff_s.as<float4>(); a.dbg_flag_s = h->dbg_flag_s.as<uint8_t>();
@@ -462,15 +549,18 @@ static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cs
     B2_CUDA(cudaMemcpyAsync(h->off_c.p, h->h_off_c.data(), (batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     B2_CUDA(cudaMemcpyAsync(h->off_s.p, h->h_off_s.data(), (batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     int mb = 1;
+    h->max_feat_c = h->max_feat_s = 0;
     for (int b = 0; b < batch; b++) {
-        int nb = (coff[b + 1] - coff[b] + S2M_FPB - 1) / S2M_FPB + (soff[b + 1] - soff[b] + S2M_FPB - 1) / S2M_FPB;
-        mb = std::max(mb, nb);
+        h->max_feat_c = std::max(h->max_feat_c, coff[b + 1] - coff[b]);
+        h->max_feat_s = std::max(h->max_feat_s, soff[b + 1] - soff[b]);
+        int nb = (coff[b + 1] - coff[b] + S2M_LAT_FPB - 1) / S2M_LAT_FPB + (soff[b + 1] - soff[b] + S2M_LAT_FPB - 1) / S2M_LAT_FPB;
+        mb = std::max(mb, nb);          // sized for the small-CTA shape, the larger count of the two
     }
     h->max_blocks = mb;
     h->batch = batch;
     B2_CHECK(h->state.reserve((size_t)batch * sizeof(S2MState)));
     B2_CHECK(h->partial.reserve((size_t)batch * mb * S2M_NPART * sizeof(double)));
-    B2_CHECK(h->ne.reserve((size_t)batch * sizeof(int)));
+    B2_CHECK(h->ne.reserve((size_t)(batch + 1) * sizeof(int)));
     if (batch == 1) {
         const size_t nc = std::max<size_t>(h->n_c, 1), ns = std::max<size_t>(h->n_s, 1);
         B2_CHECK(h->dbg_idx_c.reserve(nc * 5 * 4)); B2_CHECK(h->dbg_d2_c.reserve(nc * 5 * 4));
@@ -567,8 +657,8 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
     hs->degenerate = h->degenerate;
     B2_CUDA(cudaMemcpyAsync(h->state.p, hs, sizeof(S2MState), cudaMemcpyHostToDevice, h->stream));
     S2MArgs a = make_args(h, iter, 0, true, nullptr, 0);
-    dim3 grid((unsigned)h->max_blocks, 1);
-    k_s2m_iteration<<<grid, S2M_THREADS, 0, h->stream>>>(a); count_launch();
+    a.want_matP = matP != nullptr;
+    launch_iteration(h, a, 1);
     B2_CUDA(cudaGetLastError());
     B2_CUDA(cudaMemcpyAsync(hs, h->state.p, sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream));
@@ -584,10 +674,10 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
 }
 
 static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_done, int* converged, int* degenerate,
-                     float* matP_out, int* not_enough, float* pose_history) {
+                     float* matP_out, int* not_enough, float* pose_history, bool want_matP) {
     const int B = h->batch;
     if (max_iterations < 1) max_iterations = h->prm.max_iterations;
-    B2_CHECK(h->pin.reserve((size_t)B * sizeof(S2MState) + (size_t)B * sizeof(int)));
+    B2_CHECK(h->pin.reserve((size_t)B * sizeof(S2MState) + (size_t)B * sizeof(int) + 64));
     S2MState* hs = h->pin.as<S2MState>();
     memset(hs, 0, (size_t)B * sizeof(S2MState));
     for (int b = 0; b < B; b++) {
@@ -603,14 +693,30 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     B2_CUDA(cudaEventRecord(h->ev0, h->stream));
     B2_CUDA(cudaMemcpyAsync(h->state.p, hs, (size_t)B * sizeof(S2MState), cudaMemcpyHostToDevice, h->stream));
     if (d_hist) B2_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)B * max_iterations * 6 * sizeof(float), h->stream));
+    B2_CHECK(h->ne.reserve((size_t)(B + 1) * sizeof(int)));
+    int* d_done = h->ne.as<int>() + B;
+    B2_CUDA(cudaMemsetAsync(d_done, 0, sizeof(int), h->stream));
     k_s2m_prepare<<<(B + 127) / 128, 128, 0, h->stream>>>(h->state.as<S2MState>(), B, h->off_c.as<int>(), h->off_s.as<int>(),
-                                                          h->prm.edge_feature_min_valid_num, h->prm.surf_feature_min_valid_num, h->ne.as<int>()); count_launch();
+                                                          h->prm.edge_feature_min_valid_num, h->prm.surf_feature_min_valid_num, h->ne.as<int>(), d_done); count_launch();
     B2_CUDA(cudaGetLastError());
     S2MArgs a = make_args(h, -1, 1, false, d_hist, max_iterations);
-    dim3 grid((unsigned)h->max_blocks, (unsigned)B);
-    for (int it = 0; it < max_iterations; it++) k_s2m_iteration<<<grid, S2M_THREADS, 0, h->stream>>>(a);
-    count_launch(max_iterations);
-    B2_CUDA(cudaGetLastError());
+    a.want_matP = want_matP ? 1 : 0;
+    a.done_count = d_done;
+    // Iterations are enqueued in chunks; between chunks the host reads one int (scans finished). A finished scan's CTAs
+    // return at once, so an over-long chunk costs only empty launches; the first chunk covers the usual 3-4 iterations.
+    int* h_done = reinterpret_cast<int*>(hs + B) + B;
+    int launched = 0, n_launch = 1;
+    static const int chunk_plan[] = {4, 4, 6, 8, 8};
+    for (int c = 0; launched < max_iterations; c++) {
+        const int chunk = std::min(chunk_plan[std::min(c, 4)], max_iterations - launched);
+        for (int it = 0; it < chunk; it++) launch_iteration(h, a, B);
+        launched += chunk; n_launch += chunk;
+        B2_CUDA(cudaGetLastError());
+        if (launched >= max_iterations) break;
+        B2_CUDA(cudaMemcpyAsync(h_done, d_done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+        if (*h_done >= B) break;
+    }
     B2_CUDA(cudaEventRecord(h->ev1, h->stream));
     int* h_ne = reinterpret_cast<int*>(hs + B);
     B2_CUDA(cudaMemcpyAsync(hs, h->state.p, (size_t)B * sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
@@ -618,7 +724,7 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     if (pose_history) B2_CUDA(cudaMemcpyAsync(pose_history, d_hist, (size_t)B * max_iterations * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream));
     B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-    h->last_launches = 1 + max_iterations;
+    h->last_launches = n_launch;
     for (int b = 0; b < B; b++) {
         if (!h_ne[b]) memcpy(poses + (size_t)b * 6, hs[b].pose, 24);
         if (iters_done) iters_done[b] = hs[b].iters;
@@ -638,13 +744,13 @@ int b2_s2m_solve(b2_s2m_t h, float pose[6], int max_iterations, int* iters_done,
                  float matP[36], int* not_enough_features, float* pose_history) {
     if (!h || !pose) { set_error("b2_s2m_solve: bad argument"); return B2_ERR_ARG; }
     if (!h->have_map || !h->have_scan || h->batch != 1) { set_error("b2_s2m_solve: set_map and set_scan (single scan) first"); return B2_ERR_STATE; }
-    return run_solve(h, pose, max_iterations, iters_done, converged, degenerate, matP, not_enough_features, pose_history);
+    return run_solve(h, pose, max_iterations, iters_done, converged, degenerate, matP, not_enough_features, pose_history, matP != nullptr);
 }
 
 int b2_s2m_solve_batch(b2_s2m_t h, float* poses, int max_iterations, int* iters_done, int* converged, int* degenerate) {
     if (!h || !poses) { set_error("b2_s2m_solve_batch: bad argument"); return B2_ERR_ARG; }
     if (!h->have_map || !h->have_scan) { set_error("b2_s2m_solve_batch: set_map and set_scan_batch first"); return B2_ERR_STATE; }
-    return run_solve(h, poses, max_iterations, iters_done, converged, degenerate, nullptr, nullptr, nullptr);
+    return run_solve(h, poses, max_iterations, iters_done, converged, degenerate, nullptr, nullptr, nullptr, false);
 }
 
 int b2_s2m_get_pass(b2_s2m_t h, int which, int32_t* knn_idx, float* knn_d2, float* coeff, uint8_t* flag) {

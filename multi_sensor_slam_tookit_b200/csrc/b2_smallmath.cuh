@@ -85,40 +85,119 @@ B2_HD void sym_eigen_jacobi(float* a, float* w, float* v) {
     }
 }
 
+// 3x3 specialisation of sym_eigen_jacobi with every element in a named register. The pivot bookkeeping of the
+// generic routine (row maxima rmax[], column maxima cmax[], refreshed only for the two rotated indices) is
+// reproduced literally: for N = 3 it reduces to rmax[0] in {1,2} and cmax[2] in {0,1} (rmax[1] = 2, cmax[1] = 0).
+// Same operations in the same order as sym_eigen_jacobi<3>, so the results are bit-identical.
+B2_HD void sym_eigen_jacobi3(float a00, float a01, float a02, float a11, float a12, float a22, float (&w)[3], float (&v)[9]) {
+    float w0 = a00, w1 = a11, w2 = a22;
+    float v00 = 1.f, v01 = 0.f, v02 = 0.f, v10 = 0.f, v11 = 1.f, v12 = 0.f, v20 = 0.f, v21 = 0.f, v22 = 1.f;
+    int r0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;
+    int c2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;
+    for (int it = 0; it < 3 * 3 * 30; it++) {
+        // pivot search
+        int k = 0;
+        float mv = fabsf(r0 == 1 ? a01 : a02);
+        { float val = fabsf(a12); if (mv < val) { mv = val; k = 1; } }
+        int l = (k == 0) ? r0 : 2;
+        { float val = fabsf(a01); if (mv < val) { mv = val; k = 0; l = 1; } }
+        { float val = fabsf(c2 == 0 ? a02 : a12); if (mv < val) { mv = val; k = c2; l = 2; } }
+        const int pair = (k == 0) ? (l == 1 ? 0 : 1) : 2;            // (0,1) (0,2) (1,2)
+        const float p = pair == 0 ? a01 : (pair == 1 ? a02 : a12);
+        if (fabsf(p) <= FLT_EPSILON) break;
+        const float wk = (k == 0) ? w0 : w1, wl = (l == 1) ? w1 : w2;
+        float y = (float)((wl - wk) * 0.5);
+        float t = fabsf(y) + scaled_hypot(p, y);
+        float s = scaled_hypot(p, t);
+        float c = t / s;
+        s = p / s; t = (p / t) * p;
+        if (y < 0) { s = -s; t = -t; }
+#define B2_ROT(x, z) do { float a0_ = (x), b0_ = (z); (x) = a0_ * c - b0_ * s; (z) = a0_ * s + b0_ * c; } while (0)
+        if (pair == 0) {
+            a01 = 0; w0 -= t; w1 += t;
+            B2_ROT(a02, a12);
+            B2_ROT(v00, v10); B2_ROT(v01, v11); B2_ROT(v02, v12);
+            r0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;      // idx 0: row max ; idx 1: rmax[1] = 2, cmax[1] = 0 fixed
+        } else if (pair == 1) {
+            a02 = 0; w0 -= t; w2 += t;
+            B2_ROT(a01, a12);
+            B2_ROT(v00, v20); B2_ROT(v01, v21); B2_ROT(v02, v22);
+            r0 = (fabsf(a01) < fabsf(a02)) ? 2 : 1;      // idx 0: row max
+            c2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;      // idx 2: column max
+        } else {
+            a12 = 0; w1 -= t; w2 += t;
+            B2_ROT(a01, a02);
+            B2_ROT(v10, v20); B2_ROT(v11, v21); B2_ROT(v12, v22);
+            c2 = (fabsf(a02) < fabsf(a12)) ? 1 : 0;      // idx 2: column max (idx 1 entries are fixed)
+        }
+#undef B2_ROT
+    }
+    // selection sort, descending, rows of v follow
+#define B2_SWAPROW(wa, wb, ra0, ra1, ra2, rb0, rb1, rb2) do { float t_ = wa; wa = wb; wb = t_; t_ = ra0; ra0 = rb0; rb0 = t_; \
+        t_ = ra1; ra1 = rb1; rb1 = t_; t_ = ra2; ra2 = rb2; rb2 = t_; } while (0)
+    {
+        int m = 0;
+        if (w0 < w1) m = 1;
+        if ((m == 0 ? w0 : w1) < w2) m = 2;
+        if (m == 1) B2_SWAPROW(w1, w0, v10, v11, v12, v00, v01, v02);
+        else if (m == 2) B2_SWAPROW(w2, w0, v20, v21, v22, v00, v01, v02);
+        if (w1 < w2) B2_SWAPROW(w2, w1, v20, v21, v22, v10, v11, v12);
+    }
+#undef B2_SWAPROW
+    w[0] = w0; w[1] = w1; w[2] = w2;
+    v[0] = v00; v[1] = v01; v[2] = v02; v[3] = v10; v[4] = v11; v[5] = v12; v[6] = v20; v[7] = v21; v[8] = v22;
+}
+
 // Householder QR solve of a square system, one right-hand side; a, b destroyed, x left in b. 0 = singular.
+// No pivoting, so every index is a compile-time constant once the loops are unrolled: the whole factorisation
+// stays in registers (a serial single-thread epilogue is latency bound, local memory would triple its time).
 template <int N>
 B2_HD int solve_householder(float* a, float* b) {
     const float eps = FLT_EPSILON * 10;
     float u[N], hf[N];
+#pragma unroll
     for (int l = 0; l < N; l++) {
         const int len = N - l;
         float nrm = 0.f;
+#pragma unroll
         for (int i = 0; i < len; i++) { u[i] = a[(l + i) * N + l]; nrm += u[i] * u[i]; }
         float head = u[0];
         u[0] = u[0] + ((u[0] >= 0.0f) ? 1 : -1) * sqrtf(nrm);
         nrm = sqrtf(nrm + u[0] * u[0] - head * head);
+#pragma unroll
         for (int i = 0; i < len; i++) u[i] /= nrm;
+#pragma unroll
         for (int j = l; j < N; j++) {
             float dot = 0.f;
+#pragma unroll
             for (int i = l; i < N; i++) dot += u[i - l] * a[i * N + j];
+#pragma unroll
             for (int i = l; i < N; i++) a[i * N + j] -= 2 * u[i - l] * dot;
         }
         hf[l] = u[0] * u[0];
+#pragma unroll
         for (int i = 1; i < len; i++) a[(l + i) * N + l] = u[i] / u[0];
     }
+#pragma unroll
     for (int l = 0; l < N; l++) {
         u[0] = 1.f;
+#pragma unroll
         for (int j = 1; j < N - l; j++) u[j] = a[(j + l) * N + l];
         float dot = 0.f;
+#pragma unroll
         for (int i = l; i < N; i++) dot += u[i - l] * b[i];
+#pragma unroll
         for (int i = l; i < N; i++) b[i] -= 2 * u[i - l] * dot * hf[l];
     }
+    int ok = 1;
+#pragma unroll
     for (int i = N - 1; i >= 0; i--) {
+#pragma unroll
         for (int j = N - 1; j > i; j--) b[i] -= b[j] * a[i * N + j];
-        if (fabsf(a[i * N + i]) < eps) return 0;
-        b[i] /= a[i * N + i];
+        if (ok && fabsf(a[i * N + i]) < eps) ok = 0;
+        if (ok) b[i] /= a[i * N + i];
     }
-    return 1;
+    return ok;
 }
 
 // Inverse via LU with partial pivoting applied to an identity right-hand side; a destroyed. 0 = singular (inv zeroed).
@@ -164,13 +243,17 @@ B2_HD void matmul_dacc(const float* A, const float* B, float* C) {
 // min |M x + 1| over x for the 5x3 matrix of neighbour coordinates (rows = points): column-pivoted Householder QR
 // (pivot = largest running column norm, LAPACK WN176 downdate, rank threshold eps^2*maxnorm^2/rows*(rows-k)).
 B2_HD void plane_lsq_5x3(const float (&px)[5], const float (&py)[5], const float (&pz)[5], float& xa, float& xb, float& xc) {
+    // Every loop below has a compile-time trip count and every index is static after unrolling: the pivot column is
+    // brought in with predicated swaps instead of a data-dependent subscript, so q/tau/norms never leave registers.
     float q[5][3];
 #pragma unroll
     for (int i = 0; i < 5; i++) { q[i][0] = px[i]; q[i][1] = py[i]; q[i][2] = pz[i]; }
     float tau[3], nu[3], nd[3];
-    int tr[3];
+    int perm[3] = {0, 1, 2};
+#pragma unroll
     for (int k = 0; k < 3; k++) {
         float s = 0.f;
+#pragma unroll
         for (int i = 0; i < 5; i++) s += q[i][k] * q[i][k];
         nd[k] = sqrtf(s); nu[k] = nd[k];
     }
@@ -179,39 +262,52 @@ B2_HD void plane_lsq_5x3(const float (&px)[5], const float (&py)[5], const float
     const float thr_helper = (th * th) / 5.0f;
     const float downdate_thr = sqrtf(FLT_EPSILON);
     int rank = 3;
+#pragma unroll
     for (int k = 0; k < 3; k++) {
         int big = k; float bv = nu[k];
+#pragma unroll
         for (int j = k + 1; j < 3; j++) if (nu[j] > bv) { bv = nu[j]; big = j; }
         if (rank == 3 && bv * bv < thr_helper * (float)(5 - k)) rank = k;
-        tr[k] = big;
-        if (big != k) {
-            for (int i = 0; i < 5; i++) { float t = q[i][k]; q[i][k] = q[i][big]; q[i][big] = t; }
-            float t = nu[k]; nu[k] = nu[big]; nu[big] = t;
-            t = nd[k]; nd[k] = nd[big]; nd[big] = t;
+#pragma unroll
+        for (int j = k + 1; j < 3; j++) {
+            if (big == j) {
+#pragma unroll
+                for (int i = 0; i < 5; i++) { float t = q[i][k]; q[i][k] = q[i][j]; q[i][j] = t; }
+                float t = nu[k]; nu[k] = nu[j]; nu[j] = t;
+                t = nd[k]; nd[k] = nd[j]; nd[j] = t;
+                int tp = perm[k]; perm[k] = perm[j]; perm[j] = tp;
+            }
         }
         float tail = 0.f;
+#pragma unroll
         for (int i = k + 1; i < 5; i++) tail += q[i][k] * q[i][k];
         float c0 = q[k][k], beta, tk;
         if (tail <= FLT_MIN) {
             tk = 0.f; beta = c0;
+#pragma unroll
             for (int i = k + 1; i < 5; i++) q[i][k] = 0.f;
         } else {
             beta = sqrtf(c0 * c0 + tail);
             if (c0 >= 0.f) beta = -beta;
             float den = c0 - beta;
+#pragma unroll
             for (int i = k + 1; i < 5; i++) q[i][k] = q[i][k] / den;
             tk = (beta - c0) / beta;
         }
         tau[k] = tk; q[k][k] = beta;
         if (tk != 0.f) {
+#pragma unroll
             for (int j = k + 1; j < 3; j++) {
                 float t = 0.f;
+#pragma unroll
                 for (int i = k + 1; i < 5; i++) t += q[i][k] * q[i][j];
                 t += q[k][j];
                 q[k][j] -= tk * t;
+#pragma unroll
                 for (int i = k + 1; i < 5; i++) q[i][j] -= tk * q[i][k] * t;
             }
         }
+#pragma unroll
         for (int j = k + 1; j < 3; j++) {
             if (nu[j] != 0.f) {
                 float t = fabsf(q[k][j]) / nu[j];
@@ -221,6 +317,7 @@ B2_HD void plane_lsq_5x3(const float (&px)[5], const float (&py)[5], const float
                 float t2 = t * (r * r);
                 if (t2 <= downdate_thr) {
                     float s = 0.f;
+#pragma unroll
                     for (int i = k + 1; i < 5; i++) s += q[i][j] * q[i][j];
                     nd[j] = sqrtf(s); nu[j] = nd[j];
                 } else {
@@ -229,25 +326,36 @@ B2_HD void plane_lsq_5x3(const float (&px)[5], const float (&py)[5], const float
             }
         }
     }
-    int perm[3] = {0, 1, 2};
-    for (int k = 0; k < 3; k++) { int t = perm[k]; perm[k] = perm[tr[k]]; perm[tr[k]] = t; }
     float c[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
-    float x[3] = {0.f, 0.f, 0.f};
-    if (rank > 0) {
-        for (int k = 0; k < rank; k++) {
-            if (tau[k] == 0.f) continue;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (k < rank && tau[k] != 0.f) {
             float t = 0.f;
+#pragma unroll
             for (int i = k + 1; i < 5; i++) t += q[i][k] * c[i];
             t += c[k];
             c[k] -= tau[k] * t;
+#pragma unroll
             for (int i = k + 1; i < 5; i++) c[i] -= tau[k] * q[i][k] * t;
         }
-        for (int i = rank - 1; i >= 0; i--) {
+    }
+#pragma unroll
+    for (int i = 2; i >= 0; i--) {
+        if (i < rank) {
             float s = c[i];
-            for (int j = i + 1; j < rank; j++) s -= q[i][j] * c[j];
+#pragma unroll
+            for (int j = i + 1; j < 3; j++) if (j < rank) s -= q[i][j] * c[j];
             c[i] = s / q[i][i];
         }
-        for (int i = 0; i < rank; i++) x[perm[i]] = c[i];
+    }
+    // x[perm[i]] = c[i] for i < rank, zero elsewhere — as selects
+    float x[3];
+#pragma unroll
+    for (int o = 0; o < 3; o++) {
+        float val = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; i++) if (i < rank && perm[i] == o) val = c[i];
+        x[o] = val;
     }
     xa = x[0]; xb = x[1]; xc = x[2];
 }

@@ -151,18 +151,21 @@ class ScanToMapOptimizer:
         self.matP = matP.reshape(6, 6)
         return bool(conv.value)
 
-    def scan2MapOptimization(self, max_iterations=30, record_history=False):
-        """The whole loop on the device. Returns dict(iters, converged, not_enough, pose_history)."""
+    def scan2MapOptimization(self, max_iterations=30, record_history=False, want_matP=True):
+        """The whole loop on the device. Returns dict(iters, converged, not_enough, pose_history).
+        want_matP=False lets iteration 0 skip the 6x6 eigen-decomposition when the normal matrix is certified
+        non-degenerate (matP is only ever read when isDegenerate, mapOptmization.cpp:1253-1258)."""
         pose = np.ascontiguousarray(self.transformTobeMapped, np.float32)
         it, conv, deg, ne = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
-        matP = np.zeros(36, np.float32)
+        matP = np.zeros(36, np.float32) if want_matP else None
         hist = np.zeros((max_iterations, 6), np.float32) if record_history else None
         capi.check(capi.lib().b2_s2m_solve(self._h, capi.ptr(pose), max_iterations, C.byref(it), C.byref(conv), C.byref(deg),
                                            capi.ptr(matP), C.byref(ne), capi.ptr(hist)))
         self.transformTobeMapped = pose
         if not ne.value:
             self.isDegenerate = bool(deg.value)
-            self.matP = matP.reshape(6, 6)
+            if matP is not None:
+                self.matP = matP.reshape(6, 6)
         return dict(iters=it.value, converged=bool(conv.value), not_enough=bool(ne.value),
                     pose_history=None if hist is None else hist[:it.value])
 

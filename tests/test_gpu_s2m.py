@@ -76,7 +76,13 @@ def test_device_driven_solve_matches_oracle(b2, oracle, c1):
     assert np.all(np.abs(res["pose_history"][:, :3] - ref["pose_hist"][:, :3]) <= TOL_RAD)
     assert np.all(np.abs(g.transformTobeMapped[3:] - c1["pose_truth"][3:]) < 0.02)
     ms, launches = g.lastGpuMs()
-    assert ms > 0 and launches == 31
+    assert ms > 0 and 1 + res["iters"] <= launches <= 31
+    # the certified fast path of iteration 0 (no matP requested) must not change anything observable
+    g2, _ = _pair(b2, oracle, c1)
+    g2.transformTobeMapped = c1["pose_guess"].copy()
+    res2 = g2.scan2MapOptimization(30, record_history=True, want_matP=False)
+    assert res2["iters"] == res["iters"] and np.array_equal(res2["pose_history"], res["pose_history"])
+    assert g2.isDegenerate == g.isDegenerate
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2, 3])
