@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb2reg.so")
+LIB_PATH = os.environ.get("B2_LIB") or os.path.join(HERE, "libb2reg.so")   # B2_LIB: kernel experiments only
 _LIB = None
 
 

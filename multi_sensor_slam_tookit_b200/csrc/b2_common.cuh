@@ -82,6 +82,7 @@ struct GridDev {               // passed by value to kernels
     float ox, oy, oz, inv_h;
     int nx, ny, nz;
     int n;
+    float max_d2;              // candidates at or beyond this squared distance are never reported (max_dist^2)
 };
 struct GridIndex {
     DevBuf pts, cell_start, cell_of, tmp, raw;

@@ -80,7 +80,7 @@ int GridIndex::build(const void* host_pts, size_t stride, size_t n_, float max_d
         B2_CHECK(cell_start.reserve(3 * sizeof(uint32_t)));
         B2_CUDA(cudaMemsetAsync(cell_start.p, 0, 3 * sizeof(uint32_t), s));
         dev.pts = nullptr; dev.cell_start = cell_start.as<uint32_t>();
-        dev.ox = dev.oy = dev.oz = 0.f; dev.inv_h = 1.0f / h; dev.nx = dev.ny = dev.nz = 1; dev.n = 0;
+        dev.ox = dev.oy = dev.oz = 0.f; dev.inv_h = 1.0f / h; dev.nx = dev.ny = dev.nz = 1; dev.n = 0; dev.max_d2 = max_dist * max_dist;
         return B2_OK;
     }
     if (n > 0x7fffffffull) { set_error("grid index: too many points (%zu)", n); return B2_ERR_ARG; }
@@ -134,7 +134,7 @@ int GridIndex::build(const void* host_pts, size_t stride, size_t n_, float max_d
     B2_CUDA(cudaGetLastError());
     dev.pts = pts.as<float4>(); dev.cell_start = cell_start.as<uint32_t>();
     dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h;
-    dev.nx = g.nx; dev.ny = g.ny; dev.nz = g.nz; dev.n = (int)n;
+    dev.nx = g.nx; dev.ny = g.ny; dev.nz = g.nz; dev.n = (int)n; dev.max_d2 = max_dist * max_dist;
     return B2_OK;
 }
 

@@ -19,6 +19,10 @@
 #include <vector>
 #include <algorithm>
 
+#ifndef B2_FIT_VARIANT
+#define B2_FIT_VARIANT 1      // 0: rolled loops over per-thread arrays (small code); 1: fully unrolled, register resident
+#endif
+
 namespace b2 {
 
 constexpr int S2M_THREADS = 256;
@@ -59,6 +63,7 @@ struct S2MArgs {
     int want_matP;                                // 0: iteration 0 may skip the 6x6 eigen-decomposition when the system is
                                                   //    certified non-degenerate (matP is then left untouched)
     int* done_count;                              // number of scans whose loop has ended (host polls it between chunks)
+    long long* prof;                              // optional per-CTA clock64 stamps (B2_S2M_PROF=1), 8 per CTA
     float* pose_hist; int hist_stride;            // optional [batch][max_iters][6]
     // optional per-feature introspection (single-scan parity runs)
     int32_t* dbg_idx_c; float* dbg_d2_c; float4* dbg_coeff_c; uint8_t* dbg_flag_c;
@@ -100,7 +105,7 @@ __global__ void k_s2m_prepare(S2MState* st, int batch, const int* off_c, const i
 
 // ---- per-feature fits -------------------------------------------------------------------------------------------
 // Returns true when the feature is kept; coeff = coeffSel entry.
-__device__ __forceinline__ bool fit_line(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+__device__ __noinline__ bool fit_line(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
                                          float x0, float y0, float z0, float4& coeff) {
     float cx = 0, cy = 0, cz = 0;
 #pragma unroll
@@ -116,7 +121,12 @@ __device__ __forceinline__ bool fit_line(const float (&nx)[5], const float (&ny)
     }
     a11 /= 5; a12 /= 5; a13 /= 5; a22 /= 5; a23 /= 5; a33 /= 5;
     float w[3], v[9];
+#if B2_FIT_VARIANT == 1
     sym_eigen_jacobi3(a11, a12, a13, a22, a23, a33, w, v);
+#else
+    float m[9] = {a11, a12, a13, a12, a22, a23, a13, a23, a33};
+    sym_eigen_jacobi_c<3>(m, w, v);
+#endif
     if (!(w[0] > 3 * w[1])) return false;
     // two points on the line, 0.1 either side of the centroid (double literal: evaluated in double, narrowed)
     float x1 = cx + 0.1 * v[0], y1 = cy + 0.1 * v[1], z1 = cz + 0.1 * v[2];
@@ -135,10 +145,18 @@ __device__ __forceinline__ bool fit_line(const float (&nx)[5], const float (&ny)
     return s > 0.1;
 }
 
-__device__ __forceinline__ bool fit_plane(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+__device__ __noinline__ bool fit_plane(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
                                           float sx, float sy, float sz, float ox, float oy, float oz, float4& coeff) {
+#if B2_FIT_VARIANT == 1
     float pa, pb, pc, pd = 1;
     plane_lsq_5x3(nx, ny, nz, pa, pb, pc);
+#else
+    float q[15], x3[3];
+#pragma unroll
+    for (int j = 0; j < 5; j++) { q[j * 3 + 0] = nx[j]; q[j * 3 + 1] = ny[j]; q[j * 3 + 2] = nz[j]; }
+    plane_lsq_5x3_c(q, x3);
+    float pa = x3[0], pb = x3[1], pc = x3[2], pd = 1;
+#endif
     float ps = sqrtf(pa * pa + pb * pb + pc * pc);
     pa /= ps; pb /= ps; pc /= ps; pd /= ps;
 #pragma unroll
@@ -151,7 +169,7 @@ __device__ __forceinline__ bool fit_plane(const float (&nx)[5], const float (&ny
 }
 
 // ---- epilogue: normal equations -> pose update (single thread) ------------------------------------------------------
-__device__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, const S2MArgs& a, int scan) {
+__device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, const S2MArgs& a, int scan) {
     const int K = (int)(sums[27] + 0.5);
     s.n_sel = K;
     if (K < a.min_corr) {
@@ -213,7 +231,7 @@ __device__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, cons
     if (full_eigen) {
         float w[36], E[6], V[36], V2[36], Vi[36];
         for (int i = 0; i < 36; i++) w[i] = AtA[i];
-        sym_eigen_jacobi<6>(w, E, V);
+        sym_eigen_jacobi_c<6>(w, E, V);
         for (int i = 0; i < 36; i++) V2[i] = V[i];
         int deg = 0;
         for (int i = 5; i >= 0; i--) {
@@ -280,6 +298,8 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
     __shared__ double s_red[S2M_THREADS / 32][S2M_NPART];
     __shared__ double s_sum[S2M_NPART];
 
+    long long* prof = a.prof ? a.prof + ((size_t)scan * a.max_blocks + blockIdx.x) * 8 : nullptr;
+    if (prof && threadIdx.x == 0) { prof[0] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[6] = gt; }
     if (threadIdx.x < 12) s_xf[threadIdx.x] = st.xf[threadIdx.x];
     else if (threadIdx.x < 18) s_trig[threadIdx.x - 12] = st.trig[threadIdx.x - 12];
     __syncthreads();
@@ -319,6 +339,7 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
         }
     }
     __syncthreads();
+    if (prof && threadIdx.x == 0) prof[1] = clock64();
 
     // ---------------- phase 2: one thread per feature
     if (threadIdx.x < FPB) {
@@ -352,10 +373,9 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
                 dc[ff] = coeff; df[ff] = keep ? 1 : 0;
             }
         }
+        if (prof && threadIdx.x == 0) prof[4] = clock64();      // (overwritten by the last CTA's epilogue stamp)
         // Jacobian row (LMOptimization :1191-1222): camera-frame swap p' = (y, z, x), c' = (cy, cz, cx)
-        double acc[S2M_NPART];
-#pragma unroll
-        for (int q = 0; q < S2M_NPART; q++) acc[q] = 0.0;
+        float row[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // six columns of A and b
         if (keep) {
             const float srx = s_trig[0], crx = s_trig[1], sry = s_trig[2], cry = s_trig[3], srz = s_trig[4], crz = s_trig[5];
             const float px = oy, py = oz, pz = ox;
@@ -370,16 +390,21 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
             float arz = ((crz*srx*sry - cry*srz)*px + (-cry*crz-srx*sry*srz)*py)*cfx
                       + (crx*crz*px - crx*srz*py) * cfy
                       + ((sry*srz + cry*crz*srx)*px + (crz*sry-cry*srx*srz)*py)*cfz;
-            const double row[6] = {(double)arz, (double)arx, (double)ary, (double)cfz, (double)cfx, (double)cfy};
-            const double bb = (double)(-coeff.w);
+            row[0] = arz; row[1] = arx; row[2] = ary; row[3] = cfz; row[4] = cfx; row[5] = cfy; row[6] = -coeff.w;
+        }
+        // 21 + 6 products in fp64 (float x float is exact there) + the row count; the 28 xor-shuffle trees are independent,
+        // unrolled so their latencies overlap
+        __syncwarp();                    // the fits diverge per lane; reconverge before the full-mask shuffles
+        double acc[S2M_NPART];
+        {
             int q = 0;
 #pragma unroll
             for (int r = 0; r < 6; r++)
 #pragma unroll
-                for (int c = r; c < 6; c++) acc[q++] = row[r] * row[c];
+                for (int c = r; c < 6; c++) acc[q++] = (double)row[r] * (double)row[c];
 #pragma unroll
-            for (int r = 0; r < 6; r++) acc[21 + r] = row[r] * bb;
-            acc[27] = 1.0;
+            for (int r = 0; r < 6; r++) acc[21 + r] = (double)row[r] * (double)row[6];
+            acc[27] = keep ? 1.0 : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < S2M_NPART; q++) acc[q] = warp_sum(acc[q]);
@@ -389,6 +414,7 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
         }
     }
     __syncthreads();
+    if (prof && threadIdx.x == 0) prof[2] = clock64();
     if (threadIdx.x < S2M_NPART) {
         double v = 0.0;
 #pragma unroll
@@ -402,6 +428,7 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
         s_last = (t == (unsigned)(nblk - 1)) ? 1 : 0;
     }
     __syncthreads();
+    if (prof && threadIdx.x == 0) { prof[3] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[7] = gt; }
     if (!s_last) return;
 
     // ---------------- epilogue: the last CTA of this scan adds the partials in a fixed (slice, CTA) order
@@ -430,9 +457,11 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (prof) prof[4] = clock64();
         st.ticket = 0;
         const int iterCount = a.iter >= 0 ? a.iter : st.iters;
         lm_epilogue(st, s_sum, iterCount, a, scan);
+        if (prof) { prof[5] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[7] = gt; }
     }
 }
 
@@ -658,7 +687,32 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
     B2_CUDA(cudaMemcpyAsync(h->state.p, hs, sizeof(S2MState), cudaMemcpyHostToDevice, h->stream));
     S2MArgs a = make_args(h, iter, 0, true, nullptr, 0);
     a.want_matP = matP != nullptr;
+    const bool prof = getenv("B2_S2M_PROF") != nullptr;
+    if (prof) {
+        B2_CHECK(h->hist.reserve((size_t)h->max_blocks * 8 * sizeof(long long)));
+        B2_CUDA(cudaMemsetAsync(h->hist.p, 0, (size_t)h->max_blocks * 8 * sizeof(long long), h->stream));
+        a.prof = h->hist.as<long long>();
+    }
     launch_iteration(h, a, 1);
+    if (prof) {
+        std::vector<long long> t((size_t)h->max_blocks * 8);
+        B2_CUDA(cudaMemcpyAsync(t.data(), h->hist.p, t.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+        long long g0 = -1, g1 = 0; double p1 = 0, p2 = 0, p3 = 0, pf = 0; int nb = 0; double mx1 = 0, mx2 = 0;
+        for (int b = 0; b < h->max_blocks; b++) {
+            const long long* r = &t[(size_t)b * 8];
+            if (!r[0]) continue;
+            nb++;
+            p1 += (double)(r[1] - r[0]); p2 += (double)(r[2] - r[1]); p3 += (double)(r[3] - r[2]);
+            if (!r[5]) pf += (double)(r[4] - r[1]);
+            mx1 = std::max(mx1, (double)(r[1] - r[0])); mx2 = std::max(mx2, (double)(r[2] - r[1]));
+            if (g0 < 0 || r[6] < g0) g0 = r[6];
+            g1 = std::max(g1, r[7]);
+            if (r[5]) fprintf(stderr, "[b2 prof] last CTA %d: reduce %lld cyc, epilogue %lld cyc\n", b, r[4] - r[3], r[5] - r[4]);
+        }
+        fprintf(stderr, "[b2 prof] iter %d: %d CTAs, mean cycles phase1 %.0f (max %.0f) phase2 %.0f (max %.0f; fits %.0f) store+ticket %.0f; first start -> last end %.2f us\n",
+                iter, nb, p1 / nb, mx1, p2 / nb, mx2, pf / std::max(nb - 1, 1), p3 / nb, (double)(g1 - g0) * 1e-3);
+    }
     B2_CUDA(cudaGetLastError());
     B2_CUDA(cudaMemcpyAsync(hs, h->state.p, sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream));

@@ -360,4 +360,197 @@ B2_HD void plane_lsq_5x3(const float (&px)[5], const float (&py)[5], const float
     xa = x[0]; xb = x[1]; xc = x[2];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Compact variants: same operations in the same order as the routines above, written as rolled loops over small
+// per-thread arrays and never inlined. On the latency-critical path of one LM iteration a single warp walks this code
+// once per launch; measured on B200 that path is bound by instruction fetch (stall_no_inst, ~37 cycles per SASS
+// instruction for cold straight-line code), so code bytes matter more than register residency there.
+#if defined(__CUDACC__)
+#define B2_NOINLINE __device__ __noinline__
+#define B2_ROLL _Pragma("unroll 1")
+
+template <int N>
+B2_NOINLINE void sym_eigen_jacobi_c(float* a, float* w, float* v) {
+    int rmax[N], cmax[N];
+    B2_ROLL for (int i = 0; i < N * N; i++) v[i] = 0.f;
+    B2_ROLL for (int i = 0; i < N; i++) v[i * N + i] = 1.f;
+    B2_ROLL for (int k = 0; k < N; k++) {
+        w[k] = a[(N + 1) * k];
+        if (k < N - 1) {
+            int m = k + 1; float mv = fabsf(a[N * k + m]);
+            B2_ROLL for (int i = k + 2; i < N; i++) { float val = fabsf(a[N * k + i]); if (mv < val) { mv = val; m = i; } }
+            rmax[k] = m;
+        }
+        if (k > 0) {
+            int m = 0; float mv = fabsf(a[k]);
+            B2_ROLL for (int i = 1; i < k; i++) { float val = fabsf(a[N * i + k]); if (mv < val) { mv = val; m = i; } }
+            cmax[k] = m;
+        }
+    }
+    B2_ROLL for (int it = 0; it < N * N * 30; it++) {
+        int k = 0; float mv = fabsf(a[rmax[0]]);
+        B2_ROLL for (int i = 1; i < N - 1; i++) { float val = fabsf(a[N * i + rmax[i]]); if (mv < val) { mv = val; k = i; } }
+        int l = rmax[k];
+        B2_ROLL for (int i = 1; i < N; i++) { float val = fabsf(a[N * cmax[i] + i]); if (mv < val) { mv = val; k = cmax[i]; l = i; } }
+        float p = a[N * k + l];
+        if (fabsf(p) <= FLT_EPSILON) break;
+        float y = (float)((w[l] - w[k]) * 0.5);
+        float t = fabsf(y) + scaled_hypot(p, y);
+        float s = scaled_hypot(p, t);
+        float c = t / s;
+        s = p / s; t = (p / t) * p;
+        if (y < 0) { s = -s; t = -t; }
+        a[N * k + l] = 0;
+        w[k] -= t; w[l] += t;
+        // the three rotation ranges of the upper triangle, as one loop over i != k, l
+        B2_ROLL for (int i = 0; i < N; i++) {
+            if (i == k || i == l) continue;
+            float* x = (i < k) ? &a[N * i + k] : &a[N * k + i];
+            float* z = (i < l) ? &a[N * i + l] : &a[N * l + i];
+            float a0 = *x, b0 = *z;
+            *x = a0 * c - b0 * s; *z = a0 * s + b0 * c;
+        }
+        B2_ROLL for (int i = 0; i < N; i++) { float a0 = v[N * k + i], b0 = v[N * l + i]; v[N * k + i] = a0 * c - b0 * s; v[N * l + i] = a0 * s + b0 * c; }
+        B2_ROLL for (int j = 0; j < 2; j++) {
+            int idx = j == 0 ? k : l;
+            if (idx < N - 1) {
+                int m = idx + 1; float mm = fabsf(a[N * idx + m]);
+                B2_ROLL for (int i = idx + 2; i < N; i++) { float val = fabsf(a[N * idx + i]); if (mm < val) { mm = val; m = i; } }
+                rmax[idx] = m;
+            }
+            if (idx > 0) {
+                int m = 0; float mm = fabsf(a[idx]);
+                B2_ROLL for (int i = 1; i < idx; i++) { float val = fabsf(a[N * i + idx]); if (mm < val) { mm = val; m = i; } }
+                cmax[idx] = m;
+            }
+        }
+    }
+    B2_ROLL for (int k = 0; k < N - 1; k++) {
+        int m = k;
+        B2_ROLL for (int i = k + 1; i < N; i++) if (w[m] < w[i]) m = i;
+        if (k != m) {
+            float tw = w[m]; w[m] = w[k]; w[k] = tw;
+            B2_ROLL for (int i = 0; i < N; i++) { float tv = v[N * m + i]; v[N * m + i] = v[N * k + i]; v[N * k + i] = tv; }
+        }
+    }
+}
+
+template <int N>
+B2_NOINLINE int solve_householder_c(float* a, float* b) {
+    const float eps = FLT_EPSILON * 10;
+    float u[N], hf[N];
+    B2_ROLL for (int l = 0; l < N; l++) {
+        const int len = N - l;
+        float nrm = 0.f;
+        B2_ROLL for (int i = 0; i < len; i++) { u[i] = a[(l + i) * N + l]; nrm += u[i] * u[i]; }
+        float head = u[0];
+        u[0] = u[0] + ((u[0] >= 0.0f) ? 1 : -1) * sqrtf(nrm);
+        nrm = sqrtf(nrm + u[0] * u[0] - head * head);
+        B2_ROLL for (int i = 0; i < len; i++) u[i] /= nrm;
+        B2_ROLL for (int j = l; j < N; j++) {
+            float dot = 0.f;
+            B2_ROLL for (int i = l; i < N; i++) dot += u[i - l] * a[i * N + j];
+            B2_ROLL for (int i = l; i < N; i++) a[i * N + j] -= 2 * u[i - l] * dot;
+        }
+        hf[l] = u[0] * u[0];
+        B2_ROLL for (int i = 1; i < len; i++) a[(l + i) * N + l] = u[i] / u[0];
+    }
+    B2_ROLL for (int l = 0; l < N; l++) {
+        u[0] = 1.f;
+        B2_ROLL for (int j = 1; j < N - l; j++) u[j] = a[(j + l) * N + l];
+        float dot = 0.f;
+        B2_ROLL for (int i = l; i < N; i++) dot += u[i - l] * b[i];
+        B2_ROLL for (int i = l; i < N; i++) b[i] -= 2 * u[i - l] * dot * hf[l];
+    }
+    B2_ROLL for (int i = N - 1; i >= 0; i--) {
+        B2_ROLL for (int j = N - 1; j > i; j--) b[i] -= b[j] * a[i * N + j];
+        if (fabsf(a[i * N + i]) < eps) return 0;
+        b[i] /= a[i * N + i];
+    }
+    return 1;
+}
+
+// q: 5x3 row-major neighbour coordinates (destroyed); x: 3 outputs
+B2_NOINLINE void plane_lsq_5x3_c(float* q, float* x) {
+    float tau[3], nu[3], nd[3];
+    int perm[3];
+    B2_ROLL for (int k = 0; k < 3; k++) {
+        float s = 0.f;
+        B2_ROLL for (int i = 0; i < 5; i++) s += q[i * 3 + k] * q[i * 3 + k];
+        nd[k] = sqrtf(s); nu[k] = nd[k]; perm[k] = k;
+    }
+    float mx = fmaxf(nu[0], fmaxf(nu[1], nu[2]));
+    float th = mx * FLT_EPSILON;
+    const float thr_helper = (th * th) / 5.0f;
+    const float downdate_thr = sqrtf(FLT_EPSILON);
+    int rank = 3;
+    B2_ROLL for (int k = 0; k < 3; k++) {
+        int big = k; float bv = nu[k];
+        B2_ROLL for (int j = k + 1; j < 3; j++) if (nu[j] > bv) { bv = nu[j]; big = j; }
+        if (rank == 3 && bv * bv < thr_helper * (float)(5 - k)) rank = k;
+        if (big != k) {
+            B2_ROLL for (int i = 0; i < 5; i++) { float t = q[i * 3 + k]; q[i * 3 + k] = q[i * 3 + big]; q[i * 3 + big] = t; }
+            float t = nu[k]; nu[k] = nu[big]; nu[big] = t;
+            t = nd[k]; nd[k] = nd[big]; nd[big] = t;
+            int tp = perm[k]; perm[k] = perm[big]; perm[big] = tp;
+        }
+        float tail = 0.f;
+        B2_ROLL for (int i = k + 1; i < 5; i++) tail += q[i * 3 + k] * q[i * 3 + k];
+        float c0 = q[k * 3 + k], beta, tk;
+        if (tail <= FLT_MIN) {
+            tk = 0.f; beta = c0;
+            B2_ROLL for (int i = k + 1; i < 5; i++) q[i * 3 + k] = 0.f;
+        } else {
+            beta = sqrtf(c0 * c0 + tail);
+            if (c0 >= 0.f) beta = -beta;
+            float den = c0 - beta;
+            B2_ROLL for (int i = k + 1; i < 5; i++) q[i * 3 + k] = q[i * 3 + k] / den;
+            tk = (beta - c0) / beta;
+        }
+        tau[k] = tk; q[k * 3 + k] = beta;
+        B2_ROLL for (int j = k + 1; j < 3; j++) {
+            if (tk != 0.f) {
+                float t = 0.f;
+                B2_ROLL for (int i = k + 1; i < 5; i++) t += q[i * 3 + k] * q[i * 3 + j];
+                t += q[k * 3 + j];
+                q[k * 3 + j] -= tk * t;
+                B2_ROLL for (int i = k + 1; i < 5; i++) q[i * 3 + j] -= tk * q[i * 3 + k] * t;
+            }
+            if (nu[j] != 0.f) {
+                float t = fabsf(q[k * 3 + j]) / nu[j];
+                t = (1.f + t) * (1.f - t);
+                t = t < 0.f ? 0.f : t;
+                float r = nu[j] / nd[j];
+                float t2 = t * (r * r);
+                if (t2 <= downdate_thr) {
+                    float s = 0.f;
+                    B2_ROLL for (int i = k + 1; i < 5; i++) s += q[i * 3 + j] * q[i * 3 + j];
+                    nd[j] = sqrtf(s); nu[j] = nd[j];
+                } else {
+                    nu[j] *= sqrtf(t);
+                }
+            }
+        }
+    }
+    float c[5];
+    B2_ROLL for (int i = 0; i < 5; i++) c[i] = -1.f;
+    x[0] = 0.f; x[1] = 0.f; x[2] = 0.f;
+    B2_ROLL for (int k = 0; k < rank; k++) {
+        if (tau[k] == 0.f) continue;
+        float t = 0.f;
+        B2_ROLL for (int i = k + 1; i < 5; i++) t += q[i * 3 + k] * c[i];
+        t += c[k];
+        c[k] -= tau[k] * t;
+        B2_ROLL for (int i = k + 1; i < 5; i++) c[i] -= tau[k] * q[i * 3 + k] * t;
+    }
+    B2_ROLL for (int i = rank - 1; i >= 0; i--) {
+        float s = c[i];
+        B2_ROLL for (int j = i + 1; j < rank; j++) s -= q[i * 3 + j] * c[j];
+        c[i] = s / q[i * 3 + i];
+    }
+    B2_ROLL for (int i = 0; i < rank; i++) x[perm[i]] = c[i];
+}
+#endif  // __CUDACC__
+
 }  // namespace b2
