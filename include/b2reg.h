@@ -140,6 +140,43 @@ int  b2_s2m_solve_batch(b2_s2m_t h, float* poses, int max_iterations, int* iters
 int  b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches);
 
 /* ------------------------------------------------------------------------------------------------
+ * Per-scan front end — replaces, for one incoming scan,
+ *   ImageProjection::projectPointCloud + deskewPoint + cloudExtraction   liosam_ws/src/LIO-SAM/src/imageProjection.cpp:446-598
+ *   FeatureExtraction::calculateSmoothness + markOccludedPoints + extractFeatures   featureExtraction.cpp:81-238
+ * Input points are the reference's PointXYZIRT wire struct, 32 B: x@0 y@4 z@8 intensity@16 ring(u16)@20 time(f32)@24
+ * (imageProjection.cpp:4-15). The gyro table is the one imuDeskewInfo builds (:305-362): n_imu entries, the last one is
+ * imuPointerCur; n_imu <= 1 means imuAvailable == false (no deskew). deskew_flag = -1 disables deskew (:491).
+ * Outputs are the cloud_info arrays of msg/cloud_info.msg. Any output pointer may be NULL. */
+typedef struct b2_scan_s* b2_scan_t;
+typedef struct {
+    int   n_scan;                    /* 16    utility.h:197 */
+    int   horizon_scan;              /* 1800  utility.h:198 */
+    int   downsample_rate;           /* 1     utility.h:199 */
+    float lidar_min_range;           /* 1.0   utility.h:200 */
+    float lidar_max_range;           /* 1000  utility.h:201 */
+    float edge_threshold;            /* 1.0   config/params.yaml:57 (code default 0.1, utility.h:217) */
+    float surf_threshold;            /* 0.1   config/params.yaml:58 */
+    float odometry_surf_leaf_size;   /* 0.4   config/params.yaml:63 */
+} b2_scan_params;
+void b2_scan_default_params(b2_scan_params* p);
+int  b2_scan_create(b2_scan_t* out, const b2_scan_params* params /* NULL = defaults */);
+int  b2_scan_destroy(b2_scan_t h);
+/* extracted_xyzi / point_col_ind / point_range: capacity n_scan*horizon_scan entries; start/end_ring_index: n_scan;
+ * range_mat: n_scan*horizon_scan floats (FLT_MAX = empty); full_cloud: n_scan*horizon_scan*4 floats (NaN = empty). */
+int  b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n,
+                     const double* imu_time, const double* imu_rot_x, const double* imu_rot_y, const double* imu_rot_z, int n_imu,
+                     double time_scan_cur, int deskew_flag,
+                     size_t* n_extracted, float* extracted_xyzi, int32_t* point_col_ind, float* point_range,
+                     int32_t* start_ring_index, int32_t* end_ring_index, float* range_mat, float* full_cloud);
+/* Runs on the device-resident result of the last b2_scan_project. corner_xyzi: capacity n_scan*120 points
+ * (cornerCloud, push order), corner_index: their indices into the extracted cloud; surf_xyzi: capacity
+ * n_scan*horizon_scan points (surfaceCloud after the per-ring VoxelGrid); curvature / picked_after_mask / label:
+ * n_extracted entries (cloudCurvature, cloudNeighborPicked after markOccludedPoints, final cloudLabel). */
+int  b2_scan_extract_features(b2_scan_t h, size_t* n_corner, float* corner_xyzi, int32_t* corner_index,
+                              size_t* n_surf, float* surf_xyzi, float* curvature, int32_t* picked_after_mask, int32_t* label);
+int  b2_scan_last_gpu_ms(b2_scan_t h, float* ms);
+
+/* ------------------------------------------------------------------------------------------------
  * Rigid transform of a cloud — replaces mapOptimization::transformPointCloud (mapOptmization.cpp:286-305)
  * pose6 = (roll, pitch, yaw, x, y, z); matrix from pcl::getTransformation evaluated on the host in float. */
 int  b2_transform_cloud(const void* in, size_t in_stride, size_t n, const float pose6[6],

@@ -16,6 +16,12 @@ class B2Error(RuntimeError):
         self.code = code
 
 
+class ScanParams(C.Structure):
+    _fields_ = [("n_scan", C.c_int), ("horizon_scan", C.c_int), ("downsample_rate", C.c_int), ("lidar_min_range", C.c_float),
+                ("lidar_max_range", C.c_float), ("edge_threshold", C.c_float), ("surf_threshold", C.c_float),
+                ("odometry_surf_leaf_size", C.c_float)]
+
+
 class S2MParams(C.Structure):
     _fields_ = [("edge_feature_min_valid_num", C.c_int), ("surf_feature_min_valid_num", C.c_int),
                 ("max_iterations", C.c_int), ("min_correspondences", C.c_int), ("knn_max_dist", C.c_float),
@@ -30,6 +36,8 @@ SYMBOLS = [
     "b2_s2m_default_params", "b2_s2m_create", "b2_s2m_destroy", "b2_s2m_set_map", "b2_s2m_set_scan", "b2_s2m_iterate",
     "b2_s2m_solve", "b2_s2m_set_state", "b2_s2m_get_pass", "b2_s2m_get_normal_equations", "b2_s2m_set_scan_batch",
     "b2_s2m_solve_batch", "b2_s2m_last_gpu_ms", "b2_transform_cloud",
+    "b2_scan_default_params", "b2_scan_create", "b2_scan_destroy", "b2_scan_project", "b2_scan_extract_features",
+    "b2_scan_last_gpu_ms",
 ]
 
 
@@ -69,9 +77,16 @@ def lib():
     L.b2_s2m_solve_batch.argtypes = [vp, vp, i32, vp, vp, vp]
     L.b2_s2m_last_gpu_ms.argtypes = [vp, pf, pi]
     L.b2_transform_cloud.argtypes = [vp, sz, sz, vp, vp, sz]
+    L.b2_scan_default_params.argtypes = [C.POINTER(ScanParams)]
+    L.b2_scan_default_params.restype = None
+    L.b2_scan_create.argtypes = [C.POINTER(vp), C.POINTER(ScanParams)]
+    L.b2_scan_destroy.argtypes = [vp]
+    L.b2_scan_project.argtypes = [vp, vp, sz, vp, vp, vp, vp, i32, C.c_double, i32, C.POINTER(sz), vp, vp, vp, vp, vp, vp, vp]
+    L.b2_scan_extract_features.argtypes = [vp, C.POINTER(sz), vp, vp, C.POINTER(sz), vp, vp, vp, vp]
+    L.b2_scan_last_gpu_ms.argtypes = [vp, pf]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("b2_last_error", "b2_s2m_default_params", "b2_kernel_launch_count"):
+        if name not in ("b2_last_error", "b2_s2m_default_params", "b2_scan_default_params", "b2_kernel_launch_count"):
             fn.restype = C.c_int
     L.b2_kernel_launch_count.restype = C.c_ulonglong
     _LIB = L

@@ -1,0 +1,684 @@
+// LIO-SAM per-scan front end on the device: range-image projection with first-hit occupancy, IMU-rotation deskew,
+// per-ring compaction, curvature / occlusion masks, per-ring x 6-sector feature selection and the per-ring VoxelGrid of
+// the surf candidates.
+//
+// Replaces (liosam_ws/src/LIO-SAM/src):
+//   imageProjection.cpp   findRotation :446-471, deskewPoint :489-519, projectPointCloud :521-572, cloudExtraction :574-598
+//   featureExtraction.cpp calculateSmoothness :81-101, markOccludedPoints :103-139, extractFeatures :141-238
+//
+// Sequential semantics of the reference, made parallel:
+//   first hit wins a range-image cell      -> atomicMin of the point index per cell, then one thread per cell
+//   transStartInverse = first accepted pt  -> atomicMin over accepted indices, one thread builds the inverse
+//   ring compaction                        -> per-ring counts, then per-ring block scan at the ring's base offset
+//   sort + greedy suppression per sector   -> one CTA per ring (rings are independent, sectors of a ring are not):
+//                                             bitonic sort of (curvature, index) in shared memory, one lane walks the
+//                                             greedy passes with early exit, the CTA compacts the surf candidates
+//   per-ring VoxelGrid (featureExtraction.cpp:233-234) -> same CTA: bbox, PCL's index arithmetic, bitonic sort of
+//                                             (voxel, position), one thread per voxel sums in position order
+// Expression types follow SURVEY.md Appendix A; -fmad=false keeps every threshold operand at the reference's rounding.
+#include "b2_common.cuh"
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <algorithm>
+#include <vector>
+
+namespace b2 {
+
+struct ScanDev {
+    int n_scan, H, downsample;
+    float rmin, rmax, ang_res_x;
+    float edge_th, surf_th, surf_leaf;
+};
+
+__device__ __forceinline__ float sin_rnf(float a) { return (float)sin((double)a); }
+__device__ __forceinline__ float cos_rnf(float a) { return (float)cos((double)a); }
+
+// pcl::getTransformation(0,0,0,roll,pitch,yaw) rows (translation zero)
+__device__ __forceinline__ void rot_affine(float roll, float pitch, float yaw, float* t) {
+    float A = cos_rnf(yaw), B = sin_rnf(yaw), C = cos_rnf(pitch), D = sin_rnf(pitch), E = cos_rnf(roll), F = sin_rnf(roll);
+    float DE = D * E, DF = D * F;
+    t[0] = A * C;  t[1] = A * DF - B * E;  t[2]  = B * F + A * DE;  t[3]  = 0.f;
+    t[4] = B * C;  t[5] = A * E + B * DF;  t[6]  = B * DE - A * F;  t[7]  = 0.f;
+    t[8] = -D;     t[9] = C * F;           t[10] = C * E;           t[11] = 0.f;
+}
+
+// findRotation (imageProjection.cpp:446-471); cur = imuPointerCur (last valid index)
+__device__ __forceinline__ void find_rotation(const double* __restrict__ t, const double* __restrict__ rx, const double* __restrict__ ry,
+                                              const double* __restrict__ rz, int cur, double pointTime, float& ox, float& oy, float& oz) {
+    int front = 0;
+    while (front < cur) {
+        if (pointTime < t[front]) break;
+        ++front;
+    }
+    if (pointTime > t[front] || front == 0) {
+        ox = (float)rx[front]; oy = (float)ry[front]; oz = (float)rz[front];
+    } else {
+        const int back = front - 1;
+        const double ratioFront = (pointTime - t[back]) / (t[front] - t[back]);
+        const double ratioBack = (t[front] - pointTime) / (t[front] - t[back]);
+        ox = (float)(rx[front] * ratioFront + rx[back] * ratioBack);
+        oy = (float)(ry[front] * ratioFront + ry[back] * ratioBack);
+        oz = (float)(rz[front] * ratioFront + rz[back] * ratioBack);
+    }
+}
+
+struct RawPoint { float x, y, z, intensity, time; int ring; };
+__device__ __forceinline__ RawPoint load_raw(const unsigned char* __restrict__ raw, size_t i) {
+    const uint4* p = reinterpret_cast<const uint4*>(raw + i * 32);     // PointXYZIRT is 32 B, 16 B aligned
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    RawPoint r;
+    r.x = __uint_as_float(a.x); r.y = __uint_as_float(a.y); r.z = __uint_as_float(a.z);
+    r.intensity = __uint_as_float(b.x); r.ring = (int)(b.y & 0xffffu); r.time = __uint_as_float(b.z);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_scan_init(int* __restrict__ winner, int cells, int* __restrict__ first_idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cells) winner[i] = INT_MAX;
+    if (i == 0) *first_idx = INT_MAX;
+}
+
+// projectPointCloud, everything before the first-hit test: one thread per raw point
+__global__ void __launch_bounds__(256) k_scan_project(const unsigned char* __restrict__ raw, int n, ScanDev s, int* __restrict__ winner,
+                                                      int* __restrict__ first_idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cell = -1;
+    if (i < n) {
+        const RawPoint p = load_raw(raw, i);
+        const float range = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+        const int row = p.ring;
+        // the reference requires a dense cloud (:264-268); non-finite points are dropped here
+        bool ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && !(range < s.rmin || range > s.rmax) && row >= 0 && row < s.n_scan;
+        ok = ok && (row % s.downsample == 0);
+        if (ok) {
+            // atan2 on float arguments, then *180 in float, /M_PI in double, narrowed to float (:547)
+            const float at = (float)atan2((double)p.x, (double)p.y);
+            const float horizonAngle = (float)((double)(at * 180) / M_PI);
+            int col = (int)(-round(((double)horizonAngle - 90.0) / (double)s.ang_res_x) + (double)(s.H / 2));
+            if (col >= s.H) col -= s.H;
+            if (col >= 0 && col < s.H) cell = row * s.H + col;
+        }
+    }
+    if (cell >= 0) atomicMin(&winner[cell], i);
+    // the first accepted point in input order seeds transStartInverse: one atomic per warp
+    const int m = __reduce_min_sync(0xffffffffu, cell >= 0 ? i : INT_MAX);
+    if ((threadIdx.x & 31) == 0 && m != INT_MAX) atomicMin(first_idx, m);
+}
+
+__device__ __forceinline__ void affine_inverse(const float* a, float* o) {
+    const float m00 = a[0], m01 = a[1], m02 = a[2], m10 = a[4], m11 = a[5], m12 = a[6], m20 = a[8], m21 = a[9], m22 = a[10];
+    const float c00 = m11 * m22 - m12 * m21, c10 = m12 * m20 - m10 * m22, c20 = m10 * m21 - m11 * m20;
+    const float det = c00 * m00 + c10 * m01 + c20 * m02;
+    const float invdet = 1.0f / det;
+    o[0] = c00 * invdet; o[1] = (m02 * m21 - m01 * m22) * invdet; o[2]  = (m01 * m12 - m02 * m11) * invdet;
+    o[4] = c10 * invdet; o[5] = (m00 * m22 - m02 * m20) * invdet; o[6]  = (m02 * m10 - m00 * m12) * invdet;
+    o[8] = c20 * invdet; o[9] = (m01 * m20 - m00 * m21) * invdet; o[10] = (m00 * m11 - m01 * m10) * invdet;
+    o[3]  = -(o[0] * a[3] + o[1] * a[7] + o[2] * a[11]);
+    o[7]  = -(o[4] * a[3] + o[5] * a[7] + o[6] * a[11]);
+    o[11] = -(o[8] * a[3] + o[9] * a[7] + o[10] * a[11]);
+}
+
+// transStartInverse from the first accepted point (deskewPoint :502-506)
+__global__ void k_scan_start_inverse(const unsigned char* __restrict__ raw, const int* __restrict__ first_idx,
+                                     const double* __restrict__ it, const double* __restrict__ irx, const double* __restrict__ iry,
+                                     const double* __restrict__ irz, int cur, double t_scan, float* __restrict__ start_inv) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int i = *first_idx;
+    if (i == INT_MAX) return;
+    const RawPoint p = load_raw(raw, i);
+    float rx, ry, rz, tf[12];
+    find_rotation(it, irx, iry, irz, cur, t_scan + (double)p.time, rx, ry, rz);
+    rot_affine(rx, ry, rz, tf);
+    float inv[12];
+    affine_inverse(tf, inv);
+    for (int k = 0; k < 12; k++) start_inv[k] = inv[k];
+}
+
+// one thread per range-image cell: the cell's winner is deskewed and written (rest of projectPointCloud)
+__global__ void __launch_bounds__(256) k_scan_cells(const unsigned char* __restrict__ raw, const int* __restrict__ winner, int cells,
+                                                    const double* __restrict__ it, const double* __restrict__ irx, const double* __restrict__ iry,
+                                                    const double* __restrict__ irz, int cur, double t_scan, int deskew,
+                                                    const float* __restrict__ start_inv, float* __restrict__ range_mat, float4* __restrict__ full_cloud) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cells) return;
+    const int w = winner[c];
+    if (w == INT_MAX) {
+        range_mat[c] = FLT_MAX;
+        const float qn = __int_as_float(0x7fc00000);
+        full_cloud[c] = make_float4(qn, qn, qn, qn);
+        return;
+    }
+    const RawPoint p = load_raw(raw, w);
+    const float range = sqrtf(p.x * p.x + p.y * p.y + p.z * p.z);
+    float nx = p.x, ny = p.y, nz = p.z;
+    if (deskew) {
+        float rx, ry, rz, tf[12], bt[12];
+        find_rotation(it, irx, iry, irz, cur, t_scan + (double)p.time, rx, ry, rz);
+        rot_affine(rx, ry, rz, tf);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+                bt[r * 4 + q] = start_inv[r * 4 + 0] * tf[0 * 4 + q] + start_inv[r * 4 + 1] * tf[1 * 4 + q] + start_inv[r * 4 + 2] * tf[2 * 4 + q];
+            bt[r * 4 + 3] = start_inv[r * 4 + 0] * tf[3] + start_inv[r * 4 + 1] * tf[7] + start_inv[r * 4 + 2] * tf[11] + start_inv[r * 4 + 3];
+        }
+        nx = bt[0] * p.x + bt[1] * p.y + bt[2] * p.z + bt[3];
+        ny = bt[4] * p.x + bt[5] * p.y + bt[6] * p.z + bt[7];
+        nz = bt[8] * p.x + bt[9] * p.y + bt[10] * p.z + bt[11];
+    }
+    range_mat[c] = range;
+    full_cloud[c] = make_float4(nx, ny, nz, p.intensity);
+}
+
+// cloudExtraction, pass 1: occupied cells per ring
+__global__ void __launch_bounds__(256) k_scan_ring_count(const int* __restrict__ winner, int H, int* __restrict__ ring_count) {
+    __shared__ int ws[8];
+    const int ring = blockIdx.x;
+    int c = 0;
+    for (int j = threadIdx.x; j < H; j += blockDim.x) c += winner[ring * H + j] != INT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += ws[w]; ring_count[ring] = t; }
+}
+
+// cloudExtraction, pass 2: ordered compaction of each ring at its base offset
+__global__ void __launch_bounds__(256) k_scan_ring_compact(const int* __restrict__ winner, const float* __restrict__ range_mat,
+                                                           const float4* __restrict__ full_cloud, int H, int n_scan, const int* __restrict__ ring_count,
+                                                           float4* __restrict__ extracted, int* __restrict__ col_ind, float* __restrict__ pt_range,
+                                                           int* __restrict__ start_ring, int* __restrict__ end_ring, int* __restrict__ total) {
+    __shared__ int ws[9];
+    __shared__ int s_base;
+    const int ring = blockIdx.x;
+    if (threadIdx.x == 0) {
+        int b = 0;
+        for (int r = 0; r < ring; r++) b += ring_count[r];
+        s_base = b;
+        start_ring[ring] = b - 1 + 5;
+        end_ring[ring] = b + ring_count[ring] - 1 - 5;
+        if (ring == n_scan - 1) *total = b + ring_count[ring];
+    }
+    __syncthreads();
+    int run = s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j0 = 0; j0 < H; j0 += 256) {
+        const int j = j0 + threadIdx.x;
+        const int occ = (j < H) && winner[ring * H + j] != INT_MAX;
+        const unsigned bal = __ballot_sync(0xffffffffu, occ);
+        if (lane == 0) ws[warp] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) { int c = ws[w]; ws[w] = t; t += c; } ws[8] = t; }
+        __syncthreads();
+        if (occ) {
+            const int pos = run + ws[warp] + __popc(bal & ((1u << lane) - 1u));
+            const int cell = ring * H + j;
+            col_ind[pos] = j;
+            pt_range[pos] = range_mat[cell];
+            extracted[pos] = full_cloud[cell];
+        }
+        run += ws[8];
+        __syncthreads();
+    }
+}
+
+// calculateSmoothness + the zeroing the oracle defines for the never-written slots
+__global__ void __launch_bounds__(256) k_scan_curvature(const float* __restrict__ r, const int* __restrict__ total, float* __restrict__ curv,
+                                                        int* __restrict__ picked, int* __restrict__ label) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int M = *total;
+    if (i >= M) return;
+    float cv = 0.f;
+    if (i >= 5 && i < M - 5) {
+        float d = r[i - 5] + r[i - 4] + r[i - 3] + r[i - 2] + r[i - 1] - r[i] * 10 + r[i + 1] + r[i + 2] + r[i + 3] + r[i + 4] + r[i + 5];
+        cv = d * d;
+    }
+    curv[i] = cv; picked[i] = 0; label[i] = 0;
+}
+
+// markOccludedPoints: every mark is a store of 1, so the parallel order does not matter
+__global__ void __launch_bounds__(256) k_scan_masks(const float* __restrict__ r, const int* __restrict__ col, const int* __restrict__ total,
+                                                    int* __restrict__ picked) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 5;
+    const int M = *total;
+    if (i >= M - 6) return;
+    const float depth1 = r[i], depth2 = r[i + 1];
+    const int columnDiff = abs(col[i + 1] - col[i]);
+    if (columnDiff < 10) {
+        if ((double)(depth1 - depth2) > 0.3) {
+#pragma unroll
+            for (int k = 0; k <= 5; k++) picked[i - k] = 1;
+        } else if ((double)(depth2 - depth1) > 0.3) {
+#pragma unroll
+            for (int k = 1; k <= 6; k++) picked[i + k] = 1;
+        }
+    }
+    const float diff1 = fabsf(r[i - 1] - r[i]);
+    const float diff2 = fabsf(r[i + 1] - r[i]);
+    if ((double)diff1 > 0.02 * (double)r[i] && (double)diff2 > 0.02 * (double)r[i]) picked[i] = 1;
+}
+
+// ---- shared-memory bitonic sort of 64-bit keys, ascending; P is a power of two, all threads of the CTA call it
+__device__ void bitonic_sort_u64(unsigned long long* k, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void suppress(int ind, int M, const int* __restrict__ col, int* __restrict__ picked) {
+    for (int l = 1; l <= 5; l++) {
+        if (ind + l >= M) break;
+        if (abs(col[ind + l] - col[ind + l - 1]) > 10) break;
+        picked[ind + l] = 1;
+    }
+    for (int l = -1; l >= -5; l--) {
+        if (ind + l < 0) break;
+        if (abs(col[ind + l] - col[ind + l + 1]) > 10) break;
+        picked[ind + l] = 1;
+    }
+}
+
+// extractFeatures: one CTA per ring. Dynamic shared memory: keys[P] (u64), pts[P] (float4) with P = pow2 >= H.
+// Per-ring outputs go to fixed-capacity slots (corner: 120 per ring, surf: H per ring) and are concatenated afterwards.
+__global__ void __launch_bounds__(256) k_scan_features(const float4* __restrict__ extracted, const int* __restrict__ col, const int* __restrict__ total,
+                                                       const int* __restrict__ start_ring, const int* __restrict__ end_ring, ScanDev s, int P,
+                                                       const float* __restrict__ curv, int* __restrict__ picked, int* __restrict__ label,
+                                                       int* __restrict__ corner_idx, int* __restrict__ corner_cnt,
+                                                       int* __restrict__ surf_idx, int* __restrict__ surf_cnt,
+                                                       float4* __restrict__ surf_ds, int* __restrict__ surf_ds_cnt) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+    float4* spts = reinterpret_cast<float4*>(smem + (size_t)P * 8);
+    __shared__ int s_ncorner, s_nsurf, s_scan[9];
+    __shared__ float s_mn[3], s_mx[3];
+    __shared__ int s_geom[8];
+    __shared__ float s_inv;
+    const int ring = blockIdx.x;
+    const int M = *total;
+    const int sri = start_ring[ring], eri = end_ring[ring];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_ncorner = 0; s_nsurf = 0; }
+    __syncthreads();
+    for (int j = 0; j < 6; j++) {
+        const int sp = (sri * (6 - j) + eri * j) / 6;
+        const int ep = (sri * (5 - j) + eri * (j + 1)) / 6 - 1;
+        if (sp >= ep) continue;                                   // uniform for the CTA
+        const int n = ep - sp;                                    // [sp, ep) is sorted, ep itself is not (:162)
+        int Q = 1; while (Q < n) Q <<= 1;
+        for (int t = threadIdx.x; t < Q; t += blockDim.x) {
+            unsigned long long key = ~0ull;
+            if (t < n) {
+                const int k = sp + t;
+                const float v = (k >= 5 && k < M - 5) ? curv[k] : 0.f;      // oracle definition outside [5, M-5)
+                key = ((unsigned long long)__float_as_uint(v) << 32) | (unsigned)k;
+            }
+            keys[t] = key;
+        }
+        bitonic_sort_u64(keys, Q);
+        if (threadIdx.x == 0) {
+            // descending: at most 20 corners with curvature > edgeThreshold (:165-195). The sorted part is descending
+            // in curvature, so the first candidate at or below the threshold ends the walk (nothing later can pass).
+            int largestPickedNum = 0;
+            int nc = s_ncorner;
+            for (int k = ep; k >= sp; k--) {
+                const int ind = (k == ep) ? ep : (int)(unsigned)keys[k - sp];
+                const float cv = curv[ind];
+                if (k != ep && !(cv > s.edge_th)) break;
+                if (picked[ind] == 0 && cv > s.edge_th) {
+                    largestPickedNum++;
+                    if (largestPickedNum <= 20) { label[ind] = 1; corner_idx[ring * 120 + nc++] = ind; }
+                    else break;
+                    picked[ind] = 1;
+                    suppress(ind, M, col, picked);
+                }
+            }
+            s_ncorner = nc;
+            // ascending: surf labels (:197-225); ep is visited last
+            for (int k = sp; k <= ep; k++) {
+                const int ind = (k == ep) ? ep : (int)(unsigned)keys[k - sp];
+                const float cv = curv[ind];
+                if (k != ep && !(cv < s.surf_th)) { k = ep - 1; continue; }     // jump to the unsorted tail element
+                if (picked[ind] == 0 && cv < s.surf_th) {
+                    label[ind] = -1;
+                    picked[ind] = 1;
+                    suppress(ind, M, col, picked);
+                }
+            }
+        }
+        __syncthreads();
+        // surf candidates of the sector, in index order (:227-232)
+        int run = s_nsurf;
+        for (int k0 = sp; k0 <= ep; k0 += 256) {
+            const int k = k0 + threadIdx.x;
+            const int f = (k <= ep) && label[k] <= 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, f);
+            if (lane == 0) s_scan[warp] = __popc(bal);
+            __syncthreads();
+            if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) { int c = s_scan[w]; s_scan[w] = t; t += c; } s_scan[8] = t; }
+            __syncthreads();
+            if (f) surf_idx[ring * s.H + run + s_scan[warp] + __popc(bal & ((1u << lane) - 1u))] = k;
+            run += s_scan[8];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) s_nsurf = run;
+        __syncthreads();
+    }
+    const int ns = s_nsurf;
+    if (threadIdx.x == 0) { corner_cnt[ring] = s_ncorner; surf_cnt[ring] = ns; }
+    // ---------------- per-ring VoxelGrid of the surf candidates (downSizeFilter, :233-236)
+    if (ns == 0) { if (threadIdx.x == 0) surf_ds_cnt[ring] = 0; return; }
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int t = threadIdx.x; t < ns; t += blockDim.x) {
+        const float4 p = extracted[surf_idx[ring * s.H + t]];
+        spts[t] = p;
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+    __shared__ float s_red[8][6];
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+            mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+        }
+    if (lane == 0) { for (int d = 0; d < 3; d++) { s_red[warp][d] = mn[d]; s_red[warp][3 + d] = mx[d]; } }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int d = 0; d < 3; d++) {
+            float a = s_red[0][d], b = s_red[0][3 + d];
+            for (int w = 1; w < 8; w++) { a = fminf(a, s_red[w][d]); b = fmaxf(b, s_red[w][3 + d]); }
+            s_mn[d] = a; s_mx[d] = b;
+        }
+        const float inv = 1.0f / s.surf_leaf;
+        s_inv = inv;
+        long long dx = (long long)((s_mx[0] - s_mn[0]) * inv) + 1, dy = (long long)((s_mx[1] - s_mn[1]) * inv) + 1, dz = (long long)((s_mx[2] - s_mn[2]) * inv) + 1;
+        s_geom[6] = (dx * dy * dz > (long long)INT_MAX) ? 1 : 0;             // PCL refuses: output = input
+        int minb[3], maxb[3];
+        for (int d = 0; d < 3; d++) { minb[d] = (int)floorf(s_mn[d] * inv); maxb[d] = (int)floorf(s_mx[d] * inv); s_geom[d] = minb[d]; }
+        s_geom[3] = 1; s_geom[4] = maxb[0] - minb[0] + 1; s_geom[5] = (maxb[0] - minb[0] + 1) * (maxb[1] - minb[1] + 1);
+    }
+    __syncthreads();
+    if (s_geom[6]) {
+        for (int t = threadIdx.x; t < ns; t += blockDim.x) surf_ds[ring * s.H + t] = spts[t];
+        if (threadIdx.x == 0) surf_ds_cnt[ring] = ns;
+        return;
+    }
+    int Q = 1; while (Q < ns) Q <<= 1;
+    for (int t = threadIdx.x; t < Q; t += blockDim.x) {
+        unsigned long long key = ~0ull;
+        if (t < ns) {
+            const float4 p = spts[t];
+            const int i0 = (int)(floorf(p.x * s_inv) - (float)s_geom[0]);
+            const int i1 = (int)(floorf(p.y * s_inv) - (float)s_geom[1]);
+            const int i2 = (int)(floorf(p.z * s_inv) - (float)s_geom[2]);
+            const int idx = i0 * s_geom[3] + i1 * s_geom[4] + i2 * s_geom[5];
+            key = ((unsigned long long)(unsigned)idx << 32) | (unsigned)t;
+        }
+        keys[t] = key;
+    }
+    bitonic_sort_u64(keys, Q);
+    // one thread per run head: centroid in position order, rank = number of heads before it
+    int run = 0;
+    for (int t0 = 0; t0 < ns; t0 += 256) {
+        const int t = t0 + threadIdx.x;
+        const int head = (t < ns) && (t == 0 || (unsigned)(keys[t] >> 32) != (unsigned)(keys[t - 1] >> 32));
+        const unsigned bal = __ballot_sync(0xffffffffu, head);
+        if (lane == 0) s_scan[warp] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) { int q = 0; for (int w = 0; w < 8; w++) { int c = s_scan[w]; s_scan[w] = q; q += c; } s_scan[8] = q; }
+        __syncthreads();
+        if (head) {
+            const unsigned vox = (unsigned)(keys[t] >> 32);
+            float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+            int e = t;
+            for (; e < ns && (unsigned)(keys[e] >> 32) == vox; e++) {
+                const float4 p = spts[(unsigned)keys[e]];
+                sx += p.x; sy += p.y; sz += p.z; si += p.w;
+            }
+            const float cnt = (float)(e - t);
+            surf_ds[ring * s.H + run + s_scan[warp] + __popc(bal & ((1u << lane) - 1u))] = make_float4(sx / cnt, sy / cnt, sz / cnt, si / cnt);
+        }
+        run += s_scan[8];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) surf_ds_cnt[ring] = run;
+}
+
+// concatenate the per-ring slots in ring order
+__global__ void __launch_bounds__(256) k_scan_gather_out(const float4* __restrict__ extracted, int n_scan, int H,
+                                                         const int* __restrict__ corner_idx, const int* __restrict__ corner_cnt,
+                                                         const float4* __restrict__ surf_ds, const int* __restrict__ surf_ds_cnt,
+                                                         float4* __restrict__ corner_out, int* __restrict__ corner_idx_out, float4* __restrict__ surf_out,
+                                                         int* __restrict__ totals) {
+    const int ring = blockIdx.x;
+    __shared__ int s_cb, s_sb;
+    if (threadIdx.x == 0) {
+        int cb = 0, sb = 0;
+        for (int r = 0; r < ring; r++) { cb += corner_cnt[r]; sb += surf_ds_cnt[r]; }
+        s_cb = cb; s_sb = sb;
+        if (ring == n_scan - 1) { totals[0] = cb + corner_cnt[ring]; totals[1] = sb + surf_ds_cnt[ring]; }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < corner_cnt[ring]; t += blockDim.x) {
+        const int ind = corner_idx[ring * 120 + t];
+        corner_out[s_cb + t] = extracted[ind];
+        corner_idx_out[s_cb + t] = ind;
+    }
+    for (int t = threadIdx.x; t < surf_ds_cnt[ring]; t += blockDim.x) surf_out[s_sb + t] = surf_ds[ring * H + t];
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_scan_s {
+    b2_scan_params prm;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf raw, imu, winner, small, range_mat, full_cloud, extracted, col_ind, pt_range, rings;
+    DevBuf curv, picked, label, corner_idx, surf_idx, surf_ds, corner_out, corner_idx_out, surf_out;
+    int n_raw = 0, M = 0;
+    bool projected = false;
+    float last_ms = 0.f;
+};
+
+extern "C" {
+
+void b2_scan_default_params(b2_scan_params* p) {
+    if (!p) return;
+    p->n_scan = 16; p->horizon_scan = 1800; p->downsample_rate = 1;          // utility.h:197-199
+    p->lidar_min_range = 1.0f; p->lidar_max_range = 1000.0f;                 // utility.h:200-201
+    p->edge_threshold = 1.0f; p->surf_threshold = 0.1f;                      // config/params.yaml:57-58
+    p->odometry_surf_leaf_size = 0.4f;                                       // config/params.yaml:63
+}
+
+int b2_scan_create(b2_scan_t* out, const b2_scan_params* params) {
+    if (!out) { set_error("b2_scan_create: null out"); return B2_ERR_ARG; }
+    b2_scan_s* h = new b2_scan_s();
+    if (params) h->prm = *params; else b2_scan_default_params(&h->prm);
+    const b2_scan_params& p = h->prm;
+    if (p.n_scan < 1 || p.n_scan > 1024 || p.horizon_scan < 16 || p.horizon_scan > 8192 || p.downsample_rate < 1 || !(p.odometry_surf_leaf_size > 0.f)) {
+        delete h; set_error("b2_scan_create: bad params"); return B2_ERR_ARG;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) { set_error("b2_scan_create: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
+    *out = h;
+    return B2_OK;
+}
+
+int b2_scan_destroy(b2_scan_t h) {
+    if (!h) return B2_ERR_ARG;
+    DevBuf* bufs[] = {&h->raw, &h->imu, &h->winner, &h->small, &h->range_mat, &h->full_cloud, &h->extracted, &h->col_ind, &h->pt_range, &h->rings,
+                      &h->curv, &h->picked, &h->label, &h->corner_idx, &h->surf_idx, &h->surf_ds, &h->corner_out, &h->corner_idx_out, &h->surf_out};
+    for (DevBuf* b : bufs) b->release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B2_OK;
+}
+
+static ScanDev scan_dev(const b2_scan_params& p) {
+    ScanDev s;
+    s.n_scan = p.n_scan; s.H = p.horizon_scan; s.downsample = p.downsample_rate;
+    s.rmin = p.lidar_min_range; s.rmax = p.lidar_max_range;
+    s.ang_res_x = (float)(360.0 / (double)(float)p.horizon_scan);           // static float ang_res_x = 360.0/float(Horizon_SCAN)
+    s.edge_th = p.edge_threshold; s.surf_th = p.surf_threshold; s.surf_leaf = p.odometry_surf_leaf_size;
+    return s;
+}
+
+int b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n, const double* imu_time, const double* imu_rot_x, const double* imu_rot_y,
+                    const double* imu_rot_z, int n_imu, double time_scan_cur, int deskew_flag,
+                    size_t* n_extracted, float* extracted_xyzi, int32_t* point_col_ind, float* point_range,
+                    int32_t* start_ring_index, int32_t* end_ring_index, float* range_mat, float* full_cloud) {
+    if (!h || (n && !xyzirt) || !n_extracted || n > 0x7ffffff0ull || (n_imu > 0 && (!imu_time || !imu_rot_x || !imu_rot_y || !imu_rot_z))) {
+        set_error("b2_scan_project: bad argument"); return B2_ERR_ARG;
+    }
+    const ScanDev s = scan_dev(h->prm);
+    const int cells = s.n_scan * s.H;
+    cudaStream_t st = h->stream;
+    B2_CHECK(h->raw.reserve(std::max<size_t>(n, 1) * 32));
+    B2_CHECK(h->winner.reserve((size_t)cells * 4));
+    B2_CHECK(h->small.reserve(256));
+    B2_CHECK(h->range_mat.reserve((size_t)cells * 4));
+    B2_CHECK(h->full_cloud.reserve((size_t)cells * 16));
+    B2_CHECK(h->extracted.reserve((size_t)cells * 16));
+    B2_CHECK(h->col_ind.reserve((size_t)cells * 4));
+    B2_CHECK(h->pt_range.reserve((size_t)cells * 4));
+    B2_CHECK(h->rings.reserve((size_t)s.n_scan * 3 * 4 + 64));
+    const int ni = std::max(n_imu, 1);
+    B2_CHECK(h->imu.reserve((size_t)ni * 4 * 8));
+    double* d_imu = h->imu.as<double>();
+    int* first_idx = h->small.as<int>();
+    int* total = first_idx + 1;
+    float* start_inv = reinterpret_cast<float*>(first_idx + 4);
+    int* ring_count = h->rings.as<int>();
+    int* d_start = ring_count + s.n_scan;
+    int* d_end = d_start + s.n_scan;
+    B2_CUDA(cudaEventRecord(h->ev0, st));
+    if (n) B2_CUDA(cudaMemcpyAsync(h->raw.p, xyzirt, n * 32, cudaMemcpyHostToDevice, st));
+    if (n_imu > 0) {
+        B2_CUDA(cudaMemcpyAsync(d_imu, imu_time, (size_t)n_imu * 8, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(d_imu + ni, imu_rot_x, (size_t)n_imu * 8, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(d_imu + 2 * ni, imu_rot_y, (size_t)n_imu * 8, cudaMemcpyHostToDevice, st));
+        B2_CUDA(cudaMemcpyAsync(d_imu + 3 * ni, imu_rot_z, (size_t)n_imu * 8, cudaMemcpyHostToDevice, st));
+    }
+    const int cur = n_imu - 1;                                   // imuPointerCur after the decrement of :355
+    const int deskew = (deskew_flag != -1 && cur > 0) ? 1 : 0;  // deskewFlag == -1 || imuAvailable == false -> untouched point
+    k_scan_init<<<(cells + 255) / 256, 256, 0, st>>>(h->winner.as<int>(), cells, first_idx); count_launch();
+    if (n) { k_scan_project<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->raw.as<unsigned char>(), (int)n, s, h->winner.as<int>(), first_idx); count_launch(); }
+    if (deskew) {
+        k_scan_start_inverse<<<1, 32, 0, st>>>(h->raw.as<unsigned char>(), first_idx, d_imu, d_imu + ni, d_imu + 2 * ni, d_imu + 3 * ni, cur, time_scan_cur, start_inv);
+        count_launch();
+    }
+    k_scan_cells<<<(cells + 255) / 256, 256, 0, st>>>(h->raw.as<unsigned char>(), h->winner.as<int>(), cells, d_imu, d_imu + ni, d_imu + 2 * ni, d_imu + 3 * ni,
+                                                      cur, time_scan_cur, deskew, start_inv, h->range_mat.as<float>(), h->full_cloud.as<float4>()); count_launch();
+    k_scan_ring_count<<<s.n_scan, 256, 0, st>>>(h->winner.as<int>(), s.H, ring_count); count_launch();
+    k_scan_ring_compact<<<s.n_scan, 256, 0, st>>>(h->winner.as<int>(), h->range_mat.as<float>(), h->full_cloud.as<float4>(), s.H, s.n_scan, ring_count,
+                                                  h->extracted.as<float4>(), h->col_ind.as<int>(), h->pt_range.as<float>(), d_start, d_end, total); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaEventRecord(h->ev1, st));
+    int M = 0;
+    B2_CUDA(cudaMemcpyAsync(&M, total, 4, cudaMemcpyDeviceToHost, st));
+    if (start_ring_index) B2_CUDA(cudaMemcpyAsync(start_ring_index, d_start, (size_t)s.n_scan * 4, cudaMemcpyDeviceToHost, st));
+    if (end_ring_index) B2_CUDA(cudaMemcpyAsync(end_ring_index, d_end, (size_t)s.n_scan * 4, cudaMemcpyDeviceToHost, st));
+    if (range_mat) B2_CUDA(cudaMemcpyAsync(range_mat, h->range_mat.p, (size_t)cells * 4, cudaMemcpyDeviceToHost, st));
+    if (full_cloud) B2_CUDA(cudaMemcpyAsync(full_cloud, h->full_cloud.p, (size_t)cells * 16, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (M) {
+        if (extracted_xyzi) B2_CUDA(cudaMemcpyAsync(extracted_xyzi, h->extracted.p, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+        if (point_col_ind) B2_CUDA(cudaMemcpyAsync(point_col_ind, h->col_ind.p, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+        if (point_range) B2_CUDA(cudaMemcpyAsync(point_range, h->pt_range.p, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+        B2_CUDA(cudaStreamSynchronize(st));
+    }
+    B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->n_raw = (int)n; h->M = M; h->projected = true;
+    *n_extracted = (size_t)M;
+    return B2_OK;
+}
+
+int b2_scan_extract_features(b2_scan_t h, size_t* n_corner, float* corner_xyzi, int32_t* corner_index, size_t* n_surf, float* surf_xyzi,
+                             float* curvature, int32_t* picked_after_mask, int32_t* label) {
+    if (!h || !n_corner || !n_surf) { set_error("b2_scan_extract_features: bad argument"); return B2_ERR_ARG; }
+    if (!h->projected) { set_error("b2_scan_extract_features: call b2_scan_project first"); return B2_ERR_STATE; }
+    const ScanDev s = scan_dev(h->prm);
+    const int cells = s.n_scan * s.H;
+    const int M = h->M;
+    cudaStream_t st = h->stream;
+    *n_corner = 0; *n_surf = 0;
+    B2_CHECK(h->curv.reserve((size_t)cells * 4)); B2_CHECK(h->picked.reserve((size_t)cells * 4 * 2)); B2_CHECK(h->label.reserve((size_t)cells * 4));
+    B2_CHECK(h->corner_idx.reserve((size_t)s.n_scan * 120 * 4 + (size_t)s.n_scan * 3 * 4 + 64));
+    B2_CHECK(h->surf_idx.reserve((size_t)cells * 4)); B2_CHECK(h->surf_ds.reserve((size_t)cells * 16));
+    B2_CHECK(h->corner_out.reserve((size_t)s.n_scan * 120 * 16)); B2_CHECK(h->corner_idx_out.reserve((size_t)s.n_scan * 120 * 4));
+    B2_CHECK(h->surf_out.reserve((size_t)cells * 16));
+    int* first_idx = h->small.as<int>();
+    int* total = first_idx + 1;
+    int* totals_out = first_idx + 32;
+    int* ring_count = h->rings.as<int>();
+    int* d_start = ring_count + s.n_scan;
+    int* d_end = d_start + s.n_scan;
+    int* corner_cnt = h->corner_idx.as<int>() + (size_t)s.n_scan * 120;
+    int* surf_cnt = corner_cnt + s.n_scan;
+    int* surf_ds_cnt = surf_cnt + s.n_scan;
+    int* picked = h->picked.as<int>();
+    int* picked_mask_copy = picked + cells;
+    B2_CUDA(cudaEventRecord(h->ev0, st));
+    if (M > 0) {
+        k_scan_curvature<<<(M + 255) / 256, 256, 0, st>>>(h->pt_range.as<float>(), total, h->curv.as<float>(), picked, h->label.as<int>()); count_launch();
+        if (M > 11) { k_scan_masks<<<(M - 11 + 255) / 256, 256, 0, st>>>(h->pt_range.as<float>(), h->col_ind.as<int>(), total, picked); count_launch(); }
+        if (picked_after_mask) B2_CUDA(cudaMemcpyAsync(picked_mask_copy, picked, (size_t)M * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    int P = 1; while (P < s.H) P <<= 1;
+    const size_t smem = (size_t)P * (8 + 16);
+    static bool attr_set = false;
+    if (!attr_set) { B2_CUDA(cudaFuncSetAttribute(k_scan_features, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    if (smem > 200 * 1024) { set_error("b2_scan_extract_features: Horizon_SCAN too large for the per-ring kernel"); return B2_ERR_TOO_LARGE; }
+    k_scan_features<<<s.n_scan, 256, smem, st>>>(h->extracted.as<float4>(), h->col_ind.as<int>(), total, d_start, d_end, s, P, h->curv.as<float>(), picked,
+                                                 h->label.as<int>(), h->corner_idx.as<int>(), corner_cnt, h->surf_idx.as<int>(), surf_cnt,
+                                                 h->surf_ds.as<float4>(), surf_ds_cnt); count_launch();
+    k_scan_gather_out<<<s.n_scan, 256, 0, st>>>(h->extracted.as<float4>(), s.n_scan, s.H, h->corner_idx.as<int>(), corner_cnt, h->surf_ds.as<float4>(), surf_ds_cnt,
+                                                h->corner_out.as<float4>(), h->corner_idx_out.as<int>(), h->surf_out.as<float4>(), totals_out); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaEventRecord(h->ev1, st));
+    int tot[2] = {0, 0};
+    B2_CUDA(cudaMemcpyAsync(tot, totals_out, 8, cudaMemcpyDeviceToHost, st));
+    if (M > 0) {
+        if (curvature) B2_CUDA(cudaMemcpyAsync(curvature, h->curv.p, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+        if (picked_after_mask) B2_CUDA(cudaMemcpyAsync(picked_after_mask, picked_mask_copy, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+        if (label) B2_CUDA(cudaMemcpyAsync(label, h->label.p, (size_t)M * 4, cudaMemcpyDeviceToHost, st));
+    }
+    B2_CUDA(cudaStreamSynchronize(st));
+    if (tot[0]) {
+        if (corner_xyzi) B2_CUDA(cudaMemcpyAsync(corner_xyzi, h->corner_out.p, (size_t)tot[0] * 16, cudaMemcpyDeviceToHost, st));
+        if (corner_index) B2_CUDA(cudaMemcpyAsync(corner_index, h->corner_idx_out.p, (size_t)tot[0] * 4, cudaMemcpyDeviceToHost, st));
+    }
+    if (tot[1] && surf_xyzi) B2_CUDA(cudaMemcpyAsync(surf_xyzi, h->surf_out.p, (size_t)tot[1] * 16, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    B2_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    *n_corner = (size_t)tot[0]; *n_surf = (size_t)tot[1];
+    return B2_OK;
+}
+
+int b2_scan_last_gpu_ms(b2_scan_t h, float* ms) {
+    if (!h || !ms) return B2_ERR_ARG;
+    *ms = h->last_ms;
+    return B2_OK;
+}
+
+}  // extern "C"
