@@ -182,6 +182,84 @@ int  b2_scan_last_gpu_ms(b2_scan_t h, float* ms);
 int  b2_transform_cloud(const void* in, size_t in_stride, size_t n, const float pose6[6],
                         void* out, size_t out_stride);
 
+/* ------------------------------------------------------------------------------------------------
+ * Device-resident fp64 cloud — the object behind Multi_LiCa's Open3D calls
+ *   Calibration_Tookit/Multi_LiCa/multi_lidar_calibrator/calibration/Calibration.py
+ *     :306-307  o3d.geometry.PointCloud(self.source.pcd)          -> b2_cloud_create + b2_cloud_set_points
+ *     :314-315  pcd.voxel_down_sample(voxel_size)                 -> b2_cloud_voxel_down_sample
+ *     :327-328  pcd.estimate_normals()  (KDTreeSearchParamKNN(30)) -> b2_cloud_estimate_normals(c, 30)
+ *     :347-358  pcd.transform(T)                                  -> b2_cloud_transform
+ * Points are N x 3 doubles (np.asarray(pcd.points)); they stay in HBM between the calls.
+ * voxel_down_sample: voxel = floor((p - (min_bound - v/2)) / v), one double mean per voxel. Open3D returns the voxels
+ * in hash-map order; this library returns them in ascending (z, y, x) voxel order (compare as a set keyed by voxel).
+ * estimate_normals: covariance of the knn nearest neighbours (the point included, ties to the smaller index),
+ * eigenvector of the smallest eigenvalue; sign: first non-zero of (z, y, x) positive; (0,0,1) with < 3 neighbours. */
+typedef struct b2_cloud_s* b2_cloud_t;
+int b2_cloud_create(b2_cloud_t* out);
+int b2_cloud_destroy(b2_cloud_t c);
+int b2_cloud_set_points(b2_cloud_t c, const double* xyz, size_t n);
+/* float clouds (pcl::PointXYZ 16 B / PointXYZI 32 B strides) are widened on the device */
+int b2_cloud_set_points_f32(b2_cloud_t c, const void* base, size_t stride_bytes, size_t n);
+int b2_cloud_size(b2_cloud_t c, size_t* n, int* has_normals);
+int b2_cloud_get_points(b2_cloud_t c, double* xyz);
+int b2_cloud_get_normals(b2_cloud_t c, double* normals);
+int b2_cloud_set_normals(b2_cloud_t c, const double* normals);
+/* *out is a new cloud owned by the caller. voxel_rank_of_point (optional, n ints): for every input point the position
+ * of its voxel in the output (-1 for non-finite points). */
+int b2_cloud_voxel_down_sample(b2_cloud_t c, double voxel_size, b2_cloud_t* out, int32_t* voxel_rank_of_point);
+int b2_cloud_estimate_normals(b2_cloud_t c, int knn /* <= 32 */);
+int b2_cloud_transform(b2_cloud_t c, const double T[16] /* row-major 4x4 */);
+int b2_cloud_last_gpu_ms(b2_cloud_t c, float* ms);
+
+/* ------------------------------------------------------------------------------------------------
+ * NCCL communicator for the sharded registrations: one process per GPU; rank 0 creates the id,
+ * the host program ships its 128 bytes to the other ranks (torch.distributed / MPI / a file), every rank calls
+ * b2_comm_create after b2_set_device. libnccl.so.2 is resolved at run time (B2_NCCL_LIB overrides the name). */
+typedef struct b2_comm_s* b2_comm_t;
+int b2_comm_unique_id(unsigned char id[128]);
+int b2_comm_create(b2_comm_t* out, const unsigned char id[128], int rank, int world);
+int b2_comm_destroy(b2_comm_t c);
+int b2_comm_rank(b2_comm_t c, int* rank, int* world);
+int b2_comm_allreduce_f64(b2_comm_t c, double* values, size_t n);     /* host values, summed over ranks in place */
+
+/* ------------------------------------------------------------------------------------------------
+ * Generalized ICP — replaces o3d.pipelines.registration.registration_generalized_icp(source, target, max_corr, init,
+ *   TransformationEstimationForGeneralizedICP(epsilon), ICPConvergenceCriteria(rel_fitness, rel_rmse, max_iteration))
+ *   Calibration_Tookit/Multi_LiCa/multi_lidar_calibrator/calibration/Calibration.py:331-340
+ * Both clouds need normals (Calibration.py:327-328 always estimates them); the per-point covariance is Open3D's
+ * R diag(epsilon,1,1) R^T built from the normal. The whole loop runs on the device: correspondences (exact 1-NN
+ * within max_correspondence_distance, ties to the smaller index), J^T J / J^T r, LDL^T solve, T <- [Rz Ry Rx | t] T,
+ * stop when |d fitness| < relative_fitness and |d inlier_rmse| < relative_rmse or after max_iteration updates.
+ * sums[30] layout: J^T J upper triangle row-major (21), J^T r (6), n_corr, sum of squared point distances, sum r^2. */
+typedef struct b2_gicp_s* b2_gicp_t;
+typedef struct {
+    double max_correspondence_distance;   /* 1.0    Multi_LiCa config/params.yaml:52 */
+    double epsilon;                       /* 0.005  :58 */
+    double relative_fitness;              /* 1e-7   :59 */
+    double relative_rmse;                 /* 1e-7   :60 */
+    int    max_iteration;                 /* 100    :61 */
+} b2_gicp_params;
+void b2_gicp_default_params(b2_gicp_params* p);
+int  b2_gicp_create(b2_gicp_t* out, const b2_gicp_params* params /* NULL = defaults */);
+int  b2_gicp_destroy(b2_gicp_t h);
+int  b2_gicp_set_params(b2_gicp_t h, const b2_gicp_params* params);
+int  b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target);    /* builds the target index; the cloud may be destroyed afterwards */
+int  b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source);
+/* Source sharding for one registration spread over `world` GPUs: this process evaluates the rank-th contiguous slice
+ * of the (cell-sorted) source; the 30 sums are all-reduced over `comm` every iteration and every rank solves the same
+ * 6x6 system, so all ranks return the same T. world = 1 (the default) needs no communicator. With world > 1 and
+ * comm = NULL only b2_gicp_linearize works and returns this shard's local sums. */
+int  b2_gicp_set_shard(b2_gicp_t h, int rank, int world, b2_comm_t comm);
+/* one evaluation at T (parity tests): sums as above; corr (optional, n_source ints) = target index or -1 */
+int  b2_gicp_linearize(b2_gicp_t h, const double T[16], double sums[30], int32_t* corr);
+int  b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* fitness, double* inlier_rmse,
+                   int* iterations, int* converged);
+/* fitness / inlier_rmse of every evaluation of the last align (the first one is the evaluation at init) */
+int  b2_gicp_get_history(b2_gicp_t h, double* fitness, double* inlier_rmse, int capacity, int* n_evaluations);
+int  b2_gicp_last_gpu_ms(b2_gicp_t h, float* ms, int* launches);
+int  b2_gicp_index_info(b2_gicp_t h, double* target_cell_edge, double* target_points_per_cell,
+                        uint32_t* shard_begin, uint32_t* shard_end);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,11 @@ class S2MParams(C.Structure):
                 ("degenerate_eigen_threshold", C.c_float), ("max_batch", C.c_int)]
 
 
+class GicpParams(C.Structure):
+    _fields_ = [("max_correspondence_distance", C.c_double), ("epsilon", C.c_double), ("relative_fitness", C.c_double),
+                ("relative_rmse", C.c_double), ("max_iteration", C.c_int)]
+
+
 # every symbol include/b2reg.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = [
     "b2_version", "b2_last_error", "b2_device_count", "b2_set_device", "b2_kernel_launch_count",
@@ -38,6 +43,13 @@ SYMBOLS = [
     "b2_s2m_solve_batch", "b2_s2m_last_gpu_ms", "b2_transform_cloud",
     "b2_scan_default_params", "b2_scan_create", "b2_scan_destroy", "b2_scan_project", "b2_scan_extract_features",
     "b2_scan_last_gpu_ms",
+    "b2_cloud_create", "b2_cloud_destroy", "b2_cloud_set_points", "b2_cloud_set_points_f32", "b2_cloud_size",
+    "b2_cloud_get_points", "b2_cloud_get_normals", "b2_cloud_set_normals", "b2_cloud_voxel_down_sample",
+    "b2_cloud_estimate_normals", "b2_cloud_transform", "b2_cloud_last_gpu_ms",
+    "b2_comm_unique_id", "b2_comm_create", "b2_comm_destroy", "b2_comm_rank", "b2_comm_allreduce_f64",
+    "b2_gicp_default_params", "b2_gicp_create", "b2_gicp_destroy", "b2_gicp_set_params", "b2_gicp_set_target",
+    "b2_gicp_set_source", "b2_gicp_set_shard", "b2_gicp_linearize", "b2_gicp_align", "b2_gicp_get_history",
+    "b2_gicp_last_gpu_ms", "b2_gicp_index_info",
 ]
 
 
@@ -84,9 +96,41 @@ def lib():
     L.b2_scan_project.argtypes = [vp, vp, sz, vp, vp, vp, vp, i32, C.c_double, i32, C.POINTER(sz), vp, vp, vp, vp, vp, vp, vp]
     L.b2_scan_extract_features.argtypes = [vp, C.POINTER(sz), vp, vp, C.POINTER(sz), vp, vp, vp, vp]
     L.b2_scan_last_gpu_ms.argtypes = [vp, pf]
+    pd, dbl = C.POINTER(C.c_double), C.c_double
+    L.b2_cloud_create.argtypes = [C.POINTER(vp)]
+    L.b2_cloud_destroy.argtypes = [vp]
+    L.b2_cloud_set_points.argtypes = [vp, vp, sz]
+    L.b2_cloud_set_points_f32.argtypes = [vp, vp, sz, sz]
+    L.b2_cloud_size.argtypes = [vp, C.POINTER(sz), pi]
+    L.b2_cloud_get_points.argtypes = [vp, vp]
+    L.b2_cloud_get_normals.argtypes = [vp, vp]
+    L.b2_cloud_set_normals.argtypes = [vp, vp]
+    L.b2_cloud_voxel_down_sample.argtypes = [vp, dbl, C.POINTER(vp), vp]
+    L.b2_cloud_estimate_normals.argtypes = [vp, i32]
+    L.b2_cloud_transform.argtypes = [vp, vp]
+    L.b2_cloud_last_gpu_ms.argtypes = [vp, pf]
+    L.b2_comm_unique_id.argtypes = [vp]
+    L.b2_comm_create.argtypes = [C.POINTER(vp), vp, i32, i32]
+    L.b2_comm_destroy.argtypes = [vp]
+    L.b2_comm_rank.argtypes = [vp, pi, pi]
+    L.b2_comm_allreduce_f64.argtypes = [vp, vp, sz]
+    L.b2_gicp_default_params.argtypes = [C.POINTER(GicpParams)]
+    L.b2_gicp_default_params.restype = None
+    L.b2_gicp_create.argtypes = [C.POINTER(vp), C.POINTER(GicpParams)]
+    L.b2_gicp_destroy.argtypes = [vp]
+    L.b2_gicp_set_params.argtypes = [vp, C.POINTER(GicpParams)]
+    L.b2_gicp_set_target.argtypes = [vp, vp]
+    L.b2_gicp_set_source.argtypes = [vp, vp]
+    L.b2_gicp_set_shard.argtypes = [vp, i32, i32, vp]
+    L.b2_gicp_linearize.argtypes = [vp, vp, vp, vp]
+    L.b2_gicp_align.argtypes = [vp, vp, vp, pd, pd, pi, pi]
+    L.b2_gicp_get_history.argtypes = [vp, vp, vp, i32, pi]
+    L.b2_gicp_last_gpu_ms.argtypes = [vp, pf, pi]
+    L.b2_gicp_index_info.argtypes = [vp, pd, pd, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("b2_last_error", "b2_s2m_default_params", "b2_scan_default_params", "b2_kernel_launch_count"):
+        if name not in ("b2_last_error", "b2_s2m_default_params", "b2_scan_default_params", "b2_kernel_launch_count",
+                        "b2_gicp_default_params"):
             fn.restype = C.c_int
     L.b2_kernel_launch_count.restype = C.c_ulonglong
     _LIB = L

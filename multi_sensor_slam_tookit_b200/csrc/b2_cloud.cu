@@ -1,0 +1,685 @@
+// Device-resident fp64 cloud: grid index build, Open3D-style voxel_down_sample and estimate_normals, rigid transform.
+// Replaces, for Multi_LiCa's GICP calibration (Calibration_Tookit/Multi_LiCa/multi_lidar_calibrator/calibration/Calibration.py):
+//   :314-315  pcd.voxel_down_sample(voxel_size)   voxel = floor((p - (min - v/2)) / v), one double mean per voxel
+//   :327-328  pcd.estimate_normals()              KDTreeSearchParamKNN(30): covariance of the 30 nearest neighbours
+//                                                 (the point itself included), eigenvector of the smallest eigenvalue
+//   Calibration.py:347-358 / Lidar.py             pcd.transform(T)
+// Definitions shared with the oracle (Open3D leaves them unspecified): downsampled points come out in ascending
+// (z, y, x) voxel order, sums inside a voxel run in ascending input index, neighbour ties fall to the smaller index,
+// the normal's sign makes the first non-zero of (z, y, x) positive.
+#include "b2_cloud.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace b2 {
+
+// ------------------------------------------------------------------------------------------------ bbox (fp64)
+__device__ __forceinline__ unsigned long long dflip(double d) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+static inline double dunflip(unsigned long long u) {
+    unsigned long long v = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    double d; memcpy(&d, &v, 8); return d;
+}
+
+__global__ void k_bboxd_init(unsigned long long* bb) {
+    if (threadIdx.x < 3) bb[threadIdx.x] = ~0ull;
+    else if (threadIdx.x < 6) bb[threadIdx.x] = 0ull;
+}
+
+__global__ void __launch_bounds__(256) k_bboxd(const double* __restrict__ xyz, size_t n, unsigned long long* __restrict__ bb) {
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            mn[0] = fmin(mn[0], x); mn[1] = fmin(mn[1], y); mn[2] = fmin(mn[2], z);
+            mx[0] = fmax(mx[0], x); mx[1] = fmax(mx[1], y); mx[2] = fmax(mx[2], z);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[d] = fmin(mn[d], shfl_xor_d(0xffffffffu, mn[d], o));
+            mx[d] = fmax(mx[d], shfl_xor_d(0xffffffffu, mx[d], o));
+        }
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+            if (mn[d] <= mx[d]) { atomicMin(&bb[d], dflip(mn[d])); atomicMax(&bb[3 + d], dflip(mx[d])); }
+}
+
+int bbox_f64(const double* d_xyz, size_t n, DevBuf& scratch, cudaStream_t s, double mn[3], double mx[3]) {
+    for (int d = 0; d < 3; d++) { mn[d] = INFINITY; mx[d] = -INFINITY; }
+    if (n == 0) return B2_OK;
+    B2_CHECK(scratch.reserve(64));
+    unsigned long long* bb = scratch.as<unsigned long long>();
+    k_bboxd_init<<<1, 32, 0, s>>>(bb); count_launch();
+    const int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 8);
+    k_bboxd<<<nb, 256, 0, s>>>(d_xyz, n, bb); count_launch();
+    B2_CUDA(cudaGetLastError());
+    unsigned long long h[6];
+    B2_CUDA(cudaMemcpyAsync(h, bb, sizeof(h), cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    if (h[0] == ~0ull) return B2_OK;           // no finite point
+    for (int d = 0; d < 3; d++) { mn[d] = dunflip(h[d]); mx[d] = dunflip(h[3 + d]); }
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ grid build
+struct GridGeomD { double ox, oy, oz, inv_h; int nx, ny, nz; uint32_t ncell; };
+
+__device__ __forceinline__ uint32_t cell_of_point_d(const GridGeomD& g, double x, double y, double z) {
+    if (!(isfinite(x) && isfinite(y) && isfinite(z))) return g.ncell;
+    int cx = (int)floor((x - g.ox) * g.inv_h), cy = (int)floor((y - g.oy) * g.inv_h), cz = (int)floor((z - g.oz) * g.inv_h);
+    cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
+    return (uint32_t)(((size_t)cz * g.ny + cy) * g.nx + cx);
+}
+
+// count[c]++ ; optionally record (key, input index) for the sort
+__global__ void __launch_bounds__(256) k_celld_count(const double* __restrict__ xyz, uint32_t n, GridGeomD g, uint32_t* __restrict__ count,
+                                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cell_of_point_d(g, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2]);
+    atomicAdd(&count[c], 1u);
+    if (keys) { keys[i] = c; vals[i] = i; }
+}
+
+__global__ void __launch_bounds__(256) k_count_nonzero(const uint32_t* __restrict__ count, size_t ncell, unsigned long long* __restrict__ out) {
+    unsigned local = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) local += count[i] != 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
+}
+
+__global__ void __launch_bounds__(256) k_celld_gather(const double* __restrict__ xyz, uint32_t n, const uint32_t* __restrict__ order, P4d* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t src = order[i];
+    P4d p; p.x = xyz[3 * (size_t)src]; p.y = xyz[3 * (size_t)src + 1]; p.z = xyz[3 * (size_t)src + 2]; p.idx = (long long)src;
+    double2* o = reinterpret_cast<double2*>(&out[i]);
+    o[0] = make_double2(p.x, p.y); o[1] = make_double2(p.z, __longlong_as_double(p.idx));
+}
+
+static double cells_at(const double ext[3], double h) {
+    double c = 1.0;
+    for (int d = 0; d < 3; d++) c *= std::floor(ext[d] / h) + 1.0;
+    return c;
+}
+
+int GridD::build(const double* d_xyz, size_t n_, double h_request, double target_ppc, cudaStream_t s) {
+    n = n_; dev = GridDDev{}; ppc = 0.0;
+    if (n > 0x7fffffffull) { set_error("grid index: too many points (%zu)", n); return B2_ERR_ARG; }
+    double mn[3], mx[3];
+    B2_CHECK(bbox_f64(d_xyz, n, work, s, mn, mx));
+    if (n == 0 || !(mn[0] <= mx[0])) {
+        B2_CHECK(cell_start.reserve(3 * sizeof(uint32_t)));
+        B2_CUDA(cudaMemsetAsync(cell_start.p, 0, 3 * sizeof(uint32_t), s));
+        dev.pts = nullptr; dev.cell_start = cell_start.as<uint32_t>();
+        dev.h = h_request > 0 ? h_request : 1.0; dev.inv_h = 1.0 / dev.h; dev.nx = dev.ny = dev.nz = 1; dev.n = 0;
+        return B2_OK;
+    }
+    double ext[3];
+    for (int d = 0; d < 3; d++) ext[d] = mx[d] - mn[d];
+    const double emax = std::max(ext[0], std::max(ext[1], ext[2]));
+    const double max_cells = (double)std::min<size_t>(std::max<size_t>(16 * n, (size_t)1 << 16), (size_t)1 << 30);
+    // smallest admissible edge under the cell budget (cells_at is non-increasing in h)
+    double h_floor = 0.0;
+    if (emax > 0) {
+        double lo = emax * 1e-9, hi = emax + 1.0;
+        if (cells_at(ext, lo) <= max_cells) h_floor = lo;
+        else {
+            for (int it = 0; it < 100; it++) { const double mid = 0.5 * (lo + hi); if (cells_at(ext, mid) <= max_cells) hi = mid; else lo = mid; }
+            h_floor = hi;
+        }
+    } else h_floor = 1.0;
+    double h;
+    const bool adapt = !(h_request > 0);
+    if (!adapt) h = std::max(h_request, h_floor);
+    else {
+        double vol = 1.0;
+        for (int d = 0; d < 3; d++) vol *= std::max(ext[d], emax * 1e-3 + 1e-12);
+        h = std::max(h_floor, std::cbrt(vol * target_ppc / (double)n));
+    }
+    GridGeomD g;
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    const size_t nal = (n + 63) & ~(size_t)63;
+    unsigned long long* d_occ = nullptr;
+    for (int attempt = 0;; attempt++) {
+        g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.inv_h = 1.0 / h;
+        g.nx = (int)(std::floor(ext[0] / h) + 1.0); g.ny = (int)(std::floor(ext[1] / h) + 1.0); g.nz = (int)(std::floor(ext[2] / h) + 1.0);
+        g.ncell = (uint32_t)((size_t)g.nx * g.ny * g.nz);
+        const size_t ncount = (size_t)g.ncell + 2;
+        B2_CHECK(cell_start.reserve(ncount * sizeof(uint32_t)));
+        B2_CUDA(cudaMemsetAsync(cell_start.p, 0, ncount * sizeof(uint32_t), s));
+        const size_t need = 4 * nal * sizeof(uint32_t) + sort_tmp_bytes(n) + scan_tmp_bytes(ncount) + 1024;
+        B2_CHECK(work.reserve(need));
+        uint32_t* ka = work.as<uint32_t>();
+        uint32_t* va = ka + nal;
+        k_celld_count<<<nblk, 256, 0, s>>>(d_xyz, (uint32_t)n, g, cell_start.as<uint32_t>(), ka, va); count_launch();
+        B2_CUDA(cudaGetLastError());
+        // occupancy of this edge
+        d_occ = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(work.p) + need - 512);
+        B2_CUDA(cudaMemsetAsync(d_occ, 0, 8, s));
+        const int nb = (int)std::min<size_t>(((size_t)g.ncell + 255) / 256, (size_t)device_sm_count() * 8);
+        k_count_nonzero<<<nb, 256, 0, s>>>(cell_start.as<uint32_t>(), (size_t)g.ncell, d_occ); count_launch();
+        unsigned long long occ = 0;
+        B2_CUDA(cudaMemcpyAsync(&occ, d_occ, 8, cudaMemcpyDeviceToHost, s));
+        B2_CUDA(cudaStreamSynchronize(s));
+        ppc = occ ? (double)n / (double)occ : 0.0;
+        if (!adapt || attempt >= 5 || occ == 0) break;
+        const double ratio = ppc / target_ppc;
+        if (ratio >= 0.7 && ratio <= 1.5) break;
+        if (ratio > 1.5 && h <= h_floor) break;
+        // points lie on surfaces: occupancy grows with h^2
+        h = std::max(h_floor, h * std::min(4.0, std::max(0.25, std::sqrt(1.0 / ratio))));
+    }
+    const size_t ncount = (size_t)g.ncell + 2;
+    uint32_t* ka = work.as<uint32_t>();
+    uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
+    char* scratch = reinterpret_cast<char*>(vb + nal);
+    B2_CHECK(exclusive_scan_u32(cell_start.as<uint32_t>(), ncount, scratch + sort_tmp_bytes(n), s));
+    int bits = 1;
+    while (((size_t)1 << bits) <= (size_t)g.ncell) bits++;
+    uint32_t *ks, *vs;
+    B2_CHECK(radix_sort_pairs(ka, va, kb, vb, n, bits, scratch, s, &ks, &vs));
+    B2_CHECK(pts.reserve(n * sizeof(P4d)));
+    k_celld_gather<<<nblk, 256, 0, s>>>(d_xyz, (uint32_t)n, vs, pts.as<P4d>()); count_launch();
+    B2_CUDA(cudaGetLastError());
+    dev.pts = pts.as<P4d>(); dev.cell_start = cell_start.as<uint32_t>();
+    dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.h = h; dev.inv_h = g.inv_h;
+    dev.nx = g.nx; dev.ny = g.ny; dev.nz = g.nz;
+    // valid points = everything before the non-finite bucket; read lazily by kernels through cell_start[ncell]
+    dev.n = (uint32_t)n;
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ voxel_down_sample
+struct VdsGeom { double vmin[3]; double voxel; unsigned long long nx, ny; unsigned long long invalid; };
+
+__global__ void __launch_bounds__(256) k_vds_key(const double* __restrict__ xyz, uint32_t n, VdsGeom g, unsigned long long* __restrict__ lin,
+                                                 uint32_t* __restrict__ key_lo, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+    unsigned long long k = g.invalid;
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+        const unsigned long long cx = (unsigned long long)(long long)floor((x - g.vmin[0]) / g.voxel);
+        const unsigned long long cy = (unsigned long long)(long long)floor((y - g.vmin[1]) / g.voxel);
+        const unsigned long long cz = (unsigned long long)(long long)floor((z - g.vmin[2]) / g.voxel);
+        k = (cz * g.ny + cy) * g.nx + cx;
+    }
+    lin[i] = k; key_lo[i] = (uint32_t)k; vals[i] = i;
+}
+__global__ void __launch_bounds__(256) k_vds_key_hi(const unsigned long long* __restrict__ lin, const uint32_t* __restrict__ order, uint32_t n,
+                                                    uint32_t* __restrict__ key_hi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) key_hi[i] = (uint32_t)(lin[order[i]] >> 32);
+}
+// flags[i] = 1 where a voxel run starts in sorted order (the non-finite bucket never starts one); flags[n] = 0
+__global__ void __launch_bounds__(256) k_vds_heads(const unsigned long long* __restrict__ lin, const uint32_t* __restrict__ order, uint32_t n,
+                                                   unsigned long long invalid, uint32_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    uint32_t f = 0;
+    if (i < n) { const unsigned long long k = lin[order[i]]; f = (k != invalid) && (i == 0 || lin[order[i - 1]] != k); }
+    flags[i] = f;
+}
+// seg_start[run] = first sorted position of the run; seg_start[nruns] = end of the finite points
+__global__ void __launch_bounds__(256) k_vds_seg_start(const unsigned long long* __restrict__ lin, const uint32_t* __restrict__ order,
+                                                       const uint32_t* __restrict__ segid, uint32_t n, unsigned long long invalid,
+                                                       uint32_t* __restrict__ seg_start, int32_t* __restrict__ rank_of_point) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { if (lin[order[n - 1]] != invalid) seg_start[segid[n]] = n; return; }
+    const unsigned long long k = lin[order[i]];
+    const bool head = (i == 0) || (lin[order[i - 1]] != k);
+    if (rank_of_point) rank_of_point[order[i]] = (k == invalid) ? -1 : (int32_t)(segid[i] + (head ? 1u : 0u)) - 1;
+    if (!head) return;
+    if (k == invalid) seg_start[segid[n]] = i;
+    else seg_start[segid[i]] = i;
+}
+// one thread per voxel: double sums in ascending input index, then the mean
+__global__ void __launch_bounds__(128) k_vds_mean(const double* __restrict__ xyz, const uint32_t* __restrict__ order,
+                                                  const uint32_t* __restrict__ seg_start, uint32_t nseg, double* __restrict__ out) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    const uint32_t b = seg_start[s], e = seg_start[s + 1];
+    double sx = 0, sy = 0, sz = 0;
+    for (uint32_t i = b; i < e; i++) {
+        const size_t src = order[i];
+        sx += xyz[3 * src]; sy += xyz[3 * src + 1]; sz += xyz[3 * src + 2];
+    }
+    const double cnt = (double)(e - b);
+    out[3 * (size_t)s] = sx / cnt; out[3 * (size_t)s + 1] = sy / cnt; out[3 * (size_t)s + 2] = sz / cnt;
+}
+
+static int voxel_down_sample(b2_cloud_s* c, double voxel, b2_cloud_s* out, int32_t* h_rank) {
+    cudaStream_t s = c->stream;
+    const size_t n = c->n;
+    out->n = 0; out->has_normals = false;
+    if (n == 0) return B2_OK;
+    if (n > 0x7fffffffull) { set_error("voxel_down_sample: too many points"); return B2_ERR_ARG; }
+    const double* xyz = c->xyz.as<double>();
+    double mn[3], mx[3];
+    B2_CHECK(bbox_f64(xyz, n, c->work, s, mn, mx));
+    if (!(mn[0] <= mx[0])) return B2_OK;
+    VdsGeom g;
+    g.voxel = voxel;
+    double cnt[3];
+    for (int d = 0; d < 3; d++) {
+        g.vmin[d] = mn[d] - voxel * 0.5;
+        cnt[d] = std::floor((mx[d] - g.vmin[d]) / voxel) + 1.0;
+        if (!(cnt[d] < 2147483647.0)) { set_error("voxel_down_sample: voxel_size is too small"); return B2_ERR_TOO_LARGE; }
+    }
+    if (cnt[0] * cnt[1] * cnt[2] >= 4.0e18) { set_error("voxel_down_sample: voxel_size is too small"); return B2_ERR_TOO_LARGE; }
+    g.nx = (unsigned long long)cnt[0]; g.ny = (unsigned long long)cnt[1];
+    const unsigned long long total = g.nx * g.ny * (unsigned long long)cnt[2];
+    g.invalid = total;
+    int bits = 1;
+    while (bits < 64 && (1ull << bits) <= total) bits++;
+    const size_t nal = (n + 63) & ~(size_t)63;
+    const size_t np1 = n + 1;
+    const size_t need = nal * 8 + 4 * nal * 4 + (np1 + 64) * 4 * 2 + sort_tmp_bytes(n) + scan_tmp_bytes(np1) + 2048;
+    B2_CHECK(c->work.reserve(need));
+    unsigned long long* lin = c->work.as<unsigned long long>();
+    uint32_t* ka = reinterpret_cast<uint32_t*>(lin + nal);
+    uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
+    uint32_t* flags = vb + nal;
+    uint32_t* seg_start = flags + ((np1 + 63) & ~(size_t)63);
+    char* scratch = reinterpret_cast<char*>(seg_start + ((np1 + 63) & ~(size_t)63));
+    const unsigned nblk = (unsigned)((n + 255) / 256), nblk1 = (unsigned)((np1 + 255) / 256);
+    k_vds_key<<<nblk, 256, 0, s>>>(xyz, (uint32_t)n, g, lin, ka, va); count_launch();
+    B2_CUDA(cudaGetLastError());
+    uint32_t *ks, *vs;
+    B2_CHECK(radix_sort_pairs(ka, va, kb, vb, n, std::min(bits, 32), scratch, s, &ks, &vs));
+    if (bits > 32) {
+        // second key word: stable sort of the already low-word-sorted sequence by the high word
+        uint32_t* k2 = (ks == ka) ? kb : ka;
+        uint32_t* v2 = (vs == va) ? vb : va;
+        k_vds_key_hi<<<nblk, 256, 0, s>>>(lin, vs, (uint32_t)n, ks); count_launch();
+        B2_CHECK(radix_sort_pairs(ks, vs, k2, v2, n, bits - 32, scratch, s, &ks, &vs));
+    }
+    k_vds_heads<<<nblk1, 256, 0, s>>>(lin, vs, (uint32_t)n, g.invalid, flags); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CHECK(exclusive_scan_u32(flags, np1, scratch + sort_tmp_bytes(n), s));
+    int32_t* d_rank = nullptr;
+    DevBuf rankbuf;
+    if (h_rank) { B2_CHECK(rankbuf.reserve(n * 4)); d_rank = rankbuf.as<int32_t>(); }
+    k_vds_seg_start<<<nblk1, 256, 0, s>>>(lin, vs, flags, (uint32_t)n, g.invalid, seg_start, d_rank); count_launch();
+    B2_CUDA(cudaGetLastError());
+    uint32_t nseg = 0;
+    B2_CUDA(cudaMemcpyAsync(&nseg, flags + n, 4, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    B2_CHECK(out->xyz.reserve((size_t)std::max<uint32_t>(nseg, 1) * 24));
+    if (nseg) {
+        k_vds_mean<<<(nseg + 127) / 128, 128, 0, s>>>(xyz, vs, seg_start, nseg, out->xyz.as<double>()); count_launch();
+        B2_CUDA(cudaGetLastError());
+    }
+    if (h_rank) B2_CUDA(cudaMemcpyAsync(h_rank, d_rank, n * 4, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    rankbuf.release();
+    out->n = nseg;
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ estimate_normals
+constexpr int NRM_WARPS = 4;
+constexpr int NRM_MAXK = 32;
+
+// cyclic Jacobi of a symmetric 3x3 in double: w ascending, eigenvectors in the columns of V. Same sweep order, rotation
+// formulas and stopping rule as the oracle, IEEE div/sqrt, no FMA.
+__device__ __forceinline__ void jacobi3_f64(const double A[9], double w[3], double V[9]) {
+    double a[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { a[i] = A[i]; V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 50; sweep++) {
+        const double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+        if (off < 1e-300) break;
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int q = p + 1; q < 3; q++) {
+                const double apq = a[p * 3 + q];
+                if (apq == 0.0) continue;
+                const double theta = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const double akp = a[k * 3 + p], akq = a[k * 3 + q]; a[k * 3 + p] = c * akp - s * akq; a[k * 3 + q] = s * akp + c * akq; }
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const double apk = a[p * 3 + k], aqk = a[q * 3 + k]; a[p * 3 + k] = c * apk - s * aqk; a[q * 3 + k] = s * apk + c * aqk; }
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const double vkp = V[k * 3 + p], vkq = V[k * 3 + q]; V[k * 3 + p] = c * vkp - s * vkq; V[k * 3 + q] = s * vkp + c * vkq; }
+            }
+    }
+    w[0] = a[0]; w[1] = a[4]; w[2] = a[8];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = i + 1; j < 3; j++)
+            if (w[j] < w[i]) {
+                double t = w[i]; w[i] = w[j]; w[j] = t;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { t = V[k * 3 + i]; V[k * 3 + i] = V[k * 3 + j]; V[k * 3 + j] = t; }
+            }
+}
+
+// A warp keeps the 32 best (distance, index) pairs seen so far, one per lane, ascending; slot K-1 is the k-th best.
+struct WarpList {
+    double sd; int si; uint32_t sp;       // this lane's slot
+    double kd; int ki;                    // k-th best (uniform)
+};
+__device__ __forceinline__ void warp_offer(WarpList& L, int K, double d, int idx, uint32_t pos, bool valid) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    unsigned mask = __ballot_sync(full, valid && (d < L.kd || (d == L.kd && idx < L.ki)));
+    while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const double cd = shfl_d(full, d, src);
+        const int ci = __shfl_sync(full, idx, src);
+        const uint32_t cp = __shfl_sync(full, pos, src);
+        if (!(cd < L.kd || (cd == L.kd && ci < L.ki))) continue;
+        const bool gt = (L.sd > cd) || (L.sd == cd && L.si > ci);
+        const unsigned gm = __ballot_sync(full, gt);
+        const int ins = __ffs(gm) - 1;
+        const double ud = shfl_up_d(full, L.sd, 1);
+        const int ui = __shfl_up_sync(full, L.si, 1);
+        const uint32_t up = __shfl_up_sync(full, L.sp, 1);
+        if (lane > ins) { L.sd = ud; L.si = ui; L.sp = up; }
+        else if (lane == ins) { L.sd = cd; L.si = ci; L.sp = cp; }
+        L.kd = shfl_d(full, L.sd, K - 1);
+        L.ki = __shfl_sync(full, L.si, K - 1);
+    }
+}
+
+__device__ __forceinline__ void warp_scan_run(const GridDDev& g, WarpList& L, int K, double qx, double qy, double qz, uint32_t b, uint32_t e) {
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = b; base < e; base += 32) {
+        const uint32_t p = base + lane;
+        const bool valid = p < e;
+        double d = INFINITY; int idx = 0x7fffffff;
+        if (valid) {
+            double x, y, z; long long id;
+            load_p4d(&g.pts[p], x, y, z, id);
+            const double dx = qx - x, dy = qy - y, dz = qz - z;
+            d = dx * dx + dy * dy + dz * dz;
+            idx = (int)id;
+        }
+        warp_offer(L, K, d, idx, p, valid);
+    }
+}
+
+// One warp serves 32 consecutive cell-sorted points: phase 1 finds each one's K nearest neighbours with the whole warp,
+// phase 2 gives every lane one point: cumulants over its neighbours in ascending (distance, index), covariance,
+// Jacobi, normal. normals are written at the points' original indices.
+__global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(GridDDev g, uint32_t n_valid, int K, double* __restrict__ nrm) {
+    __shared__ uint32_t s_pos[NRM_WARPS][32][NRM_MAXK];
+    __shared__ int s_cnt[NRM_WARPS][32];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t base = (blockIdx.x * NRM_WARPS + warp) * 32u;
+    if (base >= n_valid) return;
+    double mx = 0, my = 0, mz = 0; long long mid = -1;
+    if (base + lane < n_valid) load_p4d(&g.pts[base + lane], mx, my, mz, mid);
+    const int nq = (int)min(32u, n_valid - base);
+    for (int j = 0; j < nq; j++) {
+        const double qx = shfl_d(full, mx, j), qy = shfl_d(full, my, j), qz = shfl_d(full, mz, j);
+        WarpList L; L.sd = INFINITY; L.si = 0x7fffffff; L.sp = 0; L.kd = INFINITY; L.ki = 0x7fffffff;
+        const QueryCell qc = query_cell(g, qx, qy, qz);
+        const int rmax = rings_to_cover(g, qc);
+        // rings 0 and 1: nine full rows
+        for (int i = 0; i < 9; i++) {
+            uint32_t b, e;
+            row_range(g, qc.cx - 1, qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, b, e);
+            warp_scan_run(g, L, K, qx, qy, qz, b, e);
+        }
+        int r = 1;
+        while (!(L.kd < ring_bound2(g, qc, r)) && r < rmax) {
+            r++;
+            const int side = 2 * r + 1;
+            for (int rowi = 0; rowi < side * side; rowi++) {
+                const int dy = rowi % side - r, dz = rowi / side - r;
+                uint32_t b, e;
+                if (max(abs(dy), abs(dz)) == r) {
+                    row_range(g, qc.cx - r, qc.cx + r, qc.cy + dy, qc.cz + dz, b, e);
+                    warp_scan_run(g, L, K, qx, qy, qz, b, e);
+                } else {
+                    row_range(g, qc.cx - r, qc.cx - r, qc.cy + dy, qc.cz + dz, b, e);
+                    warp_scan_run(g, L, K, qx, qy, qz, b, e);
+                    row_range(g, qc.cx + r, qc.cx + r, qc.cy + dy, qc.cz + dz, b, e);
+                    warp_scan_run(g, L, K, qx, qy, qz, b, e);
+                }
+            }
+        }
+        const unsigned have = __ballot_sync(full, lane < K && L.sd < INFINITY);
+        if (lane < K) s_pos[warp][j][lane] = L.sp;
+        if (lane == 0) s_cnt[warp][j] = __popc(have);
+    }
+    __syncwarp();
+    if (lane >= nq) return;
+    const int found = s_cnt[warp][lane];
+    double nv[3] = {0.0, 0.0, 1.0};
+    if (found >= 3) {
+        double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < found; j++) {
+            double x, y, z; long long id;
+            load_p4d(&g.pts[s_pos[warp][lane][j]], x, y, z, id);
+            c[0] += x; c[1] += y; c[2] += z;
+            c[3] += x * x; c[4] += x * y; c[5] += x * z;
+            c[6] += y * y; c[7] += y * z; c[8] += z * z;
+        }
+        const double fn = (double)found;
+#pragma unroll
+        for (int q = 0; q < 9; q++) c[q] /= fn;
+        double C[9];
+        C[0] = c[3] - c[0] * c[0]; C[4] = c[6] - c[1] * c[1]; C[8] = c[8] - c[2] * c[2];
+        C[1] = C[3] = c[4] - c[0] * c[1]; C[2] = C[6] = c[5] - c[0] * c[2]; C[5] = C[7] = c[7] - c[1] * c[2];
+        double w[3], V[9];
+        jacobi3_f64(C, w, V);
+        nv[0] = V[0]; nv[1] = V[3]; nv[2] = V[6];
+        const double nn = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+        if (nn == 0.0) { nv[0] = 0; nv[1] = 0; nv[2] = 1; }
+        if (nv[2] < 0 || (nv[2] == 0 && (nv[1] < 0 || (nv[1] == 0 && nv[0] < 0)))) { nv[0] = -nv[0]; nv[1] = -nv[1]; nv[2] = -nv[2]; }
+    }
+    double* o = &nrm[3 * (size_t)mid];
+    o[0] = nv[0]; o[1] = nv[1]; o[2] = nv[2];
+}
+
+__global__ void __launch_bounds__(256) k_fill_normals(double* __restrict__ nrm, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { nrm[3 * (size_t)i] = 0.0; nrm[3 * (size_t)i + 1] = 0.0; nrm[3 * (size_t)i + 2] = 1.0; }
+}
+
+int estimate_normals_knn(b2_cloud_s* c, int knn) {
+    if (knn < 1 || knn > NRM_MAXK) { set_error("estimate_normals: knn must be in [1, %d]", NRM_MAXK); return B2_ERR_ARG; }
+    cudaStream_t s = c->stream;
+    c->has_normals = false;
+    if (c->n == 0) { c->has_normals = true; return B2_OK; }
+    B2_CHECK(c->nrm.reserve(c->n * 24));
+    k_fill_normals<<<(unsigned)((c->n + 255) / 256), 256, 0, s>>>(c->nrm.as<double>(), (uint32_t)c->n); count_launch();
+    GridD grid;
+    int st = grid.build(c->xyz.as<double>(), c->n, 0.0, std::max(4.0, knn / 3.0), s);
+    if (st != B2_OK) { grid.release(); return st; }
+    uint32_t n_valid = 0;
+    const size_t ncell = (size_t)grid.dev.nx * grid.dev.ny * grid.dev.nz;
+    cudaError_t e = cudaMemcpyAsync(&n_valid, grid.dev.cell_start + ncell, 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { grid.release(); set_error("estimate_normals: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
+    if (n_valid) {
+        const unsigned per_block = NRM_WARPS * 32;
+        k_normals<<<(n_valid + per_block - 1) / per_block, per_block, 0, s>>>(grid.dev, n_valid, knn, c->nrm.as<double>()); count_launch();
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    grid.release();
+    if (e != cudaSuccess) { set_error("estimate_normals: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
+    c->has_normals = true;
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ transform / convert
+struct Rigid { double R[9]; double t[3]; };
+__global__ void __launch_bounds__(256) k_transform_d(double* __restrict__ xyz, double* __restrict__ nrm, uint32_t n, Rigid T) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* p = &xyz[3 * (size_t)i];
+    const double x = p[0], y = p[1], z = p[2];
+    p[0] = T.R[0] * x + T.R[1] * y + T.R[2] * z + T.t[0];
+    p[1] = T.R[3] * x + T.R[4] * y + T.R[5] * z + T.t[1];
+    p[2] = T.R[6] * x + T.R[7] * y + T.R[8] * z + T.t[2];
+    if (nrm) {
+        double* q = &nrm[3 * (size_t)i];
+        const double a = q[0], b = q[1], c = q[2];
+        q[0] = T.R[0] * a + T.R[1] * b + T.R[2] * c;
+        q[1] = T.R[3] * a + T.R[4] * b + T.R[5] * c;
+        q[2] = T.R[6] * a + T.R[7] * b + T.R[8] * c;
+    }
+}
+__global__ void __launch_bounds__(256) k_f32_to_f64(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, double* __restrict__ xyz) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    xyz[3 * (size_t)i] = (double)p[0]; xyz[3 * (size_t)i + 1] = (double)p[1]; xyz[3 * (size_t)i + 2] = (double)p[2];
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" {
+
+int b2_cloud_create(b2_cloud_t* out) {
+    if (!out) return B2_ERR_ARG;
+    *out = nullptr;
+    b2_cloud_s* c = new b2_cloud_s();
+    if (cudaGetDevice(&c->device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("b2_cloud_create: %s", cudaGetErrorString(cudaGetLastError()));
+        delete c; return B2_ERR_CUDA;
+    }
+    *out = c;
+    return B2_OK;
+}
+
+int b2_cloud_destroy(b2_cloud_t c) {
+    if (!c) return B2_OK;
+    c->xyz.release(); c->nrm.release(); c->work.release(); c->pin.release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return B2_OK;
+}
+
+int b2_cloud_set_points(b2_cloud_t c, const double* xyz, size_t n) {
+    if (!c || (n && !xyz)) return B2_ERR_ARG;
+    c->n = n; c->has_normals = false;
+    if (!n) return B2_OK;
+    B2_CHECK(c->xyz.reserve(n * 24));
+    B2_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, n * 24, cudaMemcpyHostToDevice, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2_cloud_set_points_f32(b2_cloud_t c, const void* base, size_t stride, size_t n) {
+    if (!c || (n && !base) || stride < 12 || (stride & 3)) return B2_ERR_ARG;
+    c->n = n; c->has_normals = false;
+    if (!n) return B2_OK;
+    if (n > 0x7fffffffull) return B2_ERR_ARG;
+    B2_CHECK(c->xyz.reserve(n * 24));
+    B2_CHECK(c->work.reserve(n * stride));
+    B2_CUDA(cudaMemcpyAsync(c->work.p, base, n * stride, cudaMemcpyHostToDevice, c->stream));
+    k_f32_to_f64<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->work.as<unsigned char>(), stride, (uint32_t)n, c->xyz.as<double>()); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2_cloud_size(b2_cloud_t c, size_t* n, int* has_normals) {
+    if (!c) return B2_ERR_ARG;
+    if (n) *n = c->n;
+    if (has_normals) *has_normals = c->has_normals ? 1 : 0;
+    return B2_OK;
+}
+
+int b2_cloud_get_points(b2_cloud_t c, double* xyz) {
+    if (!c || (c->n && !xyz)) return B2_ERR_ARG;
+    if (!c->n) return B2_OK;
+    B2_CUDA(cudaMemcpyAsync(xyz, c->xyz.p, c->n * 24, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2_cloud_get_normals(b2_cloud_t c, double* nrm) {
+    if (!c || (c->n && !nrm)) return B2_ERR_ARG;
+    if (!c->has_normals) { set_error("b2_cloud_get_normals: the cloud has no normals"); return B2_ERR_STATE; }
+    if (!c->n) return B2_OK;
+    B2_CUDA(cudaMemcpyAsync(nrm, c->nrm.p, c->n * 24, cudaMemcpyDeviceToHost, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2_cloud_set_normals(b2_cloud_t c, const double* nrm) {
+    if (!c || (c->n && !nrm)) return B2_ERR_ARG;
+    if (c->n) {
+        B2_CHECK(c->nrm.reserve(c->n * 24));
+        B2_CUDA(cudaMemcpyAsync(c->nrm.p, nrm, c->n * 24, cudaMemcpyHostToDevice, c->stream));
+        B2_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    c->has_normals = true;
+    return B2_OK;
+}
+
+int b2_cloud_voxel_down_sample(b2_cloud_t c, double voxel_size, b2_cloud_t* out, int32_t* voxel_rank_of_point) {
+    if (!c || !out) return B2_ERR_ARG;
+    *out = nullptr;
+    if (!(voxel_size > 0.0)) { set_error("voxel_down_sample: voxel_size <= 0"); return B2_ERR_ARG; }
+    B2_CUDA(cudaSetDevice(c->device));
+    b2_cloud_t o = nullptr;
+    B2_CHECK(b2_cloud_create(&o));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->stream);
+    const int st = voxel_down_sample(c, voxel_size, o, voxel_rank_of_point);
+    cudaEventRecord(e1, c->stream); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&c->last_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (st != B2_OK) { b2_cloud_destroy(o); return st; }
+    *out = o;
+    return B2_OK;
+}
+
+int b2_cloud_estimate_normals(b2_cloud_t c, int knn) {
+    if (!c) return B2_ERR_ARG;
+    B2_CUDA(cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->stream);
+    const int st = estimate_normals_knn(c, knn);
+    cudaEventRecord(e1, c->stream); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&c->last_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return st;
+}
+
+int b2_cloud_transform(b2_cloud_t c, const double T[16]) {
+    if (!c || !T) return B2_ERR_ARG;
+    if (!c->n) return B2_OK;
+    Rigid r;
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) r.R[i * 3 + j] = T[i * 4 + j]; r.t[i] = T[i * 4 + 3]; }
+    k_transform_d<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->xyz.as<double>(), c->has_normals ? c->nrm.as<double>() : nullptr,
+                                                                         (uint32_t)c->n, r); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2_OK;
+}
+
+int b2_cloud_last_gpu_ms(b2_cloud_t c, float* ms) {
+    if (!c || !ms) return B2_ERR_ARG;
+    *ms = c->last_ms;
+    return B2_OK;
+}
+
+}  // extern "C"

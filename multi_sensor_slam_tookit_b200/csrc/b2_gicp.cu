@@ -1,0 +1,506 @@
+// Generalized ICP on the device, fp64. Replaces Open3D's registration_generalized_icp as Multi_LiCa calls it
+//   Calibration_Tookit/Multi_LiCa/multi_lidar_calibrator/calibration/Calibration.py:331-340
+//   (TransformationEstimationForGeneralizedICP(epsilon), ICPConvergenceCriteria(rel_fitness, rel_rmse, max_iteration))
+// and is the kernel of the sharded map-to-map registration.
+//
+// One iteration = one launch of k_gicp_linearize (+ one all-reduce and a one-thread finalize kernel when the source
+// is sharded over several GPUs):
+//   phase 1  every source point of the shard is transformed by the current T and its exact nearest target point
+//            within max_correspondence_distance is found in the fp64 grid (8 lanes per query, ties to the smaller index);
+//   phase 2  one lane per correspondence: M = Ct + R Cs R^T, residual and Jacobian, 21 + 6 + 3 sums in registers;
+//   epilogue shuffle tree -> per-CTA partial -> the last CTA adds the partials in CTA order (deterministic) and, on
+//            a single GPU, solves the 6x6 system, updates T and evaluates Open3D's convergence rule, all on the device.
+//
+// Covariances. The reference never supplies covariances: Open3D derives them from the normals as R diag(eps,1,1) R^T
+// with R the rotation of e1 onto the normal (identity when n.x < -0.99), i.e. C = I - (1-eps) m m^T with m the normal
+// (or e1 in the special case). The device keeps m (24 B) instead of C (72 B). With u = m_target, v = R m_source,
+// p = u + v, q = u - v:  M = 2I - (a/2)(pp^T + qq^T), a = 1 - eps, and since p is orthogonal to q
+//   M^-1 = I/2 + a/(4 l1) pp^T + a/(4 l2) qq^T,  l1 = 2 - a|p|^2/2,  l2 = 2 - a|q|^2/2   (both >= 2 eps > 0).
+// Open3D forms W = (M^-1)^(1/2), r = W d, J = W [-[vs]x | I]; only J^T J = A^T M^-1 A, J^T r = A^T M^-1 d and
+// r^T r = d^T M^-1 d are ever used, so no matrix square root is needed.
+#include "b2_cloud.cuh"
+#include "b2_comm.cuh"
+#include <cmath>
+#include <algorithm>
+
+namespace b2 {
+
+constexpr int GICP_THREADS = 256;
+constexpr int GICP_WARPS = GICP_THREADS / 32;
+constexpr int GICP_LPG = 8;                  // lanes per nearest-neighbour query
+constexpr int GICP_NSUM = 30;                // 21 JtJ upper + 6 Jtr + n_corr + sum d^2 + sum r^2
+constexpr int GICP_HIST = 256;
+
+struct GicpState {
+    double T[16];
+    double sums[GICP_NSUM];          // global sums of the last linearisation (after the all-reduce when sharded)
+    double sums_local[GICP_NSUM];    // this GPU's sums
+    double prev_fit, prev_rmse, fitness, rmse;
+    double rel_fit, rel_rmse, n_src_total;
+    int it, max_it, done, converged;
+    unsigned ticket; int evals;
+    double hist_fit[GICP_HIST], hist_rmse[GICP_HIST];
+};
+
+struct GicpArgs {
+    GridDDev tgt;                    // target index
+    const double* tgt_m;             // effective normals of the target, grid order
+    const P4d* src;                  // source points, cell-sorted order, idx = original index
+    const double* src_m;             // effective normals of the source, same order
+    uint32_t begin, end;             // this GPU's shard of the sorted source
+    double radius2, a;               // max_correspondence_distance^2, 1 - epsilon
+    double* partials;                // [gridDim.x][GICP_NSUM]
+    int32_t* corr;                   // optional: corr[source original index] = target original index or -1
+    GicpState* st;
+    int mode;                        // 0: reduce into sums_local; 1: reduce into sums and finalize on the device
+};
+
+// LDL^T solve of the symmetric 6x6 (Open3D: SolveLinearSystemPSD -> A.ldlt().solve(b)), no pivoting, oracle order
+__device__ bool ldlt_solve6_d(const double A[36], const double b[6], double x[6]) {
+    double L[36], D[6];
+    for (int i = 0; i < 36; i++) L[i] = 0.0;
+    for (int j = 0; j < 6; j++) {
+        double d = A[j * 6 + j];
+        for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
+        D[j] = d;
+        if (d == 0.0) return false;
+        for (int i = j + 1; i < 6; i++) {
+            double v = A[i * 6 + j];
+            for (int k = 0; k < j; k++) v -= L[i * 6 + k] * L[j * 6 + k] * D[k];
+            L[i * 6 + j] = v / d;
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; i++) { double v = b[i]; for (int k = 0; k < i; k++) v -= L[i * 6 + k] * y[k]; y[i] = v; }
+    for (int i = 0; i < 6; i++) y[i] /= D[i];
+    for (int i = 5; i >= 0; i--) { double v = y[i]; for (int k = i + 1; k < 6; k++) v -= L[k * 6 + i] * x[k]; x[i] = v; }
+    return true;
+}
+
+// fitness / inlier_rmse of the evaluation just reduced, Open3D's stopping rule, and the next T = [Rz Ry Rx | t] T
+__device__ __noinline__ void gicp_finalize(GicpState* st) {
+    const double* s = st->sums;
+    const double fit = st->n_src_total > 0 ? s[27] / st->n_src_total : 0.0;
+    const double rm = s[27] > 0 ? sqrt(s[28] / s[27]) : 0.0;
+    st->fitness = fit; st->rmse = rm;
+    if (st->evals < GICP_HIST) { st->hist_fit[st->evals] = fit; st->hist_rmse[st->evals] = rm; }
+    st->evals++;
+    if (st->it > 0 && fabs(st->prev_fit - fit) < st->rel_fit && fabs(st->prev_rmse - rm) < st->rel_rmse) { st->converged = 1; st->done = 1; return; }
+    if (st->it >= st->max_it) { st->done = 1; return; }
+    st->prev_fit = fit; st->prev_rmse = rm;
+    double A[36], b[6], x[6];
+    int q = 0;
+    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) { A[r * 6 + c] = s[q]; A[c * 6 + r] = s[q]; q++; }
+    for (int r = 0; r < 6; r++) b[r] = -s[21 + r];
+    if (!(s[27] < 1.0) && ldlt_solve6_d(A, b, x)) {
+        const double ca = cos(x[0]), sa = sin(x[0]), cb = cos(x[1]), sb = sin(x[1]), cg = cos(x[2]), sg = sin(x[2]);
+        double U[16];
+        U[0] = cg * cb; U[1] = cg * sb * sa - sg * ca; U[2] = cg * sb * ca + sg * sa; U[3] = x[3];
+        U[4] = sg * cb; U[5] = sg * sb * sa + cg * ca; U[6] = sg * sb * ca - cg * sa; U[7] = x[4];
+        U[8] = -sb;     U[9] = cb * sa;                U[10] = cb * ca;               U[11] = x[5];
+        U[12] = 0; U[13] = 0; U[14] = 0; U[15] = 1;
+        double Tn[16];
+        for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) {
+            double acc = 0;
+            for (int k = 0; k < 4; k++) acc += U[i * 4 + k] * st->T[k * 4 + j];
+            Tn[i * 4 + j] = acc;
+        }
+        for (int i = 0; i < 16; i++) st->T[i] = Tn[i];
+    }
+    st->it++;
+}
+
+__global__ void k_gicp_finalize(GicpState* st) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) gicp_finalize(st);
+}
+
+__global__ void __launch_bounds__(GICP_THREADS, 2) k_gicp_linearize(GicpArgs A) {
+    GicpState* st = A.st;
+    if (st->done) return;
+    __shared__ double s_red[GICP_WARPS][GICP_NSUM];
+    __shared__ bool s_last;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double R[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) R[i * 3 + j] = st->T[i * 4 + j];
+        t[i] = st->T[i * 4 + 3];
+    }
+    double acc[GICP_NSUM];
+#pragma unroll
+    for (int i = 0; i < GICP_NSUM; i++) acc[i] = 0.0;
+
+    const uint32_t n_here = A.end - A.begin;
+    const uint32_t n_chunks = (n_here + 31) >> 5;
+    for (uint32_t chunk = blockIdx.x * GICP_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * GICP_WARPS) {
+        const uint32_t p = A.begin + (chunk << 5) + lane;
+        const bool valid = p < A.end;
+        double px = 0, py = 0, pz = 0; long long sidx = -1;
+        if (valid) load_p4d(&A.src[p], px, py, pz, sidx);
+        const double vx = R[0] * px + R[1] * py + R[2] * pz + t[0];
+        const double vy = R[3] * px + R[4] * py + R[5] * pz + t[1];
+        const double vz = R[6] * px + R[7] * py + R[8] * pz + t[2];
+        // phase 1: 32 / LPG queries per round, the owner lane keeps its own result
+        double my_d2 = INFINITY; uint32_t my_pos = 0xffffffffu;
+        constexpr int QPR = 32 / GICP_LPG;
+#pragma unroll 1
+        for (int round = 0; round < GICP_LPG; round++) {
+            const int ql = round * QPR + (lane / GICP_LPG);
+            const double qx = shfl_d(full, vx, ql), qy = shfl_d(full, vy, ql), qz = shfl_d(full, vz, ql);
+            const bool qa = __shfl_sync(full, (int)valid, ql) != 0;
+            double bd; uint32_t bp; long long bi;
+            nn1_group<GICP_LPG>(A.tgt, qx, qy, qz, qa, A.radius2, bd, bp, bi);
+            const int from = (lane % QPR) * GICP_LPG;
+            const double rd = shfl_d(full, bd, from);
+            const uint32_t rp = __shfl_sync(full, bp, from);
+            if (lane / QPR == round) { my_d2 = rd; my_pos = rp; }
+        }
+        // phase 2: one lane per correspondence
+        const bool hit = valid && my_pos != 0xffffffffu;
+        long long tidx = -1;
+        if (hit) {
+            double tx, ty, tz;
+            load_p4d(&A.tgt.pts[my_pos], tx, ty, tz, tidx);
+            const double* um = &A.tgt_m[3 * (size_t)my_pos];
+            const double* sm = &A.src_m[3 * (size_t)p];
+            const double u0 = um[0], u1 = um[1], u2 = um[2];
+            const double m0 = sm[0], m1 = sm[1], m2 = sm[2];
+            const double v0 = R[0] * m0 + R[1] * m1 + R[2] * m2;
+            const double v1 = R[3] * m0 + R[4] * m1 + R[5] * m2;
+            const double v2 = R[6] * m0 + R[7] * m1 + R[8] * m2;
+            const double p0 = u0 + v0, p1 = u1 + v1, p2 = u2 + v2;
+            const double q0 = u0 - v0, q1 = u1 - v1, q2 = u2 - v2;
+            const double l1 = 2.0 - 0.5 * A.a * (p0 * p0 + p1 * p1 + p2 * p2);
+            const double l2 = 2.0 - 0.5 * A.a * (q0 * q0 + q1 * q1 + q2 * q2);
+            const double al = A.a / (4.0 * l1), be = A.a / (4.0 * l2);
+            const double N00 = 0.5 + al * p0 * p0 + be * q0 * q0, N01 = al * p0 * p1 + be * q0 * q1, N02 = al * p0 * p2 + be * q0 * q2;
+            const double N11 = 0.5 + al * p1 * p1 + be * q1 * q1, N12 = al * p1 * p2 + be * q1 * q2;
+            const double N22 = 0.5 + al * p2 * p2 + be * q2 * q2;
+            const double d0 = vx - tx, d1 = vy - ty, d2 = vz - tz;
+            // B = N S, S = -[vs]x
+            const double B00 = N02 * vy - N01 * vz, B01 = N00 * vz - N02 * vx, B02 = N01 * vx - N00 * vy;
+            const double B10 = N12 * vy - N11 * vz, B11 = N01 * vz - N12 * vx, B12 = N11 * vx - N01 * vy;
+            const double B20 = N22 * vy - N12 * vz, B21 = N02 * vz - N22 * vx, B22 = N12 * vx - N02 * vy;
+            // top-left S^T B (symmetric), top-right S^T N = B^T, bottom-right N
+            acc[0] += vy * B20 - vz * B10; acc[1] += vy * B21 - vz * B11; acc[2] += vy * B22 - vz * B12;
+            acc[3] += B00; acc[4] += B10; acc[5] += B20;
+            acc[6] += vz * B01 - vx * B21; acc[7] += vz * B02 - vx * B22;
+            acc[8] += B01; acc[9] += B11; acc[10] += B21;
+            acc[11] += vx * B12 - vy * B02;
+            acc[12] += B02; acc[13] += B12; acc[14] += B22;
+            acc[15] += N00; acc[16] += N01; acc[17] += N02; acc[18] += N11; acc[19] += N12; acc[20] += N22;
+            const double g0 = N00 * d0 + N01 * d1 + N02 * d2, g1 = N01 * d0 + N11 * d1 + N12 * d2, g2 = N02 * d0 + N12 * d1 + N22 * d2;
+            acc[21] += vy * g2 - vz * g1; acc[22] += vz * g0 - vx * g2; acc[23] += vx * g1 - vy * g0;
+            acc[24] += g0; acc[25] += g1; acc[26] += g2;
+            acc[27] += 1.0; acc[28] += my_d2; acc[29] += d0 * g0 + d1 * g1 + d2 * g2;
+        }
+        if (A.corr && valid) A.corr[sidx] = hit ? (int32_t)tidx : -1;
+    }
+    // epilogue: warp tree, CTA partial, last CTA adds the partials in CTA order
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < GICP_NSUM; i++) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(full, v, o);
+        if (lane == 0) s_red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < GICP_NSUM) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < GICP_WARPS; w++) v += s_red[w][threadIdx.x];
+        A.partials[(size_t)blockIdx.x * GICP_NSUM + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&st->ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double* out = A.mode == 1 ? st->sums : st->sums_local;
+    if (threadIdx.x < GICP_NSUM) {
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; b++) v += __ldcg(&A.partials[(size_t)b * GICP_NSUM + threadIdx.x]);
+        out[threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        st->ticket = 0;
+        if (A.mode == 1) gicp_finalize(st);
+    }
+}
+
+// effective normal per point, gathered into the order of `order` (cell-sorted): e1 when n.x < -0.99 (Open3D's
+// GetRotationFromE1ToX returns the identity there), the normal otherwise
+__global__ void __launch_bounds__(256) k_gicp_eff_normals(const P4d* __restrict__ sorted, const double* __restrict__ nrm, uint32_t n,
+                                                          double* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y, z; long long idx;
+    load_p4d(&sorted[i], x, y, z, idx);
+    double n0 = nrm[3 * (size_t)idx], n1 = nrm[3 * (size_t)idx + 1], n2 = nrm[3 * (size_t)idx + 2];
+    if (n0 < -0.99) { n0 = 1.0; n1 = 0.0; n2 = 0.0; }
+    out[3 * (size_t)i] = n0; out[3 * (size_t)i + 1] = n1; out[3 * (size_t)i + 2] = n2;
+}
+
+__global__ void k_fill_i32(int32_t* p, uint32_t n, int32_t v) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+struct b2_gicp_s {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    b2_gicp_params prm{};
+    GridD tgt_grid, src_grid;
+    DevBuf tgt_m, src_m, partials, state, corr;
+    PinBuf pin;
+    size_t n_tgt = 0, n_src = 0;
+    uint32_t src_valid = 0;
+    bool have_tgt = false, have_src = false;
+    int rank = 0, world = 1;
+    b2_comm_s* comm = nullptr;
+    int grid_blocks = 1;
+    float last_ms = 0.f; int last_launches = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+static int gicp_valid_count(const GridD& g, cudaStream_t s, uint32_t* out) {
+    const size_t ncell = (size_t)g.dev.nx * g.dev.ny * g.dev.nz;
+    *out = 0;
+    if (!g.n) return B2_OK;
+    B2_CUDA(cudaMemcpyAsync(out, g.dev.cell_start + ncell, 4, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    return B2_OK;
+}
+
+static void gicp_fill_args(b2_gicp_s* h, GicpArgs& a, int mode, int32_t* corr) {
+    a.tgt = h->tgt_grid.dev;
+    a.tgt_m = h->tgt_m.as<double>();
+    a.src = h->src_grid.dev.pts;
+    a.src_m = h->src_m.as<double>();
+    const uint64_t nv = h->src_valid;
+    a.begin = (uint32_t)(nv * (uint64_t)h->rank / (uint64_t)h->world);
+    a.end = (uint32_t)(nv * (uint64_t)(h->rank + 1) / (uint64_t)h->world);
+    a.radius2 = h->prm.max_correspondence_distance * h->prm.max_correspondence_distance;
+    a.a = 1.0 - h->prm.epsilon;
+    a.partials = h->partials.as<double>();
+    a.corr = corr;
+    a.st = h->state.as<GicpState>();
+    a.mode = mode;
+    const uint32_t chunks = (a.end - a.begin + 31) / 32;
+    h->grid_blocks = (int)std::max<uint32_t>(1u, std::min<uint32_t>((chunks + GICP_WARPS - 1) / GICP_WARPS, (uint32_t)device_sm_count() * 2u));
+}
+
+static int gicp_prepare(b2_gicp_s* h) {
+    if (!h->have_tgt || !h->have_src) { set_error("gicp: set_target and set_source first"); return B2_ERR_STATE; }
+    B2_CHECK(h->partials.reserve((size_t)device_sm_count() * 2 * GICP_NSUM * 8 + 256));
+    B2_CHECK(h->state.reserve(sizeof(GicpState)));
+    B2_CHECK(h->pin.reserve(sizeof(GicpState)));
+    return B2_OK;
+}
+
+static int gicp_upload_state(b2_gicp_s* h, const double T[16], int max_it) {
+    GicpState* hs = h->pin.as<GicpState>();
+    memset(hs, 0, sizeof(GicpState));
+    memcpy(hs->T, T, 16 * 8);
+    hs->rel_fit = h->prm.relative_fitness; hs->rel_rmse = h->prm.relative_rmse;
+    hs->n_src_total = (double)h->n_src;
+    hs->max_it = max_it;
+    B2_CUDA(cudaMemcpyAsync(h->state.p, hs, sizeof(GicpState), cudaMemcpyHostToDevice, h->stream));
+    return B2_OK;
+}
+
+extern "C" {
+
+void b2_gicp_default_params(b2_gicp_params* p) {
+    if (!p) return;
+    p->max_correspondence_distance = 1.0;   /* Multi_LiCa config/params.yaml:52 */
+    p->epsilon = 0.005;                     /* :58 (Calibration class default 1e-4, Calibration.py:99) */
+    p->relative_fitness = 1e-7;             /* :59 */
+    p->relative_rmse = 1e-7;                /* :60 */
+    p->max_iteration = 100;                 /* :61 */
+}
+
+int b2_gicp_create(b2_gicp_t* out, const b2_gicp_params* params) {
+    if (!out) return B2_ERR_ARG;
+    *out = nullptr;
+    b2_gicp_s* h = new b2_gicp_s();
+    if (params) h->prm = *params; else b2_gicp_default_params(&h->prm);
+    if (cudaGetDevice(&h->device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&h->e0) != cudaSuccess || cudaEventCreate(&h->e1) != cudaSuccess) {
+        set_error("b2_gicp_create: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h; return B2_ERR_CUDA;
+    }
+    *out = h;
+    return B2_OK;
+}
+
+int b2_gicp_destroy(b2_gicp_t h) {
+    if (!h) return B2_OK;
+    h->tgt_grid.release(); h->src_grid.release();
+    h->tgt_m.release(); h->src_m.release(); h->partials.release(); h->state.release(); h->corr.release(); h->pin.release();
+    if (h->e0) cudaEventDestroy(h->e0);
+    if (h->e1) cudaEventDestroy(h->e1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return B2_OK;
+}
+
+int b2_gicp_set_params(b2_gicp_t h, const b2_gicp_params* p) {
+    if (!h || !p) return B2_ERR_ARG;
+    h->prm = *p;
+    return B2_OK;
+}
+
+static int gicp_set_cloud(b2_gicp_s* h, b2_cloud_s* c, GridD& grid, DevBuf& m, double ppc, uint32_t* n_valid) {
+    if (!c->has_normals) {
+        set_error("gicp: the cloud has no normals; call b2_cloud_estimate_normals first (Calibration.py:327-328 does)");
+        return B2_ERR_STATE;
+    }
+    B2_CUDA(cudaSetDevice(h->device));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    B2_CHECK(grid.build(c->xyz.as<double>(), c->n, 0.0, ppc, h->stream));
+    B2_CHECK(gicp_valid_count(grid, h->stream, n_valid));
+    B2_CHECK(m.reserve(std::max<size_t>(c->n, 1) * 24));
+    if (*n_valid) {
+        k_gicp_eff_normals<<<(*n_valid + 255) / 256, 256, 0, h->stream>>>(grid.dev.pts, c->nrm.as<double>(), *n_valid, m.as<double>()); count_launch();
+        B2_CUDA(cudaGetLastError());
+    }
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}
+
+int b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target) {
+    if (!h || !target) return B2_ERR_ARG;
+    h->have_tgt = false;
+    uint32_t nv = 0;
+    B2_CHECK(gicp_set_cloud(h, target, h->tgt_grid, h->tgt_m, 2.0, &nv));
+    h->n_tgt = target->n;
+    h->have_tgt = true;
+    return B2_OK;
+}
+
+int b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source) {
+    if (!h || !source) return B2_ERR_ARG;
+    h->have_src = false;
+    uint32_t nv = 0;
+    B2_CHECK(gicp_set_cloud(h, source, h->src_grid, h->src_m, 8.0, &nv));
+    h->n_src = source->n;
+    h->src_valid = nv;
+    h->have_src = true;
+    return B2_OK;
+}
+
+int b2_gicp_set_shard(b2_gicp_t h, int rank, int world, b2_comm_t comm) {
+    if (!h || world < 1 || rank < 0 || rank >= world) return B2_ERR_ARG;
+    if (comm && (comm->rank != rank || comm->world != world)) { set_error("gicp: communicator rank/world mismatch"); return B2_ERR_ARG; }
+    h->rank = rank; h->world = world; h->comm = world > 1 ? comm : nullptr;
+    return B2_OK;
+}
+
+int b2_gicp_linearize(b2_gicp_t h, const double T[16], double sums[30], int32_t* corr) {
+    if (!h || !T || !sums) return B2_ERR_ARG;
+    B2_CUDA(cudaSetDevice(h->device));
+    B2_CHECK(gicp_prepare(h));
+    B2_CHECK(gicp_upload_state(h, T, 0));
+    int32_t* d_corr = nullptr;
+    if (corr && h->n_src) {
+        B2_CHECK(h->corr.reserve(h->n_src * 4));
+        d_corr = h->corr.as<int32_t>();
+        k_fill_i32<<<(unsigned)((h->n_src + 255) / 256), 256, 0, h->stream>>>(d_corr, (uint32_t)h->n_src, -1); count_launch();
+    }
+    GicpArgs a;
+    gicp_fill_args(h, a, 0, d_corr);
+    k_gicp_linearize<<<h->grid_blocks, GICP_THREADS, 0, h->stream>>>(a); count_launch();
+    B2_CUDA(cudaGetLastError());
+    GicpState* ds = h->state.as<GicpState>();
+    if (h->comm) B2_CHECK(comm_allreduce_sum_f64(h->comm, ds->sums_local, ds->sums_local, GICP_NSUM, h->stream));
+    B2_CUDA(cudaMemcpyAsync(sums, ds->sums_local, GICP_NSUM * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (d_corr) B2_CUDA(cudaMemcpyAsync(corr, d_corr, h->n_src * 4, cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}
+
+int b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* fitness, double* inlier_rmse,
+                  int* iterations, int* converged) {
+    if (!h || !init || !T_out) return B2_ERR_ARG;
+    if (h->world > 1 && !h->comm) { set_error("gicp: align on a sharded source needs a communicator (b2_gicp_set_shard)"); return B2_ERR_STATE; }
+    B2_CUDA(cudaSetDevice(h->device));
+    B2_CHECK(gicp_prepare(h));
+    const int max_it = std::max(0, h->prm.max_iteration);
+    B2_CHECK(gicp_upload_state(h, init, max_it));
+    GicpArgs a;
+    gicp_fill_args(h, a, h->comm ? 0 : 1, nullptr);
+    GicpState* ds = h->state.as<GicpState>();
+    GicpState* hs = h->pin.as<GicpState>();
+    // evaluations are enqueued in chunks; between chunks the host reads the small state back (one sync per chunk)
+    const size_t per = std::max<size_t>(1, (size_t)(a.end - a.begin));
+    const int chunk = (int)std::min<size_t>(8, std::max<size_t>(1, 2000000 / per));
+    int launched = 0, launches = 0;
+    B2_CUDA(cudaEventRecord(h->e0, h->stream));
+    const int total = max_it + 1;
+    while (launched < total) {
+        const int m = std::min(chunk, total - launched);
+        for (int i = 0; i < m; i++) {
+            k_gicp_linearize<<<h->grid_blocks, GICP_THREADS, 0, h->stream>>>(a); launches++;
+            if (h->comm) {
+                B2_CHECK(comm_allreduce_sum_f64(h->comm, ds->sums_local, ds->sums, GICP_NSUM, h->stream));
+                k_gicp_finalize<<<1, 32, 0, h->stream>>>(ds); launches++;
+            }
+        }
+        B2_CUDA(cudaGetLastError());
+        launched += m;
+        B2_CUDA(cudaMemcpyAsync(&hs->it, &ds->it, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+        if (hs->done) break;
+    }
+    B2_CUDA(cudaEventRecord(h->e1, h->stream));
+    B2_CUDA(cudaMemcpyAsync(hs, ds, sizeof(GicpState), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    count_launch(launches);
+    cudaEventElapsedTime(&h->last_ms, h->e0, h->e1);
+    h->last_launches = launches;
+    memcpy(T_out, hs->T, 16 * 8);
+    if (fitness) *fitness = hs->fitness;
+    if (inlier_rmse) *inlier_rmse = hs->rmse;
+    if (iterations) *iterations = hs->it;
+    if (converged) *converged = hs->converged;
+    return B2_OK;
+}
+
+int b2_gicp_get_history(b2_gicp_t h, double* fitness, double* inlier_rmse, int capacity, int* n_evaluations) {
+    if (!h || capacity < 0) return B2_ERR_ARG;
+    const GicpState* hs = h->pin.as<GicpState>();
+    if (!hs) { set_error("gicp: no align call yet"); return B2_ERR_STATE; }
+    const int n = std::min(std::min(hs->evals, GICP_HIST), capacity);
+    for (int i = 0; i < n; i++) { if (fitness) fitness[i] = hs->hist_fit[i]; if (inlier_rmse) inlier_rmse[i] = hs->hist_rmse[i]; }
+    if (n_evaluations) *n_evaluations = hs->evals;
+    return B2_OK;
+}
+
+int b2_gicp_last_gpu_ms(b2_gicp_t h, float* ms, int* launches) {
+    if (!h) return B2_ERR_ARG;
+    if (ms) *ms = h->last_ms;
+    if (launches) *launches = h->last_launches;
+    return B2_OK;
+}
+
+int b2_gicp_index_info(b2_gicp_t h, double* target_cell_edge, double* target_points_per_cell, uint32_t* shard_begin, uint32_t* shard_end) {
+    if (!h || !h->have_tgt) return B2_ERR_STATE;
+    if (target_cell_edge) *target_cell_edge = h->tgt_grid.dev.h;
+    if (target_points_per_cell) *target_points_per_cell = h->tgt_grid.ppc;
+    const uint64_t nv = h->src_valid;
+    if (shard_begin) *shard_begin = (uint32_t)(nv * (uint64_t)h->rank / (uint64_t)h->world);
+    if (shard_end) *shard_end = (uint32_t)(nv * (uint64_t)(h->rank + 1) / (uint64_t)h->world);
+    return B2_OK;
+}
+
+}  // extern "C"

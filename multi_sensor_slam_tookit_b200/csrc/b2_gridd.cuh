@@ -1,0 +1,180 @@
+// fp64 uniform-grid index over a device-resident cloud, with exact ring-expanding nearest-neighbour search.
+// Replaces the kd-trees Open3D builds inside estimate_normals() and registration_generalized_icp()
+// (Calibration_Tookit/Multi_LiCa/multi_lidar_calibrator/calibration/Calibration.py:327-340) and the FLANN tree PCL's NDT
+// uses for getFitnessScore (Calibration_Tookit/multi_lidar/.../multi_lidar_calibrator.cpp:66).
+//
+// HBM layout:  pts        P4d[n]        cell-sorted, one 32-byte sector per point: x, y, z, original index
+//              cell_start u32[ncell+2]  exclusive prefix of per-cell counts, x fastest
+// A row of consecutive x cells is one contiguous run of pts, so a (2r+1)^3 block costs (2r+1)^2 pairs of cell_start
+// loads and then streams candidates with aligned 128-bit loads.
+//
+// Exactness: after every cell within Chebyshev ring r of the query's cell has been scanned, an unseen point is at
+// least (r + m) * h away, m = distance (in cells) from the query to the nearest face of its own cell. The search
+// stops when the k-th best squared distance is below that bound (shrunk by 1e-9 for the rounding of the cell
+// assignment), when the bound passes the caller's radius, or when the ring covers the grid.
+// Distances are (dx*dx + dy*dy) + dz*dz in double without FMA; ordering is (distance, original index).
+#pragma once
+#include "b2_common.cuh"
+
+namespace b2 {
+
+struct alignas(32) P4d { double x, y, z; long long idx; };
+
+struct GridDDev {
+    const P4d* pts;
+    const uint32_t* cell_start;
+    double ox, oy, oz, h, inv_h;
+    int nx, ny, nz;
+    uint32_t n;
+};
+
+struct GridD {
+    DevBuf pts, cell_start, work;
+    GridDDev dev{};
+    size_t n = 0;
+    double ppc = 0.0;          // points per occupied cell of the built grid
+    // d_xyz: device, n*3 doubles. h_request > 0 fixes the cell edge (raised only if the cell budget requires it);
+    // otherwise the edge is chosen so that an occupied cell holds about target_ppc points.
+    int build(const double* d_xyz, size_t n, double h_request, double target_ppc, cudaStream_t s);
+    void release() { pts.release(); cell_start.release(); work.release(); dev = GridDDev{}; n = 0; }
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void load_p4d(const P4d* p, double& x, double& y, double& z, long long& idx) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    x = a.x; y = a.y; z = b.x; idx = __double_as_longlong(b.y);
+}
+
+__device__ __forceinline__ double shfl_d(unsigned mask, double v, int src) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(mask, lo, src); hi = __shfl_sync(mask, hi, src);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_d(unsigned mask, double v, int o) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(mask, lo, o); hi = __shfl_xor_sync(mask, hi, o);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_up_d(unsigned mask, double v, int o) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(mask, lo, o); hi = __shfl_up_sync(mask, hi, o);
+    return __hiloint2double(hi, lo);
+}
+
+// Geometry of one query against a grid: cell, and the per-ring exactness bound.
+struct QueryCell {
+    int cx, cy, cz;
+    double m;          // distance to the nearest own-cell face, in cells (0..0.5)
+    bool finite;
+};
+__device__ __forceinline__ QueryCell query_cell(const GridDDev& g, double qx, double qy, double qz) {
+    QueryCell q;
+    const double fx = (qx - g.ox) * g.inv_h, fy = (qy - g.oy) * g.inv_h, fz = (qz - g.oz) * g.inv_h;
+    q.finite = isfinite(fx) && isfinite(fy) && isfinite(fz) && fabs(fx) < 1e9 && fabs(fy) < 1e9 && fabs(fz) < 1e9;
+    const double flx = floor(fx), fly = floor(fy), flz = floor(fz);
+    q.cx = q.finite ? (int)flx : 0; q.cy = q.finite ? (int)fly : 0; q.cz = q.finite ? (int)flz : 0;
+    double m = fmin(fx - flx, 1.0 - (fx - flx));
+    m = fmin(m, fmin(fy - fly, 1.0 - (fy - fly)));
+    m = fmin(m, fmin(fz - flz, 1.0 - (fz - flz)));
+    q.m = m;
+    return q;
+}
+// squared lower bound on the distance of any point outside ring r (see header comment)
+__device__ __forceinline__ double ring_bound2(const GridDDev& g, const QueryCell& q, int r) {
+    const double b = ((double)r + q.m) * g.h;
+    return b * b * (1.0 - 1e-9);
+}
+// rings needed to cover the whole grid from this query's cell
+__device__ __forceinline__ int rings_to_cover(const GridDDev& g, const QueryCell& q) {
+    int r = max(max(q.cx, g.nx - 1 - q.cx), max(max(q.cy, g.ny - 1 - q.cy), max(q.cz, g.nz - 1 - q.cz)));
+    return max(r, 0);
+}
+
+// [begin, end) of the run of pts covering cells x0..x1 (clamped) of row (y, z); empty when the row is outside
+__device__ __forceinline__ void row_range(const GridDDev& g, int x0, int x1, int y, int z, uint32_t& b, uint32_t& e) {
+    x0 = max(x0, 0); x1 = min(x1, g.nx - 1);
+    const bool ok = (x0 <= x1) && y >= 0 && y < g.ny && z >= 0 && z < g.nz;
+    const size_t row = ((size_t)(ok ? z : 0) * g.ny + (ok ? y : 0)) * g.nx;
+    b = ok ? __ldg(&g.cell_start[row + x0]) : 0u;
+    e = ok ? __ldg(&g.cell_start[row + x1 + 1]) : 0u;
+}
+
+// Exact 1-NN by a group of LPG consecutive lanes (all lanes of the warp must call; `active` per group).
+// radius2: candidates at or beyond it are ignored (GICP max_correspondence_distance^2).
+// Result on every lane of the group: best_d2 (radius2-or-larger sentinel = none), best_pos (position in g.pts), best_idx.
+template <int LPG>
+__device__ __forceinline__ void nn1_group(const GridDDev& g, double qx, double qy, double qz, bool active, double radius2,
+                                          double& best_d2, uint32_t& best_pos, long long& best_idx) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, sub = lane & (LPG - 1);
+    double bd = INFINITY; uint32_t bp = 0xffffffffu; long long bi = 0x7fffffffffffffffLL;
+    const QueryCell qc = query_cell(g, qx, qy, qz);
+    active = active && qc.finite;
+    const int rmax = rings_to_cover(g, qc);
+    auto consider = [&](uint32_t p) {
+        double x, y, z; long long idx;
+        load_p4d(&g.pts[p], x, y, z, idx);
+        const double ddx = qx - x, ddy = qy - y, ddz = qz - z;
+        const double d = ddx * ddx + ddy * ddy + ddz * ddz;
+        if (d < radius2 && (d < bd || (d == bd && idx < bi))) { bd = d; bp = p; bi = idx; }
+    };
+    auto group_min = [&]() {
+        __syncwarp();
+#pragma unroll
+        for (int o = LPG >> 1; o > 0; o >>= 1) {
+            const double od = shfl_xor_d(full, bd, o);
+            const uint32_t op = __shfl_xor_sync(full, bp, o);
+            const long long oi = ((long long)__shfl_xor_sync(full, (int)(bi >> 32), o) << 32) | (unsigned)__shfl_xor_sync(full, (int)bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bp = op; bi = oi; }
+        }
+    };
+    // rings 0 and 1 together: the 3x3x3 block is nine full rows; all eighteen bounds are requested before any is consumed
+    if (active) {
+        uint32_t rb[9], re[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) row_range(g, qc.cx - 1, qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, rb[i], re[i]);
+#pragma unroll
+        for (int i = 0; i < 9; i++)
+            for (uint32_t p = rb[i] + sub; p < re[i]; p += LPG) consider(p);
+    }
+    group_min();
+    int r = 1;
+    bool more = active;
+    {
+        const double bound2 = ring_bound2(g, qc, r);
+        if (bd < bound2 || bound2 >= radius2 || r >= rmax) more = false;
+    }
+    // rare: the neighbour (if any) lies beyond the block; widen shell by shell
+    while (__any_sync(full, more)) {
+        r++;
+        if (more) {
+            const int side = 2 * r + 1;
+            for (int rowi = 0; rowi < side * side; rowi++) {
+                const int dy = rowi % side - r, dz = rowi / side - r;
+                const bool shell_row = (max(abs(dy), abs(dz)) == r);
+                uint32_t b, e;
+                if (shell_row) {
+                    row_range(g, qc.cx - r, qc.cx + r, qc.cy + dy, qc.cz + dz, b, e);
+                    for (uint32_t p = b + sub; p < e; p += LPG) consider(p);
+                } else {                       // inner rows of the shell contribute their two end cells only
+                    row_range(g, qc.cx - r, qc.cx - r, qc.cy + dy, qc.cz + dz, b, e);
+                    for (uint32_t p = b + sub; p < e; p += LPG) consider(p);
+                    row_range(g, qc.cx + r, qc.cx + r, qc.cy + dy, qc.cz + dz, b, e);
+                    for (uint32_t p = b + sub; p < e; p += LPG) consider(p);
+                }
+            }
+        }
+        group_min();
+        if (more) {
+            const double bound2 = ring_bound2(g, qc, r);
+            if (bd < bound2 || bound2 >= radius2 || r >= rmax) more = false;
+        }
+    }
+    best_d2 = bd; best_pos = bp; best_idx = bi;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b2

@@ -84,6 +84,19 @@ def lib():
     L.o_extract_features.restype = C.c_int
     L.o_extract_features.argtypes = [f32p, i32p, C.c_int, i32p, i32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
                                      f32p, i32p, i32p, i32p, i32p, i32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    od64 = _opt(f64p)
+    L.o_o3d_voxel_down_sample.restype = C.c_int
+    L.o_o3d_voxel_down_sample.argtypes = [f64p, C.c_int, C.c_double, f64p, oi32]
+    L.o_gicp_normals_covs.argtypes = [f64p, C.c_int, C.c_int, C.c_double, od64, od64, C.c_int]
+    L.o_gicp_tree_create.restype = C.c_void_p
+    L.o_gicp_tree_create.argtypes = [f64p, C.c_int]
+    L.o_gicp_tree_destroy.argtypes = [C.c_void_p]
+    L.o_gicp_linearize.argtypes = [f64p, f64p, C.c_int, f64p, f64p, C.c_int, C.c_void_p, f64p, C.c_double, f64p, oi32, C.c_int]
+    L.o_gicp_solve_update.restype = C.c_int
+    L.o_gicp_solve_update.argtypes = [f64p, f64p]
+    L.o_gicp_register.restype = C.c_int
+    L.o_gicp_register.argtypes = [f64p, f64p, C.c_int, f64p, f64p, C.c_int, f64p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                  f64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
     _LIB = L
     return L
 
@@ -247,3 +260,64 @@ def extract_features(proj, edge_th=1.0, surf_th=0.1, surf_leaf=0.4, stable=True)
     return dict(curvature=curv, picked_mask=picked_after_mask, picked=picked, label=label,
                 corner_idx=cidx[:nc].copy(), corner=ext[cidx[:nc]].copy(), surf_idx=sidx[:ns.value].copy(),
                 surf_ring_start=srs, surf=sds[:nds.value].copy())
+
+
+# ---------------------------------------------------------------- Open3D GICP path (Multi_LiCa)
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def o3d_voxel_down_sample(pts, voxel):
+    """Open3D voxel_down_sample restatement; output in ascending (z, y, x) voxel order. Returns (points, rank_of_point)."""
+    p = _f64(pts).reshape(-1, 3)
+    out = np.empty((max(len(p), 1), 3), np.float64)
+    rank = np.empty(max(len(p), 1), np.int32)
+    m = lib().o_o3d_voxel_down_sample(p, len(p), float(voxel), out, rank)
+    return out[:m].copy(), rank[:len(p)].copy()
+
+
+def gicp_normals_covs(pts, knn=30, eps=0.005, threads=8):
+    p = _f64(pts).reshape(-1, 3)
+    nrm = np.empty((len(p), 3), np.float64)
+    cov = np.empty((len(p), 9), np.float64)
+    lib().o_gicp_normals_covs(p, len(p), int(knn), float(eps), nrm, cov, threads)
+    return nrm, cov.reshape(-1, 3, 3)
+
+
+class GicpOracle:
+    """One target (with its kd-tree) and one source, covariances given; linearize / register as Open3D does."""
+
+    def __init__(self, src, src_cov, tgt, tgt_cov, threads=8):
+        self.L = lib()
+        self.src, self.src_cov = _f64(src).reshape(-1, 3), _f64(src_cov).reshape(-1, 9)
+        self.tgt, self.tgt_cov = _f64(tgt).reshape(-1, 3), _f64(tgt_cov).reshape(-1, 9)
+        self.threads = threads
+        self.tree = self.L.o_gicp_tree_create(self.tgt, len(self.tgt))
+
+    def __del__(self):
+        if getattr(self, "tree", None):
+            self.L.o_gicp_tree_destroy(self.tree)
+            self.tree = None
+
+    def linearize(self, T, max_corr, want_corr=False, begin=0, end=None):
+        """sums[30] (+ correspondences) of source[begin:end] at transform T."""
+        end = len(self.src) if end is None else end
+        s, c = self.src[begin:end], self.src_cov[begin:end]
+        sums = np.zeros(30, np.float64)
+        corr = np.empty(max(len(s), 1), np.int32) if want_corr else None
+        self.L.o_gicp_linearize(np.ascontiguousarray(s), np.ascontiguousarray(c), len(s), self.tgt, self.tgt_cov, len(self.tgt),
+                                self.tree, _f64(T).reshape(16), float(max_corr), sums, corr, self.threads)
+        return (sums, corr[:len(s)]) if want_corr else sums
+
+    def solve_update(self, sums):
+        U = np.empty(16, np.float64)
+        ok = self.L.o_gicp_solve_update(_f64(sums), U)
+        return U.reshape(4, 4), bool(ok)
+
+    def register(self, init, max_corr, rel_fit, rel_rmse, max_it):
+        T = np.empty(16, np.float64)
+        fit, rmse = C.c_double(), C.c_double()
+        it = self.L.o_gicp_register(self.src, self.src_cov, len(self.src), self.tgt, self.tgt_cov, len(self.tgt),
+                                    _f64(init).reshape(16), float(max_corr), float(rel_fit), float(rel_rmse), int(max_it),
+                                    T, C.byref(fit), C.byref(rmse), self.threads)
+        return dict(transformation=T.reshape(4, 4), fitness=fit.value, inlier_rmse=rmse.value, iterations=it)
