@@ -44,6 +44,8 @@ int         b2_version(void);
 const char* b2_last_error(void);                 /* thread-local, never NULL */
 int         b2_device_count(void);
 int         b2_set_device(int ordinal);          /* device used by handles created afterwards on this thread */
+/* device buffers released by handles are pooled for reuse; this returns the pool to the driver */
+int         b2_trim_memory(void);
 /* number of CUDA kernels this library has launched in this process so far (bench.py's gpu_launches) */
 unsigned long long b2_kernel_launch_count(void);
 

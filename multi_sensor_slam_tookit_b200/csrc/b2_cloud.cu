@@ -1,4 +1,5 @@
-// Device-resident fp64 cloud: grid index build, Open3D-style voxel_down_sample and estimate_normals, rigid transform.
+// Device-resident fp64 cloud: grid index build, Open3D-style voxel_down_sample and estimate_normals (32-ary BVH over
+// the Morton order), rigid transform.
 // Replaces, for Multi_LiCa's GICP calibration (Calibration_Tookit/Multi_LiCa/multi_lidar_calibrator/calibration/Calibration.py):
 //   :314-315  pcd.voxel_down_sample(voxel_size)   voxel = floor((p - (min - v/2)) / v), one double mean per voxel
 //   :327-328  pcd.estimate_normals()              KDTreeSearchParamKNN(30): covariance of the 30 nearest neighbours
@@ -257,6 +258,9 @@ __global__ void __launch_bounds__(128) k_vds_mean(const double* __restrict__ xyz
     out[3 * (size_t)s] = sx / cnt; out[3 * (size_t)s + 1] = sy / cnt; out[3 * (size_t)s + 2] = sz / cnt;
 }
 
+static int sort_by_u64(const unsigned long long* lin, size_t n, int bits, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb,
+                       void* scratch, cudaStream_t s, uint32_t** order);
+
 static int voxel_down_sample(b2_cloud_s* c, double voxel, b2_cloud_s* out, int32_t* h_rank) {
     cudaStream_t s = c->stream;
     const size_t n = c->n;
@@ -294,15 +298,8 @@ static int voxel_down_sample(b2_cloud_s* c, double voxel, b2_cloud_s* out, int32
     const unsigned nblk = (unsigned)((n + 255) / 256), nblk1 = (unsigned)((np1 + 255) / 256);
     k_vds_key<<<nblk, 256, 0, s>>>(xyz, (uint32_t)n, g, lin, ka, va); count_launch();
     B2_CUDA(cudaGetLastError());
-    uint32_t *ks, *vs;
-    B2_CHECK(radix_sort_pairs(ka, va, kb, vb, n, std::min(bits, 32), scratch, s, &ks, &vs));
-    if (bits > 32) {
-        // second key word: stable sort of the already low-word-sorted sequence by the high word
-        uint32_t* k2 = (ks == ka) ? kb : ka;
-        uint32_t* v2 = (vs == va) ? vb : va;
-        k_vds_key_hi<<<nblk, 256, 0, s>>>(lin, vs, (uint32_t)n, ks); count_launch();
-        B2_CHECK(radix_sort_pairs(ks, vs, k2, v2, n, bits - 32, scratch, s, &ks, &vs));
-    }
+    uint32_t* vs = nullptr;
+    B2_CHECK(sort_by_u64(lin, n, bits, ka, va, kb, vb, scratch, s, &vs));
     k_vds_heads<<<nblk1, 256, 0, s>>>(lin, vs, (uint32_t)n, g.invalid, flags); count_launch();
     B2_CUDA(cudaGetLastError());
     B2_CHECK(exclusive_scan_u32(flags, np1, scratch + sort_tmp_bytes(n), s));
@@ -397,65 +394,163 @@ __device__ __forceinline__ void warp_offer(WarpList& L, int K, double d, int idx
     }
 }
 
-__device__ __forceinline__ void warp_scan_run(const GridDDev& g, WarpList& L, int K, double qx, double qy, double qz, uint32_t b, uint32_t e) {
-    const int lane = threadIdx.x & 31;
-    for (uint32_t base = b; base < e; base += 32) {
-        const uint32_t p = base + lane;
-        const bool valid = p < e;
-        double d = INFINITY; int idx = 0x7fffffff;
-        if (valid) {
-            double x, y, z; long long id;
-            load_p4d(&g.pts[p], x, y, z, id);
-            const double dx = qx - x, dy = qy - y, dz = qz - z;
-            d = dx * dx + dy * dy + dz * dz;
-            idx = (int)id;
+// ---- 32-ary bounding-volume hierarchy over the Morton-sorted points (one tree level per factor of 32) -------------
+// Lidar clouds vary in density by orders of magnitude, so neighbourhoods are not found with a uniform grid here: a
+// leaf is 32 consecutive points of the Morton order, a node of level l holds 32 nodes of level l-1, and a warp tests
+// the 32 children of a node in one step (one lane per child box). Children are visited nearest first and skipped
+// once their box is farther than the current k-th neighbour (strictly: equal distances are still visited, a tied
+// point with a smaller index may hide there). Box distances use the same (dx*dx + dy*dy) + dz*dz association as
+// point distances, so rounding is monotone and the pruning is exact.
+constexpr int BVH_MAXL = 7;
+struct BvhDev {
+    const P4d* pts;
+    const double* box[BVH_MAXL];     // level l: count[l] boxes of 6 doubles (min xyz, max xyz)
+    uint32_t count[BVH_MAXL];
+    int levels;
+    uint32_t n;                      // finite points
+};
+
+__device__ __forceinline__ unsigned long long morton_expand21(unsigned long long v) {
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton_key(const double* __restrict__ xyz, uint32_t n, double ox, double oy, double oz, double scale,
+                                                    unsigned long long* __restrict__ lin, uint32_t* __restrict__ key_lo, uint32_t* __restrict__ vals,
+                                                    unsigned int* __restrict__ n_valid) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        const double x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+        unsigned long long k = ~0ull;
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            const unsigned long long qx = (unsigned long long)fmin(2097151.0, fmax(0.0, (x - ox) * scale));
+            const unsigned long long qy = (unsigned long long)fmin(2097151.0, fmax(0.0, (y - oy) * scale));
+            const unsigned long long qz = (unsigned long long)fmin(2097151.0, fmax(0.0, (z - oz) * scale));
+            k = morton_expand21(qx) | (morton_expand21(qy) << 1) | (morton_expand21(qz) << 2);
+            ok = true;
         }
-        warp_offer(L, K, d, idx, p, valid);
+        lin[i] = k; key_lo[i] = (uint32_t)k; vals[i] = i;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_valid, (unsigned)__popc(m));
+}
+
+// level 0: one warp per leaf of 32 points
+__global__ void __launch_bounds__(256) k_bvh_leaf_boxes(const P4d* __restrict__ pts, uint32_t n, double* __restrict__ box, uint32_t n_leaf) {
+    const uint32_t leaf = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (leaf >= n_leaf) return;
+    const uint32_t p = leaf * 32u + lane;
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (p < n) { double x, y, z; long long id; load_p4d(&pts[p], x, y, z, id); lo[0] = hi[0] = x; lo[1] = hi[1] = y; lo[2] = hi[2] = z; }
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[d] = fmin(lo[d], shfl_xor_d(0xffffffffu, lo[d], o)); hi[d] = fmax(hi[d], shfl_xor_d(0xffffffffu, hi[d], o)); }
+    if (lane < 3) box[6 * (size_t)leaf + lane] = lo[lane];
+    else if (lane < 6) box[6 * (size_t)leaf + lane] = hi[lane - 3];
+}
+// level l: one warp per node, lane j reads child j
+__global__ void __launch_bounds__(256) k_bvh_node_boxes(const double* __restrict__ child, uint32_t n_child, double* __restrict__ box, uint32_t n_node) {
+    const uint32_t node = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (node >= n_node) return;
+    const uint32_t c = node * 32u + lane;
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (c < n_child) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) { lo[d] = child[6 * (size_t)c + d]; hi[d] = child[6 * (size_t)c + 3 + d]; }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[d] = fmin(lo[d], shfl_xor_d(0xffffffffu, lo[d], o)); hi[d] = fmax(hi[d], shfl_xor_d(0xffffffffu, hi[d], o)); }
+    if (lane < 3) box[6 * (size_t)node + lane] = lo[lane];
+    else if (lane < 6) box[6 * (size_t)node + lane] = hi[lane - 3];
+}
+
+__device__ __forceinline__ double box_dist2(const double* __restrict__ b, double qx, double qy, double qz) {
+    const double2 a0 = __ldg(reinterpret_cast<const double2*>(b)), a1 = __ldg(reinterpret_cast<const double2*>(b) + 1),
+                  a2 = __ldg(reinterpret_cast<const double2*>(b) + 2);
+    // a0 = (lo.x, lo.y), a1 = (lo.z, hi.x), a2 = (hi.y, hi.z)
+    const double dx = fmax(0.0, fmax(a0.x - qx, qx - a1.y));
+    const double dy = fmax(0.0, fmax(a0.y - qy, qy - a2.x));
+    const double dz = fmax(0.0, fmax(a1.x - qz, qz - a2.y));
+    return dx * dx + dy * dy + dz * dz;
+}
+
+__device__ __forceinline__ void bvh_scan_leaf(const BvhDev& T, WarpList& L, int K, double qx, double qy, double qz, uint32_t leaf) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t p = leaf * 32u + lane;
+    const bool valid = p < T.n;
+    double d = INFINITY; int idx = 0x7fffffff;
+    if (valid) {
+        double x, y, z; long long id;
+        load_p4d(&T.pts[p], x, y, z, id);
+        const double dx = qx - x, dy = qy - y, dz = qz - z;
+        d = dx * dx + dy * dy + dz * dz;
+        idx = (int)id;
+    }
+    warp_offer(L, K, d, idx, p, valid);
+}
+
+// warp-wide exact K nearest neighbours of (qx, qy, qz); on return lane r < K holds the r-th neighbour in L
+__device__ __forceinline__ void bvh_knn_warp(const BvhDev& T, WarpList& L, int K, double qx, double qy, double qz) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int top = T.levels - 1;
+    if (top == 0) { bvh_scan_leaf(T, L, K, qx, qy, qz, 0); return; }
+    double dch[BVH_MAXL];
+    uint32_t node[BVH_MAXL];
+    int lv = top;
+    node[lv] = 0;
+    auto expand = [&](int l, uint32_t nd) {
+        const uint32_t c = nd * 32u + lane;
+        dch[l] = (c < T.count[l - 1]) ? box_dist2(T.box[l - 1] + 6 * (size_t)c, qx, qy, qz) : INFINITY;
+    };
+    expand(lv, 0);
+    for (;;) {
+        double dmin = dch[lv]; int jmin = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = shfl_xor_d(full, dmin, o);
+            const int oj = __shfl_xor_sync(full, jmin, o);
+            if (od < dmin || (od == dmin && oj < jmin)) { dmin = od; jmin = oj; }
+        }
+        if (dmin == INFINITY || dmin > L.kd) {          // nothing left worth visiting below this node
+            if (++lv > top) break;
+            continue;
+        }
+        if (lane == jmin) dch[lv] = INFINITY;
+        const uint32_t child = node[lv] * 32u + (uint32_t)jmin;
+        if (lv == 1) bvh_scan_leaf(T, L, K, qx, qy, qz, child);
+        else { lv--; node[lv] = child; expand(lv, child); }
     }
 }
 
-// One warp serves 32 consecutive cell-sorted points: phase 1 finds each one's K nearest neighbours with the whole warp,
-// phase 2 gives every lane one point: cumulants over its neighbours in ascending (distance, index), covariance,
-// Jacobi, normal. normals are written at the points' original indices.
-__global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(GridDDev g, uint32_t n_valid, int K, double* __restrict__ nrm) {
+// One warp serves 32 consecutive Morton-sorted points: phase 1 finds each one's K nearest neighbours with the whole
+// warp, phase 2 gives every lane one point: cumulants over its neighbours in ascending (distance, index), covariance,
+// Jacobi, normal. Normals are written at the points' original indices.
+__global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, double* __restrict__ nrm) {
     __shared__ uint32_t s_pos[NRM_WARPS][32][NRM_MAXK];
     __shared__ int s_cnt[NRM_WARPS][32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t base = (blockIdx.x * NRM_WARPS + warp) * 32u;
-    if (base >= n_valid) return;
+    if (base >= T.n) return;
     double mx = 0, my = 0, mz = 0; long long mid = -1;
-    if (base + lane < n_valid) load_p4d(&g.pts[base + lane], mx, my, mz, mid);
-    const int nq = (int)min(32u, n_valid - base);
+    if (base + lane < T.n) load_p4d(&T.pts[base + lane], mx, my, mz, mid);
+    const int nq = (int)min(32u, T.n - base);
     for (int j = 0; j < nq; j++) {
         const double qx = shfl_d(full, mx, j), qy = shfl_d(full, my, j), qz = shfl_d(full, mz, j);
         WarpList L; L.sd = INFINITY; L.si = 0x7fffffff; L.sp = 0; L.kd = INFINITY; L.ki = 0x7fffffff;
-        const QueryCell qc = query_cell(g, qx, qy, qz);
-        const int rmax = rings_to_cover(g, qc);
-        // rings 0 and 1: nine full rows
-        for (int i = 0; i < 9; i++) {
-            uint32_t b, e;
-            row_range(g, qc.cx - 1, qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, b, e);
-            warp_scan_run(g, L, K, qx, qy, qz, b, e);
-        }
-        int r = 1;
-        while (!(L.kd < ring_bound2(g, qc, r)) && r < rmax) {
-            r++;
-            const int side = 2 * r + 1;
-            for (int rowi = 0; rowi < side * side; rowi++) {
-                const int dy = rowi % side - r, dz = rowi / side - r;
-                uint32_t b, e;
-                if (max(abs(dy), abs(dz)) == r) {
-                    row_range(g, qc.cx - r, qc.cx + r, qc.cy + dy, qc.cz + dz, b, e);
-                    warp_scan_run(g, L, K, qx, qy, qz, b, e);
-                } else {
-                    row_range(g, qc.cx - r, qc.cx - r, qc.cy + dy, qc.cz + dz, b, e);
-                    warp_scan_run(g, L, K, qx, qy, qz, b, e);
-                    row_range(g, qc.cx + r, qc.cx + r, qc.cy + dy, qc.cz + dz, b, e);
-                    warp_scan_run(g, L, K, qx, qy, qz, b, e);
-                }
-            }
-        }
+        bvh_knn_warp(T, L, K, qx, qy, qz);
         const unsigned have = __ballot_sync(full, lane < K && L.sd < INFINITY);
         if (lane < K) s_pos[warp][j][lane] = L.sp;
         if (lane == 0) s_cnt[warp][j] = __popc(have);
@@ -468,7 +563,7 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(GridDDev g, uint32_t
         double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int j = 0; j < found; j++) {
             double x, y, z; long long id;
-            load_p4d(&g.pts[s_pos[warp][lane][j]], x, y, z, id);
+            load_p4d(&T.pts[s_pos[warp][lane][j]], x, y, z, id);
             c[0] += x; c[1] += y; c[2] += z;
             c[3] += x * x; c[4] += x * y; c[5] += x * z;
             c[6] += y * y; c[7] += y * z; c[8] += z * z;
@@ -495,28 +590,86 @@ __global__ void __launch_bounds__(256) k_fill_normals(double* __restrict__ nrm, 
     if (i < n) { nrm[3 * (size_t)i] = 0.0; nrm[3 * (size_t)i + 1] = 0.0; nrm[3 * (size_t)i + 2] = 1.0; }
 }
 
+// stable sort of (64-bit key, input index) by the low `bits` bits: one or two 32-bit LSD radix sorts.
+// lin: keys in input order; ka = low words, va = 0..n-1 on entry. Returns the sorted index sequence.
+static int sort_by_u64(const unsigned long long* lin, size_t n, int bits, uint32_t* ka, uint32_t* va, uint32_t* kb, uint32_t* vb,
+                       void* scratch, cudaStream_t s, uint32_t** order) {
+    uint32_t *ks, *vs;
+    B2_CHECK(radix_sort_pairs(ka, va, kb, vb, n, std::min(bits, 32), scratch, s, &ks, &vs));
+    if (bits > 32) {
+        uint32_t* k2 = (ks == ka) ? kb : ka;
+        uint32_t* v2 = (vs == va) ? vb : va;
+        k_vds_key_hi<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(lin, vs, (uint32_t)n, ks); count_launch();
+        B2_CUDA(cudaGetLastError());
+        B2_CHECK(radix_sort_pairs(ks, vs, k2, v2, n, bits - 32, scratch, s, &ks, &vs));
+    }
+    *order = vs;
+    return B2_OK;
+}
+
 int estimate_normals_knn(b2_cloud_s* c, int knn) {
     if (knn < 1 || knn > NRM_MAXK) { set_error("estimate_normals: knn must be in [1, %d]", NRM_MAXK); return B2_ERR_ARG; }
     cudaStream_t s = c->stream;
     c->has_normals = false;
     if (c->n == 0) { c->has_normals = true; return B2_OK; }
-    B2_CHECK(c->nrm.reserve(c->n * 24));
-    k_fill_normals<<<(unsigned)((c->n + 255) / 256), 256, 0, s>>>(c->nrm.as<double>(), (uint32_t)c->n); count_launch();
-    GridD grid;
-    int st = grid.build(c->xyz.as<double>(), c->n, 0.0, std::max(4.0, knn / 3.0), s);
-    if (st != B2_OK) { grid.release(); return st; }
+    const size_t n = c->n;
+    if (n > 0x7fffffffull) { set_error("estimate_normals: too many points"); return B2_ERR_ARG; }
+    B2_CHECK(c->nrm.reserve(n * 24));
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    k_fill_normals<<<nblk, 256, 0, s>>>(c->nrm.as<double>(), (uint32_t)n); count_launch();
+    const double* xyz = c->xyz.as<double>();
+    double mn[3], mx[3];
+    B2_CHECK(bbox_f64(xyz, n, c->work, s, mn, mx));
+    if (!(mn[0] <= mx[0])) { c->has_normals = true; return B2_OK; }
+    const double emax = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+    const double scale = emax > 0 ? 2097151.0 / emax : 0.0;
+    // tree geometry
+    uint32_t count[BVH_MAXL]; int levels = 0;
+    for (uint32_t m = (uint32_t)((n + 31) / 32);; m = (m + 31) / 32) { count[levels++] = m; if (m == 1 || levels == BVH_MAXL) break; }
+    size_t box_doubles = 0;
+    for (int l = 0; l < levels; l++) box_doubles += 6 * (size_t)count[l];
+    const size_t nal = (n + 63) & ~(size_t)63;
+    const size_t need = nal * 8 + 4 * nal * 4 + sort_tmp_bytes(n) + 1024;
+    DevBuf pts, boxes;
+    int st = c->work.reserve(need);
+    if (st == B2_OK) st = pts.reserve(n * sizeof(P4d));
+    if (st == B2_OK) st = boxes.reserve(box_doubles * 8 + 64);
+    if (st != B2_OK) { pts.release(); boxes.release(); return st; }
+    unsigned long long* lin = c->work.as<unsigned long long>();
+    uint32_t* ka = reinterpret_cast<uint32_t*>(lin + nal);
+    uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
+    char* scratch = reinterpret_cast<char*>(vb + nal);
+    unsigned int* d_valid = reinterpret_cast<unsigned int*>(scratch + sort_tmp_bytes(n));
+    cudaError_t e = cudaMemsetAsync(d_valid, 0, 4, s);
+    k_morton_key<<<nblk, 256, 0, s>>>(xyz, (uint32_t)n, mn[0], mn[1], mn[2], scale, lin, ka, va, d_valid); count_launch();
+    uint32_t* order = nullptr;
+    st = sort_by_u64(lin, n, 64, ka, va, kb, vb, scratch, s, &order);
     uint32_t n_valid = 0;
-    const size_t ncell = (size_t)grid.dev.nx * grid.dev.ny * grid.dev.nz;
-    cudaError_t e = cudaMemcpyAsync(&n_valid, grid.dev.cell_start + ncell, 4, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { grid.release(); set_error("estimate_normals: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
-    if (n_valid) {
+    if (st == B2_OK) {
+        k_celld_gather<<<nblk, 256, 0, s>>>(xyz, (uint32_t)n, order, pts.as<P4d>()); count_launch();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&n_valid, d_valid, 4, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    }
+    if (st == B2_OK && e == cudaSuccess && n_valid) {
+        BvhDev T;
+        T.pts = pts.as<P4d>(); T.n = n_valid; T.levels = 0;
+        double* bp = boxes.as<double>();
+        for (uint32_t m = (n_valid + 31) / 32;; m = (m + 31) / 32) {
+            T.count[T.levels] = m; T.box[T.levels] = bp; bp += 6 * (size_t)m; T.levels++;
+            if (m == 1 || T.levels == BVH_MAXL) break;
+        }
+        for (int l = T.levels; l < BVH_MAXL; l++) { T.count[l] = 0; T.box[l] = nullptr; }
+        k_bvh_leaf_boxes<<<(T.count[0] + 7) / 8, 256, 0, s>>>(T.pts, n_valid, const_cast<double*>(T.box[0]), T.count[0]); count_launch();
+        for (int l = 1; l < T.levels; l++) {
+            k_bvh_node_boxes<<<(T.count[l] + 7) / 8, 256, 0, s>>>(T.box[l - 1], T.count[l - 1], const_cast<double*>(T.box[l]), T.count[l]); count_launch();
+        }
         const unsigned per_block = NRM_WARPS * 32;
-        k_normals<<<(n_valid + per_block - 1) / per_block, per_block, 0, s>>>(grid.dev, n_valid, knn, c->nrm.as<double>()); count_launch();
+        k_normals<<<(n_valid + per_block - 1) / per_block, per_block, 0, s>>>(T, knn, c->nrm.as<double>()); count_launch();
         e = cudaGetLastError();
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     }
-    grid.release();
+    pts.release(); boxes.release();
+    if (st != B2_OK) return st;
     if (e != cudaSuccess) { set_error("estimate_normals: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
     c->has_normals = true;
     return B2_OK;

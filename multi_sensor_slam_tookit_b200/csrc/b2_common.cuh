@@ -28,20 +28,25 @@ void set_error(const char* fmt, ...);
         if (_s != B2_OK) return _s;                                                                \
     } while (0)
 
+// Device memory comes from a per-process pool (b2_sort.cu): released blocks are kept and handed out again, because
+// cudaMalloc/cudaFree of the multi-megabyte index buffers cost more than the kernels that use them when a caller
+// builds an index per scan or per calibration pair. pool_free synchronises the device before a block can be reused.
+void* pool_alloc(size_t bytes, size_t* cap_out);
+void pool_free(void* p, size_t cap);
+
 // Growable device buffer owned by a handle.
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int reserve(size_t bytes) {
         if (bytes <= cap) return B2_OK;
-        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        if (p) { pool_free(p, cap); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { set_error("cudaMalloc(%zu) -> %s", want, cudaGetErrorString(e)); return B2_ERR_CUDA; }
-        cap = want;
+        p = pool_alloc(want, &cap);
+        if (!p) { cap = 0; return B2_ERR_CUDA; }
         return B2_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) pool_free(p, cap); p = nullptr; cap = 0; }
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 

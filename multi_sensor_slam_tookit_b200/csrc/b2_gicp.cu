@@ -5,11 +5,13 @@
 //
 // One iteration = one launch of k_gicp_linearize (+ one all-reduce and a one-thread finalize kernel when the source
 // is sharded over several GPUs):
-//   phase 1  every source point of the shard is transformed by the current T and its exact nearest target point
-//            within max_correspondence_distance is found in the fp64 grid (8 lanes per query, ties to the smaller index);
-//   phase 2  one lane per correspondence: M = Ct + R Cs R^T, residual and Jacobian, 21 + 6 + 3 sums in registers;
-//   epilogue shuffle tree -> per-CTA partial -> the last CTA adds the partials in CTA order (deterministic) and, on
-//            a single GPU, solves the 6x6 system, updates T and evaluates Open3D's convergence rule, all on the device.
+//   search   one thread per source point of the shard: transform by the current T, exact nearest target point within
+//            max_correspondence_distance (fine grid 3x3x3 block, certified by the ring bound; otherwise one pass over
+//            the 3x3x3 block of a coarse grid whose cell edge is the search radius; ties to the smaller index);
+//   terms    M = Ct + R Cs R^T, residual and Jacobian of the correspondence: 21 + 6 + 3 terms, reduced over the warp
+//            with a shuffle tree as they are produced (lane i keeps the running total of term i);
+//   epilogue per-CTA partial -> the last CTA adds the partials in CTA order (deterministic) and, on a single GPU,
+//            solves the 6x6 system, updates T and evaluates Open3D's convergence rule, all on the device.
 //
 // Covariances. The reference never supplies covariances: Open3D derives them from the normals as R diag(eps,1,1) R^T
 // with R the rotation of e1 onto the normal (identity when n.x < -0.99), i.e. C = I - (1-eps) m m^T with m the normal
@@ -27,7 +29,6 @@ namespace b2 {
 
 constexpr int GICP_THREADS = 256;
 constexpr int GICP_WARPS = GICP_THREADS / 32;
-constexpr int GICP_LPG = 8;                  // lanes per nearest-neighbour query
 constexpr int GICP_NSUM = 30;                // 21 JtJ upper + 6 Jtr + n_corr + sum d^2 + sum r^2
 constexpr int GICP_HIST = 256;
 
@@ -43,8 +44,11 @@ struct GicpState {
 };
 
 struct GicpArgs {
-    GridDDev tgt;                    // target index
-    const double* tgt_m;             // effective normals of the target, grid order
+    GridDDev tgt;                    // target index (fine: about two points per occupied cell)
+    GridDDev tgtc;                   // the same points in cells of edge >= max_correspondence_distance
+    const uint32_t* fine_pos_of;     // target original index -> position in the fine order
+    int have_coarse;
+    const double* tgt_m;             // effective normals of the target, fine-grid order
     const P4d* src;                  // source points, cell-sorted order, idx = original index
     const double* src_m;             // effective normals of the source, same order
     uint32_t begin, end;             // this GPU's shard of the sorted source
@@ -114,10 +118,10 @@ __global__ void k_gicp_finalize(GicpState* st) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) gicp_finalize(st);
 }
 
-__global__ void __launch_bounds__(GICP_THREADS, 2) k_gicp_linearize(GicpArgs A) {
+__global__ void __launch_bounds__(GICP_THREADS, 3) k_gicp_linearize(GicpArgs A) {
     GicpState* st = A.st;
     if (st->done) return;
-    __shared__ double s_red[GICP_WARPS][GICP_NSUM];
+    __shared__ double s_red[GICP_WARPS][32];
     __shared__ bool s_last;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -128,10 +132,7 @@ __global__ void __launch_bounds__(GICP_THREADS, 2) k_gicp_linearize(GicpArgs A) 
         for (int j = 0; j < 3; j++) R[i * 3 + j] = st->T[i * 4 + j];
         t[i] = st->T[i * 4 + 3];
     }
-    double acc[GICP_NSUM];
-#pragma unroll
-    for (int i = 0; i < GICP_NSUM; i++) acc[i] = 0.0;
-
+    double tot = 0.0;                // lane i: running total of term i
     const uint32_t n_here = A.end - A.begin;
     const uint32_t n_chunks = (n_here + 31) >> 5;
     for (uint32_t chunk = blockIdx.x * GICP_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * GICP_WARPS) {
@@ -142,28 +143,17 @@ __global__ void __launch_bounds__(GICP_THREADS, 2) k_gicp_linearize(GicpArgs A) 
         const double vx = R[0] * px + R[1] * py + R[2] * pz + t[0];
         const double vy = R[3] * px + R[4] * py + R[5] * pz + t[1];
         const double vz = R[6] * px + R[7] * py + R[8] * pz + t[2];
-        // phase 1: 32 / LPG queries per round, the owner lane keeps its own result
-        double my_d2 = INFINITY; uint32_t my_pos = 0xffffffffu;
-        constexpr int QPR = 32 / GICP_LPG;
-#pragma unroll 1
-        for (int round = 0; round < GICP_LPG; round++) {
-            const int ql = round * QPR + (lane / GICP_LPG);
-            const double qx = shfl_d(full, vx, ql), qy = shfl_d(full, vy, ql), qz = shfl_d(full, vz, ql);
-            const bool qa = __shfl_sync(full, (int)valid, ql) != 0;
-            double bd; uint32_t bp; long long bi;
-            nn1_group<GICP_LPG>(A.tgt, qx, qy, qz, qa, A.radius2, bd, bp, bi);
-            const int from = (lane % QPR) * GICP_LPG;
-            const double rd = shfl_d(full, bd, from);
-            const uint32_t rp = __shfl_sync(full, bp, from);
-            if (lane / QPR == round) { my_d2 = rd; my_pos = rp; }
-        }
-        // phase 2: one lane per correspondence
-        const bool hit = valid && my_pos != 0xffffffffu;
-        long long tidx = -1;
+        NN1 nn; nn.d2 = INFINITY; nn.pos = 0xffffffffu; nn.idx = -1;
+        if (valid) nn = nn1_thread(A.tgt, A.tgtc, A.fine_pos_of, A.have_coarse != 0, vx, vy, vz, A.radius2);
+        const bool hit = valid && nn.pos != 0xffffffffu;
+        if (A.corr && valid) A.corr[sidx] = hit ? (int32_t)nn.idx : -1;
+        __syncwarp();
+        if (!__any_sync(full, hit)) continue;
+        double term[GICP_NSUM];
+#pragma unroll
+        for (int i = 0; i < GICP_NSUM; i++) term[i] = 0.0;
         if (hit) {
-            double tx, ty, tz;
-            load_p4d(&A.tgt.pts[my_pos], tx, ty, tz, tidx);
-            const double* um = &A.tgt_m[3 * (size_t)my_pos];
+            const double* um = &A.tgt_m[3 * (size_t)nn.pos];
             const double* sm = &A.src_m[3 * (size_t)p];
             const double u0 = um[0], u1 = um[1], u2 = um[2];
             const double m0 = sm[0], m1 = sm[1], m2 = sm[2];
@@ -178,35 +168,35 @@ __global__ void __launch_bounds__(GICP_THREADS, 2) k_gicp_linearize(GicpArgs A) 
             const double N00 = 0.5 + al * p0 * p0 + be * q0 * q0, N01 = al * p0 * p1 + be * q0 * q1, N02 = al * p0 * p2 + be * q0 * q2;
             const double N11 = 0.5 + al * p1 * p1 + be * q1 * q1, N12 = al * p1 * p2 + be * q1 * q2;
             const double N22 = 0.5 + al * p2 * p2 + be * q2 * q2;
-            const double d0 = vx - tx, d1 = vy - ty, d2 = vz - tz;
+            const double d0 = vx - nn.x, d1 = vy - nn.y, d2 = vz - nn.z;
             // B = N S, S = -[vs]x
             const double B00 = N02 * vy - N01 * vz, B01 = N00 * vz - N02 * vx, B02 = N01 * vx - N00 * vy;
             const double B10 = N12 * vy - N11 * vz, B11 = N01 * vz - N12 * vx, B12 = N11 * vx - N01 * vy;
             const double B20 = N22 * vy - N12 * vz, B21 = N02 * vz - N22 * vx, B22 = N12 * vx - N02 * vy;
             // top-left S^T B (symmetric), top-right S^T N = B^T, bottom-right N
-            acc[0] += vy * B20 - vz * B10; acc[1] += vy * B21 - vz * B11; acc[2] += vy * B22 - vz * B12;
-            acc[3] += B00; acc[4] += B10; acc[5] += B20;
-            acc[6] += vz * B01 - vx * B21; acc[7] += vz * B02 - vx * B22;
-            acc[8] += B01; acc[9] += B11; acc[10] += B21;
-            acc[11] += vx * B12 - vy * B02;
-            acc[12] += B02; acc[13] += B12; acc[14] += B22;
-            acc[15] += N00; acc[16] += N01; acc[17] += N02; acc[18] += N11; acc[19] += N12; acc[20] += N22;
+            term[0] = vy * B20 - vz * B10; term[1] = vy * B21 - vz * B11; term[2] = vy * B22 - vz * B12;
+            term[3] = B00; term[4] = B10; term[5] = B20;
+            term[6] = vz * B01 - vx * B21; term[7] = vz * B02 - vx * B22;
+            term[8] = B01; term[9] = B11; term[10] = B21;
+            term[11] = vx * B12 - vy * B02;
+            term[12] = B02; term[13] = B12; term[14] = B22;
+            term[15] = N00; term[16] = N01; term[17] = N02; term[18] = N11; term[19] = N12; term[20] = N22;
             const double g0 = N00 * d0 + N01 * d1 + N02 * d2, g1 = N01 * d0 + N11 * d1 + N12 * d2, g2 = N02 * d0 + N12 * d1 + N22 * d2;
-            acc[21] += vy * g2 - vz * g1; acc[22] += vz * g0 - vx * g2; acc[23] += vx * g1 - vy * g0;
-            acc[24] += g0; acc[25] += g1; acc[26] += g2;
-            acc[27] += 1.0; acc[28] += my_d2; acc[29] += d0 * g0 + d1 * g1 + d2 * g2;
+            term[21] = vy * g2 - vz * g1; term[22] = vz * g0 - vx * g2; term[23] = vx * g1 - vy * g0;
+            term[24] = g0; term[25] = g1; term[26] = g2;
+            term[27] = 1.0; term[28] = nn.d2; term[29] = d0 * g0 + d1 * g1 + d2 * g2;
         }
-        if (A.corr && valid) A.corr[sidx] = hit ? (int32_t)tidx : -1;
-    }
-    // epilogue: warp tree, CTA partial, last CTA adds the partials in CTA order
-    __syncwarp();
+        __syncwarp();
 #pragma unroll
-    for (int i = 0; i < GICP_NSUM; i++) {
-        double v = acc[i];
+        for (int i = 0; i < GICP_NSUM; i++) {
+            double v = term[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(full, v, o);
-        if (lane == 0) s_red[warp][i] = v;
+            for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(full, v, o);
+            if (lane == i) tot += v;
+        }
     }
+    // epilogue: CTA partial, last CTA adds the partials in CTA order
+    s_red[warp][lane] = tot;
     __syncthreads();
     if (threadIdx.x < GICP_NSUM) {
         double v = 0.0;
@@ -246,6 +236,14 @@ __global__ void __launch_bounds__(256) k_gicp_eff_normals(const P4d* __restrict_
     out[3 * (size_t)i] = n0; out[3 * (size_t)i + 1] = n1; out[3 * (size_t)i + 2] = n2;
 }
 
+__global__ void __launch_bounds__(256) k_gicp_fine_pos(const P4d* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ pos_of) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y, z; long long idx;
+    load_p4d(&sorted[i], x, y, z, idx);
+    pos_of[idx] = i;
+}
+
 __global__ void k_fill_i32(int32_t* p, uint32_t n, int32_t v) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -259,8 +257,11 @@ struct b2_gicp_s {
     int device = 0;
     cudaStream_t stream = nullptr;
     b2_gicp_params prm{};
-    GridD tgt_grid, src_grid;
-    DevBuf tgt_m, src_m, partials, state, corr;
+    GridD tgt_grid, tgt_coarse, src_grid;
+    DevBuf tgt_m, src_m, partials, state, corr, tgt_xyz, fine_pos_of;
+    double coarse_for = -1.0;        // max_correspondence_distance the coarse grid was built for (< 0: none)
+    bool have_coarse = false;
+    int blocks_per_sm = 3;
     PinBuf pin;
     size_t n_tgt = 0, n_src = 0;
     uint32_t src_valid = 0;
@@ -283,6 +284,9 @@ static int gicp_valid_count(const GridD& g, cudaStream_t s, uint32_t* out) {
 
 static void gicp_fill_args(b2_gicp_s* h, GicpArgs& a, int mode, int32_t* corr) {
     a.tgt = h->tgt_grid.dev;
+    a.tgtc = h->have_coarse ? h->tgt_coarse.dev : h->tgt_grid.dev;
+    a.fine_pos_of = h->fine_pos_of.as<uint32_t>();
+    a.have_coarse = h->have_coarse ? 1 : 0;
     a.tgt_m = h->tgt_m.as<double>();
     a.src = h->src_grid.dev.pts;
     a.src_m = h->src_m.as<double>();
@@ -296,12 +300,27 @@ static void gicp_fill_args(b2_gicp_s* h, GicpArgs& a, int mode, int32_t* corr) {
     a.st = h->state.as<GicpState>();
     a.mode = mode;
     const uint32_t chunks = (a.end - a.begin + 31) / 32;
-    h->grid_blocks = (int)std::max<uint32_t>(1u, std::min<uint32_t>((chunks + GICP_WARPS - 1) / GICP_WARPS, (uint32_t)device_sm_count() * 2u));
+    h->grid_blocks = (int)std::max<uint32_t>(1u, std::min<uint32_t>((chunks + GICP_WARPS - 1) / GICP_WARPS, (uint32_t)(device_sm_count() * h->blocks_per_sm)));
+}
+
+// The coarse grid serves queries whose nearest neighbour the fine 3x3x3 block cannot certify: cell edge =
+// max_correspondence_distance * (1 + 2^-7), so its 3x3x3 block holds every point within the radius.
+static int gicp_ensure_coarse(b2_gicp_s* h) {
+    const double r = h->prm.max_correspondence_distance;
+    if (h->coarse_for == r) return B2_OK;
+    h->have_coarse = false;
+    if (h->n_tgt && r > h->tgt_grid.dev.h * 0.999) {
+        B2_CHECK(h->tgt_coarse.build(h->tgt_xyz.as<double>(), h->n_tgt, r * 1.0078125, 0.0, h->stream));
+        h->have_coarse = true;
+    } else h->tgt_coarse.release();
+    h->coarse_for = r;
+    return B2_OK;
 }
 
 static int gicp_prepare(b2_gicp_s* h) {
     if (!h->have_tgt || !h->have_src) { set_error("gicp: set_target and set_source first"); return B2_ERR_STATE; }
-    B2_CHECK(h->partials.reserve((size_t)device_sm_count() * 2 * GICP_NSUM * 8 + 256));
+    B2_CHECK(h->partials.reserve((size_t)device_sm_count() * h->blocks_per_sm * GICP_NSUM * 8 + 256));
+    B2_CHECK(gicp_ensure_coarse(h));
     B2_CHECK(h->state.reserve(sizeof(GicpState)));
     B2_CHECK(h->pin.reserve(sizeof(GicpState)));
     return B2_OK;
@@ -345,7 +364,7 @@ int b2_gicp_create(b2_gicp_t* out, const b2_gicp_params* params) {
 
 int b2_gicp_destroy(b2_gicp_t h) {
     if (!h) return B2_OK;
-    h->tgt_grid.release(); h->src_grid.release();
+    h->tgt_grid.release(); h->tgt_coarse.release(); h->src_grid.release(); h->tgt_xyz.release(); h->fine_pos_of.release();
     h->tgt_m.release(); h->src_m.release(); h->partials.release(); h->state.release(); h->corr.release(); h->pin.release();
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
@@ -384,6 +403,18 @@ int b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target) {
     uint32_t nv = 0;
     B2_CHECK(gicp_set_cloud(h, target, h->tgt_grid, h->tgt_m, 2.0, &nv));
     h->n_tgt = target->n;
+    h->coarse_for = -1.0; h->have_coarse = false;
+    // the handle keeps its own copy of the points (the caller may destroy the cloud; the coarse grid is built lazily
+    // for the search radius in force) and the original-index -> fine-position map the coarse pass needs
+    B2_CHECK(h->tgt_xyz.reserve(std::max<size_t>(target->n, 1) * 24));
+    B2_CHECK(h->fine_pos_of.reserve(std::max<size_t>(target->n, 1) * 4));
+    if (target->n) {
+        B2_CUDA(cudaMemcpyAsync(h->tgt_xyz.p, target->xyz.p, target->n * 24, cudaMemcpyDeviceToDevice, h->stream));
+        B2_CUDA(cudaMemsetAsync(h->fine_pos_of.p, 0xff, target->n * 4, h->stream));
+        if (nv) { k_gicp_fine_pos<<<(nv + 255) / 256, 256, 0, h->stream>>>(h->tgt_grid.dev.pts, nv, h->fine_pos_of.as<uint32_t>()); count_launch(); }
+        B2_CUDA(cudaGetLastError());
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+    }
     h->have_tgt = true;
     return B2_OK;
 }

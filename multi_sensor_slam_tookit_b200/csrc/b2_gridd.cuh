@@ -101,78 +101,45 @@ __device__ __forceinline__ void row_range(const GridDDev& g, int x0, int x1, int
     e = ok ? __ldg(&g.cell_start[row + x1 + 1]) : 0u;
 }
 
-// Exact 1-NN by a group of LPG consecutive lanes (all lanes of the warp must call; `active` per group).
-// radius2: candidates at or beyond it are ignored (GICP max_correspondence_distance^2).
-// Result on every lane of the group: best_d2 (radius2-or-larger sentinel = none), best_pos (position in g.pts), best_idx.
-template <int LPG>
-__device__ __forceinline__ void nn1_group(const GridDDev& g, double qx, double qy, double qz, bool active, double radius2,
-                                          double& best_d2, uint32_t& best_pos, long long& best_idx) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31, sub = lane & (LPG - 1);
-    double bd = INFINITY; uint32_t bp = 0xffffffffu; long long bi = 0x7fffffffffffffffLL;
-    const QueryCell qc = query_cell(g, qx, qy, qz);
-    active = active && qc.finite;
-    const int rmax = rings_to_cover(g, qc);
-    auto consider = [&](uint32_t p) {
-        double x, y, z; long long idx;
-        load_p4d(&g.pts[p], x, y, z, idx);
-        const double ddx = qx - x, ddy = qy - y, ddz = qz - z;
-        const double d = ddx * ddx + ddy * ddy + ddz * ddz;
-        if (d < radius2 && (d < bd || (d == bd && idx < bi))) { bd = d; bp = p; bi = idx; }
-    };
-    auto group_min = [&]() {
-        __syncwarp();
+// Exact 1-NN for one query per thread.
+//   fine   : the 3x3x3 block of the fine grid (nine contiguous runs); certified when the best squared distance is below
+//            the ring-1 bound or the bound already exceeds radius2;
+//   coarse : otherwise the 3x3x3 block of a second grid over the same points whose cell edge is >= the search radius,
+//            which contains every point closer than the radius: one pass, no shell expansion.
+// radius2: candidates at or beyond it are ignored (GICP max_correspondence_distance^2). Ties fall to the smaller index.
+// Result: d2 (INFINITY = none), idx (original index), x/y/z the neighbour's coordinates, pos its position in the FINE
+// grid's order (through `fine_pos_of`, original index -> fine position, when the coarse pass found it).
+struct NN1 { double d2; long long idx; double x, y, z; uint32_t pos; };
+
+__device__ __forceinline__ void nn1_scan_block(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best) {
+    uint32_t rb[9], re[9];
 #pragma unroll
-        for (int o = LPG >> 1; o > 0; o >>= 1) {
-            const double od = shfl_xor_d(full, bd, o);
-            const uint32_t op = __shfl_xor_sync(full, bp, o);
-            const long long oi = ((long long)__shfl_xor_sync(full, (int)(bi >> 32), o) << 32) | (unsigned)__shfl_xor_sync(full, (int)bi, o);
-            if (od < bd || (od == bd && oi < bi)) { bd = od; bp = op; bi = oi; }
-        }
-    };
-    // rings 0 and 1 together: the 3x3x3 block is nine full rows; all eighteen bounds are requested before any is consumed
-    if (active) {
-        uint32_t rb[9], re[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) row_range(g, qc.cx - 1, qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, rb[i], re[i]);
-#pragma unroll
-        for (int i = 0; i < 9; i++)
-            for (uint32_t p = rb[i] + sub; p < re[i]; p += LPG) consider(p);
-    }
-    group_min();
-    int r = 1;
-    bool more = active;
-    {
-        const double bound2 = ring_bound2(g, qc, r);
-        if (bd < bound2 || bound2 >= radius2 || r >= rmax) more = false;
-    }
-    // rare: the neighbour (if any) lies beyond the block; widen shell by shell
-    while (__any_sync(full, more)) {
-        r++;
-        if (more) {
-            const int side = 2 * r + 1;
-            for (int rowi = 0; rowi < side * side; rowi++) {
-                const int dy = rowi % side - r, dz = rowi / side - r;
-                const bool shell_row = (max(abs(dy), abs(dz)) == r);
-                uint32_t b, e;
-                if (shell_row) {
-                    row_range(g, qc.cx - r, qc.cx + r, qc.cy + dy, qc.cz + dz, b, e);
-                    for (uint32_t p = b + sub; p < e; p += LPG) consider(p);
-                } else {                       // inner rows of the shell contribute their two end cells only
-                    row_range(g, qc.cx - r, qc.cx - r, qc.cy + dy, qc.cz + dz, b, e);
-                    for (uint32_t p = b + sub; p < e; p += LPG) consider(p);
-                    row_range(g, qc.cx + r, qc.cx + r, qc.cy + dy, qc.cz + dz, b, e);
-                    for (uint32_t p = b + sub; p < e; p += LPG) consider(p);
-                }
-            }
-        }
-        group_min();
-        if (more) {
-            const double bound2 = ring_bound2(g, qc, r);
-            if (bd < bound2 || bound2 >= radius2 || r >= rmax) more = false;
+    for (int i = 0; i < 9; i++) row_range(g, qc.cx - 1, qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, rb[i], re[i]);
+#pragma unroll 1
+    for (int i = 0; i < 9; i++) {
+        for (uint32_t p = rb[i]; p < re[i]; p++) {
+            double x, y, z; long long idx;
+            load_p4d(&g.pts[p], x, y, z, idx);
+            const double ddx = qx - x, ddy = qy - y, ddz = qz - z;
+            const double d = ddx * ddx + ddy * ddy + ddz * ddz;
+            if (d < radius2 && (d < best.d2 || (d == best.d2 && idx < best.idx))) { best.d2 = d; best.idx = idx; best.x = x; best.y = y; best.z = z; best.pos = p; }
         }
     }
-    best_d2 = bd; best_pos = bp; best_idx = bi;
+}
+
+__device__ __forceinline__ NN1 nn1_thread(const GridDDev& fine, const GridDDev& coarse, const uint32_t* __restrict__ fine_pos_of,
+                                          bool have_coarse, double qx, double qy, double qz, double radius2) {
+    NN1 best; best.d2 = INFINITY; best.idx = 0x7fffffffffffffffLL; best.x = best.y = best.z = 0.0; best.pos = 0xffffffffu;
+    const QueryCell qc = query_cell(fine, qx, qy, qz);
+    if (!qc.finite) return best;
+    nn1_scan_block(fine, qc, qx, qy, qz, radius2, best);
+    const double bound2 = ring_bound2(fine, qc, 1);
+    if (best.d2 < bound2 || bound2 >= radius2 || !have_coarse) return best;
+    const QueryCell qcc = query_cell(coarse, qx, qy, qz);
+    const long long before = best.idx;
+    nn1_scan_block(coarse, qcc, qx, qy, qz, radius2, best);
+    if (best.idx != before) best.pos = __ldg(&fine_pos_of[best.idx]);
+    return best;
 }
 
 #endif  // __CUDACC__

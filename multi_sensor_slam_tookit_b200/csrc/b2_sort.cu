@@ -3,6 +3,8 @@
 // shared memory so the global writes of a tile land in per-digit runs.
 #include "b2_common.cuh"
 #include <cstdarg>
+#include <mutex>
+#include <vector>
 
 namespace b2 {
 
@@ -17,6 +19,67 @@ const char* get_error() { return g_err; }
 static unsigned long long g_launches = 0;
 void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
 unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+// ------------------------------------------------------------------------------------------------ device memory pool
+struct PoolBlock { void* p; size_t cap; int dev; };
+static std::mutex g_pool_mu;
+static std::vector<PoolBlock> g_pool;
+static size_t g_pool_bytes = 0;
+constexpr size_t POOL_LIMIT = (size_t)48 << 30;
+
+static void pool_trim_locked(int dev) {
+    for (size_t i = 0; i < g_pool.size();) {
+        if (dev < 0 || g_pool[i].dev == dev) { cudaFree(g_pool[i].p); g_pool_bytes -= g_pool[i].cap; g_pool[i] = g_pool.back(); g_pool.pop_back(); }
+        else i++;
+    }
+}
+
+void* pool_alloc(size_t bytes, size_t* cap_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        size_t best = (size_t)-1;
+        for (size_t i = 0; i < g_pool.size(); i++) {
+            const PoolBlock& b = g_pool[i];
+            if (b.dev == dev && b.cap >= bytes && b.cap <= 2 * bytes + ((size_t)1 << 20) && (best == (size_t)-1 || b.cap < g_pool[best].cap)) best = i;
+        }
+        if (best != (size_t)-1) {
+            PoolBlock b = g_pool[best];
+            g_pool[best] = g_pool.back(); g_pool.pop_back();
+            g_pool_bytes -= b.cap;
+            *cap_out = b.cap;
+            return b.p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        { std::lock_guard<std::mutex> lk(g_pool_mu); cudaDeviceSynchronize(); pool_trim_locked(dev); }
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) { set_error("cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e)); cudaGetLastError(); return nullptr; }
+    *cap_out = bytes;
+    return p;
+}
+
+void pool_free(void* p, size_t cap) {
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceSynchronize();           // nothing in flight may still use the block when another handle picks it up
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (g_pool_bytes + cap > POOL_LIMIT) { cudaFree(p); return; }
+    g_pool.push_back(PoolBlock{p, cap, dev});
+    g_pool_bytes += cap;
+}
+
+void pool_trim() {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    cudaDeviceSynchronize();
+    pool_trim_locked(-1);
+}
 
 int device_sm_count() {
     static int sm = 0;
@@ -239,6 +302,7 @@ int b2_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
+int b2_trim_memory(void) { b2::pool_trim(); return B2_OK; }
 int b2_set_device(int ordinal) {
     B2_CUDA(cudaSetDevice(ordinal));
     return B2_OK;
