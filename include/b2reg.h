@@ -262,6 +262,42 @@ int  b2_gicp_last_gpu_ms(b2_gicp_t h, float* ms, int* launches);
 int  b2_gicp_index_info(b2_gicp_t h, double* target_cell_edge, double* target_points_per_cell,
                         uint32_t* shard_begin, uint32_t* shard_end);
 
+/* ------------------------------------------------------------------------------------------------
+ * NDT — replaces pcl::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ> as used by
+ *   Calibration_Tookit/multi_lidar/src/multi_lidar_calibration/src/multi_lidar_calibrator.cpp:35-72
+ *     :37-41  setTransformationEpsilon / setStepSize / setResolution / setMaximumIterations
+ *     :43-44  setInputSource / setInputTarget
+ *     :62     align(output, guess)
+ *     :64-65  hasConverged / getFitnessScore / getTransformationProbability
+ *     :69,71  getFinalTransformation
+ * Semantics: PCL 1.10 ndt.hpp / voxel_grid_covariance.hpp (defaults: resolution 1.0, step 0.1, epsilon 0.1, 35 iterations,
+ * outlier ratio 0.55, >= 6 points per voxel). The calibrator constructs a fresh object on every 10 Hz tick (:35); the
+ * PCL-shaped shim keeps one handle per target cloud. Matrices are row-major 4x4 floats (Eigen::Matrix4f is column-major:
+ * the shim transposes). Point arrays are (base, stride_bytes, n) with x,y,z first (pcl::PointXYZ: stride 16). */
+typedef struct b2_ndt_s* b2_ndt_t;
+int b2_ndt_create(b2_ndt_t* out);
+int b2_ndt_destroy(b2_ndt_t h);
+int b2_ndt_set_transformation_epsilon(b2_ndt_t h, double epsilon);
+int b2_ndt_set_step_size(b2_ndt_t h, double step_size);
+int b2_ndt_set_resolution(b2_ndt_t h, float resolution);
+int b2_ndt_set_maximum_iterations(b2_ndt_t h, int max_iterations);
+int b2_ndt_set_input_target(b2_ndt_t h, const void* xyz, size_t stride_bytes, size_t n);
+int b2_ndt_set_input_source(b2_ndt_t h, const void* xyz, size_t stride_bytes, size_t n);
+/* out_cloud (optional): n_source points of out_stride bytes, the source transformed by the final transformation */
+int b2_ndt_align(b2_ndt_t h, const float guess[16], void* out_cloud, size_t out_stride);
+int b2_ndt_has_converged(b2_ndt_t h, int* converged);
+int b2_ndt_get_final_transformation(b2_ndt_t h, float T[16]);
+int b2_ndt_get_fitness_score(b2_ndt_t h, double* score);
+int b2_ndt_get_transformation_probability(b2_ndt_t h, double* probability);
+int b2_ndt_get_final_num_iteration(b2_ndt_t h, int* iterations);
+/* parity hooks: the voxel statistics of the target (ascending voxel index; n_points = -1 marks a rejected covariance)
+ * and one derivative pass at the pose vector p = (x, y, z, rx, ry, rz); hessian may be NULL */
+int b2_ndt_get_voxels(b2_ndt_t h, size_t capacity, size_t* n_voxels, int32_t* voxel_index, int32_t* n_points, float* centroid_xyz,
+                      double* mean, double* inverse_covariance, int32_t min_b[3], int32_t div_b[3]);
+int b2_ndt_derivatives(b2_ndt_t h, const double p[6], double* score, double gradient[6], double hessian[36], long long* n_pairs);
+/* device time of the last align (or target build), kernel launches and derivative passes it made, (point, voxel) pairs of the last pass */
+int b2_ndt_last_gpu_ms(b2_ndt_t h, float* ms, int* launches, int* evaluations, long long* pairs_last);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,10 @@ SYMBOLS = [
     "b2_gicp_default_params", "b2_gicp_create", "b2_gicp_destroy", "b2_gicp_set_params", "b2_gicp_set_target",
     "b2_gicp_set_source", "b2_gicp_set_shard", "b2_gicp_linearize", "b2_gicp_align", "b2_gicp_get_history",
     "b2_gicp_last_gpu_ms", "b2_gicp_index_info",
+    "b2_ndt_create", "b2_ndt_destroy", "b2_ndt_set_transformation_epsilon", "b2_ndt_set_step_size", "b2_ndt_set_resolution",
+    "b2_ndt_set_maximum_iterations", "b2_ndt_set_input_target", "b2_ndt_set_input_source", "b2_ndt_align", "b2_ndt_has_converged",
+    "b2_ndt_get_final_transformation", "b2_ndt_get_fitness_score", "b2_ndt_get_transformation_probability",
+    "b2_ndt_get_final_num_iteration", "b2_ndt_get_voxels", "b2_ndt_derivatives", "b2_ndt_last_gpu_ms",
 ]
 
 
@@ -127,6 +131,23 @@ def lib():
     L.b2_gicp_get_history.argtypes = [vp, vp, vp, i32, pi]
     L.b2_gicp_last_gpu_ms.argtypes = [vp, pf, pi]
     L.b2_gicp_index_info.argtypes = [vp, pd, pd, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.b2_ndt_create.argtypes = [C.POINTER(vp)]
+    L.b2_ndt_destroy.argtypes = [vp]
+    L.b2_ndt_set_transformation_epsilon.argtypes = [vp, dbl]
+    L.b2_ndt_set_step_size.argtypes = [vp, dbl]
+    L.b2_ndt_set_resolution.argtypes = [vp, f32]
+    L.b2_ndt_set_maximum_iterations.argtypes = [vp, i32]
+    L.b2_ndt_set_input_target.argtypes = [vp, vp, sz, sz]
+    L.b2_ndt_set_input_source.argtypes = [vp, vp, sz, sz]
+    L.b2_ndt_align.argtypes = [vp, vp, vp, sz]
+    L.b2_ndt_has_converged.argtypes = [vp, pi]
+    L.b2_ndt_get_final_transformation.argtypes = [vp, vp]
+    L.b2_ndt_get_fitness_score.argtypes = [vp, pd]
+    L.b2_ndt_get_transformation_probability.argtypes = [vp, pd]
+    L.b2_ndt_get_final_num_iteration.argtypes = [vp, pi]
+    L.b2_ndt_get_voxels.argtypes = [vp, sz, C.POINTER(sz), vp, vp, vp, vp, vp, vp, vp]
+    L.b2_ndt_derivatives.argtypes = [vp, vp, pd, vp, vp, C.POINTER(C.c_longlong)]
+    L.b2_ndt_last_gpu_ms.argtypes = [vp, pf, pi, pi, C.POINTER(C.c_longlong)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("b2_last_error", "b2_s2m_default_params", "b2_scan_default_params", "b2_kernel_launch_count",

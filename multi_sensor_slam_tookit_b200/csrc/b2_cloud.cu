@@ -9,6 +9,7 @@
 // (z, y, x) voxel order, sums inside a voxel run in ascending input index, neighbour ties fall to the smaller index,
 // the normal's sign makes the first non-zero of (z, y, x) positive.
 #include "b2_cloud.cuh"
+#include "b2_bvh.cuh"
 #include <cmath>
 #include <algorithm>
 
@@ -365,51 +366,6 @@ __device__ __forceinline__ void jacobi3_f64(const double A[9], double w[3], doub
             }
 }
 
-// A warp keeps the 32 best (distance, index) pairs seen so far, one per lane, ascending; slot K-1 is the k-th best.
-struct WarpList {
-    double sd; int si; uint32_t sp;       // this lane's slot
-    double kd; int ki;                    // k-th best (uniform)
-};
-__device__ __forceinline__ void warp_offer(WarpList& L, int K, double d, int idx, uint32_t pos, bool valid) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    unsigned mask = __ballot_sync(full, valid && (d < L.kd || (d == L.kd && idx < L.ki)));
-    while (mask) {
-        const int src = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const double cd = shfl_d(full, d, src);
-        const int ci = __shfl_sync(full, idx, src);
-        const uint32_t cp = __shfl_sync(full, pos, src);
-        if (!(cd < L.kd || (cd == L.kd && ci < L.ki))) continue;
-        const bool gt = (L.sd > cd) || (L.sd == cd && L.si > ci);
-        const unsigned gm = __ballot_sync(full, gt);
-        const int ins = __ffs(gm) - 1;
-        const double ud = shfl_up_d(full, L.sd, 1);
-        const int ui = __shfl_up_sync(full, L.si, 1);
-        const uint32_t up = __shfl_up_sync(full, L.sp, 1);
-        if (lane > ins) { L.sd = ud; L.si = ui; L.sp = up; }
-        else if (lane == ins) { L.sd = cd; L.si = ci; L.sp = cp; }
-        L.kd = shfl_d(full, L.sd, K - 1);
-        L.ki = __shfl_sync(full, L.si, K - 1);
-    }
-}
-
-// ---- 32-ary bounding-volume hierarchy over the Morton-sorted points (one tree level per factor of 32) -------------
-// Lidar clouds vary in density by orders of magnitude, so neighbourhoods are not found with a uniform grid here: a
-// leaf is 32 consecutive points of the Morton order, a node of level l holds 32 nodes of level l-1, and a warp tests
-// the 32 children of a node in one step (one lane per child box). Children are visited nearest first and skipped
-// once their box is farther than the current k-th neighbour (strictly: equal distances are still visited, a tied
-// point with a smaller index may hide there). Box distances use the same (dx*dx + dy*dy) + dz*dz association as
-// point distances, so rounding is monotone and the pruning is exact.
-constexpr int BVH_MAXL = 7;
-struct BvhDev {
-    const P4d* pts;
-    const double* box[BVH_MAXL];     // level l: count[l] boxes of 6 doubles (min xyz, max xyz)
-    uint32_t count[BVH_MAXL];
-    int levels;
-    uint32_t n;                      // finite points
-};
-
 __device__ __forceinline__ unsigned long long morton_expand21(unsigned long long v) {
     v &= 0x1fffffull;
     v = (v | (v << 32)) & 0x1f00000000ffffull;
@@ -473,65 +429,6 @@ __global__ void __launch_bounds__(256) k_bvh_node_boxes(const double* __restrict
         for (int o = 16; o > 0; o >>= 1) { lo[d] = fmin(lo[d], shfl_xor_d(0xffffffffu, lo[d], o)); hi[d] = fmax(hi[d], shfl_xor_d(0xffffffffu, hi[d], o)); }
     if (lane < 3) box[6 * (size_t)node + lane] = lo[lane];
     else if (lane < 6) box[6 * (size_t)node + lane] = hi[lane - 3];
-}
-
-__device__ __forceinline__ double box_dist2(const double* __restrict__ b, double qx, double qy, double qz) {
-    const double2 a0 = __ldg(reinterpret_cast<const double2*>(b)), a1 = __ldg(reinterpret_cast<const double2*>(b) + 1),
-                  a2 = __ldg(reinterpret_cast<const double2*>(b) + 2);
-    // a0 = (lo.x, lo.y), a1 = (lo.z, hi.x), a2 = (hi.y, hi.z)
-    const double dx = fmax(0.0, fmax(a0.x - qx, qx - a1.y));
-    const double dy = fmax(0.0, fmax(a0.y - qy, qy - a2.x));
-    const double dz = fmax(0.0, fmax(a1.x - qz, qz - a2.y));
-    return dx * dx + dy * dy + dz * dz;
-}
-
-__device__ __forceinline__ void bvh_scan_leaf(const BvhDev& T, WarpList& L, int K, double qx, double qy, double qz, uint32_t leaf) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t p = leaf * 32u + lane;
-    const bool valid = p < T.n;
-    double d = INFINITY; int idx = 0x7fffffff;
-    if (valid) {
-        double x, y, z; long long id;
-        load_p4d(&T.pts[p], x, y, z, id);
-        const double dx = qx - x, dy = qy - y, dz = qz - z;
-        d = dx * dx + dy * dy + dz * dz;
-        idx = (int)id;
-    }
-    warp_offer(L, K, d, idx, p, valid);
-}
-
-// warp-wide exact K nearest neighbours of (qx, qy, qz); on return lane r < K holds the r-th neighbour in L
-__device__ __forceinline__ void bvh_knn_warp(const BvhDev& T, WarpList& L, int K, double qx, double qy, double qz) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int top = T.levels - 1;
-    if (top == 0) { bvh_scan_leaf(T, L, K, qx, qy, qz, 0); return; }
-    double dch[BVH_MAXL];
-    uint32_t node[BVH_MAXL];
-    int lv = top;
-    node[lv] = 0;
-    auto expand = [&](int l, uint32_t nd) {
-        const uint32_t c = nd * 32u + lane;
-        dch[l] = (c < T.count[l - 1]) ? box_dist2(T.box[l - 1] + 6 * (size_t)c, qx, qy, qz) : INFINITY;
-    };
-    expand(lv, 0);
-    for (;;) {
-        double dmin = dch[lv]; int jmin = lane;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double od = shfl_xor_d(full, dmin, o);
-            const int oj = __shfl_xor_sync(full, jmin, o);
-            if (od < dmin || (od == dmin && oj < jmin)) { dmin = od; jmin = oj; }
-        }
-        if (dmin == INFINITY || dmin > L.kd) {          // nothing left worth visiting below this node
-            if (++lv > top) break;
-            continue;
-        }
-        if (lane == jmin) dch[lv] = INFINITY;
-        const uint32_t child = node[lv] * 32u + (uint32_t)jmin;
-        if (lv == 1) bvh_scan_leaf(T, L, K, qx, qy, qz, child);
-        else { lv--; node[lv] = child; expand(lv, child); }
-    }
 }
 
 // One warp serves 32 consecutive Morton-sorted points: phase 1 finds each one's K nearest neighbours with the whole
@@ -607,68 +504,71 @@ static int sort_by_u64(const unsigned long long* lin, size_t n, int bits, uint32
     return B2_OK;
 }
 
+int BvhIndex::build(const double* xyz, size_t n, DevBuf& work, cudaStream_t s) {
+    dev = BvhDev{};
+    if (n == 0) return B2_OK;
+    if (n > 0x7fffffffull) { set_error("bvh: too many points"); return B2_ERR_ARG; }
+    double mn[3], mx[3];
+    B2_CHECK(bbox_f64(xyz, n, work, s, mn, mx));
+    if (!(mn[0] <= mx[0])) return B2_OK;
+    const double emax = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+    const double scale = emax > 0 ? 2097151.0 / emax : 0.0;
+    const unsigned nblk = (unsigned)((n + 255) / 256);
+    size_t box_doubles = 0;
+    for (uint32_t m = (uint32_t)((n + 31) / 32);; m = (m + 31) / 32) { box_doubles += 6 * (size_t)m; if (m == 1) break; }
+    const size_t nal = (n + 63) & ~(size_t)63;
+    const size_t need = nal * 8 + 4 * nal * 4 + sort_tmp_bytes(n) + 1024;
+    B2_CHECK(work.reserve(need));
+    B2_CHECK(pts.reserve(n * sizeof(P4d)));
+    B2_CHECK(boxes.reserve(box_doubles * 8 + 64));
+    unsigned long long* lin = work.as<unsigned long long>();
+    uint32_t* ka = reinterpret_cast<uint32_t*>(lin + nal);
+    uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
+    char* scratch = reinterpret_cast<char*>(vb + nal);
+    unsigned int* d_valid = reinterpret_cast<unsigned int*>(scratch + sort_tmp_bytes(n));
+    B2_CUDA(cudaMemsetAsync(d_valid, 0, 4, s));
+    k_morton_key<<<nblk, 256, 0, s>>>(xyz, (uint32_t)n, mn[0], mn[1], mn[2], scale, lin, ka, va, d_valid); count_launch();
+    B2_CUDA(cudaGetLastError());
+    uint32_t* order = nullptr;
+    B2_CHECK(sort_by_u64(lin, n, 64, ka, va, kb, vb, scratch, s, &order));
+    k_celld_gather<<<nblk, 256, 0, s>>>(xyz, (uint32_t)n, order, pts.as<P4d>()); count_launch();
+    uint32_t n_valid = 0;
+    B2_CUDA(cudaMemcpyAsync(&n_valid, d_valid, 4, cudaMemcpyDeviceToHost, s));
+    B2_CUDA(cudaStreamSynchronize(s));
+    if (!n_valid) return B2_OK;
+    dev.pts = pts.as<P4d>(); dev.n = n_valid; dev.levels = 0;
+    double* bp = boxes.as<double>();
+    for (uint32_t m = (n_valid + 31) / 32;; m = (m + 31) / 32) {
+        dev.count[dev.levels] = m; dev.box[dev.levels] = bp; bp += 6 * (size_t)m; dev.levels++;
+        if (m == 1 || dev.levels == BVH_MAXL) break;
+    }
+    for (int l = dev.levels; l < BVH_MAXL; l++) { dev.count[l] = 0; dev.box[l] = nullptr; }
+    k_bvh_leaf_boxes<<<(dev.count[0] + 7) / 8, 256, 0, s>>>(dev.pts, n_valid, const_cast<double*>(dev.box[0]), dev.count[0]); count_launch();
+    for (int l = 1; l < dev.levels; l++) {
+        k_bvh_node_boxes<<<(dev.count[l] + 7) / 8, 256, 0, s>>>(dev.box[l - 1], dev.count[l - 1], const_cast<double*>(dev.box[l]), dev.count[l]); count_launch();
+    }
+    B2_CUDA(cudaGetLastError());
+    return B2_OK;
+}
+
 int estimate_normals_knn(b2_cloud_s* c, int knn) {
     if (knn < 1 || knn > NRM_MAXK) { set_error("estimate_normals: knn must be in [1, %d]", NRM_MAXK); return B2_ERR_ARG; }
     cudaStream_t s = c->stream;
     c->has_normals = false;
     if (c->n == 0) { c->has_normals = true; return B2_OK; }
     const size_t n = c->n;
-    if (n > 0x7fffffffull) { set_error("estimate_normals: too many points"); return B2_ERR_ARG; }
     B2_CHECK(c->nrm.reserve(n * 24));
-    const unsigned nblk = (unsigned)((n + 255) / 256);
-    k_fill_normals<<<nblk, 256, 0, s>>>(c->nrm.as<double>(), (uint32_t)n); count_launch();
-    const double* xyz = c->xyz.as<double>();
-    double mn[3], mx[3];
-    B2_CHECK(bbox_f64(xyz, n, c->work, s, mn, mx));
-    if (!(mn[0] <= mx[0])) { c->has_normals = true; return B2_OK; }
-    const double emax = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
-    const double scale = emax > 0 ? 2097151.0 / emax : 0.0;
-    // tree geometry
-    uint32_t count[BVH_MAXL]; int levels = 0;
-    for (uint32_t m = (uint32_t)((n + 31) / 32);; m = (m + 31) / 32) { count[levels++] = m; if (m == 1 || levels == BVH_MAXL) break; }
-    size_t box_doubles = 0;
-    for (int l = 0; l < levels; l++) box_doubles += 6 * (size_t)count[l];
-    const size_t nal = (n + 63) & ~(size_t)63;
-    const size_t need = nal * 8 + 4 * nal * 4 + sort_tmp_bytes(n) + 1024;
-    DevBuf pts, boxes;
-    int st = c->work.reserve(need);
-    if (st == B2_OK) st = pts.reserve(n * sizeof(P4d));
-    if (st == B2_OK) st = boxes.reserve(box_doubles * 8 + 64);
-    if (st != B2_OK) { pts.release(); boxes.release(); return st; }
-    unsigned long long* lin = c->work.as<unsigned long long>();
-    uint32_t* ka = reinterpret_cast<uint32_t*>(lin + nal);
-    uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
-    char* scratch = reinterpret_cast<char*>(vb + nal);
-    unsigned int* d_valid = reinterpret_cast<unsigned int*>(scratch + sort_tmp_bytes(n));
-    cudaError_t e = cudaMemsetAsync(d_valid, 0, 4, s);
-    k_morton_key<<<nblk, 256, 0, s>>>(xyz, (uint32_t)n, mn[0], mn[1], mn[2], scale, lin, ka, va, d_valid); count_launch();
-    uint32_t* order = nullptr;
-    st = sort_by_u64(lin, n, 64, ka, va, kb, vb, scratch, s, &order);
-    uint32_t n_valid = 0;
-    if (st == B2_OK) {
-        k_celld_gather<<<nblk, 256, 0, s>>>(xyz, (uint32_t)n, order, pts.as<P4d>()); count_launch();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&n_valid, d_valid, 4, cudaMemcpyDeviceToHost, s);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    }
-    if (st == B2_OK && e == cudaSuccess && n_valid) {
-        BvhDev T;
-        T.pts = pts.as<P4d>(); T.n = n_valid; T.levels = 0;
-        double* bp = boxes.as<double>();
-        for (uint32_t m = (n_valid + 31) / 32;; m = (m + 31) / 32) {
-            T.count[T.levels] = m; T.box[T.levels] = bp; bp += 6 * (size_t)m; T.levels++;
-            if (m == 1 || T.levels == BVH_MAXL) break;
-        }
-        for (int l = T.levels; l < BVH_MAXL; l++) { T.count[l] = 0; T.box[l] = nullptr; }
-        k_bvh_leaf_boxes<<<(T.count[0] + 7) / 8, 256, 0, s>>>(T.pts, n_valid, const_cast<double*>(T.box[0]), T.count[0]); count_launch();
-        for (int l = 1; l < T.levels; l++) {
-            k_bvh_node_boxes<<<(T.count[l] + 7) / 8, 256, 0, s>>>(T.box[l - 1], T.count[l - 1], const_cast<double*>(T.box[l]), T.count[l]); count_launch();
-        }
+    k_fill_normals<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->nrm.as<double>(), (uint32_t)n); count_launch();
+    BvhIndex bvh;
+    int st = bvh.build(c->xyz.as<double>(), n, c->work, s);
+    cudaError_t e = cudaSuccess;
+    if (st == B2_OK && bvh.dev.n) {
         const unsigned per_block = NRM_WARPS * 32;
-        k_normals<<<(n_valid + per_block - 1) / per_block, per_block, 0, s>>>(T, knn, c->nrm.as<double>()); count_launch();
+        k_normals<<<(bvh.dev.n + per_block - 1) / per_block, per_block, 0, s>>>(bvh.dev, knn, c->nrm.as<double>()); count_launch();
         e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     }
-    pts.release(); boxes.release();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    bvh.release();
     if (st != B2_OK) return st;
     if (e != cudaSuccess) { set_error("estimate_normals: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
     c->has_normals = true;

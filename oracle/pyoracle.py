@@ -85,6 +85,21 @@ def lib():
     L.o_extract_features.argtypes = [f32p, i32p, C.c_int, i32p, i32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
                                      f32p, i32p, i32p, i32p, i32p, i32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     od64 = _opt(f64p)
+    L.o_ndt_create.restype = C.c_void_p
+    L.o_ndt_create.argtypes = [C.c_float, C.c_double, C.c_double, C.c_int]
+    L.o_ndt_destroy.argtypes = [C.c_void_p]
+    L.o_ndt_set_target.restype = C.c_int
+    L.o_ndt_set_target.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.o_ndt_set_source.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.o_ndt_get_voxels.argtypes = [C.c_void_p, i32p, i32p, f32p, f64p, f64p]
+    L.o_ndt_grid_geometry.argtypes = [C.c_void_p, i32p, i32p]
+    L.o_ndt_derivatives.restype = C.c_double
+    L.o_ndt_derivatives.argtypes = [C.c_void_p, f64p, f64p, od64, C.POINTER(C.c_longlong)]
+    L.o_ndt_pose_to_matrix.argtypes = [f64p, f32p]
+    L.o_ndt_align.argtypes = [C.c_void_p, f32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.o_ndt_fitness.restype = C.c_double
+    L.o_ndt_fitness.argtypes = [C.c_void_p, f32p]
+    L.o_svd_solve6.argtypes = [f64p, f64p, f64p]
     L.o_o3d_voxel_down_sample.restype = C.c_int
     L.o_o3d_voxel_down_sample.argtypes = [f64p, C.c_int, C.c_double, f64p, oi32]
     L.o_gicp_normals_covs.argtypes = [f64p, C.c_int, C.c_int, C.c_double, od64, od64, C.c_int]
@@ -321,3 +336,64 @@ class GicpOracle:
                                     _f64(init).reshape(16), float(max_corr), float(rel_fit), float(rel_rmse), int(max_it),
                                     T, C.byref(fit), C.byref(rmse), self.threads)
         return dict(transformation=T.reshape(4, 4), fitness=fit.value, inlier_rmse=rmse.value, iterations=it)
+
+
+# ---------------------------------------------------------------- PCL NDT path (multi_lidar calibrator)
+class NdtOracle:
+    """pcl::NormalDistributionsTransform<PointXYZ, PointXYZ> restatement (serial, like PCL's)."""
+
+    def __init__(self, resolution=1.0, step_size=0.1, epsilon=0.01, max_iterations=400):
+        self.L = lib()
+        self.h = self.L.o_ndt_create(float(resolution), float(step_size), float(epsilon), int(max_iterations))
+        self.n_voxels = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.o_ndt_destroy(self.h)
+            self.h = None
+
+    def set_target(self, xyz):
+        p = _f32(xyz).reshape(-1, 3)
+        self.n_voxels = self.L.o_ndt_set_target(self.h, p, len(p))
+        return self.n_voxels
+
+    def set_source(self, xyz):
+        p = _f32(xyz).reshape(-1, 3)
+        self.L.o_ndt_set_source(self.h, p, len(p))
+
+    def voxels(self):
+        m = max(self.n_voxels, 1)
+        idx, npts = np.empty(m, np.int32), np.empty(m, np.int32)
+        cen, mean, icov = np.empty((m, 3), np.float32), np.empty((m, 3), np.float64), np.empty((m, 9), np.float64)
+        self.L.o_ndt_get_voxels(self.h, idx, npts, cen, mean, icov)
+        k = self.n_voxels
+        mn, dv = np.empty(3, np.int32), np.empty(3, np.int32)
+        self.L.o_ndt_grid_geometry(self.h, mn, dv)
+        return dict(index=idx[:k], npts=npts[:k], centroid=cen[:k], mean=mean[:k], icov=icov[:k].reshape(-1, 3, 3), min_b=mn, div_b=dv)
+
+    def derivatives(self, p):
+        g, H, pairs = np.zeros(6), np.zeros(36), C.c_longlong()
+        s = self.L.o_ndt_derivatives(self.h, _f64(p), g, H, C.byref(pairs))
+        return s, g, H.reshape(6, 6), pairs.value
+
+    def align(self, guess):
+        T = np.empty(16, np.float32)
+        it, conv, prob, ev = C.c_int(), C.c_int(), C.c_double(), C.c_int()
+        self.L.o_ndt_align(self.h, _f32(guess).reshape(16), T, C.byref(it), C.byref(conv), C.byref(prob), C.byref(ev))
+        return dict(transformation=T.reshape(4, 4), iterations=it.value, converged=bool(conv.value),
+                    transformation_probability=prob.value, evaluations=ev.value)
+
+    def fitness(self, T):
+        return self.L.o_ndt_fitness(self.h, _f32(T).reshape(16))
+
+
+def ndt_pose_to_matrix(p):
+    T = np.empty(16, np.float32)
+    lib().o_ndt_pose_to_matrix(_f64(p), T)
+    return T.reshape(4, 4)
+
+
+def svd_solve6(H, b):
+    x = np.empty(6)
+    lib().o_svd_solve6(_f64(H).reshape(36), _f64(b), x)
+    return x
