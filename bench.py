@@ -13,6 +13,8 @@ liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:1282-1310 on one VLP-16 scan agains
   batched    B scans (pose hypotheses) against the one map in a single launch per iteration
   cpu_baseline  the CPU oracle (restatement of the reference path) on the box's host cores
 --impl reference times that CPU path alone (PCL/OpenCV are not installable here: the oracle is the reference arm).
+  registration  the NDT / GICP half of the metric (Mpts/s): C3 NDT pair, C4 batched GICP pairs (round-robin over ranks),
+             C5 50 M-point map-to-map GICP (source sharded over ranks, NCCL all-reduce of 30 doubles per iteration)
 Multi-GPU: C1 does not shard — N GPUs run N independent replicas, no collective on the data path.
 """
 import argparse
@@ -303,6 +305,9 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
     dev_ms_m, e2e_s_m, act_ms_m, wall_ms_m = [float(v) for v in t.tolist()]
     iters_all, e_iters_all = [float(v) for v in u.tolist()]
+    del g, flush
+    L.b2_trim_memory()
+    registration = None if args.skip_registration else run_registration(args, rank, local_rank, world, dist, torch)
     if rank == 0:
         peak, peak_src = peaks()
         abytes, cand, compulsory = algorithmic_bytes_per_iteration(c1, guess)
@@ -344,10 +349,115 @@ def run_b200(args, rank, local_rank, world):
                                 "sample": f"{st1} solves of the same scan/map in {el1:.1f} s (kd-trees prebuilt), {it1} iterations each",
                                 "with_index_build": v_full, "threads4": v_4,
                                 "note": "CPU restatement of the reference path (oracle/), OpenMP over features as the reference"}
+        if registration:
+            line["registration"] = registration
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ NDT / GICP workloads
+def run_registration(args, rank, local_rank, world, dist, torch):
+    """Configs C3 (NDT), C4 (batched GICP pairs) and C5 (sharded map-to-map GICP) of BASELINE.json — the "NDT/GICP Mpts/s" half
+    of the metric. Unit everywhere: source-point evaluations per second. Returns the dict rank 0 prints (None elsewhere)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gicp_bench as GB
+    import ndt_bench as NB
+    from multi_sensor_slam_tookit_b200 import gicp
+    peak, peak_src = peaks()
+    out = {}
+
+    def allmax(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- C3: one NDT pair does not shard (SURVEY.md 8e) -> rank 0 only
+    if rank == 0:
+        inputs = NB.c3_inputs()
+        r, src = NB.run_c3(inputs=inputs)
+        bytes_pass = 12.0 * r["source_points"] + 96.0 * r["pairs_per_pass"]          # point + (mean, inverse covariance) per pair
+        ach = bytes_pass * r["evaluations"] / (r["align_gpu_ms"] * 1e-3) / 1e9
+        cpu = NB.cpu_c3(inputs, src)
+        out["ndt_c3"] = {
+            "workload": f"C3 multi_lidar NDT: parent {r['parent_points']} pts -> {r['voxels']} voxels of 1 m, child {r['child_points']} pts "
+                        f"-> {r['source_points']} after VoxelGrid(0.1)", "value": r["mpts_per_s"], "unit": "Mpts/s",
+            "e2e": {"value": r["e2e_mpts_per_s"], "unit": "Mpts/s", "ms": r["e2e_wall_ms"],
+                    "step": "new handle + setInputSource + setInputTarget + align + getFitnessScore from host buffers",
+                    "h2d_bytes": int(12 * (r["parent_points"] + r["source_points"])), "d2h_bytes": int(29 * 8 * r["evaluations"] + 64 + 16)},
+            "iterations": r["iterations"], "evaluations": r["evaluations"], "align_gpu_ms": r["align_gpu_ms"], "gpu_launches": r["launches"],
+            "t_err_m": r["t_err"], "r_err_rad": r["r_err"],
+            "roofline": {"kernel": "k_ndt_derivatives", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_pass,
+                         "note": "12 B point + 96 B (mean + inverse covariance) per (point, voxel) pair; 0.3 MB of voxel data, L2-resident; "
+                                 "span of align / derivative passes, includes the host line search between passes"},
+            "cpu_baseline": {"value": cpu["mpts_per_s"], "unit": "Mpts/s", "cores": 1, "kind": "port",
+                             "sample": f"the same registration, {cpu['evaluations']} derivative passes in {cpu['align_s']:.2f} s; serial like PCL's NDT"}}
+    # ---- C4: independent pairs, pair i on rank i % world, host buffers in -> transformation out
+    c4 = GB.run_c4(rank, world)
+    wall = allmax(c4["wall_s"]); gpu_ms = allmax(c4["gpu_ms"]); evals = allsum(c4["src_evals"]); npairs = allsum(c4["pairs"])
+    iters = allsum(c4["iters"]); launches = allsum(c4["launches"]); terr = allmax(c4["max_t_err"]); rerr = allmax(c4["max_r_err"])
+    if rank == 0:
+        ev, tt, tr, it = GB.cpu_c4_pair(os.cpu_count() or 1)
+        ach = 144.0 * evals / (gpu_ms * 1e-3) / 1e9 / world
+        out["gicp_c4"] = {
+            "workload": f"C4 Multi_LiCa GICP: 5 lidars 64x1024, {int(npairs)} ordered pairs, voxel 0.05, max_corr 1.0, eps 0.005, 1e-7/1e-7, 100 its",
+            "value": evals / (gpu_ms * 1e-3) / 1e6, "unit": "Mpts/s", "scaling": "pairs round-robin over ranks, no collective",
+            "e2e": {"value": evals / wall / 1e6, "unit": "Mpts/s", "ms_per_pair": 1e3 * wall * world / npairs,
+                    "step": "per pair: upload both clouds, voxel_down_sample, estimate_normals, registration_generalized_icp, result to host"},
+            "iterations_total": int(iters), "gpu_launches": int(launches), "max_t_err_m": terr, "max_r_err_rad": rerr,
+            "roofline": {"kernel": "k_gicp_linearize", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "144 B per source point per linearisation (SURVEY.md 8d), per GPU; ~50 k-point clouds: launch/latency bound"},
+            "cpu_baseline": {"value": ev / tr / 1e6, "unit": "Mpts/s", "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": f"pair (1 -> 0): {it} iterations in {tr:.3f} s (registration only), {tt:.3f} s with downsampling + normals",
+                             "e2e_value": ev / tt / 1e6}}
+    # ---- C5: one registration, source sharded over the ranks, 30 doubles all-reduced per iteration
+    comm = None
+    if world > 1:
+        ids = [gicp.Communicator.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm = gicp.Communicator(ids[0], rank, world)
+    c5 = GB.run_c5(args.c5_points, rank, world, comm)
+    ms = allmax(c5["gpu_ms"])
+    if rank == 0:
+        ach = 144.0 * c5["points"] * c5["evaluations"] / world / (ms * 1e-3) / 1e9
+        out["gicp_c5"] = {
+            "workload": f"C5 map-to-map GICP: {c5['points']} source pts vs {c5['points']} target pts (city block tiled 4x4), "
+                        f"{c5['iterations']} fixed iterations, max_corr 1.0", "value": c5["points"] * c5["evaluations"] / (ms * 1e-3) / 1e6,
+            "unit": "Mpts/s", "n_gpus": world, "scaling": "strong", "ms_per_align": ms, "ms_per_evaluation": ms / c5["evaluations"],
+            "parallelism": f"target replicated, source sharded x{world}, ncclAllReduce(30 doubles) per iteration" if world > 1 else "single GPU",
+            "gpu_launches": c5["launches"], "fitness": c5["fitness"], "inlier_rmse": c5["inlier_rmse"], "t_err_m": c5["t_err"],
+            "r_err_rad": c5["r_err"], "target_cell_edge_m": c5["cell_edge"], "setup_s": c5["setup_s"],
+            "roofline": {"kernel": "k_gicp_linearize", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": 144.0 * c5["points"] / world,
+                         "note": "144 B per source point per linearisation (SURVEY.md 8d), per GPU, over the whole align (the first "
+                                 "evaluation at the 0.3 m / 0.8 deg offset searches the coarse grid for about a fifth of the points)"}}
+        if args.c5_cpu_points > 0:
+            from oracle import pyoracle as O
+            n = args.c5_cpu_points
+            s_, t_, _ = GB.c5_clouds_torch(n, "cuda")
+            cores = os.cpu_count() or 1
+            _, sc = O.gicp_normals_covs(s_, 30, 0.005, cores)
+            _, tc = O.gicp_normals_covs(t_, 30, 0.005, cores)
+            go = O.GicpOracle(s_, sc, t_, tc, cores)
+            t0 = time.perf_counter(); reps = 0
+            while time.perf_counter() - t0 < 6.0:
+                go.linearize(np.eye(4), 1.0); reps += 1
+            el = time.perf_counter() - t0
+            out["gicp_c5"]["cpu_baseline"] = {"value": n * reps / el / 1e6, "unit": "Mpts/s", "cores": cores, "kind": "port",
+                                              "sample": f"{reps} linearisations of a {n}-point sample of the same scene in {el:.1f} s (kd-tree prebuilt)"}
+    return out if rank == 0 else None
 
 
 def main():
@@ -357,6 +467,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--c5-points", type=int, default=50_000_000, help="points of the sharded map-to-map GICP (config C5)")
+    ap.add_argument("--c5-cpu-points", type=int, default=500_000, help="sample size of the C5 cpu_baseline (0 = skip)")
+    ap.add_argument("--skip-registration", action="store_true", help="C1 only (skip the NDT / GICP workloads)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
