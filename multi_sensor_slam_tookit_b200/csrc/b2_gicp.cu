@@ -423,7 +423,7 @@ int b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source) {
     if (!h || !source) return B2_ERR_ARG;
     h->have_src = false;
     uint32_t nv = 0;
-    B2_CHECK(gicp_set_cloud(h, source, h->src_grid, h->src_m, 8.0, &nv));
+    B2_CHECK(gicp_set_cloud(h, source, h->src_grid, h->src_m, 2.0, &nv));
     h->n_src = source->n;
     h->src_valid = nv;
     h->have_src = true;

@@ -111,18 +111,57 @@ __device__ __forceinline__ void row_range(const GridDDev& g, int x0, int x1, int
 // grid's order (through `fine_pos_of`, original index -> fine position, when the coarse pass found it).
 struct NN1 { double d2; long long idx; double x, y, z; uint32_t pos; };
 
+__device__ __forceinline__ void nn1_consider(NN1& best, double radius2, double qx, double qy, double qz, double x, double y, double z,
+                                             long long idx, uint32_t p) {
+    const double ddx = qx - x, ddy = qy - y, ddz = qz - z;
+    const double d = ddx * ddx + ddy * ddy + ddz * ddz;
+    if (d < radius2 && (d < best.d2 || (d == best.d2 && idx < best.idx))) { best.d2 = d; best.idx = idx; best.x = x; best.y = y; best.z = z; best.pos = p; }
+}
+
+// candidates [b, e): four loads are issued before the first is consumed (the loop is bound by load latency otherwise)
+__device__ __forceinline__ void nn1_scan_run(const GridDDev& g, uint32_t b, uint32_t e, double qx, double qy, double qz, double radius2, NN1& best) {
+    for (uint32_t p = b; p < e; p += 4) {
+        double x[4], y[4], z[4]; long long id[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t pk = min(p + k, e - 1);
+            load_p4d(&g.pts[pk], x[k], y[k], z[k], id[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (p + k < e) nn1_consider(best, radius2, qx, qy, qz, x[k], y[k], z[k], id[k], p + k);
+    }
+}
+
+// the 3x3x3 block as nine contiguous runs, all eighteen bounds requested up front
 __device__ __forceinline__ void nn1_scan_block(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best) {
     uint32_t rb[9], re[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) row_range(g, qc.cx - 1, qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, rb[i], re[i]);
 #pragma unroll 1
-    for (int i = 0; i < 9; i++) {
-        for (uint32_t p = rb[i]; p < re[i]; p++) {
-            double x, y, z; long long idx;
-            load_p4d(&g.pts[p], x, y, z, idx);
-            const double ddx = qx - x, ddy = qy - y, ddz = qz - z;
-            const double d = ddx * ddx + ddy * ddy + ddz * ddz;
-            if (d < radius2 && (d < best.d2 || (d == best.d2 && idx < best.idx))) { best.d2 = d; best.idx = idx; best.x = x; best.y = y; best.z = z; best.pos = p; }
+    for (int i = 0; i < 9; i++) nn1_scan_run(g, rb[i], re[i], qx, qy, qz, radius2, best);
+}
+
+// the 3x3x3 block cell by cell, nearest cells first, skipping every cell whose box is farther than the best so far
+// (cells of the coarse grid hold tens of points, so a skipped cell saves more than its two bound loads cost)
+__device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best) {
+    const double fx = (qx - g.ox) * g.inv_h - (double)qc.cx, fy = (qy - g.oy) * g.inv_h - (double)qc.cy, fz = (qz - g.oz) * g.inv_h - (double)qc.cz;
+    const double h2 = g.h * g.h * (1.0 - 1e-9);
+    // offsets ordered by |dx| + |dy| + |dz|: centre, 6 faces, 12 edges, 8 corners (3 bits per axis, value + 1)
+#pragma unroll 1
+    for (int pass = 0; pass < 4; pass++) {
+#pragma unroll 1
+        for (int k = 0; k < 27; k++) {
+            const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
+            if (abs(ox) + abs(oy) + abs(oz) != pass) continue;
+            const double gx = ox < 0 ? fx : (ox > 0 ? 1.0 - fx : 0.0);
+            const double gy = oy < 0 ? fy : (oy > 0 ? 1.0 - fy : 0.0);
+            const double gz = oz < 0 ? fz : (oz > 0 ? 1.0 - fz : 0.0);
+            const double bd2 = (gx * gx + gy * gy + gz * gz) * h2;
+            if (bd2 > best.d2 || bd2 >= radius2) continue;
+            uint32_t b, e;
+            row_range(g, qc.cx + ox, qc.cx + ox, qc.cy + oy, qc.cz + oz, b, e);
+            nn1_scan_run(g, b, e, qx, qy, qz, radius2, best);
         }
     }
 }
@@ -137,7 +176,7 @@ __device__ __forceinline__ NN1 nn1_thread(const GridDDev& fine, const GridDDev& 
     if (best.d2 < bound2 || bound2 >= radius2 || !have_coarse) return best;
     const QueryCell qcc = query_cell(coarse, qx, qy, qz);
     const long long before = best.idx;
-    nn1_scan_block(coarse, qcc, qx, qy, qz, radius2, best);
+    nn1_scan_block_pruned(coarse, qcc, qx, qy, qz, radius2, best);
     if (best.idx != before) best.pos = __ldg(&fine_pos_of[best.idx]);
     return best;
 }
