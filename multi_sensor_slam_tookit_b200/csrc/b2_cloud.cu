@@ -199,6 +199,35 @@ int GridD::build(const double* d_xyz, size_t n_, double h_request, double target
     return B2_OK;
 }
 
+__global__ void __launch_bounds__(256) k_grid_cell_boxes(const P4d* __restrict__ pts, const uint32_t* __restrict__ cell_start, size_t ncell,
+                                                         float* __restrict__ box) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const uint32_t b = cell_start[c], e = cell_start[c + 1];
+    if (b >= e) return;
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t p = b; p < e; p++) {
+        double x, y, z; long long id;
+        load_p4d(&pts[p], x, y, z, id);
+        lo[0] = fmin(lo[0], x); lo[1] = fmin(lo[1], y); lo[2] = fmin(lo[2], z);
+        hi[0] = fmax(hi[0], x); hi[1] = fmax(hi[1], y); hi[2] = fmax(hi[2], z);
+    }
+    float* o = box + 6 * c;
+    o[0] = __double2float_rd(lo[0]); o[1] = __double2float_rd(lo[1]); o[2] = __double2float_rd(lo[2]);
+    o[3] = __double2float_ru(hi[0]); o[4] = __double2float_ru(hi[1]); o[5] = __double2float_ru(hi[2]);
+}
+
+int GridD::build_cell_boxes(cudaStream_t s) {
+    dev.cell_box = nullptr;
+    if (!dev.pts || !n) return B2_OK;
+    const size_t ncell = (size_t)dev.nx * dev.ny * dev.nz;
+    B2_CHECK(cell_box.reserve(ncell * 24));
+    k_grid_cell_boxes<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(dev.pts, dev.cell_start, ncell, cell_box.as<float>()); count_launch();
+    B2_CUDA(cudaGetLastError());
+    dev.cell_box = cell_box.as<float>();
+    return B2_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ voxel_down_sample
 struct VdsGeom { double vmin[3]; double voxel; unsigned long long nx, ny; unsigned long long invalid; };
 

@@ -149,9 +149,9 @@ __global__ void __launch_bounds__(GICP_THREADS, 3) k_gicp_linearize(GicpArgs A) 
         if (A.corr && valid) A.corr[sidx] = hit ? (int32_t)nn.idx : -1;
         __syncwarp();
         if (!__any_sync(full, hit)) continue;
-        double term[GICP_NSUM];
+        double term[32];
 #pragma unroll
-        for (int i = 0; i < GICP_NSUM; i++) term[i] = 0.0;
+        for (int i = 0; i < 32; i++) term[i] = 0.0;
         if (hit) {
             const double* um = &A.tgt_m[3 * (size_t)nn.pos];
             const double* sm = &A.src_m[3 * (size_t)p];
@@ -187,13 +187,7 @@ __global__ void __launch_bounds__(GICP_THREADS, 3) k_gicp_linearize(GicpArgs A) 
             term[27] = 1.0; term[28] = nn.d2; term[29] = d0 * g0 + d1 * g1 + d2 * g2;
         }
         __syncwarp();
-#pragma unroll
-        for (int i = 0; i < GICP_NSUM; i++) {
-            double v = term[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(full, v, o);
-            if (lane == i) tot += v;
-        }
+        tot += warp_reduce_scatter32(term);
     }
     // epilogue: CTA partial, last CTA adds the partials in CTA order
     s_red[warp][lane] = tot;
@@ -311,6 +305,7 @@ static int gicp_ensure_coarse(b2_gicp_s* h) {
     h->have_coarse = false;
     if (h->n_tgt && r > h->tgt_grid.dev.h * 0.999) {
         B2_CHECK(h->tgt_coarse.build(h->tgt_xyz.as<double>(), h->n_tgt, r * 1.0078125, 0.0, h->stream));
+        B2_CHECK(h->tgt_coarse.build_cell_boxes(h->stream));
         h->have_coarse = true;
     } else h->tgt_coarse.release();
     h->coarse_for = r;

@@ -23,20 +23,23 @@ struct alignas(32) P4d { double x, y, z; long long idx; };
 struct GridDDev {
     const P4d* pts;
     const uint32_t* cell_start;
+    const float* cell_box;     // optional: per cell the bounding box of its points, 6 floats rounded outward (min xyz, max xyz)
     double ox, oy, oz, h, inv_h;
     int nx, ny, nz;
     uint32_t n;
 };
 
 struct GridD {
-    DevBuf pts, cell_start, work;
+    DevBuf pts, cell_start, work, cell_box;
     GridDDev dev{};
     size_t n = 0;
     double ppc = 0.0;          // points per occupied cell of the built grid
     // d_xyz: device, n*3 doubles. h_request > 0 fixes the cell edge (raised only if the cell budget requires it);
     // otherwise the edge is chosen so that an occupied cell holds about target_ppc points.
     int build(const double* d_xyz, size_t n, double h_request, double target_ppc, cudaStream_t s);
-    void release() { pts.release(); cell_start.release(); work.release(); dev = GridDDev{}; n = 0; }
+    // tight per-cell boxes (for grids whose cells hold many points: lets a search skip a cell without touching its points)
+    int build_cell_boxes(cudaStream_t s);
+    void release() { pts.release(); cell_start.release(); work.release(); cell_box.release(); dev = GridDDev{}; n = 0; }
 };
 
 #ifdef __CUDACC__
@@ -61,6 +64,24 @@ __device__ __forceinline__ double shfl_up_d(unsigned mask, double v, int o) {
     int lo = __double2loint(v), hi = __double2hiint(v);
     lo = __shfl_up_sync(mask, lo, o); hi = __shfl_up_sync(mask, hi, o);
     return __hiloint2double(hi, lo);
+}
+
+// Transposing warp reduction: every lane brings 32 values, lane i leaves with the sum over lanes of value i.
+// 31 shuffle-adds instead of 32 x 5 (halves are exchanged, so the live set shrinks 32 -> 16 -> ... -> 1). Fixed tree order.
+__device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32]) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; k++) {
+            const double keep = up ? v[k + o] : v[k];
+            const double send = up ? v[k] : v[k + o];
+            v[k] = keep + shfl_xor_d(full, send, o);
+        }
+    }
+    return v[0];
 }
 
 // Geometry of one query against a grid: cell, and the per-ring exactness bound.
@@ -161,6 +182,17 @@ __device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const Q
             if (bd2 > best.d2 || bd2 >= radius2) continue;
             uint32_t b, e;
             row_range(g, qc.cx + ox, qc.cx + ox, qc.cy + oy, qc.cz + oz, b, e);
+            if (b < e && g.cell_box) {
+                // the points of the cell usually fill a thin slab of it: test their own box before streaming them
+                const size_t cell = ((size_t)(qc.cz + oz) * g.ny + (qc.cy + oy)) * g.nx + (qc.cx + ox);
+                const float2* bx = reinterpret_cast<const float2*>(g.cell_box + 6 * cell);
+                const float2 b0 = __ldg(bx), b1 = __ldg(bx + 1), b2 = __ldg(bx + 2);      // (lo.x, lo.y) (lo.z, hi.x) (hi.y, hi.z)
+                const double ex = fmax(0.0, fmax((double)b0.x - qx, qx - (double)b1.y));
+                const double ey = fmax(0.0, fmax((double)b0.y - qy, qy - (double)b2.x));
+                const double ez = fmax(0.0, fmax((double)b1.x - qz, qz - (double)b2.y));
+                const double pd2 = ex * ex + ey * ey + ez * ez;
+                if (pd2 > best.d2 || pd2 >= radius2) continue;
+            }
             nn1_scan_run(g, b, e, qx, qy, qz, radius2, best);
         }
     }

@@ -247,7 +247,6 @@ __device__ __forceinline__ double dot3(const double v[3], double x, double y, do
 __global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
     __shared__ double s_red[NDT_WARPS][32];
     __shared__ bool s_last;
-    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double tot = 0.0;
     const uint32_t n_chunks = (A.n_src + 31) >> 5;
@@ -255,9 +254,9 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
     for (uint32_t chunk = blockIdx.x * NDT_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * NDT_WARPS) {
         const uint32_t i = (chunk << 5) + lane;
         const bool valid = i < A.n_src;
-        double term[NDT_NSUM];
+        double term[32];
 #pragma unroll
-        for (int q = 0; q < NDT_NSUM; q++) term[q] = 0.0;
+        for (int q = 0; q < 32; q++) term[q] = 0.0;
         if (valid) {
             const float sx = A.src[3 * (size_t)i], sy = A.src[3 * (size_t)i + 1], sz = A.src[3 * (size_t)i + 2];
             const float tx = A.T[0] * sx + A.T[1] * sy + A.T[2] * sz + A.T[3];
@@ -347,13 +346,7 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
             }
         }
         __syncwarp();
-#pragma unroll
-        for (int q = 0; q < NDT_NSUM; q++) {
-            double v = term[q];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(full, v, o);
-            if (lane == q) tot += v;
-        }
+        tot += warp_reduce_scatter32(term);
     }
     s_red[warp][lane] = tot;
     __syncthreads();
