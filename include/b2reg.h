@@ -259,6 +259,8 @@ int  b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double*
 /* fitness / inlier_rmse of every evaluation of the last align (the first one is the evaluation at init) */
 int  b2_gicp_get_history(b2_gicp_t h, double* fitness, double* inlier_rmse, int capacity, int* n_evaluations);
 int  b2_gicp_last_gpu_ms(b2_gicp_t h, float* ms, int* launches);
+/* device time of every evaluation of the last align (the all-reduce and the update of a sharded run included) */
+int  b2_gicp_get_evaluation_ms(b2_gicp_t h, float* ms, int capacity, int* n_evaluations);
 int  b2_gicp_index_info(b2_gicp_t h, double* target_cell_edge, double* target_points_per_cell,
                         uint32_t* shard_begin, uint32_t* shard_end);
 

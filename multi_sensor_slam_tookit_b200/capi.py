@@ -49,7 +49,7 @@ SYMBOLS = [
     "b2_comm_unique_id", "b2_comm_create", "b2_comm_destroy", "b2_comm_rank", "b2_comm_allreduce_f64",
     "b2_gicp_default_params", "b2_gicp_create", "b2_gicp_destroy", "b2_gicp_set_params", "b2_gicp_set_target",
     "b2_gicp_set_source", "b2_gicp_set_shard", "b2_gicp_linearize", "b2_gicp_align", "b2_gicp_get_history",
-    "b2_gicp_last_gpu_ms", "b2_gicp_index_info",
+    "b2_gicp_last_gpu_ms", "b2_gicp_index_info", "b2_gicp_get_evaluation_ms",
     "b2_ndt_create", "b2_ndt_destroy", "b2_ndt_set_transformation_epsilon", "b2_ndt_set_step_size", "b2_ndt_set_resolution",
     "b2_ndt_set_maximum_iterations", "b2_ndt_set_input_target", "b2_ndt_set_input_source", "b2_ndt_align", "b2_ndt_has_converged",
     "b2_ndt_get_final_transformation", "b2_ndt_get_fitness_score", "b2_ndt_get_transformation_probability",
@@ -130,6 +130,7 @@ def lib():
     L.b2_gicp_align.argtypes = [vp, vp, vp, pd, pd, pi, pi]
     L.b2_gicp_get_history.argtypes = [vp, vp, vp, i32, pi]
     L.b2_gicp_last_gpu_ms.argtypes = [vp, pf, pi]
+    L.b2_gicp_get_evaluation_ms.argtypes = [vp, vp, i32, pi]
     L.b2_gicp_index_info.argtypes = [vp, pd, pd, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.b2_ndt_create.argtypes = [C.POINTER(vp)]
     L.b2_ndt_destroy.argtypes = [vp]

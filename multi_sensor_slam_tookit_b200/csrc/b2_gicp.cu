@@ -24,6 +24,7 @@
 #include "b2_comm.cuh"
 #include <cmath>
 #include <algorithm>
+#include <vector>
 
 namespace b2 {
 
@@ -265,6 +266,8 @@ struct b2_gicp_s {
     int grid_blocks = 1;
     float last_ms = 0.f; int last_launches = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<cudaEvent_t> ev;     // one per evaluation boundary of the last align (per-evaluation device times)
+    int ev_used = 0;
 };
 
 static int gicp_valid_count(const GridD& g, cudaStream_t s, uint32_t* out) {
@@ -363,6 +366,7 @@ int b2_gicp_destroy(b2_gicp_t h) {
     h->tgt_m.release(); h->src_m.release(); h->partials.release(); h->state.release(); h->corr.release(); h->pin.release();
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
+    for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return B2_OK;
@@ -473,10 +477,14 @@ int b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* 
     int launched = 0, launches = 0;
     B2_CUDA(cudaEventRecord(h->e0, h->stream));
     const int total = max_it + 1;
+    while ((int)h->ev.size() < std::min(total, GICP_HIST) + 1) { cudaEvent_t e; B2_CUDA(cudaEventCreate(&e)); h->ev.push_back(e); }
+    h->ev_used = 0;
+    B2_CUDA(cudaEventRecord(h->ev[0], h->stream));
     while (launched < total) {
         const int m = std::min(chunk, total - launched);
         for (int i = 0; i < m; i++) {
             k_gicp_linearize<<<h->grid_blocks, GICP_THREADS, 0, h->stream>>>(a); launches++;
+            if (h->ev_used + 1 < (int)h->ev.size()) { h->ev_used++; B2_CUDA(cudaEventRecord(h->ev[h->ev_used], h->stream)); }
             if (h->comm) {
                 B2_CHECK(comm_allreduce_sum_f64(h->comm, ds->sums_local, ds->sums, GICP_NSUM, h->stream));
                 k_gicp_finalize<<<1, 32, 0, h->stream>>>(ds); launches++;
@@ -509,6 +517,15 @@ int b2_gicp_get_history(b2_gicp_t h, double* fitness, double* inlier_rmse, int c
     const int n = std::min(std::min(hs->evals, GICP_HIST), capacity);
     for (int i = 0; i < n; i++) { if (fitness) fitness[i] = hs->hist_fit[i]; if (inlier_rmse) inlier_rmse[i] = hs->hist_rmse[i]; }
     if (n_evaluations) *n_evaluations = hs->evals;
+    return B2_OK;
+}
+
+int b2_gicp_get_evaluation_ms(b2_gicp_t h, float* ms, int capacity, int* n_evaluations) {
+    if (!h || capacity < 0) return B2_ERR_ARG;
+    const GicpState* hs = h->pin.as<GicpState>();
+    const int n = hs ? std::min(std::min(hs->evals, h->ev_used), capacity) : 0;
+    for (int i = 0; i < n; i++) { ms[i] = 0.f; cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]); }
+    if (n_evaluations) *n_evaluations = n;
     return B2_OK;
 }
 

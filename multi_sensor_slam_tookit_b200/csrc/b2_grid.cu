@@ -3,6 +3,8 @@
 //
 // HBM layout after build():  pts   float4[n]      cell-sorted (x, y, z, original index as int bits)
 //                            cell_start u32[ncell+2]  exclusive prefix of per-cell counts (x fastest)
+// Build = bbox -> (cell, rank-in-cell) per point with one counting atomic -> prefix sum -> scatter: a counting sort, eight
+// launches and one 24-byte readback for a 100 k-point map.
 // Cell edge h = max_dist * (1 + 2^-7): any point closer than max_dist to a query lies in the 3x3x3 block
 // around the query's cell even after float rounding of (p - origin) * (1/h).
 #include "b2_grid.cuh"
@@ -53,23 +55,26 @@ __device__ __forceinline__ uint32_t cell_of_point(const GridGeom& g, float x, fl
     return (uint32_t)(((size_t)cz * g.ny + cy) * g.nx + cx);
 }
 
+// cell of every point, and its rank inside the cell (the value the counting atomic returns): after the prefix sum of the
+// counts the point's slot is cell_start[cell] + rank. The order of points inside a cell is whatever the atomics gave; every
+// consumer orders candidates by (distance, original index), so results do not depend on it.
 __global__ void __launch_bounds__(256) k_cell_key(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, GridGeom g,
-                                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ count) {
+                                                  uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank_in_cell, uint32_t* __restrict__ count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
     uint32_t c = cell_of_point(g, p[0], p[1], p[2]);
-    keys[i] = c; vals[i] = i;
-    atomicAdd(&count[c], 1u);
+    cell_of[i] = c;
+    rank_in_cell[i] = atomicAdd(&count[c], 1u);
 }
 
-__global__ void __launch_bounds__(256) k_cell_gather(const unsigned char* __restrict__ raw, size_t stride, uint32_t n,
-                                                     const uint32_t* __restrict__ order, float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_cell_scatter(const unsigned char* __restrict__ raw, size_t stride, uint32_t n,
+                                                      const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ rank_in_cell,
+                                                      const uint32_t* __restrict__ cell_start, float4* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t src = order[i];
-    const float* p = reinterpret_cast<const float*>(raw + (size_t)src * stride);
-    out[i] = make_float4(p[0], p[1], p[2], __int_as_float((int)src));
+    const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    out[cell_start[cell_of[i]] + rank_in_cell[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
 }
 
 int GridIndex::build(const void* host_pts, size_t stride, size_t n_, float max_dist, cudaStream_t s) {
@@ -114,23 +119,19 @@ int GridIndex::build(const void* host_pts, size_t stride, size_t n_, float max_d
     const size_t ncount = (size_t)g.ncell + 2;
     B2_CHECK(cell_start.reserve(ncount * sizeof(uint32_t)));
     B2_CUDA(cudaMemsetAsync(cell_start.p, 0, ncount * sizeof(uint32_t), s));
-    // keys/vals ping-pong + sort scratch
+    // cell + rank per point, prefix sum of the counts, one scatter (a counting sort: no radix passes)
     const size_t nal = (n + 63) & ~(size_t)63;
-    const size_t need = 4 * nal * sizeof(uint32_t) + sort_tmp_bytes(n) + scan_tmp_bytes(ncount) + 1024;
+    const size_t need = 2 * nal * sizeof(uint32_t) + scan_tmp_bytes(ncount) + 1024;
     B2_CHECK(cell_of.reserve(need));
-    uint32_t* ka = cell_of.as<uint32_t>();
-    uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
-    char* scratch = reinterpret_cast<char*>(vb + nal);
+    uint32_t* d_cell = cell_of.as<uint32_t>();
+    uint32_t* d_rank = d_cell + nal;
+    char* scratch = reinterpret_cast<char*>(d_rank + nal);
     const unsigned nblk = (unsigned)((n + 255) / 256);
-    k_cell_key<<<nblk, 256, 0, s>>>(raw.as<unsigned char>(), stride, (uint32_t)n, g, ka, va, cell_start.as<uint32_t>()); count_launch();
+    k_cell_key<<<nblk, 256, 0, s>>>(raw.as<unsigned char>(), stride, (uint32_t)n, g, d_cell, d_rank, cell_start.as<uint32_t>()); count_launch();
     B2_CUDA(cudaGetLastError());
     B2_CHECK(exclusive_scan_u32(cell_start.as<uint32_t>(), ncount, scratch, s));
-    int bits = 1;
-    while (((size_t)1 << bits) <= (size_t)g.ncell) bits++;
-    uint32_t *ks, *vs;
-    B2_CHECK(radix_sort_pairs(ka, va, kb, vb, n, bits, scratch, s, &ks, &vs));
     B2_CHECK(pts.reserve(n * sizeof(float4)));
-    k_cell_gather<<<nblk, 256, 0, s>>>(raw.as<unsigned char>(), stride, (uint32_t)n, vs, pts.as<float4>()); count_launch();
+    k_cell_scatter<<<nblk, 256, 0, s>>>(raw.as<unsigned char>(), stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>()); count_launch();
     B2_CUDA(cudaGetLastError());
     dev.pts = pts.as<float4>(); dev.cell_start = cell_start.as<uint32_t>();
     dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h;

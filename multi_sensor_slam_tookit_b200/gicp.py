@@ -139,6 +139,7 @@ class RegistrationResult:
         self.gpu_launches = 0
         self.fitness_history = np.empty(0)
         self.rmse_history = np.empty(0)
+        self.evaluation_ms = np.empty(0, np.float32)
 
     def __repr__(self):
         return (f"RegistrationResult with fitness={self.fitness:e}, inlier_rmse={self.inlier_rmse:e}, "
@@ -254,6 +255,9 @@ class GeneralizedICP:
         hf, hr, ne = np.zeros(256), np.zeros(256), C.c_int()
         capi.check(L.b2_gicp_get_history(self._h, capi.ptr(hf), capi.ptr(hr), 256, C.byref(ne)))
         r.fitness_history, r.rmse_history = hf[:min(ne.value, 256)].copy(), hr[:min(ne.value, 256)].copy()
+        ems, ne2 = np.zeros(256, np.float32), C.c_int()
+        capi.check(L.b2_gicp_get_evaluation_ms(self._h, capi.ptr(ems), 256, C.byref(ne2)))
+        r.evaluation_ms = ems[:ne2.value].copy()
         if want_correspondences and self._comm is None:
             _, corr = self.linearize(T, want_correspondences=True)
             src = np.nonzero(corr >= 0)[0].astype(np.int32)
