@@ -71,4 +71,43 @@ private:
     b2_s2m_t h_ = nullptr;
 };
 
+// replaces pcl::NormalDistributionsTransform<PointSource, PointTarget> (multi_lidar_calibrator.cpp:35-72)
+template <typename PointSource, typename PointTarget>
+class NormalDistributionsTransform {
+public:
+    NormalDistributionsTransform() { check(b2_ndt_create(&h_), "b2_ndt_create"); }
+    ~NormalDistributionsTransform() { b2_ndt_destroy(h_); }
+    NormalDistributionsTransform(const NormalDistributionsTransform&) = delete;
+    void setTransformationEpsilon(double e) { check(b2_ndt_set_transformation_epsilon(h_, e), "setTransformationEpsilon"); }
+    void setStepSize(double s) { check(b2_ndt_set_step_size(h_, s), "setStepSize"); }
+    void setResolution(float r) { check(b2_ndt_set_resolution(h_, r), "setResolution"); }
+    void setMaximumIterations(int n) { check(b2_ndt_set_maximum_iterations(h_, n), "setMaximumIterations"); }
+    void setInputSource(const typename pcl::PointCloud<PointSource>::ConstPtr& c) {
+        src_ = c;
+        check(b2_ndt_set_input_source(h_, c->points.data(), sizeof(PointSource), c->size()), "setInputSource");
+    }
+    void setInputTarget(const typename pcl::PointCloud<PointTarget>::ConstPtr& c) {
+        check(b2_ndt_set_input_target(h_, c->points.data(), sizeof(PointTarget), c->size()), "setInputTarget");
+    }
+    // Eigen::Matrix4f is column-major, the C ABI takes row-major 4x4 floats
+    void align(pcl::PointCloud<PointSource>& output, const Eigen::Matrix4f& guess = Eigen::Matrix4f::Identity()) {
+        const Eigen::Matrix<float, 4, 4, Eigen::RowMajor> g = guess;
+        output.points.resize(src_ ? src_->size() : 0);
+        output.width = static_cast<uint32_t>(output.points.size()); output.height = 1; output.is_dense = true;
+        check(b2_ndt_align(h_, g.data(), output.points.data(), sizeof(PointSource)), "align");
+    }
+    bool hasConverged() const { int c = 0; check(b2_ndt_has_converged(h_, &c), "hasConverged"); return c != 0; }
+    double getFitnessScore() const { double s = 0; check(b2_ndt_get_fitness_score(h_, &s), "getFitnessScore"); return s; }
+    double getTransformationProbability() const { double p = 0; check(b2_ndt_get_transformation_probability(h_, &p), "getTransformationProbability"); return p; }
+    int getFinalNumIteration() const { int n = 0; check(b2_ndt_get_final_num_iteration(h_, &n), "getFinalNumIteration"); return n; }
+    Eigen::Matrix4f getFinalTransformation() const {
+        Eigen::Matrix<float, 4, 4, Eigen::RowMajor> t;
+        check(b2_ndt_get_final_transformation(h_, t.data()), "getFinalTransformation");
+        return t;
+    }
+private:
+    b2_ndt_t h_ = nullptr;
+    typename pcl::PointCloud<PointSource>::ConstPtr src_;
+};
+
 }  // namespace b2shim
