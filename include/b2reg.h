@@ -247,8 +247,9 @@ int  b2_gicp_destroy(b2_gicp_t h);
 int  b2_gicp_set_params(b2_gicp_t h, const b2_gicp_params* params);
 int  b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target);    /* builds the target index; the cloud may be destroyed afterwards */
 int  b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source);
-/* Source sharding for one registration spread over `world` GPUs: this process evaluates the rank-th contiguous slice
- * of the (cell-sorted) source; the 30 sums are all-reduced over `comm` every iteration and every rank solves the same
+/* Source sharding for one registration spread over `world` GPUs: the (cell-sorted) source is dealt to the ranks in
+ * blocks of 4096 consecutive points, round-robin (block b belongs to rank b mod world), so every rank sees the same
+ * mix of easy and hard regions; the 30 sums are all-reduced over `comm` every iteration and every rank solves the same
  * 6x6 system, so all ranks return the same T. world = 1 (the default) needs no communicator. With world > 1 and
  * comm = NULL only b2_gicp_linearize works and returns this shard's local sums. */
 int  b2_gicp_set_shard(b2_gicp_t h, int rank, int world, b2_comm_t comm);
@@ -262,7 +263,7 @@ int  b2_gicp_last_gpu_ms(b2_gicp_t h, float* ms, int* launches);
 /* device time of every evaluation of the last align (the all-reduce and the update of a sharded run included) */
 int  b2_gicp_get_evaluation_ms(b2_gicp_t h, float* ms, int capacity, int* n_evaluations);
 int  b2_gicp_index_info(b2_gicp_t h, double* target_cell_edge, double* target_points_per_cell,
-                        uint32_t* shard_begin, uint32_t* shard_end);
+                        uint32_t* shard_points, uint32_t* shard_block_points);
 
 /* ------------------------------------------------------------------------------------------------
  * NDT — replaces pcl::NormalDistributionsTransform<pcl::PointXYZ, pcl::PointXYZ> as used by

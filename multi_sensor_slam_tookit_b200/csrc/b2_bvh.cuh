@@ -120,6 +120,55 @@ __device__ __forceinline__ void bvh_knn_warp(const BvhDev& T, WarpList& L, int K
 }
 
 
+// warp-wide exact nearest neighbour (squared distance only): the same walk with a scalar bound, one lane per leaf point
+__device__ __forceinline__ double bvh_nn1_warp(const BvhDev& T, double qx, double qy, double qz) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    double best = INFINITY;
+    auto scan_leaf = [&](uint32_t leaf) {
+        const uint32_t p = leaf * 32u + lane;
+        double d = INFINITY;
+        if (p < T.n) {
+            double x, y, z; long long id;
+            load_p4d(&T.pts[p], x, y, z, id);
+            const double dx = qx - x, dy = qy - y, dz = qz - z;
+            d = dx * dx + dy * dy + dz * dz;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) d = fmin(d, shfl_xor_d(full, d, o));
+        best = fmin(best, d);
+    };
+    const int top = T.levels - 1;
+    if (top == 0) { scan_leaf(0); return best; }
+    double dch[BVH_MAXL];
+    uint32_t node[BVH_MAXL];
+    int lv = top;
+    node[lv] = 0;
+    auto expand = [&](int l, uint32_t nd) {
+        const uint32_t c = nd * 32u + lane;
+        dch[l] = (c < T.count[l - 1]) ? box_dist2(T.box[l - 1] + 6 * (size_t)c, qx, qy, qz) : INFINITY;
+    };
+    expand(lv, 0);
+    for (;;) {
+        double dmin = dch[lv]; int jmin = lane;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = shfl_xor_d(full, dmin, o);
+            const int oj = __shfl_xor_sync(full, jmin, o);
+            if (od < dmin || (od == dmin && oj < jmin)) { dmin = od; jmin = oj; }
+        }
+        if (dmin == INFINITY || dmin >= best) {          // distance only: a tie cannot improve the result
+            if (++lv > top) break;
+            continue;
+        }
+        if (lane == jmin) dch[lv] = INFINITY;
+        const uint32_t child = node[lv] * 32u + (uint32_t)jmin;
+        if (lv == 1) scan_leaf(child);
+        else { lv--; node[lv] = child; expand(lv, child); }
+    }
+    return best;
+}
+
 #endif  // __CUDACC__
 
 }  // namespace b2

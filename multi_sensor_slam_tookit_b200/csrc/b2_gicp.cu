@@ -32,6 +32,7 @@ constexpr int GICP_THREADS = 256;
 constexpr int GICP_WARPS = GICP_THREADS / 32;
 constexpr int GICP_NSUM = 30;                // 21 JtJ upper + 6 Jtr + n_corr + sum d^2 + sum r^2
 constexpr int GICP_HIST = 256;
+constexpr uint32_t GICP_SHARD_CHUNKS = 128;  // 4096 consecutive (cell-sorted) source points per dealt block
 
 struct GicpState {
     double T[16];
@@ -52,7 +53,8 @@ struct GicpArgs {
     const double* tgt_m;             // effective normals of the target, fine-grid order
     const P4d* src;                  // source points, cell-sorted order, idx = original index
     const double* src_m;             // effective normals of the source, same order
-    uint32_t begin, end;             // this GPU's shard of the sorted source
+    uint32_t n_src, n_local_chunks;  // valid source points; 32-point chunks this GPU owns
+    int rank, world;                 // block-cyclic shard: blocks of GICP_SHARD_CHUNKS chunks dealt round-robin to the ranks
     double radius2, a;               // max_correspondence_distance^2, 1 - epsilon
     double* partials;                // [gridDim.x][GICP_NSUM]
     int32_t* corr;                   // optional: corr[source original index] = target original index or -1
@@ -134,11 +136,12 @@ __global__ void __launch_bounds__(GICP_THREADS, 3) k_gicp_linearize(GicpArgs A) 
         t[i] = st->T[i * 4 + 3];
     }
     double tot = 0.0;                // lane i: running total of term i
-    const uint32_t n_here = A.end - A.begin;
-    const uint32_t n_chunks = (n_here + 31) >> 5;
-    for (uint32_t chunk = blockIdx.x * GICP_WARPS + warp; chunk < n_chunks; chunk += gridDim.x * GICP_WARPS) {
-        const uint32_t p = A.begin + (chunk << 5) + lane;
-        const bool valid = p < A.end;
+    for (uint32_t lc = blockIdx.x * GICP_WARPS + warp; lc < A.n_local_chunks; lc += gridDim.x * GICP_WARPS) {
+        // local chunk -> global chunk of the block-cyclic deal (spatially mixed shards: every rank gets its share of the
+        // points that need the coarse pass; contiguous slices left the slowest rank 40 % behind at 8 GPUs)
+        const uint32_t chunk = ((lc / GICP_SHARD_CHUNKS) * (uint32_t)A.world + (uint32_t)A.rank) * GICP_SHARD_CHUNKS + lc % GICP_SHARD_CHUNKS;
+        const uint32_t p = (chunk << 5) + lane;
+        const bool valid = p < A.n_src;
         double px = 0, py = 0, pz = 0; long long sidx = -1;
         if (valid) load_p4d(&A.src[p], px, py, pz, sidx);
         const double vx = R[0] * px + R[1] * py + R[2] * pz + t[0];
@@ -279,6 +282,19 @@ static int gicp_valid_count(const GridD& g, cudaStream_t s, uint32_t* out) {
     return B2_OK;
 }
 
+// number of 32-point chunks the block-cyclic deal gives `rank` (chunks of full blocks + its part of the last round)
+static uint32_t gicp_local_chunks(uint32_t n_valid, int rank, int world) {
+    const uint32_t total = (n_valid + 31) / 32;
+    const uint32_t S = GICP_SHARD_CHUNKS;
+    const uint32_t round_chunks = S * (uint32_t)world;
+    const uint32_t full_rounds = total / round_chunks;
+    const uint32_t rem = total % round_chunks;
+    uint32_t mine = full_rounds * S;
+    const uint32_t lo = (uint32_t)rank * S;
+    if (rem > lo) mine += std::min(S, rem - lo);
+    return mine;
+}
+
 static void gicp_fill_args(b2_gicp_s* h, GicpArgs& a, int mode, int32_t* corr) {
     a.tgt = h->tgt_grid.dev;
     a.tgtc = h->have_coarse ? h->tgt_coarse.dev : h->tgt_grid.dev;
@@ -287,16 +303,16 @@ static void gicp_fill_args(b2_gicp_s* h, GicpArgs& a, int mode, int32_t* corr) {
     a.tgt_m = h->tgt_m.as<double>();
     a.src = h->src_grid.dev.pts;
     a.src_m = h->src_m.as<double>();
-    const uint64_t nv = h->src_valid;
-    a.begin = (uint32_t)(nv * (uint64_t)h->rank / (uint64_t)h->world);
-    a.end = (uint32_t)(nv * (uint64_t)(h->rank + 1) / (uint64_t)h->world);
+    a.n_src = h->src_valid;
+    a.rank = h->rank; a.world = h->world;
+    a.n_local_chunks = gicp_local_chunks(h->src_valid, h->rank, h->world);
     a.radius2 = h->prm.max_correspondence_distance * h->prm.max_correspondence_distance;
     a.a = 1.0 - h->prm.epsilon;
     a.partials = h->partials.as<double>();
     a.corr = corr;
     a.st = h->state.as<GicpState>();
     a.mode = mode;
-    const uint32_t chunks = (a.end - a.begin + 31) / 32;
+    const uint32_t chunks = a.n_local_chunks;
     h->grid_blocks = (int)std::max<uint32_t>(1u, std::min<uint32_t>((chunks + GICP_WARPS - 1) / GICP_WARPS, (uint32_t)(device_sm_count() * h->blocks_per_sm)));
 }
 
@@ -472,7 +488,7 @@ int b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* 
     GicpState* ds = h->state.as<GicpState>();
     GicpState* hs = h->pin.as<GicpState>();
     // evaluations are enqueued in chunks; between chunks the host reads the small state back (one sync per chunk)
-    const size_t per = std::max<size_t>(1, (size_t)(a.end - a.begin));
+    const size_t per = std::max<size_t>(1, (size_t)a.n_local_chunks * 32);
     const int chunk = (int)std::min<size_t>(8, std::max<size_t>(1, 2000000 / per));
     int launched = 0, launches = 0;
     B2_CUDA(cudaEventRecord(h->e0, h->stream));
@@ -536,13 +552,19 @@ int b2_gicp_last_gpu_ms(b2_gicp_t h, float* ms, int* launches) {
     return B2_OK;
 }
 
-int b2_gicp_index_info(b2_gicp_t h, double* target_cell_edge, double* target_points_per_cell, uint32_t* shard_begin, uint32_t* shard_end) {
+int b2_gicp_index_info(b2_gicp_t h, double* target_cell_edge, double* target_points_per_cell, uint32_t* shard_points, uint32_t* shard_block_points) {
     if (!h || !h->have_tgt) return B2_ERR_STATE;
     if (target_cell_edge) *target_cell_edge = h->tgt_grid.dev.h;
     if (target_points_per_cell) *target_points_per_cell = h->tgt_grid.ppc;
-    const uint64_t nv = h->src_valid;
-    if (shard_begin) *shard_begin = (uint32_t)(nv * (uint64_t)h->rank / (uint64_t)h->world);
-    if (shard_end) *shard_end = (uint32_t)(nv * (uint64_t)(h->rank + 1) / (uint64_t)h->world);
+    if (shard_points) {
+        // points this rank evaluates (the last chunk of the cloud may be partial)
+        const uint32_t total = (h->src_valid + 31) / 32;
+        uint32_t pts = gicp_local_chunks(h->src_valid, h->rank, h->world) * 32u;
+        const uint32_t last_block_owner = total ? ((total - 1) / GICP_SHARD_CHUNKS) % (uint32_t)h->world : 0u;
+        if (total && (int)last_block_owner == h->rank) pts -= total * 32u - h->src_valid;
+        *shard_points = pts;
+    }
+    if (shard_block_points) *shard_block_points = GICP_SHARD_CHUNKS * 32u;
     return B2_OK;
 }
 

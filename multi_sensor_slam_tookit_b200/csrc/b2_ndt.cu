@@ -389,9 +389,9 @@ __global__ void __launch_bounds__(128) k_ndt_fitness(BvhDev T, const float* __re
     double sum = 0.0, cnt = 0.0;
     for (int j = 0; j < nq; j++) {
         const double qx = (double)__shfl_sync(full, tx, j), qy = (double)__shfl_sync(full, ty, j), qz = (double)__shfl_sync(full, tz, j);
-        WarpList L; L.sd = INFINITY; L.si = 0x7fffffff; L.sp = 0; L.kd = INFINITY; L.ki = 0x7fffffff;
-        if (isfinite(qx) && isfinite(qy) && isfinite(qz)) bvh_knn_warp(T, L, 1, qx, qy, qz);
-        if (L.kd < INFINITY) { sum += L.kd; cnt += 1.0; }
+        double d2 = INFINITY;
+        if (isfinite(qx) && isfinite(qy) && isfinite(qz)) d2 = bvh_nn1_warp(T, qx, qy, qz);
+        if (d2 < INFINITY) { sum += d2; cnt += 1.0; }
     }
     if (lane == 0) { atomicAdd(&out[0], sum); atomicAdd(&out[1], cnt); }
 }

@@ -178,9 +178,17 @@ class Communicator:
             pass
 
 
-def shard_range(n, rank, world):
-    """Contiguous slice [begin, end) of n source points owned by `rank` (the split libb2reg uses)."""
-    return (n * rank) // world, (n * (rank + 1)) // world
+SHARD_BLOCK_POINTS = 4096
+
+
+def shard_blocks(n, rank, world, block=SHARD_BLOCK_POINTS):
+    """[begin, end) ranges of the n (cell-sorted) source points `rank` evaluates: blocks of `block` consecutive points dealt
+    round-robin, block b to rank b % world (the deal libb2reg uses for the sharded registration)."""
+    return [(b * block, min((b + 1) * block, n)) for b in range((n + block - 1) // block) if b % world == rank]
+
+
+def shard_size(n, rank, world, block=SHARD_BLOCK_POINTS):
+    return sum(e - b for b, e in shard_blocks(n, rank, world, block))
 
 
 def pair_owner(pair_index, world):
@@ -267,7 +275,7 @@ class GeneralizedICP:
     def indexInfo(self):
         h, ppc, b, e = C.c_double(), C.c_double(), C.c_uint32(), C.c_uint32()
         capi.check(capi.lib().b2_gicp_index_info(self._h, C.byref(h), C.byref(ppc), C.byref(b), C.byref(e)))
-        return {"target_cell_edge": h.value, "target_points_per_cell": ppc.value, "shard": (b.value, e.value)}
+        return {"target_cell_edge": h.value, "target_points_per_cell": ppc.value, "shard_points": b.value, "shard_block_points": e.value}
 
 
 def registration_generalized_icp(source, target, max_correspondence_distance, init=None,

@@ -115,7 +115,7 @@ def test_linearize_matches_oracle(pair, gicp):
         assert np.array_equal(corr, ref_corr)                          # correspondence set bit-exact
         check_sums(sums, ref)
     info = g.indexInfo()
-    assert info["target_cell_edge"] > 0 and info["shard"] == (0, len(pair["sp"]))
+    assert info["target_cell_edge"] > 0 and info["shard_points"] == len(pair["sp"])
 
 
 def test_linearize_far_apart_and_small_radius(pair, gicp):
@@ -169,26 +169,29 @@ def test_align_iteration_cap_and_zero_iterations(pair, gicp):
 
 
 def test_sharded_sums_add_up(pair, gicp):
-    """The source shards of SURVEY.md §8e (C5): per-rank sums add up to the single-GPU sums (no communicator needed
-    for single evaluations), and the shards tile the source."""
+    """The source shards of SURVEY.md §8e (C5): blocks of 4096 cell-sorted points dealt round-robin. Per-rank sums add up to
+    the single-GPU sums (no communicator needed for single evaluations), the shards are disjoint and cover the source."""
     g = gicp.GeneralizedICP(1.0, pair["eps"])
     g.setInputTarget(pair["tgt"]); g.setInputSource(pair["src"])
     T = G.perturbed(pair["truth"])
     full, full_corr = g.linearize(T, want_correspondences=True)
+    n = len(pair["sp"])
     from multi_sensor_slam_tookit_b200 import capi
     for world in (2, 3, 8):
-        total = np.zeros(30); seen = np.zeros(len(pair["sp"]), bool); edges = []
+        total = np.zeros(30); seen = np.zeros(n, bool); sizes = []
         for rank in range(world):
             capi.check(capi.lib().b2_gicp_set_shard(g._h, rank, world, None))
             s, c = g.linearize(T, want_correspondences=True)
             total += s
-            edges.append(g.indexInfo()["shard"])
+            info = g.indexInfo()
+            sizes.append(info["shard_points"])
+            assert info["shard_block_points"] == gicp.SHARD_BLOCK_POINTS
+            assert info["shard_points"] == gicp.shard_size(n, rank, world)
             mine = c >= 0
             assert not np.any(seen & mine)
             assert np.array_equal(c[mine], full_corr[mine])
             seen |= mine
-        assert edges[0][0] == 0 and edges[-1][1] == len(pair["sp"]) and all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
-        assert edges == [gicp.shard_range(len(pair["sp"]), r, world) for r in range(world)]
+        assert sum(sizes) == n
         assert np.array_equal(seen, full_corr >= 0)
         assert total[27] == full[27] and rel_err(total[:27], full[:27]) <= 1e-12
     capi.check(capi.lib().b2_gicp_set_shard(g._h, 0, 1, None))

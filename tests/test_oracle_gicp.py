@@ -118,7 +118,7 @@ def _gloo_rank(rank, world, port, q):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from oracle import pyoracle as O
-    from multi_sensor_slam_tookit_b200.gicp import shard_range, pair_owner
+    from multi_sensor_slam_tookit_b200.gicp import shard_blocks, pair_owner
     import gicp_cases as GC
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -129,13 +129,13 @@ def _gloo_rank(rank, world, port, q):
     _, sc = O.gicp_normals_covs(src, 30, 0.005, threads=2)
     g = O.GicpOracle(src, sc, tgt, tc, threads=2)
     T = GC.perturbed(np.eye(4), (0.02, 0.01, 0.0), (0.1, 0.0, 0.2))
-    b, e = shard_range(len(src), rank, world)
-    local = g.linearize(T, 1.0, begin=b, end=e)
+    blocks = shard_blocks(len(src), rank, world, block=128)
+    local = sum(g.linearize(T, 1.0, begin=b, end=e) for b, e in blocks)
     t = torch.from_numpy(local.copy())
     dist.all_reduce(t, op=dist.ReduceOp.SUM)                 # the one exchange step of the sharded registration
     full = g.linearize(T, 1.0)
     owners = [pair_owner(i, world) for i in range(5)]
-    q.put((rank, (b, e), float(np.abs(t.numpy() - full).max() / np.abs(full).max()), float(t[27]), float(full[27]), owners))
+    q.put((rank, blocks[:2], float(np.abs(t.numpy() - full).max() / np.abs(full).max()), float(t[27]), float(full[27]), owners))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -153,17 +153,20 @@ def test_gloo_world2_sharded_sums():
         p.join(60)
         assert p.exitcode == 0
     (r0, s0, e0, n0, f0, o0), (r1, s1, e1, n1, f1, o1) = res
-    assert s0 == (0, 500) and s1 == (500, 1001)                # contiguous, tiling shards
+    assert s0 == [(0, 128), (256, 384)] and s1 == [(128, 256), (384, 512)]      # blocks dealt round-robin
     assert e0 <= 1e-12 and e1 <= 1e-12 and n0 == f0 == n1 == f1
     assert o0 == [0, 1, 0, 1, 0]
 
 
 def test_shard_helpers():
-    from multi_sensor_slam_tookit_b200.gicp import shard_range
-    for n in (0, 1, 7, 50_000_000):
+    from multi_sensor_slam_tookit_b200.gicp import shard_blocks, shard_size
+    for n in (0, 1, 7, 4096, 4097, 1_000_003):
         for world in (1, 2, 3, 8):
-            edges = [shard_range(n, r, world) for r in range(world)]
-            assert edges[0][0] == 0 and edges[-1][1] == n
-            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
-            sizes = [e - b for b, e in edges]
-            assert max(sizes) - min(sizes) <= 1
+            cover = np.zeros(n, np.int32)
+            for r in range(world):
+                for b, e in shard_blocks(n, r, world):
+                    cover[b:e] += 1
+                assert shard_size(n, r, world) == sum(e - b for b, e in shard_blocks(n, r, world))
+            assert np.all(cover == 1)
+            sizes = [shard_size(n, r, world) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 4096

@@ -190,7 +190,7 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
     return dict(points=int(n_points), iterations=int(res.iterations), evaluations=int(res.iterations + 1), gpu_ms=float(res.gpu_ms),
                 launches=int(res.gpu_launches), fitness=float(res.fitness), inlier_rmse=float(res.inlier_rmse),
                 t_err=float(np.linalg.norm(dT[:3, 3])), r_err=float(np.arccos(np.clip((np.trace(dT[:3, :3]) - 1) / 2, -1, 1))),
-                evaluation_ms=[round(float(v), 3) for v in res.evaluation_ms], shard=[int(v) for v in info["shard"]], cell_edge=float(info["target_cell_edge"]), ppc=float(info["target_points_per_cell"]),
+                evaluation_ms=[round(float(v), 3) for v in res.evaluation_ms], shard_points=int(info["shard_points"]), cell_edge=float(info["target_cell_edge"]), ppc=float(info["target_points_per_cell"]),
                 setup_s=dict(generate=t_gen, upload=t_up, normals_ms=n_ms, index=t_index))
 
 
