@@ -25,6 +25,7 @@
 #include <cmath>
 #include <algorithm>
 #include <vector>
+#include <cstdlib>
 
 namespace b2 {
 
@@ -121,7 +122,10 @@ __global__ void k_gicp_finalize(GicpState* st) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && !st->done) gicp_finalize(st);
 }
 
-__global__ void __launch_bounds__(GICP_THREADS, 3) k_gicp_linearize(GicpArgs A) {
+#ifndef GICP_MIN_BLOCKS
+#define GICP_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_linearize(GicpArgs A) {
     GicpState* st = A.st;
     if (st->done) return;
     __shared__ double s_red[GICP_WARPS][32];
@@ -259,7 +263,7 @@ struct b2_gicp_s {
     DevBuf tgt_m, src_m, partials, state, corr, tgt_xyz, fine_pos_of;
     double coarse_for = -1.0;        // max_correspondence_distance the coarse grid was built for (< 0: none)
     bool have_coarse = false;
-    int blocks_per_sm = 3;
+    int blocks_per_sm = GICP_MIN_BLOCKS;
     PinBuf pin;
     size_t n_tgt = 0, n_src = 0;
     uint32_t src_valid = 0;
@@ -416,7 +420,8 @@ int b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target) {
     if (!h || !target) return B2_ERR_ARG;
     h->have_tgt = false;
     uint32_t nv = 0;
-    B2_CHECK(gicp_set_cloud(h, target, h->tgt_grid, h->tgt_m, 2.0, &nv));
+    static const double tppc = [] { const char* e = getenv("B2_GICP_TARGET_PPC"); double v = e ? atof(e) : 2.0; return v > 0 ? v : 2.0; }();
+    B2_CHECK(gicp_set_cloud(h, target, h->tgt_grid, h->tgt_m, tppc, &nv));
     h->n_tgt = target->n;
     h->coarse_for = -1.0; h->have_coarse = false;
     // the handle keeps its own copy of the points (the caller may destroy the cloud; the coarse grid is built lazily
@@ -438,7 +443,8 @@ int b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source) {
     if (!h || !source) return B2_ERR_ARG;
     h->have_src = false;
     uint32_t nv = 0;
-    B2_CHECK(gicp_set_cloud(h, source, h->src_grid, h->src_m, 2.0, &nv));
+    static const double sppc = [] { const char* e = getenv("B2_GICP_TARGET_PPC"); double v = e ? atof(e) : 2.0; return v > 0 ? v : 2.0; }();
+    B2_CHECK(gicp_set_cloud(h, source, h->src_grid, h->src_m, sppc, &nv));
     h->n_src = source->n;
     h->src_valid = nv;
     h->have_src = true;
