@@ -54,6 +54,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return int(t[kernel]["dram_bytes_per_launch_last"])
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------ candidates per feature
 def pose_matrix(pose):
     r, p, y = [float(v) for v in pose[:3]]
@@ -328,7 +337,7 @@ def run_b200(args, rank, local_rank, world):
                     "step": "b2_s2m_set_map + b2_s2m_set_scan + b2_s2m_solve with pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_s2m_iteration", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic("k_s2m_iteration"), "peak_source": peak_src,
                          "bytes_per_launch": abytes, "compulsory_bytes_per_launch": compulsory,
                          "candidates_per_feature": cand, "launch_ms": launch_ms,
                          "note": "span of a solve capped at the iterations it needs / launches; working set (1.7 MB) is L2-resident "
@@ -398,7 +407,7 @@ def run_registration(args, rank, local_rank, world, dist, torch):
             "iterations": r["iterations"], "evaluations": r["evaluations"], "align_gpu_ms": r["align_gpu_ms"], "gpu_launches": r["launches"],
             "t_err_m": r["t_err"], "r_err_rad": r["r_err"],
             "roofline": {"kernel": "k_ndt_derivatives", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": bytes_pass,
+                         "traffic": measured_traffic("k_ndt_derivatives"), "peak_source": peak_src, "bytes_per_launch": bytes_pass,
                          "note": "12 B point + 96 B (mean + inverse covariance) per (point, voxel) pair; 0.3 MB of voxel data, L2-resident; "
                                  "span of align / derivative passes, includes the host line search between passes"},
             "cpu_baseline": {"value": cpu["mpts_per_s"], "unit": "Mpts/s", "cores": 1, "kind": "port",
@@ -437,10 +446,15 @@ def run_registration(args, rank, local_rank, world, dist, torch):
                         f"{c5['iterations']} fixed iterations, max_corr 1.0", "value": c5["points"] * c5["evaluations"] / (ms * 1e-3) / 1e6,
             "unit": "Mpts/s", "n_gpus": world, "scaling": "strong", "ms_per_align": ms, "ms_per_evaluation": ms / c5["evaluations"],
             "parallelism": f"target replicated, source sharded x{world}, ncclAllReduce(30 doubles) per iteration" if world > 1 else "single GPU",
+            "evaluation_ms": c5["evaluation_ms"],
+            "e2e": {"value": c5["points"] * c5["evaluations"] / c5["e2e_s"] / 1e6, "unit": "Mpts/s", "s": c5["e2e_s"],
+                    "step": "host clouds in: upload, estimate_normals (30-NN) on both, index builds, align, transformation out (this rank)",
+                    "h2d_bytes": int(2 * 24 * c5["points"]), "d2h_bytes": 128 + 16},
             "gpu_launches": c5["launches"], "fitness": c5["fitness"], "inlier_rmse": c5["inlier_rmse"], "t_err_m": c5["t_err"],
             "r_err_rad": c5["r_err"], "target_cell_edge_m": c5["cell_edge"], "setup_s": c5["setup_s"],
             "roofline": {"kernel": "k_gicp_linearize", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": 144.0 * c5["points"] / world,
+                         "traffic": measured_traffic("k_gicp_linearize") if (world == 1 and c5["points"] == 50_000_000) else None,
+                         "peak_source": peak_src, "bytes_per_launch": 144.0 * c5["points"] / world,
                          "note": "144 B per source point per linearisation (SURVEY.md 8d), per GPU, over the whole align (the first "
                                  "evaluation at the 0.3 m / 0.8 deg offset searches the coarse grid for about a fifth of the points)"}}
         if args.c5_cpu_points > 0:

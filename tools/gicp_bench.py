@@ -167,7 +167,7 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
     t0 = time.perf_counter()
     src, tgt, T_true = c5_clouds_torch(n_points, device)
     t_gen = time.perf_counter() - t0
-    t0 = time.perf_counter()
+    t0 = t_e2e = time.perf_counter()
     sp, tp = gicp.PointCloud(src), gicp.PointCloud(tgt)
     del src, tgt
     t_up = time.perf_counter() - t0
@@ -181,8 +181,11 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
         g.setShard(comm)
     info = g.indexInfo()
     best = None
+    e2e_s = None
     for _ in range(repeats + 1):
         res = g.align(np.eye(4), want_correspondences=False)
+        if e2e_s is None:
+            e2e_s = time.perf_counter() - t_e2e            # upload + normals + index builds + the first align
         if best is None or res.gpu_ms < best.gpu_ms:
             best = res
     res = best
@@ -191,7 +194,7 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
                 launches=int(res.gpu_launches), fitness=float(res.fitness), inlier_rmse=float(res.inlier_rmse),
                 t_err=float(np.linalg.norm(dT[:3, 3])), r_err=float(np.arccos(np.clip((np.trace(dT[:3, :3]) - 1) / 2, -1, 1))),
                 evaluation_ms=[round(float(v), 3) for v in res.evaluation_ms], shard_points=int(info["shard_points"]), cell_edge=float(info["target_cell_edge"]), ppc=float(info["target_points_per_cell"]),
-                setup_s=dict(generate=t_gen, upload=t_up, normals_ms=n_ms, index=t_index))
+                e2e_s=e2e_s, setup_s=dict(generate=t_gen, upload=t_up, normals_ms=n_ms, index=t_index))
 
 
 def main():

@@ -5,7 +5,7 @@ set -u
 TAG=${1:-r1}
 OUT=gpurun_out
 C1="python bench.py --steps 2 --warmup 3 --batch 16 --skip-registration"
-C5="python tools/gicp_bench.py --skip-c4 --c5-points 20000000"
+C5="python tools/gicp_bench.py --skip-c4 --c5-points ${C5_POINTS:-50000000}"
 C4="python tools/gicp_bench.py --skip-c5"
 C3="python tools/ndt_bench.py"
 $C1 > $OUT/${TAG}_plain_c1.log 2>&1 && \
@@ -21,5 +21,5 @@ ncu --set full --clock-control none --import-source on -k regex:k_normals -s 4 -
 $C5 > $OUT/${TAG}_plain_c5.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/${TAG}_launches_c5.csv $C5 > $OUT/${TAG}_ncu_c5_list.log 2>&1
 $C5 > /dev/null 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_gicp_linearize -c 5 -o $OUT/${TAG}_prof_gicp $C5 > $OUT/${TAG}_ncu_gicp.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_gicp_linearize -c 6 -o $OUT/${TAG}_prof_gicp $C5 > $OUT/${TAG}_ncu_gicp.log 2>&1
 ls -la $OUT | grep ${TAG}_
