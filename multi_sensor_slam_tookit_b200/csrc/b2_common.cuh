@@ -95,8 +95,16 @@ struct GridIndex {
     GridDev dev{};
     float h = 1.0078125f;
     size_t n = 0;
-    int build(const void* host_pts, size_t stride, size_t n, float max_dist, cudaStream_t s);
+    // build = begin (upload + bounding box, asynchronous) then finish (one 24-byte read-back, then the counting sort), so
+    // that two indexes can be built side by side on two streams (corner and surf maps of one scan)
+    int begin(const void* host_pts, size_t stride, size_t n, float max_dist, cudaStream_t s);
+    int finish(cudaStream_t s);
+    int build(const void* host_pts, size_t stride, size_t n, float max_dist, cudaStream_t s) {
+        int st = begin(host_pts, stride, n, max_dist, s);
+        return st != B2_OK ? st : finish(s);
+    }
     void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); }
+    size_t stride_ = 0; float max_dist_ = 1.f;
 };
 
 }  // namespace b2

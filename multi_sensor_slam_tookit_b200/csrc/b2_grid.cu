@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(256) k_cell_scatter(const unsigned char* __res
     out[cell_start[cell_of[i]] + rank_in_cell[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
 }
 
-int GridIndex::build(const void* host_pts, size_t stride, size_t n_, float max_dist, cudaStream_t s) {
-    n = n_;
+int GridIndex::begin(const void* host_pts, size_t stride, size_t n_, float max_dist, cudaStream_t s) {
+    n = n_; stride_ = stride; max_dist_ = max_dist;
     dev = GridDev{};
     h = max_dist * 1.0078125f;
     if (n == 0) {
@@ -98,9 +98,17 @@ int GridIndex::build(const void* host_pts, size_t stride, size_t n_, float max_d
     int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 4);
     k_bbox<<<nb, 256, 0, s>>>(raw.as<unsigned char>(), stride, n, bb); count_launch();
     B2_CUDA(cudaGetLastError());
-    uint32_t hbb[6];
-    B2_CUDA(cudaMemcpyAsync(hbb, bb, sizeof(hbb), cudaMemcpyDeviceToHost, s));
+    B2_CHECK(stage.reserve(64));
+    B2_CUDA(cudaMemcpyAsync(stage.p, bb, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    return B2_OK;
+}
+
+int GridIndex::finish(cudaStream_t s) {
+    if (n == 0) return B2_OK;
+    const size_t stride = stride_;
+    const float max_dist = max_dist_;
     B2_CUDA(cudaStreamSynchronize(s));
+    const uint32_t* hbb = stage.as<uint32_t>();
     auto unflip = [](uint32_t u) { uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
     float mn[3], mx[3];
     for (int d = 0; d < 3; d++) { mn[d] = unflip(hbb[d]); mx[d] = unflip(hbb[3 + d]); }

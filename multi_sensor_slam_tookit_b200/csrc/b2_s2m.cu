@@ -493,7 +493,8 @@ using namespace b2;
 
 struct b2_s2m_s {
     b2_s2m_params prm;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    int last_iters = 3;                            // iterations the previous single-scan solve needed (sizes the first chunk)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     GridIndex gc, gs;
     DevBuf raw_c, raw_s, scan_c, scan_s, off_c, off_s, state, partial, hist, ne;
@@ -621,6 +622,7 @@ int b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params) {
     if (params) h->prm = *params; else b2_s2m_default_params(&h->prm);
     if (h->prm.max_batch < 1 || h->prm.max_iterations < 1 || !(h->prm.knn_max_dist > 0.f)) { delete h; set_error("b2_s2m_create: bad params"); return B2_ERR_ARG; }
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e != cudaSuccess) { set_error("b2_s2m_create: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
@@ -638,6 +640,7 @@ int b2_s2m_destroy(b2_s2m_t h) {
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->stream2) cudaStreamDestroy(h->stream2);
     delete h;
     return B2_OK;
 }
@@ -646,9 +649,13 @@ int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corn
     if (!h || (n_corner && !corner) || (n_surf && !surf) || cstride < 12 || sstride < 12 || (cstride & 3) || (sstride & 3)) {
         set_error("b2_s2m_set_map: bad argument"); return B2_ERR_ARG;
     }
-    B2_CHECK(h->gc.build(corner, cstride, n_corner, h->prm.knn_max_dist, h->stream));
-    B2_CHECK(h->gs.build(surf, sstride, n_surf, h->prm.knn_max_dist, h->stream));
+    // the two indexes are built side by side: uploads and bounding boxes first, then both counting sorts
+    B2_CHECK(h->gc.begin(corner, cstride, n_corner, h->prm.knn_max_dist, h->stream));
+    B2_CHECK(h->gs.begin(surf, sstride, n_surf, h->prm.knn_max_dist, h->stream2));
+    B2_CHECK(h->gc.finish(h->stream));
+    B2_CHECK(h->gs.finish(h->stream2));
     B2_CUDA(cudaStreamSynchronize(h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream2));
     h->have_map = true;
     return B2_OK;
 }
@@ -756,29 +763,34 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     S2MArgs a = make_args(h, -1, 1, false, d_hist, max_iterations);
     a.want_matP = want_matP ? 1 : 0;
     a.done_count = d_done;
-    // Iterations are enqueued in chunks; between chunks the host reads one int (scans finished). A finished scan's CTAs
-    // return at once, so an over-long chunk costs only empty launches; the first chunk covers the usual 3-4 iterations.
-    int* h_done = reinterpret_cast<int*>(hs + B) + B;
+    // Iterations are enqueued in chunks; after each chunk the host reads the scans-finished counter together with the
+    // whole (small) result state in one batch of copies and one synchronisation, so a solve that ends inside its first
+    // chunk (the usual 3-4 iterations) costs a single host round trip. A finished scan's CTAs return at once, so an
+    // over-long chunk costs only empty launches; the first chunk is the previous solve's iteration count plus one.
+    int* h_ne = reinterpret_cast<int*>(hs + B);
+    int* h_done = h_ne + B;
     int launched = 0, n_launch = 1;
-    static const int chunk_plan[] = {4, 4, 6, 8, 8};
+    const int first = std::min(max_iterations, std::max(4, h->last_iters + 1));
+    static const int chunk_plan[] = {0, 4, 6, 8, 8};
     for (int c = 0; launched < max_iterations; c++) {
-        const int chunk = std::min(chunk_plan[std::min(c, 4)], max_iterations - launched);
+        const int chunk = std::min(c == 0 ? first : chunk_plan[std::min(c, 4)], max_iterations - launched);
         for (int it = 0; it < chunk; it++) launch_iteration(h, a, B);
         launched += chunk; n_launch += chunk;
         B2_CUDA(cudaGetLastError());
-        if (launched >= max_iterations) break;
+        B2_CUDA(cudaEventRecord(h->ev1, h->stream));
         B2_CUDA(cudaMemcpyAsync(h_done, d_done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaMemcpyAsync(hs, h->state.p, (size_t)B * sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaMemcpyAsync(h_ne, h->ne.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         B2_CUDA(cudaStreamSynchronize(h->stream));
         if (*h_done >= B) break;
     }
-    B2_CUDA(cudaEventRecord(h->ev1, h->stream));
-    int* h_ne = reinterpret_cast<int*>(hs + B);
-    B2_CUDA(cudaMemcpyAsync(hs, h->state.p, (size_t)B * sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
-    B2_CUDA(cudaMemcpyAsync(h_ne, h->ne.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    if (pose_history) B2_CUDA(cudaMemcpyAsync(pose_history, d_hist, (size_t)B * max_iterations * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    B2_CUDA(cudaStreamSynchronize(h->stream));
+    if (pose_history) {
+        B2_CUDA(cudaMemcpyAsync(pose_history, d_hist, (size_t)B * max_iterations * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+    }
     B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->last_launches = n_launch;
+    if (B == 1) h->last_iters = hs[0].iters;
     for (int b = 0; b < B; b++) {
         if (!h_ne[b]) memcpy(poses + (size_t)b * 6, hs[b].pose, 24);
         if (iters_done) iters_done[b] = hs[b].iters;
