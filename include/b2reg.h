@@ -142,6 +142,34 @@ int  b2_s2m_solve_batch(b2_s2m_t h, float* poses, int max_iterations, int* iters
 int  b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches);
 
 /* ------------------------------------------------------------------------------------------------
+ * Local-map assembly — replaces mapOptimization::extractCloud and the containers behind it
+ *   liosam_ws/src/LIO-SAM/src/mapOptmization.cpp
+ *     :1512-1524  cornerCloudKeyFrames.push_back / surfCloudKeyFrames.push_back      -> b2_localmap_add_keyframe
+ *     :899-938    extractCloud(cloudToExtract): transformPointCloud through the laserCloudMapContainer cache, `+=`
+ *                 concatenation in visiting order, downSizeFilterCorner / downSizeFilterSurf, cache cleared above
+ *                 1000 entries                                                         -> b2_localmap_extract
+ *     :1591       laserCloudMapContainer.clear() after correctPoses()                -> b2_localmap_set_pose + b2_localmap_clear_cache
+ *     :1289-1290  kdtree*FromMap->setInputCloud(laserCloud*FromMapDS)                -> b2_s2m_set_map_from_localmap
+ * Key-frame clouds are uploaded once and stay in HBM; the assembled, downsampled map never crosses PCIe. The caller
+ * keeps the key-pose bookkeeping (which key frames are near: extractNearby, :862-897, and the distance test of :905) and
+ * passes the indices in the order the reference visits them — the VoxelGrid centroid sums depend on that order.
+ * pose6 = (roll, pitch, yaw, x, y, z) of cloudKeyPoses6D. */
+typedef struct b2_localmap_s* b2_localmap_t;
+int b2_localmap_create(b2_localmap_t* out, float mapping_corner_leaf_size /* 0.2 params.yaml:64 */, float mapping_surf_leaf_size /* 0.4 :65 */);
+int b2_localmap_destroy(b2_localmap_t h);
+int b2_localmap_add_keyframe(b2_localmap_t h, const void* corner, size_t corner_stride, size_t n_corner,
+                             const void* surf, size_t surf_stride, size_t n_surf, const float pose6[6], int* key_index);
+int b2_localmap_num_keyframes(b2_localmap_t h, int* n);
+int b2_localmap_set_pose(b2_localmap_t h, int key_index, const float pose6[6]);
+int b2_localmap_clear_cache(b2_localmap_t h);
+int b2_localmap_extract(b2_localmap_t h, const int32_t* key_indices, int n_keys, size_t* n_corner_ds, size_t* n_surf_ds);
+/* which: 0 laserCloudCornerFromMap, 1 laserCloudSurfFromMap, 2 laserCloudCornerFromMapDS, 3 laserCloudSurfFromMapDS;
+ * out may be NULL to query the size */
+int b2_localmap_get(b2_localmap_t h, int which, void* out, size_t stride_bytes, size_t capacity, size_t* n);
+int b2_localmap_last_gpu_ms(b2_localmap_t h, float* ms, size_t* n_cached);
+int b2_s2m_set_map_from_localmap(b2_s2m_t s2m, b2_localmap_t h);
+
+/* ------------------------------------------------------------------------------------------------
  * Per-scan front end — replaces, for one incoming scan,
  *   ImageProjection::projectPointCloud + deskewPoint + cloudExtraction   liosam_ws/src/LIO-SAM/src/imageProjection.cpp:446-598
  *   FeatureExtraction::calculateSmoothness + markOccludedPoints + extractFeatures   featureExtraction.cpp:81-238

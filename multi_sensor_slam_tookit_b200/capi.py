@@ -50,6 +50,8 @@ SYMBOLS = [
     "b2_gicp_default_params", "b2_gicp_create", "b2_gicp_destroy", "b2_gicp_set_params", "b2_gicp_set_target",
     "b2_gicp_set_source", "b2_gicp_set_shard", "b2_gicp_linearize", "b2_gicp_align", "b2_gicp_get_history",
     "b2_gicp_last_gpu_ms", "b2_gicp_index_info", "b2_gicp_get_evaluation_ms",
+    "b2_localmap_create", "b2_localmap_destroy", "b2_localmap_add_keyframe", "b2_localmap_num_keyframes", "b2_localmap_set_pose",
+    "b2_localmap_clear_cache", "b2_localmap_extract", "b2_localmap_get", "b2_localmap_last_gpu_ms", "b2_s2m_set_map_from_localmap",
     "b2_ndt_create", "b2_ndt_destroy", "b2_ndt_set_transformation_epsilon", "b2_ndt_set_step_size", "b2_ndt_set_resolution",
     "b2_ndt_set_maximum_iterations", "b2_ndt_set_input_target", "b2_ndt_set_input_source", "b2_ndt_align", "b2_ndt_has_converged",
     "b2_ndt_get_final_transformation", "b2_ndt_get_fitness_score", "b2_ndt_get_transformation_probability",
@@ -132,6 +134,16 @@ def lib():
     L.b2_gicp_last_gpu_ms.argtypes = [vp, pf, pi]
     L.b2_gicp_get_evaluation_ms.argtypes = [vp, vp, i32, pi]
     L.b2_gicp_index_info.argtypes = [vp, pd, pd, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.b2_localmap_create.argtypes = [C.POINTER(vp), f32, f32]
+    L.b2_localmap_destroy.argtypes = [vp]
+    L.b2_localmap_add_keyframe.argtypes = [vp, vp, sz, sz, vp, sz, sz, vp, pi]
+    L.b2_localmap_num_keyframes.argtypes = [vp, pi]
+    L.b2_localmap_set_pose.argtypes = [vp, i32, vp]
+    L.b2_localmap_clear_cache.argtypes = [vp]
+    L.b2_localmap_extract.argtypes = [vp, vp, i32, C.POINTER(sz), C.POINTER(sz)]
+    L.b2_localmap_get.argtypes = [vp, i32, vp, sz, sz, C.POINTER(sz)]
+    L.b2_localmap_last_gpu_ms.argtypes = [vp, pf, C.POINTER(sz)]
+    L.b2_s2m_set_map_from_localmap.argtypes = [vp, vp]
     L.b2_ndt_create.argtypes = [C.POINTER(vp)]
     L.b2_ndt_destroy.argtypes = [vp]
     L.b2_ndt_set_transformation_epsilon.argtypes = [vp, dbl]

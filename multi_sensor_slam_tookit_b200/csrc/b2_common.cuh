@@ -98,6 +98,8 @@ struct GridIndex {
     // build = begin (upload + bounding box, asynchronous) then finish (one 24-byte read-back, then the counting sort), so
     // that two indexes can be built side by side on two streams (corner and surf maps of one scan)
     int begin(const void* host_pts, size_t stride, size_t n, float max_dist, cudaStream_t s);
+    // the same from points already in device memory (local-map assembly); d_pts must stay valid until finish() returns
+    int begin_device(const void* d_pts, size_t stride, size_t n, float max_dist, cudaStream_t s);
     int finish(cudaStream_t s);
     int build(const void* host_pts, size_t stride, size_t n, float max_dist, cudaStream_t s) {
         int st = begin(host_pts, stride, n, max_dist, s);
@@ -105,7 +107,19 @@ struct GridIndex {
     }
     void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); }
     size_t stride_ = 0; float max_dist_ = 1.f;
+    const unsigned char* src_ = nullptr;          // device points the build reads (raw.p after an upload)
 };
+
+// ---- internal couplings between the modules (not part of the C ABI)
+// VoxelGrid on device buffers: result left in the handle's output buffer (voxel_out_dev) on voxel_stream(h)
+int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride, size_t n, int n_fields, size_t out_stride,
+                     size_t out_capacity, uint32_t* m_out, int* refused, int32_t* d_vop);
+const void* voxel_out_dev(b2_voxel_s* h);
+cudaStream_t voxel_stream(b2_voxel_s* h);
+// scan-to-map: index the two map clouds from device memory (packed xyzi, 16-byte stride)
+int s2m_set_map_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf);
+// pcl::getTransformation(x, y, z, roll, pitch, yaw) in float, row-major 3x4 (pose6 = roll, pitch, yaw, x, y, z)
+void pose_to_affine_host(const float pose6[6], float xf[12]);
 
 }  // namespace b2
 

@@ -89,18 +89,26 @@ int GridIndex::begin(const void* host_pts, size_t stride, size_t n_, float max_d
         return B2_OK;
     }
     if (n > 0x7fffffffull) { set_error("grid index: too many points (%zu)", n); return B2_ERR_ARG; }
-    B2_CHECK(raw.reserve(n * stride));
-    B2_CUDA(cudaMemcpyAsync(raw.p, host_pts, n * stride, cudaMemcpyHostToDevice, s));
+    if (host_pts) {
+        B2_CHECK(raw.reserve(n * stride));
+        B2_CUDA(cudaMemcpyAsync(raw.p, host_pts, n * stride, cudaMemcpyHostToDevice, s));
+        src_ = raw.as<unsigned char>();
+    }
     // bbox on device, one small readback to size the cell table
     B2_CHECK(tmp.reserve(64));
     uint32_t* bb = tmp.as<uint32_t>();
     k_bbox_init<<<1, 32, 0, s>>>(bb); count_launch();
     int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 4);
-    k_bbox<<<nb, 256, 0, s>>>(raw.as<unsigned char>(), stride, n, bb); count_launch();
+    k_bbox<<<nb, 256, 0, s>>>(src_, stride, n, bb); count_launch();
     B2_CUDA(cudaGetLastError());
     B2_CHECK(stage.reserve(64));
     B2_CUDA(cudaMemcpyAsync(stage.p, bb, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     return B2_OK;
+}
+
+int GridIndex::begin_device(const void* d_pts, size_t stride, size_t n_, float max_dist, cudaStream_t s) {
+    src_ = static_cast<const unsigned char*>(d_pts);
+    return begin(nullptr, stride, n_, max_dist, s);
 }
 
 int GridIndex::finish(cudaStream_t s) {
@@ -135,11 +143,11 @@ int GridIndex::finish(cudaStream_t s) {
     uint32_t* d_rank = d_cell + nal;
     char* scratch = reinterpret_cast<char*>(d_rank + nal);
     const unsigned nblk = (unsigned)((n + 255) / 256);
-    k_cell_key<<<nblk, 256, 0, s>>>(raw.as<unsigned char>(), stride, (uint32_t)n, g, d_cell, d_rank, cell_start.as<uint32_t>()); count_launch();
+    k_cell_key<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, g, d_cell, d_rank, cell_start.as<uint32_t>()); count_launch();
     B2_CUDA(cudaGetLastError());
     B2_CHECK(exclusive_scan_u32(cell_start.as<uint32_t>(), ncount, scratch, s));
     B2_CHECK(pts.reserve(n * sizeof(float4)));
-    k_cell_scatter<<<nblk, 256, 0, s>>>(raw.as<unsigned char>(), stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>()); count_launch();
+    k_cell_scatter<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>()); count_launch();
     B2_CUDA(cudaGetLastError());
     dev.pts = pts.as<float4>(); dev.cell_start = cell_start.as<uint32_t>();
     dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h;

@@ -603,6 +603,28 @@ static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cs
     return B2_OK;
 }
 
+namespace b2 {
+
+void pose_to_affine_host(const float pose6[6], float xf[12]) {
+    float trig[6];
+    host_prepare_pose(pose6, xf, trig);
+}
+
+// kdtreeCornerFromMap->setInputCloud / kdtreeSurfFromMap->setInputCloud on clouds that already live in device memory
+int s2m_set_map_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf) {
+    if (!h) return B2_ERR_ARG;
+    B2_CHECK(h->gc.begin_device(d_corner, 16, n_corner, h->prm.knn_max_dist, h->stream));
+    B2_CHECK(h->gs.begin_device(d_surf, 16, n_surf, h->prm.knn_max_dist, h->stream2));
+    B2_CHECK(h->gc.finish(h->stream));
+    B2_CHECK(h->gs.finish(h->stream2));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream2));
+    h->have_map = true;
+    return B2_OK;
+}
+
+}  // namespace b2
+
 extern "C" {
 
 void b2_s2m_default_params(b2_s2m_params* p) {

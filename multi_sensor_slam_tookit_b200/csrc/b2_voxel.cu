@@ -131,7 +131,7 @@ struct b2_voxel_s {
     float leaf[3] = {0.f, 0.f, 0.f};
     unsigned min_pts = 0;
     cudaStream_t stream = nullptr;
-    DevBuf raw, work, out, small;
+    DevBuf raw, work, out, small, vop;
     PinBuf pin;
 };
 
@@ -148,7 +148,7 @@ int b2_voxel_create(b2_voxel_t* out) {
 
 int b2_voxel_destroy(b2_voxel_t h) {
     if (!h) return B2_ERR_ARG;
-    h->raw.release(); h->work.release(); h->out.release(); h->small.release(); h->pin.release();
+    h->raw.release(); h->work.release(); h->out.release(); h->small.release(); h->vop.release(); h->pin.release();
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return B2_OK;
@@ -166,28 +166,28 @@ int b2_voxel_set_min_points_per_voxel(b2_voxel_t h, unsigned min_points) {
     return B2_OK;
 }
 
-int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, int n_fields, void* out, size_t out_stride,
-                    size_t out_capacity, size_t* n_out, int* refused, int32_t* voxel_of_point) {
-    if (!h || !n_out || (n && (!in || !out)) || (n_fields != 3 && n_fields != 4) || in_stride < (size_t)(n_fields * 4) ||
-        out_stride < (size_t)(n_fields * 4) || (in_stride & 3) || (out_stride & 3) || n > 0x7ffffff0ull) {
-        set_error("b2_voxel_filter: bad argument"); return B2_ERR_ARG;
-    }
-    if (!(h->leaf[0] > 0.f)) { set_error("b2_voxel_filter: leaf size not set"); return B2_ERR_STATE; }
-    *n_out = 0;
+}  // extern "C"
+
+namespace b2 {
+
+// The filter proper, device in -> device out (h->out; *m_out voxels). d_in must stay valid until the stream has drained.
+// refused = 1: PCL's "leaf size is too small" case, the output is a copy of the input. d_vop (optional, device, n ints).
+int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride, size_t n, int n_fields, size_t out_stride,
+                     size_t out_capacity, uint32_t* m_out, int* refused, int32_t* d_vop) {
+    *m_out = 0;
     if (refused) *refused = 0;
-    if (n == 0) return B2_OK;                       // PCL: empty input -> empty output
+    if (n == 0) return B2_OK;
     cudaStream_t s = h->stream;
     const int ioff = (int)B2_INTENSITY_OFFSET(in_stride), ooff = (int)B2_INTENSITY_OFFSET(out_stride);
-    B2_CHECK(h->raw.reserve(n * in_stride));
-    B2_CUDA(cudaMemcpyAsync(h->raw.p, in, n * in_stride, cudaMemcpyHostToDevice, s));
     B2_CHECK(h->small.reserve(256));
     uint32_t* bb = h->small.as<uint32_t>();
     k_vx_bbox_init<<<1, 32, 0, s>>>(bb); count_launch();
     const int nbb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 8);
-    k_vx_bbox<<<nbb, 256, 0, s>>>(h->raw.as<unsigned char>(), in_stride, n, bb); count_launch();
+    k_vx_bbox<<<nbb, 256, 0, s>>>(d_in, in_stride, n, bb); count_launch();
     B2_CUDA(cudaGetLastError());
-    uint32_t hbb[6];
-    B2_CUDA(cudaMemcpyAsync(hbb, bb, sizeof(hbb), cudaMemcpyDeviceToHost, s));
+    B2_CHECK(h->pin.reserve(64));
+    uint32_t* hbb = h->pin.as<uint32_t>();
+    B2_CUDA(cudaMemcpyAsync(hbb, bb, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
     auto unflip = [](uint32_t u) { uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
     float mn[3], mx[3];
@@ -205,15 +205,15 @@ int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, in
         // "Leaf size is too small for the input dataset": output = input
         if (refused) *refused = 1;
         if (out_capacity < n) { set_error("b2_voxel_filter: refused (index overflow) and out_capacity < n"); return B2_ERR_CAPACITY; }
-        const unsigned char* src = static_cast<const unsigned char*>(in);
-        unsigned char* dst = static_cast<unsigned char*>(out);
-        if (in_stride == out_stride) memcpy(dst, src, n * in_stride);
-        else for (size_t i = 0; i < n; i++) {
-            memcpy(dst + i * out_stride, src + i * in_stride, 12);
-            if (n_fields == 4) memcpy(dst + i * out_stride + ooff, src + i * in_stride + ioff, 4);
+        B2_CHECK(h->out.reserve(n * out_stride));
+        if (in_stride == out_stride) B2_CUDA(cudaMemcpyAsync(h->out.p, d_in, n * in_stride, cudaMemcpyDeviceToDevice, s));
+        else {
+            B2_CUDA(cudaMemsetAsync(h->out.p, 0, n * out_stride, s));
+            B2_CUDA(cudaMemcpy2DAsync(h->out.p, out_stride, d_in, in_stride, 12, n, cudaMemcpyDeviceToDevice, s));
+            if (n_fields == 4) B2_CUDA(cudaMemcpy2DAsync(h->out.as<unsigned char>() + ooff, out_stride, d_in + ioff, in_stride, 4, n, cudaMemcpyDeviceToDevice, s));
         }
-        if (voxel_of_point) for (size_t i = 0; i < n; i++) voxel_of_point[i] = -1;
-        *n_out = n;
+        if (d_vop) B2_CUDA(cudaMemsetAsync(d_vop, 0xff, n * sizeof(int32_t), s));
+        *m_out = (uint32_t)n;
         return B2_OK;
     }
     uint64_t ncells = 1;
@@ -231,15 +231,14 @@ int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, in
 
     const size_t nal = (n + 64) & ~(size_t)63;       // room for n+1 entries
     const size_t scratch_bytes = std::max(sort_tmp_bytes(n), scan_tmp_bytes(n + 1)) + 1024;
-    B2_CHECK(h->work.reserve(7 * nal * sizeof(uint32_t) + scratch_bytes + (voxel_of_point ? nal * sizeof(int32_t) : 0)));
+    B2_CHECK(h->work.reserve(7 * nal * sizeof(uint32_t) + scratch_bytes));
     uint32_t* ka = h->work.as<uint32_t>();
     uint32_t* va = ka + nal; uint32_t* kb = va + nal; uint32_t* vb = kb + nal;
     uint32_t* segid = vb + nal; uint32_t* seg_start = segid + nal; uint32_t* keep = seg_start + nal;
     char* scratch = reinterpret_cast<char*>(keep + nal);
-    int32_t* d_vop = voxel_of_point ? reinterpret_cast<int32_t*>(scratch + scratch_bytes) : nullptr;
     const uint32_t n32 = (uint32_t)n;
     const unsigned nblk = (unsigned)((n + 255) / 256), nblk1 = (unsigned)((n + 1 + 255) / 256);
-    k_vx_key<<<nblk, 256, 0, s>>>(h->raw.as<unsigned char>(), in_stride, n32, g, ka, va, d_vop); count_launch();
+    k_vx_key<<<nblk, 256, 0, s>>>(d_in, in_stride, n32, g, ka, va, d_vop); count_launch();
     B2_CUDA(cudaGetLastError());
     uint32_t *ks, *vs;
     B2_CHECK(radix_sort_pairs(ka, va, kb, vb, n, bits, scratch, s, &ks, &vs));
@@ -252,14 +251,42 @@ int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, in
     B2_CHECK(exclusive_scan_u32(keep, n + 1, scratch, s));
     const size_t cap = std::min(n, out_capacity);
     B2_CHECK(h->out.reserve(std::max<size_t>(cap, 1) * out_stride));
-    k_vx_centroid<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(h->raw.as<unsigned char>(), in_stride, ioff, n_fields, vs, ks, seg_start, segid + n,
+    k_vx_centroid<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(d_in, in_stride, ioff, n_fields, vs, ks, seg_start, segid + n,
                                                               keep, n32, (uint32_t)cap, h->out.as<unsigned char>(), out_stride, ooff, nullptr); count_launch();
     B2_CUDA(cudaGetLastError());
-    uint32_t m = 0;
-    B2_CUDA(cudaMemcpyAsync(&m, keep + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    if (voxel_of_point) B2_CUDA(cudaMemcpyAsync(voxel_of_point, d_vop, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    uint32_t* hm = h->pin.as<uint32_t>() + 8;
+    B2_CUDA(cudaMemcpyAsync(hm, keep + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
-    if ((size_t)m > out_capacity) { set_error("b2_voxel_filter: %u voxels but out_capacity %zu", m, out_capacity); return B2_ERR_CAPACITY; }
+    if ((size_t)*hm > out_capacity) { set_error("b2_voxel_filter: %u voxels but out_capacity %zu", *hm, out_capacity); return B2_ERR_CAPACITY; }
+    *m_out = *hm;
+    return B2_OK;
+}
+
+const void* voxel_out_dev(b2_voxel_s* h) { return h->out.p; }
+cudaStream_t voxel_stream(b2_voxel_s* h) { return h->stream; }
+
+}  // namespace b2
+
+extern "C" {
+
+int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, int n_fields, void* out, size_t out_stride,
+                    size_t out_capacity, size_t* n_out, int* refused, int32_t* voxel_of_point) {
+    if (!h || !n_out || (n && (!in || !out)) || (n_fields != 3 && n_fields != 4) || in_stride < (size_t)(n_fields * 4) ||
+        out_stride < (size_t)(n_fields * 4) || (in_stride & 3) || (out_stride & 3) || n > 0x7ffffff0ull) {
+        set_error("b2_voxel_filter: bad argument"); return B2_ERR_ARG;
+    }
+    if (!(h->leaf[0] > 0.f)) { set_error("b2_voxel_filter: leaf size not set"); return B2_ERR_STATE; }
+    *n_out = 0;
+    if (refused) *refused = 0;
+    if (n == 0) return B2_OK;                       // PCL: empty input -> empty output
+    cudaStream_t s = h->stream;
+    B2_CHECK(h->raw.reserve(n * in_stride));
+    B2_CUDA(cudaMemcpyAsync(h->raw.p, in, n * in_stride, cudaMemcpyHostToDevice, s));
+    int32_t* d_vop = nullptr;
+    if (voxel_of_point) { B2_CHECK(h->vop.reserve(n * sizeof(int32_t))); d_vop = h->vop.as<int32_t>(); }
+    uint32_t m = 0;
+    B2_CHECK(voxel_filter_dev(h, h->raw.as<unsigned char>(), in_stride, n, n_fields, out_stride, out_capacity, &m, refused, d_vop));
+    if (voxel_of_point) B2_CUDA(cudaMemcpyAsync(voxel_of_point, d_vop, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (m) B2_CUDA(cudaMemcpyAsync(out, h->out.p, (size_t)m * out_stride, cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
     *n_out = m;

@@ -115,6 +115,10 @@ class ScanToMapOptimizer:
         s, ss = capi.as_points(laserCloudSurfFromMapDS)
         capi.check(capi.lib().b2_s2m_set_map(self._h, capi.ptr(c), cs, c.shape[0], capi.ptr(s), ss, s.shape[0]))
 
+    def setInputMapFromLocalMap(self, local_map):
+        """The same two setInputCloud calls on the device-resident result of LocalMap.extractCloud (no host copy)."""
+        capi.check(capi.lib().b2_s2m_set_map_from_localmap(self._h, local_map._h))
+
     def setInputScan(self, laserCloudCornerLastDS, laserCloudSurfLastDS):
         c, cs = capi.as_points(laserCloudCornerLastDS, 4)
         s, ss = capi.as_points(laserCloudSurfLastDS, 4)
@@ -196,6 +200,71 @@ class ScanToMapOptimizer:
         AtA, AtB, X = np.zeros(36, np.float32), np.zeros(6, np.float32), np.zeros(6, np.float32)
         capi.check(capi.lib().b2_s2m_get_normal_equations(self._h, capi.ptr(AtA), capi.ptr(AtB), capi.ptr(X)))
         return AtA.reshape(6, 6), AtB, X
+
+
+class LocalMap:
+    """Key-frame store + extractCloud of mapOptimization (mapOptmization.cpp:899-938), device-resident.
+    Members named after the reference's: cornerCloudKeyFrames / surfCloudKeyFrames / cloudKeyPoses6D live in the handle,
+    laserCloud{Corner,Surf}FromMap[DS] are read back with get()."""
+
+    def __init__(self, mappingCornerLeafSize=0.2, mappingSurfLeafSize=0.4, surroundingKeyframeSearchRadius=50.0):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2_localmap_create(C.byref(self._h), float(mappingCornerLeafSize), float(mappingSurfLeafSize)))
+        self.surroundingKeyframeSearchRadius = float(surroundingKeyframeSearchRadius)
+        self.cloudKeyPoses6D = []
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b2_localmap_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def saveKeyFrame(self, thisCornerKeyFrame, thisSurfKeyFrame, pose6):
+        """cornerCloudKeyFrames.push_back / surfCloudKeyFrames.push_back / cloudKeyPoses6D.push_back (:1512-1524)."""
+        c, cs = capi.as_points(thisCornerKeyFrame, 4)
+        s, ss = capi.as_points(thisSurfKeyFrame, 4)
+        p = np.ascontiguousarray(pose6, np.float32)
+        k = C.c_int()
+        capi.check(capi.lib().b2_localmap_add_keyframe(self._h, capi.ptr(c), cs, len(c), capi.ptr(s), ss, len(s), capi.ptr(p), C.byref(k)))
+        self.cloudKeyPoses6D.append(p.copy())
+        return k.value
+
+    def correctPose(self, key_index, pose6):
+        p = np.ascontiguousarray(pose6, np.float32)
+        capi.check(capi.lib().b2_localmap_set_pose(self._h, int(key_index), capi.ptr(p)))
+        self.cloudKeyPoses6D[key_index] = p.copy()
+
+    def clearMapContainer(self):
+        """laserCloudMapContainer.clear() (:1591)."""
+        capi.check(capi.lib().b2_localmap_clear_cache(self._h))
+
+    def extractCloud(self, cloudToExtract):
+        """cloudToExtract: key indices in visiting order. Applies the distance test of :905 against the latest key pose,
+        then assembles and downsamples on the device. Returns (n_corner_ds, n_surf_ds)."""
+        last = self.cloudKeyPoses6D[-1][3:6]
+        keep = [int(k) for k in cloudToExtract
+                if np.sqrt(np.float32(np.sum((self.cloudKeyPoses6D[int(k)][3:6] - last) ** 2, dtype=np.float32))) <= self.surroundingKeyframeSearchRadius]
+        idx = np.ascontiguousarray(keep, np.int32)
+        nc, ns = C.c_size_t(), C.c_size_t()
+        capi.check(capi.lib().b2_localmap_extract(self._h, capi.ptr(idx), len(idx), C.byref(nc), C.byref(ns)))
+        return nc.value, ns.value
+
+    def get(self, which):
+        """which: 'corner', 'surf' (laserCloud*FromMap) or 'cornerDS', 'surfDS' (laserCloud*FromMapDS)."""
+        w = {"corner": 0, "surf": 1, "cornerDS": 2, "surfDS": 3}[which]
+        n = C.c_size_t()
+        capi.check(capi.lib().b2_localmap_get(self._h, w, None, 16, 0, C.byref(n)))
+        out = np.empty((n.value, 4), np.float32)
+        if n.value:
+            capi.check(capi.lib().b2_localmap_get(self._h, w, capi.ptr(out), 16, n.value, C.byref(n)))
+        return out
+
+    def lastGpuMs(self):
+        ms, nc = C.c_float(), C.c_size_t()
+        capi.check(capi.lib().b2_localmap_last_gpu_ms(self._h, C.byref(ms), C.byref(nc)))
+        return ms.value, nc.value
 
 
 def transformPointCloud(cloud, transformIn):

@@ -207,3 +207,25 @@ def sample_surfaces(scene, n, seed=0, noise=0.02):
     pts = np.concatenate(out)
     pts += rng.normal(0, noise, pts.shape)
     return pts[rng.permutation(pts.shape[0])]
+
+
+def keyframes_from_map(map_corner, map_surf, n_keys=12, seed=5):
+    """Synthetic key frames for the local-map assembly (mapOptmization.cpp:899-938): chunk k of a map, moved into the sensor
+    frame of a random key pose, so that transforming each chunk by its pose and concatenating restores the map.
+    Returns a list of (corner (n, 4) f32, surf (n, 4) f32, pose6 f32 = roll, pitch, yaw, x, y, z)."""
+    rng = np.random.default_rng(seed)
+    keys = []
+    cc = np.array_split(map_corner, n_keys)
+    ss = np.array_split(map_surf, n_keys)
+    for k in range(n_keys):
+        pose = np.array([rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), rng.uniform(-3, 3),
+                         rng.uniform(-30, 30), rng.uniform(-30, 30), rng.uniform(-0.5, 0.5)], np.float32)
+        R = rot_zyx(*pose[:3].astype(np.float64))
+        t = pose[3:].astype(np.float64)
+        loc = []
+        for cloud in (cc[k], ss[k]):
+            q = cloud.copy()
+            q[:, :3] = ((cloud[:, :3].astype(np.float64) - t) @ R).astype(np.float32)
+            loc.append(np.ascontiguousarray(q))
+        keys.append((loc[0], loc[1], pose))
+    return keys
