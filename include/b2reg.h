@@ -329,6 +329,24 @@ int b2_ndt_derivatives(b2_ndt_t h, const double p[6], double* score, double grad
 /* device time of the last align (or target build), kernel launches and derivative passes it made, (point, voxel) pairs of the last pass */
 int b2_ndt_last_gpu_ms(b2_ndt_t h, float* ms, int* launches, int* evaluations, long long* pairs_last);
 
+/* ------------------------------------------------------------------------------------------------
+ * Nearest-neighbour registration error + yaw grid search — replaces, in SensorsCalibration's
+ * lidar2lidar auto-calibration, Calibration_Tookit/SensorsCalibration/lidar2lidar/auto_calib/src/registration_icp.cpp
+ *   :51-52   pcl::KdTreeFLANN kdtree; kdtree.setInputCloud(tgt_ngcloud_)          -> b2_nnerr_set_target
+ *   :78-100  CalculateICPError(kdtree, init_guess, yaw): sum of squared 1-NN distances of the transformed source
+ *                                                                                   -> b2_nnerr_evaluate
+ *   :49-76   RegistrationByICP(init_guess, transform): 37 evaluations on a shrinking yaw grid -> b2_nnerr_yaw_search
+ * T is a row-major 4x4 double (Eigen::Matrix4d is column-major: transpose). The reference's GetDeltaT converts its argument
+ * from degrees although the caller passes radians; the search reproduces that as written. */
+typedef struct b2_nnerr_s* b2_nnerr_t;
+int b2_nnerr_create(b2_nnerr_t* out);
+int b2_nnerr_destroy(b2_nnerr_t h);
+int b2_nnerr_set_target(b2_nnerr_t h, const void* pts, size_t stride_bytes, size_t n);
+int b2_nnerr_set_source(b2_nnerr_t h, const void* pts, size_t stride_bytes, size_t n);
+int b2_nnerr_evaluate(b2_nnerr_t h, const double T[16], double* dist_sum, size_t* n_found);
+int b2_nnerr_yaw_search(b2_nnerr_t h, const double init_guess[16], double T_out[16], double* best_yaw, double* min_error, int* evaluations);
+int b2_nnerr_last_gpu_ms(b2_nnerr_t h, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

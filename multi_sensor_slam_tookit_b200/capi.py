@@ -52,6 +52,8 @@ SYMBOLS = [
     "b2_gicp_last_gpu_ms", "b2_gicp_index_info", "b2_gicp_get_evaluation_ms",
     "b2_localmap_create", "b2_localmap_destroy", "b2_localmap_add_keyframe", "b2_localmap_num_keyframes", "b2_localmap_set_pose",
     "b2_localmap_clear_cache", "b2_localmap_extract", "b2_localmap_get", "b2_localmap_last_gpu_ms", "b2_s2m_set_map_from_localmap",
+    "b2_nnerr_create", "b2_nnerr_destroy", "b2_nnerr_set_target", "b2_nnerr_set_source", "b2_nnerr_evaluate", "b2_nnerr_yaw_search",
+    "b2_nnerr_last_gpu_ms",
     "b2_ndt_create", "b2_ndt_destroy", "b2_ndt_set_transformation_epsilon", "b2_ndt_set_step_size", "b2_ndt_set_resolution",
     "b2_ndt_set_maximum_iterations", "b2_ndt_set_input_target", "b2_ndt_set_input_source", "b2_ndt_align", "b2_ndt_has_converged",
     "b2_ndt_get_final_transformation", "b2_ndt_get_fitness_score", "b2_ndt_get_transformation_probability",
@@ -144,6 +146,13 @@ def lib():
     L.b2_localmap_get.argtypes = [vp, i32, vp, sz, sz, C.POINTER(sz)]
     L.b2_localmap_last_gpu_ms.argtypes = [vp, pf, C.POINTER(sz)]
     L.b2_s2m_set_map_from_localmap.argtypes = [vp, vp]
+    L.b2_nnerr_create.argtypes = [C.POINTER(vp)]
+    L.b2_nnerr_destroy.argtypes = [vp]
+    L.b2_nnerr_set_target.argtypes = [vp, vp, sz, sz]
+    L.b2_nnerr_set_source.argtypes = [vp, vp, sz, sz]
+    L.b2_nnerr_evaluate.argtypes = [vp, vp, pd, C.POINTER(sz)]
+    L.b2_nnerr_yaw_search.argtypes = [vp, vp, vp, pd, pd, pi]
+    L.b2_nnerr_last_gpu_ms.argtypes = [vp, pf]
     L.b2_ndt_create.argtypes = [C.POINTER(vp)]
     L.b2_ndt_destroy.argtypes = [vp]
     L.b2_ndt_set_transformation_epsilon.argtypes = [vp, dbl]

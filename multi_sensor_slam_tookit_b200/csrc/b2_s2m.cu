@@ -27,7 +27,11 @@ namespace b2 {
 
 constexpr int S2M_THREADS = 256;
 // two shapes of the one kernel: <lanes per feature, rounds>
-constexpr int S2M_LAT_LPF = 16, S2M_LAT_ROUNDS = 2;   // single scan: 32 features per CTA, many small CTAs (latency)
+#ifndef S2M_LAT_LPF_V
+#define S2M_LAT_LPF_V 16
+#define S2M_LAT_ROUNDS_V 2
+#endif
+constexpr int S2M_LAT_LPF = S2M_LAT_LPF_V, S2M_LAT_ROUNDS = S2M_LAT_ROUNDS_V;   // single scan: 32 features per CTA, many small CTAs (latency)
 constexpr int S2M_THR_LPF = 8,  S2M_THR_ROUNDS = 8;   // batch: 256 features per CTA, every warp busy in phase 2 (throughput)
 constexpr int S2M_LAT_FPB = S2M_THREADS / S2M_LAT_LPF * S2M_LAT_ROUNDS;
 constexpr int S2M_THR_FPB = S2M_THREADS / S2M_THR_LPF * S2M_THR_ROUNDS;

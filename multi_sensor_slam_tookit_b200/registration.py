@@ -274,3 +274,43 @@ def transformPointCloud(cloud, transformIn):
     pose = np.ascontiguousarray(transformIn, np.float32)
     capi.check(capi.lib().b2_transform_cloud(capi.ptr(pts), stride, pts.shape[0], capi.ptr(pose), capi.ptr(out), pts.shape[1] * 4))
     return out
+
+
+class ICPRegistrator:
+    """The yaw grid search of SensorsCalibration's lidar2lidar auto-calibration (auto_calib/src/registration_icp.cpp:49-100),
+    member names as there. Clouds are (n, >=3) float32 (the non-ground clouds tgt_ngcloud_ / src_ngcloud_)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2_nnerr_create(C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b2_nnerr_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def SetTargetCloud(self, ngcloud):
+        p, st = capi.as_points(ngcloud, 3)
+        capi.check(capi.lib().b2_nnerr_set_target(self._h, capi.ptr(p), st, len(p)))
+
+    def SetSourceCloud(self, ngcloud):
+        p, st = capi.as_points(ngcloud, 3)
+        capi.check(capi.lib().b2_nnerr_set_source(self._h, capi.ptr(p), st, len(p)))
+
+    def CalculateICPError(self, T):
+        T = np.ascontiguousarray(T, np.float64)
+        s, n = C.c_double(), C.c_size_t()
+        capi.check(capi.lib().b2_nnerr_evaluate(self._h, capi.ptr(T), C.byref(s), C.byref(n)))
+        return s.value
+
+    def RegistrationByICP(self, init_guess):
+        g = np.ascontiguousarray(init_guess, np.float64)
+        T = np.empty((4, 4), np.float64)
+        yaw, err, ev = C.c_double(), C.c_double(), C.c_int()
+        capi.check(capi.lib().b2_nnerr_yaw_search(self._h, capi.ptr(g), capi.ptr(T), C.byref(yaw), C.byref(err), C.byref(ev)))
+        ms = C.c_float()
+        capi.check(capi.lib().b2_nnerr_last_gpu_ms(self._h, C.byref(ms)))
+        return dict(transform=T, best_yaw=yaw.value, min_error=err.value, evaluations=ev.value, gpu_ms=ms.value)

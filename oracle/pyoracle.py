@@ -85,6 +85,13 @@ def lib():
     L.o_extract_features.argtypes = [f32p, i32p, C.c_int, i32p, i32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
                                      f32p, i32p, i32p, i32p, i32p, i32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     od64 = _opt(f64p)
+    L.o_icperr_create.restype = C.c_void_p
+    L.o_icperr_create.argtypes = [f32p, C.c_int, f32p, C.c_int]
+    L.o_icperr_destroy.argtypes = [C.c_void_p]
+    L.o_icperr_evaluate.restype = C.c_double
+    L.o_icperr_evaluate.argtypes = [C.c_void_p, f64p]
+    L.o_icperr_yaw_search.restype = C.c_int
+    L.o_icperr_yaw_search.argtypes = [C.c_void_p, f64p, f64p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.o_ndt_create.restype = C.c_void_p
     L.o_ndt_create.argtypes = [C.c_float, C.c_double, C.c_double, C.c_int]
     L.o_ndt_destroy.argtypes = [C.c_void_p]
@@ -397,3 +404,25 @@ def svd_solve6(H, b):
     x = np.empty(6)
     lib().o_svd_solve6(_f64(H).reshape(36), _f64(b), x)
     return x
+
+
+# ---------------------------------------------------------------- SensorsCalibration yaw grid search
+class IcpErrorOracle:
+    def __init__(self, tgt, src):
+        self.L = lib()
+        t, s_ = _f32(tgt).reshape(-1, 3), _f32(src).reshape(-1, 3)
+        self.h = self.L.o_icperr_create(t, len(t), s_, len(s_))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.o_icperr_destroy(self.h)
+            self.h = None
+
+    def evaluate(self, T):
+        return self.L.o_icperr_evaluate(self.h, _f64(T).reshape(16))
+
+    def yaw_search(self, init):
+        T = np.empty(16, np.float64)
+        yaw, err = C.c_double(), C.c_double()
+        ev = self.L.o_icperr_yaw_search(self.h, _f64(init).reshape(16), T, C.byref(yaw), C.byref(err))
+        return dict(transform=T.reshape(4, 4), best_yaw=yaw.value, min_error=err.value, evaluations=ev)
