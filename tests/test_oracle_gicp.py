@@ -170,3 +170,24 @@ def test_shard_helpers():
             assert np.all(cover == 1)
             sizes = [shard_size(n, r, world) for r in range(world)]
             assert max(sizes) - min(sizes) <= 4096
+
+
+def test_icp_error_oracle_against_scipy(oracle):
+    """oracle/o_icp.cpp (SensorsCalibration yaw grid search): the error sum against scipy's kd-tree, and the search loop's
+    bookkeeping (37 evaluations, the winner is a grid point, the returned transform is GetDeltaT(best_yaw) * init)."""
+    from scipy.spatial import cKDTree
+    tgt = G.lidar_cloud(0, n_rings=16, n_cols=256).astype(np.float32)
+    src = G.lidar_cloud(1, n_rings=16, n_cols=256).astype(np.float32)
+    truth = G.pair_truth(1, 0)
+    o = oracle.IcpErrorOracle(tgt, src)
+    for T in (truth, np.eye(4)):
+        q = (src.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+        d, _ = cKDTree(tgt.astype(np.float64)).query(q.astype(np.float64), k=1)
+        ref = float((d ** 2).sum())
+        assert abs(o.evaluate(T) - ref) <= 1e-5 * ref
+    init = G.perturbed(truth, (0, 0, 0), (0, 0, 0.4))
+    r = o.yaw_search(init)
+    assert r["evaluations"] == 37 and r["min_error"] <= o.evaluate(init)
+    a = np.float32(r["best_yaw"]).astype(np.float64) * np.pi / 180.0
+    D = np.eye(4); D[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+    assert np.abs(r["transform"] - D @ init).max() < 1e-12
