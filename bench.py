@@ -13,7 +13,7 @@ liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:1282-1310 on one VLP-16 scan agains
   batched    B scans (pose hypotheses) against the one map in a single launch per iteration
   cpu_baseline  the CPU oracle (restatement of the reference path) on the box's host cores
 --impl reference times that CPU path alone (PCL/OpenCV are not installable here: the oracle is the reference arm).
-  registration  the NDT / GICP half of the metric (Mpts/s): C3 NDT pair, C4 batched GICP pairs (round-robin over ranks),
+  registration  front_end_c2: the per-scan front end on the 128 x 1024 scan of config C2; then the NDT / GICP half of the metric (Mpts/s): C3 NDT pair, C4 batched GICP pairs (round-robin over ranks),
              C5 50 M-point map-to-map GICP (source sharded over ranks, NCCL all-reduce of 30 doubles per iteration)
 Multi-GPU: C1 does not shard — N GPUs run N independent replicas, no collective on the data path.
 """
@@ -435,6 +435,26 @@ def run_registration(args, rank, local_rank, world, dist, torch):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # ---- C2: the per-scan front end does not shard either -> rank 0 only
+    if rank == 0:
+        import frontend_bench as FB
+        inp = FB.c2_inputs()
+        r = FB.run_c2(inputs=inp)
+        cpu = FB.cpu_c2(inp, 5.0)
+        ach = r["algorithmic_bytes"] / ((r["project_gpu_ms"] + r["features_gpu_ms"]) * 1e-3) / 1e9
+        out["front_end_c2"] = {
+            "workload": f"C2 LIO-SAM imageProjection + deskew + featureExtraction: 128 x 1024 scan, {r['points_in']} returns -> {r['extracted']} extracted, "
+                        f"{r['corner']} corner + {r['surf']} surf features", "value": r["mpts_per_s"], "unit": "Mpts/s",
+            "project_gpu_ms": r["project_gpu_ms"], "features_gpu_ms": r["features_gpu_ms"],
+            "e2e": {"value": r["e2e_mpts_per_s"], "unit": "Mpts/s", "ms": r["e2e_ms"], "h2d_bytes": int(32 * r["points_in"] + 4 * 8 * 62),
+                    "d2h_bytes": int(24 * r["extracted"] + 16 * (r["corner"] + r["surf"]) + 1024),
+                    "step": "b2_scan_project + b2_scan_extract_features, PointXYZIRT records in, cloud_info arrays + corner / surf clouds out"},
+            "roofline": {"kernel": "k_scan_* (9 launches)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": r["algorithmic_bytes"],
+                         "note": "52 B per input point + 20 B per extracted point (SURVEY.md 8d) over the device span of both calls; 4.2 MB in, "
+                                 "launch-latency bound at this size (one scan)"},
+            "cpu_baseline": {"value": cpu["mpts_per_s"], "unit": "Mpts/s", "cores": 1, "kind": "port",
+                             "sample": f"{cpu['reps']} scans: project {cpu['project_ms']:.2f} ms + features {cpu['features_ms']:.2f} ms (serial, as the reference's two nodes are)"}}
     # ---- C3: one NDT pair does not shard -> rank 0 only
     if rank == 0:
         inputs = NB.c3_inputs()
