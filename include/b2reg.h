@@ -347,6 +347,32 @@ int b2_nnerr_evaluate(b2_nnerr_t h, const double T[16], double* dist_sum, size_t
 int b2_nnerr_yaw_search(b2_nnerr_t h, const double init_guess[16], double T_out[16], double* best_yaw, double* min_error, int* evaluations);
 int b2_nnerr_last_gpu_ms(b2_nnerr_t h, float* ms);
 
+/* ------------------------------------------------------------------------------------------------
+ * Point-to-point ICP — replaces pcl::IterativeClosestPoint<PointType, PointType> of the loop-closure
+ * thread, liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:559-586
+ *   :561-565  setMaxCorrespondenceDistance(historyKeyframeSearchRadius*2) / setMaximumIterations(100) /
+ *             setTransformationEpsilon(1e-6) / setEuclideanFitnessEpsilon(1e-6) / setRANSACIterations(0)
+ *   :568-571  setInputSource / setInputTarget / align            :573  hasConverged, getFitnessScore
+ *   :580,:586 getFinalTransformation
+ * Semantics: PCL 1.10 (icp.hpp, DefaultConvergenceCriteria, TransformationEstimationSVD); the handle starts with PCL's
+ * defaults (10 iterations, no thresholds). Matrices are row-major 4x4 floats. guess / out_cloud may be NULL. */
+typedef struct b2_icp_s* b2_icp_t;
+int b2_icp_create(b2_icp_t* out);
+int b2_icp_destroy(b2_icp_t h);
+int b2_icp_set_max_correspondence_distance(b2_icp_t h, double distance);
+int b2_icp_set_maximum_iterations(b2_icp_t h, int n);
+int b2_icp_set_transformation_epsilon(b2_icp_t h, double epsilon);
+int b2_icp_set_euclidean_fitness_epsilon(b2_icp_t h, double epsilon);
+int b2_icp_set_ransac_iterations(b2_icp_t h, int n /* only 0 */);
+int b2_icp_set_input_source(b2_icp_t h, const void* pts, size_t stride_bytes, size_t n);
+int b2_icp_set_input_target(b2_icp_t h, const void* pts, size_t stride_bytes, size_t n);
+int b2_icp_align(b2_icp_t h, const float guess[16], void* out_cloud, size_t out_stride);
+int b2_icp_has_converged(b2_icp_t h, int* converged);
+int b2_icp_get_fitness_score(b2_icp_t h, double* score);
+int b2_icp_get_final_transformation(b2_icp_t h, float T[16]);
+int b2_icp_get_final_num_iteration(b2_icp_t h, int* iterations);
+int b2_icp_last_gpu_ms(b2_icp_t h, float* ms, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,10 @@ SYMBOLS = [
     "b2_localmap_clear_cache", "b2_localmap_extract", "b2_localmap_get", "b2_localmap_last_gpu_ms", "b2_s2m_set_map_from_localmap",
     "b2_nnerr_create", "b2_nnerr_destroy", "b2_nnerr_set_target", "b2_nnerr_set_source", "b2_nnerr_evaluate", "b2_nnerr_yaw_search",
     "b2_nnerr_last_gpu_ms",
+    "b2_icp_create", "b2_icp_destroy", "b2_icp_set_max_correspondence_distance", "b2_icp_set_maximum_iterations",
+    "b2_icp_set_transformation_epsilon", "b2_icp_set_euclidean_fitness_epsilon", "b2_icp_set_ransac_iterations", "b2_icp_set_input_source",
+    "b2_icp_set_input_target", "b2_icp_align", "b2_icp_has_converged", "b2_icp_get_fitness_score", "b2_icp_get_final_transformation",
+    "b2_icp_get_final_num_iteration", "b2_icp_last_gpu_ms",
     "b2_ndt_create", "b2_ndt_destroy", "b2_ndt_set_transformation_epsilon", "b2_ndt_set_step_size", "b2_ndt_set_resolution",
     "b2_ndt_set_maximum_iterations", "b2_ndt_set_input_target", "b2_ndt_set_input_source", "b2_ndt_align", "b2_ndt_has_converged",
     "b2_ndt_get_final_transformation", "b2_ndt_get_fitness_score", "b2_ndt_get_transformation_probability",
@@ -153,6 +157,21 @@ def lib():
     L.b2_nnerr_evaluate.argtypes = [vp, vp, pd, C.POINTER(sz)]
     L.b2_nnerr_yaw_search.argtypes = [vp, vp, vp, pd, pd, pi]
     L.b2_nnerr_last_gpu_ms.argtypes = [vp, pf]
+    L.b2_icp_create.argtypes = [C.POINTER(vp)]
+    L.b2_icp_destroy.argtypes = [vp]
+    L.b2_icp_set_max_correspondence_distance.argtypes = [vp, dbl]
+    L.b2_icp_set_maximum_iterations.argtypes = [vp, i32]
+    L.b2_icp_set_transformation_epsilon.argtypes = [vp, dbl]
+    L.b2_icp_set_euclidean_fitness_epsilon.argtypes = [vp, dbl]
+    L.b2_icp_set_ransac_iterations.argtypes = [vp, i32]
+    L.b2_icp_set_input_source.argtypes = [vp, vp, sz, sz]
+    L.b2_icp_set_input_target.argtypes = [vp, vp, sz, sz]
+    L.b2_icp_align.argtypes = [vp, vp, vp, sz]
+    L.b2_icp_has_converged.argtypes = [vp, pi]
+    L.b2_icp_get_fitness_score.argtypes = [vp, pd]
+    L.b2_icp_get_final_transformation.argtypes = [vp, vp]
+    L.b2_icp_get_final_num_iteration.argtypes = [vp, pi]
+    L.b2_icp_last_gpu_ms.argtypes = [vp, pf, pi]
     L.b2_ndt_create.argtypes = [C.POINTER(vp)]
     L.b2_ndt_destroy.argtypes = [vp]
     L.b2_ndt_set_transformation_epsilon.argtypes = [vp, dbl]

@@ -314,3 +314,76 @@ class ICPRegistrator:
         ms = C.c_float()
         capi.check(capi.lib().b2_nnerr_last_gpu_ms(self._h, C.byref(ms)))
         return dict(transform=T, best_yaw=yaw.value, min_error=err.value, evaluations=ev.value, gpu_ms=ms.value)
+
+
+class IterativeClosestPoint:
+    """pcl::IterativeClosestPoint<PointType, PointType> as the loop-closure thread uses it (mapOptmization.cpp:559-586);
+    method names as PCL's. Clouds are (n, >=3) float32."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2_icp_create(C.byref(self._h)))
+        self._n_src = 0
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b2_icp_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def setMaxCorrespondenceDistance(self, d):
+        capi.check(capi.lib().b2_icp_set_max_correspondence_distance(self._h, float(d)))
+
+    def setMaximumIterations(self, n):
+        capi.check(capi.lib().b2_icp_set_maximum_iterations(self._h, int(n)))
+
+    def setTransformationEpsilon(self, e):
+        capi.check(capi.lib().b2_icp_set_transformation_epsilon(self._h, float(e)))
+
+    def setEuclideanFitnessEpsilon(self, e):
+        capi.check(capi.lib().b2_icp_set_euclidean_fitness_epsilon(self._h, float(e)))
+
+    def setRANSACIterations(self, n):
+        capi.check(capi.lib().b2_icp_set_ransac_iterations(self._h, int(n)))
+
+    def setInputSource(self, cloud):
+        p, st = capi.as_points(cloud, 3)
+        capi.check(capi.lib().b2_icp_set_input_source(self._h, capi.ptr(p), st, len(p)))
+        self._n_src = len(p)
+
+    def setInputTarget(self, cloud):
+        p, st = capi.as_points(cloud, 3)
+        capi.check(capi.lib().b2_icp_set_input_target(self._h, capi.ptr(p), st, len(p)))
+
+    def align(self, guess=None, want_output=False):
+        g = None if guess is None else np.ascontiguousarray(guess, np.float32)
+        out = np.zeros((self._n_src, 3), np.float32) if want_output else None
+        capi.check(capi.lib().b2_icp_align(self._h, capi.ptr(g), capi.ptr(out), 12))
+        return out
+
+    def hasConverged(self):
+        v = C.c_int()
+        capi.check(capi.lib().b2_icp_has_converged(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def getFitnessScore(self):
+        v = C.c_double()
+        capi.check(capi.lib().b2_icp_get_fitness_score(self._h, C.byref(v)))
+        return v.value
+
+    def getFinalTransformation(self):
+        T = np.empty((4, 4), np.float32)
+        capi.check(capi.lib().b2_icp_get_final_transformation(self._h, capi.ptr(T)))
+        return T
+
+    def getFinalNumIteration(self):
+        v = C.c_int()
+        capi.check(capi.lib().b2_icp_get_final_num_iteration(self._h, C.byref(v)))
+        return v.value
+
+    def lastGpuMs(self):
+        ms, n = C.c_float(), C.c_int()
+        capi.check(capi.lib().b2_icp_last_gpu_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

@@ -85,6 +85,9 @@ def lib():
     L.o_extract_features.argtypes = [f32p, i32p, C.c_int, i32p, i32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
                                      f32p, i32p, i32p, i32p, i32p, i32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     od64 = _opt(f64p)
+    L.o_icp_align.restype = C.c_int
+    L.o_icp_align.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, f32p, C.POINTER(C.c_int),
+                              C.POINTER(C.c_double), of32]
     L.o_icperr_create.restype = C.c_void_p
     L.o_icperr_create.argtypes = [f32p, C.c_int, f32p, C.c_int]
     L.o_icperr_destroy.argtypes = [C.c_void_p]
@@ -426,3 +429,15 @@ class IcpErrorOracle:
         yaw, err = C.c_double(), C.c_double()
         ev = self.L.o_icperr_yaw_search(self.h, _f64(init).reshape(16), T, C.byref(yaw), C.byref(err))
         return dict(transform=T.reshape(4, 4), best_yaw=yaw.value, min_error=err.value, evaluations=ev)
+
+
+def icp_align(src, tgt, max_corr_dist=30.0, max_iterations=100, transformation_epsilon=1e-6, euclidean_fitness_epsilon=1e-6):
+    """pcl::IterativeClosestPoint restatement (identity guess), as mapOptmization.cpp:559-586 configures it."""
+    s_, t_ = _f32(src).reshape(-1, 3), _f32(tgt).reshape(-1, 3)
+    T = np.empty(16, np.float32)
+    hist = np.zeros((max(max_iterations, 1), 16), np.float32)
+    conv, fit = C.c_int(), C.c_double()
+    it = lib().o_icp_align(s_, len(s_), t_, len(t_), float(max_corr_dist), int(max_iterations), float(transformation_epsilon),
+                           float(euclidean_fitness_epsilon), T, C.byref(conv), C.byref(fit), hist)
+    return dict(transformation=T.reshape(4, 4), iterations=it, converged=bool(conv.value), fitness_score=fit.value,
+                history=hist[:it].reshape(-1, 4, 4))
