@@ -373,6 +373,28 @@ int b2_icp_get_final_transformation(b2_icp_t h, float T[16]);
 int b2_icp_get_final_num_iteration(b2_icp_t h, int* iterations);
 int b2_icp_last_gpu_ms(b2_icp_t h, float* ms, int* launches);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-lidar fusion front end — replaces, in PointClouds_Fusion,
+ *   fusion_pointclouds/src/fusion_pointcloud/src/fusion_pointclouds.cpp
+ *     :62-73   pcl::transformPointCloud(*pc_local_k, *pc_trans_k, T_k.matrix())  (double matrix)  -> b2_fusion_add_cloud(.., T_k)
+ *     :80-89   pc_fusion_local = pc_local_1 [+ pc_trans_4] [+ pc_trans_3] + pc_trans_2            -> the order of the add_cloud calls
+ *     :93-108  passthroughFiter(external bounds) / conditionFiter(internal bounds)               -> b2_fusion_set_*_bounds
+ *   lidar_fusion/src/src/lidar_fusion.cpp:239-252, :333-334 (transform one cloud, cloud1 + cloud2)
+ * Points are PCL records (stride >= 16: pcl::PointXYZI 32 B, or packed xyzi 16 B). External bounds keep min <= v <= max
+ * (float limits, non-finite points dropped, as pcl::PassThrough); internal bounds keep what lies outside the box
+ * (pcl::ConditionOr of GT / LT comparisons). Output order = input order. */
+typedef struct b2_fusion_s* b2_fusion_t;
+int b2_fusion_create(b2_fusion_t* out);
+int b2_fusion_destroy(b2_fusion_t h);
+int b2_fusion_clear(b2_fusion_t h);                                  /* forget the added clouds */
+int b2_fusion_add_cloud(b2_fusion_t h, const void* pts, size_t stride_bytes, size_t n, const double T[16] /* NULL: untransformed */);
+int b2_fusion_set_external_bounds(b2_fusion_t h, int enabled, const double min_xyz[3], const double max_xyz[3]);
+int b2_fusion_set_internal_bounds(b2_fusion_t h, int enabled, const double min_xyz[3], const double max_xyz[3]);
+int b2_fusion_run(b2_fusion_t h, size_t* n_fused, size_t* n_out);
+int b2_fusion_get(b2_fusion_t h, void* out, size_t stride_bytes, size_t capacity, size_t* n);   /* out may be NULL to query n */
+int b2_fusion_device_cloud(b2_fusion_t h, const void** d_xyzi, size_t* n);                      /* packed float4 in device memory */
+int b2_fusion_last_gpu_ms(b2_fusion_t h, float* ms);
+
 #ifdef __cplusplus
 }
 #endif

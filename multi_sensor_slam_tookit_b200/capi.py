@@ -58,6 +58,8 @@ SYMBOLS = [
     "b2_icp_set_transformation_epsilon", "b2_icp_set_euclidean_fitness_epsilon", "b2_icp_set_ransac_iterations", "b2_icp_set_input_source",
     "b2_icp_set_input_target", "b2_icp_align", "b2_icp_has_converged", "b2_icp_get_fitness_score", "b2_icp_get_final_transformation",
     "b2_icp_get_final_num_iteration", "b2_icp_last_gpu_ms",
+    "b2_fusion_create", "b2_fusion_destroy", "b2_fusion_clear", "b2_fusion_add_cloud", "b2_fusion_set_external_bounds",
+    "b2_fusion_set_internal_bounds", "b2_fusion_run", "b2_fusion_get", "b2_fusion_device_cloud", "b2_fusion_last_gpu_ms",
     "b2_ndt_create", "b2_ndt_destroy", "b2_ndt_set_transformation_epsilon", "b2_ndt_set_step_size", "b2_ndt_set_resolution",
     "b2_ndt_set_maximum_iterations", "b2_ndt_set_input_target", "b2_ndt_set_input_source", "b2_ndt_align", "b2_ndt_has_converged",
     "b2_ndt_get_final_transformation", "b2_ndt_get_fitness_score", "b2_ndt_get_transformation_probability",
@@ -172,6 +174,16 @@ def lib():
     L.b2_icp_get_final_transformation.argtypes = [vp, vp]
     L.b2_icp_get_final_num_iteration.argtypes = [vp, pi]
     L.b2_icp_last_gpu_ms.argtypes = [vp, pf, pi]
+    L.b2_fusion_create.argtypes = [C.POINTER(vp)]
+    L.b2_fusion_destroy.argtypes = [vp]
+    L.b2_fusion_clear.argtypes = [vp]
+    L.b2_fusion_add_cloud.argtypes = [vp, vp, sz, sz, vp]
+    L.b2_fusion_set_external_bounds.argtypes = [vp, i32, vp, vp]
+    L.b2_fusion_set_internal_bounds.argtypes = [vp, i32, vp, vp]
+    L.b2_fusion_run.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+    L.b2_fusion_get.argtypes = [vp, vp, sz, sz, C.POINTER(sz)]
+    L.b2_fusion_device_cloud.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    L.b2_fusion_last_gpu_ms.argtypes = [vp, pf]
     L.b2_ndt_create.argtypes = [C.POINTER(vp)]
     L.b2_ndt_destroy.argtypes = [vp]
     L.b2_ndt_set_transformation_epsilon.argtypes = [vp, dbl]

@@ -387,3 +387,48 @@ class IterativeClosestPoint:
         ms, n = C.c_float(), C.c_int()
         capi.check(capi.lib().b2_icp_last_gpu_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+
+class FusionPc:
+    """The fusion callback of PointClouds_Fusion (fusion_pointclouds.cpp:55-115): transform the child clouds into the parent
+    frame, concatenate in the reference's order, external pass-through box, internal conditional-removal box."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        capi.check(capi.lib().b2_fusion_create(C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                capi.lib().b2_fusion_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def fuse(self, clouds, transforms, external_bounds=None, internal_bounds=None):
+        """clouds: list of (n, >=4) float32 in fusion order; transforms: list of 4x4 (or None) of the same length;
+        bounds: ((xmin, ymin, zmin), (xmax, ymax, zmax)) or None. Returns the fused (m, 4) xyzi cloud."""
+        L = capi.lib()
+        capi.check(L.b2_fusion_clear(self._h))
+        for c, T in zip(clouds, transforms):
+            p, st = capi.as_points(c, 4)
+            t = None if T is None else np.ascontiguousarray(T, np.float64)
+            capi.check(L.b2_fusion_add_cloud(self._h, capi.ptr(p), st, len(p), capi.ptr(t)))
+        for fn, b in ((L.b2_fusion_set_external_bounds, external_bounds), (L.b2_fusion_set_internal_bounds, internal_bounds)):
+            if b is None:
+                capi.check(fn(self._h, 0, None, None))
+            else:
+                lo, hi = np.ascontiguousarray(b[0], np.float64), np.ascontiguousarray(b[1], np.float64)
+                capi.check(fn(self._h, 1, capi.ptr(lo), capi.ptr(hi)))
+        nf, no = C.c_size_t(), C.c_size_t()
+        capi.check(L.b2_fusion_run(self._h, C.byref(nf), C.byref(no)))
+        out = np.empty((no.value, 4), np.float32)
+        if no.value:
+            capi.check(L.b2_fusion_get(self._h, capi.ptr(out), 16, no.value, C.byref(no)))
+        self.n_fused = nf.value
+        return out
+
+    def lastGpuMs(self):
+        ms = C.c_float()
+        capi.check(capi.lib().b2_fusion_last_gpu_ms(self._h, C.byref(ms)))
+        return ms.value

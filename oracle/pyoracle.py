@@ -441,3 +441,34 @@ def icp_align(src, tgt, max_corr_dist=30.0, max_iterations=100, transformation_e
                            float(euclidean_fitness_epsilon), T, C.byref(conv), C.byref(fit), hist)
     return dict(transformation=T.reshape(4, 4), iterations=it, converged=bool(conv.value), fitness_score=fit.value,
                 history=hist[:it].reshape(-1, 4, 4))
+
+
+# ---------------------------------------------------------------- PointClouds_Fusion front end (numpy restatement)
+def fuse_clouds(clouds, transforms, external_bounds=None, internal_bounds=None):
+    """fusion_pointclouds.cpp:55-115 — pcl::transformPointCloud with a double matrix (sums in double, stored float), `+`
+    concatenation in the given order, pcl::PassThrough on x, z, y (float limits, keeps min <= v <= max, drops non-finite
+    points), pcl::ConditionalRemoval with a ConditionOr of GT / LT comparisons in double (keeps what lies outside the box)."""
+    parts = []
+    for c, T in zip(clouds, transforms):
+        c = _f32(c).reshape(-1, c.shape[1])[:, :4]
+        if T is None:
+            parts.append(c.copy())
+            continue
+        T = _f64(T)
+        x, y, z = (c[:, k].astype(np.float64) for k in range(3))
+        out = c.copy()
+        for r in range(3):
+            out[:, r] = (T[r, 0] * x + T[r, 1] * y + T[r, 2] * z + T[r, 3]).astype(np.float32)
+        parts.append(out)
+    fused = np.concatenate(parts) if parts else np.zeros((0, 4), np.float32)
+    keep = np.ones(len(fused), bool)
+    if external_bounds is not None:
+        lo, hi = np.asarray(external_bounds[0], np.float64).astype(np.float32), np.asarray(external_bounds[1], np.float64).astype(np.float32)
+        keep &= np.isfinite(fused[:, :3]).all(1)
+        for d in range(3):
+            keep &= ~((fused[:, d] < lo[d]) | (fused[:, d] > hi[d]))
+    if internal_bounds is not None:
+        lo, hi = np.asarray(internal_bounds[0], np.float64), np.asarray(internal_bounds[1], np.float64)
+        v = fused[:, :3].astype(np.float64)
+        keep &= ((v > hi) | (v < lo)).any(1)
+    return fused[keep]
