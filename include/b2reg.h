@@ -374,6 +374,65 @@ int b2_icp_get_final_num_iteration(b2_icp_t h, int* iterations);
 int b2_icp_last_gpu_ms(b2_icp_t h, float* ms, int* launches);
 
 /* ------------------------------------------------------------------------------------------------
+ * cloud_info wire format and device hand-offs between the three LIO-SAM stages
+ *   msg/cloud_info.msg:1-35                           the message (ROS1 serialisation, little endian)
+ *   utility.h:286-295          publishCloud           pcl::toROSMsg of a pcl::PointXYZI cloud: height 1, width n, fields
+ *                                                     x@0 y@4 z@8 intensity@16 (FLOAT32), point_step 32, data = the points
+ *   imageProjection.cpp:600-605    publishClouds      stage 0: arrays + cloud_deskewed        -> b2_scan_write_cloud_info(.., 0, ..)
+ *   featureExtraction.cpp:66-79    laserCloudInfoHandler (fromROSMsg of cloud_deskewed)       -> b2_scan_set_from_cloud_info
+ *   featureExtraction.cpp:240-258  freeCloudInfoMemory + publishFeatureCloud: stage 1: arrays emptied, cloud_deskewed kept,
+ *                                                     cloud_corner + cloud_surface added      -> b2_scan_write_cloud_info(.., 1, ..)
+ *   mapOptmization.cpp:237-247     laserCloudInfoHandler (fromROSMsg x 2) + :940-958 downsampleCurrentScan
+ *                                                                                             -> b2_s2m_set_scan_downsampled
+ *   the same hand-off without a message when both stages live in one process                  -> b2_s2m_set_scan_from_front_end
+ * Point records are written with data[3] = 1.0f (the PointXYZI constructor) and zero padding after intensity (PCL leaves
+ * those 12 bytes uninitialised). The key_frame_* clouds are default-constructed (empty), as the reference publishes them. */
+typedef struct {
+    uint32_t seq, stamp_sec, stamp_nsec;       /* header of the message (cloudHeader) */
+    const char* frame_id;                      /* header.frame_id; NULL = "" */
+    const char* cloud_frame_id;                /* lidarFrame, the frame_id publishCloud stamps on the clouds; NULL = "" */
+    int64_t imu_available, odom_available;
+    float imu_roll_init, imu_pitch_init, imu_yaw_init;
+    float initial_guess_x, initial_guess_y, initial_guess_z, initial_guess_roll, initial_guess_pitch, initial_guess_yaw;
+} b2_cloud_info_meta;
+typedef struct {                               /* one sensor_msgs/PointCloud2 inside the message; pointers into the caller's buffer */
+    const void* data;                          /* NOT aligned; usable as the (base, stride = point_step, n = width * height) argument */
+    uint32_t height, width, point_step, row_step, n_fields;
+    int32_t off_x, off_y, off_z, off_intensity;   /* byte offsets of the FLOAT32 fields, -1 if absent */
+    uint8_t is_bigendian, is_dense;
+} b2_cloud2_view;
+typedef struct {
+    uint32_t seq, stamp_sec, stamp_nsec;
+    const char* frame_id; uint32_t frame_id_len;        /* not NUL-terminated */
+    const void* start_ring_index; uint32_t n_start_ring_index;   /* int32, NOT aligned */
+    const void* end_ring_index;   uint32_t n_end_ring_index;
+    const void* point_col_ind;    uint32_t n_point_col_ind;
+    const void* point_range;      uint32_t n_point_range;         /* float32 */
+    int64_t imu_available, odom_available;
+    float imu_roll_init, imu_pitch_init, imu_yaw_init;
+    float initial_guess_x, initial_guess_y, initial_guess_z, initial_guess_roll, initial_guess_pitch, initial_guess_yaw;
+    b2_cloud2_view cloud_deskewed, cloud_corner, cloud_surface, key_frame_cloud, key_frame_color, key_frame_poses, key_frame_map;
+} b2_cloud_info_view;
+/* Host-only walk over a serialised lio_sam/cloud_info; B2_ERR_ARG on a truncated or malformed message. */
+int b2_cloud_info_parse(const void* msg, size_t n_bytes, b2_cloud_info_view* view);
+/* Serialise the handle's device-resident result: stage 0 after b2_scan_project, stage 1 after b2_scan_extract_features.
+ * One packing kernel and one device-to-host copy into `out`; out may be NULL to query *n_bytes. */
+int b2_scan_write_cloud_info(b2_scan_t h, const b2_cloud_info_meta* meta, int stage, void* out, size_t capacity, size_t* n_bytes);
+/* The featureExtraction side: load a stage-0 message into the handle (one upload, one unpacking kernel) so that
+ * b2_scan_extract_features runs on it. */
+int b2_scan_set_from_cloud_info(b2_scan_t h, const void* msg, size_t n_bytes, size_t* n_extracted);
+/* laserCloudCornerLast / laserCloudSurfLast -> downSizeFilterCorner / downSizeFilterSurf -> the optimiser's scan, with the
+ * downsampled clouds never leaving the device. The two VoxelGrid handles carry the leaf sizes (mappingCornerLeafSize,
+ * mappingSurfLeafSize). n_*_ds: laserCloudCornerLastDSNum / laserCloudSurfLastDSNum. */
+int b2_s2m_set_scan_downsampled(b2_s2m_t h, b2_voxel_t ds_corner, const void* corner, size_t corner_stride, size_t n_corner,
+                                b2_voxel_t ds_surf, const void* surf, size_t surf_stride, size_t n_surf,
+                                size_t* n_corner_ds, size_t* n_surf_ds);
+int b2_s2m_set_scan_from_front_end(b2_s2m_t h, b2_scan_t scan, b2_voxel_t ds_corner, b2_voxel_t ds_surf,
+                                   size_t* n_corner_ds, size_t* n_surf_ds);
+/* laserCloudCornerLastDS / laserCloudSurfLastDS of the last set_scan* call (which = 0 corner, 1 surf), packed xyzi. */
+int b2_s2m_get_scan(b2_s2m_t h, int which, float* xyzi, size_t capacity, size_t* n);
+
+/* ------------------------------------------------------------------------------------------------
  * Multi-lidar fusion front end — replaces, in PointClouds_Fusion,
  *   fusion_pointclouds/src/fusion_pointcloud/src/fusion_pointclouds.cpp
  *     :62-73   pcl::transformPointCloud(*pc_local_k, *pc_trans_k, T_k.matrix())  (double matrix)  -> b2_fusion_add_cloud(.., T_k)

@@ -28,6 +28,36 @@ class S2MParams(C.Structure):
                 ("degenerate_eigen_threshold", C.c_float), ("max_batch", C.c_int)]
 
 
+class CloudInfoMeta(C.Structure):
+    _fields_ = [("seq", C.c_uint32), ("stamp_sec", C.c_uint32), ("stamp_nsec", C.c_uint32), ("frame_id", C.c_char_p),
+                ("cloud_frame_id", C.c_char_p), ("imu_available", C.c_int64), ("odom_available", C.c_int64),
+                ("imu_roll_init", C.c_float), ("imu_pitch_init", C.c_float), ("imu_yaw_init", C.c_float),
+                ("initial_guess_x", C.c_float), ("initial_guess_y", C.c_float), ("initial_guess_z", C.c_float),
+                ("initial_guess_roll", C.c_float), ("initial_guess_pitch", C.c_float), ("initial_guess_yaw", C.c_float)]
+
+
+class Cloud2View(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("height", C.c_uint32), ("width", C.c_uint32), ("point_step", C.c_uint32),
+                ("row_step", C.c_uint32), ("n_fields", C.c_uint32), ("off_x", C.c_int32), ("off_y", C.c_int32),
+                ("off_z", C.c_int32), ("off_intensity", C.c_int32), ("is_bigendian", C.c_uint8), ("is_dense", C.c_uint8)]
+
+
+class CloudInfoView(C.Structure):
+    _fields_ = [("seq", C.c_uint32), ("stamp_sec", C.c_uint32), ("stamp_nsec", C.c_uint32),
+                ("frame_id", C.c_void_p), ("frame_id_len", C.c_uint32),
+                ("start_ring_index", C.c_void_p), ("n_start_ring_index", C.c_uint32),
+                ("end_ring_index", C.c_void_p), ("n_end_ring_index", C.c_uint32),
+                ("point_col_ind", C.c_void_p), ("n_point_col_ind", C.c_uint32),
+                ("point_range", C.c_void_p), ("n_point_range", C.c_uint32),
+                ("imu_available", C.c_int64), ("odom_available", C.c_int64),
+                ("imu_roll_init", C.c_float), ("imu_pitch_init", C.c_float), ("imu_yaw_init", C.c_float),
+                ("initial_guess_x", C.c_float), ("initial_guess_y", C.c_float), ("initial_guess_z", C.c_float),
+                ("initial_guess_roll", C.c_float), ("initial_guess_pitch", C.c_float), ("initial_guess_yaw", C.c_float),
+                ("cloud_deskewed", Cloud2View), ("cloud_corner", Cloud2View), ("cloud_surface", Cloud2View),
+                ("key_frame_cloud", Cloud2View), ("key_frame_color", Cloud2View), ("key_frame_poses", Cloud2View),
+                ("key_frame_map", Cloud2View)]
+
+
 class GicpParams(C.Structure):
     _fields_ = [("max_correspondence_distance", C.c_double), ("epsilon", C.c_double), ("relative_fitness", C.c_double),
                 ("relative_rmse", C.c_double), ("max_iteration", C.c_int)]
@@ -43,6 +73,8 @@ SYMBOLS = [
     "b2_s2m_solve_batch", "b2_s2m_last_gpu_ms", "b2_transform_cloud",
     "b2_scan_default_params", "b2_scan_create", "b2_scan_destroy", "b2_scan_project", "b2_scan_extract_features",
     "b2_scan_last_gpu_ms",
+    "b2_cloud_info_parse", "b2_scan_write_cloud_info", "b2_scan_set_from_cloud_info", "b2_s2m_set_scan_downsampled",
+    "b2_s2m_set_scan_from_front_end", "b2_s2m_get_scan",
     "b2_cloud_create", "b2_cloud_destroy", "b2_cloud_set_points", "b2_cloud_set_points_f32", "b2_cloud_size",
     "b2_cloud_get_points", "b2_cloud_get_normals", "b2_cloud_set_normals", "b2_cloud_voxel_down_sample",
     "b2_cloud_estimate_normals", "b2_cloud_transform", "b2_cloud_last_gpu_ms",
@@ -110,6 +142,12 @@ def lib():
     L.b2_scan_project.argtypes = [vp, vp, sz, vp, vp, vp, vp, i32, C.c_double, i32, C.POINTER(sz), vp, vp, vp, vp, vp, vp, vp]
     L.b2_scan_extract_features.argtypes = [vp, C.POINTER(sz), vp, vp, C.POINTER(sz), vp, vp, vp, vp]
     L.b2_scan_last_gpu_ms.argtypes = [vp, pf]
+    L.b2_cloud_info_parse.argtypes = [vp, sz, C.POINTER(CloudInfoView)]
+    L.b2_scan_write_cloud_info.argtypes = [vp, C.POINTER(CloudInfoMeta), i32, vp, sz, C.POINTER(sz)]
+    L.b2_scan_set_from_cloud_info.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.b2_s2m_set_scan_downsampled.argtypes = [vp, vp, vp, sz, sz, vp, vp, sz, sz, C.POINTER(sz), C.POINTER(sz)]
+    L.b2_s2m_set_scan_from_front_end.argtypes = [vp, vp, vp, vp, C.POINTER(sz), C.POINTER(sz)]
+    L.b2_s2m_get_scan.argtypes = [vp, i32, vp, sz, C.POINTER(sz)]
     pd, dbl = C.POINTER(C.c_double), C.c_double
     L.b2_cloud_create.argtypes = [C.POINTER(vp)]
     L.b2_cloud_destroy.argtypes = [vp]

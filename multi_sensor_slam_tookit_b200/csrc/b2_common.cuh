@@ -116,6 +116,9 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
                      size_t out_capacity, uint32_t* m_out, int* refused, int32_t* d_vop);
 const void* voxel_out_dev(b2_voxel_s* h);
 cudaStream_t voxel_stream(b2_voxel_s* h);
+int voxel_filter_host_to_dev(b2_voxel_s* h, const void* in, size_t in_stride, size_t n, uint32_t* m_out);
+// per-scan front end: cornerCloud / surfaceCloud of the last b2_scan_extract_features, packed xyzi in device memory
+int scan_features_dev(b2_scan_s* h, const void** d_corner, size_t* n_corner, const void** d_surf, size_t* n_surf);
 // scan-to-map: index the two map clouds from device memory (packed xyzi, 16-byte stride)
 int s2m_set_map_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf);
 // pcl::getTransformation(x, y, z, roll, pitch, yaw) in float, row-major 3x4 (pose6 = roll, pitch, yaw, x, y, z)

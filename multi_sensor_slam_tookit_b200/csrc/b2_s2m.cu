@@ -567,17 +567,10 @@ static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, f
     return a;
 }
 
-static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cstride, const int32_t* coff,
-                           const void* surf, size_t sstride, const int32_t* soff) {
-    if (batch < 1 || batch > h->prm.max_batch) { set_error("set_scan: batch %d outside [1, %d]", batch, h->prm.max_batch); return B2_ERR_ARG; }
-    h->h_off_c.assign(coff, coff + batch + 1);
-    h->h_off_s.assign(soff, soff + batch + 1);
-    for (int b = 0; b < batch; b++)
-        if (coff[b + 1] < coff[b] || soff[b + 1] < soff[b]) { set_error("set_scan: offsets must be non-decreasing"); return B2_ERR_ARG; }
-    h->n_c = (size_t)coff[batch]; h->n_s = (size_t)soff[batch];
-    if ((h->n_c && !corner) || (h->n_s && !surf)) { set_error("set_scan: null feature array"); return B2_ERR_ARG; }
-    B2_CHECK(upload_points(h, h->raw_c, h->scan_c, corner, cstride, h->n_c));
-    B2_CHECK(upload_points(h, h->raw_s, h->scan_s, surf, sstride, h->n_s));
+// offsets, CTA counts and per-scan buffers for the features already sitting in scan_c / scan_s
+static int set_scan_finish(b2_s2m_s* h, int batch) {
+    const int32_t* coff = h->h_off_c.data();
+    const int32_t* soff = h->h_off_s.data();
     B2_CHECK(h->off_c.reserve((batch + 1) * sizeof(int)));
     B2_CHECK(h->off_s.reserve((batch + 1) * sizeof(int)));
     B2_CUDA(cudaMemcpyAsync(h->off_c.p, h->h_off_c.data(), (batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
@@ -607,11 +600,37 @@ static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cs
     return B2_OK;
 }
 
+
+static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cstride, const int32_t* coff,
+                           const void* surf, size_t sstride, const int32_t* soff) {
+    if (batch < 1 || batch > h->prm.max_batch) { set_error("set_scan: batch %d outside [1, %d]", batch, h->prm.max_batch); return B2_ERR_ARG; }
+    h->h_off_c.assign(coff, coff + batch + 1);
+    h->h_off_s.assign(soff, soff + batch + 1);
+    for (int b = 0; b < batch; b++)
+        if (coff[b + 1] < coff[b] || soff[b + 1] < soff[b]) { set_error("set_scan: offsets must be non-decreasing"); return B2_ERR_ARG; }
+    h->n_c = (size_t)coff[batch]; h->n_s = (size_t)soff[batch];
+    if ((h->n_c && !corner) || (h->n_s && !surf)) { set_error("set_scan: null feature array"); return B2_ERR_ARG; }
+    B2_CHECK(upload_points(h, h->raw_c, h->scan_c, corner, cstride, h->n_c));
+    B2_CHECK(upload_points(h, h->raw_s, h->scan_s, surf, sstride, h->n_s));
+    return set_scan_finish(h, batch);
+}
+
 namespace b2 {
 
 void pose_to_affine_host(const float pose6[6], float xf[12]) {
     float trig[6];
     host_prepare_pose(pose6, xf, trig);
+}
+
+// laserCloudCornerLastDS / laserCloudSurfLastDS handed over in device memory (packed xyzi); copies are ordered on h->stream
+int s2m_set_scan_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf) {
+    if (!h || n_corner > 0x7fffffff || n_surf > 0x7fffffff) return B2_ERR_ARG;
+    h->h_off_c.assign({0, (int32_t)n_corner});
+    h->h_off_s.assign({0, (int32_t)n_surf});
+    h->n_c = n_corner; h->n_s = n_surf;
+    if (n_corner) { B2_CHECK(h->scan_c.reserve(n_corner * sizeof(float4))); B2_CUDA(cudaMemcpyAsync(h->scan_c.p, d_corner, n_corner * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream)); }
+    if (n_surf) { B2_CHECK(h->scan_s.reserve(n_surf * sizeof(float4))); B2_CUDA(cudaMemcpyAsync(h->scan_s.p, d_surf, n_surf * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream)); }
+    return set_scan_finish(h, 1);
 }
 
 // kdtreeCornerFromMap->setInputCloud / kdtreeSurfFromMap->setInputCloud on clouds that already live in device memory
@@ -698,6 +717,51 @@ int b2_s2m_set_scan_batch(b2_s2m_t h, int batch, const void* corner, size_t cstr
                           const void* surf, size_t sstride, const int32_t* soff) {
     if (!h || !coff || !soff || cstride < 16 || sstride < 16 || (cstride & 3) || (sstride & 3)) { set_error("b2_s2m_set_scan_batch: bad argument"); return B2_ERR_ARG; }
     return set_scan_common(h, batch, corner, cstride, coff, surf, sstride, soff);
+}
+
+// mapOptimization::laserCloudInfoHandler's two fromROSMsg calls (mapOptmization.cpp:245-246) + downsampleCurrentScan (:940-958)
+int b2_s2m_set_scan_downsampled(b2_s2m_t h, b2_voxel_t ds_corner, const void* corner, size_t cstride, size_t n_corner,
+                                b2_voxel_t ds_surf, const void* surf, size_t sstride, size_t n_surf, size_t* n_corner_ds, size_t* n_surf_ds) {
+    if (!h || !ds_corner || !ds_surf || ds_corner == ds_surf || (n_corner && !corner) || (n_surf && !surf) || cstride < 16 || sstride < 16 ||
+        (cstride & 3) || (sstride & 3) || n_corner > 0x7ffffff0ull || n_surf > 0x7ffffff0ull) {
+        set_error("b2_s2m_set_scan_downsampled: bad argument"); return B2_ERR_ARG;
+    }
+    if (h->prm.max_batch < 1) return B2_ERR_STATE;
+    uint32_t mc = 0, ms = 0;
+    B2_CHECK(voxel_filter_host_to_dev(ds_corner, corner, cstride, n_corner, &mc));
+    B2_CHECK(voxel_filter_host_to_dev(ds_surf, surf, sstride, n_surf, &ms));
+    B2_CUDA(cudaStreamSynchronize(voxel_stream(ds_corner)));
+    B2_CUDA(cudaStreamSynchronize(voxel_stream(ds_surf)));
+    if (n_corner_ds) *n_corner_ds = mc;
+    if (n_surf_ds) *n_surf_ds = ms;
+    return s2m_set_scan_device(h, voxel_out_dev(ds_corner), mc, voxel_out_dev(ds_surf), ms);
+}
+
+// the same hand-off when featureExtraction and mapOptimization share the process: cornerCloud / surfaceCloud stay in HBM
+int b2_s2m_set_scan_from_front_end(b2_s2m_t h, b2_scan_t scan, b2_voxel_t ds_corner, b2_voxel_t ds_surf, size_t* n_corner_ds, size_t* n_surf_ds) {
+    if (!h || !scan || !ds_corner || !ds_surf || ds_corner == ds_surf) { set_error("b2_s2m_set_scan_from_front_end: bad argument"); return B2_ERR_ARG; }
+    const void *dc = nullptr, *dsf = nullptr; size_t nc = 0, ns = 0;
+    B2_CHECK(scan_features_dev(scan, &dc, &nc, &dsf, &ns));
+    uint32_t mc = 0, ms = 0; int refused = 0;
+    B2_CHECK(voxel_filter_dev(ds_corner, reinterpret_cast<const unsigned char*>(dc), 16, nc, 4, 16, std::max<size_t>(nc, 1), &mc, &refused, nullptr));
+    B2_CHECK(voxel_filter_dev(ds_surf, reinterpret_cast<const unsigned char*>(dsf), 16, ns, 4, 16, std::max<size_t>(ns, 1), &ms, &refused, nullptr));
+    B2_CUDA(cudaStreamSynchronize(voxel_stream(ds_corner)));
+    B2_CUDA(cudaStreamSynchronize(voxel_stream(ds_surf)));
+    if (n_corner_ds) *n_corner_ds = mc;
+    if (n_surf_ds) *n_surf_ds = ms;
+    return s2m_set_scan_device(h, voxel_out_dev(ds_corner), mc, voxel_out_dev(ds_surf), ms);
+}
+
+int b2_s2m_get_scan(b2_s2m_t h, int which, float* xyzi, size_t capacity, size_t* n) {
+    if (!h || !n || (which != 0 && which != 1)) { set_error("b2_s2m_get_scan: bad argument"); return B2_ERR_ARG; }
+    if (!h->have_scan) { set_error("b2_s2m_get_scan: no scan set"); return B2_ERR_STATE; }
+    const size_t cnt = which ? h->n_s : h->n_c;
+    *n = cnt;
+    if (!xyzi) return B2_OK;
+    if (capacity < cnt) { set_error("b2_s2m_get_scan: %zu points, capacity %zu", cnt, capacity); return B2_ERR_CAPACITY; }
+    if (cnt) B2_CUDA(cudaMemcpyAsync(xyzi, which ? h->scan_s.p : h->scan_c.p, cnt * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    return B2_OK;
 }
 
 int b2_s2m_set_state(b2_s2m_t h, int degenerate, const float matP[36]) {

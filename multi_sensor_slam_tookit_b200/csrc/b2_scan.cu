@@ -489,8 +489,9 @@ struct b2_scan_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf raw, imu, winner, small, range_mat, full_cloud, extracted, col_ind, pt_range, rings;
     DevBuf curv, picked, label, corner_idx, surf_idx, surf_ds, corner_out, corner_idx_out, surf_out;
-    int n_raw = 0, M = 0;
-    bool projected = false;
+    DevBuf wire;                          // cloud_info message staging (device)
+    int n_raw = 0, M = 0, nc = 0, ns = 0;
+    bool projected = false, featured = false;
     float last_ms = 0.f;
 };
 
@@ -523,12 +524,25 @@ int b2_scan_create(b2_scan_t* out, const b2_scan_params* params) {
 int b2_scan_destroy(b2_scan_t h) {
     if (!h) return B2_ERR_ARG;
     DevBuf* bufs[] = {&h->raw, &h->imu, &h->winner, &h->small, &h->range_mat, &h->full_cloud, &h->extracted, &h->col_ind, &h->pt_range, &h->rings,
-                      &h->curv, &h->picked, &h->label, &h->corner_idx, &h->surf_idx, &h->surf_ds, &h->corner_out, &h->corner_idx_out, &h->surf_out};
+                      &h->curv, &h->picked, &h->label, &h->corner_idx, &h->surf_idx, &h->surf_ds, &h->corner_out, &h->corner_idx_out, &h->surf_out, &h->wire};
     for (DevBuf* b : bufs) b->release();
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
+    return B2_OK;
+}
+
+static ScanDev scan_dev(const b2_scan_params& p);
+// cloudInfo.{startRingIndex,endRingIndex,pointColInd,pointRange}.assign(.., 0) of allocateMemory (imageProjection.cpp:116-120):
+// entries past the current scan's count keep what an earlier scan left there, and start at zero
+static int scan_reserve_info(b2_scan_s* h, const ScanDev& s, cudaStream_t st) {
+    const size_t cells = (size_t)s.n_scan * s.H;
+    B2_CHECK(h->small.reserve(256));
+    if (h->col_ind.cap < cells * 4) { B2_CHECK(h->col_ind.reserve(cells * 4)); B2_CUDA(cudaMemsetAsync(h->col_ind.p, 0, cells * 4, st)); }
+    if (h->pt_range.cap < cells * 4) { B2_CHECK(h->pt_range.reserve(cells * 4)); B2_CUDA(cudaMemsetAsync(h->pt_range.p, 0, cells * 4, st)); }
+    if (h->rings.cap < (size_t)s.n_scan * 3 * 4 + 64) { B2_CHECK(h->rings.reserve((size_t)s.n_scan * 3 * 4 + 64)); B2_CUDA(cudaMemsetAsync(h->rings.p, 0, (size_t)s.n_scan * 3 * 4, st)); }
+    B2_CHECK(h->extracted.reserve(cells * 16));
     return B2_OK;
 }
 
@@ -557,9 +571,7 @@ int b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n, const double* imu
     B2_CHECK(h->range_mat.reserve((size_t)cells * 4));
     B2_CHECK(h->full_cloud.reserve((size_t)cells * 16));
     B2_CHECK(h->extracted.reserve((size_t)cells * 16));
-    B2_CHECK(h->col_ind.reserve((size_t)cells * 4));
-    B2_CHECK(h->pt_range.reserve((size_t)cells * 4));
-    B2_CHECK(h->rings.reserve((size_t)s.n_scan * 3 * 4 + 64));
+    B2_CHECK(scan_reserve_info(h, s, st));
     const int ni = std::max(n_imu, 1);
     B2_CHECK(h->imu.reserve((size_t)ni * 4 * 8));
     double* d_imu = h->imu.as<double>();
@@ -606,7 +618,7 @@ int b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n, const double* imu
         B2_CUDA(cudaStreamSynchronize(st));
     }
     B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
-    h->n_raw = (int)n; h->M = M; h->projected = true;
+    h->n_raw = (int)n; h->M = M; h->projected = true; h->featured = false;
     *n_extracted = (size_t)M;
     return B2_OK;
 }
@@ -671,6 +683,7 @@ int b2_scan_extract_features(b2_scan_t h, size_t* n_corner, float* corner_xyzi, 
     float ms = 0.f;
     B2_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
+    h->nc = tot[0]; h->ns = tot[1]; h->featured = true;
     *n_corner = (size_t)tot[0]; *n_surf = (size_t)tot[1];
     return B2_OK;
 }
@@ -678,6 +691,300 @@ int b2_scan_extract_features(b2_scan_t h, size_t* n_corner, float* corner_xyzi, 
 int b2_scan_last_gpu_ms(b2_scan_t h, float* ms) {
     if (!h || !ms) return B2_ERR_ARG;
     *ms = h->last_ms;
+    return B2_OK;
+}
+
+
+// ================================================================================================================
+// cloud_info wire format: msg/cloud_info.msg:1-35, ROS1 serialisation — little endian, arrays and
+// strings prefixed by a u32 count, sensor_msgs/PointCloud2 = Header, height, width, PointField[] {name, offset, datatype,
+// count}, is_bigendian, point_step, row_step, u8[] data, is_dense.
+// ================================================================================================================
+}  // extern "C"
+
+namespace b2 {
+
+int scan_features_dev(b2_scan_s* h, const void** d_corner, size_t* n_corner, const void** d_surf, size_t* n_surf) {
+    if (!h || !h->featured) { set_error("front end: b2_scan_extract_features has not run"); return B2_ERR_STATE; }
+    *d_corner = h->corner_out.p; *n_corner = (size_t)h->nc; *d_surf = h->surf_out.p; *n_surf = (size_t)h->ns;
+    return B2_OK;
+}
+
+struct WireSect { const void* src; unsigned long long off; unsigned n; int kind; };   // kind 0: 4-byte words, 1: float4 -> 32-byte PointXYZI
+struct WireArgs { WireSect s[7]; int n_sect; unsigned char* dst; };
+
+__device__ __forceinline__ void wire_put(unsigned char* p, uint32_t w) {
+    if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) *reinterpret_cast<uint32_t*>(p) = w;
+    else { p[0] = (unsigned char)w; p[1] = (unsigned char)(w >> 8); p[2] = (unsigned char)(w >> 16); p[3] = (unsigned char)(w >> 24); }
+}
+__device__ __forceinline__ uint32_t wire_get(const unsigned char* p) {
+    if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) return *reinterpret_cast<const uint32_t*>(p);
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// One launch packs every payload section of the message at its wire offset (blockIdx.y = section).
+__global__ void __launch_bounds__(256) k_wire_pack(WireArgs a) {
+    const WireSect sc = a.s[blockIdx.y];
+    unsigned char* base = a.dst + sc.off;
+    if (sc.kind == 0) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.src);
+        for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < sc.n; i += gridDim.x * blockDim.x) wire_put(base + (size_t)i * 4, src[i]);
+    } else {
+        // eight threads per point, one word each: x y z 1.0f | intensity 0 0 0   (pcl::PointXYZI, 32 bytes)
+        const float4* src = reinterpret_cast<const float4*>(sc.src);
+        const unsigned long long words = (unsigned long long)sc.n * 8;
+        for (unsigned long long t = blockIdx.x * blockDim.x + threadIdx.x; t < words; t += (unsigned long long)gridDim.x * blockDim.x) {
+            const unsigned i = (unsigned)(t >> 3), w = (unsigned)(t & 7);
+            const float4 p = src[i];
+            const uint32_t v = w == 0 ? __float_as_uint(p.x) : w == 1 ? __float_as_uint(p.y) : w == 2 ? __float_as_uint(p.z)
+                             : w == 3 ? 0x3f800000u : w == 4 ? __float_as_uint(p.w) : 0u;
+            wire_put(base + t * 4, v);
+        }
+    }
+}
+
+struct UnwireArgs {
+    const unsigned char* msg;
+    unsigned long long off_start, off_end, off_col, off_range, off_data;
+    unsigned n_ring, n_col, n_range, n_pts, point_step;
+    int ox, oy, oz, oi;
+    int *d_start, *d_end, *col_ind, *total;
+    float* pt_range;
+    float4* extracted;
+};
+
+// blockIdx.y: 0 ring tables + count, 1 pointColInd, 2 pointRange, 3 the deskewed cloud (pcl::fromROSMsg by field name)
+__global__ void __launch_bounds__(256) k_wire_unpack(UnwireArgs a) {
+    const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, step = gridDim.x * blockDim.x;
+    if (blockIdx.y == 0) {
+        for (unsigned i = tid; i < a.n_ring; i += step) {
+            a.d_start[i] = (int)wire_get(a.msg + a.off_start + (size_t)i * 4);
+            a.d_end[i] = (int)wire_get(a.msg + a.off_end + (size_t)i * 4);
+        }
+        if (tid == 0) *a.total = (int)a.n_pts;
+    } else if (blockIdx.y == 1) {
+        for (unsigned i = tid; i < a.n_col; i += step) a.col_ind[i] = (int)wire_get(a.msg + a.off_col + (size_t)i * 4);
+    } else if (blockIdx.y == 2) {
+        for (unsigned i = tid; i < a.n_range; i += step) a.pt_range[i] = __uint_as_float(wire_get(a.msg + a.off_range + (size_t)i * 4));
+    } else {
+        for (unsigned i = tid; i < a.n_pts; i += step) {
+            const unsigned char* r = a.msg + a.off_data + (size_t)i * a.point_step;
+            float4 p;
+            p.x = a.ox >= 0 ? __uint_as_float(wire_get(r + a.ox)) : 0.f;
+            p.y = a.oy >= 0 ? __uint_as_float(wire_get(r + a.oy)) : 0.f;
+            p.z = a.oz >= 0 ? __uint_as_float(wire_get(r + a.oz)) : 0.f;
+            p.w = a.oi >= 0 ? __uint_as_float(wire_get(r + a.oi)) : 0.f;
+            a.extracted[i] = p;
+        }
+    }
+}
+
+namespace {
+
+// Serialiser over an optional output buffer: always advances, writes only when there is room (so the same walk sizes
+// the message, places the headers, and records where the device-packed payloads go).
+struct Wr {
+    unsigned char* p; size_t cap; size_t off = 0;
+    Wr(void* out, size_t c) : p(reinterpret_cast<unsigned char*>(out)), cap(c) {}
+    void raw(const void* s, size_t n) { if (p && off + n <= cap && n) memcpy(p + off, s, n); off += n; }
+    void u8(uint8_t v) { raw(&v, 1); }
+    void u32(uint32_t v) { raw(&v, 4); }
+    void i64(int64_t v) { raw(&v, 8); }
+    void f32(float v) { raw(&v, 4); }
+    void str(const char* s) { const uint32_t n = s ? (uint32_t)strlen(s) : 0; u32(n); raw(s, n); }
+    size_t skip(size_t n) { const size_t o = off; off += n; return o; }
+};
+
+void wr_header(Wr& w, uint32_t seq, uint32_t sec, uint32_t nsec, const char* frame) { w.u32(seq); w.u32(sec); w.u32(nsec); w.str(frame); }
+
+// pcl::toROSMsg(pcl::PointCloud<pcl::PointXYZI>) + publishCloud's stamp / frame_id (utility.h:286-295); returns the data offset
+size_t wr_cloud_xyzi(Wr& w, const b2_cloud_info_meta& m, uint32_t n) {
+    wr_header(w, 0, m.stamp_sec, m.stamp_nsec, m.cloud_frame_id);
+    w.u32(1); w.u32(n);                                    // height, width
+    w.u32(4);
+    static const struct { const char* name; uint32_t off; } F[4] = {{"x", 0}, {"y", 4}, {"z", 8}, {"intensity", 16}};
+    for (const auto& f : F) { w.str(f.name); w.u32(f.off); w.u8(7 /* FLOAT32 */); w.u32(1); }
+    w.u8(0);                                               // is_bigendian
+    w.u32(32); w.u32(32u * n);                             // point_step, row_step
+    w.u32(32u * n);
+    const size_t at = w.skip((size_t)32 * n);
+    w.u8(1);                                               // is_dense
+    return at;
+}
+
+void wr_cloud_empty(Wr& w) {                               // default-constructed sensor_msgs::PointCloud2
+    wr_header(w, 0, 0, 0, nullptr);
+    w.u32(0); w.u32(0); w.u32(0); w.u8(0); w.u32(0); w.u32(0); w.u32(0); w.u8(0);
+}
+
+struct Rd {
+    const unsigned char* p; size_t n; size_t off = 0; bool ok = true;
+    bool need(size_t k) { if (!ok || k > n - off) { ok = false; return false; } return true; }
+    uint8_t u8() { if (!need(1)) return 0; return p[off++]; }
+    uint32_t u32() { uint32_t v = 0; if (need(4)) { memcpy(&v, p + off, 4); off += 4; } return v; }
+    int64_t i64() { int64_t v = 0; if (need(8)) { memcpy(&v, p + off, 8); off += 8; } return v; }
+    float f32() { float v = 0; if (need(4)) { memcpy(&v, p + off, 4); off += 4; } return v; }
+    const unsigned char* bytes(size_t k) { if (!need(k)) return nullptr; const unsigned char* r = p + off; off += k; return r; }
+    const unsigned char* arr(uint32_t* count, size_t elem) { *count = u32(); if (!ok) return nullptr; if ((uint64_t)*count * elem > n - off) { ok = false; return nullptr; } return bytes((size_t)*count * elem); }
+};
+
+void rd_cloud(Rd& r, b2_cloud2_view* c) {
+    memset(c, 0, sizeof(*c));
+    c->off_x = c->off_y = c->off_z = c->off_intensity = -1;
+    r.u32(); r.u32(); r.u32();
+    uint32_t fl = 0; r.arr(&fl, 1);
+    c->height = r.u32(); c->width = r.u32();
+    c->n_fields = r.u32();
+    for (uint32_t f = 0; r.ok && f < c->n_fields; f++) {
+        uint32_t nl = 0; const unsigned char* name = r.arr(&nl, 1);
+        const uint32_t off = r.u32(); const uint8_t dt = r.u8(); r.u32();
+        if (!r.ok) break;
+        auto is = [&](const char* s) { return nl == strlen(s) && memcmp(name, s, nl) == 0; };
+        if (dt == 7) {
+            if (is("x")) c->off_x = (int32_t)off; else if (is("y")) c->off_y = (int32_t)off;
+            else if (is("z")) c->off_z = (int32_t)off; else if (is("intensity")) c->off_intensity = (int32_t)off;
+        }
+    }
+    c->is_bigendian = r.u8(); c->point_step = r.u32(); c->row_step = r.u32();
+    uint32_t nd = 0; c->data = r.arr(&nd, 1);
+    c->is_dense = r.u8();
+    if (r.ok && (uint64_t)c->width * c->height * c->point_step > nd) r.ok = false;
+}
+
+}  // namespace
+}  // namespace b2
+
+extern "C" {
+
+int b2_cloud_info_parse(const void* msg, size_t n_bytes, b2_cloud_info_view* v) {
+    if (!msg || !v) { set_error("b2_cloud_info_parse: null argument"); return B2_ERR_ARG; }
+    memset(v, 0, sizeof(*v));
+    Rd r{reinterpret_cast<const unsigned char*>(msg), n_bytes};
+    v->seq = r.u32(); v->stamp_sec = r.u32(); v->stamp_nsec = r.u32();
+    v->frame_id = reinterpret_cast<const char*>(r.arr(&v->frame_id_len, 1));
+    v->start_ring_index = r.arr(&v->n_start_ring_index, 4);
+    v->end_ring_index = r.arr(&v->n_end_ring_index, 4);
+    v->point_col_ind = r.arr(&v->n_point_col_ind, 4);
+    v->point_range = r.arr(&v->n_point_range, 4);
+    v->imu_available = r.i64(); v->odom_available = r.i64();
+    v->imu_roll_init = r.f32(); v->imu_pitch_init = r.f32(); v->imu_yaw_init = r.f32();
+    v->initial_guess_x = r.f32(); v->initial_guess_y = r.f32(); v->initial_guess_z = r.f32();
+    v->initial_guess_roll = r.f32(); v->initial_guess_pitch = r.f32(); v->initial_guess_yaw = r.f32();
+    b2_cloud2_view* clouds[7] = {&v->cloud_deskewed, &v->cloud_corner, &v->cloud_surface, &v->key_frame_cloud, &v->key_frame_color,
+                                 &v->key_frame_poses, &v->key_frame_map};
+    for (b2_cloud2_view* c : clouds) rd_cloud(r, c);
+    if (!r.ok) { set_error("b2_cloud_info_parse: truncated or malformed message (%zu bytes, stopped at %zu)", n_bytes, r.off); return B2_ERR_ARG; }
+    if (r.off != n_bytes) { set_error("b2_cloud_info_parse: %zu trailing bytes", n_bytes - r.off); return B2_ERR_ARG; }
+    return B2_OK;
+}
+
+int b2_scan_write_cloud_info(b2_scan_t h, const b2_cloud_info_meta* meta, int stage, void* out, size_t capacity, size_t* n_bytes) {
+    if (!h || !meta || !n_bytes || (stage != 0 && stage != 1)) { set_error("b2_scan_write_cloud_info: bad argument"); return B2_ERR_ARG; }
+    if (!h->projected || (stage == 1 && !h->featured)) { set_error("b2_scan_write_cloud_info: stage %d needs b2_scan_%s first", stage, stage ? "extract_features" : "project"); return B2_ERR_STATE; }
+    const ScanDev s = scan_dev(h->prm);
+    const uint32_t cells = (uint32_t)(s.n_scan * s.H);
+    const int* ring_count = h->rings.as<int>();
+    WireArgs a{}; a.n_sect = 0;
+    size_t total = 0;
+    // one walk with out == nullptr sizes the message and finds the payload offsets; the second one writes the small fields
+    for (int pass = 0; pass < 2; pass++) {
+        Wr w(pass ? out : nullptr, capacity);
+        a.n_sect = 0;
+        auto sect = [&](const void* src, size_t off, unsigned n, int kind) { if (n) { a.s[a.n_sect].src = src; a.s[a.n_sect].off = off; a.s[a.n_sect].n = n; a.s[a.n_sect].kind = kind; a.n_sect++; } };
+        wr_header(w, meta->seq, meta->stamp_sec, meta->stamp_nsec, meta->frame_id);
+        if (stage == 0) {
+            w.u32((uint32_t)s.n_scan); sect(ring_count + s.n_scan, w.skip((size_t)s.n_scan * 4), (unsigned)s.n_scan, 0);
+            w.u32((uint32_t)s.n_scan); sect(ring_count + 2 * s.n_scan, w.skip((size_t)s.n_scan * 4), (unsigned)s.n_scan, 0);
+            w.u32(cells); sect(h->col_ind.p, w.skip((size_t)cells * 4), cells, 0);
+            w.u32(cells); sect(h->pt_range.p, w.skip((size_t)cells * 4), cells, 0);
+        } else {
+            w.u32(0); w.u32(0); w.u32(0); w.u32(0);                    // freeCloudInfoMemory (featureExtraction.cpp:240-246)
+        }
+        w.i64(meta->imu_available); w.i64(meta->odom_available);
+        w.f32(meta->imu_roll_init); w.f32(meta->imu_pitch_init); w.f32(meta->imu_yaw_init);
+        w.f32(meta->initial_guess_x); w.f32(meta->initial_guess_y); w.f32(meta->initial_guess_z);
+        w.f32(meta->initial_guess_roll); w.f32(meta->initial_guess_pitch); w.f32(meta->initial_guess_yaw);
+        sect(h->extracted.p, wr_cloud_xyzi(w, *meta, (uint32_t)h->M), (unsigned)h->M, 1);
+        if (stage == 1) {
+            sect(h->corner_out.p, wr_cloud_xyzi(w, *meta, (uint32_t)h->nc), (unsigned)h->nc, 1);
+            sect(h->surf_out.p, wr_cloud_xyzi(w, *meta, (uint32_t)h->ns), (unsigned)h->ns, 1);
+        } else { wr_cloud_empty(w); wr_cloud_empty(w); }
+        for (int k = 0; k < 4; k++) wr_cloud_empty(w);                 // key_frame_cloud / color / poses / map
+        total = w.off;
+        if (pass == 0) {
+            *n_bytes = total;
+            if (!out) return B2_OK;
+            if (capacity < total) { set_error("b2_scan_write_cloud_info: message is %zu bytes, capacity %zu", total, capacity); return B2_ERR_CAPACITY; }
+            // payloads: packed on the device at their wire offsets, one copy back; the header walk then fills the gaps
+            cudaStream_t st = h->stream;
+            B2_CHECK(h->wire.reserve(total + 16));
+            a.dst = h->wire.as<unsigned char>();
+            B2_CUDA(cudaEventRecord(h->ev0, st));
+            if (a.n_sect) {
+                unsigned most = 0;
+                for (int k = 0; k < a.n_sect; k++) most = std::max(most, a.s[k].kind ? a.s[k].n * 8u : a.s[k].n);
+                dim3 grid(std::max(1u, std::min((most + 255u) / 256u, (unsigned)device_sm_count() * 8u)), (unsigned)a.n_sect);
+                k_wire_pack<<<grid, 256, 0, st>>>(a); count_launch();
+                B2_CUDA(cudaGetLastError());
+            }
+            B2_CUDA(cudaEventRecord(h->ev1, st));
+            // from the first payload byte to the last one: the gaps in between are rewritten by the second walk
+            if (a.n_sect) {
+                const size_t lo = a.s[0].off, hi = a.s[a.n_sect - 1].off + (size_t)a.s[a.n_sect - 1].n * (a.s[a.n_sect - 1].kind ? 32 : 4);
+                B2_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(out) + lo, a.dst + lo, hi - lo, cudaMemcpyDeviceToHost, st));
+            }
+            B2_CUDA(cudaStreamSynchronize(st));
+            B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+        }
+    }
+    return B2_OK;
+}
+
+int b2_scan_set_from_cloud_info(b2_scan_t h, const void* msg, size_t n_bytes, size_t* n_extracted) {
+    if (!h || !msg) { set_error("b2_scan_set_from_cloud_info: null argument"); return B2_ERR_ARG; }
+    b2_cloud_info_view v;
+    B2_CHECK(b2_cloud_info_parse(msg, n_bytes, &v));
+    const ScanDev s = scan_dev(h->prm);
+    const size_t cells = (size_t)s.n_scan * s.H;
+    const b2_cloud2_view& c = v.cloud_deskewed;
+    const size_t M = (size_t)c.width * c.height;
+    if (v.n_start_ring_index != (uint32_t)s.n_scan || v.n_end_ring_index != (uint32_t)s.n_scan) {
+        set_error("b2_scan_set_from_cloud_info: %u / %u ring entries, N_SCAN is %d", v.n_start_ring_index, v.n_end_ring_index, s.n_scan); return B2_ERR_ARG;
+    }
+    if (M > cells || v.n_point_col_ind < M || v.n_point_range < M || v.n_point_col_ind > cells || v.n_point_range > cells) {
+        set_error("b2_scan_set_from_cloud_info: %zu points, %u / %u per-point entries, range image has %zu cells", M, v.n_point_col_ind, v.n_point_range, cells); return B2_ERR_ARG;
+    }
+    if (M && (c.is_bigendian || c.off_x < 0 || c.off_y < 0 || c.off_z < 0 || (c.point_step < 12))) {
+        set_error("b2_scan_set_from_cloud_info: cloud_deskewed needs little-endian FLOAT32 x, y, z fields"); return B2_ERR_ARG;
+    }
+    const int offs[4] = {c.off_x, c.off_y, c.off_z, c.off_intensity};
+    for (int o : offs) if (M && o >= 0 && (uint32_t)o + 4 > c.point_step) { set_error("b2_scan_set_from_cloud_info: field offset %d outside point_step %u", o, c.point_step); return B2_ERR_ARG; }
+    cudaStream_t st = h->stream;
+    B2_CHECK(scan_reserve_info(h, s, st));
+    B2_CHECK(h->wire.reserve(n_bytes + 16));
+    B2_CUDA(cudaEventRecord(h->ev0, st));
+    B2_CUDA(cudaMemcpyAsync(h->wire.p, msg, n_bytes, cudaMemcpyHostToDevice, st));
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(msg);
+    auto at = [&](const void* p) { return p ? (unsigned long long)(reinterpret_cast<const unsigned char*>(p) - base) : 0ull; };
+    UnwireArgs a{};
+    a.msg = h->wire.as<unsigned char>();
+    a.off_start = at(v.start_ring_index); a.off_end = at(v.end_ring_index); a.off_col = at(v.point_col_ind); a.off_range = at(v.point_range);
+    a.off_data = at(c.data);
+    a.n_ring = (unsigned)s.n_scan; a.n_col = v.n_point_col_ind; a.n_range = v.n_point_range; a.n_pts = (unsigned)M; a.point_step = c.point_step;
+    a.ox = c.off_x; a.oy = c.off_y; a.oz = c.off_z; a.oi = c.off_intensity;
+    int* first_idx = h->small.as<int>();
+    int* ring_count = h->rings.as<int>();
+    a.total = first_idx + 1; a.d_start = ring_count + s.n_scan; a.d_end = ring_count + 2 * s.n_scan;
+    a.col_ind = h->col_ind.as<int>(); a.pt_range = h->pt_range.as<float>(); a.extracted = h->extracted.as<float4>();
+    const unsigned most = (unsigned)std::max<size_t>(std::max<size_t>(v.n_point_col_ind, v.n_point_range), std::max<size_t>(M, (size_t)s.n_scan));
+    dim3 grid(std::max(1u, std::min((most + 255u) / 256u, (unsigned)device_sm_count() * 8u)), 4);
+    k_wire_unpack<<<grid, 256, 0, st>>>(a); count_launch();
+    B2_CUDA(cudaGetLastError());
+    B2_CUDA(cudaEventRecord(h->ev1, st));
+    B2_CUDA(cudaStreamSynchronize(st));
+    B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->M = (int)M; h->n_raw = 0; h->projected = true; h->featured = false;
+    if (n_extracted) *n_extracted = M;
     return B2_OK;
 }
 

@@ -265,6 +265,17 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
 const void* voxel_out_dev(b2_voxel_s* h) { return h->out.p; }
 cudaStream_t voxel_stream(b2_voxel_s* h) { return h->stream; }
 
+// host cloud in, downsampled cloud left on the device (packed xyzi); the caller synchronises voxel_stream(h)
+int voxel_filter_host_to_dev(b2_voxel_s* h, const void* in, size_t in_stride, size_t n, uint32_t* m_out) {
+    *m_out = 0;
+    if (!(h->leaf[0] > 0.f)) { set_error("VoxelGrid: leaf size not set"); return B2_ERR_STATE; }
+    if (n == 0) return B2_OK;
+    B2_CHECK(h->raw.reserve(n * in_stride));
+    B2_CUDA(cudaMemcpyAsync(h->raw.p, in, n * in_stride, cudaMemcpyHostToDevice, h->stream));
+    int refused = 0;
+    return voxel_filter_dev(h, h->raw.as<unsigned char>(), in_stride, n, 4, 16, n, m_out, &refused, nullptr);
+}
+
 }  // namespace b2
 
 extern "C" {

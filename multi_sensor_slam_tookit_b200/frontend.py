@@ -4,6 +4,9 @@
                                      (liosam_ws/src/LIO-SAM/src/imageProjection.cpp:446-598)
   ScanFrontEnd.extractFeatures    <- FeatureExtraction::calculateSmoothness + markOccludedPoints + extractFeatures
                                      (liosam_ws/src/LIO-SAM/src/featureExtraction.cpp:81-238)
+  ScanFrontEnd.publishClouds / publishFeatureCloud / laserCloudInfoHandler  <- the lio_sam/cloud_info hand-offs between the
+                                     stages (imageProjection.cpp:600-605, featureExtraction.cpp:66-79, 240-258), ROS1 wire bytes
+  parse_cloud_info                <- host-only view of a serialised message
 Outputs carry the names of msg/cloud_info.msg. Everything computes on the GPU; there is no CPU path here.
 """
 import ctypes as C
@@ -86,3 +89,72 @@ class ScanFrontEnd:
         ms = C.c_float(0)
         capi.check(capi.lib().b2_scan_last_gpu_ms(self._h, C.byref(ms)))
         return ms.value
+
+    # ---- lio_sam/cloud_info between the stages
+    def _write(self, stage, meta):
+        m = cloud_info_meta(**(meta or {}))
+        n = C.c_size_t(0)
+        capi.check(capi.lib().b2_scan_write_cloud_info(self._h, C.byref(m), stage, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.uint8)
+        capi.check(capi.lib().b2_scan_write_cloud_info(self._h, C.byref(m), stage, capi.ptr(out), out.size, C.byref(n)))
+        return out
+
+    def publishClouds(self, **meta):
+        """ImageProjection::publishClouds (imageProjection.cpp:600-605): the deskew/cloud_info message bytes."""
+        return self._write(0, meta)
+
+    def publishFeatureCloud(self, **meta):
+        """FeatureExtraction::publishFeatureCloud (featureExtraction.cpp:248-258): the feature/cloud_info message bytes."""
+        return self._write(1, meta)
+
+    def laserCloudInfoHandler(self, msg):
+        """FeatureExtraction::laserCloudInfoHandler (:66-79) up to extractFeatures: load a deskew/cloud_info message."""
+        raw = np.ascontiguousarray(np.frombuffer(msg, np.uint8))
+        m = C.c_size_t(0)
+        capi.check(capi.lib().b2_scan_set_from_cloud_info(self._h, capi.ptr(raw), raw.size, C.byref(m)))
+        self.n_extracted = m.value
+        return self.extractFeatures()
+
+
+def cloud_info_meta(seq=0, stamp=(0, 0), frame_id="", lidarFrame="", imuAvailable=0, odomAvailable=0, imuRollInit=0.0,
+                    imuPitchInit=0.0, imuYawInit=0.0, initialGuess=(0.0,) * 6):
+    m = capi.CloudInfoMeta()
+    m.seq, m.stamp_sec, m.stamp_nsec = int(seq), int(stamp[0]), int(stamp[1])
+    m.frame_id, m.cloud_frame_id = frame_id.encode(), lidarFrame.encode()
+    m.imu_available, m.odom_available = int(imuAvailable), int(odomAvailable)
+    m.imu_roll_init, m.imu_pitch_init, m.imu_yaw_init = imuRollInit, imuPitchInit, imuYawInit
+    (m.initial_guess_x, m.initial_guess_y, m.initial_guess_z, m.initial_guess_roll, m.initial_guess_pitch,
+     m.initial_guess_yaw) = initialGuess
+    return m
+
+
+def parse_cloud_info(msg):
+    """Host-only: b2_cloud_info_parse on a serialised lio_sam/cloud_info. Returns a dict with the message's field names;
+    clouds come back as (n, point_step / 4) float32 arrays of the raw point records plus their field offsets."""
+    raw = np.ascontiguousarray(np.frombuffer(msg, np.uint8))
+    v = capi.CloudInfoView()
+    capi.check(capi.lib().b2_cloud_info_parse(capi.ptr(raw), raw.size, C.byref(v)))
+    base = raw.ctypes.data
+
+    def arr(p, n, dt):
+        return np.zeros(0, dt) if not n else raw[p - base:p - base + 4 * n].copy().view(dt)
+
+    def cloud(c):
+        n = c.width * c.height
+        pts = (raw[c.data - base:c.data - base + n * c.point_step].copy().view(np.float32).reshape(n, c.point_step // 4)
+               if n else np.zeros((0, max(c.point_step // 4, 1)), np.float32))
+        return dict(points=pts, width=c.width, height=c.height, point_step=c.point_step, row_step=c.row_step, n_fields=c.n_fields,
+                    offsets=(c.off_x, c.off_y, c.off_z, c.off_intensity), is_dense=c.is_dense, is_bigendian=c.is_bigendian)
+
+    return dict(seq=v.seq, stamp=(v.stamp_sec, v.stamp_nsec),
+                frame_id=bytes(raw[v.frame_id - base:v.frame_id - base + v.frame_id_len]).decode() if v.frame_id_len else "",
+                startRingIndex=arr(v.start_ring_index, v.n_start_ring_index, np.int32),
+                endRingIndex=arr(v.end_ring_index, v.n_end_ring_index, np.int32),
+                pointColInd=arr(v.point_col_ind, v.n_point_col_ind, np.int32),
+                pointRange=arr(v.point_range, v.n_point_range, np.float32),
+                imuAvailable=v.imu_available, odomAvailable=v.odom_available,
+                imuRollInit=v.imu_roll_init, imuPitchInit=v.imu_pitch_init, imuYawInit=v.imu_yaw_init,
+                initialGuess=(v.initial_guess_x, v.initial_guess_y, v.initial_guess_z, v.initial_guess_roll,
+                              v.initial_guess_pitch, v.initial_guess_yaw),
+                **{k: cloud(getattr(v, k)) for k in ("cloud_deskewed", "cloud_corner", "cloud_surface", "key_frame_cloud",
+                                                      "key_frame_color", "key_frame_poses", "key_frame_map")})

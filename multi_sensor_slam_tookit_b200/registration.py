@@ -125,6 +125,44 @@ class ScanToMapOptimizer:
         self._nc, self._ns = c.shape[0], s.shape[0]
         capi.check(capi.lib().b2_s2m_set_scan(self._h, capi.ptr(c), cs, c.shape[0], capi.ptr(s), ss, s.shape[0]))
 
+    def _scan_counts(self, nc, ns):
+        self._nc, self._ns = nc.value, ns.value
+        self.laserCloudCornerLastDSNum, self.laserCloudSurfLastDSNum = nc.value, ns.value
+
+    def setInputScanDownsampled(self, laserCloudCornerLast, laserCloudSurfLast, downSizeFilterCorner, downSizeFilterSurf):
+        """downsampleCurrentScan (mapOptmization.cpp:940-958): both VoxelGrids on the device, the result never leaves it."""
+        c, cs = capi.as_points(laserCloudCornerLast, 4)
+        s, ss = capi.as_points(laserCloudSurfLast, 4)
+        nc, ns = C.c_size_t(0), C.c_size_t(0)
+        capi.check(capi.lib().b2_s2m_set_scan_downsampled(self._h, downSizeFilterCorner._h, capi.ptr(c), cs, c.shape[0],
+                                                          downSizeFilterSurf._h, capi.ptr(s), ss, s.shape[0], C.byref(nc), C.byref(ns)))
+        self._scan_counts(nc, ns)
+
+    def laserCloudInfoHandler(self, msg, downSizeFilterCorner, downSizeFilterSurf):
+        """mapOptimization::laserCloudInfoHandler (:237-247) + downsampleCurrentScan on a serialised feature/cloud_info."""
+        from .frontend import parse_cloud_info
+        info = parse_cloud_info(msg)
+        self.setInputScanDownsampled(info["cloud_corner"]["points"], info["cloud_surface"]["points"], downSizeFilterCorner, downSizeFilterSurf)
+        return info
+
+    def setInputScanFromFrontEnd(self, front_end, downSizeFilterCorner, downSizeFilterSurf):
+        """The same hand-off inside one process: cornerCloud / surfaceCloud of ScanFrontEnd.extractFeatures stay in HBM."""
+        nc, ns = C.c_size_t(0), C.c_size_t(0)
+        capi.check(capi.lib().b2_s2m_set_scan_from_front_end(self._h, front_end._h, downSizeFilterCorner._h, downSizeFilterSurf._h,
+                                                             C.byref(nc), C.byref(ns)))
+        self._scan_counts(nc, ns)
+
+    def getInputScan(self):
+        """laserCloudCornerLastDS, laserCloudSurfLastDS as the optimiser holds them."""
+        out = []
+        for which in (0, 1):
+            n = C.c_size_t(0)
+            capi.check(capi.lib().b2_s2m_get_scan(self._h, which, None, 0, C.byref(n)))
+            a = np.empty((n.value, 4), np.float32)
+            capi.check(capi.lib().b2_s2m_get_scan(self._h, which, capi.ptr(a), n.value, C.byref(n)))
+            out.append(a)
+        return out
+
     def setInputScanBatch(self, corners, surfs):
         """corners / surfs: lists of (n_i, 4) clouds, one per scan."""
         co = np.zeros(len(corners) + 1, np.int32)

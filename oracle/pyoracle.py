@@ -472,3 +472,54 @@ def fuse_clouds(clouds, transforms, external_bounds=None, internal_bounds=None):
         v = fused[:, :3].astype(np.float64)
         keep &= ((v > hi) | (v < lo)).any(1)
     return fused[keep]
+
+
+# ---- lio_sam/cloud_info on the wire — ROS1 serialisation written out with struct, independent of the
+# C walk in csrc/b2_scan.cu. Follows msg/cloud_info.msg:1-35, sensor_msgs/PointCloud2 + PointField + std_msgs/Header, and
+# what pcl::toROSMsg produces for a pcl::PointXYZI cloud (utility.h:286-295). TEST INFRASTRUCTURE ONLY.
+def _ros_header(seq, stamp, frame_id):
+    import struct
+    f = frame_id.encode()
+    return struct.pack("<IIII", seq, stamp[0], stamp[1], len(f)) + f
+
+
+def _ros_cloud_xyzi(points_xyzi, stamp, frame_id):
+    import struct
+    p = np.ascontiguousarray(points_xyzi, np.float32).reshape(-1, 4)
+    n = len(p)
+    rec = np.zeros((n, 8), np.float32)
+    rec[:, :3] = p[:, :3]; rec[:, 3] = 1.0; rec[:, 4] = p[:, 3]        # PointXYZI: data[3] = 1.0f, intensity at byte 16
+    out = _ros_header(0, stamp, frame_id) + struct.pack("<II", 1, n) + struct.pack("<I", 4)
+    for name, off in (("x", 0), ("y", 4), ("z", 8), ("intensity", 16)):
+        out += struct.pack("<I", len(name)) + name.encode() + struct.pack("<IBI", off, 7, 1)
+    out += struct.pack("<BII", 0, 32, 32 * n) + struct.pack("<I", 32 * n) + rec.tobytes() + struct.pack("<B", 1)
+    return out
+
+
+def _ros_cloud_empty():
+    import struct
+    return _ros_header(0, (0, 0), "") + struct.pack("<II", 0, 0) + struct.pack("<I", 0) + struct.pack("<BII", 0, 0, 0) + struct.pack("<I", 0) + b"\0"
+
+
+def serialize_cloud_info(stage, seq=0, stamp=(0, 0), frame_id="", lidarFrame="", startRingIndex=(), endRingIndex=(), pointColInd=(),
+                         pointRange=(), imuAvailable=0, odomAvailable=0, imuRollInit=0.0, imuPitchInit=0.0, imuYawInit=0.0,
+                         initialGuess=(0.0,) * 6, cloud_deskewed=None, cloud_corner=None, cloud_surface=None):
+    """stage 0: imageProjection.cpp:600-605 (arrays + cloud_deskewed); stage 1: featureExtraction.cpp:240-258 (arrays cleared,
+    cloud_corner / cloud_surface added)."""
+    import struct
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dt).reshape(-1) if stage == 0 else np.zeros(0, dt)
+        return struct.pack("<I", len(a)) + a.tobytes()
+
+    out = _ros_header(seq, stamp, frame_id)
+    out += arr(startRingIndex, np.int32) + arr(endRingIndex, np.int32) + arr(pointColInd, np.int32) + arr(pointRange, np.float32)
+    out += struct.pack("<qq", imuAvailable, odomAvailable)
+    out += np.asarray([imuRollInit, imuPitchInit, imuYawInit, *initialGuess], np.float32).tobytes()
+    out += _ros_cloud_xyzi(cloud_deskewed, stamp, lidarFrame)
+    if stage == 1:
+        out += _ros_cloud_xyzi(cloud_corner, stamp, lidarFrame) + _ros_cloud_xyzi(cloud_surface, stamp, lidarFrame)
+    else:
+        out += _ros_cloud_empty() * 2
+    out += _ros_cloud_empty() * 4
+    return out
