@@ -84,7 +84,7 @@ int radix_sort_pairs(uint32_t* keys_a, uint32_t* vals_a, uint32_t* keys_b, uint3
 struct GridDev {               // passed by value to kernels
     const float4* pts;         // cell-sorted points: x, y, z, __int_as_float(original index)
     const uint32_t* cell_start;// ncell + 1
-    float ox, oy, oz, inv_h;
+    float ox, oy, oz, inv_h, h;
     int nx, ny, nz;
     int n;
     float max_d2;              // candidates at or beyond this squared distance are never reported (max_dist^2)

@@ -85,7 +85,7 @@ int GridIndex::begin(const void* host_pts, size_t stride, size_t n_, float max_d
         B2_CHECK(cell_start.reserve(3 * sizeof(uint32_t)));
         B2_CUDA(cudaMemsetAsync(cell_start.p, 0, 3 * sizeof(uint32_t), s));
         dev.pts = nullptr; dev.cell_start = cell_start.as<uint32_t>();
-        dev.ox = dev.oy = dev.oz = 0.f; dev.inv_h = 1.0f / h; dev.nx = dev.ny = dev.nz = 1; dev.n = 0; dev.max_d2 = max_dist * max_dist;
+        dev.ox = dev.oy = dev.oz = 0.f; dev.inv_h = 1.0f / h; dev.h = h; dev.nx = dev.ny = dev.nz = 1; dev.n = 0; dev.max_d2 = max_dist * max_dist;
         return B2_OK;
     }
     if (n > 0x7fffffffull) { set_error("grid index: too many points (%zu)", n); return B2_ERR_ARG; }
@@ -150,7 +150,7 @@ int GridIndex::finish(cudaStream_t s) {
     k_cell_scatter<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>()); count_launch();
     B2_CUDA(cudaGetLastError());
     dev.pts = pts.as<float4>(); dev.cell_start = cell_start.as<uint32_t>();
-    dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h;
+    dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h; dev.h = h;
     dev.nx = g.nx; dev.ny = g.ny; dev.nz = g.nz; dev.n = (int)n; dev.max_d2 = max_dist * max_dist;
     return B2_OK;
 }
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) k_knn(GridDev g, const unsigned char* __r
     float qx = 0.f, qy = 0.f, qz = 0.f;
     if (active) { const float* p = reinterpret_cast<const float*>(q + (size_t)qi * stride); qx = p[0]; qy = p[1]; qz = p[2]; }
     unsigned long long key[K]; uint32_t pos[K];
-    knn_group<K, LPF>(g, qx, qy, qz, active, key, pos);
+    knn_group<K, LPF>(g, qx, qy, qz, active, INFINITY, key, pos);
     const int sub = threadIdx.x & (LPF - 1);
     if (active && sub == 0) {
 #pragma unroll

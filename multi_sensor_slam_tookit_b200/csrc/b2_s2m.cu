@@ -32,7 +32,14 @@ constexpr int S2M_THREADS = 256;
 #define S2M_LAT_ROUNDS_V 2
 #endif
 constexpr int S2M_LAT_LPF = S2M_LAT_LPF_V, S2M_LAT_ROUNDS = S2M_LAT_ROUNDS_V;   // single scan: 32 features per CTA, many small CTAs (latency)
-constexpr int S2M_THR_LPF = 8,  S2M_THR_ROUNDS = 8;   // batch: 256 features per CTA, every warp busy in phase 2 (throughput)
+#ifndef S2M_THR_LPF_V
+#define S2M_THR_LPF_V 1
+#define S2M_THR_ROUNDS_V 1
+#endif
+#ifndef S2M_THR_MINB
+#define S2M_THR_MINB 4
+#endif
+constexpr int S2M_THR_LPF = S2M_THR_LPF_V, S2M_THR_ROUNDS = S2M_THR_ROUNDS_V;   // batch: 256 features per CTA, every warp busy in phase 2 (throughput)
 constexpr int S2M_LAT_FPB = S2M_THREADS / S2M_LAT_LPF * S2M_LAT_ROUNDS;
 constexpr int S2M_THR_FPB = S2M_THREADS / S2M_THR_LPF * S2M_THR_ROUNDS;
 constexpr int S2M_NPART = 28;                       // 21 (AtA upper) + 6 (Atb) + 1 (count)
@@ -67,6 +74,8 @@ struct S2MArgs {
     int want_matP;                                // 0: iteration 0 may skip the 6x6 eigen-decomposition when the system is
                                                   //    certified non-degenerate (matP is then left untouched)
     int* done_count;                              // number of scans whose loop has ended (host polls it between chunks)
+    uint32_t* nb_c; uint32_t* nb_s;               // [feature][5] grid positions of the 5 winners of the previous iteration
+    int use_prev;                                 // 1: nb_* hold the previous iteration of this scan/map; -1: they do when st.iters > 0; 0: no
     long long* prof;                              // optional per-CTA clock64 stamps (B2_S2M_PROF=1), 8 per CTA
     float* pose_hist; int hist_stride;            // optional [batch][max_iters][6]
     // optional per-feature introspection (single-scan parity runs)
@@ -274,7 +283,7 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
 // FPB = 256 / LPF * ROUNDS features and phase 2 runs on FPB threads (one warp for the latency shape <16,2>,
 // all eight warps for the throughput shape <8,8>).
 template <int LPF, int ROUNDS>
-__global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) {
+__global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == S2M_THR_ROUNDS) ? S2M_THR_MINB : 1) k_s2m_iteration(const S2MArgs a) {
     constexpr int FPR = S2M_THREADS / LPF;
     constexpr int FPB = FPR * ROUNDS;
     static_assert(FPB <= S2M_THREADS && FPB % 32 == 0, "phase 2 maps one thread per feature in whole warps");
@@ -292,6 +301,9 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
     const int nfeat = is_surf ? ns : nc;
     const float4* scanp = is_surf ? (a.scan_s + s0) : (a.scan_c + c0);
     const GridDev& g = is_surf ? a.gs : a.gc;
+    // the pose moves by millimetres between LM iterations: the previous winners bound this iteration's search radius
+    uint32_t* nbp = (is_surf ? a.nb_s + (size_t)s0 * 5 : a.nb_c + (size_t)c0 * 5);
+    const bool use_prev = LPF < 8 && (a.use_prev > 0 || (a.use_prev < 0 && st.iters > 0));
 
     __shared__ float4 s_nb[FPB][5];           // winners: x y z, original index bits
     __shared__ float s_d2[FPB][5];
@@ -323,20 +335,54 @@ __global__ void __launch_bounds__(S2M_THREADS) k_s2m_iteration(const S2MArgs a) 
             sy = s_xf[4] * po.x + s_xf[5] * po.y + s_xf[6] * po.z + s_xf[7];
             sz = s_xf[8] * po.x + s_xf[9] * po.y + s_xf[10] * po.z + s_xf[11];
         }
-        unsigned long long key[5]; uint32_t pos[5];
-        knn_group<5, LPF>(g, sx, sy, sz, active, key, pos);
-        if (active) {
-            if (sub < 5) {
-                // lane j of the group fetches winner j (static indexing keeps key/pos in registers)
-                unsigned long long kk = key[0]; uint32_t pp = pos[0];
+        float bound2 = INFINITY;
+        if (use_prev) {                                        // uniform per CTA
+            float m = 0.f;
+            for (int j = sub; j < 5; j += LPF) {
+                const uint32_t pp = active ? __ldcg(&nbp[(size_t)f * 5 + j]) : 0xffffffffu;
+                if (pp == 0xffffffffu) m = INFINITY;
+                else {
+                    const float4 c = ldg4(&g.pts[pp]);
+                    const float dx = sx - c.x, dy = sy - c.y, dz = sz - c.z;
+                    float d = dx * dx;                         // the search's own expression: these five pass its d <= bound test
+                    d = d + dy * dy;
+                    d = d + dz * dz;
+                    m = fmaxf(m, d);
+                }
+            }
+            __syncwarp();
 #pragma unroll
-                for (int j = 1; j < 5; j++) if (sub == j) { kk = key[j]; pp = pos[j]; }
-                float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                float d = INFINITY;
-                if (kk != KNN_EMPTY) { c = ldg4(&g.pts[pp]); d = __uint_as_float((uint32_t)(kk >> 32)); }
-                s_nb[slot][sub] = c;
-                s_d2[slot][sub] = d;
-            } else if (sub == 5) {
+            for (int o = LPF >> 1; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            bound2 = m;
+        }
+        unsigned long long key[5]; uint32_t pos[5];
+        knn_group<5, LPF>(g, sx, sy, sz, active, bound2, key, pos);
+        if (active) {
+            if constexpr (LPF >= 8) {
+                if (sub < 5) {
+                    // lane j of the group fetches winner j (static indexing keeps key/pos in registers)
+                    unsigned long long kk = key[0]; uint32_t pp = pos[0];
+#pragma unroll
+                    for (int j = 1; j < 5; j++) if (sub == j) { kk = key[j]; pp = pos[j]; }
+                    float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                    float d = INFINITY;
+                    if (kk != KNN_EMPTY) { c = ldg4(&g.pts[pp]); d = __uint_as_float((uint32_t)(kk >> 32)); }
+                    s_nb[slot][sub] = c;
+                    s_d2[slot][sub] = d;
+                } else if (sub == 5) {
+                    s_ori[slot] = po;
+                    s_sel[slot] = make_float4(sx, sy, sz, 0.f);
+                }
+            } else if (sub == 0) {
+#pragma unroll
+                for (int j = 0; j < 5; j++) {
+                    float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                    float d = INFINITY;
+                    if (key[j] != KNN_EMPTY) { c = ldg4(&g.pts[pos[j]]); d = __uint_as_float((uint32_t)(key[j] >> 32)); }
+                    s_nb[slot][j] = c;
+                    s_d2[slot][j] = d;
+                    __stcg(&nbp[(size_t)f * 5 + j], key[j] != KNN_EMPTY ? pos[j] : 0xffffffffu);
+                }
                 s_ori[slot] = po;
                 s_sel[slot] = make_float4(sx, sy, sz, 0.f);
             }
@@ -501,7 +547,8 @@ struct b2_s2m_s {
     int last_iters = 3;                            // iterations the previous single-scan solve needed (sizes the first chunk)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     GridIndex gc, gs;
-    DevBuf raw_c, raw_s, scan_c, scan_s, off_c, off_s, state, partial, hist, ne;
+    DevBuf raw_c, raw_s, scan_c, scan_s, off_c, off_s, state, partial, hist, ne, nb_c, nb_s;
+    bool nb_valid = false;            // nb_* were written by an iteration on the current map and scan (host-driven b2_s2m_iterate)
     DevBuf dbg_idx_c, dbg_d2_c, dbg_coeff_c, dbg_flag_c, dbg_idx_s, dbg_d2_s, dbg_coeff_s, dbg_flag_s;
     PinBuf pin;
     bool have_map = false, have_scan = false;
@@ -537,8 +584,10 @@ static int upload_points(b2_s2m_s* h, DevBuf& raw, DevBuf& packed, const void* p
 // CTAs whose second phase keeps all eight warps busy (throughput).
 static void launch_iteration(b2_s2m_s* h, const S2MArgs& a, int batch) {
     if (batch <= 2) {
+        // the previous winners' bound costs two dependent loads before the search starts: a loss on the latency shape
+        S2MArgs b = a; b.use_prev = 0;
         dim3 grid((unsigned)h->max_blocks, (unsigned)batch);
-        k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS><<<grid, S2M_THREADS, 0, h->stream>>>(a);
+        k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS><<<grid, S2M_THREADS, 0, h->stream>>>(b);
     } else {
         const int nb = (h->max_feat_c + S2M_THR_FPB - 1) / S2M_THR_FPB + (h->max_feat_s + S2M_THR_FPB - 1) / S2M_THR_FPB;
         dim3 grid((unsigned)std::max(nb, 1), (unsigned)batch);
@@ -560,6 +609,8 @@ static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, f
     a.min_corr = h->prm.min_correspondences; a.eig_thr = h->prm.degenerate_eigen_threshold;
     a.pose_hist = pose_hist; a.hist_stride = hist_stride;
     a.want_matP = 1; a.done_count = nullptr;
+    a.nb_c = h->nb_c.as<uint32_t>(); a.nb_s = h->nb_s.as<uint32_t>();
+    a.use_prev = device_driven ? -1 : 0;
     if (debug) {
         a.dbg_idx_c = h->dbg_idx_c.as<int32_t>(); a.dbg_d2_c = h->dbg_d2_c.as<float>(); a.dbg_coeff_c = h->dbg_coeff_c.as<float4>(); a.dbg_flag_c = h->dbg_flag_c.as<uint8_t>();
         a.dbg_idx_s = h->dbg_idx_s.as<int32_t>(); a.dbg_d2_s = h->dbg_d2_s.as<float>(); a.dbg_coeff_s = h->dbg_coeff_s.as<float4>(); a.dbg_flag_s = h->dbg_flag_s.as<uint8_t>();
@@ -588,6 +639,9 @@ static int set_scan_finish(b2_s2m_s* h, int batch) {
     B2_CHECK(h->state.reserve((size_t)batch * sizeof(S2MState)));
     B2_CHECK(h->partial.reserve((size_t)batch * mb * S2M_NPART * sizeof(double)));
     B2_CHECK(h->ne.reserve((size_t)(batch + 1) * sizeof(int)));
+    B2_CHECK(h->nb_c.reserve(std::max<size_t>(h->n_c, 1) * 5 * sizeof(uint32_t)));
+    B2_CHECK(h->nb_s.reserve(std::max<size_t>(h->n_s, 1) * 5 * sizeof(uint32_t)));
+    h->nb_valid = false;
     if (batch == 1) {
         const size_t nc = std::max<size_t>(h->n_c, 1), ns = std::max<size_t>(h->n_s, 1);
         B2_CHECK(h->dbg_idx_c.reserve(nc * 5 * 4)); B2_CHECK(h->dbg_d2_c.reserve(nc * 5 * 4));
@@ -642,7 +696,7 @@ int s2m_set_map_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, const
     B2_CHECK(h->gs.finish(h->stream2));
     B2_CUDA(cudaStreamSynchronize(h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream2));
-    h->have_map = true;
+    h->have_map = true; h->nb_valid = false;
     return B2_OK;
 }
 
@@ -678,7 +732,7 @@ int b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params) {
 int b2_s2m_destroy(b2_s2m_t h) {
     if (!h) return B2_ERR_ARG;
     h->gc.release(); h->gs.release();
-    DevBuf* bufs[] = {&h->raw_c, &h->raw_s, &h->scan_c, &h->scan_s, &h->off_c, &h->off_s, &h->state, &h->partial, &h->hist, &h->ne,
+    DevBuf* bufs[] = {&h->raw_c, &h->raw_s, &h->scan_c, &h->scan_s, &h->off_c, &h->off_s, &h->state, &h->partial, &h->hist, &h->ne, &h->nb_c, &h->nb_s,
                       &h->dbg_idx_c, &h->dbg_d2_c, &h->dbg_coeff_c, &h->dbg_flag_c, &h->dbg_idx_s, &h->dbg_d2_s, &h->dbg_coeff_s, &h->dbg_flag_s};
     for (DevBuf* b : bufs) b->release();
     h->pin.release();
@@ -701,7 +755,7 @@ int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corn
     B2_CHECK(h->gs.finish(h->stream2));
     B2_CUDA(cudaStreamSynchronize(h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream2));
-    h->have_map = true;
+    h->have_map = true; h->nb_valid = false;
     return B2_OK;
 }
 
@@ -784,6 +838,8 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
     B2_CUDA(cudaMemcpyAsync(h->state.p, hs, sizeof(S2MState), cudaMemcpyHostToDevice, h->stream));
     S2MArgs a = make_args(h, iter, 0, true, nullptr, 0);
     a.want_matP = matP != nullptr;
+    a.use_prev = h->nb_valid ? 1 : 0;
+    h->nb_valid = true;
     const bool prof = getenv("B2_S2M_PROF") != nullptr;
     if (prof) {
         B2_CHECK(h->hist.reserve((size_t)h->max_blocks * 8 * sizeof(long long)));
@@ -880,6 +936,7 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     }
     B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->last_launches = n_launch;
+    h->nb_valid = true;
     if (B == 1) h->last_iters = hs[0].iters;
     for (int b = 0; b < B; b++) {
         if (!h_ne[b]) memcpy(poses + (size_t)b * 6, hs[b].pose, 24);
