@@ -59,6 +59,7 @@ struct GicpArgs {
     double radius2, a;               // max_correspondence_distance^2, 1 - epsilon
     double* partials;                // [gridDim.x][GICP_NSUM]
     int32_t* corr;                   // optional: corr[source original index] = target original index or -1
+    uint32_t* prev;                  // optional: prev[source position] = fine position of the last correspondence (seeds the search)
     GicpState* st;
     int mode;                        // 0: reduce into sums_local; 1: reduce into sums and finalize on the device
 };
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_lineariz
         for (int j = 0; j < 3; j++) R[i * 3 + j] = st->T[i * 4 + j];
         t[i] = st->T[i * 4 + 3];
     }
-    double tot = 0.0;                // lane i: running total of term i
+    double totA = 0.0, totB = 0.0;   // lane l: running totals of terms (l & 15) and 16 + (l & 15)
     for (uint32_t lc = blockIdx.x * GICP_WARPS + warp; lc < A.n_local_chunks; lc += gridDim.x * GICP_WARPS) {
         // local chunk -> global chunk of the block-cyclic deal (spatially mixed shards: every rank gets its share of the
         // points that need the coarse pass; contiguous slices left the slowest rank 40 % behind at 8 GPUs)
@@ -152,14 +153,17 @@ __global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_lineariz
         const double vy = R[3] * px + R[4] * py + R[5] * pz + t[1];
         const double vz = R[6] * px + R[7] * py + R[8] * pz + t[2];
         NN1 nn; nn.d2 = INFINITY; nn.pos = 0xffffffffu; nn.idx = -1;
-        if (valid) nn = nn1_thread(A.tgt, A.tgtc, A.fine_pos_of, A.have_coarse != 0, vx, vy, vz, A.radius2);
+        if (valid) nn = nn1_thread(A.tgt, A.tgtc, A.fine_pos_of, A.have_coarse != 0, vx, vy, vz, A.radius2, A.prev ? __ldcs(&A.prev[p]) : 0xffffffffu);
         const bool hit = valid && nn.pos != 0xffffffffu;
+        if (A.prev && valid) __stcs(&A.prev[p], nn.pos);
         if (A.corr && valid) A.corr[sidx] = hit ? (int32_t)nn.idx : -1;
         __syncwarp();
         if (!__any_sync(full, hit)) continue;
-        double term[32];
+        // the 30 terms in two batches of 16 so that each batch lives in registers through its reduction:
+        // lane l accumulates term (l & 15) of batch A in totA and term 16 + (l & 15) in totB
+        double ta[16], tb[16];
 #pragma unroll
-        for (int i = 0; i < 32; i++) term[i] = 0.0;
+        for (int i = 0; i < 16; i++) { ta[i] = 0.0; tb[i] = 0.0; }
         if (hit) {
             const double* um = &A.tgt_m[3 * (size_t)nn.pos];
             const double* sm = &A.src_m[3 * (size_t)p];
@@ -182,21 +186,24 @@ __global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_lineariz
             const double B10 = N12 * vy - N11 * vz, B11 = N01 * vz - N12 * vx, B12 = N11 * vx - N01 * vy;
             const double B20 = N22 * vy - N12 * vz, B21 = N02 * vz - N22 * vx, B22 = N12 * vx - N02 * vy;
             // top-left S^T B (symmetric), top-right S^T N = B^T, bottom-right N
-            term[0] = vy * B20 - vz * B10; term[1] = vy * B21 - vz * B11; term[2] = vy * B22 - vz * B12;
-            term[3] = B00; term[4] = B10; term[5] = B20;
-            term[6] = vz * B01 - vx * B21; term[7] = vz * B02 - vx * B22;
-            term[8] = B01; term[9] = B11; term[10] = B21;
-            term[11] = vx * B12 - vy * B02;
-            term[12] = B02; term[13] = B12; term[14] = B22;
-            term[15] = N00; term[16] = N01; term[17] = N02; term[18] = N11; term[19] = N12; term[20] = N22;
+            ta[0] = vy * B20 - vz * B10; ta[1] = vy * B21 - vz * B11; ta[2] = vy * B22 - vz * B12;
+            ta[3] = B00; ta[4] = B10; ta[5] = B20;
+            ta[6] = vz * B01 - vx * B21; ta[7] = vz * B02 - vx * B22;
+            ta[8] = B01; ta[9] = B11; ta[10] = B21;
+            ta[11] = vx * B12 - vy * B02;
+            ta[12] = B02; ta[13] = B12; ta[14] = B22;
+            ta[15] = N00; tb[0] = N01; tb[1] = N02; tb[2] = N11; tb[3] = N12; tb[4] = N22;
             const double g0 = N00 * d0 + N01 * d1 + N02 * d2, g1 = N01 * d0 + N11 * d1 + N12 * d2, g2 = N02 * d0 + N12 * d1 + N22 * d2;
-            term[21] = vy * g2 - vz * g1; term[22] = vz * g0 - vx * g2; term[23] = vx * g1 - vy * g0;
-            term[24] = g0; term[25] = g1; term[26] = g2;
-            term[27] = 1.0; term[28] = nn.d2; term[29] = d0 * g0 + d1 * g1 + d2 * g2;
+            tb[5] = vy * g2 - vz * g1; tb[6] = vz * g0 - vx * g2; tb[7] = vx * g1 - vy * g0;
+            tb[8] = g0; tb[9] = g1; tb[10] = g2;
+            tb[11] = 1.0; tb[12] = nn.d2; tb[13] = d0 * g0 + d1 * g1 + d2 * g2;
         }
         __syncwarp();
-        tot += warp_reduce_scatter32(term);
+        totA += warp_reduce_scatter16(ta);
+        totB += warp_reduce_scatter16(tb);
     }
+    // lane l < 16 holds term l in totA; lane l >= 16 holds term 16 + (l & 15) = l in totB: lane l -> term l
+    const double tot = lane < 16 ? totA : totB;
     // epilogue: CTA partial, last CTA adds the partials in CTA order
     s_red[warp][lane] = tot;
     __syncthreads();
@@ -260,7 +267,7 @@ struct b2_gicp_s {
     cudaStream_t stream = nullptr;
     b2_gicp_params prm{};
     GridD tgt_grid, tgt_coarse, src_grid;
-    DevBuf tgt_m, src_m, partials, state, corr, tgt_xyz, fine_pos_of;
+    DevBuf tgt_m, src_m, partials, state, corr, tgt_xyz, fine_pos_of, prev;
     double coarse_for = -1.0;        // max_correspondence_distance the coarse grid was built for (< 0: none)
     bool have_coarse = false;
     int blocks_per_sm = GICP_MIN_BLOCKS;
@@ -314,6 +321,7 @@ static void gicp_fill_args(b2_gicp_s* h, GicpArgs& a, int mode, int32_t* corr) {
     a.a = 1.0 - h->prm.epsilon;
     a.partials = h->partials.as<double>();
     a.corr = corr;
+    a.prev = nullptr;
     a.st = h->state.as<GicpState>();
     a.mode = mode;
     const uint32_t chunks = a.n_local_chunks;
@@ -383,7 +391,7 @@ int b2_gicp_create(b2_gicp_t* out, const b2_gicp_params* params) {
 int b2_gicp_destroy(b2_gicp_t h) {
     if (!h) return B2_OK;
     h->tgt_grid.release(); h->tgt_coarse.release(); h->src_grid.release(); h->tgt_xyz.release(); h->fine_pos_of.release();
-    h->tgt_m.release(); h->src_m.release(); h->partials.release(); h->state.release(); h->corr.release(); h->pin.release();
+    h->tgt_m.release(); h->src_m.release(); h->partials.release(); h->state.release(); h->corr.release(); h->prev.release(); h->pin.release();
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -491,6 +499,13 @@ int b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* 
     B2_CHECK(gicp_upload_state(h, init, max_it));
     GicpArgs a;
     gicp_fill_args(h, a, h->comm ? 0 : 1, nullptr);
+    // the last correspondence of every source point seeds its next search (from the second evaluation on)
+    if (h->src_valid && !getenv("B2_GICP_NO_SEED")) {
+        const size_t slots = ((size_t)h->src_valid + 31) / 32 * 32;
+        B2_CHECK(h->prev.reserve(slots * sizeof(uint32_t)));
+        B2_CUDA(cudaMemsetAsync(h->prev.p, 0xff, slots * sizeof(uint32_t), h->stream));
+        a.prev = h->prev.as<uint32_t>();
+    }
     GicpState* ds = h->state.as<GicpState>();
     GicpState* hs = h->pin.as<GicpState>();
     // evaluations are enqueued in chunks; between chunks the host reads the small state back (one sync per chunk)

@@ -84,6 +84,24 @@ __device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32]) {
     return v[0];
 }
 
+// The same for 16 values: every lane leaves with the 32-lane sum of value (lane & 15). Half the live registers of the
+// 32-value form (a kernel capped at 80 registers keeps 16 doubles in registers, 32 go to local memory).
+__device__ __forceinline__ double warp_reduce_scatter16(double (&v)[16]) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; k++) {
+            const double keep = up ? v[k + o] : v[k];
+            const double send = up ? v[k] : v[k + o];
+            v[k] = keep + shfl_xor_d(full, send, o);
+        }
+    }
+    return v[0] + shfl_xor_d(full, v[0], 16);
+}
+
 // Geometry of one query against a grid: cell, and the per-ring exactness bound.
 struct QueryCell {
     int cx, cy, cz;
@@ -198,12 +216,45 @@ __device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const Q
     }
 }
 
+// the 3x3x3 block again, for a query that already holds a candidate (best.d2 finite): rows and end cells the ball of
+// radius sqrt(best.d2) cannot reach are not read. The faces' distances are shortened by an absolute slack (1e-7 cells,
+// nine orders above the rounding of the cell coordinate) and the ball is inflated by 1e-9, so the test is conservative;
+// equal distances stay reachable (the test is a strict >), which keeps ties falling to the smaller index.
+__device__ __forceinline__ void nn1_scan_block_bounded(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best) {
+    const double fx = (qx - g.ox) * g.inv_h - (double)qc.cx, fy = (qy - g.oy) * g.inv_h - (double)qc.cy, fz = (qz - g.oz) * g.inv_h - (double)qc.cz;
+    const double lim = best.d2 * (1.0 + 1e-9);
+    const double sl = 1e-7;
+    const bool inx = qc.cx >= 0 && qc.cx < g.nx, iny = qc.cy >= 0 && qc.cy < g.ny, inz = qc.cz >= 0 && qc.cz < g.nz;
+    double gxm = inx ? fmax(fx - sl, 0.0) * g.h : 0.0, gxp = inx ? fmax(1.0 - fx - sl, 0.0) * g.h : 0.0;
+    double gym = iny ? fmax(fy - sl, 0.0) * g.h : 0.0, gyp = iny ? fmax(1.0 - fy - sl, 0.0) * g.h : 0.0;
+    double gzm = inz ? fmax(fz - sl, 0.0) * g.h : 0.0, gzp = inz ? fmax(1.0 - fz - sl, 0.0) * g.h : 0.0;
+    gxm *= gxm; gxp *= gxp; gym *= gym; gyp *= gyp; gzm *= gzm; gzp *= gzp;
+    uint32_t rb[9], re[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        const double rowgap = ((i % 3) == 0 ? gym : (i % 3) == 2 ? gyp : 0.0) + ((i / 3) == 0 ? gzm : (i / 3) == 2 ? gzp : 0.0);
+        rb[i] = re[i] = 0u;
+        if (!(rowgap > lim))
+            row_range(g, (rowgap + gxm > lim) ? qc.cx : qc.cx - 1, (rowgap + gxp > lim) ? qc.cx : qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, rb[i], re[i]);
+    }
+#pragma unroll 1
+    for (int i = 0; i < 9; i++) nn1_scan_run(g, rb[i], re[i], qx, qy, qz, radius2, best);
+}
+
+// seed: position (fine order) of a target point worth trying first — the previous iteration's correspondence — or
+// 0xffffffff. It only narrows the search; the result is the exact nearest neighbour either way.
 __device__ __forceinline__ NN1 nn1_thread(const GridDDev& fine, const GridDDev& coarse, const uint32_t* __restrict__ fine_pos_of,
-                                          bool have_coarse, double qx, double qy, double qz, double radius2) {
+                                          bool have_coarse, double qx, double qy, double qz, double radius2, uint32_t seed = 0xffffffffu) {
     NN1 best; best.d2 = INFINITY; best.idx = 0x7fffffffffffffffLL; best.x = best.y = best.z = 0.0; best.pos = 0xffffffffu;
     const QueryCell qc = query_cell(fine, qx, qy, qz);
     if (!qc.finite) return best;
-    nn1_scan_block(fine, qc, qx, qy, qz, radius2, best);
+    if (seed != 0xffffffffu) {
+        double x, y, z; long long id;
+        load_p4d(&fine.pts[seed], x, y, z, id);
+        nn1_consider(best, radius2, qx, qy, qz, x, y, z, id, seed);
+    }
+    if (best.pos != 0xffffffffu) nn1_scan_block_bounded(fine, qc, qx, qy, qz, radius2, best);
+    else nn1_scan_block(fine, qc, qx, qy, qz, radius2, best);
     const double bound2 = ring_bound2(fine, qc, 1);
     if (best.d2 < bound2 || bound2 >= radius2 || !have_coarse) return best;
     const QueryCell qcc = query_cell(coarse, qx, qy, qz);
