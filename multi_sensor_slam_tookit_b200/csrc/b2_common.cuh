@@ -105,8 +105,9 @@ struct GridIndex {
         int st = begin(host_pts, stride, n, max_dist, s);
         return st != B2_OK ? st : finish(s);
     }
-    void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); }
+    void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); bb_ready_ = false; }
     size_t stride_ = 0; float max_dist_ = 1.f;
+    bool bb_ready_ = false;                       // the bounding-box words in tmp are already reset (by the last scatter)
     const unsigned char* src_ = nullptr;          // device points the build reads (raw.p after an upload)
 };
 

@@ -70,8 +70,10 @@ __global__ void __launch_bounds__(256) k_cell_key(const unsigned char* __restric
 
 __global__ void __launch_bounds__(256) k_cell_scatter(const unsigned char* __restrict__ raw, size_t stride, uint32_t n,
                                                       const uint32_t* __restrict__ cell_of, const uint32_t* __restrict__ rank_in_cell,
-                                                      const uint32_t* __restrict__ cell_start, float4* __restrict__ out) {
+                                                      const uint32_t* __restrict__ cell_start, float4* __restrict__ out, uint32_t* __restrict__ bb) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // the bounding box has been read back by now: leave it reset for the next build (saves that build a launch)
+    if (i < 6) bb[i] = i < 3 ? 0xffffffffu : 0u;
     if (i >= n) return;
     const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
     out[cell_start[cell_of[i]] + rank_in_cell[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
@@ -97,7 +99,8 @@ int GridIndex::begin(const void* host_pts, size_t stride, size_t n_, float max_d
     // bbox on device, one small readback to size the cell table
     B2_CHECK(tmp.reserve(64));
     uint32_t* bb = tmp.as<uint32_t>();
-    k_bbox_init<<<1, 32, 0, s>>>(bb); count_launch();
+    if (!bb_ready_) { k_bbox_init<<<1, 32, 0, s>>>(bb); count_launch(); }
+    bb_ready_ = false;                                           // true again once a scatter that resets it is enqueued
     int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 4);
     k_bbox<<<nb, 256, 0, s>>>(src_, stride, n, bb); count_launch();
     B2_CUDA(cudaGetLastError());
@@ -147,8 +150,9 @@ int GridIndex::finish(cudaStream_t s) {
     B2_CUDA(cudaGetLastError());
     B2_CHECK(exclusive_scan_u32(cell_start.as<uint32_t>(), ncount, scratch, s));
     B2_CHECK(pts.reserve(n * sizeof(float4)));
-    k_cell_scatter<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>()); count_launch();
+    k_cell_scatter<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>(), tmp.as<uint32_t>()); count_launch();
     B2_CUDA(cudaGetLastError());
+    bb_ready_ = true;
     dev.pts = pts.as<float4>(); dev.cell_start = cell_start.as<uint32_t>();
     dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h; dev.h = h;
     dev.nx = g.nx; dev.ny = g.ny; dev.nz = g.nz; dev.n = (int)n; dev.max_d2 = max_dist * max_dist;

@@ -543,7 +543,8 @@ using namespace b2;
 
 struct b2_s2m_s {
     b2_s2m_params prm;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream_up = nullptr;   // solve + corner index; surf index; scan uploads
+    cudaEvent_t ev_map = nullptr, ev_up = nullptr;
     int last_iters = 3;                            // iterations the previous single-scan solve needed (sizes the first chunk)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     GridIndex gc, gs;
@@ -552,6 +553,7 @@ struct b2_s2m_s {
     DevBuf dbg_idx_c, dbg_d2_c, dbg_coeff_c, dbg_flag_c, dbg_idx_s, dbg_d2_s, dbg_coeff_s, dbg_flag_s;
     PinBuf pin;
     bool have_map = false, have_scan = false;
+    bool map_pending = false, scan_pending = false;   // set_map / set_scan left work on the streams that nothing has waited for yet
     int batch = 0;
     int max_blocks = 0;
     int max_feat_c = 0, max_feat_s = 0;   // largest per-scan feature counts in the batch
@@ -570,11 +572,32 @@ static void host_prepare_pose(const float pose[6], float xf[12], float trig[6]) 
     trig[0] = sp; trig[1] = cp; trig[2] = sy; trig[3] = cy; trig[4] = sr; trig[5] = cr;
 }
 
+// set_map and set_scan return while their kernels are still queued. A second call before anything waited for the first
+// (no solve in between) would reuse or reallocate buffers those kernels still read: drain first. The usual sequence
+// set_map, set_scan, solve never takes this path (solve ends with a synchronisation).
+static int drain_pending(b2_s2m_s* h) {
+    B2_CUDA(cudaStreamSynchronize(h->stream2));
+    B2_CUDA(cudaStreamSynchronize(h->stream_up));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    h->map_pending = h->scan_pending = false;
+    return B2_OK;
+}
+
 static int upload_points(b2_s2m_s* h, DevBuf& raw, DevBuf& packed, const void* pts, size_t stride, size_t n) {
     if (n == 0) return B2_OK;
-    B2_CHECK(raw.reserve(n * stride));
     B2_CHECK(packed.reserve(n * sizeof(float4)));
-    B2_CUDA(cudaMemcpyAsync(raw.p, pts, n * stride, cudaMemcpyHostToDevice, h->stream));
+    // the copy does not queue behind the index builds of set_map (h->stream): own stream, the consumers wait for it
+    if (stride == sizeof(float4)) {
+        // already x y z intensity, 16 bytes apart: straight into place, no repacking launch
+        B2_CUDA(cudaMemcpyAsync(packed.p, pts, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream_up));
+        B2_CUDA(cudaEventRecord(h->ev_up, h->stream_up));
+        B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
+        return B2_OK;
+    }
+    B2_CHECK(raw.reserve(n * stride));
+    B2_CUDA(cudaMemcpyAsync(raw.p, pts, n * stride, cudaMemcpyHostToDevice, h->stream_up));
+    B2_CUDA(cudaEventRecord(h->ev_up, h->stream_up));
+    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
     k_pack_xyzi<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(raw.as<unsigned char>(), stride, (int)B2_INTENSITY_OFFSET(stride), (uint32_t)n, packed.as<float4>()); count_launch();
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -619,7 +642,7 @@ static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, f
 }
 
 // offsets, CTA counts and per-scan buffers for the features already sitting in scan_c / scan_s
-static int set_scan_finish(b2_s2m_s* h, int batch) {
+static int set_scan_finish(b2_s2m_s* h, int batch, bool host_upload = false) {
     const int32_t* coff = h->h_off_c.data();
     const int32_t* soff = h->h_off_s.data();
     B2_CHECK(h->off_c.reserve((batch + 1) * sizeof(int)));
@@ -649,7 +672,10 @@ static int set_scan_finish(b2_s2m_s* h, int batch) {
         B2_CHECK(h->dbg_idx_s.reserve(ns * 5 * 4)); B2_CHECK(h->dbg_d2_s.reserve(ns * 5 * 4));
         B2_CHECK(h->dbg_coeff_s.reserve(ns * 16)); B2_CHECK(h->dbg_flag_s.reserve(ns));
     }
-    B2_CUDA(cudaStreamSynchronize(h->stream));     // caller may free its buffers on return
+    // the caller may free its buffers on return: wait for the uploads only (the pack kernels and whatever set_map left on
+    // h->stream run on; the offset tables above come from pageable memory, which cudaMemcpyAsync stages before returning)
+    if (host_upload) { B2_CUDA(cudaStreamSynchronize(h->stream_up)); h->scan_pending = true; }
+    else { B2_CUDA(cudaStreamSynchronize(h->stream)); h->map_pending = h->scan_pending = false; }
     h->have_scan = true;
     return B2_OK;
 }
@@ -658,6 +684,7 @@ static int set_scan_finish(b2_s2m_s* h, int batch) {
 static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cstride, const int32_t* coff,
                            const void* surf, size_t sstride, const int32_t* soff) {
     if (batch < 1 || batch > h->prm.max_batch) { set_error("set_scan: batch %d outside [1, %d]", batch, h->prm.max_batch); return B2_ERR_ARG; }
+    if (h->scan_pending) B2_CHECK(drain_pending(h));
     h->h_off_c.assign(coff, coff + batch + 1);
     h->h_off_s.assign(soff, soff + batch + 1);
     for (int b = 0; b < batch; b++)
@@ -666,7 +693,7 @@ static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cs
     if ((h->n_c && !corner) || (h->n_s && !surf)) { set_error("set_scan: null feature array"); return B2_ERR_ARG; }
     B2_CHECK(upload_points(h, h->raw_c, h->scan_c, corner, cstride, h->n_c));
     B2_CHECK(upload_points(h, h->raw_s, h->scan_s, surf, sstride, h->n_s));
-    return set_scan_finish(h, batch);
+    return set_scan_finish(h, batch, true);
 }
 
 namespace b2 {
@@ -679,6 +706,7 @@ void pose_to_affine_host(const float pose6[6], float xf[12]) {
 // laserCloudCornerLastDS / laserCloudSurfLastDS handed over in device memory (packed xyzi); copies are ordered on h->stream
 int s2m_set_scan_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf) {
     if (!h || n_corner > 0x7fffffff || n_surf > 0x7fffffff) return B2_ERR_ARG;
+    if (h->scan_pending) B2_CHECK(drain_pending(h));
     h->h_off_c.assign({0, (int32_t)n_corner});
     h->h_off_s.assign({0, (int32_t)n_surf});
     h->n_c = n_corner; h->n_s = n_surf;
@@ -690,6 +718,7 @@ int s2m_set_scan_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, cons
 // kdtreeCornerFromMap->setInputCloud / kdtreeSurfFromMap->setInputCloud on clouds that already live in device memory
 int s2m_set_map_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf) {
     if (!h) return B2_ERR_ARG;
+    if (h->map_pending) B2_CHECK(drain_pending(h));
     B2_CHECK(h->gc.begin_device(d_corner, 16, n_corner, h->prm.knn_max_dist, h->stream));
     B2_CHECK(h->gs.begin_device(d_surf, 16, n_surf, h->prm.knn_max_dist, h->stream2));
     B2_CHECK(h->gc.finish(h->stream));
@@ -722,6 +751,9 @@ int b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params) {
     if (h->prm.max_batch < 1 || h->prm.max_iterations < 1 || !(h->prm.knn_max_dist > 0.f)) { delete h; set_error("b2_s2m_create: bad params"); return B2_ERR_ARG; }
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_map, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
     if (e != cudaSuccess) { set_error("b2_s2m_create: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
@@ -740,6 +772,9 @@ int b2_s2m_destroy(b2_s2m_t h) {
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
+    if (h->stream_up) cudaStreamDestroy(h->stream_up);
+    if (h->ev_map) cudaEventDestroy(h->ev_map);
+    if (h->ev_up) cudaEventDestroy(h->ev_up);
     delete h;
     return B2_OK;
 }
@@ -748,13 +783,18 @@ int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corn
     if (!h || (n_corner && !corner) || (n_surf && !surf) || cstride < 12 || sstride < 12 || (cstride & 3) || (sstride & 3)) {
         set_error("b2_s2m_set_map: bad argument"); return B2_ERR_ARG;
     }
+    if (h->map_pending) B2_CHECK(drain_pending(h));
     // the two indexes are built side by side: uploads and bounding boxes first, then both counting sorts
     B2_CHECK(h->gc.begin(corner, cstride, n_corner, h->prm.knn_max_dist, h->stream));
     B2_CHECK(h->gs.begin(surf, sstride, n_surf, h->prm.knn_max_dist, h->stream2));
-    B2_CHECK(h->gc.finish(h->stream));
+    B2_CHECK(h->gc.finish(h->stream));       // (measured: the small cloud first; the other order costs 3 % of the e2e step)
     B2_CHECK(h->gs.finish(h->stream2));
-    B2_CUDA(cudaStreamSynchronize(h->stream));
-    B2_CUDA(cudaStreamSynchronize(h->stream2));
+    // finish() has waited for the uploads (it needs the bounding boxes), so the caller's buffers are free; the counting sorts
+    // are still running. Everything that uses the indexes is enqueued on h->stream, which now also waits for the surf build:
+    // the host goes on to upload the scan and enqueue the solve while the indexes are being built.
+    B2_CUDA(cudaEventRecord(h->ev_map, h->stream2));
+    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_map, 0));
+    h->map_pending = true;
     h->have_map = true; h->nb_valid = false;
     return B2_OK;
 }
@@ -869,6 +909,7 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
     B2_CUDA(cudaGetLastError());
     B2_CUDA(cudaMemcpyAsync(hs, h->state.p, sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream));
+    h->map_pending = h->scan_pending = false;
     memcpy(pose, hs->pose, 24);
     h->degenerate = hs->degenerate;
     memcpy(h->matP, hs->matP, sizeof(h->matP));
@@ -924,9 +965,8 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
         launched += chunk; n_launch += chunk;
         B2_CUDA(cudaGetLastError());
         B2_CUDA(cudaEventRecord(h->ev1, h->stream));
-        B2_CUDA(cudaMemcpyAsync(h_done, d_done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         B2_CUDA(cudaMemcpyAsync(hs, h->state.p, (size_t)B * sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
-        B2_CUDA(cudaMemcpyAsync(h_ne, h->ne.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaMemcpyAsync(h_ne, h->ne.p, (size_t)(B + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));   // not-enough flags + scans finished
         B2_CUDA(cudaStreamSynchronize(h->stream));
         if (*h_done >= B) break;
     }
@@ -936,6 +976,7 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     }
     B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->last_launches = n_launch;
+    h->map_pending = h->scan_pending = false;      // h->stream has drained, and it had waited for the other two
     h->nb_valid = true;
     if (B == 1) h->last_iters = hs[0].iters;
     for (int b = 0; b < B; b++) {
