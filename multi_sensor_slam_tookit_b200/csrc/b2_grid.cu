@@ -3,11 +3,12 @@
 //
 // HBM layout after build():  pts   float4[n]      cell-sorted (x, y, z, original index as int bits)
 //                            cell_start u32[ncell+2]  exclusive prefix of per-cell counts (x fastest)
-// Build = bbox -> (cell, rank-in-cell) per point with one counting atomic -> prefix sum -> scatter: a counting sort, eight
-// launches and one 24-byte readback for a 100 k-point map.
+// Build = bbox -> (cell, rank-in-cell) per point with one counting atomic -> prefix sum -> scatter: a counting sort, two
+// launches (bounding box; one cooperative kernel for the rest) and one 24-byte readback for a 100 k-point map.
 // Cell edge h = max_dist * (1 + 2^-7): any point closer than max_dist to a query lies in the 3x3x3 block
 // around the query's cell even after float rounding of (p - origin) * (1/h).
 #include "b2_grid.cuh"
+#include <cooperative_groups.h>
 #include <cmath>
 #include <vector>
 
@@ -79,6 +80,89 @@ __global__ void __launch_bounds__(256) k_cell_scatter(const unsigned char* __res
     out[cell_start[cell_of[i]] + rank_in_cell[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
 }
 
+// The whole counting sort in ONE cooperative launch (the build of a 100 k-point map is bound by the host's launch calls,
+// not by the device): zero the counts | cell + rank per point | exclusive prefix sum of the counts | scatter, separated by
+// grid-wide barriers. The prefix sum gives every CTA one contiguous chunk of the table: chunk totals, barrier, every CTA
+// adds up the totals of the chunks before its own (at most a few hundred), then scans its chunk in place.
+constexpr int GB_THREADS = 256;
+__global__ void __launch_bounds__(GB_THREADS) k_grid_build(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, GridGeom g,
+                                                           uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank_in_cell,
+                                                           uint32_t* __restrict__ cell_start, uint32_t ncount, uint32_t* __restrict__ chunk_sum,
+                                                           float4* __restrict__ out, uint32_t* __restrict__ bb) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * GB_THREADS + threadIdx.x, nthr = gridDim.x * GB_THREADS;
+    __shared__ uint32_t s_w[GB_THREADS / 32];
+    __shared__ uint32_t s_base;
+    for (uint32_t i = tid; i < ncount; i += nthr) cell_start[i] = 0u;
+    grid.sync();
+    for (uint32_t i = tid; i < n; i += nthr) {
+        const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+        const uint32_t c = cell_of_point(g, p[0], p[1], p[2]);
+        cell_of[i] = c;
+        rank_in_cell[i] = atomicAdd(&cell_start[c], 1u);
+    }
+    grid.sync();
+    // ---- exclusive prefix sum of cell_start[0, ncount)
+    const uint32_t chunk = (ncount + gridDim.x - 1) / gridDim.x;
+    const uint32_t c0 = min(blockIdx.x * chunk, ncount), c1 = min(c0 + chunk, ncount);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto block_sum = [&](uint32_t v) {                    // every thread gets the CTA total
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = v;
+        __syncthreads();
+        uint32_t t = 0;
+        for (int w = 0; w < GB_THREADS / 32; w++) t += s_w[w];
+        return t;
+    };
+    {
+        uint32_t v = 0;
+        for (uint32_t i = c0 + threadIdx.x; i < c1; i += GB_THREADS) v += cell_start[i];
+        v = block_sum(v);
+        if (threadIdx.x == 0) chunk_sum[blockIdx.x] = v;
+    }
+    grid.sync();
+    {
+        uint32_t v = 0;
+        for (uint32_t b = threadIdx.x; b < blockIdx.x; b += GB_THREADS) v += __ldcg(&chunk_sum[b]);
+        v = block_sum(v);
+        if (threadIdx.x == 0) s_base = v;
+        __syncthreads();
+    }
+    uint32_t running = s_base;
+    for (uint32_t t0 = c0; t0 < c1; t0 += GB_THREADS) {   // tile of 256 entries: inclusive warp scans + warp totals
+        const uint32_t i = t0 + threadIdx.x;
+        const uint32_t v = i < c1 ? cell_start[i] : 0u;
+        uint32_t inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        __syncthreads();
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < GB_THREADS / 32; w++) { const uint32_t t = s_w[w]; if (w < warp) before += t; total += t; }
+        if (i < c1) cell_start[i] = running + before + inc - v;
+        running += total;
+    }
+    grid.sync();
+    if (tid < 6) bb[tid] = tid < 3 ? 0xffffffffu : 0u;   // the bounding box has been read back: leave it reset for the next build
+    for (uint32_t i = tid; i < n; i += nthr) {
+        const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+        out[cell_start[cell_of[i]] + rank_in_cell[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
+    }
+}
+
+// CTAs that can be co-resident for the cooperative launch (0: cooperative launch unavailable)
+static int grid_build_max_ctas() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    int dev = 0, coop = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_build, GB_THREADS, 0) != cudaSuccess) { cudaGetLastError(); cached = 0; return 0; }
+    cached = std::min(per_sm, 2) * device_sm_count();
+    return cached;
+}
+
 int GridIndex::begin(const void* host_pts, size_t stride, size_t n_, float max_dist, cudaStream_t s) {
     n = n_; stride_ = stride; max_dist_ = max_dist;
     dev = GridDev{};
@@ -137,21 +221,33 @@ int GridIndex::finish(cudaStream_t s) {
     g.ncell = (uint32_t)((size_t)g.nx * g.ny * g.nz);
     const size_t ncount = (size_t)g.ncell + 2;
     B2_CHECK(cell_start.reserve(ncount * sizeof(uint32_t)));
-    B2_CUDA(cudaMemsetAsync(cell_start.p, 0, ncount * sizeof(uint32_t), s));
     // cell + rank per point, prefix sum of the counts, one scatter (a counting sort: no radix passes)
     const size_t nal = (n + 63) & ~(size_t)63;
-    const size_t need = 2 * nal * sizeof(uint32_t) + scan_tmp_bytes(ncount) + 1024;
+    const size_t need = 2 * nal * sizeof(uint32_t) + scan_tmp_bytes(ncount) + 4096;
     B2_CHECK(cell_of.reserve(need));
+    B2_CHECK(pts.reserve(n * sizeof(float4)));
     uint32_t* d_cell = cell_of.as<uint32_t>();
     uint32_t* d_rank = d_cell + nal;
     char* scratch = reinterpret_cast<char*>(d_rank + nal);
-    const unsigned nblk = (unsigned)((n + 255) / 256);
-    k_cell_key<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, g, d_cell, d_rank, cell_start.as<uint32_t>()); count_launch();
-    B2_CUDA(cudaGetLastError());
-    B2_CHECK(exclusive_scan_u32(cell_start.as<uint32_t>(), ncount, scratch, s));
-    B2_CHECK(pts.reserve(n * sizeof(float4)));
-    k_cell_scatter<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>(), tmp.as<uint32_t>()); count_launch();
-    B2_CUDA(cudaGetLastError());
+    const int coop_max = ncount <= 0xffffffffull ? grid_build_max_ctas() : 0;
+    if (coop_max > 0) {
+        const size_t work = std::max<size_t>(n, ncount);
+        int ctas = (int)std::min<size_t>((size_t)coop_max, (work + GB_THREADS * 4 - 1) / (GB_THREADS * 4));
+        ctas = std::max(1, std::min(ctas, 1024));                 // chunk totals live in the first 4 KiB of the scratch area
+        const unsigned char* a_raw = src_; size_t a_stride = stride; uint32_t a_n = (uint32_t)n, a_ncount = (uint32_t)ncount;
+        uint32_t* a_cs = cell_start.as<uint32_t>(); uint32_t* a_chunk = reinterpret_cast<uint32_t*>(scratch);
+        float4* a_out = pts.as<float4>(); uint32_t* a_bb = tmp.as<uint32_t>();
+        void* args[] = {&a_raw, &a_stride, &a_n, &g, &d_cell, &d_rank, &a_cs, &a_ncount, &a_chunk, &a_out, &a_bb};
+        B2_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_grid_build), dim3((unsigned)ctas), dim3(GB_THREADS), args, 0, s)); count_launch();
+    } else {
+        B2_CUDA(cudaMemsetAsync(cell_start.p, 0, ncount * sizeof(uint32_t), s));
+        const unsigned nblk = (unsigned)((n + 255) / 256);
+        k_cell_key<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, g, d_cell, d_rank, cell_start.as<uint32_t>()); count_launch();
+        B2_CUDA(cudaGetLastError());
+        B2_CHECK(exclusive_scan_u32(cell_start.as<uint32_t>(), ncount, scratch, s));
+        k_cell_scatter<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>(), tmp.as<uint32_t>()); count_launch();
+        B2_CUDA(cudaGetLastError());
+    }
     bb_ready_ = true;
     dev.pts = pts.as<float4>(); dev.cell_start = cell_start.as<uint32_t>();
     dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h; dev.h = h;
