@@ -558,7 +558,7 @@ struct b2_s2m_s {
     int max_blocks = 0;
     int max_feat_c = 0, max_feat_s = 0;   // largest per-scan feature counts in the batch
     size_t n_c = 0, n_s = 0;          // total features over the batch
-    std::vector<int> h_off_c, h_off_s;
+    std::vector<int> h_off_c, h_off_s, h_off;
     int degenerate = 0;               // persistent members (:136,:234)
     float matP[36] = {0};
     float last_ms = 0.f; int last_launches = 0;
@@ -583,21 +583,19 @@ static int drain_pending(b2_s2m_s* h) {
     return B2_OK;
 }
 
+// host cloud -> device, on the upload stream (the copy does not queue behind the index builds set_map left on h->stream).
+// Clouds that are already x y z intensity, 16 bytes apart, go straight into place; others land in `raw` and are repacked by
+// pack_points once h->stream has been made to wait for the copies.
 static int upload_points(b2_s2m_s* h, DevBuf& raw, DevBuf& packed, const void* pts, size_t stride, size_t n) {
     if (n == 0) return B2_OK;
     B2_CHECK(packed.reserve(n * sizeof(float4)));
-    // the copy does not queue behind the index builds of set_map (h->stream): own stream, the consumers wait for it
-    if (stride == sizeof(float4)) {
-        // already x y z intensity, 16 bytes apart: straight into place, no repacking launch
-        B2_CUDA(cudaMemcpyAsync(packed.p, pts, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream_up));
-        B2_CUDA(cudaEventRecord(h->ev_up, h->stream_up));
-        B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
-        return B2_OK;
-    }
+    if (stride == sizeof(float4)) { B2_CUDA(cudaMemcpyAsync(packed.p, pts, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream_up)); return B2_OK; }
     B2_CHECK(raw.reserve(n * stride));
     B2_CUDA(cudaMemcpyAsync(raw.p, pts, n * stride, cudaMemcpyHostToDevice, h->stream_up));
-    B2_CUDA(cudaEventRecord(h->ev_up, h->stream_up));
-    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
+    return B2_OK;
+}
+static int pack_points(b2_s2m_s* h, DevBuf& raw, DevBuf& packed, size_t stride, size_t n) {
+    if (n == 0 || stride == sizeof(float4)) return B2_OK;
     k_pack_xyzi<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(raw.as<unsigned char>(), stride, (int)B2_INTENSITY_OFFSET(stride), (uint32_t)n, packed.as<float4>()); count_launch();
     B2_CUDA(cudaGetLastError());
     return B2_OK;
@@ -624,7 +622,7 @@ static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, f
     a.max_iters = hist_stride > 0 ? hist_stride : h->prm.max_iterations;
     a.gc = h->gc.dev; a.gs = h->gs.dev;
     a.scan_c = h->scan_c.as<float4>(); a.scan_s = h->scan_s.as<float4>();
-    a.off_c = h->off_c.as<int>(); a.off_s = h->off_s.as<int>();
+    a.off_c = h->off_c.as<int>(); a.off_s = h->off_c.as<int>() + (h->batch + 1);
     a.st = h->state.as<S2MState>();
     a.partial = h->partial.as<double>();
     a.max_blocks = h->max_blocks;
@@ -645,10 +643,11 @@ static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, f
 static int set_scan_finish(b2_s2m_s* h, int batch, bool host_upload = false) {
     const int32_t* coff = h->h_off_c.data();
     const int32_t* soff = h->h_off_s.data();
-    B2_CHECK(h->off_c.reserve((batch + 1) * sizeof(int)));
-    B2_CHECK(h->off_s.reserve((batch + 1) * sizeof(int)));
-    B2_CUDA(cudaMemcpyAsync(h->off_c.p, h->h_off_c.data(), (batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    B2_CUDA(cudaMemcpyAsync(h->off_s.p, h->h_off_s.data(), (batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    // both offset tables in one buffer, one copy (pageable source: staged before cudaMemcpyAsync returns)
+    h->h_off.assign(h->h_off_c.begin(), h->h_off_c.end());
+    h->h_off.insert(h->h_off.end(), h->h_off_s.begin(), h->h_off_s.end());
+    B2_CHECK(h->off_c.reserve(2 * (size_t)(batch + 1) * sizeof(int)));
+    B2_CUDA(cudaMemcpyAsync(h->off_c.p, h->h_off.data(), 2 * (size_t)(batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     int mb = 1;
     h->max_feat_c = h->max_feat_s = 0;
     for (int b = 0; b < batch; b++) {
@@ -659,7 +658,7 @@ static int set_scan_finish(b2_s2m_s* h, int batch, bool host_upload = false) {
     }
     h->max_blocks = mb;
     h->batch = batch;
-    B2_CHECK(h->state.reserve((size_t)batch * sizeof(S2MState)));
+    B2_CHECK(h->state.reserve((size_t)batch * sizeof(S2MState) + (size_t)(batch + 1) * sizeof(int)));
     B2_CHECK(h->partial.reserve((size_t)batch * mb * S2M_NPART * sizeof(double)));
     B2_CHECK(h->ne.reserve((size_t)(batch + 1) * sizeof(int)));
     B2_CHECK(h->nb_c.reserve(std::max<size_t>(h->n_c, 1) * 5 * sizeof(uint32_t)));
@@ -693,6 +692,10 @@ static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cs
     if ((h->n_c && !corner) || (h->n_s && !surf)) { set_error("set_scan: null feature array"); return B2_ERR_ARG; }
     B2_CHECK(upload_points(h, h->raw_c, h->scan_c, corner, cstride, h->n_c));
     B2_CHECK(upload_points(h, h->raw_s, h->scan_s, surf, sstride, h->n_s));
+    B2_CUDA(cudaEventRecord(h->ev_up, h->stream_up));
+    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
+    B2_CHECK(pack_points(h, h->raw_c, h->scan_c, cstride, h->n_c));
+    B2_CHECK(pack_points(h, h->raw_s, h->scan_s, sstride, h->n_s));
     return set_scan_finish(h, batch, true);
 }
 
@@ -925,7 +928,7 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
                      float* matP_out, int* not_enough, float* pose_history, bool want_matP) {
     const int B = h->batch;
     if (max_iterations < 1) max_iterations = h->prm.max_iterations;
-    B2_CHECK(h->pin.reserve((size_t)B * sizeof(S2MState) + (size_t)B * sizeof(int) + 64));
+    B2_CHECK(h->pin.reserve((size_t)B * sizeof(S2MState) + (size_t)(B + 1) * sizeof(int) + 64));
     S2MState* hs = h->pin.as<S2MState>();
     memset(hs, 0, (size_t)B * sizeof(S2MState));
     for (int b = 0; b < B; b++) {
@@ -939,13 +942,17 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
         d_hist = h->hist.as<float>();
     }
     B2_CUDA(cudaEventRecord(h->ev0, h->stream));
-    B2_CUDA(cudaMemcpyAsync(h->state.p, hs, (size_t)B * sizeof(S2MState), cudaMemcpyHostToDevice, h->stream));
+    // the not-enough flags and the scans-finished counter live right behind the states: zeroed by the same upload, read back
+    // by the same copy
+    const size_t state_bytes = (size_t)B * sizeof(S2MState), tail_bytes = (size_t)(B + 1) * sizeof(int);
+    B2_CHECK(h->state.reserve(state_bytes + tail_bytes));
+    memset(reinterpret_cast<char*>(hs) + state_bytes, 0, tail_bytes);
+    B2_CUDA(cudaMemcpyAsync(h->state.p, hs, state_bytes + tail_bytes, cudaMemcpyHostToDevice, h->stream));
     if (d_hist) B2_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)B * max_iterations * 6 * sizeof(float), h->stream));
-    B2_CHECK(h->ne.reserve((size_t)(B + 1) * sizeof(int)));
-    int* d_done = h->ne.as<int>() + B;
-    B2_CUDA(cudaMemsetAsync(d_done, 0, sizeof(int), h->stream));
-    k_s2m_prepare<<<(B + 127) / 128, 128, 0, h->stream>>>(h->state.as<S2MState>(), B, h->off_c.as<int>(), h->off_s.as<int>(),
-                                                          h->prm.edge_feature_min_valid_num, h->prm.surf_feature_min_valid_num, h->ne.as<int>(), d_done); count_launch();
+    int* d_ne = reinterpret_cast<int*>(h->state.as<char>() + state_bytes);
+    int* d_done = d_ne + B;
+    k_s2m_prepare<<<(B + 127) / 128, 128, 0, h->stream>>>(h->state.as<S2MState>(), B, h->off_c.as<int>(), h->off_c.as<int>() + (B + 1),
+                                                          h->prm.edge_feature_min_valid_num, h->prm.surf_feature_min_valid_num, d_ne, d_done); count_launch();
     B2_CUDA(cudaGetLastError());
     S2MArgs a = make_args(h, -1, 1, false, d_hist, max_iterations);
     a.want_matP = want_matP ? 1 : 0;
@@ -965,8 +972,7 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
         launched += chunk; n_launch += chunk;
         B2_CUDA(cudaGetLastError());
         B2_CUDA(cudaEventRecord(h->ev1, h->stream));
-        B2_CUDA(cudaMemcpyAsync(hs, h->state.p, (size_t)B * sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
-        B2_CUDA(cudaMemcpyAsync(h_ne, h->ne.p, (size_t)(B + 1) * sizeof(int), cudaMemcpyDeviceToHost, h->stream));   // not-enough flags + scans finished
+        B2_CUDA(cudaMemcpyAsync(hs, h->state.p, state_bytes + tail_bytes, cudaMemcpyDeviceToHost, h->stream));   // states, not-enough flags, scans finished
         B2_CUDA(cudaStreamSynchronize(h->stream));
         if (*h_done >= B) break;
     }
