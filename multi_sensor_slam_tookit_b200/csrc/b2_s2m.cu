@@ -288,6 +288,11 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     constexpr int FPB = FPR * ROUNDS;
     static_assert(FPB <= S2M_THREADS && FPB % 32 == 0, "phase 2 maps one thread per feature in whole warps");
     constexpr int P2_WARPS = FPB / 32;
+    // Programmatic dependent launch (single-scan shape): this grid may have been scheduled while the previous iteration was
+    // still running; wait for it (and its writes) here, and let the next launch be scheduled behind us right away. Both are
+    // no-ops for a launch without the attribute.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     const int scan = blockIdx.y;
     S2MState& st = a.st[scan];
     if (st.done) return;                                       // uniform per CTA, written only by a previous launch
@@ -553,6 +558,7 @@ struct b2_s2m_s {
     DevBuf dbg_idx_c, dbg_d2_c, dbg_coeff_c, dbg_flag_c, dbg_idx_s, dbg_d2_s, dbg_coeff_s, dbg_flag_s;
     PinBuf pin;
     bool have_map = false, have_scan = false;
+    bool use_pdl = getenv("B2_S2M_NO_PDL") == nullptr;
     bool map_pending = false, scan_pending = false;   // set_map / set_scan left work on the streams that nothing has waited for yet
     int batch = 0;
     int max_blocks = 0;
@@ -608,7 +614,15 @@ static void launch_iteration(b2_s2m_s* h, const S2MArgs& a, int batch) {
         // the previous winners' bound costs two dependent loads before the search starts: a loss on the latency shape
         S2MArgs b = a; b.use_prev = 0;
         dim3 grid((unsigned)h->max_blocks, (unsigned)batch);
-        k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS><<<grid, S2M_THREADS, 0, h->stream>>>(b);
+        // iteration k+1 depends on iteration k's last CTA: no overlap to gain, but the launch latency between the two
+        // (3-4 us of a 26 us kernel) goes away when the next grid is already resident and waiting
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(S2M_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = h->use_pdl ? 1 : 0;
+        cudaLaunchKernelEx(&cfg, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS>, b);
     } else {
         const int nb = (h->max_feat_c + S2M_THR_FPB - 1) / S2M_THR_FPB + (h->max_feat_s + S2M_THR_FPB - 1) / S2M_THR_FPB;
         dim3 grid((unsigned)std::max(nb, 1), (unsigned)batch);
