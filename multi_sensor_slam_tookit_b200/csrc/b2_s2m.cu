@@ -960,14 +960,27 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     // by the same copy
     const size_t state_bytes = (size_t)B * sizeof(S2MState), tail_bytes = (size_t)(B + 1) * sizeof(int);
     B2_CHECK(h->state.reserve(state_bytes + tail_bytes));
-    memset(reinterpret_cast<char*>(hs) + state_bytes, 0, tail_bytes);
+    int* h_tail = reinterpret_cast<int*>(reinterpret_cast<char*>(hs) + state_bytes);
+    memset(h_tail, 0, tail_bytes);
+    if (B == 1) {
+        // a single scan needs no preparation kernel: the host knows the pose (sines / cosines from the C library, as the
+        // reference evaluates them) and the guard of scan2MapOptimization :1287
+        host_prepare_pose(hs[0].pose, hs[0].xf, hs[0].trig);
+        const int nc = h->h_off_c[1] - h->h_off_c[0], ns = h->h_off_s[1] - h->h_off_s[0];
+        const int ne = !(nc > h->prm.edge_feature_min_valid_num && ns > h->prm.surf_feature_min_valid_num);
+        hs[0].done = ne; h_tail[0] = ne; h_tail[1] = ne;
+    }
     B2_CUDA(cudaMemcpyAsync(h->state.p, hs, state_bytes + tail_bytes, cudaMemcpyHostToDevice, h->stream));
     if (d_hist) B2_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)B * max_iterations * 6 * sizeof(float), h->stream));
     int* d_ne = reinterpret_cast<int*>(h->state.as<char>() + state_bytes);
     int* d_done = d_ne + B;
-    k_s2m_prepare<<<(B + 127) / 128, 128, 0, h->stream>>>(h->state.as<S2MState>(), B, h->off_c.as<int>(), h->off_c.as<int>() + (B + 1),
-                                                          h->prm.edge_feature_min_valid_num, h->prm.surf_feature_min_valid_num, d_ne, d_done); count_launch();
-    B2_CUDA(cudaGetLastError());
+    int n_launch = 0;
+    if (B > 1) {
+        k_s2m_prepare<<<(B + 127) / 128, 128, 0, h->stream>>>(h->state.as<S2MState>(), B, h->off_c.as<int>(), h->off_c.as<int>() + (B + 1),
+                                                              h->prm.edge_feature_min_valid_num, h->prm.surf_feature_min_valid_num, d_ne, d_done); count_launch();
+        B2_CUDA(cudaGetLastError());
+        n_launch = 1;
+    }
     S2MArgs a = make_args(h, -1, 1, false, d_hist, max_iterations);
     a.want_matP = want_matP ? 1 : 0;
     a.done_count = d_done;
@@ -977,7 +990,7 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     // over-long chunk costs only empty launches; the first chunk is the previous solve's iteration count plus one.
     int* h_ne = reinterpret_cast<int*>(hs + B);
     int* h_done = h_ne + B;
-    int launched = 0, n_launch = 1;
+    int launched = 0;
     const int first = std::min(max_iterations, std::max(4, h->last_iters + 1));
     static const int chunk_plan[] = {0, 4, 6, 8, 8};
     for (int c = 0; launched < max_iterations; c++) {
