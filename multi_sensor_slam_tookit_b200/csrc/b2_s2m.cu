@@ -780,6 +780,7 @@ int b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params) {
 
 int b2_s2m_destroy(b2_s2m_t h) {
     if (!h) return B2_ERR_ARG;
+    if (h->map_pending || h->scan_pending) drain_pending(h);     // kernels of a set_map / set_scan nobody waited for
     h->gc.release(); h->gs.release();
     DevBuf* bufs[] = {&h->raw_c, &h->raw_s, &h->scan_c, &h->scan_s, &h->off_c, &h->off_s, &h->state, &h->partial, &h->hist, &h->ne, &h->nb_c, &h->nb_s,
                       &h->dbg_idx_c, &h->dbg_d2_c, &h->dbg_coeff_c, &h->dbg_flag_c, &h->dbg_idx_s, &h->dbg_d2_s, &h->dbg_coeff_s, &h->dbg_flag_s};

@@ -161,3 +161,50 @@ def test_transform_point_cloud_bit_exact(b2, oracle, c1):
     from multi_sensor_slam_tookit_b200.registration import transformPointCloud
     out = transformPointCloud(c1["scan_surf"], c1["pose_guess"])
     assert np.array_equal(out, oracle.transform_cloud(c1["scan_surf"], c1["pose_guess"]))
+
+
+def test_calls_that_return_before_their_kernels_finish(b2, c1):
+    """set_map / set_scan return while their index builds and copies are still queued (events, not host syncs). Any order of
+    calls must give the result of the plain sequence; the caller may overwrite its buffers as soon as a call returns."""
+    from multi_sensor_slam_tookit_b200.registration import ScanToMapOptimizer
+
+    def solve(g):
+        g.transformTobeMapped = c1["pose_guess"].copy()
+        r = g.scan2MapOptimization(30, want_matP=False)
+        return np.asarray(g.transformTobeMapped).copy(), r["iters"]
+
+    ref = ScanToMapOptimizer()
+    ref.setInputMap(c1["map_corner"], c1["map_surf"]); ref.setInputScan(c1["scan_corner"], c1["scan_surf"])
+    p0, it0 = solve(ref)
+    g = ScanToMapOptimizer()
+    junk_map = np.ascontiguousarray(c1["map_surf"][::-1] + 3.0)
+    for _ in range(3):
+        # a map and a scan that are replaced before anything waited for them, buffers scribbled over right after the calls
+        mc, ms = c1["map_corner"].copy(), c1["map_surf"].copy()
+        sc, ss = c1["scan_corner"].copy(), c1["scan_surf"].copy()
+        g.setInputMap(junk_map[:5000], junk_map)
+        g.setInputScan(ss[:100], sc)
+        g.setInputMap(mc, ms); mc[:] = np.nan; ms[:] = np.nan
+        g.setInputScan(sc, ss); sc[:] = np.nan; ss[:] = np.nan
+        p, it = solve(g)
+        assert np.array_equal(p, p0) and it == it0
+        p, it = solve(g)                                   # again on the same state
+        assert np.array_equal(p, p0) and it == it0
+    # pinned host memory (truly asynchronous copies): still safe to overwrite on return
+    import torch
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()       # noqa: E731
+    mc, ms, sc, ss = pin(c1["map_corner"]), pin(c1["map_surf"]), pin(c1["scan_corner"]), pin(c1["scan_surf"])
+    g.setInputMap(mc, ms); mc[:] = np.nan; ms[:] = np.nan
+    g.setInputScan(sc, ss); sc[:] = np.nan; ss[:] = np.nan
+    p, it = solve(g)
+    assert np.array_equal(p, p0) and it == it0
+    # wider records (PointXYZI, 32 bytes) take the repacking path
+    wide_c = np.zeros((len(c1["scan_corner"]), 8), np.float32); wide_c[:, :3] = c1["scan_corner"][:, :3]; wide_c[:, 4] = c1["scan_corner"][:, 3]
+    wide_s = np.zeros((len(c1["scan_surf"]), 8), np.float32); wide_s[:, :3] = c1["scan_surf"][:, :3]; wide_s[:, 4] = c1["scan_surf"][:, 3]
+    g.setInputMap(c1["map_corner"], c1["map_surf"]); g.setInputScan(wide_c, wide_s)
+    p, it = solve(g)
+    assert np.array_equal(p, p0) and it == it0
+    # a handle destroyed with work still queued
+    h = ScanToMapOptimizer()
+    h.setInputMap(c1["map_corner"], c1["map_surf"]); h.setInputScan(c1["scan_corner"], c1["scan_surf"])
+    del h
