@@ -255,8 +255,14 @@ def check(code):
 
 
 def ptr(a):
-    """void* of a numpy array (or None)."""
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    """Address of a numpy array's buffer (or None). ndarray.ctypes.data_as costs ~5 us per call — a seventh of the C1
+    end-to-end step went into it; the buffer protocol gives the same address in under 1 us."""
+    if a is None:
+        return None
+    try:
+        return C.addressof(C.c_char.from_buffer(a))
+    except (TypeError, ValueError, BufferError):          # read-only or empty arrays
+        return a.ctypes.data
 
 
 def as_points(a, min_cols=3):
