@@ -201,7 +201,7 @@ def run_reference(args, rank, world):
                                        f"as mapOptmization.cpp:978,1070, {cores} threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -404,7 +404,7 @@ def run_b200(args, rank, local_rank, world):
                                 "note": "CPU restatement of the reference path (oracle/), OpenMP over features as the reference"}
         if registration:
             line["registration"] = registration
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -538,6 +538,15 @@ def run_registration(args, rank, local_rank, world, dist, torch):
     return out if rank == 0 else None
 
 
+_RESULT_OUT = None
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -549,6 +558,12 @@ def main():
     ap.add_argument("--c5-cpu-points", type=int, default=500_000, help="sample size of the C5 cpu_baseline (0 = skip)")
     ap.add_argument("--skip-registration", action="store_true", help="C1 only (skip the NDT / GICP workloads)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: libraries that chat on file descriptor 1 (NCCL prints its version
+    # there) are sent to stderr, and the result is written to a private copy of the original stdout
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
