@@ -112,26 +112,56 @@ __device__ __forceinline__ void knn_group(const GridDev& g, float qx, float qy, 
                 if (p < e4) scan_row(p, e4, ldg4(&g.pts[p]));
                 if (top.key[K - 1] != KNN_EMPTY) lim_now = fminf(lim_now, __uint_as_float((uint32_t)(top.key[K - 1] >> 32)));
             }
-            uint32_t rs[9], re[9];
+            if constexpr (PRUNE) {
+                // The eight outer rows as ONE candidate stream per lane. Walking them row by row makes the warp pay, for every
+                // row, the longest row among its 32 lanes (measured: 14-15 of 32 threads active per instruction); as a stream
+                // the warp runs as many steps as its busiest lane has candidates. The non-empty ranges are compacted into a
+                // small per-lane table; the next candidate is requested before the current one is tested.
+                uint32_t lb[8], le[8];
+                int nr = 0;
 #pragma unroll
-            for (int r = 0; r < 9; r++) {
-                if (CENTER_FIRST && r == 4) continue;
-                row_range(r, rs[r], re[r]);
-            }
-            // first chunk of the eight rows is requested before any of it is consumed: independent 128-bit loads
-            // in flight per lane instead of a load->compare->load chain (rows rarely exceed LPF points)
-            float4 first[9];
+                for (int r = 0; r < 9; r++) {
+                    if (r == 4) continue;
+                    uint32_t s0, e0;
+                    row_range(r, s0, e0);
+                    const uint32_t p0 = s0 + ((sub - s0) & (LPF - 1));
+                    if (p0 < e0) { lb[nr] = p0; le[nr] = e0; nr++; }
+                }
+                int k = 0;
+                uint32_t p = 0, e = 0;
+                bool have = nr > 0;
+                if (have) { p = lb[0]; e = le[0]; k = 1; }
+                float4 c = have ? ldg4(&g.pts[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                while (have) {
+                    const uint32_t pc = p;
+                    p += LPF;
+                    bool hn = true;
+                    if (p >= e) { if (k < nr) { p = lb[k]; e = le[k]; k++; } else hn = false; }
+                    const float4 cn = hn ? ldg4(&g.pts[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
+                    float d = dx * dx;
+                    d = d + dy * dy;
+                    d = d + dz * dz;
+                    if (d <= lim_now) top.push(((unsigned long long)__float_as_uint(d) << 32) | (uint32_t)__float_as_int(c.w), pc);
+                    c = cn; have = hn;
+                }
+            } else {
+                uint32_t rs[9], re[9];
 #pragma unroll
-            for (int r = 0; r < 9; r++) {
-                if (CENTER_FIRST && r == 4) continue;
-                const uint32_t p = rs[r] + ((sub - rs[r]) & (LPF - 1));
-                first[r] = (p < re[r]) ? ldg4(&g.pts[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+                for (int r = 0; r < 9; r++) row_range(r, rs[r], re[r]);
+                // first chunk of all nine rows is requested before any of it is consumed: independent 128-bit loads
+                // in flight per lane instead of a load->compare->load chain (rows rarely exceed LPF points)
+                float4 first[9];
 #pragma unroll
-            for (int r = 0; r < 9; r++) {
-                if (CENTER_FIRST && r == 4) continue;
-                const uint32_t p = rs[r] + ((sub - rs[r]) & (LPF - 1));
-                if (p < re[r]) scan_row(p, re[r], first[r]);
+                for (int r = 0; r < 9; r++) {
+                    const uint32_t p = rs[r] + ((sub - rs[r]) & (LPF - 1));
+                    first[r] = (p < re[r]) ? ldg4(&g.pts[p]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int r = 0; r < 9; r++) {
+                    const uint32_t p = rs[r] + ((sub - rs[r]) & (LPF - 1));
+                    if (p < re[r]) scan_row(p, re[r], first[r]);
+                }
             }
         }
     }
