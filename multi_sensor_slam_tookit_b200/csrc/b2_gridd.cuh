@@ -216,6 +216,9 @@ __device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const Q
     }
 }
 
+#ifndef B2_NN1_STREAM
+#define B2_NN1_STREAM 1
+#endif
 // the 3x3x3 block again, for a query that already holds a candidate (best.d2 finite): rows and end cells the ball of
 // radius sqrt(best.d2) cannot reach are not read. The faces' distances are shortened by an absolute slack (1e-7 cells,
 // nine orders above the rounding of the cell coordinate) and the ball is inflated by 1e-9, so the test is conservative;
@@ -237,8 +240,31 @@ __device__ __forceinline__ void nn1_scan_block_bounded(const GridDDev& g, const 
         if (!(rowgap > lim))
             row_range(g, (rowgap + gxm > lim) ? qc.cx : qc.cx - 1, (rowgap + gxp > lim) ? qc.cx : qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, rb[i], re[i]);
     }
+#if B2_NN1_STREAM
+    // the surviving rows as one candidate stream (lanes of a warp keep different rows of different lengths: walked row by
+    // row the warp pays the longest row of every row slot)
+    uint32_t lb[9], le[9];
+    int nr = 0;
+#pragma unroll
+    for (int i = 0; i < 9; i++) if (rb[i] < re[i]) { lb[nr] = rb[i]; le[nr] = re[i]; nr++; }
+    int k = 0;
+    uint32_t p = 0, e = 0;
+    bool have = nr > 0;
+    if (have) { p = lb[0]; e = le[0]; k = 1; }
+    while (have) {
+        double x0, y0, z0, x1, y1, z1; long long i0, i1;
+        const bool two = p + 1 < e;
+        load_p4d(&g.pts[p], x0, y0, z0, i0);
+        load_p4d(&g.pts[two ? p + 1 : p], x1, y1, z1, i1);
+        nn1_consider(best, radius2, qx, qy, qz, x0, y0, z0, i0, p);
+        if (two) nn1_consider(best, radius2, qx, qy, qz, x1, y1, z1, i1, p + 1);
+        p += 2;
+        if (p >= e) { if (k < nr) { p = lb[k]; e = le[k]; k++; } else have = false; }
+    }
+#else
 #pragma unroll 1
     for (int i = 0; i < 9; i++) nn1_scan_run(g, rb[i], re[i], qx, qy, qz, radius2, best);
+#endif
 }
 
 // seed: position (fine order) of a target point worth trying first — the previous iteration's correspondence — or
