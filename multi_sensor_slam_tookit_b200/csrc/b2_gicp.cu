@@ -124,7 +124,7 @@ __global__ void k_gicp_finalize(GicpState* st) {
 }
 
 #ifndef GICP_MIN_BLOCKS
-#define GICP_MIN_BLOCKS 3
+#define GICP_MIN_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_linearize(GicpArgs A) {
     GicpState* st = A.st;
