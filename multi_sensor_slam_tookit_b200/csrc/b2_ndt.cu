@@ -287,6 +287,12 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
                 hv[5][0] = dot3(A.ang.h[12], x, y, z); hv[5][1] = dot3(A.ang.h[13], x, y, z); hv[5][2] = dot3(A.ang.h[14], x, y, z);   // f
             }
             if (fin) {
+                // The voxels in range first, as a per-lane list (cheap tests, in cell order), the derivative terms afterwards:
+                // a point has about three voxels in range, its warp about twenty of the 27 slots with a hit in some lane, and
+                // in one loop the warp pays the ~400-flop block below once per such slot instead of once per list entry of
+                // its busiest lane. The per-point order of the voxels is unchanged, so every sum is bit-identical.
+                int32_t hit[27];
+                int nh = 0;
 #pragma unroll 1
                 for (int cell = 0; cell < 27; cell++) {
                     const int vx = c0 + (cell % 3) - 1, vy = c1 + ((cell / 3) % 3) - 1, vz = c2 + (cell / 9) - 1;
@@ -299,6 +305,11 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
                     dd = dd + ddy * ddy;
                     dd = dd + ddz * ddz;
                     if (!(dd < g.r2)) continue;
+                    hit[nh++] = rk;
+                }
+#pragma unroll 1
+                for (int hi = 0; hi < nh; hi++) {
+                    const int32_t rk = hit[hi];
                     const double* mu = &g.mean[3 * (size_t)rk];
                     const double* ci = &g.icov[9 * (size_t)rk];
                     const double xt0 = (double)tx - mu[0], xt1 = (double)ty - mu[1], xt2 = (double)tz - mu[2];
