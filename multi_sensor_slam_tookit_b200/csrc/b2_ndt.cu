@@ -18,6 +18,7 @@
 // between evaluations, in PCL's operation order; each evaluation returns 28 doubles.
 #include "b2_cloud.cuh"
 #include "b2_bvh.cuh"
+#include <atomic>
 #include <cmath>
 #include <cfloat>
 #include <climits>
@@ -53,6 +54,8 @@ struct NdtArgs {
     double* partials;
     double* sums;                    // NDT_NSUM
     unsigned* ticket;
+    double* host_sums;               // the same sums in mapped host memory, host_sums[32] = seq once they are complete
+    double seq;
 };
 
 // ---- target voxel build ---------------------------------------------------------------------------------------
@@ -377,6 +380,13 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
         double v = 0.0;
         for (unsigned b = 0; b < gridDim.x; b++) v += __ldcg(&A.partials[(size_t)b * NDT_NSUM + threadIdx.x]);
         A.sums[threadIdx.x] = v;
+        if (A.host_sums) A.host_sums[threadIdx.x] = v;
+    }
+    if (A.host_sums) {
+        // the host spins on the sequence number instead of paying a copy and a stream synchronisation per evaluation
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) { *reinterpret_cast<volatile double*>(A.host_sums + 32) = A.seq; __threadfence_system(); }
     }
     if (threadIdx.x == 0) *A.ticket = 0;
 }
@@ -508,6 +518,7 @@ using namespace b2;
 struct b2_ndt_s {
     int device = 0;
     cudaStream_t stream = nullptr;
+    double* h_res = nullptr; double* d_res = nullptr; double res_seq = 0.0;   // mapped result block (64 doubles)
     // parameters (PCL defaults: ndt.hpp constructor)
     float resolution = 1.0f;
     double step_size = 0.1, outlier_ratio = 0.55, trans_eps = 0.1;
@@ -653,6 +664,7 @@ static void ndt_fill_args(b2_ndt_s* h, NdtArgs& a, const float T[16], int mode) 
     a.ang = h->ang; a.d1 = h->gauss_d1; a.d2 = h->gauss_d2; a.mode = mode;
     a.partials = h->partials.as<double>(); a.sums = h->sums.as<double>();
     a.ticket = reinterpret_cast<unsigned*>(h->sums.as<double>() + 32);
+    a.host_sums = nullptr; a.seq = 0.0;
 }
 
 static int ndt_prepare(b2_ndt_s* h) {
@@ -670,11 +682,29 @@ static int ndt_prepare(b2_ndt_s* h) {
 static int ndt_evaluate(b2_ndt_s* h, const float T[16], int mode, double* score, double grad[6], double hess[36]) {
     NdtArgs a;
     ndt_fill_args(h, a, T, mode);
+    if (!h->h_res && !getenv("B2_NDT_NO_MAPPED")) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&h->h_res), 64 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->d_res), h->h_res, 0) != cudaSuccess) { cudaGetLastError(); h->h_res = nullptr; h->d_res = nullptr; }
+        else memset(h->h_res, 0, 64 * sizeof(double));
+    }
+    if (h->h_res) { h->res_seq += 1.0; a.host_sums = h->d_res; a.seq = h->res_seq; }
     k_ndt_derivatives<<<h->grid_blocks, NDT_THREADS, 0, h->stream>>>(a); count_launch(); h->launches++;
     B2_CUDA(cudaGetLastError());
     double* hs = h->pin.as<double>();
-    B2_CUDA(cudaMemcpyAsync(hs, h->sums.p, NDT_NSUM * 8, cudaMemcpyDeviceToHost, h->stream));
-    B2_CUDA(cudaStreamSynchronize(h->stream));
+    bool got = false;
+    if (h->h_res) {
+        // one evaluation is ~50 us of kernel: spin on the sequence number the last CTA writes after the sums
+        volatile double* flag = h->h_res + 32;
+        for (long spin = 0; spin < 40000000L; spin++) {
+            if (*flag == h->res_seq) { got = true; break; }
+            if ((spin & 0xfff) == 0xfff && cudaStreamQuery(h->stream) != cudaErrorNotReady && *flag != h->res_seq) break;   // finished without the flag: an error
+        }
+        if (got) { std::atomic_thread_fence(std::memory_order_acquire); for (int i = 0; i < NDT_NSUM; i++) hs[i] = h->h_res[i]; }
+    }
+    if (!got) {
+        B2_CUDA(cudaMemcpyAsync(hs, h->sums.p, NDT_NSUM * 8, cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+    }
     if (mode != 2) { if (score) *score = hs[0]; for (int i = 0; i < 6; i++) grad[i] = hs[1 + i]; }
     if (mode != 0) {
         int q = 7;
@@ -821,6 +851,7 @@ int b2_ndt_destroy(b2_ndt_t h) {
     h->tgt_xyz.release(); h->rank_of_cell.release(); h->centroid.release(); h->mean.release(); h->icov.release();
     h->vox_index.release(); h->vox_npts.release(); h->work.release(); h->src_xyz.release(); h->partials.release(); h->sums.release();
     h->bvh.release(); h->pin.release(); h->stage.release();
+    if (h->h_res) cudaFreeHost(h->h_res);
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
     if (h->stream) cudaStreamDestroy(h->stream);
