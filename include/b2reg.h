@@ -107,7 +107,11 @@ typedef struct {
 void b2_s2m_default_params(b2_s2m_params* p);
 int  b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params /* NULL = defaults */);
 int  b2_s2m_destroy(b2_s2m_t h);
-/* replaces kdtreeCornerFromMap->setInputCloud / kdtreeSurfFromMap->setInputCloud (:1289-1290) */
+/* replaces kdtreeCornerFromMap->setInputCloud / kdtreeSurfFromMap->setInputCloud (:1289-1290).
+ * b2_s2m_set_map and b2_s2m_set_scan return as soon as the caller's buffers have been read (they may be freed or
+ * overwritten at once); the index builds and copies may still be running on the handle's streams. Every later call on the
+ * handle is ordered behind them, and the solve / iterate calls end with the one synchronisation of the sequence, so errors
+ * of the queued work surface there. */
 int  b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t corner_stride, size_t n_corner,
                     const void* surf, size_t surf_stride, size_t n_surf);
 /* laserCloudCornerLastDS / laserCloudSurfLastDS of the current scan (:955-967) */
