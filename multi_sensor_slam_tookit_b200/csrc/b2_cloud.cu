@@ -480,7 +480,6 @@ __device__ __forceinline__ double box_box_dist2(const double* __restrict__ b, co
 
 __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, double* __restrict__ nrm) {
     __shared__ double s_d[NRM_WARPS][NRM_MAXK][32];
-    __shared__ int s_i[NRM_WARPS][NRM_MAXK][32];
     __shared__ uint32_t s_p[NRM_WARPS][NRM_MAXK][32];
     __shared__ double s_cx[NRM_WARPS][32], s_cy[NRM_WARPS][32], s_cz[NRM_WARPS][32];
     __shared__ int s_ci[NRM_WARPS][32];
@@ -496,25 +495,29 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, dou
 #pragma unroll
     for (int d = 0; d < 3; d++) { glo[d] = T.box[0][6 * (size_t)leaf0 + d]; ghi[d] = T.box[0][6 * (size_t)leaf0 + 3 + d]; }
     int cnt = 0;
-    double kd = INFINITY; int ki = 0x7fffffff;          // this lane's K-th best so far (INFINITY until the list is full)
+    double kd = INFINITY;                               // distance of this lane's K-th best so far (INFINITY until the heap is full)
 
     // The K best of a lane live in a max-heap in shared memory ([slot][lane]: a lane only ever touches its own bank), so an
     // insertion costs at most log2(K) steps for every lane; a sorted list made the warp pay the longest shift of its 32 lanes
     // on every candidate (measured: 90 % of the kernel's instructions).
+    // A heap entry is (distance, position): 12 bytes per slot instead of 16, i.e. a third more warps per SM (shared memory
+    // is what limits the occupancy of this kernel). The original index only ever decides ties between EQUAL distances, which
+    // are rare: it is read from the point record when one occurs.
+    auto idx_at = [&](int slot) { return (int)reinterpret_cast<const long long*>(&T.pts[s_p[warp][slot][lane]])[3]; };
     auto sift_down = [&](int j, int n, double d, int idx, uint32_t pos) {
         for (;;) {
             int c = 2 * j + 1;
             if (c >= n) break;
-            double cd = s_d[warp][c][lane]; int ci = s_i[warp][c][lane];
+            double cd = s_d[warp][c][lane];
             if (c + 1 < n) {
-                const double rd = s_d[warp][c + 1][lane]; const int ri = s_i[warp][c + 1][lane];
-                if (cd < rd || (cd == rd && ci < ri)) { c++; cd = rd; ci = ri; }
+                const double rd = s_d[warp][c + 1][lane];
+                if (cd < rd || (cd == rd && idx_at(c) < idx_at(c + 1))) { c++; cd = rd; }
             }
-            if (!(d < cd || (d == cd && idx < ci))) break;
-            s_d[warp][j][lane] = cd; s_i[warp][j][lane] = ci; s_p[warp][j][lane] = s_p[warp][c][lane];
+            if (!(d < cd || (d == cd && idx < idx_at(c)))) break;
+            s_d[warp][j][lane] = cd; s_p[warp][j][lane] = s_p[warp][c][lane];
             j = c;
         }
-        s_d[warp][j][lane] = d; s_i[warp][j][lane] = idx; s_p[warp][j][lane] = pos;
+        s_d[warp][j][lane] = d; s_p[warp][j][lane] = pos;
     };
     auto scan_leaf = [&](uint32_t leaf, bool mine) {
         const uint32_t p = leaf * 32u + lane;
@@ -531,16 +534,16 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, dou
                     int j = cnt++;
                     while (j > 0) {
                         const int pj = (j - 1) >> 1;
-                        const double pd = s_d[warp][pj][lane]; const int pi = s_i[warp][pj][lane];
-                        if (!(pd < d || (pd == d && pi < idx))) break;
-                        s_d[warp][j][lane] = pd; s_i[warp][j][lane] = pi; s_p[warp][j][lane] = s_p[warp][pj][lane];
+                        const double pd = s_d[warp][pj][lane];
+                        if (!(pd < d || (pd == d && idx_at(pj) < idx))) break;
+                        s_d[warp][j][lane] = pd; s_p[warp][j][lane] = s_p[warp][pj][lane];
                         j = pj;
                     }
-                    s_d[warp][j][lane] = d; s_i[warp][j][lane] = idx; s_p[warp][j][lane] = leaf * 32u + c;
-                    if (cnt == K) { kd = s_d[warp][0][lane]; ki = s_i[warp][0][lane]; }
-                } else if (d < kd || (d == kd && idx < ki)) {    // replaces the current K-th best (the root): sift down
+                    s_d[warp][j][lane] = d; s_p[warp][j][lane] = leaf * 32u + c;
+                    if (cnt == K) kd = s_d[warp][0][lane];
+                } else if (d < kd || (d == kd && idx < idx_at(0))) {    // replaces the current K-th best (the root): sift down
                     sift_down(0, K, d, idx, leaf * 32u + c);
-                    kd = s_d[warp][0][lane]; ki = s_i[warp][0][lane];
+                    kd = s_d[warp][0][lane];
                 }
             }
         }
@@ -592,8 +595,8 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, dou
     const int found = cnt;
     // heap sort in place: the cumulants below are summed in ascending (distance, index), the order the oracle pins
     for (int end = found - 1; end > 0; end--) {
-        const double d = s_d[warp][end][lane]; const int idx = s_i[warp][end][lane]; const uint32_t pos = s_p[warp][end][lane];
-        s_d[warp][end][lane] = s_d[warp][0][lane]; s_i[warp][end][lane] = s_i[warp][0][lane]; s_p[warp][end][lane] = s_p[warp][0][lane];
+        const double d = s_d[warp][end][lane]; const int idx = idx_at(end); const uint32_t pos = s_p[warp][end][lane];
+        s_d[warp][end][lane] = s_d[warp][0][lane]; s_p[warp][end][lane] = s_p[warp][0][lane];
         sift_down(0, end, d, idx, pos);
     }
     double nv[3] = {0.0, 0.0, 1.0};
