@@ -2,11 +2,13 @@
 //
 // Drop-in for the call sites of SURVEY.md §8b: the reference keeps its pcl::PointCloud<PointT> containers and calls the
 // same member names; the arithmetic runs in libb2reg.so on the GPU. The header needs only <pcl/point_cloud.h> and
-// <pcl/point_types.h> from PCL (containers and point structs, no algorithms). It is NOT compiled in this repository's
-// tests (PCL is not installed in the build image); INTEGRATION.md shows where each class goes.
+// <pcl/point_types.h> from PCL (containers and point structs, no algorithms). PCL is not installed in the build image:
+// tests/test_shim_compiles.py syntax-checks it against minimal stand-ins (tests/stubs/pcl); INTEGRATION.md shows where
+// each class goes.
 #pragma once
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
@@ -107,6 +109,43 @@ public:
     }
 private:
     b2_ndt_t h_ = nullptr;
+    typename pcl::PointCloud<PointSource>::ConstPtr src_;
+};
+
+// replaces pcl::IterativeClosestPoint<PointSource, PointTarget> as the loop-closure thread configures it (mapOptmization.cpp:559-586)
+template <typename PointSource, typename PointTarget>
+class IterativeClosestPoint {
+public:
+    IterativeClosestPoint() { check(b2_icp_create(&h_), "b2_icp_create"); }
+    ~IterativeClosestPoint() { b2_icp_destroy(h_); }
+    IterativeClosestPoint(const IterativeClosestPoint&) = delete;
+    void setMaxCorrespondenceDistance(double d) { check(b2_icp_set_max_correspondence_distance(h_, d), "setMaxCorrespondenceDistance"); }
+    void setMaximumIterations(int n) { check(b2_icp_set_maximum_iterations(h_, n), "setMaximumIterations"); }
+    void setTransformationEpsilon(double e) { check(b2_icp_set_transformation_epsilon(h_, e), "setTransformationEpsilon"); }
+    void setEuclideanFitnessEpsilon(double e) { check(b2_icp_set_euclidean_fitness_epsilon(h_, e), "setEuclideanFitnessEpsilon"); }
+    void setRANSACIterations(int n) { check(b2_icp_set_ransac_iterations(h_, n), "setRANSACIterations"); }
+    void setInputSource(const typename pcl::PointCloud<PointSource>::ConstPtr& c) {
+        src_ = c;
+        check(b2_icp_set_input_source(h_, c->points.data(), sizeof(PointSource), c->size()), "setInputSource");
+    }
+    void setInputTarget(const typename pcl::PointCloud<PointTarget>::ConstPtr& c) {
+        check(b2_icp_set_input_target(h_, c->points.data(), sizeof(PointTarget), c->size()), "setInputTarget");
+    }
+    void align(pcl::PointCloud<PointSource>& output, const Eigen::Matrix4f& guess = Eigen::Matrix4f::Identity()) {
+        const Eigen::Matrix<float, 4, 4, Eigen::RowMajor> g = guess;
+        output.points.resize(src_ ? src_->size() : 0);
+        output.width = static_cast<uint32_t>(output.points.size()); output.height = 1; output.is_dense = true;
+        check(b2_icp_align(h_, g.data(), output.points.data(), sizeof(PointSource)), "align");
+    }
+    bool hasConverged() const { int c = 0; check(b2_icp_has_converged(h_, &c), "hasConverged"); return c != 0; }
+    double getFitnessScore() const { double s = 0; check(b2_icp_get_fitness_score(h_, &s), "getFitnessScore"); return s; }
+    Eigen::Matrix4f getFinalTransformation() const {
+        Eigen::Matrix<float, 4, 4, Eigen::RowMajor> t;
+        check(b2_icp_get_final_transformation(h_, t.data()), "getFinalTransformation");
+        return t;
+    }
+private:
+    b2_icp_t h_ = nullptr;
     typename pcl::PointCloud<PointSource>::ConstPtr src_;
 };
 
