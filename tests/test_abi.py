@@ -39,3 +39,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("the oracle", ""), f
+
+
+def test_header_is_plain_c_and_links():
+    """include/b2reg.h is a C header (the reference binds it from C++, Python ctypes and, for the Go / Rust tools of the
+    wider toolkit, cgo / FFI): it must compile as C99 and a C program must link against the library."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from multi_sensor_slam_tookit_b200 import capi
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        with open(src, "w") as f:
+            f.write('#include "b2reg.h"\n#include <stdio.h>\nint main(void) { printf("%d %d\\n", b2_version(), b2_device_count() >= 0); return 0; }\n')
+        exe = os.path.join(d, "t")
+        lib_dir = os.path.dirname(capi.LIB_PATH)
+        r = subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), src, "-o", exe,
+                            "-L", lib_dir, "-l:" + os.path.basename(capi.LIB_PATH), "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0 and out.stdout.split()[0] == "100"
