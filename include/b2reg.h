@@ -209,6 +209,18 @@ int  b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n,
 int  b2_scan_extract_features(b2_scan_t h, size_t* n_corner, float* corner_xyzi, int32_t* corner_index,
                               size_t* n_surf, float* surf_xyzi, float* curvature, int32_t* picked_after_mask, int32_t* label);
 int  b2_scan_last_gpu_ms(b2_scan_t h, float* ms);
+/* Replaces ImageProjection::imuDeskewInfo (imageProjection.cpp:305-362) — host only (<= ~60 dependent
+ * double additions per scan). The IMU queue is passed as arrays in arrival order, after imuConverter (:203-204):
+ * stamp[n] = header.stamp.toSec(), orientation_xyzw[4n] (may be NULL: rpy_init untouched), angular_velocity[3n].
+ * Out: n_popped = messages dropped from the queue front (stamp < time_scan_cur - 0.01, :309-315); the table
+ * imu_time / imu_rot_{x,y,z}[0 .. n_table) exactly as b2_scan_project takes it (n_table - 1 == imuPointerCur after :356);
+ * imu_available (:361); rpy_init = cloudInfo.imu{Roll,Pitch,Yaw}Init from the newest message at or before time_scan_cur
+ * (tf getRPY in double, narrowed to the message's float32; untouched if there is none). capacity = length of the table
+ * arrays (the reference's queueLength = 2000, :45, unchecked there): B2_ERR_CAPACITY instead of writing past it. */
+int  b2_imu_deskew_info(const double* stamp, const double* orientation_xyzw, const double* angular_velocity, int n,
+                        double time_scan_cur, double time_scan_end,
+                        double* imu_time, double* imu_rot_x, double* imu_rot_y, double* imu_rot_z, int capacity,
+                        int* n_table, int* n_popped, int* imu_available, float rpy_init[3]);
 
 /* ------------------------------------------------------------------------------------------------
  * Rigid transform of a cloud — replaces mapOptimization::transformPointCloud (mapOptmization.cpp:286-305)

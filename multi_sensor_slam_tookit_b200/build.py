@@ -22,29 +22,55 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
+           [os.path.join(HERE, "..", "include", "b2reg.h")]
+
+
 def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "b2reg.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in sources() + _headers())
 
 
 def build_lib(force=False, verbose=False):
+    """One object per .cu (compiled in parallel, rebuilt only when the source or a header is newer), then one link.
+    No relocatable device code: the translation units only share host functions."""
     if not force and not _stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
-    extra = os.environ.get("B2_NVCC_EXTRA")
-    if extra:
-        cmd += extra.split()
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    env = dict(os.environ)
+    base = [nvcc]
     # the image exports CXX=/opt/gcc/bin/g++ whose driver lacks libgomp specs; nvcc only needs a plain host g++
     if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    subprocess.check_call(cmd, env=env)
+        base += ["-ccbin", "/usr/bin/g++"]
+    extra = os.environ.get("B2_NVCC_EXTRA", "").split()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    tag = os.path.join(objdir, ".flags")
+    flags_now = " ".join(NVCC_FLAGS + extra)
+    if not os.path.exists(tag) or open(tag).read() != flags_now:
+        force = True
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj
+        cmd = base + [f for f in NVCC_FLAGS if f != "-shared"] + extra + ["-c", src, "-o", obj]
+        if verbose:
+            print(" ".join(cmd), file=sys.stderr)
+        subprocess.check_call(cmd)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
+        objs = list(ex.map(compile_one, sources()))
+    open(tag, "w").write(flags_now)
+    cmd = base + ["-shared", "-o", LIB] + objs
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd)
     return LIB
 
 

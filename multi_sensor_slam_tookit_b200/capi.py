@@ -72,7 +72,7 @@ SYMBOLS = [
     "b2_s2m_solve", "b2_s2m_set_state", "b2_s2m_get_pass", "b2_s2m_get_normal_equations", "b2_s2m_set_scan_batch",
     "b2_s2m_solve_batch", "b2_s2m_last_gpu_ms", "b2_transform_cloud",
     "b2_scan_default_params", "b2_scan_create", "b2_scan_destroy", "b2_scan_project", "b2_scan_extract_features",
-    "b2_scan_last_gpu_ms",
+    "b2_scan_last_gpu_ms", "b2_imu_deskew_info",
     "b2_cloud_info_parse", "b2_scan_write_cloud_info", "b2_scan_set_from_cloud_info", "b2_s2m_set_scan_downsampled",
     "b2_s2m_set_scan_from_front_end", "b2_s2m_get_scan",
     "b2_cloud_create", "b2_cloud_destroy", "b2_cloud_set_points", "b2_cloud_set_points_f32", "b2_cloud_size",
@@ -142,6 +142,7 @@ def lib():
     L.b2_scan_project.argtypes = [vp, vp, sz, vp, vp, vp, vp, i32, C.c_double, i32, C.POINTER(sz), vp, vp, vp, vp, vp, vp, vp]
     L.b2_scan_extract_features.argtypes = [vp, C.POINTER(sz), vp, vp, C.POINTER(sz), vp, vp, vp, vp]
     L.b2_scan_last_gpu_ms.argtypes = [vp, pf]
+    L.b2_imu_deskew_info.argtypes = [vp, vp, vp, i32, C.c_double, C.c_double, vp, vp, vp, vp, i32, pi, pi, pi, vp]
     L.b2_cloud_info_parse.argtypes = [vp, sz, C.POINTER(CloudInfoView)]
     L.b2_scan_write_cloud_info.argtypes = [vp, C.POINTER(CloudInfoMeta), i32, vp, sz, C.POINTER(sz)]
     L.b2_scan_set_from_cloud_info.argtypes = [vp, vp, sz, C.POINTER(sz)]

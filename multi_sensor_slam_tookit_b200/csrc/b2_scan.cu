@@ -694,6 +694,81 @@ int b2_scan_last_gpu_ms(b2_scan_t h, float* ms) {
     return B2_OK;
 }
 
+// imuDeskewInfo (imageProjection.cpp:305-362): host only. The table is at most ~60 entries per scan and every entry
+// depends on the one before it (rot[k] = rot[k-1] + w[k] * dt in double), so SURVEY.md 8a row a3 keeps it on the host; the
+// device consumes the finished table in b2_scan_project. Three steps instead of the reference's single loop:
+// the window [first, last] of the queue, the roll/pitch/yaw of the newest message at or before the scan start, and the
+// running sum over the window. Same order of additions, so the table is bit-identical to the reference's.
+static void quat_to_rpy_tf(const double* q, double* roll, double* pitch, double* yaw) {
+    // tf::Matrix3x3::setRotation(q) followed by getEulerYPR(yaw, pitch, roll) (what getRPY calls), in double
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double s = 2.0 / (x * x + y * y + z * z + w * w);
+    const double xs = x * s, ys = y * s, zs = z * s;
+    const double r00 = 1.0 - (y * ys + z * zs), r10 = x * ys + w * zs;
+    const double r20 = x * zs - w * ys, r21 = y * zs + w * xs, r22 = 1.0 - (x * xs + y * ys);
+    if (fabs(r20) >= 1) {                       // gimbal lock branch of getEulerYPR
+        *yaw = 0;
+        *roll = atan2(r21, r22);
+        *pitch = r20 < 0 ? M_PI / 2.0 : -M_PI / 2.0;
+        return;
+    }
+    *pitch = -asin(r20);
+    const double c = cos(*pitch);
+    *roll = atan2(r21 / c, r22 / c);
+    *yaw = atan2(r10 / c, r00 / c);
+}
+
+int b2_imu_deskew_info(const double* stamp, const double* orientation_xyzw, const double* angular_velocity, int n,
+                       double time_scan_cur, double time_scan_end,
+                       double* imu_time, double* imu_rot_x, double* imu_rot_y, double* imu_rot_z, int capacity,
+                       int* n_table, int* n_popped, int* imu_available, float rpy_init[3]) {
+    if (n < 0 || (n > 0 && (!stamp || !angular_velocity)) || !imu_time || !imu_rot_x || !imu_rot_y || !imu_rot_z || capacity < 1 ||
+        !n_table || !n_popped || !imu_available) {
+        b2::set_error("b2_imu_deskew_info: bad argument");
+        return B2_ERR_ARG;
+    }
+    *imu_available = 0; *n_table = 0;
+    // messages older than 10 ms before the scan start leave the queue (:309-315)
+    int first = 0;
+    while (first < n && stamp[first] < time_scan_cur - 0.01) ++first;
+    *n_popped = first;
+    if (first == n) return B2_OK;
+    // the loop of :321-354 stops at the first message later than 10 ms after the scan end; that message is still
+    // looked at by the roll/pitch/yaw test of :329 before the break
+    int stop = first;
+    while (stop < n && !(stamp[stop] > time_scan_end + 0.01)) ++stop;
+    const int seen = stop < n ? stop + 1 : n;
+    if (orientation_xyzw && rpy_init) {
+        int newest = -1;
+        for (int i = first; i < seen; ++i)
+            if (stamp[i] <= time_scan_cur) newest = i;
+        if (newest >= 0) {
+            double r, p, y;
+            quat_to_rpy_tf(orientation_xyzw + 4 * (size_t)newest, &r, &p, &y);
+            rpy_init[0] = (float)r; rpy_init[1] = (float)p; rpy_init[2] = (float)y;
+        }
+    }
+    const int count = stop - first;
+    if (count > capacity) {
+        b2::set_error("b2_imu_deskew_info: %d gyro samples in the scan window, table holds %d (queueLength, imageProjection.cpp:45)", count, capacity);
+        return B2_ERR_CAPACITY;
+    }
+    double ax = 0, ay = 0, az = 0;
+    for (int k = 0; k < count; ++k) {
+        const int i = first + k;
+        if (k > 0) {
+            const double dt = stamp[i] - imu_time[k - 1];
+            ax = ax + angular_velocity[3 * (size_t)i + 0] * dt;
+            ay = ay + angular_velocity[3 * (size_t)i + 1] * dt;
+            az = az + angular_velocity[3 * (size_t)i + 2] * dt;
+        }
+        imu_time[k] = stamp[i]; imu_rot_x[k] = ax; imu_rot_y[k] = ay; imu_rot_z[k] = az;
+    }
+    *n_table = count;                           // imuPointerCur == count - 1 after the decrement of :356
+    *imu_available = count - 1 > 0 ? 1 : 0;
+    return B2_OK;
+}
+
 
 // ================================================================================================================
 // cloud_info wire format: msg/cloud_info.msg:1-35, ROS1 serialisation — little endian, arrays and

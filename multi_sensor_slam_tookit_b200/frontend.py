@@ -90,6 +90,11 @@ class ScanFrontEnd:
         capi.check(capi.lib().b2_scan_last_gpu_ms(self._h, C.byref(ms)))
         return ms.value
 
+    def imuDeskewInfo(self, imuQueue, timeScanCur, timeScanEnd):
+        """ImageProjection::imuDeskewInfo (imageProjection.cpp:305-362), see imu_deskew_info below; the returned dict's
+        'imu' entry is what projectPointCloud takes."""
+        return imu_deskew_info(imuQueue, timeScanCur, timeScanEnd)
+
     # ---- lio_sam/cloud_info between the stages (SURVEY.md 8f N4)
     def _write(self, stage, meta):
         m = cloud_info_meta(**(meta or {}))
@@ -114,6 +119,34 @@ class ScanFrontEnd:
         capi.check(capi.lib().b2_scan_set_from_cloud_info(self._h, capi.ptr(raw), raw.size, C.byref(m)))
         self.n_extracted = m.value
         return self.extractFeatures()
+
+
+QUEUE_LENGTH = 2000          # imageProjection.cpp:45
+
+
+def imu_deskew_info(imuQueue, timeScanCur, timeScanEnd, capacity=QUEUE_LENGTH):
+    """imuQueue: (stamp (n,), orientation_xyzw (n, 4) or None, angular_velocity (n, 3)) in arrival order, after imuConverter.
+    Returns imu = (imuTime, imuRotX, imuRotY, imuRotZ) for projectPointCloud, imuAvailable, n_popped (messages the reference
+    pops from the queue front), and imuRollInit / imuPitchInit / imuYawInit (None when no message precedes the scan start).
+    Host-only helper of the library (b2_imu_deskew_info): the table is a serial double recurrence of a few dozen terms."""
+    stamp, quat, gyro = imuQueue
+    stamp = np.ascontiguousarray(stamp, np.float64).reshape(-1)
+    gyro = np.ascontiguousarray(gyro, np.float64).reshape(-1, 3)
+    quat = None if quat is None else np.ascontiguousarray(quat, np.float64).reshape(-1, 4)
+    n = len(stamp)
+    if len(gyro) != n or (quat is not None and len(quat) != n):
+        raise ValueError("imuQueue arrays differ in length")
+    t, rx, ry, rz = (np.zeros(capacity, np.float64) for _ in range(4))
+    nt, npop, avail = C.c_int(0), C.c_int(0), C.c_int(0)
+    rpy = np.full(3, np.nan, np.float32)
+    capi.check(capi.lib().b2_imu_deskew_info(capi.ptr(stamp), capi.ptr(quat), capi.ptr(gyro), n, float(timeScanCur), float(timeScanEnd),
+                                             capi.ptr(t), capi.ptr(rx), capi.ptr(ry), capi.ptr(rz), capacity,
+                                             C.byref(nt), C.byref(npop), C.byref(avail), capi.ptr(rpy)))
+    k = nt.value
+    has_rpy = not np.isnan(rpy[0])
+    return dict(imu=(t[:k].copy(), rx[:k].copy(), ry[:k].copy(), rz[:k].copy()), imuAvailable=bool(avail.value), n_popped=npop.value,
+                imuRollInit=float(rpy[0]) if has_rpy else None, imuPitchInit=float(rpy[1]) if has_rpy else None,
+                imuYawInit=float(rpy[2]) if has_rpy else None)
 
 
 def cloud_info_meta(seq=0, stamp=(0, 0), frame_id="", lidarFrame="", imuAvailable=0, odomAvailable=0, imuRollInit=0.0,

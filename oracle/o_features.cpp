@@ -2,6 +2,7 @@
 //
 // CPU restatement of LIO-SAM's per-scan front end:
 //   liosam_ws/src/LIO-SAM/src/imageProjection.cpp
+//     imuDeskewInfo :305-362 (+ imuRPY2rosRPY, utility.h:322-334),
 //     findRotation :446-471, findPosition :473-487 (returns 0), deskewPoint :489-519,
 //     projectPointCloud :521-572, cloudExtraction :574-598
 //   liosam_ws/src/LIO-SAM/src/featureExtraction.cpp
@@ -274,6 +275,77 @@ int o_extract_features(const float* extracted, const int* pointColInd, int cloud
     surf_ring_start[N_SCAN] = nsurf;
     *n_surf_cand = nsurf; *n_surf_ds = nds;
     return ncorner;
+}
+
+// imuDeskewInfo (imageProjection.cpp:305-362), with imuRPY2rosRPY / imuAngular2rosAngular (utility.h:304-334).
+// The queue is given as arrays in arrival order: stamp[n] (header.stamp.toSec()), orientation quaternion xyzw[n*4],
+// angular velocity[n*3] — already passed through imuConverter by imuHandler (:203-204). tf::Matrix3x3(q).getRPY is
+// restated from tf's LinearMath (Matrix3x3::setRotation + getEulerYPR, solution 1), all in double.
+// Returns what the function leaves behind: *n_popped queue entries dropped from the front (:309-315), the table
+// imuTime / imuRot{X,Y,Z}[0 .. *n_table) where *n_table - 1 == imuPointerCur after the final decrement (:356),
+// *imu_available (:361), and the roll / pitch / yaw of the last message at or before timeScanCur narrowed to the
+// float32 fields of cloud_info (:329-330; untouched when no message qualifies).
+// The reference's arrays hold queueLength = 2000 entries (:45) and are not bounds-checked; `capacity` plays that role
+// here and -1 is returned instead of writing past it.
+int o_imu_deskew_info(const double* stamp, const double* quat_xyzw, const double* gyro, int n,
+                      double timeScanCur, double timeScanEnd,
+                      double* imuTime, double* imuRotX, double* imuRotY, double* imuRotZ, int capacity,
+                      int* n_table, int* n_popped, int* imu_available, float* rpy_init) {
+    *imu_available = 0;                                                    // cloudInfo.imuAvailable = false
+    int front = 0;
+    while (front < n) {                                                    // while (!imuQueue.empty())
+        if (stamp[front] < timeScanCur - 0.01) ++front;                    //   pop_front()
+        else break;
+    }
+    *n_popped = front;
+    *n_table = 0;
+    if (front == n) return 0;                                              // if (imuQueue.empty()) return;
+    int imuPointerCur = 0;
+    for (int i = front; i < n; ++i) {
+        double currentImuTime = stamp[i];
+        if (currentImuTime <= timeScanCur) {
+            const double x = quat_xyzw[4 * i + 0], y = quat_xyzw[4 * i + 1], z = quat_xyzw[4 * i + 2], w = quat_xyzw[4 * i + 3];
+            double d = x * x + y * y + z * z + w * w;
+            double s = 2.0 / d;
+            double xs = x * s, ys = y * s, zs = z * s;
+            double wx = w * xs, wy = w * ys, wz = w * zs;
+            double xx = x * xs, xy = x * ys, xz = x * zs;
+            double yy = y * ys, yz = y * zs, zz = z * zs;
+            double m00 = 1.0 - (yy + zz), m10 = xy + wz, m20 = xz - wy, m21 = yz + wx, m22 = 1.0 - (xx + yy);
+            double roll, pitch, yaw;
+            if (std::fabs(m20) >= 1) {
+                yaw = 0;
+                double delta = std::atan2(m21, m22);
+                if (m20 < 0) { pitch = M_PI / 2.0; roll = delta; }
+                else         { pitch = -M_PI / 2.0; roll = delta; }
+            } else {
+                pitch = -std::asin(m20);
+                roll = std::atan2(m21 / std::cos(pitch), m22 / std::cos(pitch));
+                yaw = std::atan2(m10 / std::cos(pitch), m00 / std::cos(pitch));
+            }
+            rpy_init[0] = (float)roll; rpy_init[1] = (float)pitch; rpy_init[2] = (float)yaw;
+        }
+        if (currentImuTime > timeScanEnd + 0.01) break;
+        if (imuPointerCur >= capacity) return -1;
+        if (imuPointerCur == 0) {
+            imuRotX[0] = 0; imuRotY[0] = 0; imuRotZ[0] = 0;
+            imuTime[0] = currentImuTime;
+            ++imuPointerCur;
+            continue;
+        }
+        double angular_x = gyro[3 * i + 0], angular_y = gyro[3 * i + 1], angular_z = gyro[3 * i + 2];
+        double timeDiff = currentImuTime - imuTime[imuPointerCur - 1];
+        imuRotX[imuPointerCur] = imuRotX[imuPointerCur - 1] + angular_x * timeDiff;
+        imuRotY[imuPointerCur] = imuRotY[imuPointerCur - 1] + angular_y * timeDiff;
+        imuRotZ[imuPointerCur] = imuRotZ[imuPointerCur - 1] + angular_z * timeDiff;
+        imuTime[imuPointerCur] = currentImuTime;
+        ++imuPointerCur;
+    }
+    --imuPointerCur;
+    *n_table = imuPointerCur + 1;
+    if (imuPointerCur <= 0) return 0;
+    *imu_available = 1;
+    return 0;
 }
 
 }  // extern "C"

@@ -81,6 +81,9 @@ def lib():
                             f64p, f64p, f64p, f64p, C.c_int, C.c_double, C.c_int,
                             f32p, f32p, i32p, f32p, i32p, f32p, i32p, i32p]
     L.o_curvature_masks.argtypes = [f32p, i32p, C.c_int, f32p, i32p, i32p]
+    L.o_imu_deskew_info.restype = C.c_int
+    L.o_imu_deskew_info.argtypes = [f64p, f64p, f64p, C.c_int, C.c_double, C.c_double, f64p, f64p, f64p, f64p, C.c_int,
+                                    C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), f32p]
     L.o_extract_features.restype = C.c_int
     L.o_extract_features.argtypes = [f32p, i32p, C.c_int, i32p, i32p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int,
                                      f32p, i32p, i32p, i32p, i32p, i32p, f32p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -252,6 +255,26 @@ def project(raw_xyzirt, N_SCAN, H, imu=None, t_cur=0.0, downsample=1, rmin=1.0, 
                     1 if deskew else -1, rm, fc, win, ext, col, rng, sr, er)
     return dict(range_mat=rm.reshape(N_SCAN, H), full_cloud=fc, winner=win.reshape(N_SCAN, H), extracted=ext[:m].copy(),
                 pointColInd=col[:m].copy(), pointRange=rng[:m].copy(), startRingIndex=sr, endRingIndex=er)
+
+
+def imu_deskew_info(stamp, quat_xyzw, gyro, t_cur, t_end, capacity=2000):
+    """imuDeskewInfo restatement (imageProjection.cpp:305-362). Returns dict(imu=(t, rx, ry, rz), imuAvailable, n_popped, rpy)."""
+    stamp = np.ascontiguousarray(stamp, np.float64).reshape(-1)
+    n = len(stamp)
+    quat = np.ascontiguousarray(quat_xyzw if quat_xyzw is not None else np.tile([0.0, 0, 0, 1], (max(n, 1), 1)), np.float64).reshape(-1, 4)
+    gyro = np.ascontiguousarray(gyro, np.float64).reshape(-1, 3)
+    if n == 0:
+        stamp, quat, gyro = np.zeros(1), np.zeros((1, 4)), np.zeros((1, 3))
+    t, rx, ry, rz = (np.zeros(capacity, np.float64) for _ in range(4))
+    nt, npop, avail = C.c_int(0), C.c_int(0), C.c_int(0)
+    rpy = np.full(3, np.nan, np.float32)
+    st = lib().o_imu_deskew_info(stamp, quat, gyro, n, float(t_cur), float(t_end), t, rx, ry, rz, capacity,
+                                 C.byref(nt), C.byref(npop), C.byref(avail), rpy)
+    if st != 0:
+        raise RuntimeError("imu table overflow")
+    k = nt.value
+    return dict(imu=(t[:k].copy(), rx[:k].copy(), ry[:k].copy(), rz[:k].copy()), imuAvailable=bool(avail.value), n_popped=npop.value,
+                rpy=None if np.isnan(rpy[0]) else rpy.copy())
 
 
 def curvature_masks(pointRange, pointColInd):
