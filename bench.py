@@ -3,11 +3,13 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B]
 
-One JSON line on stdout (rank 0). A "step" is one scan2MapOptimization call: the LM loop of
-liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:1282-1310 on one VLP-16 scan against the 100 000-point map.
-  value      LM iterations/s with map and scan already resident in HBM (device time, CUDA events on the library's
-             stream, L2 flushed between steps)
-  e2e        the same through the C ABI with HOST buffers: set_map + set_scan + solve per step, wall clock
+One JSON line on stdout (rank 0). A "step" is what the reference does per scan in scan2MapOptimization
+(liosam_ws/src/LIO-SAM/src/mapOptmization.cpp:1282-1310): index build of the two map clouds (kdtree->setInputCloud, :1289-1290)
++ the LM loop, one VLP-16 scan against the 100 000-point map. BOTH arms time this step (config.step is identical).
+  value      LM iterations/s of that step with map points and scan features already resident in HBM (device time, CUDA
+             events on the library's streams from the start of the index build to the end of the solve, L2 flushed between steps)
+  solve_only the LM loop alone on a resident index (pairs with cpu_baseline.solve_only)
+  e2e        the same step through the C ABI with HOST buffers: set_map + set_scan + solve per step, wall clock
   roofline   k_s2m_iteration: algorithmic bytes (72 B + 16 B per candidate in the 27-cell block, per feature) over
              the measured launch time, against MEASURED_PEAKS.json's HBM copy bandwidth
   batched    B scans (pose hypotheses) against the one map in a single launch per iteration
@@ -32,6 +34,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "scan_to_map_lm_iters_per_sec"
 UNIT = "iters/s"
+# the step both arms time (the driver compares the two lines; they must describe the same work)
+STEP = "index build of both map clouds (kdtree setInputCloud x2, mapOptmization.cpp:1289-1290) + scan2MapOptimization loop (<=30 LM iterations, stops on convergence)"
 
 
 def load_c1():
@@ -150,6 +154,18 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def host_cores():
+    """Threads for the CPU arm: the cores this process may run on, minus one per other rank of the job (while rank 0 times the
+    CPU path the other ranks sit in a collective, each spinning on one core; an OpenMP team that is one thread wider than the
+    free cores collapses — SCALE_r01 showed 67-89 iters/s instead of 2 300). torchrun exports OMP_NUM_THREADS=1, but the
+    oracle's parallel regions carry an explicit num_threads clause; the team size really obtained is what gets reported."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, n - (int(os.environ.get("WORLD_SIZE", "1")) - 1))
+
+
 def cpu_solve_rate(c1, threads, budget_s, include_build):
     """iters/s of the CPU restatement: solve only (trees built) or set_map + set_scan + solve per step."""
     from oracle import pyoracle as O
@@ -175,7 +191,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     c1 = load_c1()
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     t_all = time.perf_counter()
     # warm-up and timed steps: one step = kd-tree build of both maps + the LM loop (what the reference does per scan)
     from oracle import pyoracle as O
@@ -186,19 +202,22 @@ def run_reference(args, rank, world):
         return s.solve(c1["pose_guess"])["iters"]
     for _ in range(max(args.warmup, 3)):
         step()
-    iters, t0 = 0, time.perf_counter()
+    iters, per_step, t0 = 0, [], time.perf_counter()
     for _ in range(args.steps):
+        ts = time.perf_counter()
         iters += step()
+        per_step.append(time.perf_counter() - ts)
     el = time.perf_counter() - t0
     val = iters / el
+    used = O.omp_threads(cores)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(c1), "step": "kd-tree build (both maps) + scan2MapOptimization loop",
-                       "iters_per_step": iters / args.steps},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+            "config": {"workload": workload_name(c1), "step": STEP, "iters_per_step": iters / args.steps,
+                       "median_ms_per_step": 1e3 * float(np.median(per_step))},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": used, "kind": "port",
                              "sample": f"{args.steps} full steps (index build + LM loop) of the same workload, OpenMP over features "
-                                       f"as mapOptmization.cpp:978,1070, {cores} threads"},
+                                       f"as mapOptmization.cpp:978,1070, {used} threads (the reference ships numberOfCores: 4)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
     emit(line)
@@ -248,16 +267,21 @@ def run_b200(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    # ---- value: resident inputs, device time of each step (events on the library's stream)
+    # ---- value: map points and scan features resident in HBM; one step = index build of both maps + LM loop (the reference's
+    # per-scan step); device time from the start of the build to the end of the solve (events on the library's streams)
+    for _ in range(W):
+        flush_l2(); g.rebuildMapIndex(); solve()
     barrier()
     l0 = L.b2_kernel_launch_count()
-    dev_ms, wall_ms, iters = 0.0, 0.0, 0
+    dev_ms, wall_ms, iters, solve_ms = 0.0, 0.0, 0, 0.0
     for _ in range(K):
         flush_l2()
         t0 = time.perf_counter()
+        g.rebuildMapIndex()
         r = solve()
         wall_ms += (time.perf_counter() - t0) * 1e3
-        dev_ms += g.lastGpuMs()[0]
+        dev_ms += g.lastStepGpuMs()
+        solve_ms += g.lastGpuMs()[0]
         iters += r["iters"]
     launches = L.b2_kernel_launch_count() - l0
     barrier()
@@ -330,12 +354,12 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.stop() if sampler else None
 
     # ---- reductions over ranks: units summed, time = max
-    t = torch.tensor([dev_ms, e2e_s, act_ms, wall_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_s, act_ms, wall_ms, solve_ms], dtype=torch.float64, device="cuda")
     u = torch.tensor([iters, e_iters], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(u, op=dist.ReduceOp.SUM)
-    dev_ms_m, e2e_s_m, act_ms_m, wall_ms_m = [float(v) for v in t.tolist()]
+    dev_ms_m, e2e_s_m, act_ms_m, wall_ms_m, solve_ms_m = [float(v) for v in t.tolist()]
     iters_all, e_iters_all = [float(v) for v in u.tolist()]
     del g, flush
     L.b2_trim_memory()
@@ -349,15 +373,17 @@ def run_b200(args, rank, local_rank, world):
             "metric": METRIC, "value": iters_all / (dev_ms_m * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms_m / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(c1), "step": "scan2MapOptimization loop (<=30 LM iterations, stops on convergence)",
+            "config": {"workload": workload_name(c1), "step": STEP,
                        "iters_per_step": iters / K, "l2": "flushed between steps (256 MiB device write)",
                        "parallelism": f"replicas x{world} (C1 does not shard; no data-path collective)",
-                       "timing": "device ms per step = CUDA events on the library stream around each solve",
+                       "timing": "device ms per step = CUDA events on the library's streams, start of the index build -> end of the solve",
                        "wall_ms_per_step": wall_ms_m / K},
+            "solve_only": {"value": iters_all / (solve_ms_m * 1e-3), "unit": UNIT, "ms_per_step": solve_ms_m / K,
+                           "step": "scan2MapOptimization loop on a resident index (pairs with cpu_baseline.solve_only)"},
             "e2e": {"value": e_iters_all / e2e_s_m, "unit": UNIT,
                     "h2d_bytes_per_step": int(mc.nbytes + ms.nbytes + sc.nbytes + ss.nbytes + 592 + 16),
                     "d2h_bytes_per_step": int(592 + 4 + 2 * 24), "ms_per_step": 1e3 * e2e_s_m / K,
-                    "step": "b2_s2m_set_map + b2_s2m_set_scan + b2_s2m_solve with pinned host buffers"},
+                    "step": "the same step from HOST buffers: b2_s2m_set_map (upload + index build) + b2_s2m_set_scan + b2_s2m_solve, pinned memory, wall clock"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_s2m_iteration", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic("k_s2m_iteration"), "peak_source": peak_src,
@@ -374,7 +400,7 @@ def run_b200(args, rank, local_rank, world):
             dc, ds_ = O.voxel_grid(cat_c, 0.2)["out"], O.voxel_grid(cat_s, 0.4)["out"]
             so.set_map(dc, ds_); so.set_scan(c1["scan_corner"], c1["scan_surf"])
             return so.solve(c1["pose_guess"])["iters"]
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         so = O.Scan2Map(cores)
         cpu_lm_step()
         ci, t0 = 0, time.perf_counter()
@@ -393,14 +419,16 @@ def run_b200(args, rank, local_rank, world):
             batched["roofline"] = {"achieved": bb, "peak": peak, "unit": "GB/s", "frac": bb / peak,
                                    "note": "algorithmic bytes of all active (scan, iteration) pairs / device span of the step"}
             line["batched"] = batched
-        # CPU baseline on this box's host cores, bounded sample
-        cores = os.cpu_count() or 1
-        v_solve, st1, el1, it1 = cpu_solve_rate(c1, cores, 6.0, False)
-        v_full, st2, el2, _ = cpu_solve_rate(c1, cores, 6.0, True)
-        v_4, _, _, _ = cpu_solve_rate(c1, min(4, cores), 3.0, False)
-        line["cpu_baseline"] = {"value": v_solve, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{st1} solves of the same scan/map in {el1:.1f} s (kd-trees prebuilt), {it1} iterations each",
-                                "with_index_build": v_full, "threads4": v_4,
+        # CPU baseline on this box's host cores, bounded samples of the same step
+        cores = host_cores()
+        used = O.omp_threads(cores)
+        v_full, st2, el2, it1 = cpu_solve_rate(c1, cores, 6.0, True)
+        v_solve, st1, el1, _ = cpu_solve_rate(c1, cores, 6.0, False)
+        v_4, _, _, _ = cpu_solve_rate(c1, min(4, cores), 3.0, True)
+        line["cpu_baseline"] = {"value": v_full, "unit": UNIT, "cores": used, "kind": "port",
+                                "sample": f"{st2} steps (kd-tree build of both maps + LM loop, {it1} iterations each) of the same scan/map in {el2:.1f} s",
+                                "solve_only": v_solve, "solve_only_sample": f"{st1} solves in {el1:.1f} s, kd-trees prebuilt",
+                                "threads4": v_4, "threads4_note": "the same step at the reference's shipped numberOfCores: 4 (config/params.yaml:72)",
                                 "note": "CPU restatement of the reference path (oracle/), OpenMP over features as the reference"}
         if registration:
             line["registration"] = registration
@@ -481,7 +509,7 @@ def run_registration(args, rank, local_rank, world, dist, torch):
     wall = allmax(c4["wall_s"]); gpu_ms = allmax(c4["gpu_ms"]); evals = allsum(c4["src_evals"]); npairs = allsum(c4["pairs"])
     iters = allsum(c4["iters"]); launches = allsum(c4["launches"]); terr = allmax(c4["max_t_err"]); rerr = allmax(c4["max_r_err"])
     if rank == 0:
-        ev, tt, tr, it = GB.cpu_c4_pair(os.cpu_count() or 1)
+        ev, tt, tr, it = GB.cpu_c4_pair(host_cores())
         ach = 144.0 * evals / (gpu_ms * 1e-3) / 1e9 / world
         out["gicp_c4"] = {
             "workload": f"C4 Multi_LiCa GICP: 5 lidars 64x1024, {int(npairs)} ordered pairs, voxel 0.05, max_corr 1.0, eps 0.005, 1e-7/1e-7, 100 its",
@@ -492,7 +520,7 @@ def run_registration(args, rank, local_rank, world, dist, torch):
             "roofline": {"kernel": "k_gicp_linearize", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": None, "peak_source": peak_src,
                          "note": "144 B per source point per linearisation (SURVEY.md 8d), per GPU; ~50 k-point clouds: launch/latency bound"},
-            "cpu_baseline": {"value": ev / tr / 1e6, "unit": "Mpts/s", "cores": os.cpu_count() or 1, "kind": "port",
+            "cpu_baseline": {"value": ev / tr / 1e6, "unit": "Mpts/s", "cores": host_cores(), "kind": "port",
                              "sample": f"pair (1 -> 0): {it} iterations in {tr:.3f} s (registration only), {tt:.3f} s with downsampling + normals",
                              "e2e_value": ev / tt / 1e6}}
     # ---- C5: one registration, source sharded over the ranks, 30 doubles all-reduced per iteration
@@ -525,7 +553,7 @@ def run_registration(args, rank, local_rank, world, dist, torch):
             from oracle import pyoracle as O
             n = args.c5_cpu_points
             s_, t_, _ = GB.c5_clouds_torch(n, "cuda")
-            cores = os.cpu_count() or 1
+            cores = host_cores()
             _, sc = O.gicp_normals_covs(s_, 30, 0.005, cores)
             _, tc = O.gicp_normals_covs(t_, 30, 0.005, cores)
             go = O.GicpOracle(s_, sc, t_, tc, cores)

@@ -144,6 +144,12 @@ int  b2_s2m_solve_batch(b2_s2m_t h, float* poses, int max_iterations, int* iters
 /* Timing hooks for bench.py: GPU time in ms of the last solve / solve_batch call, measured with CUDA events
  * on the handle's own stream (torch.cuda.Event only sees torch's stream), and the kernel launches it made. */
 int  b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches);
+/* The two setInputCloud calls of mapOptmization.cpp:1289-1290 once more, on the map clouds the last b2_s2m_set_map /
+ * b2_s2m_set_map_from_localmap left in device memory (the reference rebuilds both kd-trees for every scan). Returns with the
+ * builds queued, like b2_s2m_set_map. b2_s2m_last_step_gpu_ms: device time from the start of that rebuild to the end of the
+ * solve that followed it (CUDA events) = one reference step "index build + LM loop" with the inputs resident in HBM. */
+int  b2_s2m_rebuild_map_index(b2_s2m_t h);
+int  b2_s2m_last_step_gpu_ms(b2_s2m_t h, float* ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Local-map assembly — replaces mapOptimization::extractCloud and the containers behind it

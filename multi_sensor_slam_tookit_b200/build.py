@@ -34,10 +34,12 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in sources() + _headers())
 
 
-def build_lib(force=False, verbose=False):
+def build_lib(force=False, verbose=False, variant=None, variant_flags=()):
     """One object per .cu (compiled in parallel, rebuilt only when the source or a header is newer), then one link.
-    No relocatable device code: the translation units only share host functions."""
-    if not force and not _stale():
+    No relocatable device code: the translation units only share host functions.
+    variant / variant_flags: kernel experiments — a second library variants/libb2reg_<variant>.so built with extra -D flags
+    (selected at run time with B2_LIB=...)."""
+    if variant is None and not force and not _stale():
         return LIB
     from concurrent.futures import ThreadPoolExecutor
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -45,8 +47,12 @@ def build_lib(force=False, verbose=False):
     # the image exports CXX=/opt/gcc/bin/g++ whose driver lacks libgomp specs; nvcc only needs a plain host g++
     if os.path.exists("/usr/bin/g++"):
         base += ["-ccbin", "/usr/bin/g++"]
-    extra = os.environ.get("B2_NVCC_EXTRA", "").split()
-    objdir = os.path.join(HERE, "build")
+    extra = os.environ.get("B2_NVCC_EXTRA", "").split() + list(variant_flags)
+    objdir = os.path.join(HERE, "build" if variant is None else os.path.join("build", variant))
+    lib_out = LIB
+    if variant is not None:
+        os.makedirs(os.path.join(HERE, "variants"), exist_ok=True)
+        lib_out = os.path.join(HERE, "variants", f"libb2reg_{variant}.so")
     os.makedirs(objdir, exist_ok=True)
     hdr_t = max(os.path.getmtime(h) for h in _headers())
     tag = os.path.join(objdir, ".flags")
@@ -67,11 +73,11 @@ def build_lib(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(compile_one, sources()))
     open(tag, "w").write(flags_now)
-    cmd = base + ["-shared", "-o", LIB] + objs
+    cmd = base + ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib_out] + objs
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)
-    return LIB
+    return lib_out
 
 
 if __name__ == "__main__":

@@ -89,8 +89,13 @@ struct GridDev {               // passed by value to kernels
     int n;
     float max_d2;              // candidates at or beyond this squared distance are never reported (max_dist^2)
 };
+// GridDev as it lives in device memory when the device sizes the grid itself (GridIndex::build_async): the geometry, the
+// bounding-box words the build reduces into, and a status (0 ok, B2_ERR_TOO_LARGE when the cells exceed the allocated table).
+struct GridDevMem { GridDev g; uint32_t bb[6]; int status; uint32_t pad; };
 struct GridIndex {
     DevBuf pts, cell_start, cell_of, tmp, raw;
+    DevBuf devmem;                                 // GridDevMem
+    size_t cell_budget = 0;                        // cells the allocated cell_start can hold (device-sized builds)
     PinBuf stage;
     GridDev dev{};
     float h = 1.0078125f;
@@ -105,7 +110,24 @@ struct GridIndex {
         int st = begin(host_pts, stride, n, max_dist, s);
         return st != B2_OK ? st : finish(s);
     }
-    void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); bb_ready_ = false; }
+    // Device-sized build, no host round trip: upload_async queues the copy of the caller's points (or adopts device points),
+    // build_async queues ONE cooperative kernel that reduces the bounding box, derives the grid geometry from it with the
+    // arithmetic of finish(), counting-sorts the points and leaves the GridDev in devmem. Consumers read dev_ptr(). If the
+    // box needs more cells than the table holds the kernel only sets the status; rebuild_exact() then takes the
+    // host-sized path (begin_device + finish), stores its GridDev in devmem and raises the budget.
+    int upload_async(const void* host_pts, const void* dev_pts, size_t stride, size_t n, float max_dist, cudaStream_t s, bool copy_dev = false);
+    int build_async(cudaStream_t s);
+    int rebuild_exact(cudaStream_t s);
+    const GridDevMem* dev_ptr() const { return devmem.as<GridDevMem>(); }
+    void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); devmem.release(); cell_budget = 0; bb_ready_ = false; }
+    // developer timeline (B2_S2M_TIMELINE=1): events after the upload, after the bounding box + read-back, after the build
+    cudaEvent_t tl_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool tl_on = false;
+    void tl_rec(int i, cudaStream_t s) {
+        if (!tl_on) return;
+        if (!tl_ev[i]) cudaEventCreate(&tl_ev[i]);
+        cudaEventRecord(tl_ev[i], s);
+    }
     size_t stride_ = 0; float max_dist_ = 1.f;
     bool bb_ready_ = false;                       // the bounding-box words in tmp are already reset (by the last scatter)
     const unsigned char* src_ = nullptr;          // device points the build reads (raw.p after an upload)

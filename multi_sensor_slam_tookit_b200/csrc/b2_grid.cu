@@ -183,11 +183,13 @@ int GridIndex::begin(const void* host_pts, size_t stride, size_t n_, float max_d
         return B2_OK;
     }
     if (n > 0x7fffffffull) { set_error("grid index: too many points (%zu)", n); return B2_ERR_ARG; }
+    tl_rec(0, s);
     if (host_pts) {
         B2_CHECK(raw.reserve(n * stride));
         B2_CUDA(cudaMemcpyAsync(raw.p, host_pts, n * stride, cudaMemcpyHostToDevice, s));
         src_ = raw.as<unsigned char>();
     }
+    tl_rec(1, s);
     // bbox on device, one small readback to size the cell table
     B2_CHECK(tmp.reserve(64));
     uint32_t* bb = tmp.as<uint32_t>();
@@ -198,6 +200,7 @@ int GridIndex::begin(const void* host_pts, size_t stride, size_t n_, float max_d
     B2_CUDA(cudaGetLastError());
     B2_CHECK(stage.reserve(64));
     B2_CUDA(cudaMemcpyAsync(stage.p, bb, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    tl_rec(2, s);
     return B2_OK;
 }
 
@@ -256,10 +259,235 @@ int GridIndex::finish(cudaStream_t s) {
         k_cell_scatter<<<nblk, 256, 0, s>>>(src_, stride, (uint32_t)n, d_cell, d_rank, cell_start.as<uint32_t>(), pts.as<float4>(), tmp.as<uint32_t>()); count_launch();
         B2_CUDA(cudaGetLastError());
     }
+    tl_rec(3, s);
     bb_ready_ = true;
     dev.pts = pts.as<float4>(); dev.cell_start = cell_start.as<uint32_t>();
     dev.ox = g.ox; dev.oy = g.oy; dev.oz = g.oz; dev.inv_h = g.inv_h; dev.h = h;
     dev.nx = g.nx; dev.ny = g.ny; dev.nz = g.nz; dev.n = (int)n; dev.max_d2 = max_dist * max_dist;
+    return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device-sized build
+// The same counting sort with the geometry decided on the device: bounding box | geometry + zeroed counts | cell + rank per
+// point | chunk totals | prefix sum | scatter, six phases of one cooperative launch. The host never waits for the bounding
+// box (that wait, two per scan, was a third of the end-to-end scan-to-map step).
+__global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, float h, float max_d2,
+                                                               uint32_t cell_budget, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank_in_cell,
+                                                               uint32_t* __restrict__ cell_start, uint32_t* __restrict__ chunk_sum,
+                                                               float4* __restrict__ out, GridDevMem* __restrict__ m) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t tid = blockIdx.x * GB_THREADS + threadIdx.x, nthr = gridDim.x * GB_THREADS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ uint32_t s_w[GB_THREADS / 32];
+    __shared__ uint32_t s_base;
+    __shared__ float s_mn[GB_THREADS / 32][3], s_mx[GB_THREADS / 32][3];
+    // ---- bounding box of the finite points
+    {
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = tid; i < n; i += nthr) {
+            const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+            const float x = p[0], y = p[1], z = p[2];
+            if (isfinite(x) && isfinite(y) && isfinite(z)) {
+                mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+                mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+                mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < 3; d++) { s_mn[warp][d] = mn[d]; s_mx[warp][d] = mx[d]; }
+        }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            const int d = threadIdx.x;
+            float a = s_mn[0][d], b = s_mx[0][d];
+            for (int w = 1; w < GB_THREADS / 32; w++) { a = fminf(a, s_mn[w][d]); b = fmaxf(b, s_mx[w][d]); }
+            if (a <= b) { atomicMin(&m->bb[d], float_flip(a)); atomicMax(&m->bb[3 + d], float_flip(b)); }
+        }
+    }
+    grid.sync();
+    // ---- geometry: every thread derives the same numbers (the arithmetic of GridIndex::finish)
+    GridGeom g;
+    {
+        float mn[3], mx[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) { mn[d] = float_unflip(__ldcg(&m->bb[d])); mx[d] = float_unflip(__ldcg(&m->bb[3 + d])); }
+        if (!(mn[0] <= mx[0])) { mn[0] = mn[1] = mn[2] = 0.f; mx[0] = mx[1] = mx[2] = 0.f; }     // no finite point
+        g.inv_h = 1.0f / h;
+        g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2];
+        double ex[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) ex[d] = floor(((double)mx[d] - (double)mn[d]) * (double)g.inv_h) + 2.0;
+        if (ex[0] * ex[1] * ex[2] > (double)cell_budget) {
+            if (tid == 0) m->status = B2_ERR_TOO_LARGE;      // bb is left as it is: rebuild_exact() resets it
+            return;                                          // uniform over the whole grid: nobody reaches another barrier
+        }
+        g.nx = (int)ex[0]; g.ny = (int)ex[1]; g.nz = (int)ex[2];
+        g.ncell = (uint32_t)((size_t)g.nx * g.ny * g.nz);
+    }
+    const uint32_t ncount = g.ncell + 2;
+    for (uint32_t i = tid; i < ncount; i += nthr) cell_start[i] = 0u;
+    grid.sync();
+    for (uint32_t i = tid; i < n; i += nthr) {
+        const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+        const uint32_t c = cell_of_point(g, p[0], p[1], p[2]);
+        cell_of[i] = c;
+        rank_in_cell[i] = atomicAdd(&cell_start[c], 1u);
+    }
+    grid.sync();
+    // ---- exclusive prefix sum of cell_start[0, ncount): one contiguous chunk per CTA
+    const uint32_t chunk = (ncount + gridDim.x - 1) / gridDim.x;
+    const uint32_t c0 = min(blockIdx.x * chunk, ncount), c1 = min(c0 + chunk, ncount);
+    auto block_sum = [&](uint32_t v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) s_w[warp] = v;
+        __syncthreads();
+        uint32_t t = 0;
+        for (int w = 0; w < GB_THREADS / 32; w++) t += s_w[w];
+        return t;
+    };
+    {
+        uint32_t v = 0;
+        for (uint32_t i = c0 + threadIdx.x; i < c1; i += GB_THREADS) v += cell_start[i];
+        v = block_sum(v);
+        if (threadIdx.x == 0) chunk_sum[blockIdx.x] = v;
+    }
+    grid.sync();
+    {
+        uint32_t v = 0;
+        for (uint32_t b = threadIdx.x; b < blockIdx.x; b += GB_THREADS) v += __ldcg(&chunk_sum[b]);
+        v = block_sum(v);
+        if (threadIdx.x == 0) s_base = v;
+        __syncthreads();
+    }
+    uint32_t running = s_base;
+    for (uint32_t t0 = c0; t0 < c1; t0 += GB_THREADS) {
+        const uint32_t i = t0 + threadIdx.x;
+        const uint32_t v = i < c1 ? cell_start[i] : 0u;
+        uint32_t inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        __syncthreads();
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        for (int w = 0; w < GB_THREADS / 32; w++) { const uint32_t t = s_w[w]; if (w < warp) before += t; total += t; }
+        if (i < c1) cell_start[i] = running + before + inc - v;
+        running += total;
+    }
+    grid.sync();
+    for (uint32_t i = tid; i < n; i += nthr) {
+        const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+        out[cell_start[cell_of[i]] + rank_in_cell[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
+    }
+    if (tid == 0) {
+        GridDev d;
+        d.pts = out; d.cell_start = cell_start;
+        d.ox = g.ox; d.oy = g.oy; d.oz = g.oz; d.inv_h = g.inv_h; d.h = h;
+        d.nx = g.nx; d.ny = g.ny; d.nz = g.nz; d.n = (int)n; d.max_d2 = max_d2;
+        m->g = d;
+        m->status = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) m->bb[k] = k < 3 ? 0xffffffffu : 0u;      // ready for the next build
+    }
+}
+
+static int grid_build_dev_max_ctas() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    int dev = 0, coop = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_build_dev, GB_THREADS, 0) != cudaSuccess) { cudaGetLastError(); cached = 0; return 0; }
+    cached = std::min(per_sm, 2) * device_sm_count();
+    return cached;
+}
+
+constexpr size_t GRID_DEFAULT_BUDGET = (size_t)4 << 20;       // cells of a device-sized table before anything is known: 16 MiB
+
+static int store_devmem(GridIndex& gi, const GridDev& d, int status, cudaStream_t s) {
+    GridDevMem hm{};
+    hm.g = d; hm.status = status;
+    for (int k = 0; k < 6; k++) hm.bb[k] = k < 3 ? 0xffffffffu : 0u;
+    B2_CUDA(cudaMemcpyAsync(gi.devmem.p, &hm, sizeof(hm), cudaMemcpyHostToDevice, s));   // pageable source: staged before the call returns
+    return B2_OK;
+}
+
+int GridIndex::upload_async(const void* host_pts, const void* dev_pts, size_t stride, size_t n_, float max_dist, cudaStream_t s, bool copy_dev) {
+    n = n_; stride_ = stride; max_dist_ = max_dist;
+    h = max_dist * 1.0078125f;
+    if (n > 0x7fffffffull) { set_error("grid index: too many points (%zu)", n); return B2_ERR_ARG; }
+    if (!devmem.p) {
+        B2_CHECK(devmem.reserve(sizeof(GridDevMem)));
+        GridDev none{};
+        B2_CHECK(store_devmem(*this, none, 0, s));
+    }
+    tl_rec(0, s);
+    if (n && host_pts) {
+        B2_CHECK(raw.reserve(n * stride));
+        B2_CUDA(cudaMemcpyAsync(raw.p, host_pts, n * stride, cudaMemcpyHostToDevice, s));
+        src_ = raw.as<unsigned char>();
+    } else if (n && dev_pts && copy_dev && dev_pts != raw.p) {
+        // device points owned by somebody else (the local map's VoxelGrid output): keep a private copy so that the build,
+        // which is still queued when this returns, does not depend on the owner leaving them alone
+        B2_CHECK(raw.reserve(n * stride));
+        B2_CUDA(cudaMemcpyAsync(raw.p, dev_pts, n * stride, cudaMemcpyDeviceToDevice, s));
+        src_ = raw.as<unsigned char>();
+    } else {
+        src_ = static_cast<const unsigned char*>(dev_pts);
+    }
+    tl_rec(1, s);
+    return B2_OK;
+}
+
+int GridIndex::build_async(cudaStream_t s) {
+    const float max_dist = max_dist_;
+    dev = GridDev{};                                  // the host copy is not valid after a device-sized build
+    if (n == 0) {
+        B2_CHECK(cell_start.reserve(3 * sizeof(uint32_t)));
+        B2_CUDA(cudaMemsetAsync(cell_start.p, 0, 3 * sizeof(uint32_t), s));
+        GridDev d{};
+        d.pts = nullptr; d.cell_start = cell_start.as<uint32_t>();
+        d.ox = d.oy = d.oz = 0.f; d.inv_h = 1.0f / h; d.h = h; d.nx = d.ny = d.nz = 1; d.n = 0; d.max_d2 = max_dist * max_dist;
+        dev = d;
+        return store_devmem(*this, d, 0, s);
+    }
+    const int coop_max = grid_build_dev_max_ctas();
+    if (coop_max <= 0) return rebuild_exact(s);
+    if (cell_budget == 0) cell_budget = GRID_DEFAULT_BUDGET;
+    B2_CHECK(cell_start.reserve((cell_budget + 2) * sizeof(uint32_t)));
+    const size_t nal = (n + 63) & ~(size_t)63;
+    B2_CHECK(cell_of.reserve(2 * nal * sizeof(uint32_t) + 4096));
+    B2_CHECK(pts.reserve(n * sizeof(float4)));
+    uint32_t* d_cell = cell_of.as<uint32_t>();
+    uint32_t* d_rank = d_cell + nal;
+    uint32_t* d_chunk = d_rank + nal;                 // chunk totals: at most 1024 CTAs
+    int ctas = (int)std::min<size_t>((size_t)coop_max, (std::max<size_t>(n, (size_t)1 << 18) + GB_THREADS * 4 - 1) / (GB_THREADS * 4));
+    ctas = std::max(1, std::min(ctas, 1024));
+    const unsigned char* a_raw = src_; size_t a_stride = stride_; uint32_t a_n = (uint32_t)n; float a_h = h, a_md2 = max_dist * max_dist;
+    uint32_t a_budget = (uint32_t)std::min<size_t>(cell_budget, 0xfffffff0u);
+    uint32_t* a_cs = cell_start.as<uint32_t>(); float4* a_out = pts.as<float4>(); GridDevMem* a_m = devmem.as<GridDevMem>();
+    void* args[] = {&a_raw, &a_stride, &a_n, &a_h, &a_md2, &a_budget, &d_cell, &d_rank, &a_cs, &d_chunk, &a_out, &a_m};
+    B2_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_grid_build_dev), dim3((unsigned)ctas), dim3(GB_THREADS), args, 0, s)); count_launch();
+    tl_rec(3, s);
+    return B2_OK;
+}
+
+int GridIndex::rebuild_exact(cudaStream_t s) {
+    const unsigned char* keep = src_;
+    B2_CHECK(begin_device(keep, stride_, n, max_dist_, s));
+    B2_CHECK(finish(s));
+    if (!devmem.p) B2_CHECK(devmem.reserve(sizeof(GridDevMem)));
+    B2_CHECK(store_devmem(*this, dev, 0, s));
+    const size_t cells = (size_t)dev.nx * dev.ny * dev.nz;
+    cell_budget = std::min<size_t>(GRID_MAX_CELLS, std::max(cell_budget, cells + cells / 2));
     return B2_OK;
 }
 

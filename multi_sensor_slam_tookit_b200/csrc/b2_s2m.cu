@@ -22,6 +22,14 @@
 #ifndef B2_FIT_VARIANT
 #define B2_FIT_VARIANT 1      // 0: rolled loops over per-thread arrays (small code); 1: fully unrolled, register resident
 #endif
+#ifndef B2_FIT_INLINE
+#define B2_FIT_INLINE 0       // 1: the two fits are inlined into the kernel (kernel experiments)
+#endif
+#if B2_FIT_INLINE
+#define B2_FIT_ATTR __forceinline__
+#else
+#define B2_FIT_ATTR __noinline__
+#endif
 
 namespace b2 {
 
@@ -31,7 +39,13 @@ constexpr int S2M_THREADS = 256;
 #define S2M_LAT_LPF_V 16
 #define S2M_LAT_ROUNDS_V 2
 #endif
-constexpr int S2M_LAT_LPF = S2M_LAT_LPF_V, S2M_LAT_ROUNDS = S2M_LAT_ROUNDS_V;   // single scan: 32 features per CTA, many small CTAs (latency)
+#ifndef S2M_LAT_ROUNDS_C_V
+#define S2M_LAT_ROUNDS_C_V 1
+#endif
+// single scan: 32 surf features per CTA, many small CTAs (latency). Corner CTAs make S2M_LAT_ROUNDS_C passes only: their line
+// fit (3x3 Jacobi, data-dependent rotation count) is the longest per-thread chain of the kernel — measured 23 k cycles against
+// 13 k for the plane fit — so they get through their neighbour search in half the time and start fitting early.
+constexpr int S2M_LAT_LPF = S2M_LAT_LPF_V, S2M_LAT_ROUNDS = S2M_LAT_ROUNDS_V, S2M_LAT_ROUNDS_C = S2M_LAT_ROUNDS_C_V;
 #ifndef S2M_THR_LPF_V
 #define S2M_THR_LPF_V 1
 #define S2M_THR_ROUNDS_V 1
@@ -41,6 +55,7 @@ constexpr int S2M_LAT_LPF = S2M_LAT_LPF_V, S2M_LAT_ROUNDS = S2M_LAT_ROUNDS_V;   
 #endif
 constexpr int S2M_THR_LPF = S2M_THR_LPF_V, S2M_THR_ROUNDS = S2M_THR_ROUNDS_V;   // batch: 256 features per CTA, every warp busy in phase 2 (throughput)
 constexpr int S2M_LAT_FPB = S2M_THREADS / S2M_LAT_LPF * S2M_LAT_ROUNDS;
+constexpr int S2M_LAT_FPB_C = S2M_THREADS / S2M_LAT_LPF * S2M_LAT_ROUNDS_C;
 constexpr int S2M_THR_FPB = S2M_THREADS / S2M_THR_LPF * S2M_THR_ROUNDS;
 constexpr int S2M_NPART = 28;                       // 21 (AtA upper) + 6 (Atb) + 1 (count)
 
@@ -57,11 +72,16 @@ struct S2MState {                 // one per scan in the batch, lives in HBM
     int n_sel;                    // laserCloudSelNum of the last iteration
     int ran;                      // 0 when n_sel < min_correspondences
     unsigned ticket;
-    int pad;
+    int grid_status;              // status words of the two device-sized map grids (0, or B2_ERR_TOO_LARGE: rebuild on the host path)
+};
+
+struct S2MInit {                  // initial state of a single-scan solve, carried by the first launch's arguments
+    float pose[6], xf[12], trig[6], matP[36];
+    int degenerate;
 };
 
 struct S2MArgs {
-    GridDev gc, gs;                               // corner / surf map grids
+    const GridDevMem* gcm; const GridDevMem* gsm; // corner / surf map grids (geometry in device memory: the device sized them)
     const float4* scan_c; const float4* scan_s;   // packed xyzi features, all scans concatenated
     const int* off_c; const int* off_s;           // batch+1 offsets
     S2MState* st;
@@ -76,7 +96,10 @@ struct S2MArgs {
     int* done_count;                              // number of scans whose loop has ended (host polls it between chunks)
     uint32_t* nb_c; uint32_t* nb_s;               // [feature][5] grid positions of the 5 winners of the previous iteration
     int use_prev;                                 // 1: nb_* hold the previous iteration of this scan/map; -1: they do when st.iters > 0; 0: no
-    long long* prof;                              // optional per-CTA clock64 stamps (B2_S2M_PROF=1), 8 per CTA
+    int use_init;                                 // 1: first launch of a single-scan solve, state = init (no upload, no state loads)
+    S2MInit init;
+    S2MState* result; volatile int* result_seq; int seq; int chunk_last;   // mapped host memory: state + sequence flag (single scan)
+    long long* prof;                              // optional per-CTA clock64 stamps (B2_S2M_PROF=1), 16 per CTA
     float* pose_hist; int hist_stride;            // optional [batch][max_iters][6]
     // optional per-feature introspection (single-scan parity runs)
     int32_t* dbg_idx_c; float* dbg_d2_c; float4* dbg_coeff_c; uint8_t* dbg_flag_c;
@@ -118,7 +141,7 @@ __global__ void k_s2m_prepare(S2MState* st, int batch, const int* off_c, const i
 
 // ---- per-feature fits -------------------------------------------------------------------------------------------
 // Returns true when the feature is kept; coeff = coeffSel entry.
-__device__ __noinline__ bool fit_line(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+__device__ B2_FIT_ATTR bool fit_line(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
                                          float x0, float y0, float z0, float4& coeff) {
     float cx = 0, cy = 0, cz = 0;
 #pragma unroll
@@ -158,7 +181,7 @@ __device__ __noinline__ bool fit_line(const float (&nx)[5], const float (&ny)[5]
     return s > 0.1;
 }
 
-__device__ __noinline__ bool fit_plane(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+__device__ B2_FIT_ATTR bool fit_plane(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
                                           float sx, float sy, float sz, float ox, float oy, float oz, float4& coeff) {
 #if B2_FIT_VARIANT == 1
     float pa, pb, pc, pd = 1;
@@ -182,7 +205,7 @@ __device__ __noinline__ bool fit_plane(const float (&nx)[5], const float (&ny)[5
 }
 
 // ---- epilogue: normal equations -> pose update (single thread) ------------------------------------------------------
-__device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, const S2MArgs& a, int scan) {
+__device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, const S2MArgs& a, int scan, long long* prof) {
     const int K = (int)(sums[27] + 0.5);
     s.n_sel = K;
     if (K < a.min_corr) {
@@ -217,6 +240,7 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
         for (int i = 0; i < 6; i++) X[i] = AtB[i];
         if (!solve_householder<6>(w, X)) for (int i = 0; i < 6; i++) X[i] = 0.f;
     }
+    if (prof) prof[8] = clock64();
     bool full_eigen = iterCount == 0;
     if (full_eigen && !a.want_matP) {
         // Degeneracy needs only "is the smallest eigenvalue below the threshold". LDL^T of (AtA - shift*I) in fp64 with
@@ -256,6 +280,7 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
         invert_lu<6>(w, Vi);
         matmul_dacc<6, 6>(Vi, V2, s.matP);
     }
+    if (prof) prof[9] = clock64();
     if (s.degenerate) {
         float X2[6];
         for (int i = 0; i < 6; i++) X2[i] = X[i];
@@ -273,6 +298,7 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
         for (int i = 0; i < 6; i++) ph[i] = s.pose[i];
     }
     s.iters += 1;
+    if (prof) prof[10] = clock64();
     if (a.device_driven) {
         if (conv) { s.done = 1; if (a.done_count) atomicAdd(a.done_count, 1); }
         else prepare_pose_device(s);
@@ -282,11 +308,12 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
 // LPF lanes serve one feature in phase 1; a CTA of 256 threads makes ROUNDS passes, so it owns
 // FPB = 256 / LPF * ROUNDS features and phase 2 runs on FPB threads (one warp for the latency shape <16,2>,
 // all eight warps for the throughput shape <8,8>).
-template <int LPF, int ROUNDS>
+template <int LPF, int ROUNDS, int ROUNDS_C>
 __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == S2M_THR_ROUNDS) ? S2M_THR_MINB : 1) k_s2m_iteration(const S2MArgs a) {
     constexpr int FPR = S2M_THREADS / LPF;
-    constexpr int FPB = FPR * ROUNDS;
-    static_assert(FPB <= S2M_THREADS && FPB % 32 == 0, "phase 2 maps one thread per feature in whole warps");
+    constexpr int FPB = FPR * ROUNDS;                 // features per surf CTA (and the size of the shared arrays)
+    constexpr int FPB_C = FPR * ROUNDS_C;             // features per corner CTA
+    static_assert(FPB <= S2M_THREADS && FPB % 32 == 0 && ROUNDS_C <= ROUNDS, "phase 2 maps one thread per feature in whole warps");
     constexpr int P2_WARPS = FPB / 32;
     // Programmatic dependent launch (single-scan shape): this grid may have been scheduled while the previous iteration was
     // still running; wait for it (and its writes) here, and let the next launch be scheduled behind us right away. Both are
@@ -295,20 +322,23 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     asm volatile("griddepcontrol.launch_dependents;");
     const int scan = blockIdx.y;
     S2MState& st = a.st[scan];
-    if (st.done) return;                                       // uniform per CTA, written only by a previous launch
+    const bool first = a.use_init != 0;                        // the state is in the launch arguments, not in memory yet
+    if (!first && st.done) return;                             // uniform per CTA, written only by a previous launch
     const int c0 = a.off_c[scan], nc = a.off_c[scan + 1] - c0;
     const int s0 = a.off_s[scan], ns = a.off_s[scan + 1] - s0;
-    const int nbc = (nc + FPB - 1) / FPB, nbs = (ns + FPB - 1) / FPB;
+    const int nbc = (nc + FPB_C - 1) / FPB_C, nbs = (ns + FPB - 1) / FPB;
     const int nblk = nbc + nbs;
     if ((int)blockIdx.x >= nblk) return;
     const bool is_surf = (int)blockIdx.x >= nbc;
-    const int fb = is_surf ? ((int)blockIdx.x - nbc) * FPB : (int)blockIdx.x * FPB;   // first feature of this CTA
+    const int fb = is_surf ? ((int)blockIdx.x - nbc) * FPB : (int)blockIdx.x * FPB_C;   // first feature of this CTA
+    const int rounds = is_surf ? ROUNDS : ROUNDS_C;
+    const int fpb = is_surf ? FPB : FPB_C;
     const int nfeat = is_surf ? ns : nc;
     const float4* scanp = is_surf ? (a.scan_s + s0) : (a.scan_c + c0);
-    const GridDev& g = is_surf ? a.gs : a.gc;
+    const GridDev g = is_surf ? a.gsm->g : a.gcm->g;
     // the pose moves by millimetres between LM iterations: the previous winners bound this iteration's search radius
     uint32_t* nbp = (is_surf ? a.nb_s + (size_t)s0 * 5 : a.nb_c + (size_t)c0 * 5);
-    const bool use_prev = LPF < 8 && (a.use_prev > 0 || (a.use_prev < 0 && st.iters > 0));
+    const bool use_prev = LPF < 8 && (a.use_prev > 0 || (a.use_prev < 0 && !first && st.iters > 0));
 
     __shared__ float4 s_nb[FPB][5];           // winners: x y z, original index bits
     __shared__ float s_d2[FPB][5];
@@ -316,19 +346,19 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     __shared__ float s_xf[12], s_trig[6];
     __shared__ int s_last;
     __shared__ double s_wsum[P2_WARPS][S2M_NPART];
-    __shared__ double s_red[S2M_THREADS / 32][S2M_NPART];
+    __shared__ double s_red[S2M_THREADS / S2M_NPART][S2M_NPART];
     __shared__ double s_sum[S2M_NPART];
 
-    long long* prof = a.prof ? a.prof + ((size_t)scan * a.max_blocks + blockIdx.x) * 8 : nullptr;
+    long long* prof = a.prof ? a.prof + ((size_t)scan * a.max_blocks + blockIdx.x) * 16 : nullptr;
     if (prof && threadIdx.x == 0) { prof[0] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[6] = gt; }
-    if (threadIdx.x < 12) s_xf[threadIdx.x] = st.xf[threadIdx.x];
-    else if (threadIdx.x < 18) s_trig[threadIdx.x - 12] = st.trig[threadIdx.x - 12];
+    if (threadIdx.x < 12) s_xf[threadIdx.x] = first ? a.init.xf[threadIdx.x] : st.xf[threadIdx.x];
+    else if (threadIdx.x < 18) s_trig[threadIdx.x - 12] = first ? a.init.trig[threadIdx.x - 12] : st.trig[threadIdx.x - 12];
     __syncthreads();
 
     // ---------------- phase 1: transform + 5-NN, LPF lanes per feature
     const int grp = threadIdx.x / LPF, sub = threadIdx.x & (LPF - 1);
 #pragma unroll 1
-    for (int r = 0; r < ROUNDS; r++) {
+    for (int r = 0; r < rounds; r++) {
         const int slot = r * FPR + grp;
         const int f = fb + slot;
         const bool active = f < nfeat;
@@ -397,14 +427,14 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     if (prof && threadIdx.x == 0) prof[1] = clock64();
 
     // ---------------- phase 2: one thread per feature
-    if (threadIdx.x < FPB) {
+    if (threadIdx.x < ((fpb + 31) & ~31)) {           // whole warps (the reduction below shuffles with a full mask)
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int slot = threadIdx.x;
         const int ff = fb + slot;
         bool keep = false;
         float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
         float ox = 0.f, oy = 0.f, oz = 0.f;
-        if (ff < nfeat) {
+        if (slot < fpb && ff < nfeat) {
             float nx[5], ny[5], nz[5];
 #pragma unroll
             for (int j = 0; j < 5; j++) { const float4 c = s_nb[slot][j]; nx[j] = c.x; ny[j] = c.y; nz[j] = c.z; }
@@ -447,6 +477,7 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
                       + ((sry*srz + cry*crz*srx)*px + (crz*sry-cry*srx*srz)*py)*cfz;
             row[0] = arz; row[1] = arx; row[2] = ary; row[3] = cfz; row[4] = cfx; row[5] = cfy; row[6] = -coeff.w;
         }
+        if (prof && threadIdx.x == 0) prof[12] = clock64();
         // 21 + 6 products in fp64 (float x float is exact there) + the row count; the 28 xor-shuffle trees are independent,
         // unrolled so their latencies overlap
         __syncwarp();                    // the fits diverge per lane; reconverge before the full-mask shuffles
@@ -472,8 +503,9 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     if (prof && threadIdx.x == 0) prof[2] = clock64();
     if (threadIdx.x < S2M_NPART) {
         double v = 0.0;
+        const int p2w = (fpb + 31) >> 5;
 #pragma unroll
-        for (int w = 0; w < P2_WARPS; w++) v += s_wsum[w][threadIdx.x];
+        for (int w = 0; w < P2_WARPS; w++) if (w < p2w) v += s_wsum[w][threadIdx.x];
         __stcg(&a.partial[((size_t)scan * a.max_blocks + blockIdx.x) * S2M_NPART + threadIdx.x], v);
         __threadfence();
     }
@@ -489,17 +521,20 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     // ---------------- epilogue: the last CTA of this scan adds the partials in a fixed (slice, CTA) order
     __threadfence();
     {
-        const int q = threadIdx.x & 31, slice = threadIdx.x >> 5;
-        if (q < S2M_NPART) {
+        // thread t owns term t % 28 of the CTAs congruent to t / 28 modulo 9; their partials are requested twelve at a time
+        // (independent loads in flight: the sum of 191 x 28 doubles costs two L2 round trips instead of six)
+        constexpr int NSL = S2M_THREADS / S2M_NPART, BATCH = 12;
+        const int q = threadIdx.x % S2M_NPART, slice = threadIdx.x / S2M_NPART;
+        if (slice < NSL) {
             const double* base = a.partial + (size_t)scan * a.max_blocks * S2M_NPART + q;
             double sum = 0.0;
-            int b = slice;
-            for (; b + 24 < nblk; b += 32) {
-                const double v0 = __ldcg(&base[(size_t)b * S2M_NPART]), v1 = __ldcg(&base[(size_t)(b + 8) * S2M_NPART]);
-                const double v2 = __ldcg(&base[(size_t)(b + 16) * S2M_NPART]), v3 = __ldcg(&base[(size_t)(b + 24) * S2M_NPART]);
-                sum += v0; sum += v1; sum += v2; sum += v3;
+            for (int b = slice; b < nblk; b += BATCH * NSL) {
+                double v[BATCH];
+#pragma unroll
+                for (int k = 0; k < BATCH; k++) v[k] = (b + k * NSL < nblk) ? __ldcg(&base[(size_t)(b + k * NSL) * S2M_NPART]) : 0.0;
+#pragma unroll
+                for (int k = 0; k < BATCH; k++) sum += v[k];
             }
-            for (; b < nblk; b += 8) sum += __ldcg(&base[(size_t)b * S2M_NPART]);
             s_red[slice][q] = sum;
         }
     }
@@ -507,16 +542,37 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     if (threadIdx.x < S2M_NPART) {
         double v = 0.0;
 #pragma unroll
-        for (int sl = 0; sl < S2M_THREADS / 32; sl++) v += s_red[sl][threadIdx.x];
+        for (int sl = 0; sl < S2M_THREADS / S2M_NPART; sl++) v += s_red[sl][threadIdx.x];
         s_sum[threadIdx.x] = v;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (prof) prof[4] = clock64();
         st.ticket = 0;
+        if (first) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) st.pose[i] = a.init.pose[i];
+            for (int i = 0; i < 36; i++) st.matP[i] = a.init.matP[i];
+            st.degenerate = a.init.degenerate;
+            st.done = 0; st.converged = 0; st.iters = 0; st.n_sel = 0; st.ran = 0;
+            st.grid_status = a.gcm->status | a.gsm->status;
+        }
         const int iterCount = a.iter >= 0 ? a.iter : st.iters;
-        lm_epilogue(st, s_sum, iterCount, a, scan);
+        lm_epilogue(st, s_sum, iterCount, a, scan, prof);
         if (prof) { prof[5] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[7] = gt; }
+    }
+    // single-scan solves: the state goes straight to mapped host memory when the loop ends or the chunk does, followed by the
+    // sequence number the host spins on (no copy, no stream synchronisation on the critical path)
+    if (a.result) {
+        __syncthreads();
+        if (st.done || a.chunk_last) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&st);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(a.result);
+            for (int i = threadIdx.x; i < (int)(sizeof(S2MState) / 4); i += S2M_THREADS) dst[i] = __ldcg(&src[i]);
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) { *a.result_seq = a.seq; __threadfence_system(); }
+        }
     }
 }
 
@@ -549,14 +605,23 @@ using namespace b2;
 struct b2_s2m_s {
     b2_s2m_params prm;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream_up = nullptr;   // solve + corner index; surf index; scan uploads
-    cudaEvent_t ev_map = nullptr, ev_up = nullptr;
+    cudaEvent_t ev_map = nullptr, ev_up = nullptr, ev_surf = nullptr;
     int last_iters = 3;                            // iterations the previous single-scan solve needed (sizes the first chunk)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_idx = nullptr;                  // start of the last b2_s2m_rebuild_map_index (device span of "index build + solve")
+    bool idx_timed = false;
     GridIndex gc, gs;
     DevBuf raw_c, raw_s, scan_c, scan_s, off_c, off_s, state, partial, hist, ne, nb_c, nb_s;
     bool nb_valid = false;            // nb_* were written by an iteration on the current map and scan (host-driven b2_s2m_iterate)
     DevBuf dbg_idx_c, dbg_d2_c, dbg_coeff_c, dbg_flag_c, dbg_idx_s, dbg_d2_s, dbg_coeff_s, dbg_flag_s;
     PinBuf pin;
+    PinBuf stage; size_t stage_used = 0; bool stage_all = true;   // pinned staging of the scan features (set_scan)
+    S2MState* h_result = nullptr;      // mapped pinned memory the last CTA writes the state into (single-scan solves) ...
+    volatile int* h_seq = nullptr;     // ... followed by the sequence number the host spins on
+    int seq = 0;
+    bool last_ms_valid = true;
+    bool grid_checked = false;         // the status words of the current map grids have been read (check_grid_status)
+    void* state_zeroed = nullptr;      // the allocation of `state` whose tickets are known to be zero
     bool have_map = false, have_scan = false;
     bool use_pdl = getenv("B2_S2M_NO_PDL") == nullptr;
     bool map_pending = false, scan_pending = false;   // set_map / set_scan left work on the streams that nothing has waited for yet
@@ -568,7 +633,17 @@ struct b2_s2m_s {
     int degenerate = 0;               // persistent members (:136,:234)
     float matP[36] = {0};
     float last_ms = 0.f; int last_launches = 0;
+    // developer timeline (B2_S2M_TIMELINE=1): host clock at the entry / exit of the three calls of a step
+    bool tl_on = getenv("B2_S2M_TIMELINE") != nullptr;
+    double tl_host[8] = {0};
+    cudaEvent_t tl_scan = nullptr;
+    int tl_count = 0;
 };
+
+static double host_us() {
+    timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec * 1e6 + (double)ts.tv_nsec * 1e-3;
+}
 
 static void host_prepare_pose(const float pose[6], float xf[12], float trig[6]) {
     // exactly what the reference evaluates on the CPU: float sin/cos from the C library
@@ -589,12 +664,38 @@ static int drain_pending(b2_s2m_s* h) {
     return B2_OK;
 }
 
+// Paths that do not carry the grid status back with their result (host-driven single iterations, batches) ask for it once
+// per map: two words, one synchronisation. A map that outgrew its device-sized table is rebuilt on the host-sized path.
+static int check_grid_status(b2_s2m_s* h) {
+    if (h->grid_checked) return B2_OK;
+    int st[2] = {0, 0};
+    B2_CUDA(cudaMemcpyAsync(&st[0], &h->gc.dev_ptr()->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaMemcpyAsync(&st[1], &h->gs.dev_ptr()->status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    if (st[0] != 0) B2_CHECK(h->gc.rebuild_exact(h->stream));
+    if (st[1] != 0) B2_CHECK(h->gs.rebuild_exact(h->stream));
+    if (st[0] != 0 || st[1] != 0) B2_CUDA(cudaStreamSynchronize(h->stream));
+    h->grid_checked = true;
+    return B2_OK;
+}
+
 // host cloud -> device, on the upload stream (the copy does not queue behind the index builds set_map left on h->stream).
 // Clouds that are already x y z intensity, 16 bytes apart, go straight into place; others land in `raw` and are repacked by
 // pack_points once h->stream has been made to wait for the copies.
+// Small clouds (the features of one scan, ~100 KB) are first copied into the handle's own pinned buffer: set_scan can then
+// return without waiting for the DMA (the wait, not the copy, was 20 us of the step).
+constexpr size_t S2M_STAGE_MAX = (size_t)512 << 10;
 static int upload_points(b2_s2m_s* h, DevBuf& raw, DevBuf& packed, const void* pts, size_t stride, size_t n) {
     if (n == 0) return B2_OK;
     B2_CHECK(packed.reserve(n * sizeof(float4)));
+    if (h->stage_used + n * stride <= S2M_STAGE_MAX) {
+        char* st = h->stage.as<char>() + h->stage_used;
+        memcpy(st, pts, n * stride);
+        h->stage_used += (n * stride + 255) & ~(size_t)255;
+        pts = st;
+    } else {
+        h->stage_all = false;
+    }
     if (stride == sizeof(float4)) { B2_CUDA(cudaMemcpyAsync(packed.p, pts, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream_up)); return B2_OK; }
     B2_CHECK(raw.reserve(n * stride));
     B2_CUDA(cudaMemcpyAsync(raw.p, pts, n * stride, cudaMemcpyHostToDevice, h->stream_up));
@@ -609,7 +710,7 @@ static int pack_points(b2_s2m_s* h, DevBuf& raw, DevBuf& packed, size_t stride, 
 
 // One LM iteration for every scan of the batch. Shape: a single scan wants many small CTAs (latency), a batch wants
 // CTAs whose second phase keeps all eight warps busy (throughput).
-static void launch_iteration(b2_s2m_s* h, const S2MArgs& a, int batch) {
+static int launch_iteration(b2_s2m_s* h, const S2MArgs& a, int batch) {
     if (batch <= 2) {
         // the previous winners' bound costs two dependent loads before the search starts: a loss on the latency shape
         S2MArgs b = a; b.use_prev = 0;
@@ -622,19 +723,22 @@ static void launch_iteration(b2_s2m_s* h, const S2MArgs& a, int batch) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = h->use_pdl ? 1 : 0;
-        cudaLaunchKernelEx(&cfg, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS>, b);
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>, b);
+        if (le != cudaSuccess) { set_error("k_s2m_iteration launch -> %s", cudaGetErrorString(le)); return B2_ERR_CUDA; }
     } else {
         const int nb = (h->max_feat_c + S2M_THR_FPB - 1) / S2M_THR_FPB + (h->max_feat_s + S2M_THR_FPB - 1) / S2M_THR_FPB;
         dim3 grid((unsigned)std::max(nb, 1), (unsigned)batch);
-        k_s2m_iteration<S2M_THR_LPF, S2M_THR_ROUNDS><<<grid, S2M_THREADS, 0, h->stream>>>(a);
+        k_s2m_iteration<S2M_THR_LPF, S2M_THR_ROUNDS, S2M_THR_ROUNDS><<<grid, S2M_THREADS, 0, h->stream>>>(a);
+        B2_CUDA(cudaGetLastError());
     }
     count_launch();
+    return B2_OK;
 }
 
 static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, float* pose_hist, int hist_stride) {
     S2MArgs a{};
     a.max_iters = hist_stride > 0 ? hist_stride : h->prm.max_iterations;
-    a.gc = h->gc.dev; a.gs = h->gs.dev;
+    a.gcm = h->gc.dev_ptr(); a.gsm = h->gs.dev_ptr();
     a.scan_c = h->scan_c.as<float4>(); a.scan_s = h->scan_s.as<float4>();
     a.off_c = h->off_c.as<int>(); a.off_s = h->off_c.as<int>() + (h->batch + 1);
     a.st = h->state.as<S2MState>();
@@ -667,12 +771,18 @@ static int set_scan_finish(b2_s2m_s* h, int batch, bool host_upload = false) {
     for (int b = 0; b < batch; b++) {
         h->max_feat_c = std::max(h->max_feat_c, coff[b + 1] - coff[b]);
         h->max_feat_s = std::max(h->max_feat_s, soff[b + 1] - soff[b]);
-        int nb = (coff[b + 1] - coff[b] + S2M_LAT_FPB - 1) / S2M_LAT_FPB + (soff[b + 1] - soff[b] + S2M_LAT_FPB - 1) / S2M_LAT_FPB;
+        int nb = (coff[b + 1] - coff[b] + S2M_LAT_FPB_C - 1) / S2M_LAT_FPB_C + (soff[b + 1] - soff[b] + S2M_LAT_FPB - 1) / S2M_LAT_FPB;
         mb = std::max(mb, nb);          // sized for the small-CTA shape, the larger count of the two
     }
     h->max_blocks = mb;
     h->batch = batch;
     B2_CHECK(h->state.reserve((size_t)batch * sizeof(S2MState) + (size_t)(batch + 1) * sizeof(int)));
+    if (h->state.p != h->state_zeroed) {
+        // single-scan solves never upload the state: the per-scan ticket must be zero when the first CTA arrives, and every
+        // launch leaves it zero again
+        B2_CUDA(cudaMemsetAsync(h->state.p, 0, h->state.cap, h->stream));
+        h->state_zeroed = h->state.p;
+    }
     B2_CHECK(h->partial.reserve((size_t)batch * mb * S2M_NPART * sizeof(double)));
     B2_CHECK(h->ne.reserve((size_t)(batch + 1) * sizeof(int)));
     B2_CHECK(h->nb_c.reserve(std::max<size_t>(h->n_c, 1) * 5 * sizeof(uint32_t)));
@@ -687,7 +797,7 @@ static int set_scan_finish(b2_s2m_s* h, int batch, bool host_upload = false) {
     }
     // the caller may free its buffers on return: wait for the uploads only (the pack kernels and whatever set_map left on
     // h->stream run on; the offset tables above come from pageable memory, which cudaMemcpyAsync stages before returning)
-    if (host_upload) { B2_CUDA(cudaStreamSynchronize(h->stream_up)); h->scan_pending = true; }
+    if (host_upload) { if (!h->stage_all) B2_CUDA(cudaStreamSynchronize(h->stream_up)); h->scan_pending = true; }
     else { B2_CUDA(cudaStreamSynchronize(h->stream)); h->map_pending = h->scan_pending = false; }
     h->have_scan = true;
     return B2_OK;
@@ -704,9 +814,12 @@ static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cs
         if (coff[b + 1] < coff[b] || soff[b + 1] < soff[b]) { set_error("set_scan: offsets must be non-decreasing"); return B2_ERR_ARG; }
     h->n_c = (size_t)coff[batch]; h->n_s = (size_t)soff[batch];
     if ((h->n_c && !corner) || (h->n_s && !surf)) { set_error("set_scan: null feature array"); return B2_ERR_ARG; }
+    B2_CHECK(h->stage.reserve(S2M_STAGE_MAX));
+    h->stage_used = 0; h->stage_all = true;
     B2_CHECK(upload_points(h, h->raw_c, h->scan_c, corner, cstride, h->n_c));
     B2_CHECK(upload_points(h, h->raw_s, h->scan_s, surf, sstride, h->n_s));
     B2_CUDA(cudaEventRecord(h->ev_up, h->stream_up));
+    if (h->tl_on) { if (!h->tl_scan) cudaEventCreate(&h->tl_scan); cudaEventRecord(h->tl_scan, h->stream_up); }
     B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
     B2_CHECK(pack_points(h, h->raw_c, h->scan_c, cstride, h->n_c));
     B2_CHECK(pack_points(h, h->raw_s, h->scan_s, sstride, h->n_s));
@@ -736,12 +849,13 @@ int s2m_set_scan_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, cons
 int s2m_set_map_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, const void* d_surf, size_t n_surf) {
     if (!h) return B2_ERR_ARG;
     if (h->map_pending) B2_CHECK(drain_pending(h));
-    B2_CHECK(h->gc.begin_device(d_corner, 16, n_corner, h->prm.knn_max_dist, h->stream));
-    B2_CHECK(h->gs.begin_device(d_surf, 16, n_surf, h->prm.knn_max_dist, h->stream2));
-    B2_CHECK(h->gc.finish(h->stream));
-    B2_CHECK(h->gs.finish(h->stream2));
-    B2_CUDA(cudaStreamSynchronize(h->stream));
-    B2_CUDA(cudaStreamSynchronize(h->stream2));
+    B2_CHECK(h->gc.upload_async(nullptr, d_corner, 16, n_corner, h->prm.knn_max_dist, h->stream, true));
+    B2_CHECK(h->gs.upload_async(nullptr, d_surf, 16, n_surf, h->prm.knn_max_dist, h->stream2, true));
+    B2_CHECK(h->gc.build_async(h->stream));
+    B2_CHECK(h->gs.build_async(h->stream2));
+    B2_CUDA(cudaEventRecord(h->ev_surf, h->stream2));
+    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_surf, 0));
+    h->map_pending = true; h->grid_checked = false;
     h->have_map = true; h->nb_valid = false;
     return B2_OK;
 }
@@ -771,8 +885,10 @@ int b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream_up, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_map, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_surf, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->ev_idx);
     if (e != cudaSuccess) { set_error("b2_s2m_create: %s", cudaGetErrorString(e)); delete h; return B2_ERR_CUDA; }
     *out = h;
     return B2_OK;
@@ -785,14 +901,17 @@ int b2_s2m_destroy(b2_s2m_t h) {
     DevBuf* bufs[] = {&h->raw_c, &h->raw_s, &h->scan_c, &h->scan_s, &h->off_c, &h->off_s, &h->state, &h->partial, &h->hist, &h->ne, &h->nb_c, &h->nb_s,
                       &h->dbg_idx_c, &h->dbg_d2_c, &h->dbg_coeff_c, &h->dbg_flag_c, &h->dbg_idx_s, &h->dbg_d2_s, &h->dbg_coeff_s, &h->dbg_flag_s};
     for (DevBuf* b : bufs) b->release();
-    h->pin.release();
+    h->pin.release(); h->stage.release();
+    if (h->h_result) { cudaStreamSynchronize(h->stream); cudaFreeHost(h->h_result); }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_idx) cudaEventDestroy(h->ev_idx);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     if (h->stream_up) cudaStreamDestroy(h->stream_up);
     if (h->ev_map) cudaEventDestroy(h->ev_map);
     if (h->ev_up) cudaEventDestroy(h->ev_up);
+    if (h->ev_surf) cudaEventDestroy(h->ev_surf);
     delete h;
     return B2_OK;
 }
@@ -802,18 +921,54 @@ int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corn
         set_error("b2_s2m_set_map: bad argument"); return B2_ERR_ARG;
     }
     if (h->map_pending) B2_CHECK(drain_pending(h));
-    // the two indexes are built side by side: uploads and bounding boxes first, then both counting sorts
-    B2_CHECK(h->gc.begin(corner, cstride, n_corner, h->prm.knn_max_dist, h->stream));
-    B2_CHECK(h->gs.begin(surf, sstride, n_surf, h->prm.knn_max_dist, h->stream2));
-    B2_CHECK(h->gc.finish(h->stream));       // (measured: the small cloud first; the other order costs 3 % of the e2e step)
-    B2_CHECK(h->gs.finish(h->stream2));
-    // finish() has waited for the uploads (it needs the bounding boxes), so the caller's buffers are free; the counting sorts
-    // are still running. Everything that uses the indexes is enqueued on h->stream, which now also waits for the surf build:
-    // the host goes on to upload the scan and enqueue the solve while the indexes are being built.
+    h->gc.tl_on = h->gs.tl_on = h->tl_on;
+    h->tl_host[0] = host_us();
+    // Both uploads are queued first (the small cloud on the solve stream, the large one on the second stream), each followed
+    // by its device-sized index build: no bounding box comes back to the host, the builds run while the caller goes on to
+    // set_scan and solve. The only wait here is for the two copies, after which the caller's buffers are free.
+    B2_CHECK(h->gc.upload_async(corner, nullptr, cstride, n_corner, h->prm.knn_max_dist, h->stream));
+    B2_CHECK(h->gs.upload_async(surf, nullptr, sstride, n_surf, h->prm.knn_max_dist, h->stream2));
+    B2_CUDA(cudaEventRecord(h->ev_up, h->stream));
     B2_CUDA(cudaEventRecord(h->ev_map, h->stream2));
-    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_map, 0));
+    B2_CHECK(h->gc.build_async(h->stream));
+    B2_CHECK(h->gs.build_async(h->stream2));
+    B2_CUDA(cudaEventRecord(h->ev_surf, h->stream2));
+    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_surf, 0));      // everything that uses the indexes is enqueued on h->stream
+    B2_CUDA(cudaEventSynchronize(h->ev_up));
+    B2_CUDA(cudaEventSynchronize(h->ev_map));
     h->map_pending = true;
-    h->have_map = true; h->nb_valid = false;
+    h->have_map = true; h->nb_valid = false; h->grid_checked = false;
+    h->tl_host[1] = host_us();
+    return B2_OK;
+}
+
+// kdtreeCornerFromMap->setInputCloud / kdtreeSurfFromMap->setInputCloud once more on the clouds the last b2_s2m_set_map (or
+// b2_s2m_set_map_from_localmap) left in device memory: the reference rebuilds both kd-trees for every scan
+// (mapOptmization.cpp:1289-1290), and this is that step with the inputs already resident in HBM.
+int b2_s2m_rebuild_map_index(b2_s2m_t h) {
+    if (!h) { set_error("b2_s2m_rebuild_map_index: null handle"); return B2_ERR_ARG; }
+    if (!h->have_map) { set_error("b2_s2m_rebuild_map_index: no map set"); return B2_ERR_STATE; }
+    if (h->map_pending || h->scan_pending) B2_CHECK(drain_pending(h));
+    const void* dc = h->gc.src_; const void* ds = h->gs.src_;
+    const size_t nc = h->gc.n, ns = h->gs.n, sc = h->gc.stride_, ss = h->gs.stride_;
+    B2_CUDA(cudaEventRecord(h->ev_idx, h->stream));
+    B2_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_idx, 0));
+    B2_CHECK(h->gc.upload_async(nullptr, dc, sc, nc, h->prm.knn_max_dist, h->stream));
+    B2_CHECK(h->gs.upload_async(nullptr, ds, ss, ns, h->prm.knn_max_dist, h->stream2));
+    B2_CHECK(h->gc.build_async(h->stream));
+    B2_CHECK(h->gs.build_async(h->stream2));
+    B2_CUDA(cudaEventRecord(h->ev_surf, h->stream2));
+    B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_surf, 0));
+    h->grid_checked = false;
+    h->map_pending = true; h->nb_valid = false; h->idx_timed = true;
+    return B2_OK;
+}
+
+int b2_s2m_last_step_gpu_ms(b2_s2m_t h, float* ms) {
+    if (!h || !ms) return B2_ERR_ARG;
+    if (!h->idx_timed) { set_error("b2_s2m_last_step_gpu_ms: call b2_s2m_rebuild_map_index and a solve first"); return B2_ERR_STATE; }
+    B2_CUDA(cudaEventSynchronize(h->ev1));
+    B2_CUDA(cudaEventElapsedTime(ms, h->ev_idx, h->ev1));
     return B2_OK;
 }
 
@@ -822,7 +977,10 @@ int b2_s2m_set_scan(b2_s2m_t h, const void* corner, size_t cstride, size_t n_cor
         set_error("b2_s2m_set_scan: bad argument"); return B2_ERR_ARG;
     }
     int32_t co[2] = {0, (int32_t)n_corner}, so[2] = {0, (int32_t)n_surf};
-    return set_scan_common(h, 1, corner, cstride, co, surf, sstride, so);
+    h->tl_host[2] = host_us();
+    const int st = set_scan_common(h, 1, corner, cstride, co, surf, sstride, so);
+    h->tl_host[3] = host_us();
+    return st;
 }
 
 int b2_s2m_set_scan_batch(b2_s2m_t h, int batch, const void* corner, size_t cstride, const int32_t* coff,
@@ -886,6 +1044,7 @@ int b2_s2m_set_state(b2_s2m_t h, int degenerate, const float matP[36]) {
 int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, int* converged, int* degenerate, float matP[36]) {
     if (!h || !pose || iter < 0) { set_error("b2_s2m_iterate: bad argument"); return B2_ERR_ARG; }
     if (!h->have_map || !h->have_scan || h->batch != 1) { set_error("b2_s2m_iterate: set_map and set_scan (single scan) first"); return B2_ERR_STATE; }
+    B2_CHECK(check_grid_status(h));
     B2_CHECK(h->pin.reserve(sizeof(S2MState)));
     S2MState* hs = h->pin.as<S2MState>();
     memset(hs, 0, sizeof(S2MState));
@@ -900,29 +1059,40 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
     h->nb_valid = true;
     const bool prof = getenv("B2_S2M_PROF") != nullptr;
     if (prof) {
-        B2_CHECK(h->hist.reserve((size_t)h->max_blocks * 8 * sizeof(long long)));
-        B2_CUDA(cudaMemsetAsync(h->hist.p, 0, (size_t)h->max_blocks * 8 * sizeof(long long), h->stream));
+        B2_CHECK(h->hist.reserve((size_t)h->max_blocks * 16 * sizeof(long long)));
+        B2_CUDA(cudaMemsetAsync(h->hist.p, 0, (size_t)h->max_blocks * 16 * sizeof(long long), h->stream));
         a.prof = h->hist.as<long long>();
     }
-    launch_iteration(h, a, 1);
+    B2_CHECK(launch_iteration(h, a, 1));
     if (prof) {
-        std::vector<long long> t((size_t)h->max_blocks * 8);
+        std::vector<long long> t((size_t)h->max_blocks * 16);
         B2_CUDA(cudaMemcpyAsync(t.data(), h->hist.p, t.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
         B2_CUDA(cudaStreamSynchronize(h->stream));
-        long long g0 = -1, g1 = 0; double p1 = 0, p2 = 0, p3 = 0, pf = 0; int nb = 0; double mx1 = 0, mx2 = 0;
+        long long g0 = -1, g1 = 0;
+        const int nbc = (h->h_off_c[1] - h->h_off_c[0] + S2M_LAT_FPB_C - 1) / S2M_LAT_FPB_C;
+        struct Acc { double p1 = 0, p2 = 0, fit = 0, row = 0, sums = 0, tail = 0, tot = 0, mx1 = 0, mx2 = 0, mxt = 0; int n = 0; } acc[2];
         for (int b = 0; b < h->max_blocks; b++) {
-            const long long* r = &t[(size_t)b * 8];
+            const long long* r = &t[(size_t)b * 16];
             if (!r[0]) continue;
-            nb++;
-            p1 += (double)(r[1] - r[0]); p2 += (double)(r[2] - r[1]); p3 += (double)(r[3] - r[2]);
-            if (!r[5]) pf += (double)(r[4] - r[1]);
-            mx1 = std::max(mx1, (double)(r[1] - r[0])); mx2 = std::max(mx2, (double)(r[2] - r[1]));
             if (g0 < 0 || r[6] < g0) g0 = r[6];
             g1 = std::max(g1, r[7]);
-            if (r[5]) fprintf(stderr, "[b2 prof] last CTA %d: reduce %lld cyc, epilogue %lld cyc\n", b, r[4] - r[3], r[5] - r[4]);
+            if (r[5]) {
+                fprintf(stderr, "[b2 prof] last CTA %d: reduce %lld cyc, epilogue %lld cyc (convert + QR solve %lld, degeneracy %lld, update %lld, next pose %lld)\n", b, r[4] - r[3], r[5] - r[4],
+                        r[8] - r[4], r[9] - r[8], r[10] - r[9], r[5] - r[10]);
+                continue;
+            }
+            Acc& A = acc[b >= nbc ? 1 : 0];
+            A.n++;
+            A.p1 += (double)(r[1] - r[0]); A.p2 += (double)(r[2] - r[1]); A.fit += (double)(r[4] - r[1]); A.row += (double)(r[12] - r[4]);
+            A.sums += (double)(r[2] - r[12]); A.tail += (double)(r[3] - r[2]); A.tot += (double)(r[3] - r[0]);
+            A.mx1 = std::max(A.mx1, (double)(r[1] - r[0])); A.mx2 = std::max(A.mx2, (double)(r[2] - r[1])); A.mxt = std::max(A.mxt, (double)(r[3] - r[0]));
         }
-        fprintf(stderr, "[b2 prof] iter %d: %d CTAs, mean cycles phase1 %.0f (max %.0f) phase2 %.0f (max %.0f; fits %.0f) store+ticket %.0f; first start -> last end %.2f us\n",
-                iter, nb, p1 / nb, mx1, p2 / nb, mx2, pf / std::max(nb - 1, 1), p3 / nb, (double)(g1 - g0) * 1e-3);
+        for (int k = 0; k < 2; k++) {
+            const Acc& A = acc[k]; const double n = std::max(A.n, 1);
+            fprintf(stderr, "[b2 prof] iter %d %s: %d CTAs, mean cycles phase1 %.0f (max %.0f) phase2 %.0f (max %.0f: fits %.0f row %.0f sums %.0f) store+ticket %.0f | CTA total %.0f (max %.0f)\n",
+                    iter, k ? "surf" : "corner", A.n, A.p1 / n, A.mx1, A.p2 / n, A.mx2, A.fit / n, A.row / n, A.sums / n, A.tail / n, A.tot / n, A.mxt);
+        }
+        fprintf(stderr, "[b2 prof] iter %d: first start -> last end %.2f us\n", iter, (double)(g1 - g0) * 1e-3);
     }
     B2_CUDA(cudaGetLastError());
     B2_CUDA(cudaMemcpyAsync(hs, h->state.p, sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
@@ -939,10 +1109,133 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
     return B2_OK;
 }
 
+// Single-scan solve (the latency path of the C1 workload). No upload and no read-back copy: the initial state rides in the
+// first launch's arguments, and the last CTA of the iteration that ends the loop (or the chunk) writes the state into mapped
+// host memory, then a sequence number the host spins on. If the device-sized map grids did not fit their tables the status
+// comes back with the state; the grids are then rebuilt on the host-sized path and the solve is repeated.
+static int run_solve_single(b2_s2m_s* h, float* pose, int max_iterations, int* iters_done, int* converged, int* degenerate,
+                            float* matP_out, int* not_enough, float* pose_history, bool want_matP) {
+    if (max_iterations < 1) max_iterations = h->prm.max_iterations;
+    const int nc = h->h_off_c[1] - h->h_off_c[0], ns = h->h_off_s[1] - h->h_off_s[0];
+    if (!(nc > h->prm.edge_feature_min_valid_num && ns > h->prm.surf_feature_min_valid_num)) {
+        // guard of scan2MapOptimization :1287: nothing runs, the pose stays
+        if (iters_done) *iters_done = 0;
+        if (converged) *converged = 0;
+        if (degenerate) *degenerate = h->degenerate;
+        if (not_enough) *not_enough = 1;
+        if (matP_out) memcpy(matP_out, h->matP, sizeof(h->matP));
+        h->last_ms = 0.f; h->last_launches = 0; h->last_ms_valid = true;
+        return B2_OK;
+    }
+    if (!h->h_result) {
+        void* p = nullptr;
+        B2_CUDA(cudaHostAlloc(&p, sizeof(S2MState) + 64, cudaHostAllocMapped));
+        memset(p, 0, sizeof(S2MState) + 64);
+        h->h_result = static_cast<S2MState*>(p);
+        h->h_seq = reinterpret_cast<volatile int*>(static_cast<char*>(p) + sizeof(S2MState));
+    }
+    S2MState* d_result = nullptr;
+    B2_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_result), h->h_result, 0));
+    volatile int* d_seq = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(d_result) + sizeof(S2MState));
+    float* d_hist = nullptr;
+    if (pose_history) {
+        B2_CHECK(h->hist.reserve((size_t)max_iterations * 6 * sizeof(float)));
+        d_hist = h->hist.as<float>();
+        B2_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)max_iterations * 6 * sizeof(float), h->stream));
+    }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        S2MArgs a = make_args(h, -1, 1, false, d_hist, max_iterations);
+        a.want_matP = want_matP ? 1 : 0;
+        a.result = d_result; a.result_seq = d_seq;
+        memcpy(a.init.pose, pose, 24);
+        host_prepare_pose(pose, a.init.xf, a.init.trig);     // float sin/cos from the C library, exactly as the reference evaluates them
+        memcpy(a.init.matP, h->matP, sizeof(h->matP));
+        a.init.degenerate = h->degenerate;
+        B2_CUDA(cudaEventRecord(h->ev0, h->stream));
+        int launched = 0, n_launch = 0;
+        // Iterations are enqueued in chunks; a finished scan's CTAs return at once, so an over-long chunk costs only empty
+        // launches. First chunk: the previous solve's iteration count plus one (consecutive scans of a trajectory behave alike).
+        const int first = std::min(max_iterations, std::max(4, h->last_iters + 1));
+        static const int chunk_plan[] = {0, 4, 6, 8, 8};
+        const S2MState* r = h->h_result;
+        for (int c = 0; launched < max_iterations; c++) {
+            const int chunk = std::min(c == 0 ? first : chunk_plan[std::min(c, 4)], max_iterations - launched);
+            const int seq = ++h->seq;
+            for (int it = 0; it < chunk; it++) {
+                a.use_init = (launched + it == 0) ? 1 : 0;
+                a.seq = seq; a.chunk_last = (it == chunk - 1) ? 1 : 0;
+                B2_CHECK(launch_iteration(h, a, 1));
+            }
+            launched += chunk; n_launch += chunk;
+            B2_CUDA(cudaEventRecord(h->ev1, h->stream));
+            // spin on the sequence number; a failed launch or a device fault shows up as a finished stream without it
+            for (unsigned spins = 0; *h->h_seq != seq; spins++) {
+                if ((spins & 0xfffu) == 0xfffu) {
+                    const cudaError_t q = cudaStreamQuery(h->stream);
+                    if (q != cudaErrorNotReady && *h->h_seq != seq) {
+                        if (q == cudaSuccess) { set_error("scan-to-map solve: the stream drained without a result"); return B2_ERR_CUDA; }
+                        set_error("scan-to-map solve: %s", cudaGetErrorString(q)); return B2_ERR_CUDA;
+                    }
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            if (r->done) break;
+        }
+        h->last_launches = n_launch;
+        h->last_ms_valid = false;                      // ev0 / ev1 are read on demand (b2_s2m_last_gpu_ms)
+        h->map_pending = h->scan_pending = false;      // every kernel that reads the maps or the scan has finished
+        if (r->grid_status != 0 && attempt == 0) {
+            // a map outgrew its device-sized cell table: host-sized rebuild (raises the budget), then once more
+            B2_CHECK(h->gc.rebuild_exact(h->stream));
+            B2_CHECK(h->gs.rebuild_exact(h->stream));
+            B2_CUDA(cudaStreamSynchronize(h->stream));
+            continue;
+        }
+        if (r->grid_status != 0) { set_error("scan-to-map solve: map index does not fit (status %d)", r->grid_status); return B2_ERR_TOO_LARGE; }
+        break;
+    }
+    const S2MState* r = h->h_result;
+    if (pose_history) {
+        B2_CUDA(cudaMemcpyAsync(pose_history, d_hist, (size_t)max_iterations * 6 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    h->nb_valid = true;
+    h->last_iters = r->iters;
+    memcpy(pose, r->pose, 24);
+    if (iters_done) *iters_done = r->iters;
+    if (converged) *converged = r->converged;
+    if (degenerate) *degenerate = r->degenerate;
+    if (not_enough) *not_enough = 0;
+    h->degenerate = r->degenerate;
+    memcpy(h->matP, r->matP, sizeof(h->matP));
+    if (matP_out) memcpy(matP_out, r->matP, sizeof(h->matP));
+    return B2_OK;
+}
+
 static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_done, int* converged, int* degenerate,
                      float* matP_out, int* not_enough, float* pose_history, bool want_matP) {
     const int B = h->batch;
+    h->tl_host[4] = host_us();
+    if (B == 1) {
+        const int st = run_solve_single(h, poses, max_iterations, iters_done, converged, degenerate, matP_out, not_enough, pose_history, want_matP);
+        h->tl_host[5] = host_us();
+        if (st == B2_OK && h->tl_on && h->gc.tl_ev[1] && h->gs.tl_ev[3] && h->gc.tl_ev[3] && h->tl_scan && ++h->tl_count % 50 == 0) {
+            cudaEventSynchronize(h->ev1);
+            auto rel = [&](cudaEvent_t e) { float ms = 0.f; cudaEventElapsedTime(&ms, h->gc.tl_ev[0], e); return ms * 1e3f; };
+            const double t0 = h->tl_host[0];
+            fprintf(stderr, "[b2 timeline us] host: set_map %.1f..%.1f set_scan %.1f..%.1f solve %.1f..%.1f | device (0 = corner upload queued): "
+                            "corner up %.1f build %.1f | surf start %.1f up %.1f build %.1f | scan up %.1f | solve ev0 %.1f ev1 %.1f\n",
+                    0.0, h->tl_host[1] - t0, h->tl_host[2] - t0, h->tl_host[3] - t0, h->tl_host[4] - t0, h->tl_host[5] - t0,
+                    rel(h->gc.tl_ev[1]), rel(h->gc.tl_ev[3]), rel(h->gs.tl_ev[0]), rel(h->gs.tl_ev[1]), rel(h->gs.tl_ev[3]), rel(h->tl_scan),
+                    rel(h->ev0), rel(h->ev1));
+        }
+        return st;
+    }
     if (max_iterations < 1) max_iterations = h->prm.max_iterations;
+    B2_CHECK(check_grid_status(h));
     B2_CHECK(h->pin.reserve((size_t)B * sizeof(S2MState) + (size_t)(B + 1) * sizeof(int) + 64));
     S2MState* hs = h->pin.as<S2MState>();
     memset(hs, 0, (size_t)B * sizeof(S2MState));
@@ -963,20 +1256,12 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     B2_CHECK(h->state.reserve(state_bytes + tail_bytes));
     int* h_tail = reinterpret_cast<int*>(reinterpret_cast<char*>(hs) + state_bytes);
     memset(h_tail, 0, tail_bytes);
-    if (B == 1) {
-        // a single scan needs no preparation kernel: the host knows the pose (sines / cosines from the C library, as the
-        // reference evaluates them) and the guard of scan2MapOptimization :1287
-        host_prepare_pose(hs[0].pose, hs[0].xf, hs[0].trig);
-        const int nc = h->h_off_c[1] - h->h_off_c[0], ns = h->h_off_s[1] - h->h_off_s[0];
-        const int ne = !(nc > h->prm.edge_feature_min_valid_num && ns > h->prm.surf_feature_min_valid_num);
-        hs[0].done = ne; h_tail[0] = ne; h_tail[1] = ne;
-    }
     B2_CUDA(cudaMemcpyAsync(h->state.p, hs, state_bytes + tail_bytes, cudaMemcpyHostToDevice, h->stream));
     if (d_hist) B2_CUDA(cudaMemsetAsync(d_hist, 0, (size_t)B * max_iterations * 6 * sizeof(float), h->stream));
     int* d_ne = reinterpret_cast<int*>(h->state.as<char>() + state_bytes);
     int* d_done = d_ne + B;
     int n_launch = 0;
-    if (B > 1) {
+    {
         k_s2m_prepare<<<(B + 127) / 128, 128, 0, h->stream>>>(h->state.as<S2MState>(), B, h->off_c.as<int>(), h->off_c.as<int>() + (B + 1),
                                                               h->prm.edge_feature_min_valid_num, h->prm.surf_feature_min_valid_num, d_ne, d_done); count_launch();
         B2_CUDA(cudaGetLastError());
@@ -996,7 +1281,7 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     static const int chunk_plan[] = {0, 4, 6, 8, 8};
     for (int c = 0; launched < max_iterations; c++) {
         const int chunk = std::min(c == 0 ? first : chunk_plan[std::min(c, 4)], max_iterations - launched);
-        for (int it = 0; it < chunk; it++) launch_iteration(h, a, B);
+        for (int it = 0; it < chunk; it++) B2_CHECK(launch_iteration(h, a, B));
         launched += chunk; n_launch += chunk;
         B2_CUDA(cudaGetLastError());
         B2_CUDA(cudaEventRecord(h->ev1, h->stream));
@@ -1009,20 +1294,16 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
         B2_CUDA(cudaStreamSynchronize(h->stream));
     }
     B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+    h->last_ms_valid = true;
     h->last_launches = n_launch;
     h->map_pending = h->scan_pending = false;      // h->stream has drained, and it had waited for the other two
     h->nb_valid = true;
-    if (B == 1) h->last_iters = hs[0].iters;
     for (int b = 0; b < B; b++) {
         if (!h_ne[b]) memcpy(poses + (size_t)b * 6, hs[b].pose, 24);
         if (iters_done) iters_done[b] = hs[b].iters;
         if (converged) converged[b] = hs[b].converged;
         if (degenerate) degenerate[b] = hs[b].degenerate;
         if (not_enough) not_enough[b] = h_ne[b];
-    }
-    if (B == 1 && !h_ne[0]) {
-        h->degenerate = hs[0].degenerate;
-        memcpy(h->matP, hs[0].matP, sizeof(h->matP));
     }
     if (matP_out) memcpy(matP_out, hs[0].matP, sizeof(h->matP));
     return B2_OK;
@@ -1068,6 +1349,11 @@ int b2_s2m_get_normal_equations(b2_s2m_t h, float AtA[36], float AtB[6], float X
 
 int b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches) {
     if (!h) return B2_ERR_ARG;
+    if (!h->last_ms_valid) {
+        B2_CUDA(cudaEventSynchronize(h->ev1));
+        B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+        h->last_ms_valid = true;
+    }
     if (ms) *ms = h->last_ms;
     if (launches) *launches = h->last_launches;
     return B2_OK;

@@ -119,6 +119,16 @@ class ScanToMapOptimizer:
         """The same two setInputCloud calls on the device-resident result of LocalMap.extractCloud (no host copy)."""
         capi.check(capi.lib().b2_s2m_set_map_from_localmap(self._h, local_map._h))
 
+    def rebuildMapIndex(self):
+        """kdtree*FromMap->setInputCloud again on the device-resident map clouds (mapOptmization.cpp:1289-1290 runs per scan)."""
+        capi.check(capi.lib().b2_s2m_rebuild_map_index(self._h))
+
+    def lastStepGpuMs(self):
+        """Device ms from the start of the last rebuildMapIndex to the end of the solve that followed it."""
+        ms = C.c_float(0)
+        capi.check(capi.lib().b2_s2m_last_step_gpu_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def setInputScan(self, laserCloudCornerLastDS, laserCloudSurfLastDS):
         c, cs = capi.as_points(laserCloudCornerLastDS, 4)
         s, ss = capi.as_points(laserCloudSurfLastDS, 4)

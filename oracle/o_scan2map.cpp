@@ -255,6 +255,17 @@ int lm_optimization(S2M& s, float T[6], int iterCount, int* ran) {
 
 extern "C" {
 
+// the team size a num_threads(requested) region gets here (bench.py reports it as cpu_baseline.cores)
+int o_omp_threads(int requested) {
+    int got = 1;
+#pragma omp parallel num_threads(requested > 0 ? requested : 1)
+    {
+#pragma omp single
+        got = omp_get_num_threads();
+    }
+    return got;
+}
+
 void* o_s2m_create(int threads) { S2M* s = new S2M(); s->threads = threads > 0 ? threads : 1; return s; }
 void o_s2m_destroy(void* h) { delete (S2M*)h; }
 

@@ -129,6 +129,14 @@ def lib():
     return L
 
 
+def omp_threads(requested):
+    """Size of the OpenMP team a `num_threads(requested)` region really gets in this process."""
+    L = lib()
+    L.o_omp_threads.restype = C.c_int
+    L.o_omp_threads.argtypes = [C.c_int]
+    return int(L.o_omp_threads(int(requested)))
+
+
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
