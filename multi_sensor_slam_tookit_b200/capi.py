@@ -99,6 +99,29 @@ SYMBOLS = [
 ]
 
 
+class _Missing:
+    def __init__(self, name):
+        self.__dict__["_name"] = name
+
+    def __call__(self, *a):
+        raise ImportError(f"{self._name} is not exported by {LIB_PATH}")
+
+
+class _ExperimentLib:
+    """B2_LIB points at a kernel-experiment build that may predate an entry point: binding it must not fail, calling it does."""
+
+    def __init__(self, cdll):
+        self.__dict__["_c"] = cdll
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._c, name)
+        except AttributeError:
+            m = _Missing(name)
+            self.__dict__[name] = m
+            return m
+
+
 def lib():
     global _LIB
     if _LIB is not None:
@@ -107,6 +130,8 @@ def lib():
         raise ImportError(f"{LIB_PATH} is missing: run `python -m multi_sensor_slam_tookit_b200.build` "
                           "(there is no CPU fallback for this path)")
     L = C.CDLL(LIB_PATH)
+    if os.environ.get("B2_LIB"):
+        L = _ExperimentLib(L)
     vp, sz, i32, f32 = C.c_void_p, C.c_size_t, C.c_int, C.c_float
     pi, pf = C.POINTER(C.c_int), C.POINTER(C.c_float)
     L.b2_last_error.restype = C.c_char_p

@@ -471,6 +471,8 @@ int GridIndex::build_async(cudaStream_t s) {
     uint32_t* d_chunk = d_rank + nal;                 // chunk totals: at most 1024 CTAs
     int ctas = (int)std::min<size_t>((size_t)coop_max, (std::max<size_t>(n, (size_t)1 << 18) + GB_THREADS * 4 - 1) / (GB_THREADS * 4));
     ctas = std::max(1, std::min(ctas, 1024));
+    static const int env_ctas = getenv("B2_GRID_CTAS") ? atoi(getenv("B2_GRID_CTAS")) : 0;          // kernel experiments
+    if (env_ctas > 0) ctas = std::min(env_ctas, coop_max);
     const unsigned char* a_raw = src_; size_t a_stride = stride_; uint32_t a_n = (uint32_t)n; float a_h = h, a_md2 = max_dist * max_dist;
     uint32_t a_budget = (uint32_t)std::min<size_t>(cell_budget, 0xfffffff0u);
     uint32_t* a_cs = cell_start.as<uint32_t>(); float4* a_out = pts.as<float4>(); GridDevMem* a_m = devmem.as<GridDevMem>();

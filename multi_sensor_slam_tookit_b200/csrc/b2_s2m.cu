@@ -99,6 +99,8 @@ struct S2MArgs {
     int use_init;                                 // 1: first launch of a single-scan solve, state = init (no upload, no state loads)
     S2MInit init;
     S2MState* result; volatile int* result_seq; int seq; int chunk_last;   // mapped host memory: state + sequence flag (single scan)
+    int persistent_iters;                         // > 0: ONE cooperative launch runs up to this many LM iterations (single scan); the
+    int* iter_flag; int flag_base;                //      last CTA of an iteration publishes flag_base + k, the other CTAs wait for it
     long long* prof;                              // optional per-CTA clock64 stamps (B2_S2M_PROF=1), 16 per CTA
     float* pose_hist; int hist_stride;            // optional [batch][max_iters][6]
     // optional per-feature introspection (single-scan parity runs)
@@ -118,10 +120,10 @@ __host__ __device__ inline void affine_from_trig(float x, float y, float z, floa
     t[8] = -D;     t[9] = C * F;           t[10] = C * E;           t[11] = z;
 }
 
-__device__ void prepare_pose_device(S2MState& s) {
-    const float roll = s.pose[0], pitch = s.pose[1], yaw = s.pose[2];
+__device__ void prepare_pose_device(S2MState& s, const float* pose) {
+    const float roll = pose[0], pitch = pose[1], yaw = pose[2];
     const float sr = sin_rn(roll), cr = cos_rn(roll), sp = sin_rn(pitch), cp = cos_rn(pitch), sy = sin_rn(yaw), cy = cos_rn(yaw);
-    affine_from_trig(s.pose[3], s.pose[4], s.pose[5], cy, sy, cp, sp, cr, sr, s.xf);
+    affine_from_trig(pose[3], pose[4], pose[5], cy, sy, cp, sp, cr, sr, s.xf);
     s.trig[0] = sp; s.trig[1] = cp;     // srx crx <- pitch
     s.trig[2] = sy; s.trig[3] = cy;     // sry cry <- yaw
     s.trig[4] = sr; s.trig[5] = cr;     // srz crz <- roll
@@ -131,7 +133,7 @@ __global__ void k_s2m_prepare(S2MState* st, int batch, const int* off_c, const i
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= batch) return;
     S2MState& s = st[b];
-    prepare_pose_device(s);
+    prepare_pose_device(s, s.pose);
     s.done = 0; s.converged = 0; s.iters = 0; s.n_sel = 0; s.ran = 0; s.ticket = 0;
     const int nc = off_c[b + 1] - off_c[b], ns = off_s[b + 1] - off_s[b];
     const int ne = !(nc > edge_min && ns > surf_min);      // guard of scan2MapOptimization :1287
@@ -206,6 +208,9 @@ __device__ B2_FIT_ATTR bool fit_plane(const float (&nx)[5], const float (&ny)[5]
 
 // ---- epilogue: normal equations -> pose update (single thread) ------------------------------------------------------
 __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int iterCount, const S2MArgs& a, int scan, long long* prof) {
+    // fields another SM may have written in an earlier iteration of a persistent launch are read with ld.cg
+    const int iters0 = __ldcg(&s.iters);
+    int degen = __ldcg(&s.degenerate);
     const int K = (int)(sums[27] + 0.5);
     s.n_sel = K;
     if (K < a.min_corr) {
@@ -214,13 +219,13 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
         s.ran = 0;
         if (a.device_driven) {
             if (a.pose_hist)
-                for (int it = s.iters; it < a.max_iters; it++)
-                    for (int i = 0; i < 6; i++) a.pose_hist[((size_t)scan * a.hist_stride + it) * 6 + i] = s.pose[i];
+                for (int it = iters0; it < a.max_iters; it++)
+                    for (int i = 0; i < 6; i++) a.pose_hist[((size_t)scan * a.hist_stride + it) * 6 + i] = __ldcg(&s.pose[i]);
             s.iters = a.max_iters;
             s.done = 1;
             if (a.done_count) atomicAdd(a.done_count, 1);
         } else {
-            s.iters += 1;
+            s.iters = iters0 + 1;
         }
         return;
     }
@@ -263,7 +268,7 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
                 Ld[i * 6 + j] = v / d;
             }
         }
-        if (pd) { s.degenerate = 0; full_eigen = false; }
+        if (pd) { s.degenerate = 0; degen = 0; full_eigen = false; }
     }
     if (full_eigen) {
         float w[36], E[6], V[36], V2[36], Vi[36];
@@ -275,18 +280,20 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
             if (E[i] < a.eig_thr) { for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f; deg = 1; }
             else break;
         }
-        s.degenerate = deg;
+        s.degenerate = deg; degen = deg;
         for (int i = 0; i < 36; i++) w[i] = V[i];
         invert_lu<6>(w, Vi);
         matmul_dacc<6, 6>(Vi, V2, s.matP);
     }
     if (prof) prof[9] = clock64();
-    if (s.degenerate) {
-        float X2[6];
+    if (degen) {
+        float X2[6], P[36];
         for (int i = 0; i < 6; i++) X2[i] = X[i];
-        matmul_dacc<6, 1>(s.matP, X2, X);
+        for (int i = 0; i < 36; i++) P[i] = __ldcg(&s.matP[i]);
+        matmul_dacc<6, 1>(P, X2, X);
     }
-    for (int i = 0; i < 6; i++) { s.X[i] = X[i]; s.pose[i] += X[i]; }
+    float pose[6];
+    for (int i = 0; i < 6; i++) { s.X[i] = X[i]; pose[i] = __ldcg(&s.pose[i]) + X[i]; s.pose[i] = pose[i]; }
     const float d0 = X[0] * 57.29578f, d1 = X[1] * 57.29578f, d2 = X[2] * 57.29578f;
     const float t0 = X[3] * 100, t1 = X[4] * 100, t2 = X[5] * 100;
     const float deltaR = (float)sqrt((double)d0 * (double)d0 + (double)d1 * (double)d1 + (double)d2 * (double)d2);
@@ -294,22 +301,28 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
     const int conv = (deltaR < 0.05 && deltaT < 0.05) ? 1 : 0;
     s.converged = conv;
     if (a.pose_hist) {
-        float* ph = a.pose_hist + ((size_t)scan * a.hist_stride + s.iters) * 6;
-        for (int i = 0; i < 6; i++) ph[i] = s.pose[i];
+        float* ph = a.pose_hist + ((size_t)scan * a.hist_stride + iters0) * 6;
+        for (int i = 0; i < 6; i++) ph[i] = pose[i];
     }
-    s.iters += 1;
+    s.iters = iters0 + 1;
     if (prof) prof[10] = clock64();
     if (a.device_driven) {
         if (conv) { s.done = 1; if (a.done_count) atomicAdd(a.done_count, 1); }
-        else prepare_pose_device(s);
+        else prepare_pose_device(s, pose);
     }
 }
 
 // LPF lanes serve one feature in phase 1; a CTA of 256 threads makes ROUNDS passes, so it owns
 // FPB = 256 / LPF * ROUNDS features and phase 2 runs on FPB threads (one warp for the latency shape <16,2>,
 // all eight warps for the throughput shape <8,8>).
+// Register budget: the latency shape must keep two CTAs on an SM (204 CTAs on 148 SMs: at 128 registers the occupancy
+// calculator grants one, and the kernel ran as two waves — 38 us instead of 23), the throughput shape four.
+#ifndef S2M_LAT_MAXREG
+#define S2M_LAT_MAXREG 120
+#endif
 template <int LPF, int ROUNDS, int ROUNDS_C>
-__global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == S2M_THR_ROUNDS) ? S2M_THR_MINB : 1) k_s2m_iteration(const S2MArgs a) {
+__global__ void __launch_bounds__(S2M_THREADS) __maxnreg__((LPF == S2M_THR_LPF && ROUNDS == S2M_THR_ROUNDS) ? 65536 / (S2M_THREADS * S2M_THR_MINB) : S2M_LAT_MAXREG)
+k_s2m_iteration(const S2MArgs a) {
     constexpr int FPR = S2M_THREADS / LPF;
     constexpr int FPB = FPR * ROUNDS;                 // features per surf CTA (and the size of the shared arrays)
     constexpr int FPB_C = FPR * ROUNDS_C;             // features per corner CTA
@@ -322,8 +335,25 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     asm volatile("griddepcontrol.launch_dependents;");
     const int scan = blockIdx.y;
     S2MState& st = a.st[scan];
-    const bool first = a.use_init != 0;                        // the state is in the launch arguments, not in memory yet
+    bool first = a.use_init != 0;                              // the state is in the launch arguments, not in memory yet
     if (!first && st.done) return;                             // uniform per CTA, written only by a previous launch
+    if (first) {
+        // a map that outgrew its device-sized cell table has no usable geometry: report it and let the host rebuild (the
+        // host-driven and batched paths check the status before they launch)
+        const int gst = a.gcm->status | a.gsm->status;
+        if (gst != 0) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                st.grid_status = gst; st.done = 1; st.iters = 0; st.converged = 0;
+                if (a.result) {
+                    a.result->grid_status = gst; a.result->done = 1; a.result->iters = 0;
+                    __threadfence_system();
+                    *a.result_seq = a.seq;
+                    __threadfence_system();
+                }
+            }
+            return;
+        }
+    }
     const int c0 = a.off_c[scan], nc = a.off_c[scan + 1] - c0;
     const int s0 = a.off_s[scan], ns = a.off_s[scan + 1] - s0;
     const int nbc = (nc + FPB_C - 1) / FPB_C, nbs = (ns + FPB - 1) / FPB;
@@ -339,6 +369,11 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     // the pose moves by millimetres between LM iterations: the previous winners bound this iteration's search radius
     uint32_t* nbp = (is_surf ? a.nb_s + (size_t)s0 * 5 : a.nb_c + (size_t)c0 * 5);
     const bool use_prev = LPF < 8 && (a.use_prev > 0 || (a.use_prev < 0 && !first && st.iters > 0));
+    // Persistent form (single scan, cooperative launch, every CTA resident): the LM loop runs inside the kernel. An iteration
+    // ends when its last CTA (atomic ticket) has solved the normal equations and published the iteration number; the other
+    // CTAs wait for that number instead of for a kernel boundary (no launch gap, no empty launches after convergence, and no
+    // guess at how many launches to enqueue). State written by another SM is read with ld.cg (L1 is not coherent).
+    const int n_pit = a.persistent_iters > 0 ? a.persistent_iters : 1;
 
     __shared__ float4 s_nb[FPB][5];           // winners: x y z, original index bits
     __shared__ float s_d2[FPB][5];
@@ -351,8 +386,10 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
 
     long long* prof = a.prof ? a.prof + ((size_t)scan * a.max_blocks + blockIdx.x) * 16 : nullptr;
     if (prof && threadIdx.x == 0) { prof[0] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[6] = gt; }
-    if (threadIdx.x < 12) s_xf[threadIdx.x] = first ? a.init.xf[threadIdx.x] : st.xf[threadIdx.x];
-    else if (threadIdx.x < 18) s_trig[threadIdx.x - 12] = first ? a.init.trig[threadIdx.x - 12] : st.trig[threadIdx.x - 12];
+#pragma unroll 1
+  for (int pit = 0; pit < n_pit; pit++) {
+    if (threadIdx.x < 12) s_xf[threadIdx.x] = first ? a.init.xf[threadIdx.x] : __ldcg(&st.xf[threadIdx.x]);
+    else if (threadIdx.x < 18) s_trig[threadIdx.x - 12] = first ? a.init.trig[threadIdx.x - 12] : __ldcg(&st.trig[threadIdx.x - 12]);
     __syncthreads();
 
     // ---------------- phase 1: transform + 5-NN, LPF lanes per feature
@@ -516,7 +553,9 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     }
     __syncthreads();
     if (prof && threadIdx.x == 0) { prof[3] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[7] = gt; }
-    if (!s_last) return;
+    if (!s_last) {
+        if (n_pit == 1) return;
+    } else {
 
     // ---------------- epilogue: the last CTA of this scan adds the partials in a fixed (slice, CTA) order
     __threadfence();
@@ -557,7 +596,7 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
             st.done = 0; st.converged = 0; st.iters = 0; st.n_sel = 0; st.ran = 0;
             st.grid_status = a.gcm->status | a.gsm->status;
         }
-        const int iterCount = a.iter >= 0 ? a.iter : st.iters;
+        const int iterCount = a.iter >= 0 ? a.iter : __ldcg(&st.iters);
         lm_epilogue(st, s_sum, iterCount, a, scan, prof);
         if (prof) { prof[5] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[7] = gt; }
     }
@@ -565,7 +604,7 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
     // sequence number the host spins on (no copy, no stream synchronisation on the critical path)
     if (a.result) {
         __syncthreads();
-        if (st.done || a.chunk_last) {
+        if (__ldcg(&st.done) || (a.chunk_last && pit == n_pit - 1)) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(&st);
             uint32_t* dst = reinterpret_cast<uint32_t*>(a.result);
             for (int i = threadIdx.x; i < (int)(sizeof(S2MState) / 4); i += S2M_THREADS) dst[i] = __ldcg(&src[i]);
@@ -574,6 +613,21 @@ __global__ void __launch_bounds__(S2M_THREADS, (LPF == S2M_THR_LPF && ROUNDS == 
             if (threadIdx.x == 0) { *a.result_seq = a.seq; __threadfence_system(); }
         }
     }
+        if (n_pit > 1 && threadIdx.x == 0) {      // publish the iteration: everything written above is visible before the flag
+            __threadfence();
+            *reinterpret_cast<volatile int*>(a.iter_flag) = a.flag_base + pit + 1;
+        }
+    }
+    if (n_pit == 1) return;
+    if (threadIdx.x == 0 && !s_last) {
+        const int target = a.flag_base + pit + 1;
+        while (*reinterpret_cast<volatile int*>(a.iter_flag) - target < 0) __nanosleep(64);
+        __threadfence();
+    }
+    __syncthreads();
+    first = false;
+    if (__ldcg(&st.done)) return;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_pack_xyzi(const unsigned char* __restrict__ raw, size_t stride, int ioff, uint32_t n, float4* __restrict__ out) {
@@ -620,6 +674,8 @@ struct b2_s2m_s {
     volatile int* h_seq = nullptr;     // ... followed by the sequence number the host spins on
     int seq = 0;
     bool last_ms_valid = true;
+    DevBuf flag; int flag_next = 0;    // iteration counter of persistent single-scan solves (device int, zeroed once)
+    int persistent_ok = -1;            // -1 unknown, 0 cooperative launch unavailable, else CTAs that can be co-resident
     bool grid_checked = false;         // the status words of the current map grids have been read (check_grid_status)
     void* state_zeroed = nullptr;      // the allocation of `state` whose tickets are known to be zero
     bool have_map = false, have_scan = false;
@@ -898,6 +954,7 @@ int b2_s2m_destroy(b2_s2m_t h) {
     if (!h) return B2_ERR_ARG;
     if (h->map_pending || h->scan_pending) drain_pending(h);     // kernels of a set_map / set_scan nobody waited for
     h->gc.release(); h->gs.release();
+    h->flag.release();
     DevBuf* bufs[] = {&h->raw_c, &h->raw_s, &h->scan_c, &h->scan_s, &h->off_c, &h->off_s, &h->state, &h->partial, &h->hist, &h->ne, &h->nb_c, &h->nb_s,
                       &h->dbg_idx_c, &h->dbg_d2_c, &h->dbg_coeff_c, &h->dbg_flag_c, &h->dbg_idx_s, &h->dbg_d2_s, &h->dbg_coeff_s, &h->dbg_flag_s};
     for (DevBuf* b : bufs) b->release();
@@ -930,6 +987,8 @@ int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corn
     B2_CHECK(h->gs.upload_async(surf, nullptr, sstride, n_surf, h->prm.knn_max_dist, h->stream2));
     B2_CUDA(cudaEventRecord(h->ev_up, h->stream));
     B2_CUDA(cudaEventRecord(h->ev_map, h->stream2));
+    static const bool builds_after_copies = getenv("B2_S2M_BUILDS_AFTER_COPIES") != nullptr;      // kernel experiments
+    if (builds_after_copies) B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_map, 0));
     B2_CHECK(h->gc.build_async(h->stream));
     B2_CHECK(h->gs.build_async(h->stream2));
     B2_CUDA(cudaEventRecord(h->ev_surf, h->stream2));
@@ -1092,6 +1151,20 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
             fprintf(stderr, "[b2 prof] iter %d %s: %d CTAs, mean cycles phase1 %.0f (max %.0f) phase2 %.0f (max %.0f: fits %.0f row %.0f sums %.0f) store+ticket %.0f | CTA total %.0f (max %.0f)\n",
                     iter, k ? "surf" : "corner", A.n, A.p1 / n, A.mx1, A.p2 / n, A.mx2, A.fit / n, A.row / n, A.sums / n, A.tail / n, A.tot / n, A.mxt);
         }
+        {
+            std::vector<double> st_us, en_us;
+            for (int b = 0; b < h->max_blocks; b++) {
+                const long long* r = &t[(size_t)b * 16];
+                if (!r[0]) continue;
+                st_us.push_back((double)(r[6] - g0) * 1e-3); en_us.push_back((double)(r[7] - g0) * 1e-3);
+            }
+            std::sort(st_us.begin(), st_us.end()); std::sort(en_us.begin(), en_us.end());
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>, S2M_THREADS, 0);
+            const size_t m = st_us.size();
+            fprintf(stderr, "[b2 prof] iter %d: CTA starts (us) p50 %.2f p90 %.2f max %.2f | ends p50 %.2f p90 %.2f max %.2f | CTAs/SM by occupancy %d\n",
+                    iter, st_us[m / 2], st_us[m * 9 / 10], st_us[m - 1], en_us[m / 2], en_us[m * 9 / 10], en_us[m - 1], occ);
+        }
         fprintf(stderr, "[b2 prof] iter %d: first start -> last end %.2f us\n", iter, (double)(g1 - g0) * 1e-3);
     }
     B2_CUDA(cudaGetLastError());
@@ -1153,21 +1226,16 @@ static int run_solve_single(b2_s2m_s* h, float* pose, int max_iterations, int* i
         a.init.degenerate = h->degenerate;
         B2_CUDA(cudaEventRecord(h->ev0, h->stream));
         int launched = 0, n_launch = 0;
-        // Iterations are enqueued in chunks; a finished scan's CTAs return at once, so an over-long chunk costs only empty
-        // launches. First chunk: the previous solve's iteration count plus one (consecutive scans of a trajectory behave alike).
-        const int first = std::min(max_iterations, std::max(4, h->last_iters + 1));
-        static const int chunk_plan[] = {0, 4, 6, 8, 8};
         const S2MState* r = h->h_result;
-        for (int c = 0; launched < max_iterations; c++) {
-            const int chunk = std::min(c == 0 ? first : chunk_plan[std::min(c, 4)], max_iterations - launched);
-            const int seq = ++h->seq;
-            for (int it = 0; it < chunk; it++) {
-                a.use_init = (launched + it == 0) ? 1 : 0;
-                a.seq = seq; a.chunk_last = (it == chunk - 1) ? 1 : 0;
-                B2_CHECK(launch_iteration(h, a, 1));
-            }
-            launched += chunk; n_launch += chunk;
-            B2_CUDA(cudaEventRecord(h->ev1, h->stream));
+        if (h->persistent_ok < 0) {
+            int dev = 0, coop = 0, per_sm = 0;
+            static const bool off = getenv("B2_S2M_NO_PERSISTENT") != nullptr;
+            if (!off && cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>, S2M_THREADS, 0) == cudaSuccess)
+                h->persistent_ok = per_sm * device_sm_count();
+            else { cudaGetLastError(); h->persistent_ok = 0; }
+        }
+        auto wait_seq = [&](int seq) -> int {
             // spin on the sequence number; a failed launch or a device fault shows up as a finished stream without it
             for (unsigned spins = 0; *h->h_seq != seq; spins++) {
                 if ((spins & 0xfffu) == 0xfffu) {
@@ -1182,7 +1250,39 @@ static int run_solve_single(b2_s2m_s* h, float* pose, int max_iterations, int* i
 #endif
             }
             __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            return B2_OK;
+        };
+        if (h->persistent_ok >= h->max_blocks) {
+            // the whole LM loop in ONE cooperative launch (every CTA resident, iterations separated by a flag in L2)
+            if (!h->flag.p) { B2_CHECK(h->flag.reserve(64)); B2_CUDA(cudaMemsetAsync(h->flag.p, 0, 64, h->stream)); h->flag_next = 0; }
+            a.use_init = 1; a.persistent_iters = max_iterations; a.iter_flag = h->flag.as<int>(); a.flag_base = h->flag_next;
+            h->flag_next += max_iterations;
+            const int seq = ++h->seq;
+            a.seq = seq; a.chunk_last = 1;
+            void* kargs[] = {&a};
+            B2_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>),
+                                                dim3((unsigned)h->max_blocks, 1u), dim3(S2M_THREADS), kargs, 0, h->stream)); count_launch();
+            n_launch = 1; launched = max_iterations;
+            B2_CUDA(cudaEventRecord(h->ev1, h->stream));
+            B2_CHECK(wait_seq(seq));
+        } else {
+        // Iterations are enqueued in chunks; a finished scan's CTAs return at once, so an over-long chunk costs only empty
+        // launches. First chunk: the previous solve's iteration count plus one (consecutive scans of a trajectory behave alike).
+        const int first = std::min(max_iterations, std::max(4, h->last_iters + 1));
+        static const int chunk_plan[] = {0, 4, 6, 8, 8};
+        for (int c = 0; launched < max_iterations; c++) {
+            const int chunk = std::min(c == 0 ? first : chunk_plan[std::min(c, 4)], max_iterations - launched);
+            const int seq = ++h->seq;
+            for (int it = 0; it < chunk; it++) {
+                a.use_init = (launched + it == 0) ? 1 : 0;
+                a.seq = seq; a.chunk_last = (it == chunk - 1) ? 1 : 0;
+                B2_CHECK(launch_iteration(h, a, 1));
+            }
+            launched += chunk; n_launch += chunk;
+            B2_CUDA(cudaEventRecord(h->ev1, h->stream));
+            B2_CHECK(wait_seq(seq));
             if (r->done) break;
+        }
         }
         h->last_launches = n_launch;
         h->last_ms_valid = false;                      // ev0 / ev1 are read on demand (b2_s2m_last_gpu_ms)

@@ -208,3 +208,47 @@ def test_calls_that_return_before_their_kernels_finish(b2, c1):
     h = ScanToMapOptimizer()
     h.setInputMap(c1["map_corner"], c1["map_surf"]); h.setInputScan(c1["scan_corner"], c1["scan_surf"])
     del h
+
+
+def test_map_larger_than_the_device_sized_cell_table(b2, oracle, c1):
+    """The device sizes the grid itself inside a table of 4 Mi cells; two stray returns 560 m apart blow the bounding box up to
+    ~12 M cells: the solve reports it, the maps are rebuilt on the host-sized path and the result is still the oracle's. The
+    next scan on the same handle (budget raised) goes through the device-sized path again."""
+    from multi_sensor_slam_tookit_b200.registration import ScanToMapOptimizer
+    stray = np.array([[-200.0, -200.0, 30.0, 1.0], [200.0, 200.0, 60.0, 1.0]], np.float32)
+    ms = np.concatenate([c1["map_surf"], stray])
+    mc = np.concatenate([c1["map_corner"], stray[::-1]])
+    o = oracle.Scan2Map(4)
+    o.set_map(mc, ms); o.set_scan(c1["scan_corner"], c1["scan_surf"])
+    ref = o.solve(c1["pose_guess"])
+    g = ScanToMapOptimizer()
+    for rep in range(2):
+        g.setInputMap(mc, ms)
+        g.setInputScan(c1["scan_corner"], c1["scan_surf"])
+        g.transformTobeMapped = c1["pose_guess"].copy()
+        res = g.scan2MapOptimization(30, record_history=True)
+        assert res["iters"] == ref["iters"] and res["converged"] == ref["converged"]
+        assert np.all(np.abs(res["pose_history"][:, 3:] - ref["pose_hist"][:, 3:]) <= TOL_M)
+        assert np.all(np.abs(res["pose_history"][:, :3] - ref["pose_hist"][:, :3]) <= TOL_RAD)
+    # the host-driven single iteration and the batched solve check the status on their own
+    g2 = ScanToMapOptimizer()
+    g2.setInputMap(mc, ms); g2.setInputScan(c1["scan_corner"], c1["scan_surf"])
+    g2.transformTobeMapped = c1["pose_guess"].copy()
+    g2.LMIteration(0)
+    r = o.iterate(c1["pose_guess"], 0)
+    assert g2.laserCloudSelNum == r["n_sel"]
+
+
+def test_persistent_and_chunked_solves_agree_bit_for_bit(b2, c1, monkeypatch):
+    """One cooperative launch for the whole LM loop vs one launch per iteration: same kernels, same arithmetic."""
+    from multi_sensor_slam_tookit_b200.registration import ScanToMapOptimizer
+    out = []
+    for no_persistent in (False, True):
+        if no_persistent:
+            monkeypatch.setenv("B2_S2M_NO_PERSISTENT", "1")
+        g = ScanToMapOptimizer()
+        g.setInputMap(c1["map_corner"], c1["map_surf"]); g.setInputScan(c1["scan_corner"], c1["scan_surf"])
+        g.transformTobeMapped = c1["pose_guess"].copy()
+        res = g.scan2MapOptimization(30, record_history=True)
+        out.append((res["iters"], res["pose_history"].copy(), g.lastGpuMs()[1]))
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
