@@ -273,8 +273,8 @@ int GridIndex::finish(cudaStream_t s) {
 // box (that wait, two per scan, was a third of the end-to-end scan-to-map step).
 __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, float h, float max_d2,
                                                                uint32_t cell_budget, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank_in_cell,
-                                                               uint32_t* __restrict__ cell_start, uint32_t* __restrict__ chunk_sum,
-                                                               float4* __restrict__ out, GridDevMem* __restrict__ m) {
+                                                               uint32_t* __restrict__ cell_start, uint32_t* __restrict__ other_table, int active_half,
+                                                               uint32_t* __restrict__ chunk_sum, float4* __restrict__ out, GridDevMem* __restrict__ m) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const uint32_t tid = blockIdx.x * GB_THREADS + threadIdx.x, nthr = gridDim.x * GB_THREADS;
@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
     __shared__ uint32_t s_w[GB_THREADS / 32];
     __shared__ uint32_t s_base;
     __shared__ float s_mn[GB_THREADS / 32][3], s_mx[GB_THREADS / 32][3];
+    const uint32_t other_dirty = __ldcg(&m->dirty[active_half ^ 1]);   // read before the first barrier, rewritten after the last one
     // ---- bounding box of the finite points
     {
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -334,8 +335,7 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
         g.ncell = (uint32_t)((size_t)g.nx * g.ny * g.nz);
     }
     const uint32_t ncount = g.ncell + 2;
-    for (uint32_t i = tid; i < ncount; i += nthr) cell_start[i] = 0u;
-    grid.sync();
+    // the table arrives zeroed (the previous build cleared it after its scatter): counting starts right away
     for (uint32_t i = tid; i < n; i += nthr) {
         const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
         const uint32_t c = cell_of_point(g, p[0], p[1], p[2]);
@@ -388,7 +388,10 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
         const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
         out[cell_start[cell_of[i]] + rank_in_cell[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
     }
+    // the other half of the table (the previous build's offsets, nobody reads them any more) is cleared for the next build
+    for (uint32_t i = tid; i < other_dirty; i += nthr) other_table[i] = 0u;
     if (tid == 0) {
+        m->dirty[active_half] = ncount; m->dirty[active_half ^ 1] = 0u;
         GridDev d;
         d.pts = out; d.cell_start = cell_start;
         d.ox = g.ox; d.oy = g.oy; d.oz = g.oz; d.inv_h = g.inv_h; d.h = h;
@@ -457,32 +460,49 @@ int GridIndex::build_async(cudaStream_t s) {
         d.pts = nullptr; d.cell_start = cell_start.as<uint32_t>();
         d.ox = d.oy = d.oz = 0.f; d.inv_h = 1.0f / h; d.h = h; d.nx = d.ny = d.nz = 1; d.n = 0; d.max_d2 = max_dist * max_dist;
         dev = d;
+        tables_clean_ = false;
         return store_devmem(*this, d, 0, s);
     }
     const int coop_max = grid_build_dev_max_ctas();
     if (coop_max <= 0) return rebuild_exact(s);
     if (cell_budget == 0) cell_budget = GRID_DEFAULT_BUDGET;
-    B2_CHECK(cell_start.reserve((cell_budget + 2) * sizeof(uint32_t)));
+    // two tables of cell_budget + 2 entries: the build counts into the one the previous build left zeroed, and zeroes the other
+    // one (its predecessor's offsets) when it is done — no clearing pass and no barrier for it on the critical path
+    const size_t half = (cell_budget + 2 + 63) & ~(size_t)63;
+    const void* before = cell_start.p;
+    B2_CHECK(cell_start.reserve(2 * half * sizeof(uint32_t)));
+    if (cell_start.p != before || !tables_clean_) {
+        B2_CUDA(cudaMemsetAsync(cell_start.p, 0, 2 * half * sizeof(uint32_t), s));
+        const uint32_t zero2[2] = {0u, 0u};
+        B2_CUDA(cudaMemcpyAsync(&devmem.as<GridDevMem>()->dirty[0], zero2, sizeof(zero2), cudaMemcpyHostToDevice, s));
+        tables_clean_ = true; table_active_ = 0;
+    }
+    table_active_ ^= 1;
+    uint32_t* a_cs = cell_start.as<uint32_t>() + (size_t)table_active_ * half;
+    uint32_t* a_other = cell_start.as<uint32_t>() + (size_t)(table_active_ ^ 1) * half;
+    int a_half = table_active_;
     const size_t nal = (n + 63) & ~(size_t)63;
     B2_CHECK(cell_of.reserve(2 * nal * sizeof(uint32_t) + 4096));
     B2_CHECK(pts.reserve(n * sizeof(float4)));
     uint32_t* d_cell = cell_of.as<uint32_t>();
     uint32_t* d_rank = d_cell + nal;
     uint32_t* d_chunk = d_rank + nal;                 // chunk totals: at most 1024 CTAs
-    int ctas = (int)std::min<size_t>((size_t)coop_max, (std::max<size_t>(n, (size_t)1 << 18) + GB_THREADS * 4 - 1) / (GB_THREADS * 4));
+    // one CTA per SM: the phases are short (a 100 k-point map), what counts is the cost of the four grid barriers
+    int ctas = std::min(coop_max, device_sm_count());
     ctas = std::max(1, std::min(ctas, 1024));
     static const int env_ctas = getenv("B2_GRID_CTAS") ? atoi(getenv("B2_GRID_CTAS")) : 0;          // kernel experiments
     if (env_ctas > 0) ctas = std::min(env_ctas, coop_max);
     const unsigned char* a_raw = src_; size_t a_stride = stride_; uint32_t a_n = (uint32_t)n; float a_h = h, a_md2 = max_dist * max_dist;
     uint32_t a_budget = (uint32_t)std::min<size_t>(cell_budget, 0xfffffff0u);
-    uint32_t* a_cs = cell_start.as<uint32_t>(); float4* a_out = pts.as<float4>(); GridDevMem* a_m = devmem.as<GridDevMem>();
-    void* args[] = {&a_raw, &a_stride, &a_n, &a_h, &a_md2, &a_budget, &d_cell, &d_rank, &a_cs, &d_chunk, &a_out, &a_m};
+    float4* a_out = pts.as<float4>(); GridDevMem* a_m = devmem.as<GridDevMem>();
+    void* args[] = {&a_raw, &a_stride, &a_n, &a_h, &a_md2, &a_budget, &d_cell, &d_rank, &a_cs, &a_other, &a_half, &d_chunk, &a_out, &a_m};
     B2_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_grid_build_dev), dim3((unsigned)ctas), dim3(GB_THREADS), args, 0, s)); count_launch();
     tl_rec(3, s);
     return B2_OK;
 }
 
 int GridIndex::rebuild_exact(cudaStream_t s) {
+    tables_clean_ = false;                            // the host-sized path uses the front of cell_start as one table
     const unsigned char* keep = src_;
     B2_CHECK(begin_device(keep, stride_, n, max_dist_, s));
     B2_CHECK(finish(s));

@@ -365,7 +365,6 @@ k_s2m_iteration(const S2MArgs a) {
     const int fpb = is_surf ? FPB : FPB_C;
     const int nfeat = is_surf ? ns : nc;
     const float4* scanp = is_surf ? (a.scan_s + s0) : (a.scan_c + c0);
-    const GridDev g = is_surf ? a.gsm->g : a.gcm->g;
     // the pose moves by millimetres between LM iterations: the previous winners bound this iteration's search radius
     uint32_t* nbp = (is_surf ? a.nb_s + (size_t)s0 * 5 : a.nb_c + (size_t)c0 * 5);
     const bool use_prev = LPF < 8 && (a.use_prev > 0 || (a.use_prev < 0 && !first && st.iters > 0));
@@ -393,6 +392,7 @@ k_s2m_iteration(const S2MArgs a) {
     __syncthreads();
 
     // ---------------- phase 1: transform + 5-NN, LPF lanes per feature
+    const GridDev g = is_surf ? a.gsm->g : a.gcm->g;          // (loaded per iteration: 14 registers that need not live across the loop)
     const int grp = threadIdx.x / LPF, sub = threadIdx.x & (LPF - 1);
 #pragma unroll 1
     for (int r = 0; r < rounds; r++) {
@@ -621,7 +621,7 @@ k_s2m_iteration(const S2MArgs a) {
     if (n_pit == 1) return;
     if (threadIdx.x == 0 && !s_last) {
         const int target = a.flag_base + pit + 1;
-        while (*reinterpret_cast<volatile int*>(a.iter_flag) - target < 0) __nanosleep(64);
+        while (*reinterpret_cast<volatile int*>(a.iter_flag) - target < 0) __nanosleep(200);
         __threadfence();
     }
     __syncthreads();
@@ -993,8 +993,16 @@ int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corn
     B2_CHECK(h->gs.build_async(h->stream2));
     B2_CUDA(cudaEventRecord(h->ev_surf, h->stream2));
     B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_surf, 0));      // everything that uses the indexes is enqueued on h->stream
-    B2_CUDA(cudaEventSynchronize(h->ev_up));
-    B2_CUDA(cudaEventSynchronize(h->ev_map));
+    // (busy wait: cudaEventSynchronize wakes up 5-9 us after the copy has landed, on a step of ~170 us)
+    for (cudaEvent_t ev : {h->ev_up, h->ev_map}) {
+        cudaError_t q;
+        while ((q = cudaEventQuery(ev)) == cudaErrorNotReady) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        if (q != cudaSuccess) { set_error("b2_s2m_set_map: %s", cudaGetErrorString(q)); return B2_ERR_CUDA; }
+    }
     h->map_pending = true;
     h->have_map = true; h->nb_valid = false; h->grid_checked = false;
     h->tl_host[1] = host_us();
