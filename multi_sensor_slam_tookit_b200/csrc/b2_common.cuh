@@ -91,12 +91,12 @@ struct GridDev {               // passed by value to kernels
 };
 // GridDev as it lives in device memory when the device sizes the grid itself (GridIndex::build_async): the geometry, the
 // bounding-box words the build reduces into, and a status (0 ok, B2_ERR_TOO_LARGE when the cells exceed the allocated table).
-struct GridDevMem { GridDev g; uint32_t bb[6]; int status; uint32_t dirty[2]; uint32_t pad; };   // dirty: entries in use in each half of the cell table
+struct GridDevMem { GridDev g; uint32_t bb[6]; int status; uint32_t dirty[2]; uint32_t bar; long long tl[8]; };   // bar: arrivals at the build kernel's grid barriers   // dirty: entries in use in each half of the cell table
 struct GridIndex {
     DevBuf pts, cell_start, cell_of, tmp, raw;
     DevBuf devmem;                                 // GridDevMem
     size_t cell_budget = 0;                        // cells the allocated cell_start can hold (device-sized builds)
-    bool tables_clean_ = false; int table_active_ = 0;   // the two halves of cell_start (build_async)
+    bool tables_clean_ = false; int table_active_ = 0; uint32_t bar_total_ = 0;   // the two halves of cell_start (build_async)
     PinBuf stage;
     GridDev dev{};
     float h = 1.0078125f;

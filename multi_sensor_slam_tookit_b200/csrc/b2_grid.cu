@@ -274,15 +274,31 @@ int GridIndex::finish(cudaStream_t s) {
 __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, float h, float max_d2,
                                                                uint32_t cell_budget, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank_in_cell,
                                                                uint32_t* __restrict__ cell_start, uint32_t* __restrict__ other_table, int active_half,
-                                                               uint32_t* __restrict__ chunk_sum, float4* __restrict__ out, GridDevMem* __restrict__ m) {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
+                                                               uint32_t* __restrict__ chunk_sum, float4* __restrict__ out, GridDevMem* __restrict__ m,
+                                                               uint32_t bar_base) {
+    // Grid barrier on a counter in device memory (arrivals accumulate over the launches: barrier k of this launch is complete at
+    // bar_base + (k + 1) * gridDim.x). A plain launch: measured on B200, a cooperative launch of this kernel starts ~12 us later
+    // than a plain one, more than the kernel runs. All CTAs are resident by construction (one per SM, the host checks it).
+    uint32_t bar_target = bar_base;
+    auto grid_sync = [&]() {
+        bar_target += gridDim.x;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(&m->bar, 1u);
+            while ((int)(*reinterpret_cast<volatile uint32_t*>(&m->bar) - bar_target) < 0) { }
+            __threadfence();
+        }
+        __syncthreads();
+    };
     const uint32_t tid = blockIdx.x * GB_THREADS + threadIdx.x, nthr = gridDim.x * GB_THREADS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ uint32_t s_w[GB_THREADS / 32];
     __shared__ uint32_t s_base;
     __shared__ float s_mn[GB_THREADS / 32][3], s_mx[GB_THREADS / 32][3];
     const uint32_t other_dirty = __ldcg(&m->dirty[active_half ^ 1]);   // read before the first barrier, rewritten after the last one
+    auto stamp = [&](int k) { if (tid == 0) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); m->tl[k] = gt; } };
+    stamp(0);
     // ---- bounding box of the finite points
     {
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -314,7 +330,8 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
             if (a <= b) { atomicMin(&m->bb[d], float_flip(a)); atomicMax(&m->bb[3 + d], float_flip(b)); }
         }
     }
-    grid.sync();
+    grid_sync();
+    stamp(1);
     // ---- geometry: every thread derives the same numbers (the arithmetic of GridIndex::finish)
     GridGeom g;
     {
@@ -329,23 +346,36 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
         for (int d = 0; d < 3; d++) ex[d] = floor(((double)mx[d] - (double)mn[d]) * (double)g.inv_h) + 2.0;
         if (ex[0] * ex[1] * ex[2] > (double)cell_budget) {
             if (tid == 0) m->status = B2_ERR_TOO_LARGE;      // bb is left as it is: rebuild_exact() resets it
-            return;                                          // uniform over the whole grid: nobody reaches another barrier
+            if (threadIdx.x == 0) atomicAdd(&m->bar, 3u);    // the three barriers nobody will reach (the host counts four per launch)
+            return;                                          // uniform over the whole grid
         }
         g.nx = (int)ex[0]; g.ny = (int)ex[1]; g.nz = (int)ex[2];
         g.ncell = (uint32_t)((size_t)g.nx * g.ny * g.nz);
     }
     const uint32_t ncount = g.ncell + 2;
-    // the table arrives zeroed (the previous build cleared it after its scatter): counting starts right away
-    for (uint32_t i = tid; i < n; i += nthr) {
-        const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
-        const uint32_t c = cell_of_point(g, p[0], p[1], p[2]);
-        cell_of[i] = c;
-        rank_in_cell[i] = atomicAdd(&cell_start[c], 1u);
+    // the table arrives zeroed (the previous build cleared it after its scatter): counting starts right away. Four points per
+    // thread are in flight (loads first, then the counting atomics): a 100 k-point map is 2-3 points per thread on 148 CTAs.
+    for (uint32_t i0 = tid; i0 < n; i0 += 4 * nthr) {
+        uint32_t c[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t i = i0 + k * nthr;
+            if (i < n) { const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride); c[k] = cell_of_point(g, p[0], p[1], p[2]); }
+        }
+        uint32_t r[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + k * nthr < n) r[k] = atomicAdd(&cell_start[c[k]], 1u);
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (i0 + k * nthr < n) { cell_of[i0 + k * nthr] = c[k]; rank_in_cell[i0 + k * nthr] = r[k]; }
     }
-    grid.sync();
-    // ---- exclusive prefix sum of cell_start[0, ncount): one contiguous chunk per CTA
-    const uint32_t chunk = (ncount + gridDim.x - 1) / gridDim.x;
+    grid_sync();
+    stamp(2);
+    // ---- exclusive prefix sum of cell_start[0, ncount): one contiguous chunk per CTA, a multiple of 8 entries. The usual map
+    // (a few hundred thousand cells) gives every thread at most 8 consecutive entries: they are loaded once (two 128-bit loads),
+    // stay in registers across the barrier and are written back as offsets — one pass over the table instead of two.
+    const uint32_t chunk = (((ncount + gridDim.x - 1) / gridDim.x) + 7u) & ~7u;
     const uint32_t c0 = min(blockIdx.x * chunk, ncount), c1 = min(c0 + chunk, ncount);
+    const bool in_regs = chunk <= GB_THREADS * 8;
     auto block_sum = [&](uint32_t v) {
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         __syncthreads();
@@ -355,13 +385,30 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
         for (int w = 0; w < GB_THREADS / 32; w++) t += s_w[w];
         return t;
     };
+    uint32_t e[8];
+    uint32_t mine = 0;
     {
         uint32_t v = 0;
-        for (uint32_t i = c0 + threadIdx.x; i < c1; i += GB_THREADS) v += cell_start[i];
+        if (in_regs) {
+            const uint32_t b = c0 + threadIdx.x * 8;          // c0 and the table are 32-byte aligned
+            if (b + 8 <= c1) {
+                const uint4 lo = *reinterpret_cast<const uint4*>(cell_start + b), hi = *reinterpret_cast<const uint4*>(cell_start + b + 4);
+                e[0] = lo.x; e[1] = lo.y; e[2] = lo.z; e[3] = lo.w; e[4] = hi.x; e[5] = hi.y; e[6] = hi.z; e[7] = hi.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; k++) e[k] = (b + k < c1) ? cell_start[b + k] : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) v += e[k];
+            mine = v;
+        } else {
+            for (uint32_t i = c0 + threadIdx.x; i < c1; i += GB_THREADS) v += cell_start[i];
+        }
         v = block_sum(v);
         if (threadIdx.x == 0) chunk_sum[blockIdx.x] = v;
     }
-    grid.sync();
+    grid_sync();
+    stamp(3);
     {
         uint32_t v = 0;
         for (uint32_t b = threadIdx.x; b < blockIdx.x; b += GB_THREADS) v += __ldcg(&chunk_sum[b]);
@@ -369,29 +416,53 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
         if (threadIdx.x == 0) s_base = v;
         __syncthreads();
     }
-    uint32_t running = s_base;
-    for (uint32_t t0 = c0; t0 < c1; t0 += GB_THREADS) {
-        const uint32_t i = t0 + threadIdx.x;
-        const uint32_t v = i < c1 ? cell_start[i] : 0u;
-        uint32_t inc = v;
+    if (in_regs) {
+        uint32_t inc = mine;                                   // exclusive scan of the per-thread totals over the CTA
         for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-        __syncthreads();
         if (lane == 31) s_w[warp] = inc;
         __syncthreads();
-        uint32_t before = 0, total = 0;
-        for (int w = 0; w < GB_THREADS / 32; w++) { const uint32_t t = s_w[w]; if (w < warp) before += t; total += t; }
-        if (i < c1) cell_start[i] = running + before + inc - v;
-        running += total;
+        uint32_t before = 0;
+        for (int w = 0; w < warp; w++) before += s_w[w];
+        uint32_t run = s_base + before + inc - mine;
+        const uint32_t b = c0 + threadIdx.x * 8;
+        uint32_t o8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { o8[k] = run; run += e[k]; }
+        if (b + 8 <= c1) {
+            *reinterpret_cast<uint4*>(cell_start + b) = make_uint4(o8[0], o8[1], o8[2], o8[3]);
+            *reinterpret_cast<uint4*>(cell_start + b + 4) = make_uint4(o8[4], o8[5], o8[6], o8[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) if (b + k < c1) cell_start[b + k] = o8[k];
+        }
+    } else {
+        uint32_t running = s_base;
+        for (uint32_t t0 = c0; t0 < c1; t0 += GB_THREADS) {
+            const uint32_t i = t0 + threadIdx.x;
+            const uint32_t v = i < c1 ? cell_start[i] : 0u;
+            uint32_t inc = v;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+            __syncthreads();
+            if (lane == 31) s_w[warp] = inc;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+            for (int w = 0; w < GB_THREADS / 32; w++) { const uint32_t t = s_w[w]; if (w < warp) before += t; total += t; }
+            if (i < c1) cell_start[i] = running + before + inc - v;
+            running += total;
+        }
     }
-    grid.sync();
+    grid_sync();
+    stamp(4);
     for (uint32_t i = tid; i < n; i += nthr) {
         const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
         out[cell_start[cell_of[i]] + rank_in_cell[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)i));
     }
+    stamp(5);
     // the other half of the table (the previous build's offsets, nobody reads them any more) is cleared for the next build
     for (uint32_t i = tid; i < other_dirty; i += nthr) other_table[i] = 0u;
     if (tid == 0) {
         m->dirty[active_half] = ncount; m->dirty[active_half ^ 1] = 0u;
+        stamp(6);
         GridDev d;
         d.pts = out; d.cell_start = cell_start;
         d.ox = g.ox; d.oy = g.oy; d.oz = g.oz; d.inv_h = g.inv_h; d.h = h;
@@ -406,10 +477,10 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
 static int grid_build_dev_max_ctas() {
     static int cached = -1;
     if (cached >= 0) return cached;
-    int dev = 0, coop = 0, per_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_build_dev, GB_THREADS, 0) != cudaSuccess) { cudaGetLastError(); cached = 0; return 0; }
-    cached = std::min(per_sm, 2) * device_sm_count();
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_build_dev, GB_THREADS, 0) != cudaSuccess) { cudaGetLastError(); cached = 0; return 0; }
+    // four builds may be in flight on one device (two handles, two maps each): each gets at most a quarter of the resident slots
+    cached = per_sm >= 4 ? device_sm_count() : (per_sm * device_sm_count()) / 4;
     return cached;
 }
 
@@ -420,6 +491,7 @@ static int store_devmem(GridIndex& gi, const GridDev& d, int status, cudaStream_
     hm.g = d; hm.status = status;
     for (int k = 0; k < 6; k++) hm.bb[k] = k < 3 ? 0xffffffffu : 0u;
     B2_CUDA(cudaMemcpyAsync(gi.devmem.p, &hm, sizeof(hm), cudaMemcpyHostToDevice, s));   // pageable source: staged before the call returns
+    gi.bar_total_ = 0;
     return B2_OK;
 }
 
@@ -495,8 +567,10 @@ int GridIndex::build_async(cudaStream_t s) {
     const unsigned char* a_raw = src_; size_t a_stride = stride_; uint32_t a_n = (uint32_t)n; float a_h = h, a_md2 = max_dist * max_dist;
     uint32_t a_budget = (uint32_t)std::min<size_t>(cell_budget, 0xfffffff0u);
     float4* a_out = pts.as<float4>(); GridDevMem* a_m = devmem.as<GridDevMem>();
-    void* args[] = {&a_raw, &a_stride, &a_n, &a_h, &a_md2, &a_budget, &d_cell, &d_rank, &a_cs, &a_other, &a_half, &d_chunk, &a_out, &a_m};
-    B2_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_grid_build_dev), dim3((unsigned)ctas), dim3(GB_THREADS), args, 0, s)); count_launch();
+    k_grid_build_dev<<<(unsigned)ctas, GB_THREADS, 0, s>>>(a_raw, a_stride, a_n, a_h, a_md2, a_budget, d_cell, d_rank, a_cs, a_other, a_half, d_chunk, a_out, a_m, bar_total_);
+    count_launch();
+    B2_CUDA(cudaGetLastError());
+    bar_total_ += 4u * (uint32_t)ctas;
     tl_rec(3, s);
     return B2_OK;
 }

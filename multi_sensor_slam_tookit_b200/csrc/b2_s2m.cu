@@ -18,6 +18,7 @@
 #include <cmath>
 #include <vector>
 #include <algorithm>
+#include <mutex>
 
 #ifndef B2_FIT_VARIANT
 #define B2_FIT_VARIANT 1      // 0: rolled loops over per-thread arrays (small code); 1: fully unrolled, register resident
@@ -96,6 +97,8 @@ struct S2MArgs {
     int* done_count;                              // number of scans whose loop has ended (host polls it between chunks)
     uint32_t* nb_c; uint32_t* nb_s;               // [feature][5] grid positions of the 5 winners of the previous iteration
     int use_prev;                                 // 1: nb_* hold the previous iteration of this scan/map; -1: they do when st.iters > 0; 0: no
+    int single;                                   // 1: one scan, its feature counts ride in the arguments (no offset table to upload or read)
+    int single_nc, single_ns;
     int use_init;                                 // 1: first launch of a single-scan solve, state = init (no upload, no state loads)
     S2MInit init;
     S2MState* result; volatile int* result_seq; int seq; int chunk_last;   // mapped host memory: state + sequence flag (single scan)
@@ -354,8 +357,8 @@ k_s2m_iteration(const S2MArgs a) {
             return;
         }
     }
-    const int c0 = a.off_c[scan], nc = a.off_c[scan + 1] - c0;
-    const int s0 = a.off_s[scan], ns = a.off_s[scan + 1] - s0;
+    const int c0 = a.single ? 0 : a.off_c[scan], nc = a.single ? a.single_nc : a.off_c[scan + 1] - c0;
+    const int s0 = a.single ? 0 : a.off_s[scan], ns = a.single ? a.single_ns : a.off_s[scan + 1] - s0;
     const int nbc = (nc + FPB_C - 1) / FPB_C, nbs = (ns + FPB - 1) / FPB;
     const int nblk = nbc + nbs;
     if ((int)blockIdx.x >= nblk) return;
@@ -669,6 +672,7 @@ struct b2_s2m_s {
     bool nb_valid = false;            // nb_* were written by an iteration on the current map and scan (host-driven b2_s2m_iterate)
     DevBuf dbg_idx_c, dbg_d2_c, dbg_coeff_c, dbg_flag_c, dbg_idx_s, dbg_d2_s, dbg_coeff_s, dbg_flag_s;
     PinBuf pin;
+    float4* scan_s_alias = nullptr;    // surf features inside scan_c's allocation (both clouds uploaded with one copy)
     PinBuf stage; size_t stage_used = 0; bool stage_all = true;   // pinned staging of the scan features (set_scan)
     S2MState* h_result = nullptr;      // mapped pinned memory the last CTA writes the state into (single-scan solves) ...
     volatile int* h_seq = nullptr;     // ... followed by the sequence number the host spins on
@@ -695,6 +699,8 @@ struct b2_s2m_s {
     cudaEvent_t tl_scan = nullptr;
     int tl_count = 0;
 };
+
+static std::mutex g_persist_mu;      // one persistent (barrier-synchronised) solve at a time per process: two could starve each other of SM slots
 
 static double host_us() {
     timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -795,8 +801,10 @@ static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, f
     S2MArgs a{};
     a.max_iters = hist_stride > 0 ? hist_stride : h->prm.max_iterations;
     a.gcm = h->gc.dev_ptr(); a.gsm = h->gs.dev_ptr();
-    a.scan_c = h->scan_c.as<float4>(); a.scan_s = h->scan_s.as<float4>();
+    a.scan_c = h->scan_c.as<float4>(); a.scan_s = h->scan_s_alias ? h->scan_s_alias : h->scan_s.as<float4>();
     a.off_c = h->off_c.as<int>(); a.off_s = h->off_c.as<int>() + (h->batch + 1);
+    a.single = (h->batch == 1 && h->h_off_c[0] == 0 && h->h_off_s[0] == 0) ? 1 : 0;
+    if (a.single) { a.single_nc = h->h_off_c[1] - h->h_off_c[0]; a.single_ns = h->h_off_s[1] - h->h_off_s[0]; }
     a.st = h->state.as<S2MState>();
     a.partial = h->partial.as<double>();
     a.max_blocks = h->max_blocks;
@@ -821,7 +829,7 @@ static int set_scan_finish(b2_s2m_s* h, int batch, bool host_upload = false) {
     h->h_off.assign(h->h_off_c.begin(), h->h_off_c.end());
     h->h_off.insert(h->h_off.end(), h->h_off_s.begin(), h->h_off_s.end());
     B2_CHECK(h->off_c.reserve(2 * (size_t)(batch + 1) * sizeof(int)));
-    B2_CUDA(cudaMemcpyAsync(h->off_c.p, h->h_off.data(), 2 * (size_t)(batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    if (batch > 1 || coff[0] != 0 || soff[0] != 0) B2_CUDA(cudaMemcpyAsync(h->off_c.p, h->h_off.data(), 2 * (size_t)(batch + 1) * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     int mb = 1;
     h->max_feat_c = h->max_feat_s = 0;
     for (int b = 0; b < batch; b++) {
@@ -872,13 +880,28 @@ static int set_scan_common(b2_s2m_s* h, int batch, const void* corner, size_t cs
     if ((h->n_c && !corner) || (h->n_s && !surf)) { set_error("set_scan: null feature array"); return B2_ERR_ARG; }
     B2_CHECK(h->stage.reserve(S2M_STAGE_MAX));
     h->stage_used = 0; h->stage_all = true;
+    h->scan_s_alias = nullptr;
+    const size_t off_s = (h->n_c * sizeof(float4) + 255) & ~(size_t)255;
+    if (cstride == sizeof(float4) && sstride == sizeof(float4) && off_s + h->n_s * sizeof(float4) <= S2M_STAGE_MAX && h->n_c + h->n_s > 0) {
+        // both clouds packed: staged side by side and moved with ONE copy (each small DMA costs ~7 us before its first byte,
+        // and the first iteration waits for the features)
+        B2_CHECK(h->scan_c.reserve(off_s + h->n_s * sizeof(float4)));
+        char* st = h->stage.as<char>();
+        if (h->n_c) memcpy(st, corner, h->n_c * sizeof(float4));
+        if (h->n_s) memcpy(st + off_s, surf, h->n_s * sizeof(float4));
+        B2_CUDA(cudaMemcpyAsync(h->scan_c.p, st, off_s + h->n_s * sizeof(float4), cudaMemcpyHostToDevice, h->stream_up));
+        h->scan_s_alias = reinterpret_cast<float4*>(h->scan_c.as<char>() + off_s);
+    } else {
     B2_CHECK(upload_points(h, h->raw_c, h->scan_c, corner, cstride, h->n_c));
     B2_CHECK(upload_points(h, h->raw_s, h->scan_s, surf, sstride, h->n_s));
+    }
     B2_CUDA(cudaEventRecord(h->ev_up, h->stream_up));
     if (h->tl_on) { if (!h->tl_scan) cudaEventCreate(&h->tl_scan); cudaEventRecord(h->tl_scan, h->stream_up); }
     B2_CUDA(cudaStreamWaitEvent(h->stream, h->ev_up, 0));
-    B2_CHECK(pack_points(h, h->raw_c, h->scan_c, cstride, h->n_c));
-    B2_CHECK(pack_points(h, h->raw_s, h->scan_s, sstride, h->n_s));
+    if (!h->scan_s_alias) {
+        B2_CHECK(pack_points(h, h->raw_c, h->scan_c, cstride, h->n_c));
+        B2_CHECK(pack_points(h, h->raw_s, h->scan_s, sstride, h->n_s));
+    }
     return set_scan_finish(h, batch, true);
 }
 
@@ -896,6 +919,7 @@ int s2m_set_scan_device(b2_s2m_s* h, const void* d_corner, size_t n_corner, cons
     h->h_off_c.assign({0, (int32_t)n_corner});
     h->h_off_s.assign({0, (int32_t)n_surf});
     h->n_c = n_corner; h->n_s = n_surf;
+    h->scan_s_alias = nullptr;
     if (n_corner) { B2_CHECK(h->scan_c.reserve(n_corner * sizeof(float4))); B2_CUDA(cudaMemcpyAsync(h->scan_c.p, d_corner, n_corner * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream)); }
     if (n_surf) { B2_CHECK(h->scan_s.reserve(n_surf * sizeof(float4))); B2_CUDA(cudaMemcpyAsync(h->scan_s.p, d_surf, n_surf * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream)); }
     return set_scan_finish(h, 1);
@@ -1096,7 +1120,8 @@ int b2_s2m_get_scan(b2_s2m_t h, int which, float* xyzi, size_t capacity, size_t*
     *n = cnt;
     if (!xyzi) return B2_OK;
     if (capacity < cnt) { set_error("b2_s2m_get_scan: %zu points, capacity %zu", cnt, capacity); return B2_ERR_CAPACITY; }
-    if (cnt) B2_CUDA(cudaMemcpyAsync(xyzi, which ? h->scan_s.p : h->scan_c.p, cnt * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    const void* d_surf = h->scan_s_alias ? static_cast<const void*>(h->scan_s_alias) : h->scan_s.p;
+    if (cnt) B2_CUDA(cudaMemcpyAsync(xyzi, which ? d_surf : h->scan_c.p, cnt * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream));
     return B2_OK;
 }
@@ -1236,10 +1261,10 @@ static int run_solve_single(b2_s2m_s* h, float* pose, int max_iterations, int* i
         int launched = 0, n_launch = 0;
         const S2MState* r = h->h_result;
         if (h->persistent_ok < 0) {
-            int dev = 0, coop = 0, per_sm = 0;
+            int per_sm = 0;
             static const bool off = getenv("B2_S2M_NO_PERSISTENT") != nullptr;
-            if (!off && cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>, S2M_THREADS, 0) == cudaSuccess)
+
+            if (!off && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>, S2M_THREADS, 0) == cudaSuccess)
                 h->persistent_ok = per_sm * device_sm_count();
             else { cudaGetLastError(); h->persistent_ok = 0; }
         }
@@ -1261,15 +1286,18 @@ static int run_solve_single(b2_s2m_s* h, float* pose, int max_iterations, int* i
             return B2_OK;
         };
         if (h->persistent_ok >= h->max_blocks) {
-            // the whole LM loop in ONE cooperative launch (every CTA resident, iterations separated by a flag in L2)
+            // the whole LM loop in ONE launch (every CTA resident, iterations separated by a flag in L2)
+            std::lock_guard<std::mutex> persist_lock(g_persist_mu);
             if (!h->flag.p) { B2_CHECK(h->flag.reserve(64)); B2_CUDA(cudaMemsetAsync(h->flag.p, 0, 64, h->stream)); h->flag_next = 0; }
             a.use_init = 1; a.persistent_iters = max_iterations; a.iter_flag = h->flag.as<int>(); a.flag_base = h->flag_next;
             h->flag_next += max_iterations;
             const int seq = ++h->seq;
             a.seq = seq; a.chunk_last = 1;
-            void* kargs[] = {&a};
-            B2_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>),
-                                                dim3((unsigned)h->max_blocks, 1u), dim3(S2M_THREADS), kargs, 0, h->stream)); count_launch();
+            // a plain launch (a cooperative one starts ~10 us later on B200): every CTA is resident because max_blocks fits the
+            // occupancy and g_persist_mu keeps a second persistent solve of this process off the device until this one is done
+            k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C><<<dim3((unsigned)h->max_blocks, 1u), S2M_THREADS, 0, h->stream>>>(a);
+            count_launch();
+            B2_CUDA(cudaGetLastError());
             n_launch = 1; launched = max_iterations;
             B2_CUDA(cudaEventRecord(h->ev1, h->stream));
             B2_CHECK(wait_seq(seq));
@@ -1339,6 +1367,13 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
                     0.0, h->tl_host[1] - t0, h->tl_host[2] - t0, h->tl_host[3] - t0, h->tl_host[4] - t0, h->tl_host[5] - t0,
                     rel(h->gc.tl_ev[1]), rel(h->gc.tl_ev[3]), rel(h->gs.tl_ev[0]), rel(h->gs.tl_ev[1]), rel(h->gs.tl_ev[3]), rel(h->tl_scan),
                     rel(h->ev0), rel(h->ev1));
+            GridDevMem gm[2];
+            cudaMemcpy(&gm[0], h->gc.dev_ptr(), sizeof(GridDevMem), cudaMemcpyDeviceToHost);
+            cudaMemcpy(&gm[1], h->gs.dev_ptr(), sizeof(GridDevMem), cudaMemcpyDeviceToHost);
+            for (int k = 0; k < 2; k++)
+                fprintf(stderr, "[b2 timeline us] %s build phases: bbox %.1f geometry+count %.1f chunk sums %.1f scan %.1f scatter %.1f zero-other %.1f (grid %d x %d x %d)\n", k ? "surf" : "corner",
+                        (gm[k].tl[1] - gm[k].tl[0]) * 1e-3, (gm[k].tl[2] - gm[k].tl[1]) * 1e-3, (gm[k].tl[3] - gm[k].tl[2]) * 1e-3, (gm[k].tl[4] - gm[k].tl[3]) * 1e-3,
+                        (gm[k].tl[5] - gm[k].tl[4]) * 1e-3, (gm[k].tl[6] - gm[k].tl[5]) * 1e-3, gm[k].g.nx, gm[k].g.ny, gm[k].g.nz);
         }
         return st;
     }
