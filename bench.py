@@ -325,19 +325,45 @@ def run_b200(args, rank, local_rank, world):
     lm_pts = (int(sum(len(k[0]) for k in kfs)), int(sum(len(k[1]) for k in kfs)), int(len(lm.get("cornerDS"))), int(len(lm.get("surfDS"))))
     g.setInputMap(mc, ms)
     barrier()
-    # ---- batched: B pose hypotheses of the scan against the resident map, one launch per iteration
+    # ---- batched: B (scan, initial guess) problems against the resident map, two launches per LM iteration (search, fits).
+    # The scans are DISTINCT: 16 VLP-16 sweeps ray-cast at 16 poses 0.6 m apart along the street, features from the library's
+    # own front end (b2_scan_*) and VoxelGrids, each registered from 16 different initial guesses.
     batched = None
     B = args.batch
     if B > 1:
+        from multi_sensor_slam_tookit_b200.frontend import ScanFrontEnd
+        from multi_sensor_slam_tookit_b200.registration import VoxelGrid
+        n_distinct = min(16, B)
+        scene = synth.CityBlock(synth.MASTER_SEED)
+        fe = ScanFrontEnd()
+        vgc, vgs = VoxelGrid(), VoxelGrid()
+        vgc.setLeafSize(0.2, 0.2, 0.2); vgs.setLeafSize(0.4, 0.4, 0.4)
+        scans, truths = [], []
+        for k in range(n_distinct):
+            pk = c1["pose_truth"].astype(np.float64).copy()
+            pk[3] += (k - n_distinct // 2) * 0.6 + 0.3
+            raw = synth.ring_scan(scene, pk, seed=synth.MASTER_SEED + 7000 + k)
+            fe.projectPointCloud(raw, imu=None, deskew=False)
+            f = fe.extractFeatures()
+            vgc.setInputCloud(f["corner"]); vgs.setInputCloud(f["surf"])
+            scans.append((np.ascontiguousarray(vgc.filter()), np.ascontiguousarray(vgs.filter())))
+            truths.append(pk.astype(np.float32))
         rng = np.random.default_rng(7)
-        poses = np.tile(c1["pose_truth"], (B, 1)).astype(np.float32)
+        idx = np.arange(B) % n_distinct
+        poses = np.stack([truths[i] for i in idx]).astype(np.float32)
         poses[:, 3:] += rng.uniform(-0.15, 0.15, (B, 3)).astype(np.float32)
         poses[:, :3] += np.deg2rad(rng.uniform(-1.0, 1.0, (B, 3))).astype(np.float32)
         gb = ScanToMapOptimizer(max_batch=B)
         gb.setInputMap(mc, ms)
-        gb.setInputScanBatch([sc] * B, [ss] * B)
+        gb.setInputScanBatch([scans[i][0] for i in idx], [scans[i][1] for i in idx])
         rb = gb.scan2MapOptimizationBatch(poses)
         b_max = int(rb["iters"].max())
+        # one counted solve: candidates the search really loads, and the features of every active (scan, iteration) pair
+        gb.countCandidates(True)
+        rc = gb.scan2MapOptimizationBatch(poses, b_max)
+        cand_total = gb.countCandidates(False)
+        feat_per_scan = np.array([len(scans[i][0]) + len(scans[i][1]) for i in idx], np.float64)
+        feat_iters = float((feat_per_scan * rc["iters"]).sum())
         for _ in range(3):
             flush_l2(); gb.scan2MapOptimizationBatch(poses, b_max)
         Kb = max(3, min(K, 20))
@@ -347,9 +373,12 @@ def run_b200(args, rank, local_rank, world):
             rb = gb.scan2MapOptimizationBatch(poses, b_max)
             b_ms += gb.lastGpuMs()[0]
             b_iters += int(rb["iters"].sum())
-        batched = {"scans": B, "steps": Kb, "value": b_iters / (b_ms * 1e-3), "unit": UNIT, "ms_per_step": b_ms / Kb,
-                   "iters_per_step": b_iters / Kb, "converged": int(rb["converged"].sum()), "max_iters_in_batch": b_max}
-        del gb
+        b_bytes = 72.0 * feat_iters + 16.0 * float(cand_total) + 224.0 * float(rc["iters"].sum())
+        batched = {"scans": B, "distinct_scans": n_distinct, "steps": Kb, "value": b_iters / (b_ms * 1e-3), "unit": UNIT, "ms_per_step": b_ms / Kb,
+                   "iters_per_step": b_iters / Kb, "converged": int(rb["converged"].sum()), "max_iters_in_batch": b_max,
+                   "features_per_scan": float(feat_per_scan.mean()), "candidates_read_per_feature": float(cand_total) / max(feat_iters, 1.0),
+                   "bytes_per_step": b_bytes, "gpu_launches_per_step": int(gb.lastGpuMs()[1])}
+        del gb, fe, vgc, vgs
     barrier()
     clocks = sampler.stop() if sampler else None
 
@@ -415,9 +444,12 @@ def run_b200(args, rank, local_rank, world):
             "cpu_baseline": {"value": cpu_lm, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "the same step on the oracle (transformPointCloud x 24, two VoxelGrids, two kd-trees, LM loop) for 4 s"}}
         if batched:
-            bb = abytes * batched["iters_per_step"] / (batched["ms_per_step"] * 1e-3) / 1e9
-            batched["roofline"] = {"achieved": bb, "peak": peak, "unit": "GB/s", "frac": bb / peak,
-                                   "note": "algorithmic bytes of all active (scan, iteration) pairs / device span of the step"}
+            bb = batched["bytes_per_step"] / (batched["ms_per_step"] * 1e-3) / 1e9
+            batched["roofline"] = {"kernel": "k_s2m_iteration<1,1,1,1> (search) + <1,1,1,2> (fits)", "bound": "hbm", "achieved": bb, "peak": peak,
+                                   "unit": "GB/s", "frac": bb / peak, "traffic": measured_traffic("k_s2m_batched"),
+                                   "note": "algorithmic bytes = 72 B per feature + 16 B per candidate the search LOADED (counted on the device in a "
+                                           "separate solve) + 224 B per (scan, iteration), over the device span of the step. The map (1.6 MB) is "
+                                           "L2-resident: this is L2-to-SM traffic against the HBM peak, DRAM itself stays nearly idle (see profiles/)"}
             line["batched"] = batched
         # CPU baseline on this box's host cores, bounded samples of the same step
         cores = host_cores()

@@ -148,6 +148,9 @@ int  b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches);
  * b2_s2m_set_map_from_localmap left in device memory (the reference rebuilds both kd-trees for every scan). Returns with the
  * builds queued, like b2_s2m_set_map. b2_s2m_last_step_gpu_ms: device time from the start of that rebuild to the end of the
  * solve that followed it (CUDA events) = one reference step "index build + LM loop" with the inputs resident in HBM. */
+/* Measurement hook: while enabled, batched solves count the map points their neighbour search actually loads (all scans, all
+ * iterations of the solve); last_count returns the total of the last counted solve. Used for the roofline numerator. */
+int  b2_s2m_count_candidates(b2_s2m_t h, int enable, unsigned long long* last_count);
 int  b2_s2m_rebuild_map_index(b2_s2m_t h);
 int  b2_s2m_last_step_gpu_ms(b2_s2m_t h, float* ms);
 

@@ -70,7 +70,7 @@ SYMBOLS = [
     "b2_knn_create", "b2_knn_destroy", "b2_knn_set_input_cloud", "b2_knn_nearest_k_search",
     "b2_s2m_default_params", "b2_s2m_create", "b2_s2m_destroy", "b2_s2m_set_map", "b2_s2m_set_scan", "b2_s2m_iterate",
     "b2_s2m_solve", "b2_s2m_set_state", "b2_s2m_get_pass", "b2_s2m_get_normal_equations", "b2_s2m_set_scan_batch",
-    "b2_s2m_solve_batch", "b2_s2m_last_gpu_ms", "b2_s2m_rebuild_map_index", "b2_s2m_last_step_gpu_ms", "b2_transform_cloud",
+    "b2_s2m_solve_batch", "b2_s2m_last_gpu_ms", "b2_s2m_rebuild_map_index", "b2_s2m_last_step_gpu_ms", "b2_s2m_count_candidates", "b2_transform_cloud",
     "b2_scan_default_params", "b2_scan_create", "b2_scan_destroy", "b2_scan_project", "b2_scan_extract_features",
     "b2_scan_last_gpu_ms", "b2_imu_deskew_info",
     "b2_cloud_info_parse", "b2_scan_write_cloud_info", "b2_scan_set_from_cloud_info", "b2_s2m_set_scan_downsampled",
@@ -160,6 +160,7 @@ def lib():
     L.b2_s2m_solve_batch.argtypes = [vp, vp, i32, vp, vp, vp]
     L.b2_s2m_last_gpu_ms.argtypes = [vp, pf, pi]
     L.b2_s2m_rebuild_map_index.argtypes = [vp]
+    L.b2_s2m_count_candidates.argtypes = [vp, i32, C.POINTER(C.c_ulonglong)]
     L.b2_s2m_last_step_gpu_ms.argtypes = [vp, pf]
     L.b2_transform_cloud.argtypes = [vp, sz, sz, vp, vp, sz]
     L.b2_scan_default_params.argtypes = [C.POINTER(ScanParams)]

@@ -52,7 +52,8 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned mask, unsign
 // faces (a few float ulps of the cell coordinate; slack is ~80x that), and the faces' distances are shortened by it.
 template <int K, int LPF>
 __device__ __forceinline__ void knn_group(const GridDev& g, float qx, float qy, float qz, bool active, float bound2,
-                                          unsigned long long (&out_key)[K], uint32_t (&out_pos)[K]) {
+                                          unsigned long long (&out_key)[K], uint32_t (&out_pos)[K], uint32_t* visited = nullptr) {
+    uint32_t n_visited = 0;                       // candidates this lane loaded (statistics for the roofline numerator; dead code when unused)
     const int lane = threadIdx.x & 31;
     const int sub = lane & (LPF - 1);
     TopK<K> top; top.clear();
@@ -88,6 +89,7 @@ __device__ __forceinline__ void knn_group(const GridDev& g, float qx, float qy, 
             };
             auto scan_row = [&](uint32_t p, uint32_t e, float4 c) {
                 for (;;) {
+                    n_visited++;
                     const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
                     float d = dx * dx;
                     d = d + dy * dy;
@@ -134,6 +136,7 @@ __device__ __forceinline__ void knn_group(const GridDev& g, float qx, float qy, 
                 if (have) { p = lb[0]; e = le[0]; k = 1; }
                 while (have) {
                     const float4 c = ldg4(&g.pts[p]);
+                    n_visited++;
                     const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z;
                     float d = dx * dx;
                     d = d + dy * dy;
@@ -162,6 +165,7 @@ __device__ __forceinline__ void knn_group(const GridDev& g, float qx, float qy, 
             }
         }
     }
+    if (visited) *visited += n_visited;
     // merge the LPF sorted lists: K rounds of group-min. The scan above diverges per lane (row lengths differ); without an
     // explicit reconvergence point the full-mask shuffles below run on the divergent slow path (measured 5x slower).
     __syncwarp();

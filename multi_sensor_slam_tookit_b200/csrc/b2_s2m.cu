@@ -104,6 +104,7 @@ struct S2MArgs {
     S2MState* result; volatile int* result_seq; int seq; int chunk_last;   // mapped host memory: state + sequence flag (single scan)
     int persistent_iters;                         // > 0: ONE cooperative launch runs up to this many LM iterations (single scan); the
     int* iter_flag; int flag_base;                //      last CTA of an iteration publishes flag_base + k, the other CTAs wait for it
+    unsigned long long* cand_count;               // optional: candidates loaded by the neighbour search, summed over the launch
     long long* prof;                              // optional per-CTA clock64 stamps (B2_S2M_PROF=1), 16 per CTA
     float* pose_hist; int hist_stride;            // optional [batch][max_iters][6]
     // optional per-feature introspection (single-scan parity runs)
@@ -323,8 +324,17 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
 #ifndef S2M_LAT_MAXREG
 #define S2M_LAT_MAXREG 120
 #endif
-template <int LPF, int ROUNDS, int ROUNDS_C>
-__global__ void __launch_bounds__(S2M_THREADS) __maxnreg__((LPF == S2M_THR_LPF && ROUNDS == S2M_THR_ROUNDS) ? 65536 / (S2M_THREADS * S2M_THR_MINB) : S2M_LAT_MAXREG)
+// PHASES: 3 = neighbour search and fits in one kernel (single scan, latency); the batched shape runs them as two launches with
+// their own register budgets — 1 = search only (winners' grid positions to HBM, 20 B per feature), 2 = fits, Jacobian rows,
+// reduction and epilogue from those positions. Fused at 64 registers the fits spilled ~440 MB of local memory per launch.
+#ifndef S2M_THR_KNN_MAXREG
+#define S2M_THR_KNN_MAXREG 64
+#endif
+#ifndef S2M_THR_FIT_MAXREG
+#define S2M_THR_FIT_MAXREG 128
+#endif
+template <int LPF, int ROUNDS, int ROUNDS_C, int PHASES>
+__global__ void __launch_bounds__(S2M_THREADS) __maxnreg__(PHASES == 1 ? S2M_THR_KNN_MAXREG : (PHASES == 2 ? S2M_THR_FIT_MAXREG : S2M_LAT_MAXREG))
 k_s2m_iteration(const S2MArgs a) {
     constexpr int FPR = S2M_THREADS / LPF;
     constexpr int FPB = FPR * ROUNDS;                 // features per surf CTA (and the size of the shared arrays)
@@ -397,6 +407,36 @@ k_s2m_iteration(const S2MArgs a) {
     // ---------------- phase 1: transform + 5-NN, LPF lanes per feature
     const GridDev g = is_surf ? a.gsm->g : a.gcm->g;          // (loaded per iteration: 14 registers that need not live across the loop)
     const int grp = threadIdx.x / LPF, sub = threadIdx.x & (LPF - 1);
+    if constexpr (PHASES == 2) {
+        // the search ran in its own launch: winners come back from HBM by position, distances are recomputed with the search's
+        // own expression (same bits), everything lands in shared memory where the fused kernel would have put it
+        const int slot = threadIdx.x, f = fb + slot;
+        if (slot < fpb && f < nfeat) {
+            const float4 po = __ldg(&scanp[f]);
+            const float sx = s_xf[0] * po.x + s_xf[1] * po.y + s_xf[2] * po.z + s_xf[3];
+            const float sy = s_xf[4] * po.x + s_xf[5] * po.y + s_xf[6] * po.z + s_xf[7];
+            const float sz = s_xf[8] * po.x + s_xf[9] * po.y + s_xf[10] * po.z + s_xf[11];
+            uint32_t pp[5];
+#pragma unroll
+            for (int j = 0; j < 5; j++) pp[j] = __ldcg(&nbp[(size_t)f * 5 + j]);
+#pragma unroll
+            for (int j = 0; j < 5; j++) {
+                float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                float d = INFINITY;
+                if (pp[j] != 0xffffffffu) {
+                    c = ldg4(&g.pts[pp[j]]);
+                    const float dx = sx - c.x, dy = sy - c.y, dz = sz - c.z;
+                    d = dx * dx;
+                    d = d + dy * dy;
+                    d = d + dz * dz;
+                }
+                s_nb[slot][j] = c;
+                s_d2[slot][j] = d;
+            }
+            s_ori[slot] = po;
+            s_sel[slot] = make_float4(sx, sy, sz, 0.f);
+        }
+    } else {
 #pragma unroll 1
     for (int r = 0; r < rounds; r++) {
         const int slot = r * FPR + grp;
@@ -431,7 +471,17 @@ k_s2m_iteration(const S2MArgs a) {
             bound2 = m;
         }
         unsigned long long key[5]; uint32_t pos[5];
-        knn_group<5, LPF>(g, sx, sy, sz, active, bound2, key, pos);
+        if constexpr (PHASES == 1) {
+            uint32_t visited = 0;
+            knn_group<5, LPF>(g, sx, sy, sz, active, bound2, key, pos, &visited);
+            if (a.cand_count) {                    // statistics run (bench.py): one atomic per warp
+                __syncwarp();
+                const uint32_t w = __reduce_add_sync(0xffffffffu, visited);
+                if ((threadIdx.x & 31) == 0 && w) atomicAdd(a.cand_count, (unsigned long long)w);
+            }
+        } else {
+            knn_group<5, LPF>(g, sx, sy, sz, active, bound2, key, pos);
+        }
         if (active) {
             if constexpr (LPF >= 8) {
                 if (sub < 5) {
@@ -451,18 +501,24 @@ k_s2m_iteration(const S2MArgs a) {
             } else if (sub == 0) {
 #pragma unroll
                 for (int j = 0; j < 5; j++) {
-                    float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-                    float d = INFINITY;
-                    if (key[j] != KNN_EMPTY) { c = ldg4(&g.pts[pos[j]]); d = __uint_as_float((uint32_t)(key[j] >> 32)); }
-                    s_nb[slot][j] = c;
-                    s_d2[slot][j] = d;
+                    if constexpr (PHASES == 3) {
+                        float4 c = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+                        float d = INFINITY;
+                        if (key[j] != KNN_EMPTY) { c = ldg4(&g.pts[pos[j]]); d = __uint_as_float((uint32_t)(key[j] >> 32)); }
+                        s_nb[slot][j] = c;
+                        s_d2[slot][j] = d;
+                    }
                     __stcg(&nbp[(size_t)f * 5 + j], key[j] != KNN_EMPTY ? pos[j] : 0xffffffffu);
                 }
-                s_ori[slot] = po;
-                s_sel[slot] = make_float4(sx, sy, sz, 0.f);
+                if constexpr (PHASES == 3) {
+                    s_ori[slot] = po;
+                    s_sel[slot] = make_float4(sx, sy, sz, 0.f);
+                }
             }
         }
     }
+    }
+    if constexpr (PHASES == 1) return;               // search only: the fits run in the next launch
     __syncthreads();
     if (prof && threadIdx.x == 0) prof[1] = clock64();
 
@@ -678,6 +734,7 @@ struct b2_s2m_s {
     volatile int* h_seq = nullptr;     // ... followed by the sequence number the host spins on
     int seq = 0;
     bool last_ms_valid = true;
+    DevBuf cand; bool count_candidates = false; unsigned long long last_candidates = 0;   // b2_s2m_count_candidates
     DevBuf flag; int flag_next = 0;    // iteration counter of persistent single-scan solves (device int, zeroed once)
     int persistent_ok = -1;            // -1 unknown, 0 cooperative launch unavailable, else CTAs that can be co-resident
     bool grid_checked = false;         // the status words of the current map grids have been read (check_grid_status)
@@ -785,13 +842,15 @@ static int launch_iteration(b2_s2m_s* h, const S2MArgs& a, int batch) {
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr; cfg.numAttrs = h->use_pdl ? 1 : 0;
-        const cudaError_t le = cudaLaunchKernelEx(&cfg, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>, b);
+        const cudaError_t le = cudaLaunchKernelEx(&cfg, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C, 3>, b);
         if (le != cudaSuccess) { set_error("k_s2m_iteration launch -> %s", cudaGetErrorString(le)); return B2_ERR_CUDA; }
     } else {
         const int nb = (h->max_feat_c + S2M_THR_FPB - 1) / S2M_THR_FPB + (h->max_feat_s + S2M_THR_FPB - 1) / S2M_THR_FPB;
         dim3 grid((unsigned)std::max(nb, 1), (unsigned)batch);
-        k_s2m_iteration<S2M_THR_LPF, S2M_THR_ROUNDS, S2M_THR_ROUNDS><<<grid, S2M_THREADS, 0, h->stream>>>(a);
+        k_s2m_iteration<S2M_THR_LPF, S2M_THR_ROUNDS, S2M_THR_ROUNDS, 1><<<grid, S2M_THREADS, 0, h->stream>>>(a);
+        k_s2m_iteration<S2M_THR_LPF, S2M_THR_ROUNDS, S2M_THR_ROUNDS, 2><<<grid, S2M_THREADS, 0, h->stream>>>(a);
         B2_CUDA(cudaGetLastError());
+        count_launch();
     }
     count_launch();
     return B2_OK;
@@ -814,6 +873,7 @@ static S2MArgs make_args(b2_s2m_s* h, int iter, int device_driven, bool debug, f
     a.want_matP = 1; a.done_count = nullptr;
     a.nb_c = h->nb_c.as<uint32_t>(); a.nb_s = h->nb_s.as<uint32_t>();
     a.use_prev = device_driven ? -1 : 0;
+    a.cand_count = (h->count_candidates && h->cand.p) ? h->cand.as<unsigned long long>() : nullptr;
     if (debug) {
         a.dbg_idx_c = h->dbg_idx_c.as<int32_t>(); a.dbg_d2_c = h->dbg_d2_c.as<float>(); a.dbg_coeff_c = h->dbg_coeff_c.as<float4>(); a.dbg_flag_c = h->dbg_flag_c.as<uint8_t>();
         a.dbg_idx_s = h->dbg_idx_s.as<int32_t>(); a.dbg_d2_s = h->dbg_d2_s.as<float>(); a.dbg_coeff_s = h->dbg_coeff_s.as<float4>(); a.dbg_flag_s = h->dbg_flag_s.as<uint8_t>();
@@ -978,7 +1038,7 @@ int b2_s2m_destroy(b2_s2m_t h) {
     if (!h) return B2_ERR_ARG;
     if (h->map_pending || h->scan_pending) drain_pending(h);     // kernels of a set_map / set_scan nobody waited for
     h->gc.release(); h->gs.release();
-    h->flag.release();
+    h->flag.release(); h->cand.release();
     DevBuf* bufs[] = {&h->raw_c, &h->raw_s, &h->scan_c, &h->scan_s, &h->off_c, &h->off_s, &h->state, &h->partial, &h->hist, &h->ne, &h->nb_c, &h->nb_s,
                       &h->dbg_idx_c, &h->dbg_d2_c, &h->dbg_coeff_c, &h->dbg_flag_c, &h->dbg_idx_s, &h->dbg_d2_s, &h->dbg_coeff_s, &h->dbg_flag_s};
     for (DevBuf* b : bufs) b->release();
@@ -1193,7 +1253,7 @@ int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, in
             }
             std::sort(st_us.begin(), st_us.end()); std::sort(en_us.begin(), en_us.end());
             int occ = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>, S2M_THREADS, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C, 3>, S2M_THREADS, 0);
             const size_t m = st_us.size();
             fprintf(stderr, "[b2 prof] iter %d: CTA starts (us) p50 %.2f p90 %.2f max %.2f | ends p50 %.2f p90 %.2f max %.2f | CTAs/SM by occupancy %d\n",
                     iter, st_us[m / 2], st_us[m * 9 / 10], st_us[m - 1], en_us[m / 2], en_us[m * 9 / 10], en_us[m - 1], occ);
@@ -1264,7 +1324,7 @@ static int run_solve_single(b2_s2m_s* h, float* pose, int max_iterations, int* i
             int per_sm = 0;
             static const bool off = getenv("B2_S2M_NO_PERSISTENT") != nullptr;
 
-            if (!off && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C>, S2M_THREADS, 0) == cudaSuccess)
+            if (!off && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C, 3>, S2M_THREADS, 0) == cudaSuccess)
                 h->persistent_ok = per_sm * device_sm_count();
             else { cudaGetLastError(); h->persistent_ok = 0; }
         }
@@ -1295,7 +1355,7 @@ static int run_solve_single(b2_s2m_s* h, float* pose, int max_iterations, int* i
             a.seq = seq; a.chunk_last = 1;
             // a plain launch (a cooperative one starts ~10 us later on B200): every CTA is resident because max_blocks fits the
             // occupancy and g_persist_mu keeps a second persistent solve of this process off the device until this one is done
-            k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C><<<dim3((unsigned)h->max_blocks, 1u), S2M_THREADS, 0, h->stream>>>(a);
+            k_s2m_iteration<S2M_LAT_LPF, S2M_LAT_ROUNDS, S2M_LAT_ROUNDS_C, 3><<<dim3((unsigned)h->max_blocks, 1u), S2M_THREADS, 0, h->stream>>>(a);
             count_launch();
             B2_CUDA(cudaGetLastError());
             n_launch = 1; launched = max_iterations;
@@ -1410,6 +1470,10 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
         B2_CUDA(cudaGetLastError());
         n_launch = 1;
     }
+    if (h->count_candidates) {
+        B2_CHECK(h->cand.reserve(64));
+        B2_CUDA(cudaMemsetAsync(h->cand.p, 0, 64, h->stream));
+    }
     S2MArgs a = make_args(h, -1, 1, false, d_hist, max_iterations);
     a.want_matP = want_matP ? 1 : 0;
     a.done_count = d_done;
@@ -1439,6 +1503,10 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
     B2_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
     h->last_ms_valid = true;
     h->last_launches = n_launch;
+    if (h->count_candidates) {
+        B2_CUDA(cudaMemcpyAsync(&h->last_candidates, h->cand.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+    }
     h->map_pending = h->scan_pending = false;      // h->stream has drained, and it had waited for the other two
     h->nb_valid = true;
     for (int b = 0; b < B; b++) {
@@ -1487,6 +1555,15 @@ int b2_s2m_get_normal_equations(b2_s2m_t h, float AtA[36], float AtB[6], float X
     if (AtA) memcpy(AtA, hs.AtA, sizeof(hs.AtA));
     if (AtB) memcpy(AtB, hs.AtB, sizeof(hs.AtB));
     if (X) memcpy(X, hs.X, sizeof(hs.X));
+    return B2_OK;
+}
+
+// Statistics for the roofline numerator: with `enable` the batched solves count every candidate their neighbour search loads
+// (one atomic per warp; costs a few percent, so bench.py switches it on for one untimed solve only).
+int b2_s2m_count_candidates(b2_s2m_t h, int enable, unsigned long long* last_count) {
+    if (!h) return B2_ERR_ARG;
+    h->count_candidates = enable != 0;
+    if (last_count) *last_count = h->last_candidates;
     return B2_OK;
 }
 

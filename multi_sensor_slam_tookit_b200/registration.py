@@ -235,6 +235,12 @@ class ScanToMapOptimizer:
         capi.check(capi.lib().b2_s2m_last_gpu_ms(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def countCandidates(self, enable):
+        """Measurement hook: batched solves count the map points their search loads; returns the last counted total."""
+        n = C.c_ulonglong(0)
+        capi.check(capi.lib().b2_s2m_count_candidates(self._h, 1 if enable else 0, C.byref(n)))
+        return n.value
+
     def getPass(self, which):
         n = self._ns if which else self._nc
         idx = np.empty((n, 5), np.int32)
