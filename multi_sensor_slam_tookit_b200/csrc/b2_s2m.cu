@@ -147,7 +147,7 @@ __global__ void k_s2m_prepare(S2MState* st, int batch, const int* off_c, const i
 
 // ---- per-feature fits -------------------------------------------------------------------------------------------
 // Returns true when the feature is kept; coeff = coeffSel entry.
-__device__ B2_FIT_ATTR bool fit_line(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+__device__ __forceinline__ bool fit_line_impl(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
                                          float x0, float y0, float z0, float4& coeff) {
     float cx = 0, cy = 0, cz = 0;
 #pragma unroll
@@ -187,7 +187,7 @@ __device__ B2_FIT_ATTR bool fit_line(const float (&nx)[5], const float (&ny)[5],
     return s > 0.1;
 }
 
-__device__ B2_FIT_ATTR bool fit_plane(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+__device__ __forceinline__ bool fit_plane_impl(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
                                           float sx, float sy, float sz, float ox, float oy, float oz, float4& coeff) {
 #if B2_FIT_VARIANT == 1
     float pa, pb, pc, pd = 1;
@@ -208,6 +208,16 @@ __device__ B2_FIT_ATTR bool fit_plane(const float (&nx)[5], const float (&ny)[5]
     float s = 1 - 0.9 * fabsf(pd2) / sqrtf(sqrtf(ox * ox + oy * oy + oz * oz));
     coeff = make_float4(s * pa, s * pb, s * pc, s * pd2);
     return s > 0.1;
+}
+
+// Out-of-line copies for the single-scan kernel (one warp walks the fits once per launch: code size is what it pays for); the
+// batched fit kernel inlines them, so the neighbour coordinates stay in registers instead of going through local memory.
+__device__ B2_FIT_ATTR bool fit_line(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5], float x0, float y0, float z0, float4& coeff) {
+    return fit_line_impl(nx, ny, nz, x0, y0, z0, coeff);
+}
+__device__ B2_FIT_ATTR bool fit_plane(const float (&nx)[5], const float (&ny)[5], const float (&nz)[5],
+                                      float sx, float sy, float sz, float ox, float oy, float oz, float4& coeff) {
+    return fit_plane_impl(nx, ny, nz, sx, sy, sz, ox, oy, oz, coeff);
 }
 
 // ---- epilogue: normal equations -> pose update (single thread) ------------------------------------------------------
@@ -331,7 +341,7 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
 #define S2M_THR_KNN_MAXREG 64
 #endif
 #ifndef S2M_THR_FIT_MAXREG
-#define S2M_THR_FIT_MAXREG 128
+#define S2M_THR_FIT_MAXREG 80
 #endif
 template <int LPF, int ROUNDS, int ROUNDS_C, int PHASES>
 __global__ void __launch_bounds__(S2M_THREADS) __maxnreg__(PHASES == 1 ? S2M_THR_KNN_MAXREG : (PHASES == 2 ? S2M_THR_FIT_MAXREG : S2M_LAT_MAXREG))
@@ -538,8 +548,13 @@ k_s2m_iteration(const S2MArgs a) {
             ox = po.x; oy = po.y; oz = po.z;
             const float d4 = s_d2[slot][4];
             if (d4 < 1.0) {
-                if (is_surf) keep = fit_plane(nx, ny, nz, ps.x, ps.y, ps.z, ox, oy, oz, coeff);
-                else keep = fit_line(nx, ny, nz, ps.x, ps.y, ps.z, coeff);
+                if constexpr (PHASES == 2) {
+                    if (is_surf) keep = fit_plane_impl(nx, ny, nz, ps.x, ps.y, ps.z, ox, oy, oz, coeff);
+                    else keep = fit_line_impl(nx, ny, nz, ps.x, ps.y, ps.z, coeff);
+                } else {
+                    if (is_surf) keep = fit_plane(nx, ny, nz, ps.x, ps.y, ps.z, ox, oy, oz, coeff);
+                    else keep = fit_line(nx, ny, nz, ps.x, ps.y, ps.z, coeff);
+                }
             }
             int32_t* di = is_surf ? a.dbg_idx_s : a.dbg_idx_c;
             if (di) {
