@@ -3,12 +3,13 @@
 // Drop-in for the call sites of SURVEY.md §8b: the reference keeps its pcl::PointCloud<PointT> containers and calls the
 // same member names; the arithmetic runs in libb2reg.so on the GPU. The header needs only <pcl/point_cloud.h> and
 // <pcl/point_types.h> from PCL (containers and point structs, no algorithms). PCL is not installed in the build image:
-// tests/test_shim_compiles.py syntax-checks it against minimal stand-ins (tests/stubs/pcl); INTEGRATION.md shows where
-// each class goes.
+// tests/test_shim_compiles.py type-checks it against minimal stand-ins (tests/stubs/pcl) and, on the GPU box, compiles and RUNS
+// a program through it on the C1 workload (tests/shim_c1_main.cpp); INTEGRATION.md shows where each class goes.
 #pragma once
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <cstdint>
 #include <vector>
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
@@ -71,6 +72,106 @@ public:
     }
 private:
     b2_s2m_t h_ = nullptr;
+};
+
+// replaces pcl::KdTreeFLANN<PointT> where the reference issues one nearestKSearch per point inside a loop
+// (mapOptmization.cpp:987,1079; the loop bodies of :978-1063 and :1070-1134 when only the search is moved to the GPU).
+// A per-query GPU call is useless, so the batched overload takes all queries of the loop at once; the single-point overload
+// keeps PCL's signature (returns the number of neighbours found) for the few call sites outside a loop. Exact k-NN within
+// `max_dist` (the reference consumes nothing beyond 1 m, :993,1089); neighbours farther than that are reported as -1 / inf.
+// radiusSearch on key poses (:871,460,624 — a few thousand points) stays on pcl::KdTreeFLANN.
+template <typename PointT>
+class KdTreeFLANN {
+public:
+    explicit KdTreeFLANN(float max_dist = 1.0f) { check(b2_knn_create(&h_, max_dist), "b2_knn_create"); }
+    ~KdTreeFLANN() { b2_knn_destroy(h_); }
+    KdTreeFLANN(const KdTreeFLANN&) = delete;
+    void setInputCloud(const typename pcl::PointCloud<PointT>::ConstPtr& cloud) {
+        check(b2_knn_set_input_cloud(h_, cloud->points.data(), sizeof(PointT), cloud->size()), "setInputCloud");
+    }
+    // all queries of one loop: k_indices / k_sqr_distances get queries.size() * k entries, row per query, ascending distance
+    void nearestKSearch(const pcl::PointCloud<PointT>& queries, int k, std::vector<int>& k_indices, std::vector<float>& k_sqr_distances) const {
+        k_indices.resize(queries.size() * static_cast<size_t>(k));
+        k_sqr_distances.resize(queries.size() * static_cast<size_t>(k));
+        static_assert(sizeof(int) == sizeof(int32_t), "int32 indices");
+        check(b2_knn_nearest_k_search(h_, queries.points.data(), sizeof(PointT), queries.size(), k,
+                                      reinterpret_cast<int32_t*>(k_indices.data()), k_sqr_distances.data()), "nearestKSearch");
+    }
+    int nearestKSearch(const PointT& point, int k, std::vector<int>& k_indices, std::vector<float>& k_sqr_distances) const {
+        k_indices.resize(k); k_sqr_distances.resize(k);
+        check(b2_knn_nearest_k_search(h_, &point, sizeof(PointT), 1, k, reinterpret_cast<int32_t*>(k_indices.data()), k_sqr_distances.data()), "nearestKSearch");
+        int found = 0;
+        while (found < k && k_indices[found] >= 0) found++;
+        k_indices.resize(found); k_sqr_distances.resize(found);
+        return found;
+    }
+private:
+    b2_knn_t h_ = nullptr;
+};
+
+// replaces the per-scan bodies of ImageProjection (imageProjection.cpp:180-195: imuDeskewInfo inside deskewInfo(),
+// projectPointCloud(), cloudExtraction()) and FeatureExtraction (featureExtraction.cpp:66-79: calculateSmoothness(),
+// markOccludedPoints(), extractFeatures()). RawPoint is the node's PointXYZIRT (32 bytes, imageProjection.cpp:4-15); the
+// outputs are the arrays of lio_sam/cloud_info plus the three clouds the nodes publish.
+struct CloudInfoArrays {                              // msg/cloud_info.msg:4-8
+    std::vector<int32_t> startRingIndex, endRingIndex, pointColInd;
+    std::vector<float> pointRange;
+};
+struct ImuQueueView {                                 // the node's std::deque<sensor_msgs::Imu>, after imuConverter, as arrays
+    const double* stamp = nullptr; const double* orientation_xyzw = nullptr; const double* angular_velocity = nullptr; int n = 0;
+};
+class ScanFrontEnd {
+public:
+    explicit ScanFrontEnd(const b2_scan_params* p = nullptr) {
+        if (p) prm_ = *p; else b2_scan_default_params(&prm_);
+        check(b2_scan_create(&h_, &prm_), "b2_scan_create");
+        imuTime_.resize(2000); imuRotX_.resize(2000); imuRotY_.resize(2000); imuRotZ_.resize(2000);      // queueLength, imageProjection.cpp:45
+    }
+    ~ScanFrontEnd() { b2_scan_destroy(h_); }
+    ScanFrontEnd(const ScanFrontEnd&) = delete;
+    // imuDeskewInfo (:305-362): returns cloudInfo.imuAvailable; n_popped messages are to be popped from the node's queue
+    bool imuDeskewInfo(const ImuQueueView& q, double timeScanCur, double timeScanEnd, int& n_popped, float rpyInit[3]) {
+        int avail = 0;
+        check(b2_imu_deskew_info(q.stamp, q.orientation_xyzw, q.angular_velocity, q.n, timeScanCur, timeScanEnd, imuTime_.data(), imuRotX_.data(),
+                                 imuRotY_.data(), imuRotZ_.data(), static_cast<int>(imuTime_.size()), &nImu_, &n_popped, &avail, rpyInit), "imuDeskewInfo");
+        return avail != 0;
+    }
+    // projectPointCloud + cloudExtraction (:521-598): laserCloudIn -> extractedCloud + cloud_info arrays. deskewFlag as :491.
+    template <typename RawPoint>
+    void projectPointCloud(const pcl::PointCloud<RawPoint>& laserCloudIn, double timeScanCur, int deskewFlag,
+                           pcl::PointCloud<pcl::PointXYZI>& extractedCloud, CloudInfoArrays& info) {
+        static_assert(sizeof(RawPoint) == 32, "PointXYZIRT is 32 bytes: x y z _ intensity ring time _");
+        const size_t cells = static_cast<size_t>(prm_.n_scan) * prm_.horizon_scan;
+        xyzi_.resize(cells * 4);
+        info.pointColInd.resize(cells); info.pointRange.resize(cells);
+        info.startRingIndex.resize(prm_.n_scan); info.endRingIndex.resize(prm_.n_scan);
+        size_t m = 0;
+        check(b2_scan_project(h_, laserCloudIn.points.data(), laserCloudIn.size(), imuTime_.data(), imuRotX_.data(), imuRotY_.data(), imuRotZ_.data(),
+                              nImu_, timeScanCur, deskewFlag, &m, xyzi_.data(), info.pointColInd.data(), info.pointRange.data(),
+                              info.startRingIndex.data(), info.endRingIndex.data(), nullptr, nullptr), "projectPointCloud");
+        info.pointColInd.resize(m); info.pointRange.resize(m);
+        unpack(xyzi_.data(), m, extractedCloud);
+    }
+    // calculateSmoothness + markOccludedPoints + extractFeatures (:81-238) on the projection the handle holds
+    void extractFeatures(pcl::PointCloud<pcl::PointXYZI>& cornerCloud, pcl::PointCloud<pcl::PointXYZI>& surfaceCloud) {
+        const size_t cells = static_cast<size_t>(prm_.n_scan) * prm_.horizon_scan;
+        std::vector<float> c(static_cast<size_t>(prm_.n_scan) * 120 * 4), s(cells * 4);
+        std::vector<int32_t> ci(static_cast<size_t>(prm_.n_scan) * 120);
+        size_t nc = 0, ns = 0;
+        check(b2_scan_extract_features(h_, &nc, c.data(), ci.data(), &ns, s.data(), nullptr, nullptr, nullptr), "extractFeatures");
+        unpack(c.data(), nc, cornerCloud); unpack(s.data(), ns, surfaceCloud);
+    }
+    b2_scan_t handle() const { return h_; }           // for b2_s2m_set_scan_from_front_end when the three stages share a process
+private:
+    static void unpack(const float* xyzi, size_t n, pcl::PointCloud<pcl::PointXYZI>& out) {
+        out.points.resize(n); out.width = static_cast<uint32_t>(n); out.height = 1; out.is_dense = true;
+        for (size_t i = 0; i < n; i++) { auto& p = out.points[i]; p.x = xyzi[4 * i]; p.y = xyzi[4 * i + 1]; p.z = xyzi[4 * i + 2]; p.intensity = xyzi[4 * i + 3]; }
+    }
+    b2_scan_params prm_{};
+    b2_scan_t h_ = nullptr;
+    std::vector<double> imuTime_, imuRotX_, imuRotY_, imuRotZ_;
+    int nImu_ = 0;
+    std::vector<float> xyzi_;
 };
 
 // replaces pcl::NormalDistributionsTransform<PointSource, PointTarget> (multi_lidar_calibrator.cpp:35-72)
