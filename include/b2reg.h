@@ -276,6 +276,11 @@ int b2_comm_create(b2_comm_t* out, const unsigned char id[128], int rank, int wo
 int b2_comm_destroy(b2_comm_t c);
 int b2_comm_rank(b2_comm_t c, int* rank, int* world);
 int b2_comm_allreduce_f64(b2_comm_t c, double* values, size_t n);     /* host values, summed over ranks in place */
+/* Sharded set-up of a large registration (config C5; every rank holds the same host cloud, as the ranks of the reference's
+ * batch scheduler would, multi_lidar_calibrator.py:202-219): upload 1/world of the rows per rank + all-gather over NVLink;
+ * normals of 1/world of the points per rank + all-gather (bit-identical to b2_cloud_estimate_normals). */
+int b2_cloud_set_points_sharded(b2_cloud_t c, const double* xyz, size_t n, b2_comm_t comm);
+int b2_cloud_estimate_normals_sharded(b2_cloud_t c, int knn, b2_comm_t comm);
 
 /* ------------------------------------------------------------------------------------------------
  * Generalized ICP — replaces o3d.pipelines.registration.registration_generalized_icp(source, target, max_corr, init,
@@ -300,6 +305,9 @@ int  b2_gicp_destroy(b2_gicp_t h);
 int  b2_gicp_set_params(b2_gicp_t h, const b2_gicp_params* params);
 int  b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target);    /* builds the target index; the cloud may be destroyed afterwards */
 int  b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source);
+/* sharded registration: index only rows [begin, end) of the source on this rank (all of them are processed here; the sums are
+ * all-reduced over the communicator of b2_gicp_set_shard, the fitness refers to the whole cloud) */
+int  b2_gicp_set_source_slice(b2_gicp_t h, b2_cloud_t source, size_t begin, size_t end);
 /* Source sharding for one registration spread over `world` GPUs: the (cell-sorted) source is dealt to the ranks in
  * blocks of 4096 consecutive points, round-robin (block b belongs to rank b mod world), so every rank sees the same
  * mix of easy and hard regions; the 30 sums are all-reduced over `comm` every iteration and every rank solves the same

@@ -77,10 +77,10 @@ SYMBOLS = [
     "b2_s2m_set_scan_from_front_end", "b2_s2m_get_scan",
     "b2_cloud_create", "b2_cloud_destroy", "b2_cloud_set_points", "b2_cloud_set_points_f32", "b2_cloud_size",
     "b2_cloud_get_points", "b2_cloud_get_normals", "b2_cloud_set_normals", "b2_cloud_voxel_down_sample",
-    "b2_cloud_estimate_normals", "b2_cloud_transform", "b2_cloud_last_gpu_ms",
+    "b2_cloud_estimate_normals", "b2_cloud_transform", "b2_cloud_last_gpu_ms", "b2_cloud_set_points_sharded", "b2_cloud_estimate_normals_sharded",
     "b2_comm_unique_id", "b2_comm_create", "b2_comm_destroy", "b2_comm_rank", "b2_comm_allreduce_f64",
     "b2_gicp_default_params", "b2_gicp_create", "b2_gicp_destroy", "b2_gicp_set_params", "b2_gicp_set_target",
-    "b2_gicp_set_source", "b2_gicp_set_shard", "b2_gicp_linearize", "b2_gicp_align", "b2_gicp_get_history",
+    "b2_gicp_set_source", "b2_gicp_set_source_slice", "b2_gicp_set_shard", "b2_gicp_linearize", "b2_gicp_align", "b2_gicp_get_history",
     "b2_gicp_last_gpu_ms", "b2_gicp_index_info", "b2_gicp_get_evaluation_ms",
     "b2_localmap_create", "b2_localmap_destroy", "b2_localmap_add_keyframe", "b2_localmap_num_keyframes", "b2_localmap_set_pose",
     "b2_localmap_clear_cache", "b2_localmap_extract", "b2_localmap_get", "b2_localmap_last_gpu_ms", "b2_s2m_set_map_from_localmap",
@@ -188,6 +188,8 @@ def lib():
     L.b2_cloud_set_normals.argtypes = [vp, vp]
     L.b2_cloud_voxel_down_sample.argtypes = [vp, dbl, C.POINTER(vp), vp]
     L.b2_cloud_estimate_normals.argtypes = [vp, i32]
+    L.b2_cloud_estimate_normals_sharded.argtypes = [vp, i32, vp]
+    L.b2_cloud_set_points_sharded.argtypes = [vp, vp, sz, vp]
     L.b2_cloud_transform.argtypes = [vp, vp]
     L.b2_cloud_last_gpu_ms.argtypes = [vp, pf]
     L.b2_comm_unique_id.argtypes = [vp]
@@ -202,6 +204,7 @@ def lib():
     L.b2_gicp_set_params.argtypes = [vp, C.POINTER(GicpParams)]
     L.b2_gicp_set_target.argtypes = [vp, vp]
     L.b2_gicp_set_source.argtypes = [vp, vp]
+    L.b2_gicp_set_source_slice.argtypes = [vp, vp, sz, sz]
     L.b2_gicp_set_shard.argtypes = [vp, i32, i32, vp]
     L.b2_gicp_linearize.argtypes = [vp, vp, vp, vp]
     L.b2_gicp_align.argtypes = [vp, vp, vp, pd, pd, pi, pi]

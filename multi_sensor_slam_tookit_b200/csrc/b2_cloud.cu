@@ -9,6 +9,7 @@
 // (z, y, x) voxel order, sums inside a voxel run in ascending input index, neighbour ties fall to the smaller index,
 // the normal's sign makes the first non-zero of (z, y, x) positive.
 #include "b2_cloud.cuh"
+#include "b2_comm.cuh"
 #include "b2_bvh.cuh"
 #include <cmath>
 #include <algorithm>
@@ -478,15 +479,17 @@ __device__ __forceinline__ double box_box_dist2(const double* __restrict__ b, co
     return dx * dx + dy * dy + dz * dz;
 }
 
-__global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, double* __restrict__ nrm) {
+// leaf_begin / leaf_end: the leaves (32 consecutive points of the Morton order) this launch serves; morton_out: write normal i of
+// the Morton order to nrm[3 i] instead of nrm[3 * original index] (the sharded set-up all-gathers contiguous leaf ranges).
+__global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, double* __restrict__ nrm, uint32_t leaf_begin, uint32_t leaf_end, int morton_out) {
     __shared__ double s_d[NRM_WARPS][NRM_MAXK][32];
     __shared__ uint32_t s_p[NRM_WARPS][NRM_MAXK][32];
     __shared__ double s_cx[NRM_WARPS][32], s_cy[NRM_WARPS][32], s_cz[NRM_WARPS][32];
     __shared__ int s_ci[NRM_WARPS][32];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t leaf0 = blockIdx.x * NRM_WARPS + warp;
-    if (leaf0 >= T.count[0]) return;
+    const uint32_t leaf0 = leaf_begin + blockIdx.x * NRM_WARPS + warp;
+    if (leaf0 >= leaf_end) return;
     const uint32_t me = leaf0 * 32u + lane;
     const bool valid = me < T.n;
     double qx = 0, qy = 0, qz = 0; long long mid = -1;
@@ -622,8 +625,17 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, dou
         if (nn == 0.0) { nv[0] = 0; nv[1] = 0; nv[2] = 1; }
         if (nv[2] < 0 || (nv[2] == 0 && (nv[1] < 0 || (nv[1] == 0 && nv[0] < 0)))) { nv[0] = -nv[0]; nv[1] = -nv[1]; nv[2] = -nv[2]; }
     }
-    double* o = &nrm[3 * (size_t)mid];
+    double* o = &nrm[3 * (size_t)(morton_out ? (long long)me : mid)];
     o[0] = nv[0]; o[1] = nv[1]; o[2] = nv[2];
+}
+
+// normals gathered in Morton order -> the cloud's own order
+__global__ void __launch_bounds__(256) k_normals_unsort(const P4d* __restrict__ pts, uint32_t n, const double* __restrict__ nrm_m, double* __restrict__ nrm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y, z; long long id;
+    load_p4d(&pts[i], x, y, z, id);
+    nrm[3 * (size_t)id] = nrm_m[3 * (size_t)i]; nrm[3 * (size_t)id + 1] = nrm_m[3 * (size_t)i + 1]; nrm[3 * (size_t)id + 2] = nrm_m[3 * (size_t)i + 2];
 }
 
 __global__ void __launch_bounds__(256) k_fill_normals(double* __restrict__ nrm, uint32_t n) {
@@ -695,7 +707,7 @@ int BvhIndex::build(const double* xyz, size_t n, DevBuf& work, cudaStream_t s) {
     return B2_OK;
 }
 
-int estimate_normals_knn(b2_cloud_s* c, int knn) {
+int estimate_normals_knn(b2_cloud_s* c, int knn, b2_comm_s* comm) {
     if (knn < 1 || knn > NRM_MAXK) { set_error("estimate_normals: knn must be in [1, %d]", NRM_MAXK); return B2_ERR_ARG; }
     cudaStream_t s = c->stream;
     c->has_normals = false;
@@ -706,12 +718,31 @@ int estimate_normals_knn(b2_cloud_s* c, int knn) {
     BvhIndex bvh;
     int st = bvh.build(c->xyz.as<double>(), n, c->work, s);
     cudaError_t e = cudaSuccess;
-    if (st == B2_OK && bvh.dev.n) {
-        k_normals<<<(bvh.dev.count[0] + NRM_WARPS - 1) / NRM_WARPS, NRM_WARPS * 32, 0, s>>>(bvh.dev, knn, c->nrm.as<double>()); count_launch();
+    DevBuf gathered;
+    if (st == B2_OK && bvh.dev.n && comm && comm->world > 1) {
+        // Sharded set-up (config C5): every rank holds the whole cloud and the same BVH (the neighbourhood of a point may reach
+        // anywhere), but serves only its contiguous range of leaves; the ranges are exchanged with one all-gather over NVLink
+        // (24 B per point) and put back into the cloud's order. The 30-NN search is ~95 % of estimate_normals.
+        const uint32_t L = bvh.dev.count[0];
+        const uint32_t per = (L + (uint32_t)comm->world - 1) / (uint32_t)comm->world;
+        const uint32_t lb = std::min(L, per * (uint32_t)comm->rank), le = std::min(L, lb + per);
+        st = gathered.reserve((size_t)per * comm->world * 32 * 24);
+        double* gm = gathered.as<double>();
+        if (st == B2_OK && le > lb) {
+            k_normals<<<(le - lb + NRM_WARPS - 1) / NRM_WARPS, NRM_WARPS * 32, 0, s>>>(bvh.dev, knn, gm, lb, le, 1); count_launch();
+            e = cudaGetLastError();
+        }
+        if (st == B2_OK && e == cudaSuccess) st = comm_allgather_f64(comm, gm + (size_t)per * comm->rank * 96, gm, (size_t)per * 96, s);
+        if (st == B2_OK && e == cudaSuccess) {
+            k_normals_unsort<<<(bvh.dev.n + 255) / 256, 256, 0, s>>>(bvh.dev.pts, bvh.dev.n, gm, c->nrm.as<double>()); count_launch();
+            e = cudaGetLastError();
+        }
+    } else if (st == B2_OK && bvh.dev.n) {
+        k_normals<<<(bvh.dev.count[0] + NRM_WARPS - 1) / NRM_WARPS, NRM_WARPS * 32, 0, s>>>(bvh.dev, knn, c->nrm.as<double>(), 0u, bvh.dev.count[0], 0); count_launch();
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    bvh.release();
+    bvh.release(); gathered.release();
     if (st != B2_OK) return st;
     if (e != cudaSuccess) { set_error("estimate_normals: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
     c->has_normals = true;
@@ -853,11 +884,45 @@ int b2_cloud_estimate_normals(b2_cloud_t c, int knn) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c->stream);
-    const int st = estimate_normals_knn(c, knn);
+    const int st = estimate_normals_knn(c, knn, nullptr);
     cudaEventRecord(e1, c->stream); cudaEventSynchronize(e1);
     cudaEventElapsedTime(&c->last_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return st;
+}
+
+// The same with the work split over the ranks of `comm` (every rank calls it on an identical cloud): each rank estimates the
+// normals of 1/world of the points, one NCCL all-gather hands everybody all of them. Results are bit-identical to the
+// single-GPU call (same kernel, same BVH).
+int b2_cloud_estimate_normals_sharded(b2_cloud_t c, int knn, b2_comm_t comm) {
+    if (!c) return B2_ERR_ARG;
+    B2_CUDA(cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->stream);
+    const int st = estimate_normals_knn(c, knn, comm);
+    cudaEventRecord(e1, c->stream); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&c->last_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return st;
+}
+
+// b2_cloud_set_points when every rank of `comm` holds the same host array: each rank uploads 1/world of the rows over its own
+// PCIe link and the slices are all-gathered over NVLink (world x less host-to-device traffic per rank).
+int b2_cloud_set_points_sharded(b2_cloud_t c, const double* xyz, size_t n, b2_comm_t comm) {
+    if (!comm || comm->world <= 1) return b2_cloud_set_points(c, xyz, n);
+    if (!c || (n && !xyz)) return B2_ERR_ARG;
+    B2_CUDA(cudaSetDevice(c->device));
+    c->n = n; c->has_normals = false;
+    if (!n) return B2_OK;
+    const size_t per = (n + comm->world - 1) / comm->world;
+    B2_CHECK(c->xyz.reserve(per * comm->world * 24));
+    const size_t b = std::min(n, per * (size_t)comm->rank), e = std::min(n, b + per);
+    double* d = c->xyz.as<double>();
+    if (e > b) B2_CUDA(cudaMemcpyAsync(d + 3 * b, xyz + 3 * b, (e - b) * 24, cudaMemcpyHostToDevice, c->stream));
+    B2_CHECK(comm_allgather_f64(comm, d + 3 * per * comm->rank, d, 3 * per, c->stream));
+    B2_CUDA(cudaStreamSynchronize(c->stream));
+    return B2_OK;
 }
 
 int b2_cloud_transform(b2_cloud_t c, const double T[16]) {

@@ -4,6 +4,7 @@
 // Points stay in HBM between those calls; nothing goes back to the host unless the caller asks for it.
 #pragma once
 #include "b2_common.cuh"
+#include "b2_comm.cuh"
 #include "b2_gridd.cuh"
 
 struct b2_cloud_s {
@@ -22,5 +23,5 @@ namespace b2 {
 // min/max of n device points (3 doubles each) -> host mn[3], mx[3]; returns B2_OK; empty/non-finite clouds give mn > mx
 int bbox_f64(const double* d_xyz, size_t n, DevBuf& scratch, cudaStream_t s, double mn[3], double mx[3]);
 // cumulants -> covariance -> eigenvector of the smallest eigenvalue, as Open3D's estimate_normals does per point
-int estimate_normals_knn(b2_cloud_s* c, int knn);
+int estimate_normals_knn(b2_cloud_s* c, int knn, ::b2_comm_s* comm);
 }  // namespace b2

@@ -12,6 +12,7 @@ typedef int (*fn_get_unique_id)(NcclId*);
 typedef int (*fn_comm_init_rank)(void**, int, NcclId, int);
 typedef int (*fn_comm_destroy)(void*);
 typedef int (*fn_all_reduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_all_gather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef const char* (*fn_error_string)(int);
 
 struct NcclApi {
@@ -20,6 +21,7 @@ struct NcclApi {
     fn_comm_init_rank comm_init_rank = nullptr;
     fn_comm_destroy comm_destroy = nullptr;
     fn_all_reduce all_reduce = nullptr;
+    fn_all_gather all_gather = nullptr;
     fn_error_string error_string = nullptr;
     bool ok = false;
 };
@@ -39,8 +41,9 @@ static void load_nccl() {
     g_nccl.comm_init_rank = (fn_comm_init_rank)dlsym(g_nccl.handle, "ncclCommInitRank");
     g_nccl.comm_destroy = (fn_comm_destroy)dlsym(g_nccl.handle, "ncclCommDestroy");
     g_nccl.all_reduce = (fn_all_reduce)dlsym(g_nccl.handle, "ncclAllReduce");
+    g_nccl.all_gather = (fn_all_gather)dlsym(g_nccl.handle, "ncclAllGather");
     g_nccl.error_string = (fn_error_string)dlsym(g_nccl.handle, "ncclGetErrorString");
-    g_nccl.ok = g_nccl.get_unique_id && g_nccl.comm_init_rank && g_nccl.comm_destroy && g_nccl.all_reduce && g_nccl.error_string;
+    g_nccl.ok = g_nccl.get_unique_id && g_nccl.comm_init_rank && g_nccl.comm_destroy && g_nccl.all_reduce && g_nccl.all_gather && g_nccl.error_string;
 }
 
 static int nccl_api(NcclApi** out) {
@@ -60,6 +63,14 @@ int comm_allreduce_sum_f64(b2_comm_s* c, const double* d_send, double* d_recv, s
     NcclApi* api;
     B2_CHECK(nccl_api(&api));
     B2_NCCL(api, api->all_reduce(d_send, d_recv, n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, s));
+    return B2_OK;
+}
+
+// all-gather of `count` doubles per rank into d_recv (rank r's block at d_recv + r * count); in place when d_send is that block
+int comm_allgather_f64(b2_comm_s* c, const double* d_send, double* d_recv, size_t count, cudaStream_t s) {
+    NcclApi* api;
+    B2_CHECK(nccl_api(&api));
+    B2_NCCL(api, api->all_gather(d_send, d_recv, count, /*ncclFloat64*/ 8, c->comm, s));
     return B2_OK;
 }
 

@@ -13,4 +13,6 @@ struct b2_comm_s {
 namespace b2 {
 // sum-all-reduce of n doubles, in place allowed, on stream s
 int comm_allreduce_sum_f64(b2_comm_s* c, const double* d_send, double* d_recv, size_t n, cudaStream_t s);
+// all-gather of `count` doubles per rank (rank r's block lands at d_recv + r * count; in place when d_send is that block)
+int comm_allgather_f64(b2_comm_s* c, const double* d_send, double* d_recv, size_t count, cudaStream_t s);
 }

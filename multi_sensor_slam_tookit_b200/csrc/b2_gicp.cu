@@ -275,6 +275,7 @@ struct b2_gicp_s {
     size_t n_tgt = 0, n_src = 0;
     uint32_t src_valid = 0;
     bool have_tgt = false, have_src = false;
+    bool src_slice = false;          // src_grid holds only this rank's rows of the source (b2_gicp_set_source_slice)
     int rank = 0, world = 1;
     b2_comm_s* comm = nullptr;
     int grid_blocks = 1;
@@ -315,8 +316,9 @@ static void gicp_fill_args(b2_gicp_s* h, GicpArgs& a, int mode, int32_t* corr) {
     a.src = h->src_grid.dev.pts;
     a.src_m = h->src_m.as<double>();
     a.n_src = h->src_valid;
-    a.rank = h->rank; a.world = h->world;
-    a.n_local_chunks = gicp_local_chunks(h->src_valid, h->rank, h->world);
+    // a sliced source is all local: the deal over the ranks was made when the slice was taken
+    a.rank = h->src_slice ? 0 : h->rank; a.world = h->src_slice ? 1 : h->world;
+    a.n_local_chunks = gicp_local_chunks(h->src_valid, a.rank, a.world);
     a.radius2 = h->prm.max_correspondence_distance * h->prm.max_correspondence_distance;
     a.a = 1.0 - h->prm.epsilon;
     a.partials = h->partials.as<double>();
@@ -406,18 +408,20 @@ int b2_gicp_set_params(b2_gicp_t h, const b2_gicp_params* p) {
     return B2_OK;
 }
 
-static int gicp_set_cloud(b2_gicp_s* h, b2_cloud_s* c, GridD& grid, DevBuf& m, double ppc, uint32_t* n_valid) {
+static int gicp_set_cloud(b2_gicp_s* h, b2_cloud_s* c, GridD& grid, DevBuf& m, double ppc, uint32_t* n_valid, size_t begin = 0, size_t end = (size_t)-1) {
+    end = std::min(end, c->n); begin = std::min(begin, end);
     if (!c->has_normals) {
         set_error("gicp: the cloud has no normals; call b2_cloud_estimate_normals first (Calibration.py:327-328 does)");
         return B2_ERR_STATE;
     }
     B2_CUDA(cudaSetDevice(h->device));
     B2_CUDA(cudaStreamSynchronize(c->stream));
-    B2_CHECK(grid.build(c->xyz.as<double>(), c->n, 0.0, ppc, h->stream));
+    // [begin, end): the rows this handle indexes (a rank's slice of a sharded source); grid indices are relative to `begin`
+    B2_CHECK(grid.build(c->xyz.as<double>() + 3 * begin, end - begin, 0.0, ppc, h->stream));
     B2_CHECK(gicp_valid_count(grid, h->stream, n_valid));
-    B2_CHECK(m.reserve(std::max<size_t>(c->n, 1) * 24));
+    B2_CHECK(m.reserve(std::max<size_t>(end - begin, 1) * 24));
     if (*n_valid) {
-        k_gicp_eff_normals<<<(*n_valid + 255) / 256, 256, 0, h->stream>>>(grid.dev.pts, c->nrm.as<double>(), *n_valid, m.as<double>()); count_launch();
+        k_gicp_eff_normals<<<(*n_valid + 255) / 256, 256, 0, h->stream>>>(grid.dev.pts, c->nrm.as<double>() + 3 * begin, *n_valid, m.as<double>()); count_launch();
         B2_CUDA(cudaGetLastError());
     }
     B2_CUDA(cudaStreamSynchronize(h->stream));
@@ -455,6 +459,24 @@ int b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source) {
     B2_CHECK(gicp_set_cloud(h, source, h->src_grid, h->src_m, sppc, &nv));
     h->n_src = source->n;
     h->src_valid = nv;
+    h->src_slice = false;
+    h->have_src = true;
+    return B2_OK;
+}
+
+// Sharded registration with a sharded set-up: this rank indexes only rows [begin, end) of the source (its own 1/world of the
+// cloud: the sort of the source grid, the largest part of set_source, shrinks with the number of ranks) and processes all of
+// them; the 30 sums are all-reduced as before and the fitness is taken over the whole cloud. For clouds in random order (the
+// fused map of config C5) row slices are as well balanced as the block-cyclic deal of the cell-sorted source.
+int b2_gicp_set_source_slice(b2_gicp_t h, b2_cloud_t source, size_t begin, size_t end) {
+    if (!h || !source || begin > end) return B2_ERR_ARG;
+    h->have_src = false;
+    uint32_t nv = 0;
+    static const double sppc = [] { const char* e = getenv("B2_GICP_TARGET_PPC"); double v = e ? atof(e) : 2.0; return v > 0 ? v : 2.0; }();
+    B2_CHECK(gicp_set_cloud(h, source, h->src_grid, h->src_m, sppc, &nv, begin, end));
+    h->n_src = source->n;                      // fitness = correspondences / all source points
+    h->src_valid = nv;
+    h->src_slice = true;
     h->have_src = true;
     return B2_OK;
 }

@@ -97,6 +97,20 @@ class PointCloud:
         pc = PointCloud(_handle=out)
         return (pc, rank) if return_voxel_rank else pc
 
+    @classmethod
+    def from_host_sharded(cls, points, comm):
+        """Every rank passes the same (n, 3) float64 array; each uploads 1/world of it and the slices are all-gathered."""
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        if pts.ndim != 2 or pts.shape[1] != 3:
+            raise ValueError("points must be (n, 3)")
+        self = cls()
+        capi.check(capi.lib().b2_cloud_set_points_sharded(self._h, capi.ptr(pts), pts.shape[0], comm._h if comm is not None else None))
+        return self
+
+    def estimate_normals_sharded(self, comm, knn=30):
+        """estimate_normals() with the 30-NN work split over the ranks of comm (identical clouds on every rank)."""
+        capi.check(capi.lib().b2_cloud_estimate_normals_sharded(self._h, int(knn), comm._h if comm is not None else None))
+
     def estimate_normals(self, knn=30):
         """Calibration.py:327-328 (Open3D default search parameter: KDTreeSearchParamKNN(knn=30))."""
         capi.check(capi.lib().b2_cloud_estimate_normals(self._h, int(knn)))
@@ -191,6 +205,13 @@ def shard_size(n, rank, world, block=SHARD_BLOCK_POINTS):
     return sum(e - b for b, e in shard_blocks(n, rank, world, block))
 
 
+def row_slice(n, rank, world):
+    """Rows [begin, end) of an n-point cloud that rank owns when the source is sliced by rows."""
+    per = (n + world - 1) // world
+    b = min(n, per * rank)
+    return b, min(n, b + per)
+
+
 def pair_owner(pair_index, world):
     """Round-robin owner of an independent calibration pair (multi_lidar_calibrator.py:202-219)."""
     return pair_index % world
@@ -229,6 +250,11 @@ class GeneralizedICP:
 
     def setInputSource(self, cloud):
         capi.check(capi.lib().b2_gicp_set_source(self._h, cloud._h))
+        self._n_src = len(cloud)
+
+    def setInputSourceSlice(self, cloud, begin, end):
+        """Index rows [begin, end) of the source only (this rank's slice of a sharded registration); see row_slice()."""
+        capi.check(capi.lib().b2_gicp_set_source_slice(self._h, cloud._h, int(begin), int(end)))
         self._n_src = len(cloud)
 
     def setShard(self, comm):

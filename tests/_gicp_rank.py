@@ -29,7 +29,21 @@ def main():
     g.setInputTarget(t); g.setInputSource(s)
     g.setShard(comm)
     r = g.align(d["init"])
-    json.dump({"T": r.transformation.tolist(), "iterations": r.iterations, "fitness": r.fitness, "rmse": r.inlier_rmse},
+    # the sharded set-up of config C5: slice upload + all-gather, sharded normals + all-gather, source grid over this rank's rows
+    s2 = gicp.PointCloud.from_host_sharded(d["sp"], comm); t2 = gicp.PointCloud.from_host_sharded(d["tp"], comm)
+    pts_equal = bool(np.array_equal(s2.points, d["sp"]) and np.array_equal(t2.points, d["tp"]))
+    s2.estimate_normals_sharded(comm); t2.estimate_normals_sharded(comm)
+    s1 = gicp.PointCloud(d["sp"]); s1.estimate_normals()
+    nrm_equal = bool(np.array_equal(s2.normals, s1.normals))
+    g2 = gicp.GeneralizedICP(1.0, 0.005)
+    g2.setInputTarget(t2)
+    b, e = gicp.row_slice(len(d["sp"]), rank, world)
+    g2.setInputSourceSlice(s2, b, e)
+    g2.setShard(comm)
+    r2 = g2.align(d["init"], want_correspondences=False)
+    json.dump({"T": r.transformation.tolist(), "iterations": r.iterations, "fitness": r.fitness, "rmse": r.inlier_rmse,
+               "pts_equal": pts_equal, "nrm_equal": nrm_equal, "T2": r2.transformation.tolist(), "iterations2": r2.iterations,
+               "fitness2": r2.fitness, "slice": [b, e]},
               open(os.path.join(work, f"rank{rank}.json"), "w"))
     dist.barrier()
     dist.destroy_process_group()

@@ -230,3 +230,13 @@ def test_two_gpu_sharded_align(pair, gicp, tmp_path):
     ref = single.align(G.perturbed(pair["truth"]))
     assert r0["iterations"] == ref.iterations and r0["fitness"] == ref.fitness
     assert np.abs(np.array(r0["T"]) - ref.transformation).max() <= 1e-9
+    # sharded set-up: all-gathered points and normals bit-identical to the single-GPU calls on every rank, and the registration
+    # on row slices of the source (normals from estimate_normals on both sides, so compared with a single-GPU run of the same)
+    assert r0["pts_equal"] and r1["pts_equal"] and r0["nrm_equal"] and r1["nrm_equal"]
+    assert r0["T2"] == r1["T2"] and r0["slice"][1] == r1["slice"][0]
+    s1 = gicp.PointCloud(pair["sp"]); t1 = gicp.PointCloud(pair["tp"])
+    s1.estimate_normals(); t1.estimate_normals()
+    one = gicp.GeneralizedICP(1.0, pair["eps"]); one.setInputTarget(t1); one.setInputSource(s1)
+    ref2 = one.align(G.perturbed(pair["truth"]))
+    assert r0["iterations2"] == ref2.iterations and abs(r0["fitness2"] - ref2.fitness) <= 1e-12
+    assert np.abs(np.array(r0["T2"]) - ref2.transformation).max() <= 1e-9

@@ -168,27 +168,42 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
     src, tgt, T_true = c5_clouds_torch(n_points, device)
     t_gen = time.perf_counter() - t0
     t0 = t_e2e = time.perf_counter()
-    sp, tp = gicp.PointCloud(src), gicp.PointCloud(tgt)
+    if comm is not None:
+        # sharded set-up: 1/world of each cloud over this rank's PCIe link + all-gather, 1/world of the 30-NN normals + all-gather,
+        # the source grid over this rank's rows only (the target and its two grids are replicated)
+        sp, tp = gicp.PointCloud.from_host_sharded(src, comm), gicp.PointCloud.from_host_sharded(tgt, comm)
+    else:
+        sp, tp = gicp.PointCloud(src), gicp.PointCloud(tgt)
+    n_src = len(src)
     del src, tgt
     t_up = time.perf_counter() - t0
-    sp.estimate_normals(); n_ms = sp.lastGpuMs()
-    tp.estimate_normals(); n_ms += tp.lastGpuMs()
+    if comm is not None:
+        sp.estimate_normals_sharded(comm); n_ms = sp.lastGpuMs()
+        tp.estimate_normals_sharded(comm); n_ms += tp.lastGpuMs()
+    else:
+        sp.estimate_normals(); n_ms = sp.lastGpuMs()
+        tp.estimate_normals(); n_ms += tp.lastGpuMs()
     g = gicp.GeneralizedICP(1.0, 0.005, -1.0, -1.0, iterations)         # negative thresholds: never "converged", fixed iterations
     t0 = time.perf_counter()
-    g.setInputTarget(tp); g.setInputSource(sp)
+    g.setInputTarget(tp)
+    if comm is not None:
+        b, e = gicp.row_slice(n_src, rank, world)
+        g.setInputSourceSlice(sp, b, e)
+    else:
+        g.setInputSource(sp)
     t_index = time.perf_counter() - t0
     if comm is not None:
         g.setShard(comm)
     info = g.indexInfo()
-    best = None
+    runs = []
     e2e_s = None
     for _ in range(repeats + 1):
         res = g.align(np.eye(4), want_correspondences=False)
         if e2e_s is None:
             e2e_s = time.perf_counter() - t_e2e            # upload + normals + index builds + the first align
-        if best is None or res.gpu_ms < best.gpu_ms:
-            best = res
-    res = best
+        runs.append(res)
+    runs.sort(key=lambda r: r.gpu_ms)
+    res = runs[len(runs) // 2]                            # median of the aligns (3 by default)
     dT = np.linalg.inv(T_true) @ res.transformation
     return dict(points=int(n_points), iterations=int(res.iterations), evaluations=int(res.iterations + 1), gpu_ms=float(res.gpu_ms),
                 launches=int(res.gpu_launches), fitness=float(res.fitness), inlier_rmse=float(res.inlier_rmse),
