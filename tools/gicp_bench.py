@@ -167,6 +167,11 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
     t0 = time.perf_counter()
     src, tgt, T_true = c5_clouds_torch(n_points, device)
     t_gen = time.perf_counter() - t0
+    if comm is not None:
+        # NCCL sets its channels up at the first collective of each kind on a communicator (hundreds of ms): not part of the step
+        comm.allreduce(np.zeros(4))
+        warm = gicp.PointCloud.from_host_sharded(np.zeros((4096, 3)) + np.arange(4096)[:, None], comm)
+        del warm
     t0 = t_e2e = time.perf_counter()
     if comm is not None:
         # sharded set-up: 1/world of each cloud over this rank's PCIe link + all-gather, 1/world of the 30-NN normals + all-gather,
