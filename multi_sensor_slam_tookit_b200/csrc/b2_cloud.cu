@@ -801,6 +801,7 @@ int b2_cloud_destroy(b2_cloud_t c) {
 }
 
 int b2_cloud_set_points(b2_cloud_t c, const double* xyz, size_t n) {
+    B2_NVTX("b2_cloud_set_points");
     if (!c || (n && !xyz)) return B2_ERR_ARG;
     c->n = n; c->has_normals = false;
     if (!n) return B2_OK;
@@ -860,6 +861,7 @@ int b2_cloud_set_normals(b2_cloud_t c, const double* nrm) {
 }
 
 int b2_cloud_voxel_down_sample(b2_cloud_t c, double voxel_size, b2_cloud_t* out, int32_t* voxel_rank_of_point) {
+    B2_NVTX("b2_cloud_voxel_down_sample");
     if (!c || !out) return B2_ERR_ARG;
     *out = nullptr;
     if (!(voxel_size > 0.0)) { set_error("voxel_down_sample: voxel_size <= 0"); return B2_ERR_ARG; }
@@ -879,6 +881,7 @@ int b2_cloud_voxel_down_sample(b2_cloud_t c, double voxel_size, b2_cloud_t* out,
 }
 
 int b2_cloud_estimate_normals(b2_cloud_t c, int knn) {
+    B2_NVTX("b2_cloud_estimate_normals");
     if (!c) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
@@ -895,6 +898,7 @@ int b2_cloud_estimate_normals(b2_cloud_t c, int knn) {
 // normals of 1/world of the points, one NCCL all-gather hands everybody all of them. Results are bit-identical to the
 // single-GPU call (same kernel, same BVH).
 int b2_cloud_estimate_normals_sharded(b2_cloud_t c, int knn, b2_comm_t comm) {
+    B2_NVTX("b2_cloud_estimate_normals_sharded");
     if (!c) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
@@ -910,6 +914,7 @@ int b2_cloud_estimate_normals_sharded(b2_cloud_t c, int knn, b2_comm_t comm) {
 // b2_cloud_set_points when every rank of `comm` holds the same host array: each rank uploads 1/world of the rows over its own
 // PCIe link and the slices are all-gathered over NVLink (world x less host-to-device traffic per rank).
 int b2_cloud_set_points_sharded(b2_cloud_t c, const double* xyz, size_t n, b2_comm_t comm) {
+    B2_NVTX("b2_cloud_set_points_sharded");
     if (!comm || comm->world <= 1) return b2_cloud_set_points(c, xyz, n);
     if (!c || (n && !xyz)) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(c->device));

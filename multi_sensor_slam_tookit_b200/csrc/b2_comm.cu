@@ -127,7 +127,11 @@ int b2_comm_allreduce_f64(b2_comm_t c, double* values, size_t n) {
     double* d = nullptr;
     B2_CUDA(cudaMalloc(&d, n * 8));
     cudaStream_t s;
-    B2_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("b2_comm_allreduce_f64: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(d);
+        return B2_ERR_CUDA;
+    }
     int st = B2_OK;
     if (cudaMemcpyAsync(d, values, n * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) st = B2_ERR_CUDA;
     if (st == B2_OK) st = comm_allreduce_sum_f64(c, d, d, n, s);

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/b2reg.h"
 
 namespace b2 {
@@ -68,6 +69,27 @@ struct PinBuf {
 };
 
 int device_sm_count();
+
+// NVTX range per C-ABI call (header-only NVTX 3: a no-op function pointer unless a tool such as nsys / ncu --nvtx is attached)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+};
+#define B2_NVTX(name) b2::NvtxRange nvtx_range_(name)
+
+// Every handle records the device it was created on; its entry points (and its destroy, which may run on another host
+// thread, e.g. from a Python finaliser) make that device current for the duration of the call.
+struct DeviceScope {
+    int prev = -1;
+    explicit DeviceScope(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && dev >= 0) { if (cudaSetDevice(dev) == cudaSuccess) prev = cur; }
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+};
+inline int current_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); d = 0; } return d; }
 void count_launch(int n = 1);     // bookkeeping for b2_kernel_launch_count()
 
 // ---- scan / sort primitives (b2_sort.cu) -------------------------------------------------------

@@ -159,6 +159,7 @@ int b2_fusion_set_internal_bounds(b2_fusion_t h, int enabled, const double min_x
 }
 
 int b2_fusion_run(b2_fusion_t h, size_t* n_fused, size_t* n_out) {
+    B2_NVTX("b2_fusion_run");
     if (!h) return B2_ERR_ARG;
     cudaStream_t s = h->stream;
     cudaEventRecord(h->e0, s);

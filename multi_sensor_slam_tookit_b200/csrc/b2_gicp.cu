@@ -429,6 +429,7 @@ static int gicp_set_cloud(b2_gicp_s* h, b2_cloud_s* c, GridD& grid, DevBuf& m, d
 }
 
 int b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target) {
+    B2_NVTX("b2_gicp_set_target");
     if (!h || !target) return B2_ERR_ARG;
     h->have_tgt = false;
     uint32_t nv = 0;
@@ -452,6 +453,7 @@ int b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target) {
 }
 
 int b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source) {
+    B2_NVTX("b2_gicp_set_source");
     if (!h || !source) return B2_ERR_ARG;
     h->have_src = false;
     uint32_t nv = 0;
@@ -469,6 +471,7 @@ int b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source) {
 // them; the 30 sums are all-reduced as before and the fitness is taken over the whole cloud. For clouds in random order (the
 // fused map of config C5) row slices are as well balanced as the block-cyclic deal of the cell-sorted source.
 int b2_gicp_set_source_slice(b2_gicp_t h, b2_cloud_t source, size_t begin, size_t end) {
+    B2_NVTX("b2_gicp_set_source_slice");
     if (!h || !source || begin > end) return B2_ERR_ARG;
     h->have_src = false;
     uint32_t nv = 0;
@@ -489,6 +492,7 @@ int b2_gicp_set_shard(b2_gicp_t h, int rank, int world, b2_comm_t comm) {
 }
 
 int b2_gicp_linearize(b2_gicp_t h, const double T[16], double sums[30], int32_t* corr) {
+    B2_NVTX("b2_gicp_linearize");
     if (!h || !T || !sums) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(h->device));
     B2_CHECK(gicp_prepare(h));
@@ -513,6 +517,7 @@ int b2_gicp_linearize(b2_gicp_t h, const double T[16], double sums[30], int32_t*
 
 int b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* fitness, double* inlier_rmse,
                   int* iterations, int* converged) {
+    B2_NVTX("b2_gicp_align");
     if (!h || !init || !T_out) return B2_ERR_ARG;
     if (h->world > 1 && !h->comm) { set_error("gicp: align on a sharded source needs a communicator (b2_gicp_set_shard)"); return B2_ERR_STATE; }
     B2_CUDA(cudaSetDevice(h->device));

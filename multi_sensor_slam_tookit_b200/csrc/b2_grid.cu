@@ -617,6 +617,7 @@ struct b2_knn_s {
     b2::DevBuf q, oidx, od2;
     cudaStream_t stream = nullptr;
     float max_dist = 1.0f;
+    int device = b2::current_device();      // the device the handle was created on
     bool built = false;
 };
 
@@ -633,6 +634,7 @@ int b2_knn_create(b2_knn_t* out, float max_dist) {
 }
 
 int b2_knn_destroy(b2_knn_t h) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     h->grid.release(); h->q.release(); h->oidx.release(); h->od2.release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -641,6 +643,8 @@ int b2_knn_destroy(b2_knn_t h) {
 }
 
 int b2_knn_set_input_cloud(b2_knn_t h, const void* pts, size_t stride, size_t n) {
+    B2_NVTX("b2_knn_set_input_cloud");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || (n && !pts) || stride < 12 || (stride & 3)) { b2::set_error("b2_knn_set_input_cloud: bad argument"); return B2_ERR_ARG; }
     B2_CHECK(h->grid.build(pts, stride, n, h->max_dist, h->stream));
     B2_CUDA(cudaStreamSynchronize(h->stream));
@@ -649,6 +653,8 @@ int b2_knn_set_input_cloud(b2_knn_t h, const void* pts, size_t stride, size_t n)
 }
 
 int b2_knn_nearest_k_search(b2_knn_t h, const void* queries, size_t stride, size_t m, int k, int32_t* indices, float* sq_dists) {
+    B2_NVTX("b2_knn_nearest_k_search");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || (m && (!queries || !indices || !sq_dists)) || stride < 12 || (stride & 3) || k < 1 || k > 8) {
         b2::set_error("b2_knn_nearest_k_search: bad argument"); return B2_ERR_ARG;
     }

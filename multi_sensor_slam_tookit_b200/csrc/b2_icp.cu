@@ -340,6 +340,7 @@ int b2_icp_set_input_source(b2_icp_t h, const void* pts, size_t stride, size_t n
 
 /* icp.hpp computeTransformation; guess may be NULL (identity). out_cloud (optional): the source under the final transformation. */
 int b2_icp_align(b2_icp_t h, const float guess[16], void* out_cloud, size_t out_stride) {
+    B2_NVTX("b2_icp_align");
     if (!h) return B2_ERR_ARG;
     if (!h->have_src || !h->have_tgt) { set_error("b2_icp_align: setInputSource and setInputTarget first"); return B2_ERR_STATE; }
     B2_CUDA(cudaSetDevice(h->device));

@@ -78,6 +78,7 @@ struct LmKeyFrame {
 struct b2_localmap_s {
     cudaStream_t stream = nullptr;
     b2_voxel_t vox_corner = nullptr, vox_surf = nullptr;
+    int device = b2::current_device();      // the device the handle was created on
     std::vector<LmKeyFrame*> keys;
     size_t n_cached = 0;
     DevBuf raw, cat_corner, cat_surf, seg;
@@ -124,6 +125,7 @@ int b2_localmap_create(b2_localmap_t* out, float mapping_corner_leaf_size, float
 }
 
 int b2_localmap_destroy(b2_localmap_t h) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_OK;
     for (LmKeyFrame* k : h->keys) { k->corner.release(); k->surf.release(); k->t_corner.release(); k->t_surf.release(); delete k; }
     h->raw.release(); h->cat_corner.release(); h->cat_surf.release(); h->seg.release(); h->pin.release();
@@ -138,6 +140,8 @@ int b2_localmap_destroy(b2_localmap_t h) {
 
 int b2_localmap_add_keyframe(b2_localmap_t h, const void* corner, size_t corner_stride, size_t n_corner,
                              const void* surf, size_t surf_stride, size_t n_surf, const float pose6[6], int* key_index) {
+    B2_NVTX("b2_localmap_add_keyframe");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !pose6 || (n_corner && !corner) || (n_surf && !surf) || corner_stride < 16 || surf_stride < 16 || (corner_stride & 3) || (surf_stride & 3) ||
         n_corner > 0x7fffffffull || n_surf > 0x7fffffffull) { set_error("b2_localmap_add_keyframe: bad argument"); return B2_ERR_ARG; }
     LmKeyFrame* k = new LmKeyFrame();
@@ -152,6 +156,7 @@ int b2_localmap_add_keyframe(b2_localmap_t h, const void* corner, size_t corner_
 }
 
 int b2_localmap_num_keyframes(b2_localmap_t h, int* n) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !n) return B2_ERR_ARG;
     *n = (int)h->keys.size();
     return B2_OK;
@@ -159,12 +164,14 @@ int b2_localmap_num_keyframes(b2_localmap_t h, int* n) {
 
 /* correctPoses(): a corrected pose only matters once the cache is dropped, as in the reference (:1591) */
 int b2_localmap_set_pose(b2_localmap_t h, int key_index, const float pose6[6]) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !pose6 || key_index < 0 || key_index >= (int)h->keys.size()) return B2_ERR_ARG;
     memcpy(h->keys[key_index]->pose, pose6, 24);
     return B2_OK;
 }
 
 int b2_localmap_clear_cache(b2_localmap_t h) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     cudaStreamSynchronize(h->stream);
     lm_drop_cache(h);
@@ -173,6 +180,8 @@ int b2_localmap_clear_cache(b2_localmap_t h) {
 
 /* extractCloud(cloudToExtract) for the key frames the caller kept after the distance test of :905 */
 int b2_localmap_extract(b2_localmap_t h, const int32_t* key_indices, int n_keys, size_t* n_corner_ds, size_t* n_surf_ds) {
+    B2_NVTX("b2_localmap_extract");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || n_keys < 0 || (n_keys && !key_indices)) return B2_ERR_ARG;
     for (int i = 0; i < n_keys; i++)
         if (key_indices[i] < 0 || key_indices[i] >= (int)h->keys.size()) { set_error("b2_localmap_extract: key index %d out of range", key_indices[i]); return B2_ERR_ARG; }
@@ -237,6 +246,7 @@ int b2_localmap_extract(b2_localmap_t h, const int32_t* key_indices, int n_keys,
 
 /* which: 0 laserCloudCornerFromMap, 1 laserCloudSurfFromMap (before the filters), 2 / 3 the DS clouds after them */
 int b2_localmap_get(b2_localmap_t h, int which, void* out, size_t stride, size_t capacity, size_t* n) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || which < 0 || which > 3 || !n || stride < 16 || (stride & 3)) return B2_ERR_ARG;
     if (!h->extracted) { set_error("b2_localmap_get: extract first"); return B2_ERR_STATE; }
     const uint32_t cnt = which == 0 ? h->n_cat_corner : which == 1 ? h->n_cat_surf : which == 2 ? h->n_ds_corner : h->n_ds_surf;
@@ -258,12 +268,15 @@ int b2_localmap_get(b2_localmap_t h, int which, void* out, size_t stride, size_t
 
 /* kdtreeCornerFromMap->setInputCloud(laserCloudCornerFromMapDS); kdtreeSurfFromMap->setInputCloud(laserCloudSurfFromMapDS) (:1289-1290) */
 int b2_s2m_set_map_from_localmap(b2_s2m_t s2m, b2_localmap_t h) {
+    B2_NVTX("b2_s2m_set_map_from_localmap");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!s2m || !h) return B2_ERR_ARG;
     if (!h->extracted) { set_error("b2_s2m_set_map_from_localmap: extract first"); return B2_ERR_STATE; }
     return s2m_set_map_device(s2m, voxel_out_dev(h->vox_corner), h->n_ds_corner, voxel_out_dev(h->vox_surf), h->n_ds_surf);
 }
 
 int b2_localmap_last_gpu_ms(b2_localmap_t h, float* ms, size_t* n_cached) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     if (ms) *ms = h->last_ms;
     if (n_cached) *n_cached = h->n_cached;

@@ -870,6 +870,7 @@ int b2_ndt_set_resolution(b2_ndt_t h, float resolution) {
 int b2_ndt_set_maximum_iterations(b2_ndt_t h, int n) { if (!h) return B2_ERR_ARG; h->max_iterations = n; return B2_OK; }
 
 int b2_ndt_set_input_target(b2_ndt_t h, const void* xyz, size_t stride, size_t n) {
+    B2_NVTX("b2_ndt_set_input_target");
     if (!h) return B2_ERR_ARG;
     h->have_tgt = false; h->bvh_valid = false;
     B2_CHECK(ndt_set_cloud(h, xyz, stride, n, h->tgt_xyz));
@@ -883,6 +884,7 @@ int b2_ndt_set_input_target(b2_ndt_t h, const void* xyz, size_t stride, size_t n
 }
 
 int b2_ndt_set_input_source(b2_ndt_t h, const void* xyz, size_t stride, size_t n) {
+    B2_NVTX("b2_ndt_set_input_source");
     if (!h) return B2_ERR_ARG;
     h->have_src = false;
     B2_CHECK(ndt_set_cloud(h, xyz, stride, n, h->src_xyz));
@@ -933,6 +935,7 @@ int b2_ndt_derivatives(b2_ndt_t h, const double p[6], double* score, double grad
 
 /* ndt.hpp computeTransformation */
 int b2_ndt_align(b2_ndt_t h, const float guess[16], void* out_cloud, size_t out_stride) {
+    B2_NVTX("b2_ndt_align");
     if (!h || !guess) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(h->device));
     B2_CHECK(ndt_prepare(h));
@@ -997,6 +1000,7 @@ int b2_ndt_get_final_num_iteration(b2_ndt_t h, int* n) { if (!h || !n) return B2
 
 /* pcl::Registration::getFitnessScore(): mean squared distance from every transformed source point to its nearest target point */
 int b2_ndt_get_fitness_score(b2_ndt_t h, double* score) {
+    B2_NVTX("b2_ndt_get_fitness_score");
     if (!h || !score) return B2_ERR_ARG;
     if (!h->have_tgt || !h->have_src) return B2_ERR_STATE;
     B2_CUDA(cudaSetDevice(h->device));

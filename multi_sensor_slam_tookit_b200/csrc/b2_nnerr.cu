@@ -168,12 +168,14 @@ int b2_nnerr_set_source(b2_nnerr_t h, const void* pts, size_t stride, size_t n) 
 }
 
 int b2_nnerr_evaluate(b2_nnerr_t h, const double T[16], double* dist_sum, size_t* n_found) {
+    B2_NVTX("b2_nnerr_evaluate");
     if (!h || !T || !dist_sum) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(h->device));
     return nnerr_eval(h, T, dist_sum, n_found);
 }
 
 int b2_nnerr_yaw_search(b2_nnerr_t h, const double init_guess[16], double T_out[16], double* best_yaw_out, double* min_error_out, int* evaluations) {
+    B2_NVTX("b2_nnerr_yaw_search");
     if (!h || !init_guess || !T_out) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(h->device));
     h->evaluations = 0;

@@ -712,8 +712,10 @@ __global__ void __launch_bounds__(256) k_pack_xyzi(const unsigned char* __restri
     out[i] = make_float4(f[0], f[1], f[2], *reinterpret_cast<const float*>(p + ioff));
 }
 
+struct Xf12 { float v[12]; };
 __global__ void __launch_bounds__(256) k_transform_cloud(const unsigned char* __restrict__ in, size_t istride, int ioff_in, uint32_t n,
-                                                         const float* __restrict__ xf, unsigned char* __restrict__ out, size_t ostride, int ioff_out) {
+                                                         const Xf12 xfm, unsigned char* __restrict__ out, size_t ostride, int ioff_out) {
+    const float* xf = xfm.v;
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned char* p = in + (size_t)i * istride;
@@ -733,6 +735,7 @@ using namespace b2;
 struct b2_s2m_s {
     b2_s2m_params prm;
     cudaStream_t stream = nullptr, stream2 = nullptr, stream_up = nullptr;   // solve + corner index; surf index; scan uploads
+    int device = b2::current_device();      // the device the handle was created on
     cudaEvent_t ev_map = nullptr, ev_up = nullptr, ev_surf = nullptr;
     int last_iters = 3;                            // iterations the previous single-scan solve needed (sizes the first chunk)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -1050,6 +1053,7 @@ int b2_s2m_create(b2_s2m_t* out, const b2_s2m_params* params) {
 }
 
 int b2_s2m_destroy(b2_s2m_t h) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     if (h->map_pending || h->scan_pending) drain_pending(h);     // kernels of a set_map / set_scan nobody waited for
     h->gc.release(); h->gs.release();
@@ -1073,6 +1077,8 @@ int b2_s2m_destroy(b2_s2m_t h) {
 }
 
 int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corner, const void* surf, size_t sstride, size_t n_surf) {
+    B2_NVTX("b2_s2m_set_map");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || (n_corner && !corner) || (n_surf && !surf) || cstride < 12 || sstride < 12 || (cstride & 3) || (sstride & 3)) {
         set_error("b2_s2m_set_map: bad argument"); return B2_ERR_ARG;
     }
@@ -1112,6 +1118,8 @@ int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corn
 // b2_s2m_set_map_from_localmap) left in device memory: the reference rebuilds both kd-trees for every scan
 // (mapOptmization.cpp:1289-1290), and this is that step with the inputs already resident in HBM.
 int b2_s2m_rebuild_map_index(b2_s2m_t h) {
+    B2_NVTX("b2_s2m_rebuild_map_index");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) { set_error("b2_s2m_rebuild_map_index: null handle"); return B2_ERR_ARG; }
     if (!h->have_map) { set_error("b2_s2m_rebuild_map_index: no map set"); return B2_ERR_STATE; }
     if (h->map_pending || h->scan_pending) B2_CHECK(drain_pending(h));
@@ -1131,6 +1139,7 @@ int b2_s2m_rebuild_map_index(b2_s2m_t h) {
 }
 
 int b2_s2m_last_step_gpu_ms(b2_s2m_t h, float* ms) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !ms) return B2_ERR_ARG;
     if (!h->idx_timed) { set_error("b2_s2m_last_step_gpu_ms: call b2_s2m_rebuild_map_index and a solve first"); return B2_ERR_STATE; }
     B2_CUDA(cudaEventSynchronize(h->ev1));
@@ -1139,6 +1148,8 @@ int b2_s2m_last_step_gpu_ms(b2_s2m_t h, float* ms) {
 }
 
 int b2_s2m_set_scan(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corner, const void* surf, size_t sstride, size_t n_surf) {
+    B2_NVTX("b2_s2m_set_scan");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || cstride < 16 || sstride < 16 || (cstride & 3) || (sstride & 3) || n_corner > 0x7fffffff || n_surf > 0x7fffffff) {
         set_error("b2_s2m_set_scan: bad argument"); return B2_ERR_ARG;
     }
@@ -1151,6 +1162,8 @@ int b2_s2m_set_scan(b2_s2m_t h, const void* corner, size_t cstride, size_t n_cor
 
 int b2_s2m_set_scan_batch(b2_s2m_t h, int batch, const void* corner, size_t cstride, const int32_t* coff,
                           const void* surf, size_t sstride, const int32_t* soff) {
+    B2_NVTX("b2_s2m_set_scan_batch");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !coff || !soff || cstride < 16 || sstride < 16 || (cstride & 3) || (sstride & 3)) { set_error("b2_s2m_set_scan_batch: bad argument"); return B2_ERR_ARG; }
     return set_scan_common(h, batch, corner, cstride, coff, surf, sstride, soff);
 }
@@ -1158,6 +1171,8 @@ int b2_s2m_set_scan_batch(b2_s2m_t h, int batch, const void* corner, size_t cstr
 // mapOptimization::laserCloudInfoHandler's two fromROSMsg calls (mapOptmization.cpp:245-246) + downsampleCurrentScan (:940-958)
 int b2_s2m_set_scan_downsampled(b2_s2m_t h, b2_voxel_t ds_corner, const void* corner, size_t cstride, size_t n_corner,
                                 b2_voxel_t ds_surf, const void* surf, size_t sstride, size_t n_surf, size_t* n_corner_ds, size_t* n_surf_ds) {
+    B2_NVTX("b2_s2m_set_scan_downsampled");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !ds_corner || !ds_surf || ds_corner == ds_surf || (n_corner && !corner) || (n_surf && !surf) || cstride < 16 || sstride < 16 ||
         (cstride & 3) || (sstride & 3) || n_corner > 0x7ffffff0ull || n_surf > 0x7ffffff0ull) {
         set_error("b2_s2m_set_scan_downsampled: bad argument"); return B2_ERR_ARG;
@@ -1175,6 +1190,8 @@ int b2_s2m_set_scan_downsampled(b2_s2m_t h, b2_voxel_t ds_corner, const void* co
 
 // the same hand-off when featureExtraction and mapOptimization share the process: cornerCloud / surfaceCloud stay in HBM
 int b2_s2m_set_scan_from_front_end(b2_s2m_t h, b2_scan_t scan, b2_voxel_t ds_corner, b2_voxel_t ds_surf, size_t* n_corner_ds, size_t* n_surf_ds) {
+    B2_NVTX("b2_s2m_set_scan_from_front_end");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !scan || !ds_corner || !ds_surf || ds_corner == ds_surf) { set_error("b2_s2m_set_scan_from_front_end: bad argument"); return B2_ERR_ARG; }
     const void *dc = nullptr, *dsf = nullptr; size_t nc = 0, ns = 0;
     B2_CHECK(scan_features_dev(scan, &dc, &nc, &dsf, &ns));
@@ -1189,6 +1206,7 @@ int b2_s2m_set_scan_from_front_end(b2_s2m_t h, b2_scan_t scan, b2_voxel_t ds_cor
 }
 
 int b2_s2m_get_scan(b2_s2m_t h, int which, float* xyzi, size_t capacity, size_t* n) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !n || (which != 0 && which != 1)) { set_error("b2_s2m_get_scan: bad argument"); return B2_ERR_ARG; }
     if (!h->have_scan) { set_error("b2_s2m_get_scan: no scan set"); return B2_ERR_STATE; }
     const size_t cnt = which ? h->n_s : h->n_c;
@@ -1202,6 +1220,7 @@ int b2_s2m_get_scan(b2_s2m_t h, int which, float* xyzi, size_t capacity, size_t*
 }
 
 int b2_s2m_set_state(b2_s2m_t h, int degenerate, const float matP[36]) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     h->degenerate = degenerate ? 1 : 0;
     if (matP) memcpy(h->matP, matP, sizeof(h->matP));
@@ -1209,6 +1228,8 @@ int b2_s2m_set_state(b2_s2m_t h, int degenerate, const float matP[36]) {
 }
 
 int b2_s2m_iterate(b2_s2m_t h, float pose[6], int iter, int* n_sel, int* ran, int* converged, int* degenerate, float matP[36]) {
+    B2_NVTX("b2_s2m_iterate");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !pose || iter < 0) { set_error("b2_s2m_iterate: bad argument"); return B2_ERR_ARG; }
     if (!h->have_map || !h->have_scan || h->batch != 1) { set_error("b2_s2m_iterate: set_map and set_scan (single scan) first"); return B2_ERR_STATE; }
     B2_CHECK(check_grid_status(h));
@@ -1537,18 +1558,23 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
 
 int b2_s2m_solve(b2_s2m_t h, float pose[6], int max_iterations, int* iters_done, int* converged, int* degenerate,
                  float matP[36], int* not_enough_features, float* pose_history) {
+    B2_NVTX("b2_s2m_solve");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !pose) { set_error("b2_s2m_solve: bad argument"); return B2_ERR_ARG; }
     if (!h->have_map || !h->have_scan || h->batch != 1) { set_error("b2_s2m_solve: set_map and set_scan (single scan) first"); return B2_ERR_STATE; }
     return run_solve(h, pose, max_iterations, iters_done, converged, degenerate, matP, not_enough_features, pose_history, matP != nullptr);
 }
 
 int b2_s2m_solve_batch(b2_s2m_t h, float* poses, int max_iterations, int* iters_done, int* converged, int* degenerate) {
+    B2_NVTX("b2_s2m_solve_batch");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !poses) { set_error("b2_s2m_solve_batch: bad argument"); return B2_ERR_ARG; }
     if (!h->have_map || !h->have_scan) { set_error("b2_s2m_solve_batch: set_map and set_scan_batch first"); return B2_ERR_STATE; }
     return run_solve(h, poses, max_iterations, iters_done, converged, degenerate, nullptr, nullptr, nullptr, false);
 }
 
 int b2_s2m_get_pass(b2_s2m_t h, int which, int32_t* knn_idx, float* knn_d2, float* coeff, uint8_t* flag) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !h->have_scan || h->batch != 1) { set_error("b2_s2m_get_pass: single-scan state required"); return B2_ERR_STATE; }
     const size_t n = which ? h->n_s : h->n_c;
     if (n == 0) return B2_OK;
@@ -1563,6 +1589,7 @@ int b2_s2m_get_pass(b2_s2m_t h, int which, int32_t* knn_idx, float* knn_d2, floa
 }
 
 int b2_s2m_get_normal_equations(b2_s2m_t h, float AtA[36], float AtB[6], float X[6]) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !h->have_scan) { set_error("b2_s2m_get_normal_equations: no scan"); return B2_ERR_STATE; }
     S2MState hs;
     B2_CUDA(cudaMemcpyAsync(&hs, h->state.p, sizeof(S2MState), cudaMemcpyDeviceToHost, h->stream));
@@ -1576,6 +1603,7 @@ int b2_s2m_get_normal_equations(b2_s2m_t h, float AtA[36], float AtB[6], float X
 // Statistics for the roofline numerator: with `enable` the batched solves count every candidate their neighbour search loads
 // (one atomic per warp; costs a few percent, so bench.py switches it on for one untimed solve only).
 int b2_s2m_count_candidates(b2_s2m_t h, int enable, unsigned long long* last_count) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     h->count_candidates = enable != 0;
     if (last_count) *last_count = h->last_candidates;
@@ -1583,6 +1611,7 @@ int b2_s2m_count_candidates(b2_s2m_t h, int enable, unsigned long long* last_cou
 }
 
 int b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     if (!h->last_ms_valid) {
         B2_CUDA(cudaEventSynchronize(h->ev1));
@@ -1595,25 +1624,30 @@ int b2_s2m_last_gpu_ms(b2_s2m_t h, float* ms, int* launches) {
 }
 
 int b2_transform_cloud(const void* in, size_t in_stride, size_t n, const float pose6[6], void* out, size_t out_stride) {
+    B2_NVTX("b2_transform_cloud");
     if ((n && (!in || !out)) || !pose6 || in_stride < 16 || out_stride < 16 || (in_stride & 3) || (out_stride & 3)) { set_error("b2_transform_cloud: bad argument"); return B2_ERR_ARG; }
     if (n == 0) return B2_OK;
-    float xf[12], trig[6];
-    host_prepare_pose(pose6, xf, trig);
-    unsigned char *d_in = nullptr, *d_out = nullptr; float* d_xf = nullptr;
-    B2_CUDA(cudaMalloc(&d_in, n * in_stride));
-    cudaError_t e = cudaMalloc(&d_out, n * out_stride);
-    if (e == cudaSuccess) e = cudaMalloc(&d_xf, sizeof(xf));
-    if (e == cudaSuccess) e = cudaMemcpy(d_in, in, n * in_stride, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemset(d_out, 0, n * out_stride);
-    if (e == cudaSuccess) e = cudaMemcpy(d_xf, xf, sizeof(xf), cudaMemcpyHostToDevice);
+    Xf12 xf; float trig[6];
+    host_prepare_pose(pose6, xf.v, trig);
+    // pooled buffers and a stream of its own (no cudaMalloc / cudaFree and no legacy-stream copies per call)
+    size_t cap_in = 0, cap_out = 0;
+    void* d_in = pool_alloc(n * in_stride, &cap_in);
+    void* d_out = d_in ? pool_alloc(n * out_stride, &cap_out) : nullptr;
+    cudaStream_t st = nullptr;
+    cudaError_t e = (d_in && d_out) ? cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) : cudaErrorMemoryAllocation;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, n * in_stride, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_out, 0, n * out_stride, st);
     if (e == cudaSuccess) {
-        k_transform_cloud<<<(unsigned)((n + 255) / 256), 256>>>(d_in, in_stride, (int)B2_INTENSITY_OFFSET(in_stride), (uint32_t)n, d_xf,
-                                                                d_out, out_stride, (int)B2_INTENSITY_OFFSET(out_stride)); count_launch();
+        k_transform_cloud<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const unsigned char*>(d_in), in_stride, (int)B2_INTENSITY_OFFSET(in_stride), (uint32_t)n, xf,
+                                                                      static_cast<unsigned char*>(d_out), out_stride, (int)B2_INTENSITY_OFFSET(out_stride)); count_launch();
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * out_stride, cudaMemcpyDeviceToHost);
-    cudaFree(d_in); cudaFree(d_out); cudaFree(d_xf);
-    if (e != cudaSuccess) { set_error("b2_transform_cloud: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, n * out_stride, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (st) cudaStreamDestroy(st);
+    if (d_in) pool_free(d_in, cap_in);
+    if (d_out) pool_free(d_out, cap_out);
+    if (e != cudaSuccess) { set_error("b2_transform_cloud: %s", cudaGetErrorString(e)); cudaGetLastError(); return B2_ERR_CUDA; }
     return B2_OK;
 }
 

@@ -487,6 +487,7 @@ struct b2_scan_s {
     b2_scan_params prm;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int device = b2::current_device();      // the device the handle was created on
     DevBuf raw, imu, winner, small, range_mat, full_cloud, extracted, col_ind, pt_range, rings;
     DevBuf curv, picked, label, corner_idx, surf_idx, surf_ds, corner_out, corner_idx_out, surf_out;
     DevBuf wire;                          // cloud_info message staging (device)
@@ -522,6 +523,7 @@ int b2_scan_create(b2_scan_t* out, const b2_scan_params* params) {
 }
 
 int b2_scan_destroy(b2_scan_t h) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     DevBuf* bufs[] = {&h->raw, &h->imu, &h->winner, &h->small, &h->range_mat, &h->full_cloud, &h->extracted, &h->col_ind, &h->pt_range, &h->rings,
                       &h->curv, &h->picked, &h->label, &h->corner_idx, &h->surf_idx, &h->surf_ds, &h->corner_out, &h->corner_idx_out, &h->surf_out, &h->wire};
@@ -559,6 +561,8 @@ int b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n, const double* imu
                     const double* imu_rot_z, int n_imu, double time_scan_cur, int deskew_flag,
                     size_t* n_extracted, float* extracted_xyzi, int32_t* point_col_ind, float* point_range,
                     int32_t* start_ring_index, int32_t* end_ring_index, float* range_mat, float* full_cloud) {
+    B2_NVTX("b2_scan_project");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || (n && !xyzirt) || !n_extracted || n > 0x7ffffff0ull || (n_imu > 0 && (!imu_time || !imu_rot_x || !imu_rot_y || !imu_rot_z))) {
         set_error("b2_scan_project: bad argument"); return B2_ERR_ARG;
     }
@@ -625,6 +629,8 @@ int b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n, const double* imu
 
 int b2_scan_extract_features(b2_scan_t h, size_t* n_corner, float* corner_xyzi, int32_t* corner_index, size_t* n_surf, float* surf_xyzi,
                              float* curvature, int32_t* picked_after_mask, int32_t* label) {
+    B2_NVTX("b2_scan_extract_features");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !n_corner || !n_surf) { set_error("b2_scan_extract_features: bad argument"); return B2_ERR_ARG; }
     if (!h->projected) { set_error("b2_scan_extract_features: call b2_scan_project first"); return B2_ERR_STATE; }
     const ScanDev s = scan_dev(h->prm);
@@ -689,6 +695,7 @@ int b2_scan_extract_features(b2_scan_t h, size_t* n_corner, float* corner_xyzi, 
 }
 
 int b2_scan_last_gpu_ms(b2_scan_t h, float* ms) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !ms) return B2_ERR_ARG;
     *ms = h->last_ms;
     return B2_OK;
@@ -722,6 +729,7 @@ int b2_imu_deskew_info(const double* stamp, const double* orientation_xyzw, cons
                        double time_scan_cur, double time_scan_end,
                        double* imu_time, double* imu_rot_x, double* imu_rot_y, double* imu_rot_z, int capacity,
                        int* n_table, int* n_popped, int* imu_available, float rpy_init[3]) {
+    B2_NVTX("b2_imu_deskew_info");
     if (n < 0 || (n > 0 && (!stamp || !angular_velocity)) || !imu_time || !imu_rot_x || !imu_rot_y || !imu_rot_z || capacity < 1 ||
         !n_table || !n_popped || !imu_available) {
         b2::set_error("b2_imu_deskew_info: bad argument");
@@ -954,6 +962,8 @@ int b2_cloud_info_parse(const void* msg, size_t n_bytes, b2_cloud_info_view* v) 
 }
 
 int b2_scan_write_cloud_info(b2_scan_t h, const b2_cloud_info_meta* meta, int stage, void* out, size_t capacity, size_t* n_bytes) {
+    B2_NVTX("b2_scan_write_cloud_info");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !meta || !n_bytes || (stage != 0 && stage != 1)) { set_error("b2_scan_write_cloud_info: bad argument"); return B2_ERR_ARG; }
     if (!h->projected || (stage == 1 && !h->featured)) { set_error("b2_scan_write_cloud_info: stage %d needs b2_scan_%s first", stage, stage ? "extract_features" : "project"); return B2_ERR_STATE; }
     const ScanDev s = scan_dev(h->prm);
@@ -1016,6 +1026,8 @@ int b2_scan_write_cloud_info(b2_scan_t h, const b2_cloud_info_meta* meta, int st
 }
 
 int b2_scan_set_from_cloud_info(b2_scan_t h, const void* msg, size_t n_bytes, size_t* n_extracted) {
+    B2_NVTX("b2_scan_set_from_cloud_info");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !msg) { set_error("b2_scan_set_from_cloud_info: null argument"); return B2_ERR_ARG; }
     b2_cloud_info_view v;
     B2_CHECK(b2_cloud_info_parse(msg, n_bytes, &v));

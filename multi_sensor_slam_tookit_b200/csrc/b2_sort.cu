@@ -66,9 +66,16 @@ void* pool_alloc(size_t bytes, size_t* cap_out) {
 
 void pool_free(void* p, size_t cap) {
     if (!p) return;
+    // the block belongs to the device it was allocated on, whatever device the calling thread has current (a handle may be
+    // destroyed from another thread, or after b2_set_device): ask the pointer, synchronise and tag THAT device
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceSynchronize();           // nothing in flight may still use the block when another handle picks it up
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) dev = at.device; else cudaGetLastError();
+    {
+        DeviceScope scope(dev);
+        cudaDeviceSynchronize();       // nothing in flight may still use the block when another handle picks it up
+    }
     std::lock_guard<std::mutex> lk(g_pool_mu);
     if (g_pool_bytes + cap > POOL_LIMIT) { cudaFree(p); return; }
     g_pool.push_back(PoolBlock{p, cap, dev});

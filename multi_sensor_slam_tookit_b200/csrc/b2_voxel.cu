@@ -132,6 +132,7 @@ struct b2_voxel_s {
     unsigned min_pts = 0;
     cudaStream_t stream = nullptr;
     DevBuf raw, work, out, small, vop;
+    int device = b2::current_device();      // the device the handle was created on
     PinBuf pin;
 };
 
@@ -147,6 +148,7 @@ int b2_voxel_create(b2_voxel_t* out) {
 }
 
 int b2_voxel_destroy(b2_voxel_t h) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     h->raw.release(); h->work.release(); h->out.release(); h->small.release(); h->vop.release(); h->pin.release();
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -155,12 +157,14 @@ int b2_voxel_destroy(b2_voxel_t h) {
 }
 
 int b2_voxel_set_leaf_size(b2_voxel_t h, float lx, float ly, float lz) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !(lx > 0.f) || !(ly > 0.f) || !(lz > 0.f)) { set_error("b2_voxel_set_leaf_size: leaf must be > 0"); return B2_ERR_ARG; }
     h->leaf[0] = lx; h->leaf[1] = ly; h->leaf[2] = lz;
     return B2_OK;
 }
 
 int b2_voxel_set_min_points_per_voxel(b2_voxel_t h, unsigned min_points) {
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     h->min_pts = min_points;
     return B2_OK;
@@ -282,6 +286,8 @@ extern "C" {
 
 int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, int n_fields, void* out, size_t out_stride,
                     size_t out_capacity, size_t* n_out, int* refused, int32_t* voxel_of_point) {
+    B2_NVTX("b2_voxel_filter");
+    b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h || !n_out || (n && (!in || !out)) || (n_fields != 3 && n_fields != 4) || in_stride < (size_t)(n_fields * 4) ||
         out_stride < (size_t)(n_fields * 4) || (in_stride & 3) || (out_stride & 3) || n > 0x7ffffff0ull) {
         set_error("b2_voxel_filter: bad argument"); return B2_ERR_ARG;
