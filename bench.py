@@ -555,6 +555,15 @@ def run_registration(args, rank, local_rank, world, dist, torch):
             "cpu_baseline": {"value": ev / tr / 1e6, "unit": "Mpts/s", "cores": host_cores(), "kind": "port",
                              "sample": f"pair (1 -> 0): {it} iterations in {tr:.3f} s (registration only), {tt:.3f} s with downsampling + normals",
                              "e2e_value": ev / tt / 1e6}}
+    # ---- C4, standard mode: the 4 pairs (every other lidar onto lidar 0) of multi_lidar_calibrator.py:202-219
+    c4s = GB.run_c4(rank, world, mode="standard")
+    wall_s = allmax(c4s["wall_s"]); gpu_ms_s = allmax(c4s["gpu_ms"]); evals_s = allsum(c4s["src_evals"]); npairs_s = allsum(c4s["pairs"])
+    if rank == 0:
+        out["gicp_c4_standard"] = {
+            "workload": f"C4 Multi_LiCa GICP, standard mode: {int(npairs_s)} pairs onto lidar 0 (multi_lidar_calibrator.py:202-219), same parameters",
+            "value": evals_s / max(gpu_ms_s, 1e-9) / 1e3, "unit": "Mpts/s", "scaling": "pairs round-robin over ranks (at most 4 ranks have work), no collective",
+            "e2e": {"value": evals_s / wall_s / 1e6, "unit": "Mpts/s", "ms_per_pair": 1e3 * wall_s * min(world, max(int(npairs_s), 1)) / max(npairs_s, 1),
+                    "step": "per pair: upload both clouds, voxel_down_sample, estimate_normals, registration_generalized_icp, result to host"}}
     # ---- C5: one registration, source sharded over the ranks, 30 doubles all-reduced per iteration
     comm = None
     if world > 1:

@@ -53,7 +53,11 @@ def c4_clouds(n_rings=64, n_cols=1024):
     return out
 
 
-def c4_pairs():
+def c4_pairs(mode="fitness"):
+    """fitness mode: the 20 ordered pairs of multi_lidar_calibrator.py:302-321; standard mode: every other lidar onto the
+    target lidar 0, 4 pairs (multi_lidar_calibrator.py:202-219)."""
+    if mode == "standard":
+        return [(s, 0) for s in range(1, 5)]
     return [(s, t) for t in range(5) for s in range(5) if s != t]        # 20 ordered pairs
 
 
@@ -107,13 +111,13 @@ def c5_clouds_torch(n, device, seed=20261018 + 5):
 
 
 # ------------------------------------------------------------------------------------------------ C4
-def run_c4(rank=0, world=1, n_cols=1024, repeats=1):
+def run_c4(rank=0, world=1, n_cols=1024, repeats=1, mode="fitness"):
     """Each rank calibrates its round-robin share of the 20 ordered pairs, host buffers in, result out (what
     Calibration.compute_gicp_transformation does per pair). Returns per-rank totals."""
     from multi_sensor_slam_tookit_b200 import gicp
     clouds = c4_clouds(n_cols=n_cols)
     P = C4_PARAMS
-    pairs = c4_pairs()
+    pairs = c4_pairs(mode)
     mine = [i for i in range(len(pairs)) if gicp.pair_owner(i, world) == rank]
     stats = dict(pairs=len(mine), src_evals=0.0, gpu_ms=0.0, wall_s=0.0, iters=0, max_t_err=0.0, max_r_err=0.0, launches=0,
                  pts_in=0, pts_ds=0, prep_ms=0.0)
