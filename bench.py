@@ -305,7 +305,8 @@ def run_b200(args, rank, local_rank, world):
     # ---- local map on the device: key frames resident in HBM, extractCloud + index + solve per step
     from multi_sensor_slam_tookit_b200 import synth
     from multi_sensor_slam_tookit_b200.registration import LocalMap
-    kfs = synth.keyframes_from_map(c1["map_corner"], c1["map_surf"], 12, 5)
+    # 50 overlapping key frames (consecutive scans see the same surfaces): ~1 M points into the two map VoxelGrids, ~100 k out
+    kfs = synth.keyframes_overlapping(c1["map_corner"], c1["map_surf"], 50, 0.2)
     lm = LocalMap(0.2, 0.4, surroundingKeyframeSearchRadius=1e9)
     for kc, ks_, kp in kfs:
         lm.saveKeyFrame(kc, ks_, kp)
@@ -436,11 +437,25 @@ def run_b200(args, rank, local_rank, world):
         while time.perf_counter() - t0 < 4.0:
             ci += cpu_lm_step()
         cpu_lm = ci / (time.perf_counter() - t0)
+        # the same step with the assembled map crossing PCIe instead (what a caller without the device-resident key frames pays)
+        g_up = ScanToMapOptimizer()
+        mcd, msd = pin(lm.get("cornerDS")), pin(lm.get("surfDS"))
+        for _ in range(W):
+            g_up.setInputMap(mcd, msd); g_up.setInputScan(sc, ss); g_up.transformTobeMapped = guess.copy(); g_up.scan2MapOptimization(30, want_matP=False)
+        ui, t0 = 0, time.perf_counter()
+        for _ in range(K):
+            g_up.setInputMap(mcd, msd); g_up.setInputScan(sc, ss); g_up.transformTobeMapped = guess.copy()
+            ui += g_up.scan2MapOptimization(30, want_matP=False)["iters"]
+        up_s = time.perf_counter() - t0
+        del g_up
         line["local_map"] = {
-            "workload": f"extractCloud over {len(kfs)} device-resident key frames ({lm_pts[0]} corner + {lm_pts[1]} surf points -> {lm_pts[2]} + {lm_pts[3]} "
+            "workload": f"extractCloud over {len(kfs)} overlapping device-resident key frames ({lm_pts[0]} corner + {lm_pts[1]} surf points -> {lm_pts[2]} + {lm_pts[3]} "
                         "after VoxelGrid 0.2 / 0.4), index build, set_scan, LM loop; the map never crosses PCIe (mapOptmization.cpp:899-938, 1282-1310)",
             "e2e": {"value": lm_iters / lm_s, "unit": UNIT, "ms_per_step": 1e3 * lm_s / K, "h2d_bytes_per_step": int(sc.nbytes + ss.nbytes + 592 + 16 + 96 * len(kfs)),
                     "d2h_bytes_per_step": 644 + 2 * 28}, "extract_gpu_ms": lm_ms / K,
+            "upload_path": {"value": ui / up_s, "unit": UNIT, "ms_per_step": 1e3 * up_s / K,
+                            "step": "the already assembled + downsampled map uploaded from the host (set_map) + set_scan + LM loop: what the "
+                                    "device-resident path has to beat although it also does the assembly and both VoxelGrids"},
             "cpu_baseline": {"value": cpu_lm, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "the same step on the oracle (transformPointCloud x 24, two VoxelGrids, two kd-trees, LM loop) for 4 s"}}
         if batched:
@@ -515,6 +530,38 @@ def run_registration(args, rank, local_rank, world, dist, torch):
                                  "launch-latency bound at this size (one scan)"},
             "cpu_baseline": {"value": cpu["mpts_per_s"], "unit": "Mpts/s", "cores": 1, "kind": "port",
                              "sample": f"{cpu['reps']} scans: project {cpu['project_ms']:.2f} ms + features {cpu['features_ms']:.2f} ms (serial, as the reference's two nodes are)"}}
+    # ---- pcl::VoxelGrid at the sizes the local map feeds it (0.3-1 M points in, ~100 k out; 4 M = a long session)
+    if rank == 0:
+        from multi_sensor_slam_tookit_b200.registration import VoxelGrid
+        from oracle import pyoracle as O
+        c1v = load_c1()
+        rngv = np.random.default_rng(3)
+        out["voxel_grid"] = {}
+        for n_in in (1_000_000, 4_000_000):
+            base = c1v["map_surf"][rngv.integers(0, len(c1v["map_surf"]), n_in)].copy()
+            base[:, :3] += rngv.normal(0.0, 0.05, (n_in, 3)).astype(np.float32)
+            hostbuf = torch.from_numpy(np.ascontiguousarray(base)).pin_memory().numpy()
+            vg = VoxelGrid(); vg.setLeafSize(0.4, 0.4, 0.4); vg.setInputCloud(hostbuf)
+            for _ in range(3):
+                res = vg.filter()
+            reps, dev, t0 = 10, 0.0, time.perf_counter()
+            for _ in range(reps):
+                res = vg.filter(); dev += vg.lastGpuMs()
+            wall = time.perf_counter() - t0
+            t0 = time.perf_counter(); ref = O.voxel_grid(base, 0.4)["out"]; cpu_s = time.perf_counter() - t0
+            assert len(ref) == len(res)
+            abytes = 16.0 * n_in + 16.0 * len(res)
+            ach = abytes / (dev / reps * 1e-3) / 1e9
+            out["voxel_grid"][f"{n_in // 1_000_000}M"] = {
+                "workload": f"pcl::VoxelGrid(0.4 m) on {n_in} PointXYZI (map points resampled with 5 cm noise) -> {len(res)} voxels (mapOptmization.cpp:928,932)",
+                "value": n_in / (dev / reps * 1e-3) / 1e6, "unit": "Mpts/s", "gpu_ms": dev / reps,
+                "e2e": {"value": n_in * reps / wall / 1e6, "unit": "Mpts/s", "ms": 1e3 * wall / reps, "h2d_bytes": int(16 * n_in), "d2h_bytes": int(16 * len(res)),
+                        "step": "b2_voxel_filter: pinned host cloud in, downsampled cloud out"},
+                "roofline": {"kernel": "k_vx_* + k_rs_* (bbox, key, radix sort of (voxel, index) pairs, run heads, centroids)", "bound": "hbm", "achieved": ach,
+                             "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": abytes,
+                             "note": "16 B read + 16 B x (voxels / points) written per input point (SURVEY.md 8d) over the device span of the whole filter"},
+                "cpu_baseline": {"value": n_in / cpu_s / 1e6, "unit": "Mpts/s", "cores": 1, "kind": "port", "sample": f"one filter of the same cloud in {cpu_s:.2f} s (serial, as pcl::VoxelGrid)"}}
+            del vg
     # ---- C3: one NDT pair does not shard -> rank 0 only
     if rank == 0:
         inputs = NB.c3_inputs()

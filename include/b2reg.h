@@ -69,6 +69,8 @@ int b2_voxel_set_min_points_per_voxel(b2_voxel_t h, unsigned min_points);
 int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, int n_fields,
                     void* out, size_t out_stride, size_t out_capacity, size_t* n_out,
                     int* refused, int32_t* voxel_of_point);
+/* device ms of the last b2_voxel_filter, copies excluded (CUDA events on the handle's stream) */
+int b2_voxel_last_gpu_ms(b2_voxel_t h, float* ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched nearest-neighbour index — replaces pcl::KdTreeFLANN<PointType>::{setInputCloud,nearestKSearch}

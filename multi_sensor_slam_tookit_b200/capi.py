@@ -66,7 +66,7 @@ class GicpParams(C.Structure):
 # every symbol include/b2reg.h declares (tests/test_abi.py checks the library exports all of them)
 SYMBOLS = [
     "b2_version", "b2_last_error", "b2_device_count", "b2_set_device", "b2_kernel_launch_count", "b2_trim_memory",
-    "b2_voxel_create", "b2_voxel_destroy", "b2_voxel_set_leaf_size", "b2_voxel_set_min_points_per_voxel", "b2_voxel_filter",
+    "b2_voxel_create", "b2_voxel_destroy", "b2_voxel_set_leaf_size", "b2_voxel_set_min_points_per_voxel", "b2_voxel_filter", "b2_voxel_last_gpu_ms",
     "b2_knn_create", "b2_knn_destroy", "b2_knn_set_input_cloud", "b2_knn_nearest_k_search",
     "b2_s2m_default_params", "b2_s2m_create", "b2_s2m_destroy", "b2_s2m_set_map", "b2_s2m_set_scan", "b2_s2m_iterate",
     "b2_s2m_solve", "b2_s2m_set_state", "b2_s2m_get_pass", "b2_s2m_get_normal_equations", "b2_s2m_set_scan_batch",
@@ -140,6 +140,7 @@ def lib():
     L.b2_voxel_destroy.argtypes = [vp]
     L.b2_voxel_set_leaf_size.argtypes = [vp, f32, f32, f32]
     L.b2_voxel_set_min_points_per_voxel.argtypes = [vp, C.c_uint]
+    L.b2_voxel_last_gpu_ms.argtypes = [vp, pf]
     L.b2_voxel_filter.argtypes = [vp, vp, sz, sz, i32, vp, sz, sz, C.POINTER(sz), pi, vp]
     L.b2_knn_create.argtypes = [C.POINTER(vp), f32]
     L.b2_knn_destroy.argtypes = [vp]

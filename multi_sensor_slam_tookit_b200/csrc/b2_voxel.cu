@@ -133,6 +133,8 @@ struct b2_voxel_s {
     cudaStream_t stream = nullptr;
     DevBuf raw, work, out, small, vop;
     int device = b2::current_device();      // the device the handle was created on
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device span of the last filter, upload and download excluded (b2_voxel_last_gpu_ms)
+    bool timed = false;
     PinBuf pin;
 };
 
@@ -148,6 +150,7 @@ int b2_voxel_create(b2_voxel_t* out) {
 }
 
 int b2_voxel_destroy(b2_voxel_t h) {
+    if (h && h->ev0) { cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1); h->ev0 = h->ev1 = nullptr; }
     b2::DeviceScope device_scope_(h ? h->device : -1);
     if (!h) return B2_ERR_ARG;
     h->raw.release(); h->work.release(); h->out.release(); h->small.release(); h->vop.release(); h->pin.release();
@@ -302,11 +305,25 @@ int b2_voxel_filter(b2_voxel_t h, const void* in, size_t in_stride, size_t n, in
     int32_t* d_vop = nullptr;
     if (voxel_of_point) { B2_CHECK(h->vop.reserve(n * sizeof(int32_t))); d_vop = h->vop.as<int32_t>(); }
     uint32_t m = 0;
+    if (!h->ev0) { B2_CUDA(cudaEventCreate(&h->ev0)); B2_CUDA(cudaEventCreate(&h->ev1)); }
+    B2_CUDA(cudaEventRecord(h->ev0, s));
     B2_CHECK(voxel_filter_dev(h, h->raw.as<unsigned char>(), in_stride, n, n_fields, out_stride, out_capacity, &m, refused, d_vop));
+    B2_CUDA(cudaEventRecord(h->ev1, s));
+    h->timed = true;
     if (voxel_of_point) B2_CUDA(cudaMemcpyAsync(voxel_of_point, d_vop, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     if (m) B2_CUDA(cudaMemcpyAsync(out, h->out.p, (size_t)m * out_stride, cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
     *n_out = m;
+    return B2_OK;
+}
+
+// device time of the last b2_voxel_filter between the end of the upload and the start of the download (CUDA events)
+int b2_voxel_last_gpu_ms(b2_voxel_t h, float* ms) {
+    if (!h || !ms) return B2_ERR_ARG;
+    b2::DeviceScope device_scope_(h->device);
+    if (!h->timed) { set_error("b2_voxel_last_gpu_ms: no filter has run"); return B2_ERR_STATE; }
+    B2_CUDA(cudaEventSynchronize(h->ev1));
+    B2_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return B2_OK;
 }
 

@@ -56,6 +56,15 @@ class VoxelGrid:
         return (res, vop[:n]) if return_voxel_index else res
 
 
+def _voxel_last_gpu_ms(self):
+    ms = C.c_float(0)
+    capi.check(capi.lib().b2_voxel_last_gpu_ms(self._h, C.byref(ms)))
+    return ms.value
+
+
+VoxelGrid.lastGpuMs = _voxel_last_gpu_ms
+
+
 class KdTreeFLANN:
     """Batched drop-in for the kd-tree queries of the LM loop. Exact for neighbours closer than max_dist."""
 

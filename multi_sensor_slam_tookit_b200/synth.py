@@ -229,3 +229,26 @@ def keyframes_from_map(map_corner, map_surf, n_keys=12, seed=5):
             loc.append(np.ascontiguousarray(q))
         keys.append((loc[0], loc[1], pose))
     return keys
+
+
+def keyframes_overlapping(map_corner, map_surf, n_keys=50, frac=0.2, noise=0.02, seed=11):
+    """Key frames as LIO-SAM really accumulates them for the local map (mapOptmization.cpp:899-938): consecutive scans see mostly
+    the SAME surfaces, so the concatenation the two map VoxelGrids receive is several times the size of their output. Key frame k
+    is a random `frac` of the map points (+ N(0, noise) range noise), moved into the sensor frame of a key pose.
+    Returns a list of (corner (n, 4) f32, surf (n, 4) f32, pose6 f32)."""
+    rng = np.random.default_rng(seed)
+    keys = []
+    for k in range(n_keys):
+        pose = np.array([rng.uniform(-0.05, 0.05), rng.uniform(-0.05, 0.05), rng.uniform(-3, 3),
+                         rng.uniform(-30, 30), rng.uniform(-30, 30), rng.uniform(-0.5, 0.5)], np.float32)
+        R = rot_zyx(*pose[:3].astype(np.float64))
+        t = pose[3:].astype(np.float64)
+        loc = []
+        for cloud in (map_corner, map_surf):
+            pick = rng.random(len(cloud)) < frac
+            q = cloud[pick].copy()
+            w = q[:, :3].astype(np.float64) + rng.normal(0.0, noise, (len(q), 3))
+            q[:, :3] = ((w - t) @ R).astype(np.float32)
+            loc.append(np.ascontiguousarray(q))
+        keys.append((loc[0], loc[1], pose))
+    return keys
