@@ -315,6 +315,13 @@ int  b2_gicp_set_source_slice(b2_gicp_t h, b2_cloud_t source, size_t begin, size
  * mix of easy and hard regions; the 30 sums are all-reduced over `comm` every iteration and every rank solves the same
  * 6x6 system, so all ranks return the same T. world = 1 (the default) needs no communicator. With world > 1 and
  * comm = NULL only b2_gicp_linearize works and returns this shard's local sums. */
+/* Fused linearise + exchange for sharded registrations (no NCCL call and no epilogue launch per iteration): each rank exports
+ * its exchange area (CUDA IPC handle, 64 bytes), the host program gathers the handles of all ranks in rank order and hands them
+ * to every rank; the last CTA of k_gicp_linearize then stores its 30 sums into every peer over NVLink (240 B per peer and
+ * iteration) and waits for theirs. Needs P2P access between the GPUs; when a peer cannot be mapped b2_gicp_set_peers fails
+ * and the NCCL all-reduce of b2_gicp_set_shard stays in use. Call after b2_gicp_set_shard. */
+int  b2_gicp_peer_handle(b2_gicp_t h, unsigned char handle[64]);
+int  b2_gicp_set_peers(b2_gicp_t h, int rank, int world, const unsigned char* handles /* world x 64 bytes */);
 int  b2_gicp_set_shard(b2_gicp_t h, int rank, int world, b2_comm_t comm);
 /* one evaluation at T (parity tests): sums as above; corr (optional, n_source ints) = target index or -1 */
 int  b2_gicp_linearize(b2_gicp_t h, const double T[16], double sums[30], int32_t* corr);

@@ -46,6 +46,16 @@ struct GicpState {
     double hist_fit[GICP_HIST], hist_rmse[GICP_HIST];
 };
 
+// Exchange area of the fused linearise + all-reduce (sharded registrations): every rank owns one, the peers map it through CUDA
+// IPC and store their 30 local sums straight into it over NVLink, then a sequence number. Two slots alternate between
+// evaluations (a rank can be at most one evaluation ahead of the slowest one: it cannot finish evaluation k + 1 before every
+// peer has contributed to it, i.e. has finished reading evaluation k).
+constexpr int GICP_MAX_WORLD = 16;
+struct GicpPeerArea {
+    double sums[2][GICP_MAX_WORLD][32];
+    unsigned flag[2][GICP_MAX_WORLD];
+};
+
 struct GicpArgs {
     GridDDev tgt;                    // target index (fine: about two points per occupied cell)
     GridDDev tgtc;                   // the same points in cells of edge >= max_correspondence_distance
@@ -61,7 +71,11 @@ struct GicpArgs {
     int32_t* corr;                   // optional: corr[source original index] = target original index or -1
     uint32_t* prev;                  // optional: prev[source position] = fine position of the last correspondence (seeds the search)
     GicpState* st;
-    int mode;                        // 0: reduce into sums_local; 1: reduce into sums and finalize on the device
+    int mode;                        // 0: reduce into sums_local; 1: reduce into sums and finalize on the device;
+                                     // 2: exchange the local sums with the peers inside the kernel, then finalize (every rank alike)
+    GicpPeerArea* peers[GICP_MAX_WORLD];   // mode 2: exchange areas of all ranks (peers[rank] is this GPU's own)
+    unsigned seq_base;               // mode 2: sequence numbers of this align are seq_base + evaluation + 1
+    int xrank, xworld;               // mode 2: rank / size of the exchange (the shard deal above may be 0 / 1 for a sliced source)
 };
 
 // LDL^T solve of the symmetric 6x6 (Open3D: SolveLinearSystemPSD -> A.ldlt().solve(b)), no pivoting, oracle order
@@ -220,15 +234,40 @@ __global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_lineariz
     if (!s_last) return;
     __threadfence();
     double* out = A.mode == 1 ? st->sums : st->sums_local;
+    double v = 0.0;
     if (threadIdx.x < GICP_NSUM) {
-        double v = 0.0;
         for (unsigned b = 0; b < gridDim.x; b++) v += __ldcg(&A.partials[(size_t)b * GICP_NSUM + threadIdx.x]);
         out[threadIdx.x] = v;
+    }
+    if (A.mode == 2) {
+        // Fused exchange: this GPU's 30 sums go straight into every rank's exchange area (peer stores over NVLink, 240 B per
+        // peer), then the sequence number of this evaluation; the epilogue waits for all ranks' numbers, adds the contributions
+        // in rank order — the same bits on every rank — and runs the same finalisation as the single-GPU path. No NCCL launch
+        // and no separate epilogue kernel per iteration.
+        const int slot = st->evals & 1;
+        const unsigned seq = A.seq_base + (unsigned)st->evals + 1u;
+        if (threadIdx.x < GICP_NSUM)
+            for (int p = 0; p < A.xworld; p++) A.peers[p]->sums[slot][A.xrank][threadIdx.x] = v;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < A.xworld) {
+            *reinterpret_cast<volatile unsigned*>(&A.peers[threadIdx.x]->flag[slot][A.xrank]) = seq;
+            __threadfence_system();
+            volatile unsigned* mine = reinterpret_cast<volatile unsigned*>(&A.peers[A.xrank]->flag[slot][threadIdx.x]);
+            while (*mine != seq) __nanosleep(100);
+            __threadfence_system();
+        }
+        __syncthreads();
+        if (threadIdx.x < GICP_NSUM) {
+            double t = 0.0;
+            for (int r = 0; r < A.xworld; r++) t += *reinterpret_cast<volatile double*>(&A.peers[A.xrank]->sums[slot][r][threadIdx.x]);
+            st->sums[threadIdx.x] = t;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         st->ticket = 0;
-        if (A.mode == 1) gicp_finalize(st);
+        if (A.mode != 0) gicp_finalize(st);
     }
 }
 
@@ -275,6 +314,10 @@ struct b2_gicp_s {
     size_t n_tgt = 0, n_src = 0;
     uint32_t src_valid = 0;
     bool have_tgt = false, have_src = false;
+    GicpPeerArea* peer_own = nullptr;                 // this GPU's exchange area (cudaMalloc: exported through CUDA IPC)
+    GicpPeerArea* peer_ptr[GICP_MAX_WORLD] = {nullptr};
+    int peer_world = 0, peer_rank = 0;                // > 0 once b2_gicp_set_peers succeeded: align exchanges inside the kernel
+    unsigned peer_seq = 0;
     bool src_slice = false;          // src_grid holds only this rank's rows of the source (b2_gicp_set_source_slice)
     int rank = 0, world = 1;
     b2_comm_s* comm = nullptr;
@@ -326,6 +369,8 @@ static void gicp_fill_args(b2_gicp_s* h, GicpArgs& a, int mode, int32_t* corr) {
     a.prev = nullptr;
     a.st = h->state.as<GicpState>();
     a.mode = mode;
+    for (int p = 0; p < GICP_MAX_WORLD; p++) a.peers[p] = h->peer_ptr[p];
+    a.seq_base = h->peer_seq; a.xrank = h->peer_rank; a.xworld = h->peer_world;
     const uint32_t chunks = a.n_local_chunks;
     h->grid_blocks = (int)std::max<uint32_t>(1u, std::min<uint32_t>((chunks + GICP_WARPS - 1) / GICP_WARPS, (uint32_t)(device_sm_count() * h->blocks_per_sm)));
 }
@@ -394,6 +439,9 @@ int b2_gicp_destroy(b2_gicp_t h) {
     if (!h) return B2_OK;
     h->tgt_grid.release(); h->tgt_coarse.release(); h->src_grid.release(); h->tgt_xyz.release(); h->fine_pos_of.release();
     h->tgt_m.release(); h->src_m.release(); h->partials.release(); h->state.release(); h->corr.release(); h->prev.release(); h->pin.release();
+    for (int p = 0; p < GICP_MAX_WORLD; p++)
+        if (h->peer_ptr[p] && h->peer_ptr[p] != h->peer_own) cudaIpcCloseMemHandle(h->peer_ptr[p]);
+    if (h->peer_own) cudaFree(h->peer_own);
     if (h->e0) cudaEventDestroy(h->e0);
     if (h->e1) cudaEventDestroy(h->e1);
     for (cudaEvent_t e : h->ev) cudaEventDestroy(e);
@@ -491,6 +539,45 @@ int b2_gicp_set_shard(b2_gicp_t h, int rank, int world, b2_comm_t comm) {
     return B2_OK;
 }
 
+// Fused exchange set-up. b2_gicp_peer_handle allocates this rank's exchange area and returns its CUDA IPC handle (64 bytes); the
+// host program gathers the handles of all ranks (as it distributes the NCCL id) and passes them to b2_gicp_set_peers, which
+// maps the peers' areas. From then on b2_gicp_align exchanges the 30 sums inside k_gicp_linearize instead of calling NCCL.
+int b2_gicp_peer_handle(b2_gicp_t h, unsigned char handle[64]) {
+    if (!h || !handle) return B2_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    B2_CUDA(cudaSetDevice(h->device));
+    if (!h->peer_own) {
+        B2_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->peer_own), sizeof(GicpPeerArea)));
+        B2_CUDA(cudaMemset(h->peer_own, 0, sizeof(GicpPeerArea)));
+    }
+    cudaIpcMemHandle_t ipc;
+    B2_CUDA(cudaIpcGetMemHandle(&ipc, h->peer_own));
+    memcpy(handle, &ipc, 64);
+    return B2_OK;
+}
+
+int b2_gicp_set_peers(b2_gicp_t h, int rank, int world, const unsigned char* handles) {
+    if (!h || !handles || world < 2 || world > GICP_MAX_WORLD || rank < 0 || rank >= world) { set_error("b2_gicp_set_peers: bad argument"); return B2_ERR_ARG; }
+    if (!h->peer_own) { set_error("b2_gicp_set_peers: call b2_gicp_peer_handle first"); return B2_ERR_STATE; }
+    B2_CUDA(cudaSetDevice(h->device));
+    h->peer_world = 0;
+    for (int p = 0; p < world; p++) {
+        if (p == rank) { h->peer_ptr[p] = h->peer_own; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, handles + 64 * (size_t)p, 64);
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("b2_gicp_set_peers: rank %d cannot map rank %d's exchange area (%s); the NCCL all-reduce stays in use", rank, p, cudaGetErrorString(e));
+            return B2_ERR_CUDA;
+        }
+        h->peer_ptr[p] = static_cast<GicpPeerArea*>(ptr);
+    }
+    h->peer_rank = rank; h->peer_world = world; h->peer_seq = 0;
+    return B2_OK;
+}
+
 int b2_gicp_linearize(b2_gicp_t h, const double T[16], double sums[30], int32_t* corr) {
     B2_NVTX("b2_gicp_linearize");
     if (!h || !T || !sums) return B2_ERR_ARG;
@@ -525,7 +612,9 @@ int b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* 
     const int max_it = std::max(0, h->prm.max_iteration);
     B2_CHECK(gicp_upload_state(h, init, max_it));
     GicpArgs a;
-    gicp_fill_args(h, a, h->comm ? 0 : 1, nullptr);
+    const bool fused = h->comm && h->peer_world == h->world && h->world > 1;
+    gicp_fill_args(h, a, fused ? 2 : (h->comm ? 0 : 1), nullptr);
+    if (fused) h->peer_seq += (unsigned)max_it + 2u;      // every rank advances alike (same parameters on all ranks)
     // the last correspondence of every source point seeds its next search (from the second evaluation on)
     if (h->src_valid && !getenv("B2_GICP_NO_SEED")) {
         const size_t slots = ((size_t)h->src_valid + 31) / 32 * 32;
@@ -549,7 +638,7 @@ int b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* 
         for (int i = 0; i < m; i++) {
             k_gicp_linearize<<<h->grid_blocks, GICP_THREADS, 0, h->stream>>>(a); launches++;
             if (h->ev_used + 1 < (int)h->ev.size()) { h->ev_used++; B2_CUDA(cudaEventRecord(h->ev[h->ev_used], h->stream)); }
-            if (h->comm) {
+            if (h->comm && !fused) {
                 B2_CHECK(comm_allreduce_sum_f64(h->comm, ds->sums_local, ds->sums, GICP_NSUM, h->stream));
                 k_gicp_finalize<<<1, 32, 0, h->stream>>>(ds); launches++;
             }

@@ -265,6 +265,22 @@ class GeneralizedICP:
         else:
             capi.check(capi.lib().b2_gicp_set_shard(self._h, comm.rank, comm.world, comm._h))
 
+    def peerHandle(self):
+        """CUDA IPC handle (64 bytes) of this rank's exchange area; gather them over the ranks and pass them to setPeers."""
+        h = np.zeros(64, np.uint8)
+        capi.check(capi.lib().b2_gicp_peer_handle(self._h, capi.ptr(h)))
+        return h.tobytes()
+
+    def setPeers(self, rank, world, handles):
+        """handles: the peerHandle() bytes of all ranks in rank order. Returns False (and keeps the NCCL all-reduce) when the
+        GPUs cannot map each other's memory."""
+        buf = np.frombuffer(b"".join(handles), np.uint8).copy()
+        try:
+            capi.check(capi.lib().b2_gicp_set_peers(self._h, int(rank), int(world), capi.ptr(buf)))
+            return True
+        except capi.B2Error:
+            return False
+
     def linearize(self, T, want_correspondences=False):
         T = np.ascontiguousarray(T, dtype=np.float64)
         sums = np.zeros(30, np.float64)

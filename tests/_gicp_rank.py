@@ -41,9 +41,16 @@ def main():
     g2.setInputSourceSlice(s2, b, e)
     g2.setShard(comm)
     r2 = g2.align(d["init"], want_correspondences=False)
+    # the same with the exchange fused into the kernel (peer stores over NVLink instead of ncclAllReduce + an epilogue launch)
+    hs = [None] * world
+    dist.all_gather_object(hs, g2.peerHandle())
+    fused = g2.setPeers(rank, world, hs)
+    r3 = g2.align(d["init"], want_correspondences=False) if fused else r2
+    r4 = g2.align(d["init"], want_correspondences=False) if fused else r2        # a second align on the same handle (sequence numbers go on)
     json.dump({"T": r.transformation.tolist(), "iterations": r.iterations, "fitness": r.fitness, "rmse": r.inlier_rmse,
                "pts_equal": pts_equal, "nrm_equal": nrm_equal, "T2": r2.transformation.tolist(), "iterations2": r2.iterations,
-               "fitness2": r2.fitness, "slice": [b, e]},
+               "fitness2": r2.fitness, "slice": [b, e],
+               "fused": bool(fused), "T3": r3.transformation.tolist(), "iterations3": r3.iterations, "T4": r4.transformation.tolist()},
               open(os.path.join(work, f"rank{rank}.json"), "w"))
     dist.barrier()
     dist.destroy_process_group()
