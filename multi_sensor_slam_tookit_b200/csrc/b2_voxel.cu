@@ -124,87 +124,6 @@ __global__ void __launch_bounds__(128) k_vx_centroid(const unsigned char* __rest
 }
 
 
-// ------------------------------------------------------------------------------------------------ dense (counting) path
-// When the voxel lattice of the bounding box is small enough to keep one counter per cell (the local-map filters: a 170 m box
-// at 0.4 m is 11 M cells), the radix sort of (voxel, index) pairs — four passes of four launches at a million points — is replaced
-// by a counting sort: count per cell | prefix sum | scatter (order inside a cell = whatever the atomics gave) | one thread per
-// occupied cell puts its few indices in ascending order (the summation order the oracle pins) and averages. Same results bit for
-// bit; the sort path remains for lattices that are too large and for cells holding more than VXD_MAX_RUN points.
-constexpr uint32_t VXD_MAX_RUN = 192;
-constexpr uint64_t VXD_MAX_CELLS = (uint64_t)24 << 20;
-
-__global__ void __launch_bounds__(256) k_vxd_count(const unsigned char* __restrict__ raw, size_t stride, uint32_t n, VoxelGeom g,
-                                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ cnt, uint32_t* __restrict__ max_run,
-                                                   int32_t* __restrict__ vop) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t mine = 0;
-    if (i < n) {
-        const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
-        const float x = p[0], y = p[1], z = p[2];
-        uint32_t key = g.invalid_key;
-        int32_t v = -1;
-        if (isfinite(x) && isfinite(y) && isfinite(z)) {
-            const int i0 = (int)(floorf(x * g.inv[0]) - (float)g.min_b[0]);
-            const int i1 = (int)(floorf(y * g.inv[1]) - (float)g.min_b[1]);
-            const int i2 = (int)(floorf(z * g.inv[2]) - (float)g.min_b[2]);
-            v = i0 * g.mul[0] + i1 * g.mul[1] + i2 * g.mul[2];
-            key = (uint32_t)v;
-        }
-        keys[i] = key;
-        if (vop) vop[i] = v;
-        const uint32_t before = atomicAdd(&cnt[key], 1u);
-        if (key != g.invalid_key) mine = before + 1u;
-    }
-    mine = __reduce_max_sync(0xffffffffu, mine);
-    if ((threadIdx.x & 31) == 0 && mine > 1u) atomicMax(max_run, mine);
-}
-
-// keep[v] = 1 for cells whose count reaches max(min_pts, 1); keep[ncells] = keep[ncells + 1] = 0
-__global__ void __launch_bounds__(256) k_vxd_keep(const uint32_t* __restrict__ cnt, uint32_t ncells, uint32_t min_pts, uint32_t* __restrict__ keep) {
-    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v > ncells + 1u) return;
-    keep[v] = (v < ncells && cnt[v] >= (min_pts > 1u ? min_pts : 1u)) ? 1u : 0u;
-}
-
-// cursor[] enters as the exclusive prefix of the counts and leaves as the END of every cell's run
-__global__ void __launch_bounds__(256) k_vxd_scatter(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ cursor, uint32_t* __restrict__ order) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    order[atomicAdd(&cursor[keys[i]], 1u)] = i;
-}
-
-__global__ void __launch_bounds__(128) k_vxd_centroid(const unsigned char* __restrict__ raw, size_t stride, int ioff, int n_fields,
-                                                      uint32_t* __restrict__ order, const uint32_t* __restrict__ run_end, const uint32_t* __restrict__ keep_scan,
-                                                      uint32_t ncells, uint32_t out_cap, unsigned char* __restrict__ out, size_t ostride, int ooff) {
-    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= ncells) return;
-    const uint32_t rank = keep_scan[v];
-    if (keep_scan[v + 1] == rank || rank >= out_cap) return;
-    const uint32_t e = run_end[v], b = v ? run_end[v - 1] : 0u;
-    // ascending input index: insertion sort of the run, in place (runs are a handful of points; the host sent anything longer
-    // than VXD_MAX_RUN down the sort path)
-    for (uint32_t i = b + 1; i < e; i++) {
-        const uint32_t x = order[i];
-        uint32_t j = i;
-        while (j > b && order[j - 1] > x) { order[j] = order[j - 1]; j--; }
-        order[j] = x;
-    }
-    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    for (uint32_t i = b; i < e; i++) {
-        const unsigned char* p = raw + (size_t)order[i] * stride;
-        const float* f = reinterpret_cast<const float*>(p);
-        sx += f[0]; sy += f[1]; sz += f[2];
-        if (n_fields == 4) si += *reinterpret_cast<const float*>(p + ioff);
-    }
-    const float cnt = (float)(e - b);
-    float* of = reinterpret_cast<float*>(out + (size_t)rank * ostride);
-    const int words = (int)(ostride >> 2);
-    for (int w = 3; w < words; w++) of[w] = 0.f;
-    of[0] = sx / cnt; of[1] = sy / cnt; of[2] = sz / cnt;
-    if (words >= 4 && !(n_fields == 4 && ooff == 12)) of[3] = 1.0f;          // PCL's homogeneous pad word
-    if (n_fields == 4) of[ooff >> 2] = si / cnt;
-}
-
 }  // namespace b2
 
 using namespace b2;
@@ -319,46 +238,6 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
     while (bits < 32 && ((uint64_t)1 << bits) <= ncells) bits++;
 
 
-    // ---- dense counting path (see k_vxd_count)
-    static const bool no_dense = getenv("B2_VOXEL_NO_DENSE") != nullptr;
-    if (!no_dense && ncells <= VXD_MAX_CELLS && ncells <= (uint64_t)64 * n + 65536) {
-        const uint32_t nc = (uint32_t)ncells;
-        const size_t tab = ((size_t)nc + 2 + 63) & ~(size_t)63;
-        const size_t nal2 = (n + 63) & ~(size_t)63;
-        const size_t scr = scan_tmp_bytes(tab) + 1024;
-        B2_CHECK(h->work.reserve((2 * nal2 + 2 * tab + 64) * sizeof(uint32_t) + scr));
-        uint32_t* keys = h->work.as<uint32_t>();
-        uint32_t* order = keys + nal2;
-        uint32_t* cnt = order + nal2;                 // counts -> prefix -> run ends
-        uint32_t* keepv = cnt + tab;
-        uint32_t* max_run = keepv + tab;
-        char* scratch2 = reinterpret_cast<char*>(max_run + 64);
-        B2_CUDA(cudaMemsetAsync(cnt, 0, (tab + tab + 64) * sizeof(uint32_t), s));
-        const uint32_t n32d = (uint32_t)n;
-        k_vxd_count<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_in, in_stride, n32d, g, keys, cnt, max_run, d_vop); count_launch();
-        B2_CUDA(cudaGetLastError());
-        uint32_t* hmx = h->pin.as<uint32_t>() + 12;
-        B2_CUDA(cudaMemcpyAsync(hmx, max_run, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        k_vxd_keep<<<(nc + 2 + 255) / 256, 256, 0, s>>>(cnt, nc, h->min_pts, keepv); count_launch();
-        B2_CHECK(exclusive_scan_u32(cnt, (size_t)nc + 2, scratch2, s));
-        B2_CHECK(exclusive_scan_u32(keepv, (size_t)nc + 2, scratch2, s));
-        B2_CUDA(cudaStreamSynchronize(s));
-        if (*hmx <= VXD_MAX_RUN) {
-            k_vxd_scatter<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(keys, n32d, cnt, order); count_launch();
-            const size_t cap = std::min(n, out_capacity);
-            B2_CHECK(h->out.reserve(std::max<size_t>(cap, 1) * out_stride));
-            k_vxd_centroid<<<(nc + 127) / 128, 128, 0, s>>>(d_in, in_stride, ioff, n_fields, order, cnt, keepv, nc, (uint32_t)cap,
-                                                             h->out.as<unsigned char>(), out_stride, ooff); count_launch();
-            B2_CUDA(cudaGetLastError());
-            uint32_t* hm2 = h->pin.as<uint32_t>() + 8;
-            B2_CUDA(cudaMemcpyAsync(hm2, keepv + nc, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-            B2_CUDA(cudaStreamSynchronize(s));
-            if ((size_t)*hm2 > out_capacity) { set_error("b2_voxel_filter: %u voxels but out_capacity %zu", *hm2, out_capacity); return B2_ERR_CAPACITY; }
-            *m_out = *hm2;
-            return B2_OK;
-        }
-        // a crowded cell: fall through to the sort path (d_vop is already filled and stays valid)
-    }
     const size_t nal = (n + 64) & ~(size_t)63;       // room for n+1 entries
     const size_t scratch_bytes = std::max(sort_tmp_bytes(n), scan_tmp_bytes(n + 1)) + 1024;
     B2_CHECK(h->work.reserve(7 * nal * sizeof(uint32_t) + scratch_bytes));
