@@ -715,10 +715,10 @@ int estimate_normals_knn(b2_cloud_s* c, int knn, b2_comm_s* comm) {
     const size_t n = c->n;
     B2_CHECK(c->nrm.reserve(n * 24));
     k_fill_normals<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(c->nrm.as<double>(), (uint32_t)n); count_launch();
-    BvhIndex bvh;
+    BvhIndex& bvh = c->bvh;              // (a previous call's kernel has finished: bvh.build synchronises the stream for its bounding box)
+    DevBuf& gathered = c->gathered;
     int st = bvh.build(c->xyz.as<double>(), n, c->work, s);
     cudaError_t e = cudaSuccess;
-    DevBuf gathered;
     if (st == B2_OK && bvh.dev.n && comm && comm->world > 1) {
         // Sharded set-up (config C5): every rank holds the whole cloud and the same BVH (the neighbourhood of a point may reach
         // anywhere), but serves only its contiguous range of leaves; the ranges are exchanged with one all-gather over NVLink
@@ -741,8 +741,7 @@ int estimate_normals_knn(b2_cloud_s* c, int knn, b2_comm_s* comm) {
         k_normals<<<(bvh.dev.count[0] + NRM_WARPS - 1) / NRM_WARPS, NRM_WARPS * 32, 0, s>>>(bvh.dev, knn, c->nrm.as<double>(), 0u, bvh.dev.count[0], 0); count_launch();
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    bvh.release(); gathered.release();
+    // no synchronisation here: the search is left running (see b2_cloud_s); a fault shows up at the consumer's synchronisation
     if (st != B2_OK) return st;
     if (e != cudaSuccess) { set_error("estimate_normals: %s", cudaGetErrorString(e)); return B2_ERR_CUDA; }
     c->has_normals = true;
@@ -794,7 +793,9 @@ int b2_cloud_create(b2_cloud_t* out) {
 
 int b2_cloud_destroy(b2_cloud_t c) {
     if (!c) return B2_OK;
-    c->xyz.release(); c->nrm.release(); c->work.release(); c->pin.release();
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    c->xyz.release(); c->nrm.release(); c->work.release(); c->pin.release(); c->bvh.release(); c->gathered.release();
+    if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return B2_OK;
@@ -874,6 +875,7 @@ int b2_cloud_voxel_down_sample(b2_cloud_t c, double voxel_size, b2_cloud_t* out,
     const int st = voxel_down_sample(c, voxel_size, o, voxel_rank_of_point);
     cudaEventRecord(e1, c->stream); cudaEventSynchronize(e1);
     cudaEventElapsedTime(&c->last_ms, e0, e1);
+    c->ms_pending = false;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (st != B2_OK) { b2_cloud_destroy(o); return st; }
     *out = o;
@@ -884,13 +886,11 @@ int b2_cloud_estimate_normals(b2_cloud_t c, int knn) {
     B2_NVTX("b2_cloud_estimate_normals");
     if (!c) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(c->device));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, c->stream);
+    if (!c->ev0) { B2_CUDA(cudaEventCreate(&c->ev0)); B2_CUDA(cudaEventCreate(&c->ev1)); }
+    B2_CUDA(cudaEventRecord(c->ev0, c->stream));
     const int st = estimate_normals_knn(c, knn, nullptr);
-    cudaEventRecord(e1, c->stream); cudaEventSynchronize(e1);
-    cudaEventElapsedTime(&c->last_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    B2_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ms_pending = true;                  // b2_cloud_last_gpu_ms waits for the events; this call does not
     return st;
 }
 
@@ -901,13 +901,11 @@ int b2_cloud_estimate_normals_sharded(b2_cloud_t c, int knn, b2_comm_t comm) {
     B2_NVTX("b2_cloud_estimate_normals_sharded");
     if (!c) return B2_ERR_ARG;
     B2_CUDA(cudaSetDevice(c->device));
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0); cudaEventCreate(&e1);
-    cudaEventRecord(e0, c->stream);
+    if (!c->ev0) { B2_CUDA(cudaEventCreate(&c->ev0)); B2_CUDA(cudaEventCreate(&c->ev1)); }
+    B2_CUDA(cudaEventRecord(c->ev0, c->stream));
     const int st = estimate_normals_knn(c, knn, comm);
-    cudaEventRecord(e1, c->stream); cudaEventSynchronize(e1);
-    cudaEventElapsedTime(&c->last_ms, e0, e1);
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    B2_CUDA(cudaEventRecord(c->ev1, c->stream));
+    c->ms_pending = true;                  // b2_cloud_last_gpu_ms waits for the events; this call does not
     return st;
 }
 
@@ -944,6 +942,11 @@ int b2_cloud_transform(b2_cloud_t c, const double T[16]) {
 
 int b2_cloud_last_gpu_ms(b2_cloud_t c, float* ms) {
     if (!c || !ms) return B2_ERR_ARG;
+    if (c->ms_pending) {
+        B2_CUDA(cudaEventSynchronize(c->ev1));
+        B2_CUDA(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+        c->ms_pending = false;
+    }
     *ms = c->last_ms;
     return B2_OK;
 }

@@ -6,6 +6,7 @@
 #include "b2_common.cuh"
 #include "b2_comm.cuh"
 #include "b2_gridd.cuh"
+#include "b2_bvh.cuh"
 
 struct b2_cloud_s {
     int device = 0;
@@ -17,6 +18,13 @@ struct b2_cloud_s {
     b2::DevBuf work;           // scratch for downsampling
     b2::PinBuf pin;
     float last_ms = 0.f;
+    // estimate_normals leaves its search kernel queued on `stream` (everything that consumes the normals is ordered behind it on
+    // the same stream or synchronises it): the two clouds of a registration pair are two single-wave launches that overlap
+    // instead of running back to back. The BVH and the event pair therefore outlive the call.
+    b2::BvhIndex bvh;
+    b2::DevBuf gathered;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ms_pending = false;
 };
 
 namespace b2 {
