@@ -74,6 +74,7 @@ struct S2MState {                 // one per scan in the batch, lives in HBM
     int ran;                      // 0 when n_sel < min_correspondences
     unsigned ticket;
     int grid_status;              // status words of the two device-sized map grids (0, or B2_ERR_TOO_LARGE: rebuild on the host path)
+    long long tl[8];              // %globaltimer stamps of a persistent solve: [0] first CTA in, [1 + k] end of iteration k (k < 6), [7] result written
 };
 
 struct S2MInit {                  // initial state of a single-scan solve, carried by the first launch's arguments
@@ -359,6 +360,7 @@ k_s2m_iteration(const S2MArgs a) {
     const int scan = blockIdx.y;
     S2MState& st = a.st[scan];
     bool first = a.use_init != 0;                              // the state is in the launch arguments, not in memory yet
+    if (first && a.persistent_iters > 0 && blockIdx.x == 0 && threadIdx.x == 0) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); st.tl[0] = gt; }
     if (!first && st.done) return;                             // uniform per CTA, written only by a previous launch
     if (first) {
         // a map that outgrew its device-sized cell table has no usable geometry: report it and let the host rebuild (the
@@ -673,6 +675,7 @@ k_s2m_iteration(const S2MArgs a) {
         const int iterCount = a.iter >= 0 ? a.iter : __ldcg(&st.iters);
         lm_epilogue(st, s_sum, iterCount, a, scan, prof);
         if (prof) { prof[5] = clock64(); long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); prof[7] = gt; }
+        if (a.persistent_iters > 0 && pit < 6) { long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); st.tl[1 + pit] = gt; }
     }
     // single-scan solves: the state goes straight to mapped host memory when the loop ends or the chunk does, followed by the
     // sequence number the host spins on (no copy, no stream synchronisation on the critical path)
@@ -1463,6 +1466,11 @@ static int run_solve(b2_s2m_s* h, float* poses, int max_iterations, int* iters_d
                     0.0, h->tl_host[1] - t0, h->tl_host[2] - t0, h->tl_host[3] - t0, h->tl_host[4] - t0, h->tl_host[5] - t0,
                     rel(h->gc.tl_ev[1]), rel(h->gc.tl_ev[3]), rel(h->gs.tl_ev[0]), rel(h->gs.tl_ev[1]), rel(h->gs.tl_ev[3]), rel(h->tl_scan),
                     rel(h->ev0), rel(h->ev1));
+            {
+                const S2MState* r = h->h_result;
+                fprintf(stderr, "[b2 timeline us] solve kernel (device clock): first CTA -> end of iteration 1 / 2 / 3: %.1f / %.1f / %.1f; events ev0 -> ev1 %.1f\n",
+                        (r->tl[1] - r->tl[0]) * 1e-3, (r->tl[2] - r->tl[0]) * 1e-3, (r->tl[3] - r->tl[0]) * 1e-3, rel(h->ev1) - rel(h->ev0));
+            }
             GridDevMem gm[2];
             cudaMemcpy(&gm[0], h->gc.dev_ptr(), sizeof(GridDevMem), cudaMemcpyDeviceToHost);
             cudaMemcpy(&gm[1], h->gs.dev_ptr(), sizeof(GridDevMem), cudaMemcpyDeviceToHost);

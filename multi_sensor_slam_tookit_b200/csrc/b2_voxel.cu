@@ -35,10 +35,21 @@ __global__ void __launch_bounds__(256) k_vx_bbox(const unsigned char* __restrict
             mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
             mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
         }
-    if ((threadIdx.x & 31) == 0)
+    // six atomics per CTA, not per warp (thousands of warps queueing on six words: 43 us of a 266 us filter at a million points)
+    __shared__ float s_mn[8][3], s_mx[8][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
 #pragma unroll
-        for (int d = 0; d < 3; d++)
-            if (mn[d] <= mx[d]) { atomicMin(&bb[d], float_flip(mn[d])); atomicMax(&bb[3 + d], float_flip(mx[d])); }
+        for (int d = 0; d < 3; d++) { s_mn[warp][d] = mn[d]; s_mx[warp][d] = mx[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int d = threadIdx.x;
+        float a = s_mn[0][d], b = s_mx[0][d];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) { a = fminf(a, s_mn[w][d]); b = fmaxf(b, s_mx[w][d]); }
+        if (a <= b) { atomicMin(&bb[d], float_flip(a)); atomicMax(&bb[3 + d], float_flip(b)); }
+    }
+}
 }
 
 struct VoxelGeom { float inv[3]; int min_b[3]; int mul[3]; uint32_t invalid_key; };
@@ -190,7 +201,7 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
     B2_CHECK(h->small.reserve(256));
     uint32_t* bb = h->small.as<uint32_t>();
     k_vx_bbox_init<<<1, 32, 0, s>>>(bb); count_launch();
-    const int nbb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 8);
+    const int nbb = (int)std::min<size_t>((n + 255) / 256, (size_t)device_sm_count() * 4);
     k_vx_bbox<<<nbb, 256, 0, s>>>(d_in, in_stride, n, bb); count_launch();
     B2_CUDA(cudaGetLastError());
     B2_CHECK(h->pin.reserve(64));
