@@ -289,6 +289,23 @@ __device__ __forceinline__ void suppress(int ind, int M, const int* __restrict__
     }
 }
 
+// The same for a whole warp walking one candidate: lanes 0-4 look at ind+1..ind+5, lanes 5-9 at ind-1..ind-5; the "stop at the first
+// column gap" of the two loops is the lowest set bit of a ballot. All lanes pass the same ind. Ends with a warp barrier so the
+// next candidate's picked test sees the marks.
+__device__ __forceinline__ void suppress_warp(int ind, int M, const int* col, int* picked, int lane) {
+    const bool up = lane < 5, down = lane >= 5 && lane < 10;
+    const int l = up ? lane + 1 : -(lane - 4);
+    bool stop = false;
+    if (up) stop = (ind + l >= M) || abs(col[min(ind + l, M - 1)] - col[min(ind + l, M - 1) - 1]) > 10;
+    if (down) stop = (ind + l < 0) || abs(col[max(ind + l, 0)] - col[max(ind + l, 0) + 1]) > 10;
+    const unsigned b = __ballot_sync(0xffffffffu, stop);
+    const unsigned bu = b & 0x1fu, bd = (b >> 5) & 0x1fu;
+    const int first_up = bu ? __ffs(bu) - 1 : 5, first_down = bd ? __ffs(bd) - 1 : 5;      // offsets 1..first are marked
+    if (up && lane < first_up) picked[ind + l] = 1;
+    if (down && (lane - 5) < first_down) picked[ind + l] = 1;
+    __syncwarp();
+}
+
 // extractFeatures: one CTA per ring. Dynamic shared memory: keys[P] (u64), pts[P] (float4) with P = pow2 >= H.
 // Per-ring outputs go to fixed-capacity slots (corner: 120 per ring, surf: H per ring) and are concatenated afterwards.
 __global__ void __launch_bounds__(256) k_scan_features(const float4* __restrict__ extracted, const int* __restrict__ col, const int* __restrict__ total,
@@ -343,9 +360,10 @@ __global__ void __launch_bounds__(256) k_scan_features(const float4* __restrict_
             keys[t] = key;
         }
         bitonic_sort_u64(keys, Q);
-        if (threadIdx.x == 0) {
-            // descending: at most 20 corners with curvature > edgeThreshold (:165-195). The sorted part is descending
-            // in curvature, so the first candidate at or below the threshold ends the walk (nothing later can pass).
+        if (warp == 0) {
+            // One warp walks the sector (every lane runs the same control flow on the same shared-memory words; the +-5 suppression is
+            // spread over ten lanes). descending: at most 20 corners with curvature > edgeThreshold (:165-195). The sorted part is
+            // descending in curvature, so the first candidate at or below the threshold ends the walk (nothing later can pass).
             int largestPickedNum = 0;
             int nc = s_ncorner;
             for (int k = ep; k >= sp; k--) {
@@ -354,24 +372,25 @@ __global__ void __launch_bounds__(256) k_scan_features(const float4* __restrict_
                 if (k != ep && !(cv > s.edge_th)) break;
                 if (picked_l[ind] == 0 && cv > s.edge_th) {
                     largestPickedNum++;
-                    if (largestPickedNum <= 20) { label_l[ind] = 1; corner_idx[ring * 120 + nc++] = ind; }
+                    if (largestPickedNum <= 20) { if (lane == 0) { label_l[ind] = 1; corner_idx[ring * 120 + nc] = ind; } nc++; }
                     else break;
-                    picked_l[ind] = 1;
-                    suppress(ind, M, col_l, picked_l);
+                    if (lane == 0) picked_l[ind] = 1;
+                    suppress_warp(ind, M, col_l, picked_l, lane);
                 }
             }
-            s_ncorner = nc;
+            __syncwarp();
+            if (lane == 0) s_ncorner = nc;
             // ascending: surf labels (:197-225); ep is visited last
             for (int k = sp; k <= ep; k++) {
                 const int ind = (k == ep) ? ep : (int)(unsigned)keys[k - sp];
                 const float cv = curv_l[ind];
                 if (k != ep && !(cv < s.surf_th)) { k = ep - 1; continue; }     // jump to the unsorted tail element
                 if (picked_l[ind] == 0 && cv < s.surf_th) {
-                    label_l[ind] = -1;
-                    picked_l[ind] = 1;
-                    suppress(ind, M, col_l, picked_l);
+                    if (lane == 0) { label_l[ind] = -1; picked_l[ind] = 1; }
+                    suppress_warp(ind, M, col_l, picked_l, lane);
                 }
             }
+            __syncwarp();
         }
         __syncthreads();
         // surf candidates of the sector, in index order (:227-232)

@@ -50,7 +50,6 @@ __global__ void __launch_bounds__(256) k_vx_bbox(const unsigned char* __restrict
         if (a <= b) { atomicMin(&bb[d], float_flip(a)); atomicMax(&bb[3 + d], float_flip(b)); }
     }
 }
-}
 
 struct VoxelGeom { float inv[3]; int min_b[3]; int mul[3]; uint32_t invalid_key; };
 
