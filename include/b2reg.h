@@ -310,6 +310,9 @@ int  b2_gicp_set_source(b2_gicp_t h, b2_cloud_t source);
 /* sharded registration: index only rows [begin, end) of the source on this rank (all of them are processed here; the sums are
  * all-reduced over the communicator of b2_gicp_set_shard, the fitness refers to the whole cloud) */
 int  b2_gicp_set_source_slice(b2_gicp_t h, b2_cloud_t source, size_t begin, size_t end);
+/* the same with spatially dense shards: blocks of 4096 consecutive points of the cloud's Morton order (left by estimate_normals),
+ * block b on rank b mod world. The preferred deal for large registrations (better locality than row slices of a shuffled cloud). */
+int  b2_gicp_set_source_blocks(b2_gicp_t h, b2_cloud_t source, int rank, int world);
 /* Source sharding for one registration spread over `world` GPUs: the (cell-sorted) source is dealt to the ranks in
  * blocks of 4096 consecutive points, round-robin (block b belongs to rank b mod world), so every rank sees the same
  * mix of easy and hard regions; the 30 sums are all-reduced over `comm` every iteration and every rank solves the same

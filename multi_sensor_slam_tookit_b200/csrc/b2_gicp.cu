@@ -306,7 +306,7 @@ struct b2_gicp_s {
     cudaStream_t stream = nullptr;
     b2_gicp_params prm{};
     GridD tgt_grid, tgt_coarse, src_grid;
-    DevBuf tgt_m, src_m, partials, state, corr, tgt_xyz, fine_pos_of, prev;
+    DevBuf tgt_m, src_m, partials, state, corr, tgt_xyz, fine_pos_of, prev, sub_xyz, sub_nrm;
     double coarse_for = -1.0;        // max_correspondence_distance the coarse grid was built for (< 0: none)
     bool have_coarse = false;
     int blocks_per_sm = GICP_MIN_BLOCKS;
@@ -438,7 +438,7 @@ int b2_gicp_create(b2_gicp_t* out, const b2_gicp_params* params) {
 int b2_gicp_destroy(b2_gicp_t h) {
     if (!h) return B2_OK;
     h->tgt_grid.release(); h->tgt_coarse.release(); h->src_grid.release(); h->tgt_xyz.release(); h->fine_pos_of.release();
-    h->tgt_m.release(); h->src_m.release(); h->partials.release(); h->state.release(); h->corr.release(); h->prev.release(); h->pin.release();
+    h->sub_xyz.release(); h->sub_nrm.release(); h->tgt_m.release(); h->src_m.release(); h->partials.release(); h->state.release(); h->corr.release(); h->prev.release(); h->pin.release();
     for (int p = 0; p < GICP_MAX_WORLD; p++)
         if (h->peer_ptr[p] && h->peer_ptr[p] != h->peer_own) cudaIpcCloseMemHandle(h->peer_ptr[p]);
     if (h->peer_own) cudaFree(h->peer_own);
@@ -456,6 +456,18 @@ int b2_gicp_set_params(b2_gicp_t h, const b2_gicp_params* p) {
     return B2_OK;
 }
 
+static int gicp_index_points(b2_gicp_s* h, const double* d_xyz, const double* d_nrm, size_t n, GridD& grid, DevBuf& m, double ppc, uint32_t* n_valid) {
+    B2_CHECK(grid.build(d_xyz, n, 0.0, ppc, h->stream));
+    B2_CHECK(gicp_valid_count(grid, h->stream, n_valid));
+    B2_CHECK(m.reserve(std::max<size_t>(n, 1) * 24));
+    if (*n_valid) {
+        k_gicp_eff_normals<<<(*n_valid + 255) / 256, 256, 0, h->stream>>>(grid.dev.pts, d_nrm, *n_valid, m.as<double>()); count_launch();
+        B2_CUDA(cudaGetLastError());
+    }
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    return B2_OK;
+}
+
 static int gicp_set_cloud(b2_gicp_s* h, b2_cloud_s* c, GridD& grid, DevBuf& m, double ppc, uint32_t* n_valid, size_t begin = 0, size_t end = (size_t)-1) {
     end = std::min(end, c->n); begin = std::min(begin, end);
     if (!c->has_normals) {
@@ -465,15 +477,22 @@ static int gicp_set_cloud(b2_gicp_s* h, b2_cloud_s* c, GridD& grid, DevBuf& m, d
     B2_CUDA(cudaSetDevice(h->device));
     B2_CUDA(cudaStreamSynchronize(c->stream));
     // [begin, end): the rows this handle indexes (a rank's slice of a sharded source); grid indices are relative to `begin`
-    B2_CHECK(grid.build(c->xyz.as<double>() + 3 * begin, end - begin, 0.0, ppc, h->stream));
-    B2_CHECK(gicp_valid_count(grid, h->stream, n_valid));
-    B2_CHECK(m.reserve(std::max<size_t>(end - begin, 1) * 24));
-    if (*n_valid) {
-        k_gicp_eff_normals<<<(*n_valid + 255) / 256, 256, 0, h->stream>>>(grid.dev.pts, c->nrm.as<double>() + 3 * begin, *n_valid, m.as<double>()); count_launch();
-        B2_CUDA(cudaGetLastError());
-    }
-    B2_CUDA(cudaStreamSynchronize(h->stream));
-    return B2_OK;
+    return gicp_index_points(h, c->xyz.as<double>() + 3 * begin, c->nrm.as<double>() + 3 * begin, end - begin, grid, m, ppc, n_valid);
+}
+
+// this rank's blocks of GICP_SHARD_CHUNKS * 32 consecutive points of the cloud's Morton order (block b -> rank b mod world), with
+// their normals: spatially dense pieces spread evenly over the scene
+__global__ void __launch_bounds__(256) k_gicp_take_blocks(const P4d* __restrict__ morton, uint32_t n, const double* __restrict__ nrm, int rank, int world,
+                                                          uint32_t m, double* __restrict__ xyz_out, double* __restrict__ nrm_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t B = GICP_SHARD_CHUNKS * 32u;
+    const uint32_t pos = ((i / B) * (uint32_t)world + (uint32_t)rank) * B + (i % B);
+    if (pos >= n) return;                       // (cannot happen: m counts only existing points)
+    double x, y, z; long long id;
+    load_p4d(&morton[pos], x, y, z, id);
+    xyz_out[3 * (size_t)i] = x; xyz_out[3 * (size_t)i + 1] = y; xyz_out[3 * (size_t)i + 2] = z;
+    nrm_out[3 * (size_t)i] = nrm[3 * (size_t)id]; nrm_out[3 * (size_t)i + 1] = nrm[3 * (size_t)id + 1]; nrm_out[3 * (size_t)i + 2] = nrm[3 * (size_t)id + 2];
 }
 
 int b2_gicp_set_target(b2_gicp_t h, b2_cloud_t target) {
@@ -526,6 +545,42 @@ int b2_gicp_set_source_slice(b2_gicp_t h, b2_cloud_t source, size_t begin, size_
     static const double sppc = [] { const char* e = getenv("B2_GICP_TARGET_PPC"); double v = e ? atof(e) : 2.0; return v > 0 ? v : 2.0; }();
     B2_CHECK(gicp_set_cloud(h, source, h->src_grid, h->src_m, sppc, &nv, begin, end));
     h->n_src = source->n;                      // fitness = correspondences / all source points
+    h->src_valid = nv;
+    h->src_slice = true;
+    h->have_src = true;
+    return B2_OK;
+}
+
+// Sharded registration, spatially dense shards: the source is dealt to the ranks in blocks of 4096 consecutive points of its
+// Morton order (the BVH estimate_normals left in the cloud), block b -> rank b mod world; this rank copies its blocks out and
+// indexes only them. Dense blocks keep the target accesses of a warp inside a few cells (row slices of a randomly ordered cloud
+// thin every shard out to 1/world of the density: measured 0.86 ms per steady evaluation at 8 GPUs against 0.63 ms), the
+// round-robin deal keeps the ranks balanced, and the source sort shrinks with the number of ranks.
+int b2_gicp_set_source_blocks(b2_gicp_t h, b2_cloud_t source, int rank, int world) {
+    B2_NVTX("b2_gicp_set_source_blocks");
+    if (!h || !source || world < 1 || rank < 0 || rank >= world) return B2_ERR_ARG;
+    if (!source->has_normals || source->bvh.dev.n == 0 || source->bvh.dev.n > source->n) {
+        set_error("b2_gicp_set_source_blocks: the cloud needs normals from b2_cloud_estimate_normals[_sharded] (its Morton order is reused)");
+        return B2_ERR_STATE;
+    }
+    B2_CUDA(cudaSetDevice(h->device));
+    B2_CUDA(cudaStreamSynchronize(source->stream));
+    h->have_src = false;
+    const uint32_t n = source->bvh.dev.n, B = GICP_SHARD_CHUNKS * 32u;
+    const uint32_t nblocks = (n + B - 1) / B;
+    uint64_t m = 0;
+    for (uint32_t b = (uint32_t)rank; b < nblocks; b += (uint32_t)world) m += std::min<uint64_t>(B, (uint64_t)n - (uint64_t)b * B);
+    B2_CHECK(h->sub_xyz.reserve(std::max<uint64_t>(m, 1) * 24));
+    B2_CHECK(h->sub_nrm.reserve(std::max<uint64_t>(m, 1) * 24));
+    if (m) {
+        k_gicp_take_blocks<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(source->bvh.dev.pts, n, source->nrm.as<double>(), rank, world, (uint32_t)m,
+                                                                               h->sub_xyz.as<double>(), h->sub_nrm.as<double>()); count_launch();
+        B2_CUDA(cudaGetLastError());
+    }
+    uint32_t nv = 0;
+    static const double sppc = [] { const char* e = getenv("B2_GICP_TARGET_PPC"); double v = e ? atof(e) : 2.0; return v > 0 ? v : 2.0; }();
+    B2_CHECK(gicp_index_points(h, h->sub_xyz.as<double>(), h->sub_nrm.as<double>(), (size_t)m, h->src_grid, h->src_m, sppc, &nv));
+    h->n_src = source->n;
     h->src_valid = nv;
     h->src_slice = true;
     h->have_src = true;

@@ -257,6 +257,11 @@ class GeneralizedICP:
         capi.check(capi.lib().b2_gicp_set_source_slice(self._h, cloud._h, int(begin), int(end)))
         self._n_src = len(cloud)
 
+    def setInputSourceBlocks(self, cloud, rank, world):
+        """This rank's blocks of the source's Morton order (4096 points each, dealt round-robin): dense, balanced shards."""
+        capi.check(capi.lib().b2_gicp_set_source_blocks(self._h, cloud._h, int(rank), int(world)))
+        self._n_src = len(cloud)
+
     def setShard(self, comm):
         """Shard the source over the ranks of `comm` (None = single GPU)."""
         self._comm = comm

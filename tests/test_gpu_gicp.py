@@ -240,6 +240,8 @@ def test_two_gpu_sharded_align(pair, gicp, tmp_path):
     ref2 = one.align(G.perturbed(pair["truth"]))
     assert r0["iterations2"] == ref2.iterations and abs(r0["fitness2"] - ref2.fitness) <= 1e-12
     assert np.abs(np.array(r0["T2"]) - ref2.transformation).max() <= 1e-9
+    assert r0["T5"] == r1["T5"] and r0["iterations5"] == ref2.iterations and abs(r0["fitness5"] - ref2.fitness) <= 1e-12
+    assert np.abs(np.array(r0["T5"]) - ref2.transformation).max() <= 1e-9           # Morton-block shards: same registration
     # fused linearise + exchange (CUDA IPC peer stores): bit-identical on both ranks, and to the NCCL path (two ranks: a + b either way)
     assert r0["fused"] and r1["fused"], "the two GPUs of the box cannot map each other's memory"
     assert r0["T3"] == r1["T3"] and r0["T3"] == r0["T2"] and r0["iterations3"] == r0["iterations2"] and r0["T4"] == r0["T3"]

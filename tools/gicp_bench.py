@@ -196,8 +196,7 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
     t0 = time.perf_counter()
     g.setInputTarget(tp)
     if comm is not None:
-        b, e = gicp.row_slice(n_src, rank, world)
-        g.setInputSourceSlice(sp, b, e)
+        g.setInputSourceBlocks(sp, rank, world)
     else:
         g.setInputSource(sp)
     t_index = time.perf_counter() - t0
