@@ -140,21 +140,26 @@ __global__ void k_gicp_finalize(GicpState* st) {
 #ifndef GICP_MIN_BLOCKS
 #define GICP_MIN_BLOCKS 4
 #endif
+#ifdef B2_NN1_STATS
+__device__ unsigned long long g_nn1_stats[8];
+#endif
 __global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_linearize(GicpArgs A) {
     GicpState* st = A.st;
     if (st->done) return;
     __shared__ double s_red[GICP_WARPS][32];
     __shared__ bool s_last;
+    __shared__ uint32_t s_tab[18][GICP_THREADS];       // per-thread row-range tables of the search (column = thread: no bank conflicts)
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double R[9], t[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-#pragma unroll
-        for (int j = 0; j < 3; j++) R[i * 3 + j] = st->T[i * 4 + j];
-        t[i] = st->T[i * 4 + 3];
-    }
+    // The pose is the same for every thread: kept in shared memory and read where it is used (broadcast loads). As 24 registers
+    // per thread it was spilled around the search at the 64-register cap (local-memory traffic through L2 on every query).
+    __shared__ double s_T[12];
+    if (threadIdx.x < 12) s_T[threadIdx.x] = st->T[threadIdx.x < 9 ? (threadIdx.x / 3) * 4 + threadIdx.x % 3 : (threadIdx.x - 9) * 4 + 3];
+    __syncthreads();
+    const volatile double* R = s_T;          // R[0..8] row-major rotation
+    const volatile double* t = s_T + 9;      // translation
     double totA = 0.0, totB = 0.0;   // lane l: running totals of terms (l & 15) and 16 + (l & 15)
+    B2_STAT(NN1Stats stats = {};)
     for (uint32_t lc = blockIdx.x * GICP_WARPS + warp; lc < A.n_local_chunks; lc += gridDim.x * GICP_WARPS) {
         // local chunk -> global chunk of the block-cyclic deal (spatially mixed shards: every rank gets its share of the
         // points that need the coarse pass; contiguous slices left the slowest rank 40 % behind at 8 GPUs)
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_lineariz
         const double vy = R[3] * px + R[4] * py + R[5] * pz + t[1];
         const double vz = R[6] * px + R[7] * py + R[8] * pz + t[2];
         NN1 nn; nn.d2 = INFINITY; nn.pos = 0xffffffffu; nn.idx = -1;
-        if (valid) nn = nn1_thread(A.tgt, A.tgtc, A.fine_pos_of, A.have_coarse != 0, vx, vy, vz, A.radius2, A.prev ? __ldcs(&A.prev[p]) : 0xffffffffu);
+        if (valid) nn = nn1_thread<GICP_THREADS>(A.tgt, A.tgtc, A.fine_pos_of, A.have_coarse != 0, vx, vy, vz, A.radius2, &s_tab[0][threadIdx.x], A.prev ? __ldcs(&A.prev[p]) : 0xffffffffu B2_STAT(, &stats));
         const bool hit = valid && nn.pos != 0xffffffffu;
         if (A.prev && valid) __stcs(&A.prev[p], nn.pos);
         if (A.corr && valid) A.corr[sidx] = hit ? (int32_t)nn.idx : -1;
@@ -216,6 +221,9 @@ __global__ void __launch_bounds__(GICP_THREADS, GICP_MIN_BLOCKS) k_gicp_lineariz
         totA += warp_reduce_scatter16(ta);
         totB += warp_reduce_scatter16(tb);
     }
+    B2_STAT(atomicAdd(&g_nn1_stats[0], stats.fine_cycles); atomicAdd(&g_nn1_stats[1], stats.coarse_cycles); atomicAdd(&g_nn1_stats[2], stats.coarse_queries);
+            atomicAdd(&g_nn1_stats[3], stats.coarse_cands); atomicAdd(&g_nn1_stats[4], stats.coarse_exact); atomicAdd(&g_nn1_stats[5], stats.coarse_cells);
+            atomicAdd(&g_nn1_stats[6], stats.unseeded);)
     // lane l < 16 holds term l in totA; lane l >= 16 holds term 16 + (l & 15) = l in totB: lane l -> term l
     const double tot = lane < 16 ? totA : totB;
     // epilogue: CTA partial, last CTA adds the partials in CTA order
@@ -383,7 +391,7 @@ static int gicp_ensure_coarse(b2_gicp_s* h) {
     h->have_coarse = false;
     if (h->n_tgt && r > h->tgt_grid.dev.h * 0.999) {
         B2_CHECK(h->tgt_coarse.build(h->tgt_xyz.as<double>(), h->n_tgt, r * 1.0078125, 0.0, h->stream));
-        B2_CHECK(h->tgt_coarse.build_cell_boxes(h->stream));
+        B2_CHECK(h->tgt_coarse.build_cell_boxes(h->stream, true));
         h->have_coarse = true;
     } else h->tgt_coarse.release();
     h->coarse_for = r;
@@ -692,6 +700,14 @@ int b2_gicp_align(b2_gicp_t h, const double init[16], double T_out[16], double* 
         const int m = std::min(chunk, total - launched);
         for (int i = 0; i < m; i++) {
             k_gicp_linearize<<<h->grid_blocks, GICP_THREADS, 0, h->stream>>>(a); launches++;
+#ifdef B2_NN1_STATS
+            {
+                unsigned long long z[8] = {}, v[8];
+                cudaStreamSynchronize(h->stream); cudaMemcpyFromSymbol(v, g_nn1_stats, sizeof(v)); cudaMemcpyToSymbol(g_nn1_stats, z, sizeof(z));
+                fprintf(stderr, "[nn1 stats] eval %d: fine cycles %.3g, coarse cycles %.3g (thread sums), coarse queries %llu, cells %llu, candidates %llu, exact %llu, unseeded %llu\n",
+                        launched + i, (double)v[0], (double)v[1], v[2], v[5], v[3], v[4], v[6]);
+            }
+#endif
             if (h->ev_used + 1 < (int)h->ev.size()) { h->ev_used++; B2_CUDA(cudaEventRecord(h->ev[h->ev_used], h->stream)); }
             if (h->comm && !fused) {
                 B2_CHECK(comm_allreduce_sum_f64(h->comm, ds->sums_local, ds->sums, GICP_NSUM, h->stream));

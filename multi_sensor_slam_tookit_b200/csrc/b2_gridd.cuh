@@ -24,22 +24,24 @@ struct GridDDev {
     const P4d* pts;
     const uint32_t* cell_start;
     const float* cell_box;     // optional: per cell the bounding box of its points, 6 floats rounded outward (min xyz, max xyz)
+    const float4* pts_rel;     // optional fp32 screening copy, same order as pts: xyz relative to the corner of the point's own cell
     double ox, oy, oz, h, inv_h;
     int nx, ny, nz;
     uint32_t n;
 };
 
 struct GridD {
-    DevBuf pts, cell_start, work, cell_box;
+    DevBuf pts, cell_start, work, cell_box, pts_rel;
     GridDDev dev{};
     size_t n = 0;
     double ppc = 0.0;          // points per occupied cell of the built grid
     // d_xyz: device, n*3 doubles. h_request > 0 fixes the cell edge (raised only if the cell budget requires it);
     // otherwise the edge is chosen so that an occupied cell holds about target_ppc points.
     int build(const double* d_xyz, size_t n, double h_request, double target_ppc, cudaStream_t s);
-    // tight per-cell boxes (for grids whose cells hold many points: lets a search skip a cell without touching its points)
-    int build_cell_boxes(cudaStream_t s);
-    void release() { pts.release(); cell_start.release(); work.release(); cell_box.release(); dev = GridDDev{}; n = 0; }
+    // tight per-cell boxes (for grids whose cells hold many points: lets a search skip a cell without touching its points);
+    // screening: also the fp32 copy of the points relative to their cells (nn1_scan_block_pruned tests it before the fp64 point)
+    int build_cell_boxes(cudaStream_t s, bool screening = false);
+    void release() { pts.release(); cell_start.release(); work.release(); cell_box.release(); pts_rel.release(); dev = GridDDev{}; n = 0; }
 };
 
 #ifdef __CUDACC__
@@ -149,6 +151,13 @@ __device__ __forceinline__ void row_range(const GridDDev& g, int x0, int x1, int
 // Result: d2 (INFINITY = none), idx (original index), x/y/z the neighbour's coordinates, pos its position in the FINE
 // grid's order (through `fine_pos_of`, original index -> fine position, when the coarse pass found it).
 struct NN1 { double d2; long long idx; double x, y, z; uint32_t pos; };
+#ifdef B2_NN1_STATS
+// developer statistics (variant build only): per-thread counters the kernel adds up
+struct NN1Stats { unsigned long long fine_cycles, coarse_cycles, coarse_queries, coarse_cands, coarse_exact, coarse_cells, unseeded; };
+#define B2_STAT(...) __VA_ARGS__
+#else
+#define B2_STAT(...)
+#endif
 
 __device__ __forceinline__ void nn1_consider(NN1& best, double radius2, double qx, double qy, double qz, double x, double y, double z,
                                              long long idx, uint32_t p) {
@@ -173,17 +182,24 @@ __device__ __forceinline__ void nn1_scan_run(const GridDDev& g, uint32_t b, uint
 }
 
 // the 3x3x3 block as nine contiguous runs, all eighteen bounds requested up front
-__device__ __forceinline__ void nn1_scan_block(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best) {
-    uint32_t rb[9], re[9];
+// tab: this thread's column of an 18-row table in shared memory (row i at tab[i * TS]); a rolled loop over per-thread arrays
+// would index them dynamically, which puts them in local memory (measured: half of the kernel's L2 traffic)
+template <int TS>
+__device__ __forceinline__ void nn1_scan_block(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best, uint32_t* tab) {
 #pragma unroll
-    for (int i = 0; i < 9; i++) row_range(g, qc.cx - 1, qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, rb[i], re[i]);
+    for (int i = 0; i < 9; i++) {
+        uint32_t b, e;
+        row_range(g, qc.cx - 1, qc.cx + 1, qc.cy + (i % 3) - 1, qc.cz + (i / 3) - 1, b, e);
+        tab[i * TS] = b; tab[(9 + i) * TS] = e;
+    }
 #pragma unroll 1
-    for (int i = 0; i < 9; i++) nn1_scan_run(g, rb[i], re[i], qx, qy, qz, radius2, best);
+    for (int i = 0; i < 9; i++) nn1_scan_run(g, tab[i * TS], tab[(9 + i) * TS], qx, qy, qz, radius2, best);
 }
 
 // the 3x3x3 block cell by cell, nearest cells first, skipping every cell whose box is farther than the best so far
 // (cells of the coarse grid hold tens of points, so a skipped cell saves more than its two bound loads cost)
-__device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best) {
+__device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best
+                                                      B2_STAT(, NN1Stats* stats = nullptr)) {
     const double fx = (qx - g.ox) * g.inv_h - (double)qc.cx, fy = (qy - g.oy) * g.inv_h - (double)qc.cy, fz = (qz - g.oz) * g.inv_h - (double)qc.cz;
     const double h2 = g.h * g.h * (1.0 - 1e-9);
     // offsets ordered by |dx| + |dy| + |dz|: centre, 6 faces, 12 edges, 8 corners (3 bits per axis, value + 1)
@@ -211,7 +227,36 @@ __device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const Q
                 const double pd2 = ex * ex + ey * ey + ez * ez;
                 if (pd2 > best.d2 || pd2 >= radius2) continue;
             }
-            nn1_scan_run(g, b, e, qx, qy, qz, radius2, best);
+            B2_STAT(stats->coarse_cells++; stats->coarse_cands += e - b;)
+            if (g.pts_rel) {
+                // fp32 screening: the candidate relative to its cell's corner against the query relative to the same corner.
+                // Both roundings are below 2^-24 * 2h per coordinate, which moves a squared distance below h^2 by less
+                // than 1.3e-6 h^2; the margin is eight times that, so no candidate that could win (or tie) is skipped,
+                // and those that pass are decided by the fp64 point as before: the result is the exact search's.
+                const double cox = g.ox + (double)(qc.cx + ox) * g.h, coy = g.oy + (double)(qc.cy + oy) * g.h, coz = g.oz + (double)(qc.cz + oz) * g.h;
+                const float qfx = (float)(qx - cox), qfy = (float)(qy - coy), qfz = (float)(qz - coz);
+                const float margin = 1e-5f * (float)h2;
+                float limf = __double2float_ru(fmin(best.d2, radius2)) * (1.f + 1e-5f) + margin;
+                for (uint32_t p = b; p < e; p += 4) {
+                    float4 c[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) c[q] = __ldg(&g.pts_rel[min(p + q, e - 1)]);
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float dx = qfx - c[q].x, dy = qfy - c[q].y, dz = qfz - c[q].z;
+                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        if (p + q < e && d <= limf) {
+                            B2_STAT(stats->coarse_exact++;)
+                            double x, y, z; long long id;
+                            load_p4d(&g.pts[p + q], x, y, z, id);
+                            nn1_consider(best, radius2, qx, qy, qz, x, y, z, id, p + q);
+                            limf = __double2float_ru(fmin(best.d2, radius2)) * (1.f + 1e-5f) + margin;
+                        }
+                    }
+                }
+            } else {
+                nn1_scan_run(g, b, e, qx, qy, qz, radius2, best);
+            }
         }
     }
 }
@@ -223,7 +268,8 @@ __device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const Q
 // radius sqrt(best.d2) cannot reach are not read. The faces' distances are shortened by an absolute slack (1e-7 cells,
 // nine orders above the rounding of the cell coordinate) and the ball is inflated by 1e-9, so the test is conservative;
 // equal distances stay reachable (the test is a strict >), which keeps ties falling to the smaller index.
-__device__ __forceinline__ void nn1_scan_block_bounded(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best) {
+template <int TS>
+__device__ __forceinline__ void nn1_scan_block_bounded(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best, uint32_t* tab) {
     const double fx = (qx - g.ox) * g.inv_h - (double)qc.cx, fy = (qy - g.oy) * g.inv_h - (double)qc.cy, fz = (qz - g.oz) * g.inv_h - (double)qc.cz;
     const double lim = best.d2 * (1.0 + 1e-9);
     const double sl = 1e-7;
@@ -243,14 +289,14 @@ __device__ __forceinline__ void nn1_scan_block_bounded(const GridDDev& g, const 
 #if B2_NN1_STREAM
     // the surviving rows as one candidate stream (lanes of a warp keep different rows of different lengths: walked row by
     // row the warp pays the longest row of every row slot)
-    uint32_t lb[9], le[9];
+    // (the compacted table lives in the thread's shared-memory column: nr indexes it dynamically)
     int nr = 0;
 #pragma unroll
-    for (int i = 0; i < 9; i++) if (rb[i] < re[i]) { lb[nr] = rb[i]; le[nr] = re[i]; nr++; }
+    for (int i = 0; i < 9; i++) if (rb[i] < re[i]) { tab[nr * TS] = rb[i]; tab[(9 + nr) * TS] = re[i]; nr++; }
     int k = 0;
     uint32_t p = 0, e = 0;
     bool have = nr > 0;
-    if (have) { p = lb[0]; e = le[0]; k = 1; }
+    if (have) { p = tab[0]; e = tab[9 * TS]; k = 1; }
     while (have) {
         double x0, y0, z0, x1, y1, z1; long long i0, i1;
         const bool two = p + 1 < e;
@@ -259,7 +305,7 @@ __device__ __forceinline__ void nn1_scan_block_bounded(const GridDDev& g, const 
         nn1_consider(best, radius2, qx, qy, qz, x0, y0, z0, i0, p);
         if (two) nn1_consider(best, radius2, qx, qy, qz, x1, y1, z1, i1, p + 1);
         p += 2;
-        if (p >= e) { if (k < nr) { p = lb[k]; e = le[k]; k++; } else have = false; }
+        if (p >= e) { if (k < nr) { p = tab[k * TS]; e = tab[(9 + k) * TS]; k++; } else have = false; }
     }
 #else
 #pragma unroll 1
@@ -269,8 +315,14 @@ __device__ __forceinline__ void nn1_scan_block_bounded(const GridDDev& g, const 
 
 // seed: position (fine order) of a target point worth trying first — the previous iteration's correspondence — or
 // 0xffffffff. It only narrows the search; the result is the exact nearest neighbour either way.
+// tab: the calling thread's column of an 18-row table in shared memory (row i at tab[i * TS]).
+// (Parking the queries that need the coarse pass in a per-warp queue and running it for 32 of them at a time measured no
+// gain: they come in runs of consecutive source points anyway, so the warps that take the coarse pass are already full.)
+template <int TS>
 __device__ __forceinline__ NN1 nn1_thread(const GridDDev& fine, const GridDDev& coarse, const uint32_t* __restrict__ fine_pos_of,
-                                          bool have_coarse, double qx, double qy, double qz, double radius2, uint32_t seed = 0xffffffffu) {
+                                          bool have_coarse, double qx, double qy, double qz, double radius2, uint32_t* tab, uint32_t seed = 0xffffffffu
+                                          B2_STAT(, NN1Stats* stats = nullptr)) {
+    B2_STAT(const long long t0 = clock64();)
     NN1 best; best.d2 = INFINITY; best.idx = 0x7fffffffffffffffLL; best.x = best.y = best.z = 0.0; best.pos = 0xffffffffu;
     const QueryCell qc = query_cell(fine, qx, qy, qz);
     if (!qc.finite) return best;
@@ -279,14 +331,17 @@ __device__ __forceinline__ NN1 nn1_thread(const GridDDev& fine, const GridDDev& 
         load_p4d(&fine.pts[seed], x, y, z, id);
         nn1_consider(best, radius2, qx, qy, qz, x, y, z, id, seed);
     }
-    if (best.pos != 0xffffffffu) nn1_scan_block_bounded(fine, qc, qx, qy, qz, radius2, best);
-    else nn1_scan_block(fine, qc, qx, qy, qz, radius2, best);
+    B2_STAT(if (best.pos == 0xffffffffu) stats->unseeded++;)
+    if (best.pos != 0xffffffffu) nn1_scan_block_bounded<TS>(fine, qc, qx, qy, qz, radius2, best, tab);
+    else nn1_scan_block<TS>(fine, qc, qx, qy, qz, radius2, best, tab);
     const double bound2 = ring_bound2(fine, qc, 1);
+    B2_STAT(const long long t1 = clock64(); stats->fine_cycles += t1 - t0;)
     if (best.d2 < bound2 || bound2 >= radius2 || !have_coarse) return best;
     const QueryCell qcc = query_cell(coarse, qx, qy, qz);
     const long long before = best.idx;
-    nn1_scan_block_pruned(coarse, qcc, qx, qy, qz, radius2, best);
+    nn1_scan_block_pruned(coarse, qcc, qx, qy, qz, radius2, best B2_STAT(, stats));
     if (best.idx != before) best.pos = __ldg(&fine_pos_of[best.idx]);
+    B2_STAT(stats->coarse_cycles += clock64() - t1; stats->coarse_queries++;)
     return best;
 }
 

@@ -338,6 +338,9 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
 // PHASES: 3 = neighbour search and fits in one kernel (single scan, latency); the batched shape runs them as two launches with
 // their own register budgets — 1 = search only (winners' grid positions to HBM, 20 B per feature), 2 = fits, Jacobian rows,
 // reduction and epilogue from those positions. Fused at 64 registers the fits spilled ~440 MB of local memory per launch.
+#ifndef B2_S2M_ARGS_QUAL
+#define B2_S2M_ARGS_QUAL __grid_constant__
+#endif
 #ifndef S2M_THR_KNN_MAXREG
 #define S2M_THR_KNN_MAXREG 64
 #endif
@@ -346,7 +349,8 @@ __device__ __noinline__ void lm_epilogue(S2MState& s, const double* sums, int it
 #endif
 template <int LPF, int ROUNDS, int ROUNDS_C, int PHASES>
 __global__ void __launch_bounds__(S2M_THREADS) __maxnreg__(PHASES == 1 ? S2M_THR_KNN_MAXREG : (PHASES == 2 ? S2M_THR_FIT_MAXREG : S2M_LAT_MAXREG))
-k_s2m_iteration(const S2MArgs a) {
+k_s2m_iteration(const B2_S2M_ARGS_QUAL S2MArgs a) {   // __grid_constant__: lm_epilogue takes `a` by reference; without it every
+                                                        // thread copies the 512-byte argument block to its local-memory stack first
     constexpr int FPR = S2M_THREADS / LPF;
     constexpr int FPB = FPR * ROUNDS;                 // features per surf CTA (and the size of the shared arrays)
     constexpr int FPB_C = FPR * ROUNDS_C;             // features per corner CTA
