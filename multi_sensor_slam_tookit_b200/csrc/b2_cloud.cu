@@ -200,39 +200,44 @@ int GridD::build(const double* d_xyz, size_t n_, double h_request, double target
     return B2_OK;
 }
 
-__global__ void __launch_bounds__(256) k_grid_cell_boxes(const P4d* __restrict__ pts, const uint32_t* __restrict__ cell_start, size_t ncell,
-                                                         float* __restrict__ box, GridDDev g, float4* __restrict__ rel) {
+// one thread per cell: the cell's record (run of its points + their box in 1/256 cell steps relative to the cell's corner)
+// and the fp32 copy of its points relative to the same corner — the expression nn1_scan_block_pruned evaluates on the query's side
+__global__ void __launch_bounds__(256) k_grid_cell_records(GridDDev g, size_t ncell, uint4* __restrict__ rec, float4* __restrict__ rel) {
     const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
-    const uint32_t b = cell_start[c], e = cell_start[c + 1];
-    if (b >= e) return;
-    // corner of this cell: the expression nn1_scan_block_pruned evaluates for the query's side
+    const uint32_t b = g.cell_start[c], e = g.cell_start[c + 1];
+    if (b >= e) { rec[c] = make_uint4(b, b, 0u, 0u); return; }
     const int cx = (int)(c % (size_t)g.nx), cy = (int)((c / (size_t)g.nx) % (size_t)g.ny), cz = (int)(c / ((size_t)g.nx * g.ny));
     const double cox = g.ox + (double)cx * g.h, coy = g.oy + (double)cy * g.h, coz = g.oz + (double)cz * g.h;
     double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (uint32_t p = b; p < e; p++) {
         double x, y, z; long long id;
-        load_p4d(&pts[p], x, y, z, id);
-        if (rel) rel[p] = make_float4((float)(x - cox), (float)(y - coy), (float)(z - coz), 0.f);
+        load_p4d(&g.pts[p], x, y, z, id);
+        x -= cox; y -= coy; z -= coz;
+        rel[p] = make_float4((float)x, (float)y, (float)z, 0.f);
         lo[0] = fmin(lo[0], x); lo[1] = fmin(lo[1], y); lo[2] = fmin(lo[2], z);
         hi[0] = fmax(hi[0], x); hi[1] = fmax(hi[1], y); hi[2] = fmax(hi[2], z);
     }
-    float* o = box + 6 * c;
-    o[0] = __double2float_rd(lo[0]); o[1] = __double2float_rd(lo[1]); o[2] = __double2float_rd(lo[2]);
-    o[3] = __double2float_ru(hi[0]); o[4] = __double2float_ru(hi[1]); o[5] = __double2float_ru(hi[2]);
+    // step index of a coordinate: floor(v / h * 256) clamped to the cell (a point a rounding error outside its cell lands on
+    // the first / last step; the search widens the box by 1e-6 h, far above that)
+    uint32_t ql = 0, qh = 0;
+    for (int a = 0; a < 3; a++) {
+        const double sl = floor(lo[a] * g.inv_h * 256.0), sh = floor(hi[a] * g.inv_h * 256.0);
+        ql |= (uint32_t)fmin(fmax(sl, 0.0), 255.0) << (8 * a);
+        qh |= (uint32_t)fmin(fmax(sh, 0.0), 255.0) << (8 * a);
+    }
+    rec[c] = make_uint4(b, e, ql, qh);
 }
 
-int GridD::build_cell_boxes(cudaStream_t s, bool screening) {
-    dev.cell_box = nullptr; dev.pts_rel = nullptr;
+int GridD::build_cell_records(cudaStream_t s) {
+    dev.cell_rec = nullptr; dev.pts_rel = nullptr;
     if (!dev.pts || !n) return B2_OK;
     const size_t ncell = (size_t)dev.nx * dev.ny * dev.nz;
-    B2_CHECK(cell_box.reserve(ncell * 24));
-    if (screening) B2_CHECK(pts_rel.reserve(n * sizeof(float4)));
-    k_grid_cell_boxes<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(dev.pts, dev.cell_start, ncell, cell_box.as<float>(), dev,
-                                                                      screening ? pts_rel.as<float4>() : nullptr); count_launch();
+    B2_CHECK(cell_rec.reserve(ncell * sizeof(uint4)));
+    B2_CHECK(pts_rel.reserve(n * sizeof(float4)));
+    k_grid_cell_records<<<(unsigned)((ncell + 255) / 256), 256, 0, s>>>(dev, ncell, cell_rec.as<uint4>(), pts_rel.as<float4>()); count_launch();
     B2_CUDA(cudaGetLastError());
-    dev.cell_box = cell_box.as<float>();
-    if (screening) dev.pts_rel = pts_rel.as<float4>();
+    dev.cell_rec = cell_rec.as<uint4>(); dev.pts_rel = pts_rel.as<float4>();
     return B2_OK;
 }
 

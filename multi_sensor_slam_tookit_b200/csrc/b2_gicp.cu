@@ -391,7 +391,7 @@ static int gicp_ensure_coarse(b2_gicp_s* h) {
     h->have_coarse = false;
     if (h->n_tgt && r > h->tgt_grid.dev.h * 0.999) {
         B2_CHECK(h->tgt_coarse.build(h->tgt_xyz.as<double>(), h->n_tgt, r * 1.0078125, 0.0, h->stream));
-        B2_CHECK(h->tgt_coarse.build_cell_boxes(h->stream, true));
+        B2_CHECK(h->tgt_coarse.build_cell_records(h->stream));
         h->have_coarse = true;
     } else h->tgt_coarse.release();
     h->coarse_for = r;

@@ -23,25 +23,26 @@ struct alignas(32) P4d { double x, y, z; long long idx; };
 struct GridDDev {
     const P4d* pts;
     const uint32_t* cell_start;
-    const float* cell_box;     // optional: per cell the bounding box of its points, 6 floats rounded outward (min xyz, max xyz)
-    const float4* pts_rel;     // optional fp32 screening copy, same order as pts: xyz relative to the corner of the point's own cell
+    const uint4* cell_rec;     // optional, with pts_rel (coarse grids): per cell {begin, end, box lo, box hi}: the run of its points and their
+                               // bounding box relative to the cell's corner in 1/256 cell, 8 bits per axis (lo rounded down, hi = last step touched)
+    const float4* pts_rel;     // fp32 screening copy, same order as pts: xyz relative to the corner of the point's own cell
     double ox, oy, oz, h, inv_h;
     int nx, ny, nz;
     uint32_t n;
 };
 
 struct GridD {
-    DevBuf pts, cell_start, work, cell_box, pts_rel;
+    DevBuf pts, cell_start, work, cell_rec, pts_rel;
     GridDDev dev{};
     size_t n = 0;
     double ppc = 0.0;          // points per occupied cell of the built grid
     // d_xyz: device, n*3 doubles. h_request > 0 fixes the cell edge (raised only if the cell budget requires it);
     // otherwise the edge is chosen so that an occupied cell holds about target_ppc points.
     int build(const double* d_xyz, size_t n, double h_request, double target_ppc, cudaStream_t s);
-    // tight per-cell boxes (for grids whose cells hold many points: lets a search skip a cell without touching its points);
-    // screening: also the fp32 copy of the points relative to their cells (nn1_scan_block_pruned tests it before the fp64 point)
-    int build_cell_boxes(cudaStream_t s, bool screening = false);
-    void release() { pts.release(); cell_start.release(); work.release(); cell_box.release(); pts_rel.release(); dev = GridDDev{}; n = 0; }
+    // cell records + fp32 screening copy of the points (for grids whose cells hold many points: nn1_scan_block_pruned skips a
+    // cell on its box without touching its points, and tests the fp32 copy before the fp64 point)
+    int build_cell_records(cudaStream_t s);
+    void release() { pts.release(); cell_start.release(); work.release(); cell_rec.release(); pts_rel.release(); dev = GridDDev{}; n = 0; }
 };
 
 #ifdef __CUDACC__
@@ -196,66 +197,98 @@ __device__ __forceinline__ void nn1_scan_block(const GridDDev& g, const QueryCel
     for (int i = 0; i < 9; i++) nn1_scan_run(g, tab[i * TS], tab[(9 + i) * TS], qx, qy, qz, radius2, best);
 }
 
-// the 3x3x3 block cell by cell, nearest cells first, skipping every cell whose box is farther than the best so far
-// (cells of the coarse grid hold tens of points, so a skipped cell saves more than its two bound loads cost)
+// The 3x3x3 block of a grid with cell records (the coarse pass), for a query the fine block could not certify — in the first
+// evaluations of a registration that is almost every query, and most of them have NO target point within the radius, so the
+// search has to prove the ball empty. That is 27 cells x (record, maybe candidates): a chain of dependent loads when walked
+// cell by cell (measured: 120 k cycles per query, the launch latency-bound). Here instead
+//   1. the 27 records (9 rows x 48 contiguous bytes) are prefetched into L1 — no registers held, one round trip;
+//   2. sweep 1 tests every cell's box against the ball (fp32, conservative) and prefetches the points of the survivors;
+//   3. sweep 2 walks the survivors nearest first, re-tests the box against the best so far and screens the fp32 copy of the
+//      points; only a candidate that could win or tie loads its fp64 point and is decided exactly as before.
+// Roundings: a box step is h/256 and the box is widened by one part in 1e6 of h; the fp32 coordinates (relative to the cell
+// corner, below 2h) are within 2^-24 * 2h; a squared distance below h^2 moves by less than 1.3e-6 h^2 and the margin is eight
+// times that, so nothing that could win is skipped: the result is the exact search's.
 __device__ __forceinline__ void nn1_scan_block_pruned(const GridDDev& g, const QueryCell& qc, double qx, double qy, double qz, double radius2, NN1& best
                                                       B2_STAT(, NN1Stats* stats = nullptr)) {
-    const double fx = (qx - g.ox) * g.inv_h - (double)qc.cx, fy = (qy - g.oy) * g.inv_h - (double)qc.cy, fz = (qz - g.oz) * g.inv_h - (double)qc.cz;
-    const double h2 = g.h * g.h * (1.0 - 1e-9);
-    // offsets ordered by |dx| + |dy| + |dz|: centre, 6 faces, 12 edges, 8 corners (3 bits per axis, value + 1)
-#pragma unroll 1
-    for (int pass = 0; pass < 4; pass++) {
-#pragma unroll 1
-        for (int k = 0; k < 27; k++) {
-            const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
-            if (abs(ox) + abs(oy) + abs(oz) != pass) continue;
-            const double gx = ox < 0 ? fx : (ox > 0 ? 1.0 - fx : 0.0);
-            const double gy = oy < 0 ? fy : (oy > 0 ? 1.0 - fy : 0.0);
-            const double gz = oz < 0 ? fz : (oz > 0 ? 1.0 - fz : 0.0);
-            const double bd2 = (gx * gx + gy * gy + gz * gz) * h2;
-            if (bd2 > best.d2 || bd2 >= radius2) continue;
-            uint32_t b, e;
-            row_range(g, qc.cx + ox, qc.cx + ox, qc.cy + oy, qc.cz + oz, b, e);
-            if (b < e && g.cell_box) {
-                // the points of the cell usually fill a thin slab of it: test their own box before streaming them
-                const size_t cell = ((size_t)(qc.cz + oz) * g.ny + (qc.cy + oy)) * g.nx + (qc.cx + ox);
-                const float2* bx = reinterpret_cast<const float2*>(g.cell_box + 6 * cell);
-                const float2 b0 = __ldg(bx), b1 = __ldg(bx + 1), b2 = __ldg(bx + 2);      // (lo.x, lo.y) (lo.z, hi.x) (hi.y, hi.z)
-                const double ex = fmax(0.0, fmax((double)b0.x - qx, qx - (double)b1.y));
-                const double ey = fmax(0.0, fmax((double)b0.y - qy, qy - (double)b2.x));
-                const double ez = fmax(0.0, fmax((double)b1.x - qz, qz - (double)b2.y));
-                const double pd2 = ex * ex + ey * ey + ez * ez;
-                if (pd2 > best.d2 || pd2 >= radius2) continue;
-            }
-            B2_STAT(stats->coarse_cells++; stats->coarse_cands += e - b;)
-            if (g.pts_rel) {
-                // fp32 screening: the candidate relative to its cell's corner against the query relative to the same corner.
-                // Both roundings are below 2^-24 * 2h per coordinate, which moves a squared distance below h^2 by less
-                // than 1.3e-6 h^2; the margin is eight times that, so no candidate that could win (or tie) is skipped,
-                // and those that pass are decided by the fp64 point as before: the result is the exact search's.
-                const double cox = g.ox + (double)(qc.cx + ox) * g.h, coy = g.oy + (double)(qc.cy + oy) * g.h, coz = g.oz + (double)(qc.cz + oz) * g.h;
-                const float qfx = (float)(qx - cox), qfy = (float)(qy - coy), qfz = (float)(qz - coz);
-                const float margin = 1e-5f * (float)h2;
-                float limf = __double2float_ru(fmin(best.d2, radius2)) * (1.f + 1e-5f) + margin;
-                for (uint32_t p = b; p < e; p += 4) {
-                    float4 c[4];
+    const float hf = (float)g.h;
+    const float margin = 1e-5f * hf * hf;
+    float limf = __double2float_ru(fmin(best.d2, radius2)) * (1.f + 1e-5f) + margin;
+    // query relative to the corner of its own cell (fp64 difference, then narrowed); a neighbour's corner is +-h away
+    const float q0x = (float)(qx - (g.ox + (double)qc.cx * g.h)), q0y = (float)(qy - (g.oy + (double)qc.cy * g.h)), q0z = (float)(qz - (g.oz + (double)qc.cz * g.h));
+    const bool xin = qc.cx >= 1 && qc.cx + 1 < g.nx;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) c[q] = __ldg(&g.pts_rel[min(p + q, e - 1)]);
+    for (int r = 0; r < 9; r++) {
+        const int y = qc.cy + (r % 3) - 1, z = qc.cz + (r / 3) - 1;
+        if (y >= 0 && y < g.ny && z >= 0 && z < g.nz && qc.cx + 1 >= 0 && qc.cx - 1 < g.nx) {
+            const uint4* row = g.cell_rec + ((size_t)z * g.ny + y) * g.nx;
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(row + min(max(qc.cx - 1, 0), g.nx - 1)));
+            if (xin) asm volatile("prefetch.global.L1 [%0];" :: "l"(row + qc.cx + 1));
+        }
+    }
+    const float step = hf * (1.f / 256.f), slack = 1e-6f * hf;
+    // box distance of cell (ox, oy, oz) from the query, squared (fp32, never above the true distance to any of its points)
+    auto box_d2 = [&](const uint4 rec, int ox, int oy, int oz) {
+        const float qfx = q0x - (float)ox * hf, qfy = q0y - (float)oy * hf, qfz = q0z - (float)oz * hf;     // relative to that cell's corner
+        const float lx = (float)(rec.z & 255u) * step - slack, ly = (float)((rec.z >> 8) & 255u) * step - slack, lz = (float)((rec.z >> 16) & 255u) * step - slack;
+        const float ux = (float)((rec.w & 255u) + 1u) * step + slack, uy = (float)(((rec.w >> 8) & 255u) + 1u) * step + slack, uz = (float)(((rec.w >> 16) & 255u) + 1u) * step + slack;
+        const float ex = fmaxf(0.f, fmaxf(lx - qfx, qfx - ux)), ey = fmaxf(0.f, fmaxf(ly - qfy, qfy - uy)), ez = fmaxf(0.f, fmaxf(lz - qfz, qfz - uz));
+        return (ex * ex + ey * ey + ez * ez) * (1.f - 1e-5f);
+    };
+    // nearest-first rank of cell k = (oz + 1) * 9 + (oy + 1) * 3 + (ox + 1): centre, 6 faces, 12 edges, 8 corners
+    constexpr unsigned char rank_of[27] = {19, 11, 20, 12, 5, 13, 21, 14, 22,   7, 3, 8, 1, 0, 2, 9, 4, 10,   23, 15, 24, 16, 6, 17, 25, 18, 26};
+    // the inverse, 5 bits per entry: ranks 0-11, 12-23, 24-26
+    const unsigned long long ord0 = 13ull | (12ull << 5) | (14ull << 10) | (10ull << 15) | (16ull << 20) | (4ull << 25) | (22ull << 30)
+                                  | (9ull << 35) | (11ull << 40) | (15ull << 45) | (17ull << 50) | (1ull << 55);
+    const unsigned long long ord1 = 3ull | (5ull << 5) | (7ull << 10) | (19ull << 15) | (21ull << 20) | (23ull << 25) | (25ull << 30)
+                                  | (0ull << 35) | (2ull << 40) | (6ull << 45) | (8ull << 50) | (18ull << 55);
+    const unsigned ord2 = 20u | (24u << 5) | (26u << 10);
+    // sweep 1 (rolled: the kernel is at the size of the instruction cache as it is — fully unrolled this loop made the whole
+    // launch 15 % slower): bit `rank` of `live` marks a non-empty cell whose box the ball reaches
+    uint32_t live = 0;
+#pragma unroll 1
+    for (int r = 0; r < 9; r++) {
+        const int oy = r % 3 - 1, oz = r / 3 - 1;
+        const int y = qc.cy + oy, z = qc.cz + oz;
+        if (!(y >= 0 && y < g.ny && z >= 0 && z < g.nz)) continue;
+        const uint4* row = g.cell_rec + (((size_t)z * g.ny + y) * g.nx + qc.cx);
+#pragma unroll 1
+        for (int a = 0; a < 3; a++) {
+            const int x = qc.cx + a - 1;
+            if (x < 0 || x >= g.nx) continue;
+            const uint4 rec = __ldg(row + (a - 1));
+            if (rec.x >= rec.y || box_d2(rec, a - 1, oy, oz) > limf) continue;
+            live |= 1u << rank_of[r * 3 + a];
+            // its points, 128 bytes (8 points) per request, up to 2 KB: sweep 2 then reads them from L1
+            const uint32_t pe = min(rec.y, rec.x + 128u);
+            for (uint32_t p = rec.x; p < pe; p += 8u) asm volatile("prefetch.global.L1 [%0];" :: "l"(g.pts_rel + p));
+        }
+    }
+    // sweep 2: the marked cells, nearest first
+    while (live) {
+        const int i = __ffs(live) - 1;
+        live &= live - 1u;
+        const int k = (int)((i < 12 ? ord0 >> (5 * i) : (i < 24 ? ord1 >> (5 * (i - 12)) : (unsigned long long)(ord2 >> (5 * (i - 24))))) & 31u);
+        const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
+        const uint4 rec = __ldg(&g.cell_rec[((size_t)(qc.cz + oz) * g.ny + (qc.cy + oy)) * g.nx + (qc.cx + ox)]);
+        if (box_d2(rec, ox, oy, oz) > limf) continue;
+        B2_STAT(stats->coarse_cells++; stats->coarse_cands += rec.y - rec.x;)
+        const float qfx = q0x - (float)ox * hf, qfy = q0y - (float)oy * hf, qfz = q0z - (float)oz * hf;
+        const uint32_t b = rec.x, e = rec.y;
+        for (uint32_t p = b; p < e; p += 4) {
+            float4 c[4];
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const float dx = qfx - c[q].x, dy = qfy - c[q].y, dz = qfz - c[q].z;
-                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        if (p + q < e && d <= limf) {
-                            B2_STAT(stats->coarse_exact++;)
-                            double x, y, z; long long id;
-                            load_p4d(&g.pts[p + q], x, y, z, id);
-                            nn1_consider(best, radius2, qx, qy, qz, x, y, z, id, p + q);
-                            limf = __double2float_ru(fmin(best.d2, radius2)) * (1.f + 1e-5f) + margin;
-                        }
-                    }
+            for (int q = 0; q < 4; q++) c[q] = __ldg(&g.pts_rel[min(p + q, e - 1)]);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float dx = qfx - c[q].x, dy = qfy - c[q].y, dz = qfz - c[q].z;
+                const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (p + q < e && d <= limf) {
+                    B2_STAT(stats->coarse_exact++;)
+                    double x, y, z; long long id;
+                    load_p4d(&g.pts[p + q], x, y, z, id);
+                    nn1_consider(best, radius2, qx, qy, qz, x, y, z, id, p + q);
+                    limf = __double2float_ru(fmin(best.d2, radius2)) * (1.f + 1e-5f) + margin;
                 }
-            } else {
-                nn1_scan_run(g, b, e, qx, qy, qz, radius2, best);
             }
         }
     }
@@ -332,6 +365,8 @@ __device__ __forceinline__ NN1 nn1_thread(const GridDDev& fine, const GridDDev& 
         nn1_consider(best, radius2, qx, qy, qz, x, y, z, id, seed);
     }
     B2_STAT(if (best.pos == 0xffffffffu) stats->unseeded++;)
+    // (Sending a query without a usable seed straight to the coarse block — exact on its own — measured slower: from the
+    // second evaluation on, many of them have a neighbour the fine block certifies for a fraction of the coarse pass.)
     if (best.pos != 0xffffffffu) nn1_scan_block_bounded<TS>(fine, qc, qx, qy, qz, radius2, best, tab);
     else nn1_scan_block<TS>(fine, qc, qx, qy, qz, radius2, best, tab);
     const double bound2 = ring_bound2(fine, qc, 1);
