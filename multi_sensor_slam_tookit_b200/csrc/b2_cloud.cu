@@ -494,8 +494,7 @@ __device__ __forceinline__ double box_box_dist2(const double* __restrict__ b, co
 // leaf_begin / leaf_end: the leaves (32 consecutive points of the Morton order) this launch serves; morton_out: write normal i of
 // the Morton order to nrm[3 i] instead of nrm[3 * original index] (the sharded set-up all-gathers contiguous leaf ranges).
 __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, double* __restrict__ nrm, uint32_t leaf_begin, uint32_t leaf_end, int morton_out) {
-    __shared__ double s_d[NRM_WARPS][NRM_MAXK][32];
-    __shared__ uint32_t s_p[NRM_WARPS][NRM_MAXK][32];
+    __shared__ uint2 s_h[NRM_WARPS][NRM_MAXK][32];      // heap entry: (fp32 image of the squared distance, position in T.pts)
     __shared__ double s_cx[NRM_WARPS][32], s_cy[NRM_WARPS][32], s_cz[NRM_WARPS][32];
     __shared__ int s_ci[NRM_WARPS][32];
     const unsigned full = 0xffffffffu;
@@ -510,30 +509,82 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, dou
 #pragma unroll
     for (int d = 0; d < 3; d++) { glo[d] = T.box[0][6 * (size_t)leaf0 + d]; ghi[d] = T.box[0][6 * (size_t)leaf0 + 3 + d]; }
     int cnt = 0;
-    double kd = INFINITY;                               // distance of this lane's K-th best so far (INFINITY until the heap is full)
+    uint32_t kkey = 0x7f800000u;                        // key of this lane's K-th best so far (+inf until the heap is full)
+    double kd = INFINITY;                               // an upper bound of its squared distance (the next float up), for the box tests
 
     // The K best of a lane live in a max-heap in shared memory ([slot][lane]: a lane only ever touches its own bank), so an
     // insertion costs at most log2(K) steps for every lane; a sorted list made the warp pay the longest shift of its 32 lanes
     // on every candidate (measured: 90 % of the kernel's instructions).
-    // A heap entry is (distance, position): 12 bytes per slot instead of 16, i.e. a third more warps per SM (shared memory
-    // is what limits the occupancy of this kernel). The original index only ever decides ties between EQUAL distances, which
-    // are rare: it is read from the point record when one occurs.
-    auto idx_at = [&](int slot) { return (int)reinterpret_cast<const long long*>(&T.pts[s_p[warp][slot][lane]])[3]; };
-    auto sift_down = [&](int j, int n, double d, int idx, uint32_t pos) {
+    // The heap is ordered by (squared distance, original index) exactly, but an entry stores only the fp32 image of the
+    // distance next to the position: rounding to float is monotone, so two different keys order their entries the way the
+    // doubles do, and EQUAL keys (a few in ten million comparisons) are settled by recomputing both distances from the point
+    // records — the same expression, the same bits — and then by the index. 8 bytes per slot instead of 12 (shared memory is
+    // what limits the occupancy of this kernel: 24 warps per SM instead of 16), one 64-bit load and one integer compare per
+    // step instead of a double load, a double compare with a tie branch and a second array (the sifts were 73 % of the launch).
+    auto key_of = [](double d) { return __float_as_uint(__double2float_rn(d)); };       // d >= 0: the bit pattern orders like the value
+    auto exact_at = [&](int slot, double& d, int& idx) {
+        double x, y, z; long long id;
+        load_p4d(&T.pts[s_h[warp][slot][lane].y], x, y, z, id);
+        const double dx = qx - x, dy = qy - y, dz = qz - z;
+        d = dx * dx + dy * dy + dz * dz; idx = (int)id;
+    };
+    // (d, idx) of a new element against heap slot `slot`: is the new one smaller?
+    auto new_less = [&](uint32_t key, double d, int idx, int slot, uint32_t skey) {
+        if (key != skey) return key < skey;
+        double sd; int si; exact_at(slot, sd, si);
+        return d < sd || (d == sd && idx < si);
+    };
+    auto slot_less_new = [&](int slot, uint32_t skey, uint32_t key, double d, int idx) {     // heap slot smaller than the new element?
+        if (key != skey) return skey < key;
+        double sd; int si; exact_at(slot, sd, si);
+        return sd < d || (sd == d && si < idx);
+    };
+    auto slot_less = [&](int a, uint32_t ka, int b, uint32_t kb) {     // heap slot a smaller than heap slot b?
+        if (ka != kb) return ka < kb;
+        double da, db; int ia, ib; exact_at(a, da, ia); exact_at(b, db, ib);
+        return da < db || (da == db && ia < ib);
+    };
+    auto sift_down = [&](int j, int n, uint32_t key, double d, int idx, uint32_t pos) {
         for (;;) {
             int c = 2 * j + 1;
             if (c >= n) break;
-            double cd = s_d[warp][c][lane];
+            uint2 ce = s_h[warp][c][lane];
             if (c + 1 < n) {
-                const double rd = s_d[warp][c + 1][lane];
-                if (cd < rd || (cd == rd && idx_at(c) < idx_at(c + 1))) { c++; cd = rd; }
+                const uint2 re = s_h[warp][c + 1][lane];
+                if (slot_less(c, ce.x, c + 1, re.x)) { c++; ce = re; }
             }
-            if (!(d < cd || (d == cd && idx < idx_at(c)))) break;
-            s_d[warp][j][lane] = cd; s_p[warp][j][lane] = s_p[warp][c][lane];
+            if (!new_less(key, d, idx, c, ce.x)) break;
+            s_h[warp][j][lane] = ce;
             j = c;
         }
-        s_d[warp][j][lane] = d; s_p[warp][j][lane] = pos;
+        s_h[warp][j][lane] = make_uint2(key, pos);
     };
+    auto set_bound = [&]() {
+        kkey = s_h[warp][0][lane].x;
+        kd = kkey >= 0x7f800000u ? INFINITY : (double)__uint_as_float(kkey + 1u);
+    };
+    // One candidate into this lane's heap (fill, or replace the K-th best when it is smaller).
+    auto offer = [&](uint32_t key, double d, int idx, uint32_t pos) {
+        if (cnt < K) {                                   // still filling: sift up
+            int j = cnt++;
+            while (j > 0) {
+                const int pj = (j - 1) >> 1;
+                const uint2 pe = s_h[warp][pj][lane];
+                if (!slot_less_new(pj, pe.x, key, d, idx)) break;     // the parent moves down while it is smaller than the new element
+                s_h[warp][j][lane] = pe;
+                j = pj;
+            }
+            s_h[warp][j][lane] = make_uint2(key, pos);
+            if (cnt == K) set_bound();
+        } else if (key <= kkey && new_less(key, d, idx, 0, kkey)) {    // replaces the current K-th best (the root): sift down
+            sift_down(0, K, key, d, idx, pos);
+            set_bound();
+        }
+    };
+    // (Measured and dropped, 10 M points, 77.9 ms with the loop below: marking a leaf's candidates first and inserting them
+    // afterwards, so that the warp runs as many sifts as its busiest lane needs — 86 ms, the busiest lane still has 13 marks per
+    // leaf; parking the candidates in a per-lane queue and draining all lanes together — 94 / 97 / 118 ms for queues of
+    // 8 / 16 / 32: the bound a lane prunes with goes stale, and the extra candidates and leaves cost more than the shared sifts save.)
     auto scan_leaf = [&](uint32_t leaf, bool mine) {
         const uint32_t p = leaf * 32u + lane;
         __syncwarp();
@@ -541,43 +592,11 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, dou
         __syncwarp();
         const int nc = (int)min(32u, T.n - leaf * 32u);
         if (mine) {
-            // Two passes. Inserting while walking the 32 candidates makes the warp run a whole sift (log2 K dependent
-            // shared-memory steps) at every candidate that ANY lane takes — measured: nearly every one, 150 warp instructions
-            // per candidate, 90 % of the kernel. So pass 1 only marks the candidates that can enter this lane's heap as it
-            // stands (all of them while it is still filling); pass 2 inserts the marked ones, and the warp runs as many
-            // sifts as its busiest lane has marks. A marked candidate is re-tested against the bound the earlier insertions
-            // of this pass have tightened (its distance is recomputed by the same expression: the same bits). The K best
-            // of a lane do not depend on the order they were offered in.
-            uint32_t marks = nc == 32 ? 0xffffffffu : ((1u << nc) - 1u);
-            if (cnt >= K) {
-                marks = 0u;
-                for (int c = 0; c < nc; c++) {
-                    const double dx = qx - s_cx[warp][c], dy = qy - s_cy[warp][c], dz = qz - s_cz[warp][c];
-                    const double d = dx * dx + dy * dy + dz * dz;
-                    if (d <= kd) marks |= 1u << c;              // ties are decided by the index in pass 2
-                }
-            }
-            while (marks) {
-                const int c = __ffs(marks) - 1;
-                marks &= marks - 1u;
+            for (int c = 0; c < nc; c++) {
                 const double dx = qx - s_cx[warp][c], dy = qy - s_cy[warp][c], dz = qz - s_cz[warp][c];
                 const double d = dx * dx + dy * dy + dz * dz;
-                const int idx = s_ci[warp][c];
-                if (cnt < K) {                                   // still filling: sift up
-                    int j = cnt++;
-                    while (j > 0) {
-                        const int pj = (j - 1) >> 1;
-                        const double pd = s_d[warp][pj][lane];
-                        if (!(pd < d || (pd == d && idx_at(pj) < idx))) break;
-                        s_d[warp][j][lane] = pd; s_p[warp][j][lane] = s_p[warp][pj][lane];
-                        j = pj;
-                    }
-                    s_d[warp][j][lane] = d; s_p[warp][j][lane] = leaf * 32u + c;
-                    if (cnt == K) kd = s_d[warp][0][lane];
-                } else if (d < kd || (d == kd && idx < idx_at(0))) {    // replaces the current K-th best (the root): sift down
-                    sift_down(0, K, d, idx, leaf * 32u + c);
-                    kd = s_d[warp][0][lane];
-                }
+                const uint32_t key = key_of(d);
+                if (cnt < K || key <= kkey) offer(key, d, s_ci[warp][c], leaf * 32u + c);      // equal keys are decided exactly inside
             }
         }
     };
@@ -628,16 +647,17 @@ __global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, dou
     const int found = cnt;
     // heap sort in place: the cumulants below are summed in ascending (distance, index), the order the oracle pins
     for (int end = found - 1; end > 0; end--) {
-        const double d = s_d[warp][end][lane]; const int idx = idx_at(end); const uint32_t pos = s_p[warp][end][lane];
-        s_d[warp][end][lane] = s_d[warp][0][lane]; s_p[warp][end][lane] = s_p[warp][0][lane];
-        sift_down(0, end, d, idx, pos);
+        const uint2 e = s_h[warp][end][lane];
+        double d; int idx; exact_at(end, d, idx);
+        s_h[warp][end][lane] = s_h[warp][0][lane];
+        sift_down(0, end, e.x, d, idx, e.y);
     }
     double nv[3] = {0.0, 0.0, 1.0};
     if (found >= 3) {
         double c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         for (int j = 0; j < found; j++) {
             double x, y, z; long long id;
-            load_p4d(&T.pts[s_p[warp][j][lane]], x, y, z, id);
+            load_p4d(&T.pts[s_h[warp][j][lane].y], x, y, z, id);
             c[0] += x; c[1] += y; c[2] += z;
             c[3] += x * x; c[4] += x * y; c[5] += x * z;
             c[6] += y * y; c[7] += y * z; c[8] += z * z;
