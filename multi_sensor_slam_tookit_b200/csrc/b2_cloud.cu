@@ -493,7 +493,7 @@ __device__ __forceinline__ double box_box_dist2(const double* __restrict__ b, co
 
 // leaf_begin / leaf_end: the leaves (32 consecutive points of the Morton order) this launch serves; morton_out: write normal i of
 // the Morton order to nrm[3 i] instead of nrm[3 * original index] (the sharded set-up all-gathers contiguous leaf ranges).
-__global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(BvhDev T, int K, double* __restrict__ nrm, uint32_t leaf_begin, uint32_t leaf_end, int morton_out) {
+__global__ void __launch_bounds__(NRM_WARPS * 32) k_normals(const __grid_constant__ BvhDev T, int K, double* __restrict__ nrm, uint32_t leaf_begin, uint32_t leaf_end, int morton_out) {
     __shared__ uint2 s_h[NRM_WARPS][NRM_MAXK][32];      // heap entry: (fp32 image of the squared distance, position in T.pts)
     __shared__ double s_cx[NRM_WARPS][32], s_cy[NRM_WARPS][32], s_cz[NRM_WARPS][32];
     __shared__ int s_ci[NRM_WARPS][32];

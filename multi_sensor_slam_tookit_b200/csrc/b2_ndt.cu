@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
 }
 
 // ---- fitness score: mean squared distance to the nearest target point -------------------------------------------
-__global__ void __launch_bounds__(128) k_ndt_fitness(BvhDev T, const float* __restrict__ src, uint32_t n_src, NdtArgs X, double* __restrict__ out) {
+__global__ void __launch_bounds__(128) k_ndt_fitness(const __grid_constant__ BvhDev T, const float* __restrict__ src, uint32_t n_src, NdtArgs X, double* __restrict__ out) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -17,7 +17,7 @@ namespace b2 {
 
 struct NnT { double m[12]; };
 
-__global__ void __launch_bounds__(128) k_nnerr(BvhDev T, const float* __restrict__ src, uint32_t n_src, NnT X, double* __restrict__ partial, uint32_t* __restrict__ found) {
+__global__ void __launch_bounds__(128) k_nnerr(const __grid_constant__ BvhDev T, const float* __restrict__ src, uint32_t n_src, NnT X, double* __restrict__ partial, uint32_t* __restrict__ found) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
