@@ -392,21 +392,25 @@ __global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
 }
 
 // ---- fitness score: mean squared distance to the nearest target point -------------------------------------------
+// A warp answers NDT_FIT_QPW queries one after the other (each a warp-cooperative descent of the BVH: a chain of dependent loads).
+// With 32 queries per warp a 85 k-point source was 2 700 warps — 18 per SM, each a 32-long serial chain: 1 ms. Eight per warp
+// gives the SMs four times the chains to overlap. The sums are accumulated with atomics (order-free, as before).
+constexpr uint32_t NDT_FIT_QPW = 8;
 __global__ void __launch_bounds__(128) k_ndt_fitness(const __grid_constant__ BvhDev T, const float* __restrict__ src, uint32_t n_src, NdtArgs X, double* __restrict__ out) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t base = warp * 32u;
+    const uint32_t base = warp * NDT_FIT_QPW;
     if (base >= n_src) return;
     float tx = 0, ty = 0, tz = 0;
-    if (base + lane < n_src) {
+    if ((uint32_t)lane < NDT_FIT_QPW && base + lane < n_src) {
         const size_t i = base + lane;
         const float sx = src[3 * i], sy = src[3 * i + 1], sz = src[3 * i + 2];
         tx = X.T[0] * sx + X.T[1] * sy + X.T[2] * sz + X.T[3];
         ty = X.T[4] * sx + X.T[5] * sy + X.T[6] * sz + X.T[7];
         tz = X.T[8] * sx + X.T[9] * sy + X.T[10] * sz + X.T[11];
     }
-    const int nq = (int)min(32u, n_src - base);
+    const int nq = (int)min(NDT_FIT_QPW, n_src - base);
     double sum = 0.0, cnt = 0.0;
     for (int j = 0; j < nq; j++) {
         const double qx = (double)__shfl_sync(full, tx, j), qy = (double)__shfl_sync(full, ty, j), qz = (double)__shfl_sync(full, tz, j);
@@ -1023,7 +1027,7 @@ int b2_ndt_get_fitness_score(b2_ndt_t h, double* score) {
     ndt_fill_args(h, a, h->final_T, 0);
     double* acc = h->sums.as<double>() + 40;
     B2_CUDA(cudaMemsetAsync(acc, 0, 16, s));
-    const uint32_t warps = (uint32_t)((h->n_src + 31) / 32);
+    const uint32_t warps = (uint32_t)((h->n_src + NDT_FIT_QPW - 1) / NDT_FIT_QPW);
     k_ndt_fitness<<<(warps + 3) / 4, 128, 0, s>>>(h->bvh.dev, a.src, a.n_src, a, acc); count_launch();
     B2_CUDA(cudaGetLastError());
     double hacc[2];
