@@ -325,6 +325,8 @@ int  b2_gicp_set_source_blocks(b2_gicp_t h, b2_cloud_t source, int rank, int wor
  * and the NCCL all-reduce of b2_gicp_set_shard stays in use. Call after b2_gicp_set_shard. */
 int  b2_gicp_peer_handle(b2_gicp_t h, unsigned char handle[64]);
 int  b2_gicp_set_peers(b2_gicp_t h, int rank, int world, const unsigned char* handles /* world x 64 bytes */);
+/* both in one: the handles travel over the communicator given to b2_gicp_set_shard (one 64-byte all-gather) */
+int  b2_gicp_exchange_setup(b2_gicp_t h);
 int  b2_gicp_set_shard(b2_gicp_t h, int rank, int world, b2_comm_t comm);
 /* one evaluation at T (parity tests): sums as above; corr (optional, n_source ints) = target index or -1 */
 int  b2_gicp_linearize(b2_gicp_t h, const double T[16], double sums[30], int32_t* corr);

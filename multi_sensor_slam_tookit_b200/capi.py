@@ -80,7 +80,7 @@ SYMBOLS = [
     "b2_cloud_estimate_normals", "b2_cloud_transform", "b2_cloud_last_gpu_ms", "b2_cloud_set_points_sharded", "b2_cloud_estimate_normals_sharded",
     "b2_comm_unique_id", "b2_comm_create", "b2_comm_destroy", "b2_comm_rank", "b2_comm_allreduce_f64",
     "b2_gicp_default_params", "b2_gicp_create", "b2_gicp_destroy", "b2_gicp_set_params", "b2_gicp_set_target",
-    "b2_gicp_set_source", "b2_gicp_set_source_slice", "b2_gicp_set_source_blocks", "b2_gicp_set_shard", "b2_gicp_peer_handle", "b2_gicp_set_peers", "b2_gicp_linearize", "b2_gicp_align", "b2_gicp_get_history",
+    "b2_gicp_set_source", "b2_gicp_set_source_slice", "b2_gicp_set_source_blocks", "b2_gicp_set_shard", "b2_gicp_peer_handle", "b2_gicp_set_peers", "b2_gicp_exchange_setup", "b2_gicp_linearize", "b2_gicp_align", "b2_gicp_get_history",
     "b2_gicp_last_gpu_ms", "b2_gicp_index_info", "b2_gicp_get_evaluation_ms",
     "b2_localmap_create", "b2_localmap_destroy", "b2_localmap_add_keyframe", "b2_localmap_num_keyframes", "b2_localmap_set_pose",
     "b2_localmap_clear_cache", "b2_localmap_extract", "b2_localmap_get", "b2_localmap_last_gpu_ms", "b2_s2m_set_map_from_localmap",
@@ -209,6 +209,7 @@ def lib():
     L.b2_gicp_set_source_blocks.argtypes = [vp, vp, i32, i32]
     L.b2_gicp_peer_handle.argtypes = [vp, vp]
     L.b2_gicp_set_peers.argtypes = [vp, i32, i32, vp]
+    L.b2_gicp_exchange_setup.argtypes = [vp]
     L.b2_gicp_set_shard.argtypes = [vp, i32, i32, vp]
     L.b2_gicp_linearize.argtypes = [vp, vp, vp, vp]
     L.b2_gicp_align.argtypes = [vp, vp, vp, pd, pd, pi, pi]

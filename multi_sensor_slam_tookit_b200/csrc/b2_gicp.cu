@@ -641,6 +641,25 @@ int b2_gicp_set_peers(b2_gicp_t h, int rank, int world, const unsigned char* han
     return B2_OK;
 }
 
+// The two calls above in one, for callers that have no side channel of their own: the 64-byte handles of all ranks are
+// all-gathered over the registration's communicator (the one given to b2_gicp_set_shard; rank and world are its own).
+int b2_gicp_exchange_setup(b2_gicp_t h) {
+    if (!h) return B2_ERR_ARG;
+    if (!h->comm || h->world < 2) { set_error("b2_gicp_exchange_setup: call b2_gicp_set_shard with a communicator first"); return B2_ERR_STATE; }
+    if (h->world > GICP_MAX_WORLD) { set_error("b2_gicp_exchange_setup: at most %d ranks", GICP_MAX_WORLD); return B2_ERR_ARG; }
+    unsigned char mine[64];
+    B2_CHECK(b2_gicp_peer_handle(h, mine));
+    DevBuf buf;
+    B2_CHECK(buf.reserve((size_t)h->world * 64));
+    unsigned char* d = buf.as<unsigned char>();
+    B2_CUDA(cudaMemcpyAsync(d + 64 * (size_t)h->rank, mine, 64, cudaMemcpyHostToDevice, h->stream));
+    B2_CHECK(comm_allgather_f64(h->comm, reinterpret_cast<const double*>(d + 64 * (size_t)h->rank), reinterpret_cast<double*>(d), 8, h->stream));
+    std::vector<unsigned char> all((size_t)h->world * 64);
+    B2_CUDA(cudaMemcpyAsync(all.data(), d, all.size(), cudaMemcpyDeviceToHost, h->stream));
+    B2_CUDA(cudaStreamSynchronize(h->stream));
+    return b2_gicp_set_peers(h, h->rank, h->world, all.data());
+}
+
 int b2_gicp_linearize(b2_gicp_t h, const double T[16], double sums[30], int32_t* corr) {
     B2_NVTX("b2_gicp_linearize");
     if (!h || !T || !sums) return B2_ERR_ARG;

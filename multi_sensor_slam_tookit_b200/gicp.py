@@ -286,6 +286,15 @@ class GeneralizedICP:
         except capi.B2Error:
             return False
 
+    def setupExchange(self):
+        """peerHandle + setPeers in one call: the handles travel over the communicator given to setShard. Returns False (and
+        keeps the NCCL all-reduce) when the GPUs cannot map each other's memory."""
+        try:
+            capi.check(capi.lib().b2_gicp_exchange_setup(self._h))
+            return True
+        except capi.B2Error:
+            return False
+
     def linearize(self, T, want_correspondences=False):
         T = np.ascontiguousarray(T, dtype=np.float64)
         sums = np.zeros(30, np.float64)

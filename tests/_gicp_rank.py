@@ -51,10 +51,14 @@ def main():
     g5 = gicp.GeneralizedICP(1.0, 0.005)
     g5.setInputTarget(t2); g5.setInputSourceBlocks(s2, rank, world); g5.setShard(comm)
     r5 = g5.align(d["init"], want_correspondences=False)
+    # ... and the one-call exchange set-up (handles all-gathered over the communicator) on the block shards
+    fused6 = g5.setupExchange()
+    r6 = g5.align(d["init"], want_correspondences=False) if fused6 else r5
     json.dump({"T": r.transformation.tolist(), "iterations": r.iterations, "fitness": r.fitness, "rmse": r.inlier_rmse,
                "pts_equal": pts_equal, "nrm_equal": nrm_equal, "T2": r2.transformation.tolist(), "iterations2": r2.iterations,
                "fitness2": r2.fitness, "slice": [b, e],
-               "T5": r5.transformation.tolist(), "iterations5": r5.iterations, "fitness5": r5.fitness, "fused": bool(fused), "T3": r3.transformation.tolist(), "iterations3": r3.iterations, "T4": r4.transformation.tolist()},
+               "T5": r5.transformation.tolist(), "iterations5": r5.iterations, "fitness5": r5.fitness, "fused": bool(fused), "T3": r3.transformation.tolist(), "iterations3": r3.iterations, "T4": r4.transformation.tolist(),
+               "fused6": bool(fused6), "T6": r6.transformation.tolist(), "iterations6": r6.iterations},
               open(os.path.join(work, f"rank{rank}.json"), "w"))
     dist.barrier()
     dist.destroy_process_group()

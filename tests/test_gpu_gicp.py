@@ -245,3 +245,6 @@ def test_two_gpu_sharded_align(pair, gicp, tmp_path):
     # fused linearise + exchange (CUDA IPC peer stores): bit-identical on both ranks, and to the NCCL path (two ranks: a + b either way)
     assert r0["fused"] and r1["fused"], "the two GPUs of the box cannot map each other's memory"
     assert r0["T3"] == r1["T3"] and r0["T3"] == r0["T2"] and r0["iterations3"] == r0["iterations2"] and r0["T4"] == r0["T3"]
+    # b2_gicp_exchange_setup (handles over the communicator) on the Morton-block shards: the same bits as their NCCL run
+    assert r0["fused6"] and r1["fused6"]
+    assert r0["T6"] == r1["T6"] and r0["T6"] == r0["T5"] and r0["iterations6"] == r0["iterations5"]

@@ -201,14 +201,13 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
         g.setInputSource(sp)
     t_index = time.perf_counter() - t0
     fused = False
+    t0 = time.perf_counter()
     if comm is not None:
         g.setShard(comm)
         if not os.environ.get("B2_GICP_NO_FUSED_EXCHANGE"):
-            # fused linearise + exchange: CUDA IPC handles of the ranks' exchange areas travel through the host program
-            import torch.distributed as dist
-            hs = [None] * world
-            dist.all_gather_object(hs, g.peerHandle())
-            fused = g.setPeers(rank, world, hs)
+            # fused linearise + exchange: the CUDA IPC handles of the ranks' exchange areas travel over the communicator
+            fused = g.setupExchange()
+    t_peers = time.perf_counter() - t0
     info = g.indexInfo()
     runs = []
     e2e_s = None
@@ -224,7 +223,7 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
                 launches=int(res.gpu_launches), fitness=float(res.fitness), inlier_rmse=float(res.inlier_rmse),
                 t_err=float(np.linalg.norm(dT[:3, 3])), r_err=float(np.arccos(np.clip((np.trace(dT[:3, :3]) - 1) / 2, -1, 1))),
                 evaluation_ms=[round(float(v), 3) for v in res.evaluation_ms], shard_points=int(info["shard_points"]), cell_edge=float(info["target_cell_edge"]), ppc=float(info["target_points_per_cell"]),
-                e2e_s=e2e_s, setup_s=dict(generate=t_gen, upload=t_up, normals_ms=n_ms, index=t_index), fused_exchange=bool(fused))
+                e2e_s=e2e_s, setup_s=dict(generate=t_gen, upload=t_up, normals_ms=n_ms, index=t_index, exchange_setup=t_peers), fused_exchange=bool(fused))
 
 
 def main():
