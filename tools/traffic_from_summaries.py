@@ -34,7 +34,7 @@ def main():
     P = os.path.join(ROOT, "profiles")
     old = json.load(open(os.path.join(P, "traffic.json")))
     t = {"source": f"ncu --set full --clock-control none, profiles/{tag}_ncu_*.txt (cold-cache, serialised launches); "
-                   "k_gicp_linearize from the capture named in its entry"}
+                   "k_gicp_linearize: see its entry"}
     s = launches(os.path.join(P, f"{tag}_ncu_s2m.txt"), r"k_s2m_iteration")
     t["k_s2m_iteration"] = {"launches": s, "dram_bytes_per_launch_last": s[-1]["dram_bytes"], "us_last": s[-1]["us"],
                             "note": "one persistent launch = one whole solve (3 iterations)"}
@@ -45,7 +45,13 @@ def main():
                           "note": "per ITERATION of 256 scans: search launch + fit launch (last pair of the capture); a step is 3-4 iterations"}
     n = launches(os.path.join(P, f"{tag}_ncu_ndt.txt"), r"k_ndt_derivatives")
     t["k_ndt_derivatives"] = {"launches": n, "dram_bytes_per_launch_last": n[-1]["dram_bytes"], "us_last": n[-1]["us"]}
-    t["k_gicp_linearize"] = old["k_gicp_linearize"]
+    gp = os.path.join(P, f"{tag}_ncu_gicp.txt")
+    if os.path.exists(gp):
+        g = launches(gp, r"k_gicp_linearize")
+        t["k_gicp_linearize"] = {"launches": g, "dram_bytes_per_launch_last": g[-1]["dram_bytes"], "us_last": g[-1]["us"],
+                                 "capture": f"profiles/{tag}_ncu_gicp.txt (the first six evaluations of the 50 M-point align)"}
+    else:
+        t["k_gicp_linearize"] = old["k_gicp_linearize"]
     json.dump(t, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print(json.dumps({k: (v if isinstance(v, str) else {"last": v["dram_bytes_per_launch_last"], "us": v["us_last"]}) for k, v in t.items()}, indent=1))
 
