@@ -176,6 +176,10 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
         comm.allreduce(np.zeros(4))
         warm = gicp.PointCloud.from_host_sharded(np.zeros((4096, 3)) + np.arange(4096)[:, None], comm)
         del warm
+        if not os.environ.get("B2_GICP_NO_FUSED_EXCHANGE"):
+            # likewise the first mapping of a peer GPU's memory in this process (cudaIpcOpenMemHandle enables peer access: ~13 ms per peer)
+            wg = gicp.GeneralizedICP(1.0, 0.005); wg.setShard(comm); wg.setupExchange()
+            del wg
     t0 = t_e2e = time.perf_counter()
     if comm is not None:
         # sharded set-up: 1/world of each cloud over this rank's PCIe link + all-gather, 1/world of the 30-NN normals + all-gather,
