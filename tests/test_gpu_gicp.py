@@ -93,6 +93,23 @@ def test_estimate_normals_uneven_density(gicp, oracle):
     assert np.abs(c.normals - ref).max() < 1e-9
 
 
+def test_estimate_normals_lattice_ties_and_far_coordinates(gicp, oracle):
+    """The neighbour heap orders by the fp32 image of the squared distance and settles equal images exactly. A
+    lattice is nothing but equal distances (the 30th neighbour is one of many at the same radius: the smaller index wins, as in
+    the oracle), and 6 km from the origin distinct fp64 distances share fp32 images all the time."""
+    gx, gy = np.meshgrid(np.arange(60) * 0.25, np.arange(50) * 0.25, indexing="ij")
+    z = 0.125 * ((np.arange(60)[:, None] + 2 * np.arange(50)[None, :]) % 3)          # three interleaved height levels
+    lattice = np.stack([gx.ravel(), gy.ravel(), z.ravel()], 1)
+    rng = np.random.default_rng(5)
+    lattice = lattice[rng.permutation(len(lattice))]                                    # index order unrelated to position
+    for shift in (np.zeros(3), np.array([6000.0, -2500.0, 40.0])):
+        pts = lattice + shift
+        c = gicp.PointCloud(pts); c.estimate_normals()
+        ref, _ = oracle.gicp_normals_covs(pts, 30, 0.005)
+        assert np.all(c.normals == ref, axis=1).mean() > 0.999
+        assert np.abs(c.normals - ref).max() < 1e-9
+
+
 def rel_err(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
@@ -136,6 +153,36 @@ def test_linearize_far_apart_and_small_radius(pair, gicp):
     T[:3, 3] += 1e4
     sums, corr = g.linearize(T, want_correspondences=True)
     assert sums[27] == 0 and np.all(corr == -1) and np.all(sums == 0)
+
+
+def test_coarse_pass_screening_far_coordinates_and_ties(pair, gicp, oracle):
+    """The coarse pass decides on an fp32 copy of the target relative to the cell corners and on boxes quantised to 1/256 cell
+    before it touches the fp64 points. Clouds 7 km from the origin (where a plain fp32 coordinate would be off by
+    half a millimetre), duplicated target points (exact ties: the smaller index wins) and an offset that sends nearly every query
+    through the coarse pass: the correspondence set still equals the oracle's bit for bit."""
+    rng = np.random.default_rng(20261018)
+    sel_s = rng.choice(len(pair["sp"]), 6000, replace=False); sel_t = rng.choice(len(pair["tp"]), 9000, replace=False)
+    shift = np.array([5000.0, -4800.0, 130.0])
+    sp = pair["sp"][sel_s] + shift
+    tp = pair["tp"][sel_t] + shift
+    dup = rng.choice(len(tp), 600, replace=False)
+    tp = np.concatenate([tp, tp[dup]])                                  # ties between equal points
+    sn, tn = pair["sn"][sel_s], np.concatenate([pair["tn"][sel_t], pair["tn"][sel_t][dup]])
+    src, tgt = gicp.PointCloud(sp), gicp.PointCloud(tp)
+    src.normals = sn; tgt.normals = tn
+    sc, tc = pair["sc"][sel_s], np.concatenate([pair["tc"][sel_t], pair["tc"][sel_t][dup]])     # covariances do not move with the shift
+    ref_o = oracle.GicpOracle(sp, sc, tp, tc)
+    for radius, off in ((1.0, [0.45, -0.3, 0.25]), (2.5, [1.2, 0.8, -0.4]), (0.6, [0.0, 0.0, 0.0])):
+        g = gicp.GeneralizedICP(radius, pair["eps"])
+        g.setInputTarget(tgt); g.setInputSource(src)
+        # the pose moves the source about its own position (a rotation about the far origin would throw it kilometres away)
+        T = np.eye(4); T[:3, :3] = G.perturbed(np.eye(4))[:3, :3]
+        c0 = sp.mean(0); T[:3, 3] = c0 - T[:3, :3] @ c0 + np.array(off)
+        sums, corr = g.linearize(T, want_correspondences=True)
+        ref, ref_corr = ref_o.linearize(T, radius, want_corr=True)
+        assert np.array_equal(corr, ref_corr)
+        assert (corr >= 0).sum() > 100
+        check_sums(sums, ref)
 
 
 def test_align_matches_oracle(pair, gicp):
