@@ -625,7 +625,9 @@ def run_registration(args, rank, local_rank, world, dist, torch):
             "workload": f"C5 map-to-map GICP: {c5['points']} source pts vs {c5['points']} target pts (city block tiled 4x4), "
                         f"{c5['iterations']} fixed iterations, max_corr 1.0", "value": c5["points"] * c5["evaluations"] / (ms * 1e-3) / 1e6,
             "unit": "Mpts/s", "n_gpus": world, "scaling": "strong", "ms_per_align": ms, "ms_per_evaluation": ms / c5["evaluations"],
-            "parallelism": f"target replicated, source sharded x{world}, ncclAllReduce(30 doubles) per iteration" if world > 1 else "single GPU",
+            "parallelism": (f"target replicated, source sharded x{world} (Morton blocks), the 30 sums exchanged "
+                            + ("inside k_gicp_linearize over NVLink peer memory" if c5.get("fused_exchange") else "by ncclAllReduce")
+                            + "; upload and normals sharded + all-gathered") if world > 1 else "single GPU",
             "evaluation_ms": c5["evaluation_ms"],
             "e2e": {"value": c5["points"] * c5["evaluations"] / c5["e2e_s"] / 1e6, "unit": "Mpts/s", "s": c5["e2e_s"],
                     "step": "host clouds in: upload, estimate_normals (30-NN) on both, index builds, align, transformation out (this rank)",
@@ -635,8 +637,9 @@ def run_registration(args, rank, local_rank, world, dist, torch):
             "roofline": {"kernel": "k_gicp_linearize", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": measured_traffic("k_gicp_linearize") if (world == 1 and c5["points"] == 50_000_000) else None,
                          "peak_source": peak_src, "bytes_per_launch": 144.0 * c5["points"] / world,
-                         "note": "144 B per source point per linearisation (SURVEY.md 8d), per GPU, over the whole align (the first "
-                                 "evaluation at the 0.3 m / 0.8 deg offset searches the coarse grid for about a fifth of the points)"}}
+                         "note": "144 B per source point per linearisation (SURVEY.md 8d), per GPU, over the whole align (in the first evaluations, "
+                                 "at the 0.3 m / 0.8 deg offset, most queries go through the coarse pass and have no target point within the "
+                                 "radius: they are instruction-bound, see evaluation_ms)"}}
         if args.c5_cpu_points > 0:
             from oracle import pyoracle as O
             n = args.c5_cpu_points
