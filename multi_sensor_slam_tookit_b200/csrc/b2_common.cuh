@@ -142,7 +142,7 @@ struct GridIndex {
     int build_async(cudaStream_t s);
     int rebuild_exact(cudaStream_t s);
     const GridDevMem* dev_ptr() const { return devmem.as<GridDevMem>(); }
-    void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); devmem.release(); cell_budget = 0; bb_ready_ = false; }
+    void release() { pts.release(); cell_start.release(); cell_of.release(); tmp.release(); raw.release(); stage.release(); devmem.release(); ingest_flag_.release(); cell_budget = 0; bb_ready_ = false; }
     // developer timeline (B2_S2M_TIMELINE=1): events after the upload, after the bounding box + read-back, after the build
     cudaEvent_t tl_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool tl_on = false;
@@ -154,6 +154,24 @@ struct GridIndex {
     size_t stride_ = 0; float max_dist_ = 1.f;
     bool bb_ready_ = false;                       // the bounding-box words in tmp are already reset (by the last scatter)
     const unsigned char* src_ = nullptr;          // device points the build reads (raw.p after an upload)
+    const unsigned char* pinned_src_ = nullptr;   // pinned host points the build kernel copies into raw itself (no DMA), or nullptr
+    // the kernel writes ingest_seq_ into this pinned word once it has read the last of the caller's points: wait_ingest() is how a
+    // caller-facing function keeps the promise that the caller's buffers are free when it returns
+    PinBuf ingest_flag_;
+    uint32_t ingest_seq_ = 0; bool ingest_wait_ = false;
+    int wait_ingest() {
+        if (!ingest_wait_) return B2_OK;
+        ingest_wait_ = false;
+        volatile uint32_t* f = ingest_flag_.as<volatile uint32_t>();
+        for (unsigned long long spins = 0; *f != ingest_seq_; spins++) {
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+            // the kernel was launched without an error; if the device has died since, do not spin forever
+            if ((spins & 0xfffffull) == 0xfffffull && cudaPeekAtLastError() != cudaSuccess) { set_error("grid index: device error while reading the caller's points"); return B2_ERR_CUDA; }
+        }
+        return B2_OK;
+    }
 };
 
 // ---- internal couplings between the modules (not part of the C ABI)

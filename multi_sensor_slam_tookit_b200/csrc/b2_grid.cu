@@ -267,6 +267,9 @@ int GridIndex::finish(cudaStream_t s) {
     return B2_OK;
 }
 
+#ifndef B2_GRID_ZERO_COPY_DEFAULT
+#define B2_GRID_ZERO_COPY_DEFAULT false
+#endif
 // ------------------------------------------------------------------------------------------------ device-sized build
 // The same counting sort with the geometry decided on the device: bounding box | geometry + zeroed counts | cell + rank per
 // point | chunk totals | prefix sum | scatter, six phases of one cooperative launch. The host never waits for the bounding
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
                                                                uint32_t cell_budget, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ rank_in_cell,
                                                                uint32_t* __restrict__ cell_start, uint32_t* __restrict__ other_table, int active_half,
                                                                uint32_t* __restrict__ chunk_sum, float4* __restrict__ out, GridDevMem* __restrict__ m,
-                                                               uint32_t bar_base) {
+                                                               uint32_t bar_base, const float4* __restrict__ pinned_src, volatile uint32_t* ingest_flag, uint32_t ingest_seq) {
     // Grid barrier on a counter in device memory (arrivals accumulate over the launches: barrier k of this launch is complete at
     // bar_base + (k + 1) * gridDim.x). A plain launch: measured on B200, a cooperative launch of this kernel starts ~12 us later
     // than a plain one, more than the kernel runs. All CTAs are resident by construction (one per SM, the host checks it).
@@ -302,12 +305,26 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
     // ---- bounding box of the finite points
     {
         float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-        for (uint32_t i = tid; i < n; i += nthr) {
-            const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
-            const float x = p[0], y = p[1], z = p[2];
+        auto take = [&](float x, float y, float z) {
             if (isfinite(x) && isfinite(y) && isfinite(z)) {
                 mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
                 mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+            }
+        };
+        if (pinned_src) {
+            // the upload itself: 16-byte records from pinned host memory, four loads in flight per thread, into the device copy
+            float4* dst = reinterpret_cast<float4*>(const_cast<unsigned char*>(raw));
+            uint32_t i = tid;
+            for (; i + 3 * nthr < n; i += 4 * nthr) {
+                const float4 a = __ldcs(pinned_src + i), b = __ldcs(pinned_src + i + nthr), c = __ldcs(pinned_src + i + 2 * nthr), d = __ldcs(pinned_src + i + 3 * nthr);
+                dst[i] = a; dst[i + nthr] = b; dst[i + 2 * nthr] = c; dst[i + 3 * nthr] = d;
+                take(a.x, a.y, a.z); take(b.x, b.y, b.z); take(c.x, c.y, c.z); take(d.x, d.y, d.z);
+            }
+            for (; i < n; i += nthr) { const float4 a = __ldcs(pinned_src + i); dst[i] = a; take(a.x, a.y, a.z); }
+        } else {
+            for (uint32_t i = tid; i < n; i += nthr) {
+                const float* p = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+                take(p[0], p[1], p[2]);
             }
         }
 #pragma unroll
@@ -331,6 +348,7 @@ __global__ void __launch_bounds__(GB_THREADS) k_grid_build_dev(const unsigned ch
         }
     }
     grid_sync();
+    if (pinned_src && tid == 0) { *ingest_flag = ingest_seq; __threadfence_system(); }      // every CTA is past its last read of the caller's buffer
     stamp(1);
     // ---- geometry: every thread derives the same numbers (the arithmetic of GridIndex::finish)
     GridGeom g;
@@ -505,9 +523,23 @@ int GridIndex::upload_async(const void* host_pts, const void* dev_pts, size_t st
         B2_CHECK(store_devmem(*this, none, 0, s));
     }
     tl_rec(0, s);
+    pinned_src_ = nullptr;
     if (n && host_pts) {
         B2_CHECK(raw.reserve(n * stride));
-        B2_CUDA(cudaMemcpyAsync(raw.p, host_pts, n * stride, cudaMemcpyHostToDevice, s));
+        // Pinned 16-byte records: the build kernel's first phase reads them over PCIe itself (128-bit loads from mapped host
+        // memory), writes the device copy and reduces the bounding box on the way — no DMA descriptor, no copy -> kernel
+        // hand-off. Measured (B2_GRID_ZERO_COPY=1): the PCIe read runs at the copy engine's speed (1.3 MB in 43 us), and as long as
+        // b2_s2m_set_map keeps its promise that the caller's buffers are free when it returns (it waits for the kernel's last
+        // read, as it waits for the DMA) the end-to-end step is the same 159-160 us either way; returning early instead would save
+        // 5-10 us and break that promise. Off by default; anything else goes through the copy engine.
+        const bool zero_copy = getenv("B2_GRID_ZERO_COPY") ? atoi(getenv("B2_GRID_ZERO_COPY")) != 0 : B2_GRID_ZERO_COPY_DEFAULT;
+        if (zero_copy && stride == 16 && (reinterpret_cast<uintptr_t>(host_pts) & 15u) == 0 && grid_build_dev_max_ctas() > 0) {
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, host_pts) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+                pinned_src_ = static_cast<const unsigned char*>(at.devicePointer);
+            else cudaGetLastError();
+        }
+        if (!pinned_src_) B2_CUDA(cudaMemcpyAsync(raw.p, host_pts, n * stride, cudaMemcpyHostToDevice, s));
         src_ = raw.as<unsigned char>();
     } else if (n && dev_pts && copy_dev && dev_pts != raw.p) {
         // device points owned by somebody else (the local map's VoxelGrid output): keep a private copy so that the build,
@@ -536,7 +568,10 @@ int GridIndex::build_async(cudaStream_t s) {
         return store_devmem(*this, d, 0, s);
     }
     const int coop_max = grid_build_dev_max_ctas();
-    if (coop_max <= 0) return rebuild_exact(s);
+    if (coop_max <= 0) {
+        if (pinned_src_) { B2_CUDA(cudaMemcpyAsync(raw.p, pinned_src_, n * stride_, cudaMemcpyDefault, s)); pinned_src_ = nullptr; }
+        return rebuild_exact(s);
+    }
     if (cell_budget == 0) cell_budget = GRID_DEFAULT_BUDGET;
     // two tables of cell_budget + 2 entries: the build counts into the one the previous build left zeroed, and zeroes the other
     // one (its predecessor's offsets) when it is done — no clearing pass and no barrier for it on the critical path
@@ -567,9 +602,16 @@ int GridIndex::build_async(cudaStream_t s) {
     const unsigned char* a_raw = src_; size_t a_stride = stride_; uint32_t a_n = (uint32_t)n; float a_h = h, a_md2 = max_dist * max_dist;
     uint32_t a_budget = (uint32_t)std::min<size_t>(cell_budget, 0xfffffff0u);
     float4* a_out = pts.as<float4>(); GridDevMem* a_m = devmem.as<GridDevMem>();
-    k_grid_build_dev<<<(unsigned)ctas, GB_THREADS, 0, s>>>(a_raw, a_stride, a_n, a_h, a_md2, a_budget, d_cell, d_rank, a_cs, a_other, a_half, d_chunk, a_out, a_m, bar_total_);
+    volatile uint32_t* a_flag = nullptr; uint32_t a_seq = 0;
+    if (pinned_src_) {
+        if (!ingest_flag_.p) { B2_CHECK(ingest_flag_.reserve(64)); *ingest_flag_.as<uint32_t>() = 0; }
+        a_flag = ingest_flag_.as<volatile uint32_t>(); a_seq = ++ingest_seq_;
+    }
+    k_grid_build_dev<<<(unsigned)ctas, GB_THREADS, 0, s>>>(a_raw, a_stride, a_n, a_h, a_md2, a_budget, d_cell, d_rank, a_cs, a_other, a_half, d_chunk, a_out, a_m, bar_total_, reinterpret_cast<const float4*>(pinned_src_), a_flag, a_seq);
     count_launch();
     B2_CUDA(cudaGetLastError());
+    ingest_wait_ = pinned_src_ != nullptr;
+    pinned_src_ = nullptr;                            // the device copy exists once this launch has run: later rebuilds read it
     bar_total_ += 4u * (uint32_t)ctas;
     tl_rec(3, s);
     return B2_OK;

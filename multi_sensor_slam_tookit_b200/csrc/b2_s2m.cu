@@ -1115,6 +1115,7 @@ int b2_s2m_set_map(b2_s2m_t h, const void* corner, size_t cstride, size_t n_corn
         }
         if (q != cudaSuccess) { set_error("b2_s2m_set_map: %s", cudaGetErrorString(q)); return B2_ERR_CUDA; }
     }
+    B2_CHECK(h->gc.wait_ingest()); B2_CHECK(h->gs.wait_ingest());      // pinned maps are read by the build kernels themselves: wait for their last read
     h->map_pending = true;
     h->have_map = true; h->nb_valid = false; h->grid_checked = false;
     h->tl_host[1] = host_us();

@@ -252,3 +252,33 @@ def test_persistent_and_chunked_solves_agree_bit_for_bit(b2, c1, monkeypatch):
         res = g.scan2MapOptimization(30, record_history=True)
         out.append((res["iters"], res["pose_history"].copy(), g.lastGpuMs()[1]))
     assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
+
+
+def test_pinned_map_is_read_in_place_and_gives_the_same_solve(b2, c1, monkeypatch):
+    """With B2_GRID_ZERO_COPY=1 a pinned, 16-byte-record map is not copied by DMA: the index build reads it over PCIe itself.
+    Same points, same index, same solve as the pageable upload — bit for bit — and a later rebuild reads the device copy, not
+    the host buffer (which is overwritten here before the rebuild)."""
+    import torch
+    from multi_sensor_slam_tookit_b200.registration import ScanToMapOptimizer
+    monkeypatch.setenv("B2_GRID_ZERO_COPY", "1")
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    out = []
+    keep = []
+    for pinned in (False, True):
+        mc, ms = c1["map_corner"], c1["map_surf"]
+        if pinned:
+            tc, ts = pin(mc), pin(ms); keep += [tc, ts]
+            mc, ms = tc.numpy(), ts.numpy()
+        g = ScanToMapOptimizer()
+        g.setInputMap(mc, ms); g.setInputScan(c1["scan_corner"], c1["scan_surf"])
+        g.transformTobeMapped = c1["pose_guess"].copy()
+        res = g.scan2MapOptimization(30, record_history=True)
+        first = (res["iters"], res["pose_history"].copy())
+        if pinned:
+            mc[:] = 0.0; ms[:] = 0.0                     # the host copy is gone; the index is rebuilt from the device copy
+        g.rebuildMapIndex()
+        g.transformTobeMapped = c1["pose_guess"].copy()
+        res2 = g.scan2MapOptimization(30, record_history=True)
+        assert res2["iters"] == first[0] and np.array_equal(res2["pose_history"], first[1])
+        out.append(first)
+    assert out[0][0] == out[1][0] and np.array_equal(out[0][1], out[1][1])
