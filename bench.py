@@ -524,8 +524,8 @@ def run_registration(args, rank, local_rank, world, dist, torch):
             "e2e": {"value": r["e2e_mpts_per_s"], "unit": "Mpts/s", "ms": r["e2e_ms"], "h2d_bytes": int(32 * r["points_in"] + 4 * 8 * 62),
                     "d2h_bytes": int(24 * r["extracted"] + 16 * (r["corner"] + r["surf"]) + 1024),
                     "step": "b2_scan_project + b2_scan_extract_features, PointXYZIRT records in, cloud_info arrays + corner / surf clouds out"},
-            "roofline": {"kernel": "k_scan_* (9 launches)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_launch": r["algorithmic_bytes"],
+            "roofline": {"kernel": "k_scan_* (10 launches)", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": measured_traffic("k_scan_all"), "peak_source": peak_src, "bytes_per_launch": r["algorithmic_bytes"],
                          "note": "52 B per input point + 20 B per extracted point (SURVEY.md 8d) over the device span of both calls; 4.2 MB in, "
                                  "launch-latency bound at this size (one scan)"},
             "cpu_baseline": {"value": cpu["mpts_per_s"], "unit": "Mpts/s", "cores": 1, "kind": "port",
@@ -558,7 +558,7 @@ def run_registration(args, rank, local_rank, world, dist, torch):
                 "e2e": {"value": n_in * reps / wall / 1e6, "unit": "Mpts/s", "ms": 1e3 * wall / reps, "h2d_bytes": int(16 * n_in), "d2h_bytes": int(16 * len(res)),
                         "step": "b2_voxel_filter: pinned host cloud in, downsampled cloud out"},
                 "roofline": {"kernel": "k_vx_* + k_rs_* (bbox, key, radix sort of (voxel, index) pairs, run heads, centroids)", "bound": "hbm", "achieved": ach,
-                             "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src, "bytes_per_launch": abytes,
+                             "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": measured_traffic("k_vx_all") if n_in == 1_000_000 else None, "peak_source": peak_src, "bytes_per_launch": abytes,
                              "note": "16 B read + 16 B x (voxels / points) written per input point (SURVEY.md 8d) over the device span of the whole filter"},
                 "cpu_baseline": {"value": n_in / cpu_s / 1e6, "unit": "Mpts/s", "cores": 1, "kind": "port", "sample": f"one filter of the same cloud in {cpu_s:.2f} s (serial, as pcl::VoxelGrid)"}}
             del vg
@@ -597,7 +597,7 @@ def run_registration(args, rank, local_rank, world, dist, torch):
                     "step": "per pair: upload both clouds, voxel_down_sample, estimate_normals, registration_generalized_icp, result to host"},
             "iterations_total": int(iters), "gpu_launches": int(launches), "max_t_err_m": terr, "max_r_err_rad": rerr,
             "roofline": {"kernel": "k_gicp_linearize", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic("k_gicp_linearize_c4"), "peak_source": peak_src,
                          "note": "144 B per source point per linearisation (SURVEY.md 8d), per GPU; ~50 k-point clouds: launch/latency bound"},
             "cpu_baseline": {"value": ev / tr / 1e6, "unit": "Mpts/s", "cores": host_cores(), "kind": "port",
                              "sample": f"pair (1 -> 0): {it} iterations in {tr:.3f} s (registration only), {tt:.3f} s with downsampling + normals",

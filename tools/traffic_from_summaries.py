@@ -52,6 +52,25 @@ def main():
                                  "capture": f"profiles/{tag}_ncu_gicp.txt (the first six evaluations of the 50 M-point align)"}
     else:
         t["k_gicp_linearize"] = old["k_gicp_linearize"]
+    # multi-kernel paths: DRAM bytes summed over the launches of ONE call (the capture holds one scan / the first filter)
+    sp = os.path.join(P, f"{tag}_ncu_scan.txt")
+    if os.path.exists(sp):
+        sc = launches(sp, r"k_scan_")[:10]
+        t["k_scan_all"] = {"launches": sc, "dram_bytes_per_launch_last": sum(l["dram_bytes"] for l in sc), "us_last": round(sum(l["us"] for l in sc), 2),
+                           "note": "sum over the ten k_scan_* launches of one sweep (project + extract_features)"}
+    vp = os.path.join(P, f"{tag}_ncu_vx.txt")
+    if os.path.exists(vp):
+        vx = launches(vp, r"k_vx_|k_rs_|k_scan_apply|k_scan_tile")
+        # one filter = from a k_vx_bbox_init to the next one
+        starts = [i for i, l in enumerate(vx) if "k_vx_bbox_init" in l["kernel"]]
+        one = vx[starts[0]:starts[1]] if len(starts) > 1 else vx
+        t["k_vx_all"] = {"launches": one, "dram_bytes_per_launch_last": sum(l["dram_bytes"] for l in one), "us_last": round(sum(l["us"] for l in one), 2),
+                         "note": "sum over the launches of one VoxelGrid filter in the capture (1 M points)"}
+    cp = os.path.join(P, f"{tag}_ncu_c4.txt")
+    if os.path.exists(cp):
+        c4 = launches(cp, r"k_gicp_linearize")
+        t["k_gicp_linearize_c4"] = {"launches": c4, "dram_bytes_per_launch_last": c4[-1]["dram_bytes"], "us_last": c4[-1]["us"],
+                                    "note": "one evaluation of a C4 pair (about 53 k source points)"}
     json.dump(t, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     print(json.dumps({k: (v if isinstance(v, str) else {"last": v["dram_bytes_per_launch_last"], "us": v["us_last"]}) for k, v in t.items()}, indent=1))
 
