@@ -17,6 +17,7 @@
 //                                             (voxel, position), one thread per voxel sums in position order
 // Expression types follow SURVEY.md Appendix A; -fmad=false keeps every threshold operand at the reference's rounding.
 #include "b2_common.cuh"
+#include "b2_atan2f.cuh"
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -92,8 +93,8 @@ __global__ void __launch_bounds__(256) k_scan_project(const unsigned char* __res
         bool ok = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && !(range < s.rmin || range > s.rmax) && row >= 0 && row < s.n_scan;
         ok = ok && (row % s.downsample == 0);
         if (ok) {
-            // atan2 on float arguments, then *180 in float, /M_PI in double, narrowed to float (:547)
-            const float at = (float)atan2((double)p.x, (double)p.y);
+            // atan2 on float arguments (glibc's atan2f, restated in b2_atan2f.cuh), then *180 in float, /M_PI in double, narrowed to float (:547)
+            const float at = port_atan2f(p.x, p.y);
             const float horizonAngle = (float)((double)(at * 180) / M_PI);
             int col = (int)(-round(((double)horizonAngle - 90.0) / (double)s.ang_res_x) + (double)(s.H / 2));
             if (col >= s.H) col -= s.H;

@@ -216,3 +216,47 @@ def test_real_fixture_is_the_shipped_data():
         xyz = np.stack([d["x"], d["y"], d["z"]], 1)
         assert xyz.shape == (n, 3) and np.array_equal(xyz, fx[name])
     assert np.array_equal(fx["initial_extrinsic_rpy_deg_xyz"][1], [0, 0, 90, -0.06763169358385032, 0.6257701373941718, -0.35145357319239473])
+
+
+def test_device_atan2f_restatement_equals_the_c_library(tmp_path):
+    """imageProjection.cpp:547 takes atan2 of two floats: glibc's atan2f, which (up to glibc 2.39; ROS Noetic ships 2.31) is within
+    1 ulp but not correctly rounded. The projection kernel uses the restatement in csrc/b2_atan2f.cuh, so that a return on a column
+    edge lands where the reference puts it. Here the same header, compiled by gcc, is compared bit for bit with the C library on
+    random bit patterns, lidar-like coordinates, the special cases, and the (x, y) of the shipped 64-ring sweep."""
+    import platform
+    import subprocess
+    libc, ver = platform.libc_ver()
+    if libc == "glibc" and tuple(int(v) for v in ver.split(".")[:2]) >= (2, 40):
+        pytest.skip("glibc >= 2.40 rounds atan2f correctly: not the reference platform's function any more")
+    d = np.load(os.path.join(ROOT, "tests", "golden", "real_lidar2lidar_0001.npz"))
+    xy = np.ascontiguousarray(d["lidar_1"][:, :2], dtype=np.float32)
+    xy.tofile(tmp_path / "xy.bin")
+    src = tmp_path / "t.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <stdlib.h>
+#include <math.h>
+#include "b2_atan2f.cuh"
+static int same(float a, float b) { return at_bits(a) == at_bits(b) || (a != a && b != b); }
+int main(int argc, char** argv) {
+    unsigned long long bad = 0; unsigned s = 20261018u;
+    for (long i = 0; i < 6000000; i++) {
+        s = s * 1664525u + 1013904223u; unsigned a = s; s = s * 1664525u + 1013904223u; unsigned b = s;
+        float y, x;
+        if (i % 3 == 0) { memcpy(&y, &a, 4); memcpy(&x, &b, 4); }
+        else { y = ((int)(a >> 8) - (1 << 23)) * (200.0f / (1 << 23)); x = ((int)(b >> 8) - (1 << 23)) * (200.0f / (1 << 23)); }
+        bad += !same(atan2f(y, x), port_atan2f(y, x));
+    }
+    const float sp[] = {0.0f, -0.0f, 1.0f, -1.0f, INFINITY, -INFINITY, NAN, 1e-45f, -1e-45f, 3.4e38f, -3.4e38f, 1e-30f, 0.4375f, 0.6875f, 1.1875f, 2.4375f};
+    for (unsigned i = 0; i < sizeof(sp) / 4; i++) for (unsigned j = 0; j < sizeof(sp) / 4; j++) bad += !same(atan2f(sp[i], sp[j]), port_atan2f(sp[i], sp[j]));
+    FILE* f = fopen(argv[1], "rb"); float v[2]; long n = 0;
+    while (fread(v, 4, 2, f) == 2) { bad += !same(atan2f(v[0], v[1]), port_atan2f(v[0], v[1])); n++; }
+    printf("%llu %ld\n", bad, n);
+    return 0;
+}
+""")
+    exe = tmp_path / "t"
+    inc = os.path.join(ROOT, "multi_sensor_slam_tookit_b200", "csrc")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-I", inc, "-x", "c", str(src), "-o", str(exe), "-lm"], check=True)
+    out = subprocess.run([str(exe), str(tmp_path / "xy.bin")], check=True, capture_output=True, text=True).stdout.split()
+    assert int(out[0]) == 0 and int(out[1]) == len(xy)
