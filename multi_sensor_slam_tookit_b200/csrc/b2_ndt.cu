@@ -247,7 +247,10 @@ __global__ void __launch_bounds__(128) k_ndt_voxel_stats(const float* __restrict
 // ---- derivative pass -------------------------------------------------------------------------------------------
 __device__ __forceinline__ double dot3(const double v[3], double x, double y, double z) { return x * v[0] + y * v[1] + z * v[2]; }
 
-__global__ void __launch_bounds__(NDT_THREADS, 2) k_ndt_derivatives(NdtArgs A) {
+#ifndef NDT_MIN_BLOCKS
+#define NDT_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(NDT_THREADS, NDT_MIN_BLOCKS) k_ndt_derivatives(NdtArgs A) {
     __shared__ double s_red[NDT_WARPS][32];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
