@@ -178,6 +178,11 @@ struct GridIndex {
 // VoxelGrid on device buffers: result left in the handle's output buffer (voxel_out_dev) on voxel_stream(h)
 int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride, size_t n, int n_fields, size_t out_stride,
                      size_t out_capacity, uint32_t* m_out, int* refused, int32_t* d_vop);
+// the same in three stages (see b2_voxel.cu): two filters on two handles can be interleaved from one host thread
+int voxel_filter_dev_begin(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride, size_t n, int n_fields, size_t out_stride,
+                           size_t out_capacity, int32_t* d_vop);
+int voxel_filter_dev_middle(b2_voxel_s* h);
+int voxel_filter_dev_end(b2_voxel_s* h, uint32_t* m_out, int* refused);
 const void* voxel_out_dev(b2_voxel_s* h);
 cudaStream_t voxel_stream(b2_voxel_s* h);
 int voxel_filter_host_to_dev(b2_voxel_s* h, const void* in, size_t in_stride, size_t n, uint32_t* m_out);

@@ -14,7 +14,6 @@
 #include "b2_common.cuh"
 #include <vector>
 #include <algorithm>
-#include <thread>
 
 namespace b2 {
 
@@ -228,22 +227,22 @@ int b2_localmap_extract(b2_localmap_t h, const int32_t* key_indices, int n_keys,
     }
     B2_CUDA(cudaStreamSynchronize(s));
     // 3. downSizeFilterCorner / downSizeFilterSurf, device to device (each on its own handle's stream)
-    // The two filters are independent handles with their own streams, but each has two host waits inside (its bounding box, its
-    // voxel count): run one after the other they cost the sum. The corner filter gets a host thread of its own.
+    // The two filters are independent handles with their own streams, and each has two host waits inside (its bounding box, its
+    // voxel count): run one after the other they cost the sum. Their stages are interleaved instead — both boxes queued, then both
+    // pipelines, then both counts — so the waits overlap and the two streams run side by side (round 2 first used a host thread
+    // for the corner filter: creating and joining it cost more than it hid).
     uint32_t mc = 0, ms = 0;
-    int refused = 0, refused_c = 0, st_c = B2_OK;
-    char err_c[256] = "";
-    std::thread corner_job([&] {
-        cudaSetDevice(h->device);
-        st_c = voxel_filter_dev(h->vox_corner, h->cat_corner.as<unsigned char>(), 16, oc, 4, 16, std::max<size_t>(oc, 1), &mc, &refused_c, nullptr);
-        if (st_c == B2_OK && cudaStreamSynchronize(voxel_stream(h->vox_corner)) != cudaSuccess) st_c = B2_ERR_CUDA;
-        if (st_c != B2_OK) snprintf(err_c, sizeof(err_c), "%s", b2_last_error());      // the message is thread-local: carry it over
-    });
-    int st_s = voxel_filter_dev(h->vox_surf, h->cat_surf.as<unsigned char>(), 16, os, 4, 16, std::max<size_t>(os, 1), &ms, &refused, nullptr);
-    if (st_s == B2_OK && cudaStreamSynchronize(voxel_stream(h->vox_surf)) != cudaSuccess) { set_error("b2_localmap_extract: %s", cudaGetErrorString(cudaGetLastError())); st_s = B2_ERR_CUDA; }
-    corner_job.join();
-    if (st_c != B2_OK) { set_error("%s", err_c); return st_c; }
-    if (st_s != B2_OK) return st_s;
+    int refused = 0, refused_c = 0;
+    B2_CHECK(voxel_filter_dev_begin(h->vox_corner, h->cat_corner.as<unsigned char>(), 16, oc, 4, 16, std::max<size_t>(oc, 1), nullptr));
+    B2_CHECK(voxel_filter_dev_begin(h->vox_surf, h->cat_surf.as<unsigned char>(), 16, os, 4, 16, std::max<size_t>(os, 1), nullptr));
+    B2_CHECK(voxel_filter_dev_middle(h->vox_corner));
+    B2_CHECK(voxel_filter_dev_middle(h->vox_surf));
+    B2_CHECK(voxel_filter_dev_end(h->vox_corner, &mc, &refused_c));
+    B2_CHECK(voxel_filter_dev_end(h->vox_surf, &ms, &refused));
+    // (a refused filter — PCL's "leaf size too small" — leaves its copy queued on the filter's stream)
+    if (cudaStreamSynchronize(voxel_stream(h->vox_corner)) != cudaSuccess || cudaStreamSynchronize(voxel_stream(h->vox_surf)) != cudaSuccess) {
+        set_error("b2_localmap_extract: %s", cudaGetErrorString(cudaGetLastError())); return B2_ERR_CUDA;
+    }
     h->n_ds_corner = mc; h->n_ds_surf = ms;
     // 4. "clear map cache if too large" (:936-937)
     if (h->n_cached > 1000) lm_drop_cache(h);

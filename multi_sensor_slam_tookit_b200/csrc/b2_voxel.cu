@@ -161,7 +161,13 @@ __global__ void __launch_bounds__(128) k_vx_centroid(const unsigned char* __rest
 
 using namespace b2;
 
+// a filter in flight between voxel_filter_dev_begin and voxel_filter_dev_end (stage: 1 box queued, 2 count queued, 3 finished)
+struct VoxelJob {
+    const unsigned char* d_in = nullptr; size_t in_stride = 0, n = 0, out_stride = 0, out_capacity = 0; int n_fields = 0; int32_t* d_vop = nullptr;
+    int stage = 0, refused = 0; uint32_t m = 0;
+};
 struct b2_voxel_s {
+    VoxelJob job;
     float leaf[3] = {0.f, 0.f, 0.f};
     unsigned min_pts = 0;
     cudaStream_t stream = nullptr;
@@ -213,13 +219,16 @@ namespace b2 {
 
 // The filter proper, device in -> device out (h->out; *m_out voxels). d_in must stay valid until the stream has drained.
 // refused = 1: PCL's "leaf size is too small" case, the output is a copy of the input. d_vop (optional, device, n ints).
-int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride, size_t n, int n_fields, size_t out_stride,
-                     size_t out_capacity, uint32_t* m_out, int* refused, int32_t* d_vop) {
-    *m_out = 0;
-    if (refused) *refused = 0;
-    if (n == 0) return B2_OK;
+// The filter in three stages, so that a caller with two filters to run (the local map's corner and surf clouds, each on its own
+// handle and stream) can interleave them from one host thread: begin = bounding box queued; middle = wait for the box, PCL's
+// geometry on the host, everything up to the centroids queued; end = wait for the voxel count. voxel_filter_dev is the three in a row.
+int voxel_filter_dev_begin(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride, size_t n, int n_fields, size_t out_stride,
+                           size_t out_capacity, int32_t* d_vop) {
+    VoxelJob& j = h->job;
+    j = VoxelJob{};
+    j.d_in = d_in; j.in_stride = in_stride; j.n = n; j.n_fields = n_fields; j.out_stride = out_stride; j.out_capacity = out_capacity; j.d_vop = d_vop;
+    if (n == 0) { j.stage = 3; return B2_OK; }
     cudaStream_t s = h->stream;
-    const int ioff = (int)B2_INTENSITY_OFFSET(in_stride), ooff = (int)B2_INTENSITY_OFFSET(out_stride);
     B2_CHECK(h->small.reserve(256));
     uint32_t* bb = h->small.as<uint32_t>();
     k_vx_bbox_init<<<1, 32, 0, s>>>(bb); count_launch();
@@ -228,9 +237,21 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
     else { k_vx_bbox<false><<<nbb, 256, 0, s>>>(d_in, in_stride, n, bb); count_launch(); }
     B2_CUDA(cudaGetLastError());
     B2_CHECK(h->pin.reserve(64));
+    B2_CUDA(cudaMemcpyAsync(h->pin.as<uint32_t>(), bb, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    j.stage = 1;
+    return B2_OK;
+}
+
+int voxel_filter_dev_middle(b2_voxel_s* h) {
+    VoxelJob& j = h->job;
+    if (j.stage != 1) return B2_OK;
+    const unsigned char* d_in = j.d_in; const size_t in_stride = j.in_stride, n = j.n, out_stride = j.out_stride, out_capacity = j.out_capacity;
+    const int n_fields = j.n_fields; int32_t* d_vop = j.d_vop;
+    cudaStream_t s = h->stream;
+    const int ioff = (int)B2_INTENSITY_OFFSET(in_stride), ooff = (int)B2_INTENSITY_OFFSET(out_stride);
     uint32_t* hbb = h->pin.as<uint32_t>();
-    B2_CUDA(cudaMemcpyAsync(hbb, bb, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     B2_CUDA(cudaStreamSynchronize(s));
+    j.stage = 3;
     auto unflip = [](uint32_t u) { uint32_t v = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &v, 4); return f; };
     float mn[3], mx[3];
     for (int d = 0; d < 3; d++) { mn[d] = unflip(hbb[d]); mx[d] = unflip(hbb[3 + d]); }
@@ -245,7 +266,7 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
     }
     if (dxyz[0] * dxyz[1] * dxyz[2] > (int64_t)INT32_MAX) {
         // "Leaf size is too small for the input dataset": output = input
-        if (refused) *refused = 1;
+        j.refused = 1;
         if (out_capacity < n) { set_error("b2_voxel_filter: refused (index overflow) and out_capacity < n"); return B2_ERR_CAPACITY; }
         B2_CHECK(h->out.reserve(n * out_stride));
         if (in_stride == out_stride) B2_CUDA(cudaMemcpyAsync(h->out.p, d_in, n * in_stride, cudaMemcpyDeviceToDevice, s));
@@ -255,7 +276,7 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
             if (n_fields == 4) B2_CUDA(cudaMemcpy2DAsync(h->out.as<unsigned char>() + ooff, out_stride, d_in + ioff, in_stride, 4, n, cudaMemcpyDeviceToDevice, s));
         }
         if (d_vop) B2_CUDA(cudaMemsetAsync(d_vop, 0xff, n * sizeof(int32_t), s));
-        *m_out = (uint32_t)n;
+        j.m = (uint32_t)n;
         return B2_OK;
     }
     uint64_t ncells = 1;
@@ -270,7 +291,6 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
     g.invalid_key = (uint32_t)ncells;               // sorts after every real voxel
     int bits = 1;
     while (bits < 32 && ((uint64_t)1 << bits) <= ncells) bits++;
-
 
     const size_t nal = (n + 64) & ~(size_t)63;       // room for n+1 entries
     const size_t scratch_bytes = std::max(sort_tmp_bytes(n), scan_tmp_bytes(n + 1)) + 1024;
@@ -299,10 +319,32 @@ int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride,
     B2_CUDA(cudaGetLastError());
     uint32_t* hm = h->pin.as<uint32_t>() + 8;
     B2_CUDA(cudaMemcpyAsync(hm, keep + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    B2_CUDA(cudaStreamSynchronize(s));
-    if ((size_t)*hm > out_capacity) { set_error("b2_voxel_filter: %u voxels but out_capacity %zu", *hm, out_capacity); return B2_ERR_CAPACITY; }
-    *m_out = *hm;
+    j.stage = 2;
     return B2_OK;
+}
+
+int voxel_filter_dev_end(b2_voxel_s* h, uint32_t* m_out, int* refused) {
+    VoxelJob& j = h->job;
+    *m_out = 0;
+    if (refused) *refused = j.refused;
+    if (j.stage == 2) {
+        B2_CUDA(cudaStreamSynchronize(h->stream));
+        const uint32_t* hm = h->pin.as<uint32_t>() + 8;
+        j.stage = 3;
+        if ((size_t)*hm > j.out_capacity) { set_error("b2_voxel_filter: %u voxels but out_capacity %zu", *hm, j.out_capacity); return B2_ERR_CAPACITY; }
+        j.m = *hm;
+    }
+    *m_out = j.m;
+    return B2_OK;
+}
+
+int voxel_filter_dev(b2_voxel_s* h, const unsigned char* d_in, size_t in_stride, size_t n, int n_fields, size_t out_stride,
+                     size_t out_capacity, uint32_t* m_out, int* refused, int32_t* d_vop) {
+    *m_out = 0;
+    if (refused) *refused = 0;
+    B2_CHECK(voxel_filter_dev_begin(h, d_in, in_stride, n, n_fields, out_stride, out_capacity, d_vop));
+    B2_CHECK(voxel_filter_dev_middle(h));
+    return voxel_filter_dev_end(h, m_out, refused);
 }
 
 const void* voxel_out_dev(b2_voxel_s* h) { return h->out.p; }
