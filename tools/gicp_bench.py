@@ -166,6 +166,9 @@ def cpu_c4_pair(threads, s=1, t=0, n_cols=1024):
 
 
 # ------------------------------------------------------------------------------------------------ C5
+_KEEP = []
+
+
 def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, device="cuda"):
     from multi_sensor_slam_tookit_b200 import gicp
     t0 = time.perf_counter()
@@ -179,7 +182,7 @@ def run_c5(n_points, rank=0, world=1, comm=None, iterations=10, repeats=2, devic
         if not os.environ.get("B2_GICP_NO_FUSED_EXCHANGE"):
             # likewise the first mapping of a peer GPU's memory in this process (cudaIpcOpenMemHandle enables peer access: ~13 ms per peer)
             wg = gicp.GeneralizedICP(1.0, 0.005); wg.setShard(comm); wg.setupExchange()
-            del wg
+            _KEEP.append(wg)      # kept for the life of the process: its peers have the area mapped, it is not freed under them
     t0 = t_e2e = time.perf_counter()
     if comm is not None:
         # sharded set-up: 1/world of each cloud over this rank's PCIe link + all-gather, 1/world of the 30-NN normals + all-gather,
